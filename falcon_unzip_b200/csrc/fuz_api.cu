@@ -1,0 +1,141 @@
+// Fused batch entry (device pointers) and the host-buffer entry that the reference-facing
+// Python layer calls (H2D, the four stages, D2H of the filled row prefixes).
+#include <string.h>
+
+#include "fuz_internal.cuh"
+
+int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
+int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out);
+int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out);
+int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out);
+
+extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
+    if (!ctx || !in || !out) return FUZ_E_ARG;
+    int rc = fuz_het_call_impl(ctx, in, out);
+    if (rc) return rc;
+    if ((rc = fuz_association_impl(ctx, in->n_ctg, out))) return rc;
+    if ((rc = fuz_blocks_impl(ctx, in->n_ctg, out))) return rc;
+    return fuz_reads_impl(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out);
+}
+
+static int ensure_stage(fuz_ctx *ctx, size_t dev_bytes, size_t pin_bytes) {
+    if (dev_bytes > ctx->stage_dev_cap) {
+        FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage_dev) FUZ_CUDA(ctx, cudaFree(ctx->stage_dev));
+        ctx->stage_dev = nullptr; ctx->stage_dev_cap = 0;
+        size_t want = dev_bytes + (dev_bytes >> 3) + (1 << 20);
+        cudaError_t e = cudaMalloc(&ctx->stage_dev, want);
+        if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "device staging of %zu bytes: %s", want, cudaGetErrorString(e));
+        ctx->stage_dev_cap = want;
+    }
+    if (pin_bytes > ctx->stage_pin_cap) {
+        FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage_pin) FUZ_CUDA(ctx, cudaFreeHost(ctx->stage_pin));
+        ctx->stage_pin = nullptr; ctx->stage_pin_cap = 0;
+        size_t want = pin_bytes + 4096;
+        cudaError_t e = cudaMallocHost(&ctx->stage_pin, want);
+        if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "pinned staging of %zu bytes: %s", want, cudaGetErrorString(e));
+        ctx->stage_pin_cap = want;
+    }
+    return FUZ_OK;
+}
+
+extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_outputs *out, fuz_status *h_status,
+                                    int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!ctx || !in || !out || !h_status) return FUZ_E_ARG;
+    if (in->n_ctg < 1 || in->n_rec < 0) return fuz_fail(ctx, FUZ_E_ARG, "fuz_phase_batch_host: empty batch");
+    const int n_ctg = in->n_ctg, n_rec = in->n_rec;
+    cudaStream_t st = ctx->stream;
+    // tile-aligned global offsets (host, tiny)
+    int64_t total_nq = 0;
+    FuzLayout P;   // pinned
+    size_t p_goff = P.add(8 * (size_t)(n_ctg + 1));
+    FuzLayout D;   // device
+    size_t d_rec = D.add((size_t)in->rec_bytes + 16), d_off = D.add(8 * (size_t)(n_rec + 1)), d_qid = D.add(4 * (size_t)(n_rec + 1));
+    size_t d_cro = D.add(4 * (size_t)(n_ctg + 1)), d_clen = D.add(4 * (size_t)n_ctg), d_goff = D.add(8 * (size_t)(n_ctg + 1));
+    size_t d_cnq = D.add(4 * (size_t)n_ctg);
+    const int64_t cs = out->cap_sites, cv = out->cap_vmap, ca = out->cap_atable, cr = out->cap_reads;
+    size_t o_sctg = D.add(4 * (size_t)cs), o_spos = D.add(4 * (size_t)cs), o_scnt = D.add(16 * (size_t)cs);
+    size_t o_sal = D.add(2 * (size_t)cs), o_stop = D.add(2 * (size_t)cs);
+    size_t o_vs = D.add(4 * (size_t)cv), o_vq = D.add(4 * (size_t)cv), o_vb = D.add((size_t)cv);
+    size_t o_a1 = D.add(4 * (size_t)ca), o_a2 = D.add(4 * (size_t)ca), o_act = D.add(16 * (size_t)ca);
+    size_t o_pst = D.add((size_t)cs), o_ple = D.add(4 * (size_t)cs), o_pre = D.add(4 * (size_t)cs);
+    size_t o_pls = D.add(4 * (size_t)cs), o_prs = D.add(4 * (size_t)cs), o_pb = D.add(4 * (size_t)cs);
+    size_t o_rc = D.add(4 * (size_t)cr), o_rq = D.add(4 * (size_t)cr), o_rb = D.add(4 * (size_t)cr);
+    size_t o_rp = D.add(4 * (size_t)cr), o_r0 = D.add(4 * (size_t)cr), o_r1 = D.add(4 * (size_t)cr);
+    int rc = ensure_stage(ctx, D.off, P.off);
+    if (rc) return rc;
+    int64_t *goff = reinterpret_cast<int64_t *>(ctx->stage_pin + p_goff);
+    goff[0] = 0;
+    for (int c = 0; c < n_ctg; c++) {
+        if (in->h_ctg_len[c] < 0) return fuz_fail(ctx, FUZ_E_ARG, "negative contig length");
+        int64_t padded = ((int64_t)in->h_ctg_len[c] + FUZ_TILE - 1) / FUZ_TILE * FUZ_TILE;
+        if (padded == 0) padded = FUZ_TILE;
+        goff[c + 1] = goff[c] + padded;
+        total_nq += in->h_ctg_nq[c];
+    }
+    uint8_t *dv = ctx->stage_dev;
+    int64_t up = 0;
+    auto h2d = [&](size_t off, const void *src, size_t bytes) -> cudaError_t {
+        up += (int64_t)bytes;
+        return bytes ? cudaMemcpyAsync(dv + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    };
+    FUZ_CUDA(ctx, h2d(d_rec, in->h_rec_buf, (size_t)in->rec_bytes));
+    FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 16, st));
+    FUZ_CUDA(ctx, h2d(d_off, in->h_rec_off, 8 * (size_t)(n_rec + 1)));
+    FUZ_CUDA(ctx, h2d(d_qid, in->h_rec_qid, 4 * (size_t)n_rec));
+    FUZ_CUDA(ctx, h2d(d_cro, in->h_ctg_rec_off, 4 * (size_t)(n_ctg + 1)));
+    FUZ_CUDA(ctx, h2d(d_clen, in->h_ctg_len, 4 * (size_t)n_ctg));
+    FUZ_CUDA(ctx, h2d(d_goff, goff, 8 * (size_t)(n_ctg + 1)));
+    FUZ_CUDA(ctx, h2d(d_cnq, in->h_ctg_nq, 4 * (size_t)n_ctg));
+    fuz_batch b;
+    memset(&b, 0, sizeof(b));
+    b.n_ctg = n_ctg; b.n_rec = n_rec; b.rec_bytes = in->rec_bytes;
+    b.d_rec_buf = dv + d_rec; b.d_rec_off = reinterpret_cast<int64_t *>(dv + d_off);
+    b.d_rec_qid = reinterpret_cast<int32_t *>(dv + d_qid); b.d_ctg_rec_off = reinterpret_cast<int32_t *>(dv + d_cro);
+    b.d_ctg_len = reinterpret_cast<int32_t *>(dv + d_clen); b.d_ctg_goff = reinterpret_cast<int64_t *>(dv + d_goff);
+    b.d_ctg_nq = reinterpret_cast<int32_t *>(dv + d_cnq);
+    b.total_glen = goff[n_ctg]; b.total_nq = total_nq;
+    fuz_outputs o;
+    memset(&o, 0, sizeof(o));
+    o.cap_sites = cs; o.cap_vmap = cv; o.cap_atable = ca; o.cap_reads = cr;
+#define DP(T, off) reinterpret_cast<T *>(dv + (off))
+    o.d_site_ctg = DP(int32_t, o_sctg); o.d_site_pos = DP(int32_t, o_spos); o.d_site_cnt = DP(int32_t, o_scnt);
+    o.d_site_al = DP(uint8_t, o_sal); o.d_site_top = DP(uint8_t, o_stop);
+    o.d_vm_site = DP(int32_t, o_vs); o.d_vm_qid = DP(int32_t, o_vq); o.d_vm_base = DP(uint8_t, o_vb);
+    o.d_at_s1 = DP(int32_t, o_a1); o.d_at_s2 = DP(int32_t, o_a2); o.d_at_ct = DP(int32_t, o_act);
+    o.d_ph_state = DP(uint8_t, o_pst); o.d_ph_lext = DP(int32_t, o_ple); o.d_ph_rext = DP(int32_t, o_pre);
+    o.d_ph_lscore = DP(int32_t, o_pls); o.d_ph_rscore = DP(int32_t, o_prs); o.d_ph_block = DP(int32_t, o_pb);
+    o.d_pr_ctg = DP(int32_t, o_rc); o.d_pr_qid = DP(int32_t, o_rq); o.d_pr_block = DP(int32_t, o_rb);
+    o.d_pr_phase = DP(int32_t, o_rp); o.d_pr_n0 = DP(int32_t, o_r0); o.d_pr_n1 = DP(int32_t, o_r1);
+#undef DP
+    o.d_counts = nullptr;
+    if ((rc = fuz_phase_batch(ctx, &b, &o))) return rc;
+    rc = fuz_get_status(ctx, h_status);          // synchronises; row counts now known
+    if (h2d_bytes) *h2d_bytes = up;
+    if (d2h_bytes) *d2h_bytes = (int64_t)sizeof(fuz_status);
+    if (rc) return rc;
+    int64_t down = (int64_t)sizeof(fuz_status);
+    auto d2h = [&](void *dst, size_t off, size_t bytes) -> cudaError_t {
+        down += (int64_t)bytes;
+        return (bytes && dst) ? cudaMemcpyAsync(dst, dv + off, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    const size_t ns = (size_t)h_status->n_sites, nv = (size_t)h_status->n_vmap, na = (size_t)h_status->n_atable,
+                 nr = (size_t)h_status->n_reads;
+    FUZ_CUDA(ctx, d2h(out->site_ctg, o_sctg, 4 * ns)); FUZ_CUDA(ctx, d2h(out->site_pos, o_spos, 4 * ns));
+    FUZ_CUDA(ctx, d2h(out->site_cnt, o_scnt, 16 * ns)); FUZ_CUDA(ctx, d2h(out->site_al, o_sal, 2 * ns));
+    FUZ_CUDA(ctx, d2h(out->site_top, o_stop, 2 * ns));
+    FUZ_CUDA(ctx, d2h(out->vm_site, o_vs, 4 * nv)); FUZ_CUDA(ctx, d2h(out->vm_qid, o_vq, 4 * nv));
+    FUZ_CUDA(ctx, d2h(out->vm_base, o_vb, nv));
+    FUZ_CUDA(ctx, d2h(out->at_s1, o_a1, 4 * na)); FUZ_CUDA(ctx, d2h(out->at_s2, o_a2, 4 * na));
+    FUZ_CUDA(ctx, d2h(out->at_ct, o_act, 16 * na));
+    FUZ_CUDA(ctx, d2h(out->ph_state, o_pst, ns)); FUZ_CUDA(ctx, d2h(out->ph_lext, o_ple, 4 * ns));
+    FUZ_CUDA(ctx, d2h(out->ph_rext, o_pre, 4 * ns)); FUZ_CUDA(ctx, d2h(out->ph_lscore, o_pls, 4 * ns));
+    FUZ_CUDA(ctx, d2h(out->ph_rscore, o_prs, 4 * ns)); FUZ_CUDA(ctx, d2h(out->ph_block, o_pb, 4 * ns));
+    FUZ_CUDA(ctx, d2h(out->pr_ctg, o_rc, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_qid, o_rq, 4 * nr));
+    FUZ_CUDA(ctx, d2h(out->pr_block, o_rb, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_phase, o_rp, 4 * nr));
+    FUZ_CUDA(ctx, d2h(out->pr_n0, o_r0, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_n1, o_r1, 4 * nr));
+    FUZ_CUDA(ctx, cudaStreamSynchronize(st));
+    if (d2h_bytes) *d2h_bytes = down;
+    return FUZ_OK;
+}

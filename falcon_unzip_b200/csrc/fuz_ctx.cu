@@ -1,0 +1,212 @@
+// Context, scratch arena, status block, scan primitive.
+#include <string.h>
+
+#include "fuz_internal.cuh"
+
+static std::string g_create_err;
+
+int fuz_fail(fuz_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+extern "C" int fuz_version(void) { return FUZ_VERSION; }
+extern "C" int fuz_tile_size(void) { return FUZ_TILE; }
+
+extern "C" const char *fuz_last_error(fuz_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int fuz_ctx_create(int device, fuz_ctx **out) {
+    if (!out) return fuz_fail(nullptr, FUZ_E_ARG, "fuz_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fuz_fail(nullptr, FUZ_E_CUDA, "no CUDA device available (%s); libfuz has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fuz_fail(nullptr, FUZ_E_ARG, "device %d out of range [0,%d)", device, n);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return fuz_fail(nullptr, FUZ_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fuz_fail(nullptr, FUZ_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fuz_fail(nullptr, FUZ_E_CUDA, "device %d is sm_%d%d; libfuz is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+    fuz_ctx *ctx = new fuz_ctx();
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fuz_fail(nullptr, FUZ_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+    if ((e = cudaMalloc(&ctx->d_status, sizeof(fuz_status))) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_status, sizeof(fuz_status))) != cudaSuccess) {
+        fuz_ctx_destroy(ctx);
+        return fuz_fail(nullptr, FUZ_E_CUDA, "status allocation: %s", cudaGetErrorString(e));
+    }
+    cudaMemset(ctx->d_status, 0, sizeof(fuz_status));
+    *out = ctx;
+    return FUZ_OK;
+}
+
+extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
+    if (!ctx) return FUZ_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->timing_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+    if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FUZ_OK;
+}
+
+extern "C" int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return FUZ_E_ARG;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return FUZ_OK;
+}
+
+extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return FUZ_E_ARG;
+    if (!strcmp(key, "pileup_impl")) {
+        if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "pileup_impl must be 0 or 1");
+        ctx->pileup_impl = (int)value;
+    } else if (!strcmp(key, "max_pairs_per_site")) {
+        if (value < 1) return fuz_fail(ctx, FUZ_E_ARG, "max_pairs_per_site must be >= 1");
+        ctx->max_pairs_per_site = value;
+    } else {
+        return fuz_fail(ctx, FUZ_E_ARG, "unknown option '%s'", key);
+    }
+    return FUZ_OK;
+}
+
+extern "C" int fuz_sync(fuz_ctx *ctx) {
+    if (!ctx) return FUZ_E_ARG;
+    FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FUZ_OK;
+}
+
+extern "C" int fuz_get_status(fuz_ctx *ctx, fuz_status *h_status) {
+    if (!ctx || !h_status) return FUZ_E_ARG;
+    FUZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(fuz_status), cudaMemcpyDeviceToHost, ctx->stream));
+    FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_status = *ctx->h_status;
+    if (h_status->error != FUZ_OK) {
+        static const char *names[] = {"ok", "cuda", "arg", "capacity", "bad record", "unsorted records",
+                                      "pileup depth > 65535", "internal inconsistency", "format"};
+        int e = h_status->error;
+        return fuz_fail(ctx, e, "device reported error %d (%s) at index %d", e,
+                        (e >= 0 && e <= 8) ? names[e] : "?", h_status->error_index);
+    }
+    return FUZ_OK;
+}
+
+extern "C" int64_t fuz_launch_count(fuz_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int fuz_kernel_timing(fuz_ctx *ctx, int enable) {
+    if (!ctx) return FUZ_E_ARG;
+    ctx->timing = enable != 0;
+    ctx->timing_used = 0;
+    return FUZ_OK;
+}
+
+extern "C" int fuz_get_kernel_timing(fuz_ctx *ctx, double *h_ms_total, int64_t *h_launches) {
+    if (!ctx || !h_ms_total || !h_launches) return FUZ_E_ARG;
+    FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    for (size_t i = 0; i < ctx->timing_used; i++) {
+        float ms = 0;
+        FUZ_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->timing_events[i].first, ctx->timing_events[i].second));
+        total += ms;
+    }
+    *h_ms_total = total;
+    *h_launches = (int64_t)ctx->timing_used;
+    return FUZ_OK;
+}
+
+int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
+    if (l.off <= ctx->arena_cap) return FUZ_OK;
+    FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->arena) FUZ_CUDA(ctx, cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_cap = 0;
+    size_t want = l.off + (l.off >> 2) + (1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->arena, want);
+    if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(e));
+    ctx->arena_cap = want;
+    return FUZ_OK;
+}
+
+// ------------------------------------------------------------------ single-CTA scan
+// One CTA of 1024 threads walks the array in chunks of 4096 carrying the running total.
+// The arrays scanned on this path (records, tiles, sites, q_ids) are at most a few
+// million entries; the scan is never the dominant kernel.
+__global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                   int64_t n_cap, const int64_t *__restrict__ d_n,
+                                                   int64_t *__restrict__ d_total64) {
+    __shared__ int warp_tot[32];
+    __shared__ long long carry_s;
+    int64_t n = d_n ? *d_n : n_cap;
+    if (n > n_cap) n = n_cap;
+    if (n < 0) n = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 4096) {
+        int v[4];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int64_t i = base + (int64_t)tid * 4 + k;
+            v[k] = i < n ? in[i] : 0;
+            s += v[k];
+        }
+        int incl = fuz_warp_incl_scan(s, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane];
+            int ti = fuz_warp_incl_scan(t, lane);
+            warp_tot[lane] = ti - t;  // exclusive offset of each warp
+        }
+        __syncthreads();
+        long long carry = carry_s;
+        long long excl = carry + warp_tot[warp] + (incl - s);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int64_t i = base + (int64_t)tid * 4 + k;
+            if (i < n) out[i] = (int32_t)excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl;  // excl now = carry + chunk total
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out[n] = (int32_t)carry_s;
+        if (d_total64) *d_total64 = carry_s;
+    }
+}
+
+int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n,
+                 int64_t *d_total64) {
+    k_scan_i32<<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n_cap, d_n, d_total64);
+    FUZ_LAUNCH_CHECK(ctx, "k_scan_i32");
+    return FUZ_OK;
+}

@@ -1,0 +1,720 @@
+// Stage 1 of the phasing path: record scan + filter, pileup, het call, variant_map rows.
+// Reproduces reference falcon_unzip/phasing.py:14-134 (make_het_call) for a batch of
+// contigs; see DESIGN.md for the data layout and the equivalence argument
+// (streaming flush == full pileup evaluated for pos < POS_last).
+#include "fuz_internal.cuh"
+
+namespace {
+
+// scratch of the het-call stage (device pointers into the context arena)
+struct HetScratch {
+    int32_t *r_gstart, *r_gend, *r_seg_off, *r_nseg, *r_segcnt;
+    int64_t *r_seq;
+    uint8_t *r_flags;
+    int32_t *seg_rs, *seg_len, *seg_qs;
+    int32_t *ctg_last_rec, *ctg_maxspan, *ctg_poslast_g;
+    int32_t *tile_ctg, *tile_rlo, *tile_rhi, *tile_site_base, *tile_site_cnt, *tile_site_off;
+    int32_t *us_gpos;
+    uint32_t *us_cnt;
+    int32_t *s_gpos, *site_rows, *site_row_off;
+    uint32_t *counts;
+    int64_t seg_cap;
+    int32_t n_tiles;
+};
+
+__device__ __forceinline__ bool op_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+
+// ---------------------------------------------------------------- init
+__global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_maxspan, int n_ctg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        st->error = 0; st->error_index = 0;
+        st->n_sites = st->n_vmap = st->n_atable = st->n_reads = 0;
+        st->need_sites = st->need_vmap = st->need_atable = st->need_reads = st->need_pairs = 0;
+        st->n_accepted = 0; st->aligned_bases = 0; st->n_segments = 0;
+    }
+    for (; i < n_ctg; i += gridDim.x * blockDim.x) { ctg_last_rec[i] = -1; ctg_maxspan[i] = 0; }
+}
+
+// upper bound of the number of match segments of each record: ceil(n_cigar / 2)
+__global__ void k_rec_segbound(const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off,
+                               int n_rec, int32_t *__restrict__ segcnt) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        uint32_t w = fuz_ld_u32_un(rec_buf + rec_off[r] + 16);   // n_cigar_op:u16, flag:u16
+        segcnt[r] = (int)((w & 0xFFFFu) + 1) >> 1;
+    }
+}
+
+// ---------------------------------------------------------------- record scan
+// One warp per record.  Pass 1: totals for the filter (phasing.py:63-75).  Pass 2 (accepted
+// records): ref/query prefix of every CIGAR op and the match segments = maximal runs of
+// M/=/X ops not interrupted by S/I/D (N/H/P advance nothing, phasing.py:77-96 quirk).
+__global__ void __launch_bounds__(256) k_scan_records(
+    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
+    const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg,
+    HetScratch S, fuz_status *st) {
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    long long acc_aligned = 0, acc_accepted = 0, acc_segs = 0;
+    for (int r = warp_g; r < n_rec; r += n_warps) {
+        const uint8_t *rec = rec_buf + rec_off[r];
+        // contig of the record = position of r in ctg_rec_off (records grouped by contig)
+        int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
+        const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
+        const uint32_t w12 = fuz_ld_u32_un(rec + 12);     // l_read_name, mapq, bin
+        const uint32_t w16 = fuz_ld_u32_un(rec + 16);     // n_cigar_op, flag
+        const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
+        const int l_name = w12 & 0xFF;
+        const int n_cig = w16 & 0xFFFF;
+        const uint8_t *cig = rec + 36 + l_name;
+        const int64_t seq_off = rec_off[r] + 36 + l_name + 4 * (int64_t)n_cig;
+        const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
+        bool bad = false;
+        if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 ||
+            rec_off[r + 1] - rec_off[r] != (int64_t)block_size + 4 ||
+            36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4)
+            bad = true;
+        if (lane == 0) { S.r_flags[r] = 0; S.r_nseg[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_seq[r] = seq_off; }
+        if (bad) {
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+            continue;
+        }
+        const int64_t goff = ctg_goff[c];
+        const int64_t gstart64 = goff + pos;
+        // coordinate order inside the contig
+        if (lane == 0 && r > ctg_rec_off[c]) {
+            int32_t prev_pos = (int32_t)fuz_ld_u32_un(rec_buf + rec_off[r - 1] + 8);
+            if (prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
+        }
+        // ---- pass 1: total / soft-clip lengths (phasing.py:63-70)
+        long long total = 0, skip = 0, aligned = 0;
+        bool badop = false;
+        for (int k = lane; k < n_cig; k += 32) {
+            uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
+            uint32_t len = cw >> 4, op = cw & 15;
+            if (op > 8) badop = true;
+            total += len;
+            if (op == 4) skip += len;
+            if (op_is_match(op)) aligned += len;
+        }
+        total = fuz_warp_sum64(total);
+        skip = fuz_warp_sum64(skip);
+        aligned = fuz_warp_sum64(aligned);
+        badop = __any_sync(0xffffffffu, badop);
+        if (badop || total == 0) {           // unknown op / ZeroDivisionError at phasing.py:72
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+            continue;
+        }
+        // phasing.py:72-75 in IEEE double, same operation order as the reference
+        bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
+        int32_t gstart = (int32_t)gstart64;
+        if (!accept) {
+            if (lane == 0) {
+                S.r_gstart[r] = gstart; S.r_gend[r] = gstart; S.r_flags[r] = 0; S.r_nseg[r] = 0;
+                S.r_seq[r] = seq_off;
+            }
+            continue;
+        }
+        // ---- pass 2: prefix positions + match segments
+        const int seg_base = S.r_seg_off[r];
+        int carry_rp = gstart, carry_qp = 0;
+        bool open = false;
+        int open_rs = 0, open_qs = 0, nseg = 0;
+        bool overrun = false;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int k0 = 0; k0 < n_cig; k0 += 32) {
+            int k = k0 + lane;
+            bool valid = k < n_cig;
+            uint32_t cw = valid ? fuz_ld_u32_un(cig + 4 * k) : 0u;
+            int len = (int)(cw >> 4);
+            uint32_t op = cw & 15;
+            bool is_m = valid && op_is_match(op) && len > 0;
+            bool brk = valid && (op == 1 || op == 2 || op == 4);          // I D S
+            int radv = (valid && (op_is_match(op) || op == 2)) ? len : 0;  // M = X D
+            int qadv = (valid && (op_is_match(op) || op == 1 || op == 4)) ? len : 0;  // M = X I S
+            int rinc = fuz_warp_incl_scan(radv, lane);
+            int qinc = fuz_warp_incl_scan(qadv, lane);
+            int rp0 = carry_rp + rinc - radv;
+            int qp0 = carry_qp + qinc - qadv;
+            if (is_m && (long long)qp0 + len > (long long)l_seq) overrun = true;  // IndexError :84
+            uint32_t mmask = __ballot_sync(0xffffffffu, is_m);
+            uint32_t bmask = __ballot_sync(0xffffffffu, brk);
+            int last_m = (mmask & lt) ? 31 - __clz(mmask & lt) : -1;
+            int last_b = (bmask & lt) ? 31 - __clz(bmask & lt) : -1;
+            bool open_before = last_m > last_b ? true : (last_b > last_m ? false : open);
+            bool starts = is_m && !open_before;
+            bool ends_here = brk && open_before;
+            uint32_t smask = __ballot_sync(0xffffffffu, starts);
+            uint32_t emask = __ballot_sync(0xffffffffu, ends_here);
+            uint32_t sm = smask & lt;
+            int src = sm ? 31 - __clz(sm) : 0;
+            int rs_s = __shfl_sync(0xffffffffu, rp0, src);
+            int qs_s = __shfl_sync(0xffffffffu, qp0, src);
+            if (ends_here) {
+                int rs = sm ? rs_s : open_rs, qs = sm ? qs_s : open_qs;
+                int idx = seg_base + nseg + __popc(emask & lt);
+                S.seg_rs[idx] = rs; S.seg_len[idx] = rp0 - rs; S.seg_qs[idx] = qs;
+            }
+            nseg += __popc(emask);
+            int last_m_all = mmask ? 31 - __clz(mmask) : -1;
+            int last_b_all = bmask ? 31 - __clz(bmask) : -1;
+            // the group open at the end of the chunk starts at the first start after the last break
+            uint32_t sm2 = last_b_all >= 0 ? (last_b_all == 31 ? 0u : (smask & ~((2u << last_b_all) - 1u))) : smask;
+            int src2 = sm2 ? __ffs(sm2) - 1 : 0;
+            int rs2 = __shfl_sync(0xffffffffu, rp0, src2);
+            int qs2 = __shfl_sync(0xffffffffu, qp0, src2);
+            if (last_m_all > last_b_all) {
+                if (sm2) { open_rs = rs2; open_qs = qs2; }
+                open = true;
+            } else if (last_b_all > last_m_all) {
+                open = false;
+            }
+            carry_rp += __shfl_sync(0xffffffffu, rinc, 31);
+            carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
+        }
+        if (open) {
+            if (lane == 0) {
+                int idx = seg_base + nseg;
+                S.seg_rs[idx] = open_rs; S.seg_len[idx] = carry_rp - open_rs; S.seg_qs[idx] = open_qs;
+            }
+            nseg++;
+        }
+        overrun = __any_sync(0xffffffffu, overrun);
+        if (overrun) {
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+            continue;
+        }
+        if (lane == 0) {
+            S.r_gstart[r] = gstart; S.r_gend[r] = carry_rp; S.r_flags[r] = 1; S.r_nseg[r] = nseg;
+            S.r_seq[r] = seq_off;
+            atomicMax(&S.ctg_last_rec[c], r);
+            atomicMax(&S.ctg_maxspan[c], carry_rp - gstart);
+            acc_aligned += aligned; acc_accepted += 1; acc_segs += nseg;
+        }
+    }
+    if (lane == 0 && acc_accepted) {
+        atomicAdd((unsigned long long *)&st->aligned_bases, (unsigned long long)acc_aligned);
+        atomicAdd((unsigned long long *)&st->n_accepted, (unsigned long long)acc_accepted);
+        atomicAdd((unsigned long long *)&st->n_segments, (unsigned long long)acc_segs);
+    }
+}
+
+// POS_last of each contig in global coordinates: start of the last accepted record in
+// file order; positions >= POS_last are never evaluated (no final flush, phasing.py:98-129).
+__global__ void k_ctg_finish(int n_ctg, const int64_t *__restrict__ ctg_goff, HetScratch S) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_ctg; c += gridDim.x * blockDim.x) {
+        int lr = S.ctg_last_rec[c];
+        S.ctg_poslast_g[c] = lr >= 0 ? S.r_gstart[lr] : (int32_t)ctg_goff[c];
+    }
+}
+
+// candidate record range of every pileup tile
+__global__ void k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict__ ctg_goff,
+                              const int32_t *__restrict__ ctg_rec_off, HetScratch S) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        int64_t t0 = (int64_t)t * FUZ_TILE;
+        int lo = 0, hi = n_ctg + 1;                      // last c with ctg_goff[c] <= t0
+        while (lo < hi) { int m = (lo + hi) >> 1; if (ctg_goff[m] <= t0) lo = m + 1; else hi = m; }
+        int c = lo - 1;
+        if (c >= n_ctg) c = n_ctg - 1;
+        int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
+        int t1 = (int)(t0 + FUZ_TILE);
+        int span = S.ctg_maxspan[c];
+        S.tile_ctg[t] = c;
+        S.tile_rlo[t] = fuz_lower_bound(S.r_gstart, r0, r1, (int)t0 - span + 1);
+        S.tile_rhi[t] = fuz_lower_bound(S.r_gstart, r0, r1, t1);
+    }
+}
+
+// ---------------------------------------------------------------- het test + site emission
+// key = count*4 + base index: descending key order == the reference's sort()+reverse() on
+// (count, base) tuples (phasing.py:116-117; T > G > C > A on ties).
+__device__ __forceinline__ bool het_test(uint32_t cA, uint32_t cC, uint32_t cG, uint32_t cT) {
+    uint32_t total = cA + cC + cG + cT;
+    if (total < 10) return false;                                    // phasing.py:112
+    uint32_t k[4] = {cA << 2, (cC << 2) | 1, (cG << 2) | 2, (cT << 2) | 3};
+    uint32_t m0 = max(max(k[0], k[1]), max(k[2], k[3]));
+    uint32_t m1 = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (k[b] != m0) m1 = max(m1, k[b]);
+    uint32_t c0 = m0 >> 2, c1 = m1 >> 2;
+    // c0/total < 0.75 and c1/total > 0.25 (phasing.py:118-120), exact in integers (B.2)
+    return 4 * c0 < 3 * total && 4 * c1 > total;
+}
+
+// Ordered compaction of the het positions of one tile: every thread owns 8 consecutive
+// positions with counts cnt[i][0..3]; sites of a tile land contiguously (in position
+// order) at an atomically claimed base; tiles are put in order afterwards.
+__device__ __forceinline__ void emit_tile_sites(const uint32_t (&cnt)[8][4], int tile, int t0, int pos_limit,
+                                                HetScratch &S, int64_t cap_sites, fuz_status *st,
+                                                int *s_warp_tot, int *s_base) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t hetmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int p = t0 + tid * 8 + i;
+        if (p < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
+    }
+    int nh = __popc(hetmask);
+    int incl = fuz_warp_incl_scan(nh, lane);
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < FUZ_NW ? s_warp_tot[lane] : 0;
+        int ti = fuz_warp_incl_scan(t, lane);
+        if (lane < FUZ_NW) s_warp_tot[lane] = ti - t;
+        if (lane == FUZ_NW - 1) {
+            int total = ti;
+            int base = 0;
+            if (total > 0) base = (int)atomicAdd((unsigned long long *)&st->need_sites, (unsigned long long)total);
+            S.tile_site_base[tile] = base;
+            S.tile_site_cnt[tile] = total;
+            *s_base = base;
+        }
+    }
+    __syncthreads();
+    if (nh) {
+        int64_t o = (int64_t)*s_base + s_warp_tot[warp] + (incl - nh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (hetmask & (1u << i)) {
+                if (o < cap_sites) {
+                    S.us_gpos[o] = t0 + tid * 8 + i;
+                    reinterpret_cast<uint4 *>(S.us_cnt)[o] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+                }
+                o++;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tiled pileup (default)
+// 8 nibbles (query bases qn0..qn0+7, BAM 4-bit codes) -> one word, base i at bits 4i.
+__device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {
+    const uint8_t *addr = seq + (q0 >> 1);
+    uintptr_t a = reinterpret_cast<uintptr_t>(addr);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    uint32_t lo = __funnelshift_r(w0, w1, sh);          // bytes 0..3
+    uint32_t b4 = (w1 >> sh) & 0xFFu;                   // byte 4
+    // BAM stores the first base of a byte in the high nibble: swap nibbles inside bytes
+    uint32_t s_lo = ((lo & 0x0F0F0F0Fu) << 4) | ((lo >> 4) & 0x0F0F0F0Fu);
+    uint32_t s_b4 = ((b4 & 0x0Fu) << 4) | (b4 >> 4);
+    return __funnelshift_r(s_lo, s_b4, (uint32_t)(q0 & 1) * 4);
+}
+
+// nibble mask covering nibble indices [lo, hi), 0 <= lo < hi <= 8
+__device__ __forceinline__ uint32_t nibble_mask(int lo, int hi) {
+    uint32_t m = hi >= 8 ? 0xFFFFFFFFu : ((1u << (4 * hi)) - 1u);
+    return m & ~((1u << (4 * lo)) - 1u);
+}
+
+// One warp writes the part of record `rec` that falls into tile [t0, t0 + FUZ_TILE) into
+// its staging slot as 4-bit codes in reference coordinates (0 = no base).
+__device__ __forceinline__ void project_record(int rec, int t0, uint32_t *slot, int lane,
+                                               const uint8_t *__restrict__ rec_buf, const HetScratch &S) {
+    const int t1 = t0 + FUZ_TILE;
+    const int sbase = S.r_seg_off[rec];
+    const int nseg = S.r_nseg[rec];
+    const uint8_t *seq = rec_buf + S.r_seq[rec];
+    // 32-ary search: first segment whose end is > t0
+    int first = nseg, lo = 0, hi = nseg;
+    while (lo < hi) {
+        int n = hi - lo, step = (n + 31) >> 5;
+        int sb = lo + lane * step;
+        bool valid = sb < hi;
+        int sl = min(sb + step, hi) - 1;
+        int e = valid ? S.seg_rs[sbase + sl] + S.seg_len[sbase + sl] : 0x7fffffff;
+        uint32_t m = __ballot_sync(0xffffffffu, valid && e > t0);
+        if (!m) break;
+        int b = __ffs(m) - 1;
+        int cand = min(lo + (b + 1) * step, hi) - 1;
+        first = cand;
+        lo = lo + b * step;
+        hi = cand;
+    }
+    for (int c0 = first; c0 < nseg; c0 += 32) {
+        int si = c0 + lane;
+        bool valid = si < nseg;
+        int rs = valid ? S.seg_rs[sbase + si] : 0x7fffffff;
+        int ln = valid ? S.seg_len[sbase + si] : 0;
+        int qs = valid ? S.seg_qs[sbase + si] : 0;
+        uint32_t act = __ballot_sync(0xffffffffu, valid && rs < t1);
+        int n_act = __popc(act);                        // segments are sorted: a prefix of lanes
+        for (int j = 0; j < n_act; j++) {
+            int rs_j = __shfl_sync(0xffffffffu, rs, j);
+            int ln_j = __shfl_sync(0xffffffffu, ln, j);
+            int qs_j = __shfl_sync(0xffffffffu, qs, j);
+            int a = max(rs_j, t0), b = min(rs_j + ln_j, t1);
+            if (a < b) {
+                int wa = (a - t0) >> 3, wb = (b - 1 - t0) >> 3;
+                for (int W = wa + lane; W <= wb; W += 32) {
+                    int pw = t0 + 8 * W;
+                    uint32_t v = fetch8(seq, qs_j + (pw - rs_j));
+                    v &= nibble_mask(max(a - pw, 0), min(b - pw, 8));
+                    slot[W] |= v;
+                }
+            }
+            __syncwarp();
+        }
+        if (n_act < 32) break;
+    }
+}
+
+__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_tile(
+    const uint8_t *__restrict__ rec_buf, HetScratch S, int64_t cap_sites, uint32_t *__restrict__ counts_out,
+    fuz_status *st) {
+    if (st->error) return;   // an earlier kernel rejected the batch: scratch may be undefined
+    __shared__ uint32_t stage[FUZ_NSLOT][FUZ_TILE_THREADS];
+    __shared__ int list[FUZ_TILE_THREADS];
+    __shared__ int s_warp_tot[FUZ_NW];
+    __shared__ int s_n, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int t0 = tile * FUZ_TILE, t1 = t0 + FUZ_TILE;
+    const int c = S.tile_ctg[tile];
+    const int rlo = S.tile_rlo[tile], rhi = S.tile_rhi[tile];
+#pragma unroll
+    for (int s = 0; s < FUZ_NSLOT; s++) stage[s][tid] = 0;
+    // c16[b][j]: 16-bit counters of base b for positions 2j (low half) and 2j+1 (high half)
+    uint32_t c16[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) c16[b][j] = 0;
+    int n_reads_seen = 0;
+    __syncthreads();
+    for (int cb = rlo; cb < rhi; cb += FUZ_TILE_THREADS) {
+        // compact the records overlapping the tile (any order: only counts matter here)
+        int r = cb + tid;
+        bool ok = r < rhi && S.r_flags[r] && S.r_gend[r] > t0 && S.r_gstart[r] < t1;
+        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < FUZ_NW; w++) { int v = s_warp_tot[w]; if (w < warp) off += v; tot += v; }
+        if (ok) list[off + __popc(m & ((1u << lane) - 1u))] = r;
+        __syncthreads();
+        n_reads_seen += tot;
+        for (int g = 0; g < tot; g += FUZ_NSLOT) {
+            int ns = min(FUZ_NSLOT, tot - g);
+            for (int s = warp; s < ns; s += FUZ_NW) project_record(list[g + s], t0, stage[s], lane, rec_buf, S);
+            __syncthreads();
+            // count: 4-bit lanes, at most FUZ_NSLOT (<= 15) increments per lane per round
+            uint32_t c4[4] = {0, 0, 0, 0};
+            const uint32_t M = 0x11111111u;
+            for (int s = 0; s < ns; s++) {
+                uint32_t w = stage[s][tid];
+                stage[s][tid] = 0;
+                uint32_t p0 = w & M, p1 = (w >> 1) & M, p2 = (w >> 2) & M, p3 = (w >> 3) & M;
+                uint32_t sum = p0 + p1 + p2 + p3;
+                uint32_t multi = ((sum >> 1) | (sum >> 2)) & M;   // codes with 2+ bits (M R S V W Y H K D B N)
+                if (multi) { p0 &= ~multi; p1 &= ~multi; p2 &= ~multi; p3 &= ~multi; }
+                c4[0] += p0; c4[1] += p1; c4[2] += p2; c4[3] += p3;   // A=1 C=2 G=4 T=8
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t x = c4[b];
+                c16[b][0] += (x & 0xFu) | ((x & 0xF0u) << 12);
+                c16[b][1] += ((x >> 8) & 0xFu) | ((x & 0xF000u) << 4);
+                c16[b][2] += ((x >> 16) & 0xFu) | ((x >> 4) & 0xF0000u);
+                c16[b][3] += ((x >> 24) & 0xFu) | ((x >> 12) & 0xF0000u);
+            }
+            __syncthreads();
+        }
+    }
+    if (n_reads_seen > 65535 && tid == 0) fuz_raise(st, FUZ_E_DEPTH, tile);
+    uint32_t cnt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) cnt[i][b] = (c16[b][i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+    if (counts_out) {
+        uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+    }
+    emit_tile_sites(cnt, tile, t0, S.ctg_poslast_g[c], S, cap_sites, st, s_warp_tot, &s_base);
+}
+
+// ---------------------------------------------------------------- cross-check pileup (impl 1)
+// One warp per accepted record walks its CIGAR and adds every M/=/X base with a global
+// atomic.  Slow by design (L2 atomics); kept as an independent device implementation that
+// the tests compare against the tiled kernel.
+__global__ void __launch_bounds__(256) k_pileup_atomic(
+    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
+    const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S,
+    uint32_t *__restrict__ counts, const fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp_g; r < n_rec; r += n_warps) {
+        if (!S.r_flags[r]) continue;
+        const uint8_t *rec = rec_buf + rec_off[r];
+        int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
+        const int64_t gend = ctg_goff[c + 1];
+        const int l_name = fuz_ld_u32_un(rec + 12) & 0xFF;
+        const int n_cig = fuz_ld_u32_un(rec + 16) & 0xFFFF;
+        const uint8_t *cig = rec + 36 + l_name;
+        const uint8_t *seq = cig + 4 * (int64_t)n_cig;
+        int64_t rp = S.r_gstart[r];
+        int qp = 0;
+        for (int k = 0; k < n_cig; k++) {
+            uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
+            int len = (int)(cw >> 4);
+            uint32_t op = cw & 15;
+            if (op == 4 || op == 1) qp += len;
+            else if (op == 2) rp += len;
+            else if (op_is_match(op)) {
+                for (int i = lane; i < len; i += 32) {
+                    int q = qp + i;
+                    uint32_t byte = seq[q >> 1];
+                    uint32_t nib = (q & 1) ? (byte & 15u) : (byte >> 4);
+                    int b = nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1;
+                    int64_t p = rp + i;
+                    if (b >= 0 && p < gend) atomicAdd(&counts[4 * p + b], 1u);
+                }
+                rp += len; qp += len;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
+    const uint32_t *__restrict__ counts, HetScratch S, int64_t cap_sites, fuz_status *st) {
+    if (st->error) return;
+    __shared__ int s_warp_tot[FUZ_NW];
+    __shared__ int s_base;
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int t0 = tile * FUZ_TILE;
+    uint32_t cnt[8][4];
+    const uint4 *in = reinterpret_cast<const uint4 *>(counts) + (size_t)t0 + (size_t)tid * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint4 v = in[i];
+        cnt[i][0] = v.x; cnt[i][1] = v.y; cnt[i][2] = v.z; cnt[i][3] = v.w;
+    }
+    emit_tile_sites(cnt, tile, t0, S.ctg_poslast_g[S.tile_ctg[tile]], S, cap_sites, st, s_warp_tot, &s_base);
+}
+
+// ---------------------------------------------------------------- ordered sites + rows
+__global__ void k_sites_count(int n_tiles, HetScratch S, int64_t cap_sites, fuz_status *st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
+        int64_t total = S.tile_site_off[n_tiles];
+        st->need_sites = total;
+        if (total > cap_sites) { fuz_raise(st, FUZ_E_CAPACITY, 0); total = 0; }
+        st->n_sites = total;
+    }
+}
+
+__global__ void k_order_sites(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff, fuz_outputs O,
+                              fuz_status *st) {
+    if (st->error) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        int cnt = S.tile_site_cnt[t];
+        if (!cnt) continue;
+        int src = S.tile_site_base[t], dst = S.tile_site_off[t], c = S.tile_ctg[t];
+        for (int j = 0; j < cnt; j++) {
+            int gp = S.us_gpos[src + j];
+            uint4 v = reinterpret_cast<const uint4 *>(S.us_cnt)[src + j];
+            uint32_t k[4] = {v.x << 2, (v.y << 2) | 1, (v.z << 2) | 2, (v.w << 2) | 3};
+            uint32_t m0 = max(max(k[0], k[1]), max(k[2], k[3])), m1 = 0;
+            for (int b = 0; b < 4; b++) if (k[b] != m0) m1 = max(m1, k[b]);
+            int b0 = m0 & 3, b1 = m1 & 3;
+            int d = dst + j;
+            S.s_gpos[d] = gp;
+            O.d_site_ctg[d] = c;
+            O.d_site_pos[d] = (int32_t)(gp - ctg_goff[c]) + 1;
+            reinterpret_cast<uint4 *>(O.d_site_cnt)[d] = v;
+            O.d_site_top[2 * d] = (uint8_t)b0; O.d_site_top[2 * d + 1] = (uint8_t)b1;
+            // allele order of the association table = order by "ACTG" (SURVEY.md B.1):
+            // rank A=0 C=1 T=2 G=3
+            const int rank[4] = {0, 1, 3, 2};
+            bool sw = rank[b0] > rank[b1];
+            O.d_site_al[2 * d] = (uint8_t)(sw ? b1 : b0); O.d_site_al[2 * d + 1] = (uint8_t)(sw ? b0 : b1);
+            S.site_rows[d] = (int)((m0 >> 2) + (m1 >> 2));
+        }
+    }
+}
+
+__global__ void k_rows_count(HetScratch S, int64_t cap_vmap, fuz_status *st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
+        int64_t total = S.site_row_off[st->n_sites];
+        st->need_vmap = total;
+        if (total > cap_vmap) { fuz_raise(st, FUZ_E_CAPACITY, 1); total = 0; }
+        st->n_vmap = total;
+    }
+}
+
+// One warp per site: the records covering the site, in record (= file) order, 32 at a
+// time; ballot/popc turn "my read carries the major / minor allele" into ordered row
+// slots (phasing.py:125-128: all major-allele reads, then all minor-allele reads).
+__global__ void __launch_bounds__(256) k_signature(
+    const uint8_t *__restrict__ rec_buf, const int32_t *__restrict__ rec_qid,
+    const int32_t *__restrict__ ctg_rec_off, HetScratch S, fuz_outputs O, fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_sites = (int)st->n_sites;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int s = warp_g; s < n_sites; s += n_warps) {
+        const int gp = S.s_gpos[s];
+        const int c = O.d_site_ctg[s];
+        const int b0 = O.d_site_top[2 * s], b1 = O.d_site_top[2 * s + 1];
+        const uint32_t code0 = 1u << b0, code1 = 1u << b1;
+        const int n0 = O.d_site_cnt[4 * s + b0], n1 = O.d_site_cnt[4 * s + b1];
+        const int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
+        const int rhi = fuz_upper_bound(S.r_gstart, r0, r1, gp);
+        const int rlo = fuz_lower_bound(S.r_gstart, r0, r1, gp - S.ctg_maxspan[c] + 1);
+        const int64_t off0 = S.site_row_off[s], off1 = off0 + n0;
+        int run0 = 0, run1 = 0;
+        for (int rb = rlo; rb < rhi; rb += 32) {
+            int r = rb + lane;
+            uint32_t nib = 0;
+            if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp) {
+                const int sb = S.r_seg_off[r];
+                int lo = 0, hi = S.r_nseg[r];                 // last segment with rs <= gp
+                while (lo < hi) { int m = (lo + hi) >> 1; if (S.seg_rs[sb + m] <= gp) lo = m + 1; else hi = m; }
+                if (lo > 0) {
+                    int si = sb + lo - 1;
+                    int rs = S.seg_rs[si];
+                    if (gp < rs + S.seg_len[si]) {
+                        int q = S.seg_qs[si] + (gp - rs);
+                        uint32_t byte = rec_buf[S.r_seq[r] + (q >> 1)];
+                        nib = (q & 1) ? (byte & 15u) : (byte >> 4);
+                    }
+                }
+            }
+            uint32_t m0 = __ballot_sync(0xffffffffu, nib == code0);
+            uint32_t m1 = __ballot_sync(0xffffffffu, nib == code1);
+            if (nib == code0 || nib == code1) {
+                bool first = nib == code0;
+                int64_t i = first ? off0 + run0 + __popc(m0 & lt) : off1 + run1 + __popc(m1 & lt);
+                if (i < O.cap_vmap) {
+                    O.d_vm_site[i] = s;
+                    O.d_vm_base[i] = (uint8_t)(first ? b0 : b1);
+                    O.d_vm_qid[i] = rec_qid[r];
+                }
+            }
+            run0 += __popc(m0); run1 += __popc(m1);
+        }
+        if (lane == 0 && (run0 != n0 || run1 != n1)) fuz_raise(st, FUZ_E_INTERNAL, s);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
+    if (!ctx || !in || !out) return FUZ_E_ARG;
+    if (in->n_ctg < 1 || in->n_rec < 0) return fuz_fail(ctx, FUZ_E_ARG, "fuz_het_call: empty batch");
+    if (in->total_glen <= 0 || in->total_glen % FUZ_TILE || in->total_glen > 0x7fff0000LL)
+        return fuz_fail(ctx, FUZ_E_ARG, "total_glen %lld must be a positive multiple of %d below 2^31",
+                        (long long)in->total_glen, FUZ_TILE);
+    cudaStream_t st = ctx->stream;
+    const int n_rec = in->n_rec, n_ctg = in->n_ctg;
+    const int n_tiles = (int)(in->total_glen / FUZ_TILE);
+    const int64_t seg_cap = in->rec_bytes / 8 + n_rec + 1;   // sum ceil(n_cigar/2) <= rec_bytes/8 + n_rec
+    const int64_t cap_sites = out->cap_sites;
+    HetScratch S;
+    FuzLayout L;
+    size_t o_gstart = L.add(4 * (size_t)(n_rec + 1)), o_gend = L.add(4 * (size_t)(n_rec + 1));
+    size_t o_segoff = L.add(4 * (size_t)(n_rec + 2)), o_nseg = L.add(4 * (size_t)(n_rec + 1));
+    size_t o_segcnt = L.add(4 * (size_t)(n_rec + 2)), o_rseq = L.add(8 * (size_t)(n_rec + 1));
+    size_t o_flags = L.add((size_t)n_rec + 1);
+    size_t o_srs = L.add(4 * (size_t)seg_cap), o_slen = L.add(4 * (size_t)seg_cap), o_sqs = L.add(4 * (size_t)seg_cap);
+    size_t o_clast = L.add(4 * (size_t)n_ctg), o_cspan = L.add(4 * (size_t)n_ctg), o_cpl = L.add(4 * (size_t)n_ctg);
+    size_t o_tctg = L.add(4 * (size_t)n_tiles), o_tlo = L.add(4 * (size_t)n_tiles), o_thi = L.add(4 * (size_t)n_tiles);
+    size_t o_tbase = L.add(4 * (size_t)n_tiles), o_tcnt = L.add(4 * (size_t)(n_tiles + 1)),
+           o_toff = L.add(4 * (size_t)(n_tiles + 2));
+    size_t o_usg = L.add(4 * (size_t)cap_sites), o_usc = L.add(16 * (size_t)cap_sites);
+    size_t o_sg = L.add(4 * (size_t)cap_sites), o_srow = L.add(4 * (size_t)(cap_sites + 1)),
+           o_sroff = L.add(4 * (size_t)(cap_sites + 2));
+    size_t o_counts = 0;
+    const bool need_counts = ctx->pileup_impl == 1 && !out->d_counts;
+    if (need_counts) o_counts = L.add(16 * (size_t)in->total_glen);
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    S.r_gstart = fuz_at<int32_t>(ctx, o_gstart); S.r_gend = fuz_at<int32_t>(ctx, o_gend);
+    S.r_seg_off = fuz_at<int32_t>(ctx, o_segoff); S.r_nseg = fuz_at<int32_t>(ctx, o_nseg);
+    S.r_segcnt = fuz_at<int32_t>(ctx, o_segcnt); S.r_seq = fuz_at<int64_t>(ctx, o_rseq);
+    S.r_flags = fuz_at<uint8_t>(ctx, o_flags);
+    S.seg_rs = fuz_at<int32_t>(ctx, o_srs); S.seg_len = fuz_at<int32_t>(ctx, o_slen); S.seg_qs = fuz_at<int32_t>(ctx, o_sqs);
+    S.ctg_last_rec = fuz_at<int32_t>(ctx, o_clast); S.ctg_maxspan = fuz_at<int32_t>(ctx, o_cspan);
+    S.ctg_poslast_g = fuz_at<int32_t>(ctx, o_cpl);
+    S.tile_ctg = fuz_at<int32_t>(ctx, o_tctg); S.tile_rlo = fuz_at<int32_t>(ctx, o_tlo); S.tile_rhi = fuz_at<int32_t>(ctx, o_thi);
+    S.tile_site_base = fuz_at<int32_t>(ctx, o_tbase); S.tile_site_cnt = fuz_at<int32_t>(ctx, o_tcnt);
+    S.tile_site_off = fuz_at<int32_t>(ctx, o_toff);
+    S.us_gpos = fuz_at<int32_t>(ctx, o_usg); S.us_cnt = fuz_at<uint32_t>(ctx, o_usc);
+    S.s_gpos = fuz_at<int32_t>(ctx, o_sg); S.site_rows = fuz_at<int32_t>(ctx, o_srow);
+    S.site_row_off = fuz_at<int32_t>(ctx, o_sroff);
+    S.counts = out->d_counts ? out->d_counts : (need_counts ? fuz_at<uint32_t>(ctx, o_counts) : nullptr);
+    S.seg_cap = seg_cap; S.n_tiles = n_tiles;
+
+    k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, n_ctg);
+    FUZ_LAUNCH_CHECK(ctx, "k_het_init");
+    if (n_rec > 0) {
+        k_rec_segbound<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S.r_segcnt);
+        FUZ_LAUNCH_CHECK(ctx, "k_rec_segbound");
+    }
+    if ((rc = fuz_scan_i32(ctx, S.r_segcnt, S.r_seg_off, n_rec, nullptr, nullptr))) return rc;
+    if (n_rec > 0) {
+        k_scan_records<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
+                                                         in->d_ctg_goff, n_ctg, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_scan_records");
+    }
+    k_ctg_finish<<<(n_ctg + 255) / 256, 256, 0, st>>>(n_ctg, in->d_ctg_goff, S);
+    FUZ_LAUNCH_CHECK(ctx, "k_ctg_finish");
+    k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S);
+    FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->timing) {
+        if (ctx->timing_used == ctx->timing_events.size()) {
+            cudaEvent_t a, b;
+            FUZ_CUDA(ctx, cudaEventCreate(&a));
+            FUZ_CUDA(ctx, cudaEventCreate(&b));
+            ctx->timing_events.push_back({a, b});
+        }
+        ev0 = ctx->timing_events[ctx->timing_used].first;
+        ev1 = ctx->timing_events[ctx->timing_used].second;
+        ctx->timing_used++;
+    }
+    if (ctx->pileup_impl == 0) {
+        if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
+        k_pileup_tile<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(in->d_rec_buf, S, cap_sites, out->d_counts, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_pileup_tile");
+        if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
+    } else {
+        FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
+        if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
+        if (n_rec > 0) {
+            k_pileup_atomic<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
+                                                              in->d_ctg_goff, n_ctg, S, S.counts, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_pileup_atomic");
+        }
+        if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
+        k_het_from_counts<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S.counts, S, cap_sites, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
+    }
+    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, nullptr))) return rc;
+    k_sites_count<<<1, 32, 0, st>>>(n_tiles, S, cap_sites, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_sites_count");
+    k_order_sites<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_order_sites");
+    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, nullptr))) return rc;
+    k_rows_count<<<1, 32, 0, st>>>(S, out->cap_vmap, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_rows_count");
+    k_signature<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_signature");
+    return FUZ_OK;
+}
+
+extern "C" int fuz_het_call(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
+    return fuz_het_call_impl(ctx, in, out);
+}

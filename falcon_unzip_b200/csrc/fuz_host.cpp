@@ -1,0 +1,110 @@
+// Host-side helpers of the phasing path (no CUDA): record index, QNAME -> q_id, CPython-2
+// dict order.  They feed the device kernels and format their results; none of them
+// computes any pileup / phasing result.
+#include <stdint.h>
+#include <string.h>
+
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "fuz.h"
+
+extern "C" int fuz_host_index_records(const uint8_t *h_rec_buf, int64_t rec_bytes, int64_t *h_rec_off, int64_t cap_rec,
+                                      int64_t *n_rec) {
+    if (!h_rec_buf || !n_rec || rec_bytes < 0) return FUZ_E_ARG;
+    int64_t o = 0, n = 0;
+    while (o < rec_bytes) {
+        if (o + 4 > rec_bytes) return FUZ_E_BADRECORD;
+        int32_t bs;
+        memcpy(&bs, h_rec_buf + o, 4);
+        if (bs < 32 || o + 4 + (int64_t)bs > rec_bytes) return FUZ_E_BADRECORD;
+        if (h_rec_off) {
+            if (n >= cap_rec) return FUZ_E_CAPACITY;
+            h_rec_off[n] = o;
+        }
+        o += 4 + (int64_t)bs;
+        n++;
+    }
+    if (h_rec_off) {
+        if (n > cap_rec) return FUZ_E_CAPACITY;
+        h_rec_off[n] = o;
+    }
+    *n_rec = n;
+    return FUZ_OK;
+}
+
+// first-seen QNAME -> q_id, assigned before any filtering (reference phasing.py:47-54)
+extern "C" int fuz_host_assign_qids(const uint8_t *h_rec_buf, const int64_t *h_rec_off, int64_t n_rec,
+                                    const int32_t *h_ctg_rec_off, int32_t n_ctg, int32_t *h_rec_qid, int32_t *h_ctg_nq,
+                                    int64_t *h_name_first) {
+    if (!h_rec_buf || !h_rec_off || !h_ctg_rec_off || !h_rec_qid || !h_ctg_nq || n_ctg < 1) return FUZ_E_ARG;
+    int64_t q_base = 0;
+    for (int32_t c = 0; c < n_ctg; c++) {
+        const int64_t r0 = h_ctg_rec_off[c], r1 = h_ctg_rec_off[c + 1];
+        if (r0 > r1 || r1 > n_rec) return FUZ_E_ARG;
+        std::unordered_map<std::string_view, int32_t> table;
+        table.reserve((size_t)(r1 - r0) * 2 + 16);
+        for (int64_t r = r0; r < r1; r++) {
+            const uint8_t *rec = h_rec_buf + h_rec_off[r];
+            const int l_name = rec[12];
+            if (l_name < 1) return FUZ_E_BADRECORD;
+            std::string_view name(reinterpret_cast<const char *>(rec + 36), (size_t)l_name - 1);
+            auto it = table.find(name);
+            int32_t q;
+            if (it == table.end()) {
+                q = (int32_t)table.size();
+                table.emplace(name, q);
+                if (h_name_first) h_name_first[q_base + q] = r;
+            } else {
+                q = it->second;
+            }
+            h_rec_qid[r] = q;
+        }
+        h_ctg_nq[c] = (int32_t)table.size();
+        q_base += (int64_t)table.size();
+    }
+    return FUZ_OK;
+}
+
+// CPython 2.7 Objects/dictobject.c, insert-only, int keys (hash(i) = i, -1 -> -2):
+// iteration order = slot order.
+extern "C" int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int64_t *out) {
+    if ((!keys || !out) && n > 0) return FUZ_E_ARG;
+    struct Entry { int64_t hash; int64_t key; bool used; };
+    std::vector<Entry> slots(8, Entry{0, 0, false});
+    uint64_t mask = 7;
+    int64_t used = 0;
+    auto find_slot = [](std::vector<Entry> &tab, uint64_t m, int64_t hash, int64_t key, bool match) -> size_t {
+        uint64_t i = (uint64_t)hash & m;
+        uint64_t perturb = (uint64_t)hash;
+        for (;;) {
+            Entry &e = tab[i & m];
+            if (!e.used || (match && e.hash == hash && e.key == key)) return (size_t)(i & m);
+            i = i * 5 + perturb + 1;
+            perturb >>= 5;
+        }
+    };
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t key = keys[k];
+        const int64_t hash = key == -1 ? -2 : key;
+        size_t s = find_slot(slots, mask, hash, key, true);
+        if (slots[s].used) continue;
+        slots[s] = Entry{hash, key, true};
+        used++;
+        if ((uint64_t)used * 3 >= (mask + 1) * 2) {
+            const uint64_t minused = (uint64_t)(used > 50000 ? 2 : 4) * (uint64_t)used;
+            uint64_t newsize = 8;
+            while (newsize <= minused) newsize <<= 1;
+            std::vector<Entry> fresh(newsize, Entry{0, 0, false});
+            for (const Entry &e : slots)
+                if (e.used) fresh[find_slot(fresh, newsize - 1, e.hash, e.key, false)] = e;
+            slots.swap(fresh);
+            mask = newsize - 1;
+        }
+    }
+    int64_t w = 0;
+    for (const Entry &e : slots)
+        if (e.used) out[w++] = e.key;
+    return FUZ_OK;
+}

@@ -1,0 +1,127 @@
+// Internal declarations shared by the translation units of libfuz.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "fuz.h"
+
+#define FUZ_TILE 2048              // reference positions per pileup tile (one CTA)
+#define FUZ_TILE_THREADS 256       // 8 positions (one 32-bit word of 4-bit codes) per thread
+#define FUZ_NW (FUZ_TILE_THREADS / 32)
+#define FUZ_NSLOT 15               // reads staged per counting round (4-bit lanes hold <= 15)
+#define FUZ_GRID_BLOCKS (148 * 4)  // grid-stride kernels: 4 CTAs of 256 threads per SM
+
+struct fuz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // scratch arena (device), grown on demand, reused across calls
+    uint8_t *arena = nullptr;
+    size_t arena_cap = 0;
+    // status block
+    fuz_status *d_status = nullptr;
+    fuz_status *h_status = nullptr;   // pinned
+    int64_t launches = 0;
+    int pileup_impl = 0;
+    int64_t max_pairs_per_site = 96;
+    // timing of the dominant kernel
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    size_t timing_used = 0;
+    // device + pinned staging for the *_host entry points
+    uint8_t *stage_dev = nullptr; size_t stage_dev_cap = 0;
+    uint8_t *stage_pin = nullptr; size_t stage_pin_cap = 0;
+};
+
+int fuz_fail(fuz_ctx *ctx, int code, const char *fmt, ...);
+
+#define FUZ_CUDA(ctx, expr)                                                              \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fuz_fail((ctx), FUZ_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define FUZ_LAUNCH_CHECK(ctx, name)                                                      \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e_ = cudaGetLastError();                                             \
+        if (e_ != cudaSuccess)                                                           \
+            return fuz_fail((ctx), FUZ_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// Bump layout over the context arena: add() all buffers, then commit() (grows the arena
+// if needed; growing synchronises the stream) and resolve pointers with at().
+struct FuzLayout {
+    size_t off = 0;
+    size_t add(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l);
+template <typename T>
+static inline T *fuz_at(fuz_ctx *ctx, size_t off) { return reinterpret_cast<T *>(ctx->arena + off); }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ void fuz_raise(fuz_status *st, int code, int idx) {
+    if (atomicCAS(&st->error, 0, code) == 0) st->error_index = idx;
+}
+
+// 32-bit little-endian load from an arbitrarily aligned address.  Always touches the
+// aligned word after it: callers guarantee >= 8 readable bytes past any loaded field
+// (rec_buf carries 16 bytes of slack).
+__device__ __forceinline__ uint32_t fuz_ld_u32_un(const uint8_t *p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
+}
+
+__device__ __forceinline__ int fuz_warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int fuz_warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ long long fuz_warp_sum64(long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+// first index in [lo, hi) with a[i] >= key
+__device__ __forceinline__ int fuz_lower_bound(const int32_t *a, int lo, int hi, int key) {
+    while (lo < hi) {
+        int m = (lo + hi) >> 1;
+        if (a[m] < key) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+// first index in [lo, hi) with a[i] > key
+__device__ __forceinline__ int fuz_upper_bound(const int32_t *a, int lo, int hi, int key) {
+    while (lo < hi) {
+        int m = (lo + hi) >> 1;
+        if (a[m] <= key) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+#endif
+
+// exclusive scan of n int32 values (n read from *d_n if d_n != nullptr, clamped to cap);
+// out has n+1 entries (out[n] = total); optionally stores the total as int64.
+int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap,
+                 const int64_t *d_n, int64_t *d_total64);

@@ -1,0 +1,626 @@
+// Stages 2-4 of the phasing path on device arrays:
+//   association table   reference falcon_unzip/phasing.py:137-206
+//   phased blocks       reference falcon_unzip/phasing.py:208-421
+//   phased reads        reference falcon_unzip/phasing.py:423-480
+// All row counts live in the device status block; no host synchronisation in between.
+#include "fuz_internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ shared helpers
+__global__ void k_set_counts(fuz_status *st, int64_t n_sites, int64_t n_vmap, int64_t n_atable, int reset_error) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (reset_error) { st->error = 0; st->error_index = 0; }
+        if (n_sites >= 0) st->n_sites = n_sites;
+        if (n_vmap >= 0) st->n_vmap = n_vmap;
+        if (n_atable >= 0) st->n_atable = n_atable;
+    }
+}
+
+// row range of every site inside the (site-grouped) vmap rows
+__global__ void k_site_rowoff(const int32_t *__restrict__ vm_site, int32_t *__restrict__ row_off, const fuz_status *st) {
+    if (st->error) return;
+    const int n_sites = (int)st->n_sites, n_vmap = (int)st->n_vmap;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x)
+        row_off[s] = s == n_sites ? n_vmap : fuz_lower_bound(vm_site, 0, n_vmap, s);
+}
+
+// first site index of every contig
+__global__ void k_ctg_siteoff(const int32_t *__restrict__ site_ctg, int n_ctg, int32_t *__restrict__ ctg_site_off,
+                              const fuz_status *st) {
+    if (st->error) return;
+    const int n_sites = (int)st->n_sites;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= n_ctg; c += gridDim.x * blockDim.x)
+        ctg_site_off[c] = c == n_ctg ? n_sites : fuz_lower_bound(site_ctg, 0, n_sites, c);
+}
+
+// One warp per site.  dup[i] = an earlier row of the same (site, allele) carries the same
+// q_id (the reference builds set(qids): phasing.py:189, :448-449).
+__global__ void __launch_bounds__(256) k_dup_flags(const int32_t *__restrict__ row_off, const uint8_t *__restrict__ vm_base,
+                                                   const int32_t *__restrict__ vm_qid, uint8_t *__restrict__ dup,
+                                                   const fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_sites = (int)st->n_sites;
+    for (int s = warp_g; s < n_sites; s += n_warps) {
+        const int off = row_off[s], n = row_off[s + 1] - off;
+        for (int i = lane; i < n; i += 32) {
+            const int q = vm_qid[off + i];
+            const uint8_t b = vm_base[off + i];
+            uint8_t d = 0;
+            for (int j = 0; j < i; j++)
+                if (vm_qid[off + j] == q && vm_base[off + j] == b) { d = 1; break; }
+            dup[off + i] = d;
+        }
+    }
+}
+
+// ================================================================== association table
+struct AssocScratch {
+    int32_t *row_off, *uq, *uq_n, *na0, *qmin, *qmax, *cand_cnt, *cand_off, *at_cnt, *at_off;
+    int4 *pair_ct;
+    uint8_t *dup;
+    int64_t max_pairs;
+};
+
+// sorted unique q_id lists per (site, allele): uq[row_off[s] ..) for allele al0 and
+// uq[row_off[s] + na0[s] ..) for allele al1, lengths uq_n[2s], uq_n[2s+1].
+__global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ site_al, const uint8_t *__restrict__ vm_base,
+                                                    const int32_t *__restrict__ vm_qid, AssocScratch A, fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_sites = (int)st->n_sites;
+    for (int s = warp_g; s < n_sites; s += n_warps) {
+        const int off = A.row_off[s], n = A.row_off[s + 1] - off;
+        const uint8_t al0 = site_al[2 * s], al1 = site_al[2 * s + 1];
+        int c0 = 0, u0 = 0, u1 = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
+        bool bad = al0 == al1 || al0 > 3 || al1 > 3;
+        for (int i = lane; i < n; i += 32) {
+            uint8_t b = vm_base[off + i];
+            int q = vm_qid[off + i];
+            if (b != al0 && b != al1) bad = true;
+            c0 += b == al0;
+            if (!A.dup[off + i]) { u0 += b == al0; u1 += b == al1; }
+            mn = min(mn, q); mx = max(mx, q);
+        }
+        c0 = fuz_warp_sum(c0); u0 = fuz_warp_sum(u0); u1 = fuz_warp_sum(u1);
+        for (int d = 16; d > 0; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (bad || c0 == 0 || c0 == n) {          // a site must carry exactly two alleles
+            if (lane == 0) fuz_raise(st, FUZ_E_FORMAT, s);
+            continue;
+        }
+        // rank of every non-duplicate q among the non-duplicates of its allele
+        for (int i = lane; i < n; i += 32) {
+            if (A.dup[off + i]) continue;
+            const uint8_t b = vm_base[off + i];
+            const int q = vm_qid[off + i];
+            int rank = 0;
+            for (int j = 0; j < n; j++)
+                rank += (!A.dup[off + j] && vm_base[off + j] == b && vm_qid[off + j] < q);
+            A.uq[off + (b == al0 ? 0 : c0) + rank] = q;
+        }
+        if (lane == 0) {
+            A.na0[s] = c0; A.uq_n[2 * s] = u0; A.uq_n[2 * s + 1] = u1; A.qmin[s] = mn; A.qmax[s] = mx;
+        }
+    }
+}
+
+// number of later sites of the same contig within 65536 bp (phasing.py:166-170)
+__global__ void k_cand_count(const int32_t *__restrict__ site_ctg, const int32_t *__restrict__ site_pos, AssocScratch A,
+                             const fuz_status *st) {
+    if (st->error) return;
+    const int n_sites = (int)st->n_sites;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
+        const int c = site_ctg[s];
+        const long long lim = (long long)site_pos[s] + (1 << 16);
+        int lo = s + 1, hi = n_sites;                // first index with (ctg,pos) > (c, lim)
+        while (lo < hi) {
+            int m = (lo + hi) >> 1;
+            bool le = site_ctg[m] < c || (site_ctg[m] == c && (long long)site_pos[m] <= lim);
+            if (le) lo = m + 1; else hi = m;
+        }
+        A.cand_cnt[s] = lo - s - 1;
+    }
+}
+
+__global__ void k_pairs_check(AssocScratch A, fuz_status *st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
+        int64_t total = A.cand_off[st->n_sites];
+        st->need_pairs = total;
+        if (total > A.max_pairs) fuz_raise(st, FUZ_E_CAPACITY, 4);
+    }
+}
+
+__device__ __forceinline__ int sorted_intersect(const int32_t *__restrict__ a, int na, const int32_t *__restrict__ b, int nb) {
+    int i = 0, j = 0, s = 0;
+    while (i < na && j < nb) {
+        int x = a[i], y = b[j];
+        s += x == y; i += x <= y; j += y <= x;
+    }
+    return s;
+}
+
+// One warp per left site, one lane per candidate partner: 2x2 set-intersection sizes
+// (phasing.py:187-191), kept for the fill pass; emitted rows are capped at 501 per left
+// site AFTER the total >= 6 filter (phasing.py:192-206).
+__global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_sites = (int)st->n_sites;
+    for (int i1 = warp_g; i1 < n_sites; i1 += n_warps) {
+        const int nc = A.cand_cnt[i1];
+        const int64_t base = A.cand_off[i1];
+        const int o1 = A.row_off[i1], n10 = A.uq_n[2 * i1], n11 = A.uq_n[2 * i1 + 1];
+        const int32_t *a0 = A.uq + o1, *a1 = A.uq + o1 + A.na0[i1];
+        const int mn1 = A.qmin[i1], mx1 = A.qmax[i1];
+        int emitted = 0;
+        for (int k0 = 0; k0 < nc && emitted <= 500; k0 += 32) {
+            const int k = k0 + lane;
+            const bool valid = k < nc;
+            int4 ct = make_int4(0, 0, 0, 0);
+            if (valid) {
+                const int i2 = i1 + 1 + k;
+                if (A.qmin[i2] <= mx1 && mn1 <= A.qmax[i2]) {     // q_id ranges overlap
+                    const int o2 = A.row_off[i2], n20 = A.uq_n[2 * i2], n21 = A.uq_n[2 * i2 + 1];
+                    const int32_t *b0 = A.uq + o2, *b1 = A.uq + o2 + A.na0[i2];
+                    ct.x = sorted_intersect(a0, n10, b0, n20);
+                    ct.y = sorted_intersect(a0, n10, b1, n21);
+                    ct.z = sorted_intersect(a1, n11, b0, n20);
+                    ct.w = sorted_intersect(a1, n11, b1, n21);
+                }
+                A.pair_ct[base + k] = ct;
+            }
+            emitted += __popc(__ballot_sync(0xffffffffu, valid && ct.x + ct.y + ct.z + ct.w >= 6));
+        }
+        if (lane == 0) A.at_cnt[i1] = min(emitted, 501);
+    }
+}
+
+__global__ void k_atable_count(AssocScratch A, int64_t cap_atable, fuz_status *st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
+        int64_t total = A.at_off[st->n_sites];
+        st->need_atable = total;
+        if (total > cap_atable) { fuz_raise(st, FUZ_E_CAPACITY, 2); total = 0; }
+        st->n_atable = total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pair_fill(AssocScratch A, fuz_outputs O, const fuz_status *st) {
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_sites = (int)st->n_sites;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int i1 = warp_g; i1 < n_sites; i1 += n_warps) {
+        const int nc = A.cand_cnt[i1];
+        const int64_t base = A.cand_off[i1];
+        const int64_t out0 = A.at_off[i1];
+        int run = 0;
+        for (int k0 = 0; k0 < nc && run <= 500; k0 += 32) {
+            const int k = k0 + lane;
+            const bool valid = k < nc;
+            int4 ct = valid ? A.pair_ct[base + k] : make_int4(0, 0, 0, 0);
+            const bool pass = valid && ct.x + ct.y + ct.z + ct.w >= 6;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            const int rank = run + __popc(m & lt);
+            if (pass && rank <= 500) {
+                const int64_t o = out0 + rank;
+                O.d_at_s1[o] = i1; O.d_at_s2[o] = i1 + 1 + k;
+                reinterpret_cast<int4 *>(O.d_at_ct)[o] = ct;
+            }
+            run += __popc(m);
+        }
+    }
+}
+
+// ================================================================== phased blocks
+struct BlockScratch {
+    int32_t *ctg_site_off, *left_cnt, *left_off, *left_cur, *left_row, *right_off, *minleft_row;
+    uint32_t *fp;   // forest pointer: parent * 2 + parity bit
+};
+
+__device__ __forceinline__ int row_d(const int32_t *__restrict__ at_ct, int row) {       // cis - trans
+    int4 c = reinterpret_cast<const int4 *>(at_ct)[row];
+    return (c.x + c.w) - (c.y + c.z);
+}
+
+__global__ void k_blk_init(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+    if (st->error) return;
+    const int n_sites = (int)st->n_sites;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
+        B.left_cnt[s] = 0;
+        if (s < n_sites) { B.left_cur[s] = 0; B.minleft_row[s] = -1; }
+    }
+}
+
+// accepted rows |cis - trans| >= 6 (phasing.py:245) -> in-degree of the right site
+__global__ void k_edge_count(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+    if (st->error) return;
+    const int n_at = (int)st->n_atable;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_at; r += gridDim.x * blockDim.x) {
+        int d = row_d(O.d_at_ct, r);
+        int s2 = O.d_at_s2[r];
+        if (abs(d) >= 6 && s2 >= 0 && s2 < (int)st->n_sites) atomicAdd(&B.left_cnt[s2], 1);
+    }
+}
+
+__global__ void k_edge_fill(BlockScratch B, fuz_outputs O, fuz_status *st) {
+    if (st->error) return;
+    const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_at; r += gridDim.x * blockDim.x) {
+        const int s1 = O.d_at_s1[r], s2 = O.d_at_s2[r];
+        if (s1 < 0 || s2 <= s1 || s2 >= n_sites || O.d_site_ctg[s1] != O.d_site_ctg[s2] ||
+            (r > 0 && (O.d_at_s1[r - 1] > s1 || (O.d_at_s1[r - 1] == s1 && O.d_at_s2[r - 1] >= s2)))) {
+            fuz_raise(st, FUZ_E_FORMAT, r);     // rows must be strictly ordered by (site1, site2)
+            continue;
+        }
+        if (abs(row_d(O.d_at_ct, r)) >= 6) B.left_row[B.left_off[s2] + atomicAdd(&B.left_cur[s2], 1)] = r;
+    }
+}
+
+// per site: row range as left site; accepted row with the smallest left partner
+__global__ void k_site_prep(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+    if (st->error) return;
+    const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
+        B.right_off[s] = s == n_sites ? n_at : fuz_lower_bound(O.d_at_s1, 0, n_at, s);
+        if (s < n_sites) {
+            int best = -1, best_s1 = 0x7fffffff;
+            for (int k = B.left_off[s]; k < B.left_off[s + 1]; k++) {
+                int row = B.left_row[k], s1 = O.d_at_s1[row];
+                if (s1 < best_s1) { best_s1 = s1; best = row; }
+            }
+            B.minleft_row[s] = best;
+        }
+    }
+}
+
+// One CTA per contig: pass-1 forest + pointer jumping, pass-2 sweep, pass-3 extents and
+// scores, pass-4 block chaining (phasing.py:240-408; parallel forms of SURVEY.md A.3).
+__global__ void __launch_bounds__(1024) k_ctg_phase(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+    if (st->error) return;
+    const int c = blockIdx.x;
+    const int cs0 = B.ctg_site_off[c], cs1 = B.ctg_site_off[c + 1];
+    const int n = cs1 - cs0;
+    if (n <= 0) return;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    volatile uint32_t *fp = B.fp;
+    // ---- pass 1 as a forest (rows are ordered by (site1, site2), ties impossible)
+    for (int x = cs0 + tid; x < cs1; x += nt) {
+        int parent = x, bit = 0;
+        bool in_pos = false;
+        int ml = B.minleft_row[x];
+        if (ml >= 0) {
+            in_pos = true;
+            parent = O.d_at_s1[ml];
+            bit = row_d(O.d_at_ct, ml) < 0;                    // trans > cis flips the state
+        } else {
+            for (int r = B.right_off[x]; r < B.right_off[x + 1]; r++) {
+                int d = row_d(O.d_at_ct, r);
+                if (abs(d) < 6) continue;
+                in_pos = true;                                 // first accepted row = smallest right partner
+                int rm = O.d_at_s2[r];
+                int mlr = B.minleft_row[rm];
+                // partner already has a state when x is first touched iff it has a left partner < x
+                if (mlr >= 0 && O.d_at_s1[mlr] < x) { parent = rm; bit = d < 0; }
+                break;
+            }
+        }
+        fp[x] = ((uint32_t)parent << 1) | (uint32_t)bit;
+        O.d_ph_state[x] = in_pos ? 0 : 255;
+    }
+    __syncthreads();
+    int rounds = 1;
+    while ((1 << rounds) < n) rounds++;
+    rounds++;
+    for (int it = 0; it < rounds; it++) {
+        for (int x = cs0 + tid; x < cs1; x += nt) {
+            uint32_t me = fp[x];
+            int p = (int)(me >> 1);
+            if (p != x) {
+                uint32_t pp = fp[p];
+                fp[x] = (pp & ~1u) | ((me ^ pp) & 1u);
+            }
+        }
+        __syncthreads();
+    }
+    for (int x = cs0 + tid; x < cs1; x += nt)
+        if (O.d_ph_state[x] != 255) O.d_ph_state[x] = (uint8_t)(fp[x] & 1u);
+    __syncthreads();
+    // ---- pass 2: one left-to-right sweep (a second sweep never changes anything)
+    if (tid < 32) {
+        volatile uint8_t *state = O.d_ph_state;
+        for (int x = cs0; x < cs1; x++) {
+            const int l0 = B.left_off[x], l1 = B.left_off[x + 1];
+            if (l0 == l1) continue;
+            int s0 = 0;                                         // score(state 0) - score(state 1)
+            for (int k = l0 + lane; k < l1; k += 32) {
+                int row = B.left_row[k];
+                int d = row_d(O.d_at_ct, row);
+                s0 += state[O.d_at_s1[row]] == 0 ? d : -d;
+            }
+            s0 = fuz_warp_sum(s0);
+            if (lane == 0) { if (s0 < 0) state[x] = 1; else if (s0 > 0) state[x] = 0; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- pass 3: scores and extents (positions are the 1-based file positions)
+    for (int x = cs0 + tid; x < cs1; x += nt) {
+        const uint8_t sx = O.d_ph_state[x];
+        int lscore = 0, rscore = 0, lext = O.d_site_pos[x], rext = O.d_site_pos[x];
+        if (sx != 255) {
+            for (int k = B.left_off[x]; k < B.left_off[x + 1]; k++) {
+                int row = B.left_row[k], q = O.d_at_s1[row];
+                int d = row_d(O.d_at_ct, row);
+                int dd = O.d_ph_state[q] == sx ? d : -d;
+                lscore += dd;
+                if (dd > 0) lext = min(lext, O.d_site_pos[q]);
+            }
+            for (int r = B.right_off[x]; r < B.right_off[x + 1]; r++) {
+                int d = row_d(O.d_at_ct, r);
+                if (abs(d) < 6) continue;
+                int q = O.d_at_s2[r];
+                int dd = O.d_ph_state[q] == sx ? d : -d;
+                rscore += dd;
+                if (dd > 0) rext = max(rext, O.d_site_pos[q]);
+            }
+        }
+        O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
+        O.d_ph_block[x] = 0;
+    }
+    __syncthreads();
+    // ---- pass 4: chain sites into blocks by the running maximum of right extents
+    if (tid == 0) {
+        int block_id = 1, max_right_ext = 0, pb_first = -1, pb_n = 0;
+        for (int x = cs0; x < cs1; x++) {
+            if (O.d_ph_state[x] == 255 || O.d_ph_rscore[x] < 10 || O.d_ph_lscore[x] < 10) continue;
+            if (max_right_ext < O.d_ph_lext[x]) {
+                if (pb_n > 3) block_id++;
+                else for (int y = pb_first; y >= 0 && y < x; y++) O.d_ph_block[y] = 0;
+                pb_first = x; pb_n = 0;
+            }
+            O.d_ph_block[x] = block_id; pb_n++;
+            max_right_ext = max(max_right_ext, O.d_ph_rext[x]);
+        }
+        if (pb_n <= 3) for (int y = pb_first; y >= 0 && y < cs1; y++) O.d_ph_block[y] = 0;
+    }
+}
+
+// ================================================================== phased reads
+struct ReadScratch {
+    int32_t *row_off, *ctg_q_off, *q_cnt, *q_off, *q_cur, *q_ent, *pr_cnt, *pr_off;
+    uint8_t *dup;
+    int64_t total_nq;
+};
+
+__global__ void k_rd_init(ReadScratch R) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= R.total_nq; q += (int64_t)gridDim.x * blockDim.x) {
+        R.q_cnt[q] = 0;
+        if (q < R.total_nq) R.q_cur[q] = 0;
+    }
+}
+
+// rows that can vote: first occurrence of (site, allele, q_id), site inside a block
+__device__ __forceinline__ int voting_gq(int i, const ReadScratch &R, const fuz_outputs &O, fuz_status *st) {
+    if (R.dup[i]) return -1;
+    const int s = O.d_vm_site[i];
+    if (O.d_ph_block[s] <= 0) return -1;
+    const int c = O.d_site_ctg[s];
+    const int q = O.d_vm_qid[i];
+    if (q < 0 || q >= R.ctg_q_off[c + 1] - R.ctg_q_off[c]) { fuz_raise(st, FUZ_E_FORMAT, i); return -1; }
+    return R.ctg_q_off[c] + q;
+}
+
+__global__ void k_q_count(ReadScratch R, fuz_outputs O, fuz_status *st) {
+    if (st->error) return;
+    const int n_vmap = (int)st->n_vmap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
+        int gq = voting_gq(i, R, O, st);
+        if (gq >= 0) atomicAdd(&R.q_cnt[gq], 1);
+    }
+}
+
+__global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
+    if (st->error) return;
+    const int n_vmap = (int)st->n_vmap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
+        int gq = voting_gq(i, R, O, st);
+        if (gq >= 0) R.q_ent[R.q_off[gq] + atomicAdd(&R.q_cur[gq], 1)] = i;
+    }
+}
+
+// One thread per read: distinct phased variants -> (block, phase) counts; blocks in
+// ascending id; a row when |n0 - n1| > 1 (phasing.py:465-480).  fill = 0 counts rows.
+__global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_status *st) {
+    if (st->error) return;
+    for (int64_t gq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gq < R.total_nq; gq += (int64_t)gridDim.x * blockDim.x) {
+        const int e0 = R.q_off[gq], e1 = R.q_off[gq + 1];
+        int rows = 0, last = 0;
+        int64_t out = fill ? R.pr_off[gq] : 0;
+        int c = -1;
+        while (e0 < e1) {
+            int cur = 0x7fffffff;
+            for (int e = e0; e < e1; e++) {
+                int b = O.d_ph_block[O.d_vm_site[R.q_ent[e]]];
+                if (b > last && b < cur) cur = b;
+            }
+            if (cur == 0x7fffffff) break;
+            int n0 = 0, n1 = 0;
+            for (int e = e0; e < e1; e++) {
+                int i = R.q_ent[e], s = O.d_vm_site[i];
+                if (O.d_ph_block[s] != cur) continue;
+                uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
+                if (O.d_vm_base[i] == h0) n0++; else n1++;
+            }
+            int phase = n0 - n1 > 1 ? 0 : (n1 - n0 > 1 ? 1 : -1);
+            if (phase >= 0) {
+                if (fill && out < O.cap_reads) {
+                    if (c < 0) c = fuz_upper_bound(R.ctg_q_off, 0, n_ctg + 1, (int)gq) - 1;
+                    O.d_pr_ctg[out] = c; O.d_pr_qid[out] = (int)gq - R.ctg_q_off[c];
+                    O.d_pr_block[out] = cur; O.d_pr_phase[out] = phase; O.d_pr_n0[out] = n0; O.d_pr_n1[out] = n1;
+                }
+                out++; rows++;
+            }
+            last = cur;
+        }
+        if (!fill) R.pr_cnt[gq] = rows;
+    }
+}
+
+__global__ void k_reads_count(ReadScratch R, int64_t cap_reads, fuz_status *st) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
+        int64_t total = R.pr_off[R.total_nq];
+        st->need_reads = total;
+        if (total > cap_reads) { fuz_raise(st, FUZ_E_CAPACITY, 3); total = 0; }
+        st->n_reads = total;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
+    (void)n_ctg;
+    cudaStream_t st = ctx->stream;
+    const int64_t cs = out->cap_sites, cv = out->cap_vmap;
+    AssocScratch A;
+    A.max_pairs = ctx->max_pairs_per_site * (cs > 0 ? cs : 1);
+    FuzLayout L;
+    size_t o_roff = L.add(4 * (size_t)(cs + 2)), o_uq = L.add(4 * (size_t)(cv + 1)), o_uqn = L.add(8 * (size_t)(cs + 1));
+    size_t o_na0 = L.add(4 * (size_t)(cs + 1)), o_qmin = L.add(4 * (size_t)(cs + 1)), o_qmax = L.add(4 * (size_t)(cs + 1));
+    size_t o_cc = L.add(4 * (size_t)(cs + 2)), o_co = L.add(4 * (size_t)(cs + 2));
+    size_t o_ac = L.add(4 * (size_t)(cs + 2)), o_ao = L.add(4 * (size_t)(cs + 2));
+    size_t o_pc = L.add(16 * (size_t)(A.max_pairs + 1)), o_dup = L.add((size_t)cv + 1);
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    A.row_off = fuz_at<int32_t>(ctx, o_roff); A.uq = fuz_at<int32_t>(ctx, o_uq); A.uq_n = fuz_at<int32_t>(ctx, o_uqn);
+    A.na0 = fuz_at<int32_t>(ctx, o_na0); A.qmin = fuz_at<int32_t>(ctx, o_qmin); A.qmax = fuz_at<int32_t>(ctx, o_qmax);
+    A.cand_cnt = fuz_at<int32_t>(ctx, o_cc); A.cand_off = fuz_at<int32_t>(ctx, o_co);
+    A.at_cnt = fuz_at<int32_t>(ctx, o_ac); A.at_off = fuz_at<int32_t>(ctx, o_ao);
+    A.pair_ct = fuz_at<int4>(ctx, o_pc); A.dup = fuz_at<uint8_t>(ctx, o_dup);
+    const int64_t *d_ns = &ctx->d_status->n_sites;
+
+    k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, A.row_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
+    k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A.row_off, out->d_vm_base, out->d_vm_qid, A.dup, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
+    k_uniq_lists<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
+    k_cand_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_ctg, out->d_site_pos, A, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_cand_count");
+    if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, nullptr))) return rc;
+    k_pairs_check<<<1, 32, 0, st>>>(A, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_pairs_check");
+    k_pair_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
+    if ((rc = fuz_scan_i32(ctx, A.at_cnt, A.at_off, cs, d_ns, nullptr))) return rc;
+    k_atable_count<<<1, 32, 0, st>>>(A, out->cap_atable, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_atable_count");
+    k_pair_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_pair_fill");
+    return FUZ_OK;
+}
+
+int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t cs = out->cap_sites, ca = out->cap_atable;
+    BlockScratch B;
+    FuzLayout L;
+    size_t o_cso = L.add(4 * (size_t)(n_ctg + 2)), o_lc = L.add(4 * (size_t)(cs + 2)), o_lo = L.add(4 * (size_t)(cs + 2));
+    size_t o_lcur = L.add(4 * (size_t)(cs + 1)), o_lrow = L.add(4 * (size_t)(ca + 1)), o_ro = L.add(4 * (size_t)(cs + 2));
+    size_t o_ml = L.add(4 * (size_t)(cs + 1)), o_fp = L.add(4 * (size_t)(cs + 1));
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    B.ctg_site_off = fuz_at<int32_t>(ctx, o_cso); B.left_cnt = fuz_at<int32_t>(ctx, o_lc); B.left_off = fuz_at<int32_t>(ctx, o_lo);
+    B.left_cur = fuz_at<int32_t>(ctx, o_lcur); B.left_row = fuz_at<int32_t>(ctx, o_lrow); B.right_off = fuz_at<int32_t>(ctx, o_ro);
+    B.minleft_row = fuz_at<int32_t>(ctx, o_ml); B.fp = fuz_at<uint32_t>(ctx, o_fp);
+    k_ctg_siteoff<<<(n_ctg + 256) / 256, 256, 0, st>>>(out->d_site_ctg, n_ctg, B.ctg_site_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_ctg_siteoff");
+    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
+    k_edge_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
+    if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, nullptr))) return rc;
+    k_edge_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
+    k_site_prep<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_site_prep");
+    k_ctg_phase<<<n_ctg, 1024, 0, st>>>(B, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_ctg_phase");
+    return FUZ_OK;
+}
+
+int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t cs = out->cap_sites, cv = out->cap_vmap;
+    ReadScratch R;
+    R.total_nq = total_nq;
+    FuzLayout L;
+    size_t o_roff = L.add(4 * (size_t)(cs + 2)), o_cq = L.add(4 * (size_t)(n_ctg + 2));
+    size_t o_qc = L.add(4 * (size_t)(total_nq + 2)), o_qo = L.add(4 * (size_t)(total_nq + 2)), o_qcur = L.add(4 * (size_t)(total_nq + 1));
+    size_t o_qe = L.add(4 * (size_t)(cv + 1)), o_pc = L.add(4 * (size_t)(total_nq + 2)), o_po = L.add(4 * (size_t)(total_nq + 2));
+    size_t o_dup = L.add((size_t)cv + 1);
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    R.row_off = fuz_at<int32_t>(ctx, o_roff); R.ctg_q_off = fuz_at<int32_t>(ctx, o_cq);
+    R.q_cnt = fuz_at<int32_t>(ctx, o_qc); R.q_off = fuz_at<int32_t>(ctx, o_qo); R.q_cur = fuz_at<int32_t>(ctx, o_qcur);
+    R.q_ent = fuz_at<int32_t>(ctx, o_qe); R.pr_cnt = fuz_at<int32_t>(ctx, o_pc); R.pr_off = fuz_at<int32_t>(ctx, o_po);
+    R.dup = fuz_at<uint8_t>(ctx, o_dup);
+    if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, nullptr))) return rc;
+    k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, R.row_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
+    k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
+    k_rd_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R);
+    FUZ_LAUNCH_CHECK(ctx, "k_rd_init");
+    k_q_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_q_count");
+    if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, nullptr))) return rc;
+    k_q_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_q_fill");
+    k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 0, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
+    if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, nullptr))) return rc;
+    k_reads_count<<<1, 32, 0, st>>>(R, out->cap_reads, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_reads_count");
+    k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 1, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
+    return FUZ_OK;
+}
+
+static int set_counts(fuz_ctx *ctx, int64_t n_sites, int64_t n_vmap, int64_t n_atable) {
+    k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_status, n_sites, n_vmap, n_atable, 1);
+    FUZ_LAUNCH_CHECK(ctx, "k_set_counts");
+    return FUZ_OK;
+}
+
+extern "C" int fuz_association_table(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, int64_t n_vmap, fuz_outputs *out) {
+    if (!ctx || !out || n_sites < 0 || n_vmap < 0 || n_sites > out->cap_sites || n_vmap > out->cap_vmap)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_association_table: bad arguments");
+    int rc = set_counts(ctx, n_sites, n_vmap, 0);
+    return rc ? rc : fuz_association_impl(ctx, n_ctg, out);
+}
+
+extern "C" int fuz_phased_blocks(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, int64_t n_atable, fuz_outputs *out) {
+    if (!ctx || !out || n_ctg < 1 || n_sites < 0 || n_atable < 0 || n_sites > out->cap_sites || n_atable > out->cap_atable)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_phased_blocks: bad arguments");
+    int rc = set_counts(ctx, n_sites, -1, n_atable);
+    return rc ? rc : fuz_blocks_impl(ctx, n_ctg, out);
+}
+
+extern "C" int fuz_phased_reads(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, int64_t n_sites,
+                                int64_t n_vmap, fuz_outputs *out) {
+    if (!ctx || !out || n_ctg < 1 || !d_ctg_nq || total_nq < 0 || n_sites < 0 || n_vmap < 0 || n_sites > out->cap_sites ||
+        n_vmap > out->cap_vmap)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_phased_reads: bad arguments");
+    int rc = set_counts(ctx, n_sites, n_vmap, -1);
+    return rc ? rc : fuz_reads_impl(ctx, n_ctg, d_ctg_nq, total_nq, out);
+}

@@ -1,0 +1,401 @@
+"""Host side of the device pipeline: batch preparation (record index, QNAME -> q_id),
+buffer ownership (PyTorch tensors), calls into libfuz.so, capacity retry.
+
+PyTorch is plumbing here: it owns device / pinned memory and the CUDA stream; every
+computation of the phasing path happens in the hand-written kernels of libfuz.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import FuzError, lib
+
+
+def _np_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+# --------------------------------------------------------------------------- batches
+@dataclasses.dataclass
+class PreparedBatch:
+    """Host arrays of one batch of contigs (see include/fuz.h, fuz_host_batch)."""
+    records: np.ndarray          # uint8 [rec_bytes] verbatim BAM records
+    rec_off: np.ndarray          # int64 [n_rec + 1]
+    rec_qid: np.ndarray          # int32 [n_rec]
+    ctg_rec_off: np.ndarray      # int32 [n_ctg + 1]
+    ctg_len: np.ndarray          # int32 [n_ctg]
+    ctg_nq: np.ndarray           # int32 [n_ctg]
+    name_first: np.ndarray       # int64 [sum nq] record index of the first record of each q_id
+    ctg_names: List[str]
+    pinned: Dict[str, object] = dataclasses.field(default_factory=dict)  # torch tensors keeping pinned memory alive
+
+    @property
+    def n_ctg(self) -> int:
+        return len(self.ctg_len)
+
+    @property
+    def n_rec(self) -> int:
+        return len(self.rec_off) - 1
+
+    @property
+    def ctg_q_off(self) -> np.ndarray:
+        return np.concatenate([[0], np.cumsum(self.ctg_nq)]).astype(np.int64)
+
+    def goff(self) -> np.ndarray:
+        t = lib().fuz_tile_size()
+        padded = np.maximum((self.ctg_len.astype(np.int64) + t - 1) // t * t, t)
+        return np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+
+    def qname(self, c: int, q: int) -> str:
+        r = int(self.name_first[int(self.ctg_q_off[c]) + q])
+        o = int(self.rec_off[r])
+        l_name = int(self.records[o + 12])
+        return self.records[o + 36:o + 36 + l_name - 1].tobytes().decode("ascii")
+
+    def qnames(self, c: int) -> List[str]:
+        return [self.qname(c, q) for q in range(int(self.ctg_nq[c]))]
+
+
+def index_records(records: np.ndarray) -> np.ndarray:
+    """Offsets of the records of a concatenated record buffer (block_size chain)."""
+    records = np.ascontiguousarray(records, dtype=np.uint8)
+    n = C.c_int64(0)
+    rc = lib().fuz_host_index_records(_np_ptr(records), len(records), None, 0, C.byref(n))
+    if rc:
+        raise FuzError(rc, "corrupt BAM record stream")
+    off = np.empty(n.value + 1, dtype=np.int64)
+    rc = lib().fuz_host_index_records(_np_ptr(records), len(records), _np_ptr(off), n.value, C.byref(n))
+    if rc:
+        raise FuzError(rc, "corrupt BAM record stream")
+    return off
+
+
+def record_refids(records: np.ndarray, rec_off: np.ndarray) -> np.ndarray:
+    idx = rec_off[:-1, None] + 4 + np.arange(4)[None, :]
+    return records[idx].copy().view("<i4").reshape(-1)
+
+
+def prepare_batch(records, ctg_names: Sequence[str], ctg_lens: Sequence[int],
+                  rec_off: Optional[np.ndarray] = None, ctg_rec_off: Optional[np.ndarray] = None,
+                  pin: bool = False) -> PreparedBatch:
+    """records: concatenated BAM records grouped by contig in the order of ctg_names (refID
+    ascending, i.e. a coordinate-sorted BAM).  If ctg_rec_off is None the grouping is read
+    from the refID fields, which must be 0..n_ctg-1 in order."""
+    if not isinstance(records, np.ndarray):
+        records = np.frombuffer(records, dtype=np.uint8)
+    records = np.ascontiguousarray(records, dtype=np.uint8)
+    if rec_off is None:
+        rec_off = index_records(records)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+    n_rec, n_ctg = len(rec_off) - 1, len(ctg_names)
+    if ctg_rec_off is None:
+        refid = record_refids(records, rec_off) if n_rec else np.zeros(0, np.int32)
+        if n_rec and (np.any(np.diff(refid) < 0) or refid.min() < 0 or refid.max() >= n_ctg):
+            raise FuzError(_lib.FUZ_E_UNSORTED, "records are not grouped by reference id 0..%d" % (n_ctg - 1))
+        ctg_rec_off = np.searchsorted(refid, np.arange(n_ctg + 1), side="left")
+    ctg_rec_off = np.ascontiguousarray(ctg_rec_off, dtype=np.int32)
+    rec_qid = np.empty(n_rec, dtype=np.int32)
+    ctg_nq = np.zeros(n_ctg, dtype=np.int32)
+    name_first = np.empty(max(n_rec, 1), dtype=np.int64)
+    rc = lib().fuz_host_assign_qids(_np_ptr(records), _np_ptr(rec_off), n_rec, _np_ptr(ctg_rec_off), n_ctg,
+                                    _np_ptr(rec_qid), _np_ptr(ctg_nq), _np_ptr(name_first))
+    if rc:
+        raise FuzError(rc, "fuz_host_assign_qids failed")
+    pb = PreparedBatch(records, rec_off, rec_qid, ctg_rec_off, np.asarray(ctg_lens, dtype=np.int32), ctg_nq,
+                       name_first[:int(ctg_nq.sum())].copy(), list(ctg_names))
+    if pin:
+        pin_batch(pb)
+    return pb
+
+
+def pin_batch(pb: PreparedBatch) -> None:
+    """Move the batch's arrays into pinned host memory (torch owns it)."""
+    import torch
+    for name in ("records", "rec_off", "rec_qid", "ctg_rec_off", "ctg_len", "ctg_nq"):
+        a = getattr(pb, name)
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        pb.pinned[name] = t
+        setattr(pb, name, t.numpy())
+
+
+# --------------------------------------------------------------------------- results
+@dataclasses.dataclass
+class PhaseResult:
+    arrays: Dict[str, np.ndarray]
+    n_sites: int
+    n_vmap: int
+    n_atable: int
+    n_reads: int
+    n_accepted: int
+    aligned_bases: int
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["arrays"][name]
+        except KeyError:
+            raise AttributeError(name)
+
+
+_CAP_KEY_N = {"sites": "n_sites", "vmap": "n_vmap", "atable": "n_atable", "reads": "n_reads"}
+
+
+def default_caps(total_len: int, n_rec: int) -> Dict[str, int]:
+    sites = max(4096, total_len // 128)
+    return dict(sites=sites, vmap=max(1 << 16, sites * 64), atable=max(1 << 16, sites * 24),
+                reads=max(1 << 12, 2 * n_rec))
+
+
+def _grow(caps: Dict[str, int], st: _lib.Status) -> Dict[str, int]:
+    new = dict(caps)
+    for key, need in (("sites", st.need_sites), ("vmap", st.need_vmap), ("atable", st.need_atable),
+                      ("reads", st.need_reads)):
+        if need > caps[key]:
+            new[key] = int(need * 1.25) + 1024
+    return new
+
+
+class DeviceOutputs:
+    """fuz_outputs backed by torch tensors on the context's device."""
+
+    def __init__(self, caps: Dict[str, int], device, counts_len: int = 0):
+        import torch
+        self.caps = dict(caps)
+        self.t: Dict[str, "torch.Tensor"] = {}
+        self.c = _lib.Outputs()
+        for key in ("sites", "vmap", "atable", "reads"):
+            setattr(self.c, "cap_" + key, caps[key])
+        for name, dt, key, width in _lib.OUTPUT_ARRAYS:
+            t = torch.zeros(max(caps[key] * width, 4), dtype=torch.int32 if dt == "i4" else torch.uint8,
+                            device=device)
+            self.t[name] = t
+            setattr(self.c, "d_" + name, t.data_ptr())
+        self.counts = None
+        if counts_len:
+            self.counts = torch.zeros(counts_len * 4, dtype=torch.int32, device=device)
+            self.c.d_counts = self.counts.data_ptr()
+
+    def set(self, name: str, values: np.ndarray) -> None:
+        import torch
+        v = torch.from_numpy(np.ascontiguousarray(values).reshape(-1))
+        self.t[name][:v.numel()].copy_(v.view(self.t[name].dtype) if v.dtype != self.t[name].dtype else v)
+
+    def fetch(self, st: _lib.Status) -> Dict[str, np.ndarray]:
+        out = {}
+        for name, dt, key, width in _lib.OUTPUT_ARRAYS:
+            n = int(getattr(st, _CAP_KEY_N[key]))
+            a = self.t[name][:n * width].cpu().numpy()
+            out[name] = a.reshape(n, width) if width > 1 else a
+        return out
+
+
+class DeviceBatch:
+    """fuz_batch backed by torch tensors."""
+
+    def __init__(self, pb: PreparedBatch, device):
+        import torch
+        self.pb = pb
+        goff = pb.goff()
+
+        def up(a, pad=0):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pad:
+                d = torch.zeros(t.numel() + pad, dtype=t.dtype, device=device)
+                d[:t.numel()].copy_(t, non_blocking=True)
+                return d
+            return t.to(device, non_blocking=True)
+        self.rec_buf = up(pb.records, pad=16)
+        self.rec_off = up(pb.rec_off)
+        self.rec_qid = up(pb.rec_qid) if pb.n_rec else torch.zeros(1, dtype=torch.int32, device=device)
+        self.ctg_rec_off = up(pb.ctg_rec_off)
+        self.ctg_len = up(pb.ctg_len)
+        self.ctg_goff = up(goff)
+        self.ctg_nq = up(pb.ctg_nq)
+        self.total_glen = int(goff[-1])
+        b = _lib.Batch()
+        b.n_ctg, b.n_rec, b.rec_bytes = pb.n_ctg, pb.n_rec, len(pb.records)
+        b.d_rec_buf, b.d_rec_off, b.d_rec_qid = self.rec_buf.data_ptr(), self.rec_off.data_ptr(), self.rec_qid.data_ptr()
+        b.d_ctg_rec_off, b.d_ctg_len = self.ctg_rec_off.data_ptr(), self.ctg_len.data_ptr()
+        b.d_ctg_goff, b.d_ctg_nq = self.ctg_goff.data_ptr(), self.ctg_nq.data_ptr()
+        b.total_glen, b.total_nq = self.total_glen, int(pb.ctg_nq.sum())
+        self.c = b
+
+
+class Engine:
+    """One libfuz context = one GPU = one stream (not thread safe; include/fuz.h)."""
+
+    def __init__(self, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("falcon_unzip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device_index = device
+        self.device = torch.device("cuda", device)
+        self.ctx = C.c_void_p()
+        rc = lib().fuz_ctx_create(device, C.byref(self.ctx))
+        if rc:
+            raise FuzError(rc, lib().fuz_last_error(None).decode())
+        self._torch = torch
+
+    def close(self) -> None:
+        if self.ctx:
+            lib().fuz_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options / status
+    def set_option(self, key: str, value: int) -> None:
+        _lib.check(self.ctx, lib().fuz_set_option(self.ctx, key.encode(), value))
+
+    def status(self, raise_on_error: bool = True) -> _lib.Status:
+        st = _lib.Status()
+        rc = lib().fuz_get_status(self.ctx, C.byref(st))
+        if rc and raise_on_error:
+            _lib.check(self.ctx, rc)
+        return st
+
+    def sync(self) -> None:
+        _lib.check(self.ctx, lib().fuz_sync(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(lib().fuz_launch_count(self.ctx))
+
+    def kernel_timing(self, enable: bool) -> None:
+        _lib.check(self.ctx, lib().fuz_kernel_timing(self.ctx, int(enable)))
+
+    def get_kernel_timing(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        _lib.check(self.ctx, lib().fuz_get_kernel_timing(self.ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ---- device-resident path
+    def upload(self, pb: PreparedBatch) -> DeviceBatch:
+        db = DeviceBatch(pb, self.device)
+        self._torch.cuda.synchronize(self.device)
+        return db
+
+    def alloc_outputs(self, caps: Dict[str, int], counts_len: int = 0) -> DeviceOutputs:
+        do = DeviceOutputs(caps, self.device, counts_len)
+        self._torch.cuda.synchronize(self.device)
+        return do
+
+    def phase_batch_async(self, db: DeviceBatch, do: DeviceOutputs) -> None:
+        _lib.check(self.ctx, lib().fuz_phase_batch(self.ctx, C.byref(db.c), C.byref(do.c)))
+
+    def het_call_async(self, db: DeviceBatch, do: DeviceOutputs) -> None:
+        _lib.check(self.ctx, lib().fuz_het_call(self.ctx, C.byref(db.c), C.byref(do.c)))
+
+    def association_async(self, n_ctg: int, n_sites: int, n_vmap: int, do: DeviceOutputs) -> None:
+        _lib.check(self.ctx, lib().fuz_association_table(self.ctx, n_ctg, n_sites, n_vmap, C.byref(do.c)))
+
+    def blocks_async(self, n_ctg: int, n_sites: int, n_atable: int, do: DeviceOutputs) -> None:
+        _lib.check(self.ctx, lib().fuz_phased_blocks(self.ctx, n_ctg, n_sites, n_atable, C.byref(do.c)))
+
+    def reads_async(self, n_ctg: int, ctg_nq: np.ndarray, n_sites: int, n_vmap: int, do: DeviceOutputs) -> None:
+        t = self._torch.from_numpy(np.ascontiguousarray(ctg_nq, dtype=np.int32)).to(self.device)
+        self._torch.cuda.synchronize(self.device)
+        _lib.check(self.ctx, lib().fuz_phased_reads(self.ctx, n_ctg, t.data_ptr(), int(np.sum(ctg_nq)), n_sites,
+                                                    n_vmap, C.byref(do.c)))
+        self.sync()
+
+    def _retry(self, caps, counts_len, run):
+        """run(outputs) launches; on FUZ_E_CAPACITY grow the failing capacity and rerun."""
+        for _ in range(8):
+            do = self.alloc_outputs(caps, counts_len)
+            run(do)
+            st = self.status(raise_on_error=False)
+            if st.error == _lib.FUZ_OK:
+                return do, st
+            if st.error != _lib.FUZ_E_CAPACITY:
+                self.status()      # raises with the library's message
+            if st.need_pairs > 0 and st.error_index == 4:
+                per_site = st.need_pairs // max(caps["sites"], 1) + 2
+                self.set_option("max_pairs_per_site", int(per_site))
+            caps = _grow(caps, st)
+        raise FuzError(_lib.FUZ_E_CAPACITY, "capacity retry did not converge")
+
+    def phase_device(self, pb: PreparedBatch, caps: Optional[Dict[str, int]] = None,
+                     want_counts: bool = False, stage: str = "all") -> PhaseResult:
+        """Upload, run (all four stages or only "het"), download everything."""
+        db = self.upload(pb)
+        caps = caps or default_caps(int(pb.ctg_len.sum()), pb.n_rec)
+        run = (lambda do: self.phase_batch_async(db, do)) if stage == "all" else (lambda do: self.het_call_async(db, do))
+        do, st = self._retry(caps, db.total_glen if want_counts else 0, run)
+        arrays = do.fetch(st)
+        if want_counts:
+            arrays["counts"] = do.counts.cpu().numpy().view(np.uint32).reshape(-1, 4)
+            arrays["goff"] = pb.goff()
+        return PhaseResult(arrays, int(st.n_sites), int(st.n_vmap), int(st.n_atable), int(st.n_reads),
+                           int(st.n_accepted), int(st.aligned_bases))
+
+    # ---- host-buffer path (what the reference-facing functions and bench e2e use)
+    def phase_host(self, pb: PreparedBatch, caps: Optional[Dict[str, int]] = None,
+                   host_out: Optional[Dict[str, np.ndarray]] = None) -> PhaseResult:
+        caps = caps or default_caps(int(pb.ctg_len.sum()), pb.n_rec)
+        hb = _lib.HostBatch()
+        hb.n_ctg, hb.n_rec, hb.rec_bytes = pb.n_ctg, pb.n_rec, len(pb.records)
+        hb.h_rec_buf, hb.h_rec_off, hb.h_rec_qid = _np_ptr(pb.records), _np_ptr(pb.rec_off), _np_ptr(pb.rec_qid)
+        hb.h_ctg_rec_off, hb.h_ctg_len, hb.h_ctg_nq = _np_ptr(pb.ctg_rec_off), _np_ptr(pb.ctg_len), _np_ptr(pb.ctg_nq)
+        for _ in range(8):
+            bufs = host_out if host_out is not None and host_out.get("_caps") == caps else alloc_host_outputs(caps)
+            ho = _lib.HostOutputs()
+            for key in ("sites", "vmap", "atable", "reads"):
+                setattr(ho, "cap_" + key, caps[key])
+            for name, _dt, _key, _w in _lib.OUTPUT_ARRAYS:
+                setattr(ho, name, _np_ptr(bufs[name]))
+            st = _lib.Status()
+            up, down = C.c_int64(0), C.c_int64(0)
+            rc = lib().fuz_phase_batch_host(self.ctx, C.byref(hb), C.byref(ho), C.byref(st), C.byref(up), C.byref(down))
+            if rc == _lib.FUZ_OK:
+                arrays = {}
+                for name, _dt, key, width in _lib.OUTPUT_ARRAYS:
+                    n = int(getattr(st, _CAP_KEY_N[key]))
+                    a = bufs[name][:n * width]
+                    arrays[name] = a.reshape(n, width) if width > 1 else a
+                return PhaseResult(arrays, int(st.n_sites), int(st.n_vmap), int(st.n_atable), int(st.n_reads),
+                                   int(st.n_accepted), int(st.aligned_bases), up.value, down.value)
+            if rc != _lib.FUZ_E_CAPACITY:
+                _lib.check(self.ctx, rc)
+            if st.need_pairs > 0 and st.error_index == 4:
+                self.set_option("max_pairs_per_site", int(st.need_pairs // max(caps["sites"], 1) + 2))
+            caps = _grow(caps, st)
+            host_out = None
+        raise FuzError(_lib.FUZ_E_CAPACITY, "capacity retry did not converge")
+
+
+def alloc_host_outputs(caps: Dict[str, int], pin: bool = False) -> Dict[str, np.ndarray]:
+    out: Dict[str, object] = {"_caps": dict(caps)}
+    keep = []
+    for name, dt, key, width in _lib.OUTPUT_ARRAYS:
+        n = max(caps[key] * width, 4)
+        if pin:
+            import torch
+            t = torch.empty(n, dtype=torch.int32 if dt == "i4" else torch.uint8).pin_memory()
+            keep.append(t)
+            out[name] = t.numpy()
+        else:
+            out[name] = np.empty(n, dtype=np.int32 if dt == "i4" else np.uint8)
+    out["_keep"] = keep
+    return out
+
+
+_engines: Dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (contexts are cheap to keep, costly to create)."""
+    e = _engines.get(device)
+    if e is None or not e.ctx:
+        e = Engine(device)
+        _engines[device] = e
+    return e

@@ -1,0 +1,129 @@
+"""Text renderings of the device results: byte-identical to the files the reference
+writes (reference falcon_unzip/phasing.py:124-134,199,418-421,
+478-480) including the Python-2 semantics of Appendix B (row order of phased_reads B.3,
+``str(float)`` B.5, single-space separators B.6)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from ._lib import lib
+
+BASES = "ACGT"
+
+
+def py27_float_str(v: float) -> str:
+    """Python 2 ``str(float)`` = '%.12g', plus '.0' when no '.', 'e', inf or nan appears."""
+    s = "%.12g" % v
+    if "." not in s and "e" not in s and "n" not in s:
+        s += ".0"
+    return s
+
+
+def py27_int_dict_order(keys) -> np.ndarray:
+    """Iteration order of a CPython-2.7 dict whose int keys were inserted in this order."""
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    uniq_n = len(np.unique(keys))
+    out = np.empty(max(uniq_n, 1), dtype=np.int64)
+    rc = lib().fuz_host_py27_int_dict_order(keys.ctypes.data, len(keys), out.ctypes.data)
+    if rc:
+        raise RuntimeError("fuz_host_py27_int_dict_order failed: %d" % rc)
+    return out[:uniq_n]
+
+
+def contig_slices(res, n_ctg: int) -> Dict[str, np.ndarray]:
+    """Row ranges of every contig inside the batch-wide row arrays."""
+    site_off = np.searchsorted(res.site_ctg, np.arange(n_ctg + 1), side="left")
+    vm_off = np.searchsorted(res.vm_site, site_off, side="left")
+    at_off = np.searchsorted(res.at_s1, site_off, side="left")
+    pr_off = np.searchsorted(res.pr_ctg, np.arange(n_ctg + 1), side="left")
+    return dict(site=site_off, vmap=vm_off, atable=at_off, reads=pr_off)
+
+
+def variant_pos_text(res, s0: int, s1: int, ref_seq: str) -> str:
+    """het_call/variant_pos: ``pos ref total b0 c0 b1 c1 b2 c2 b3 c3`` (phasing.py:124)."""
+    pos = res.site_pos[s0:s1].tolist()
+    cnt = res.site_cnt[s0:s1]
+    key = cnt.astype(np.int64) * 4 + np.arange(4)[None, :]
+    order = np.argsort(-key, axis=1, kind="stable")            # descending (count, base)
+    tot = cnt.sum(axis=1).tolist()
+    so = order.tolist()
+    sc = np.take_along_axis(cnt, order, axis=1).tolist()
+    return "".join("%d %s %d %s %d %s %d %s %d %s %d\n" % (
+        p, ref_seq[p - 1], t, BASES[o[0]], c[0], BASES[o[1]], c[1], BASES[o[2]], c[2], BASES[o[3]], c[3])
+        for p, t, o, c in zip(pos, tot, so, sc))
+
+
+def variant_map_text(res, s0: int, v0: int, v1: int, ref_seq: str) -> str:
+    """het_call/variant_map: ``pos ref allele q_id`` (phasing.py:126,128)."""
+    pos = res.site_pos[res.vm_site[v0:v1]].tolist()
+    return "".join("%d %s %s %d\n" % (p, ref_seq[p - 1], BASES[b], q)
+                   for p, b, q in zip(pos, res.vm_base[v0:v1].tolist(), res.vm_qid[v0:v1].tolist()))
+
+
+def q_id_map_text(names: Sequence[str]) -> str:
+    """het_call/q_id_map (phasing.py:132-134); dense int keys iterate ascending."""
+    return "".join("%d %s\n" % (i, n) for i, n in enumerate(names))
+
+
+def atable_text(res, a0: int, a1: int) -> str:
+    """g_atable/atable: ``pos1 b11 b12 pos2 b21 b22 c11 c12 c21 c22`` (phasing.py:199)."""
+    s1, s2 = res.at_s1[a0:a1], res.at_s2[a0:a1]
+    p1, p2 = res.site_pos[s1].tolist(), res.site_pos[s2].tolist()
+    al1, al2 = res.site_al[s1].tolist(), res.site_al[s2].tolist()
+    return "".join("%d %s %s %d %s %s %d %d %d %d\n" % (
+        x, BASES[a[0]], BASES[a[1]], y, BASES[b[0]], BASES[b[1]], c[0], c[1], c[2], c[3])
+        for x, a, y, b, c in zip(p1, al1, p2, al2, res.at_ct[a0:a1].tolist()))
+
+
+def phased_variants_text(res, s0: int, s1: int, ref_base) -> str:
+    """get_phased_blocks/phased_variants: P and V rows (phasing.py:411-421).
+    ref_base: str indexed by pos-1, or a dict pos -> base (file-level stage)."""
+    blk = res.ph_block[s0:s1]
+    out: List[str] = []
+    n_blocks = int(blk.max()) if len(blk) else 0
+    order = np.argsort(blk, kind="stable")
+    bounds = np.searchsorted(blk[order], np.arange(1, n_blocks + 2), side="left")
+    pos = res.site_pos[s0:s1]
+    for pid in range(1, n_blocks + 1):
+        idx = order[bounds[pid - 1]:bounds[pid]]
+        if len(idx) == 0:
+            continue
+        ps = pos[idx]
+        mn, mx = int(ps.min()), int(ps.max())
+        out.append("P %d %d %d %d %d %s\n" % (pid, mn, mx, mx - mn, len(idx),
+                                                py27_float_str(1.0 * (mx - mn) / len(idx))))
+        st = res.ph_state[s0:s1][idx].tolist()
+        al = res.site_al[s0:s1][idx].tolist()
+        for p, s, a, le, re_, ls, rs in zip(ps.tolist(), st, al, res.ph_lext[s0:s1][idx].tolist(),
+                                            res.ph_rext[s0:s1][idx].tolist(),
+                                            res.ph_lscore[s0:s1][idx].tolist(),
+                                            res.ph_rscore[s0:s1][idx].tolist()):
+            rb = ref_base[p] if isinstance(ref_base, dict) else ref_base[p - 1]
+            out.append("V %d %d %d_%s_%s %d_%s_%s %d %d %d %d\n" % (
+                pid, p, p, rb, BASES[a[s]], p, rb, BASES[a[1 - s]], le, re_, ls, rs))
+    return "".join(out)
+
+
+def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, names) -> str:
+    """phased_reads: ``q_id ctg block phase n0 n1 qname`` (phasing.py:478,480), reads in the
+    iteration order of the reference's ``read_to_variants`` dict (Python-2 int dict, keys
+    inserted in order of first appearance in variant_map)."""
+    vq = res.vm_qid[v0:v1]
+    if len(vq) == 0:
+        return ""
+    _, first = np.unique(vq, return_index=True)
+    order = py27_int_dict_order(vq[np.sort(first)])
+    q = res.pr_qid[r0:r1]
+    lo = np.searchsorted(q, order, side="left")
+    hi = np.searchsorted(q, order, side="right")
+    blk, ph = res.pr_block[r0:r1].tolist(), res.pr_phase[r0:r1].tolist()
+    n0, n1 = res.pr_n0[r0:r1].tolist(), res.pr_n1[r0:r1].tolist()
+    out: List[str] = []
+    for qq, a, b in zip(order.tolist(), lo.tolist(), hi.tolist()):
+        for i in range(a, b):
+            nm = names[qq] if not isinstance(names, dict) else names[qq]
+            out.append("%d %s %d %d %d %d %s\n" % (qq, ctg_id, blk[i], ph[i], n0[i], n1[i], nm))
+    return "".join(out)

@@ -1,0 +1,207 @@
+/*
+ * fuz.h -- C ABI of libfuz.so, the B200 (sm_100a) implementation of FALCON-Unzip's
+ * read-phasing hot path.  Plain pointers and sizes only; every function returns an int
+ * status (0 = FUZ_OK) and records a message retrievable with fuz_last_error().
+ *
+ * Reference interfaces replaced (PacificBiosciences/FALCON_unzip):
+ *   fuz_het_call            falcon_unzip/phasing.py:14-134   make_het_call
+ *   fuz_association_table   falcon_unzip/phasing.py:137-206  generate_association_table
+ *   fuz_phased_blocks       falcon_unzip/phasing.py:208-421  get_score + get_phased_blocks
+ *   fuz_phased_reads        falcon_unzip/phasing.py:423-480  get_phased_reads
+ *   fuz_phase_batch         falcon_unzip/phasing.py:482-553  phasing() (the four stages
+ *                           chained on the device for a batch of contigs)
+ *   fuz_host_*              host-side helpers of the same path (record index, QNAME ->
+ *                           q_id of phasing.py:47-54)
+ *
+ * Conventions
+ *   - "d_" pointers are DEVICE pointers owned by the caller (PyTorch tensors in the
+ *     Python host layer); "h_" pointers are host pointers.  The library never frees
+ *     caller memory.  Scratch memory is owned by the context and grows on demand.
+ *   - Outputs go into caller-provided capacity; if a capacity is too small the call
+ *     fails with FUZ_E_CAPACITY and fuz_status.need_* says how much is needed.
+ *   - A context is bound to one device and one stream and is not thread safe
+ *     (the reference runs one OS process per contig, unzip.py:255).
+ *   - No CPU fallback exists: without a CUDA device fuz_ctx_create fails.
+ *
+ * Device data model (struct-of-arrays, all little endian)
+ *   records   verbatim uncompressed BAM alignment records (block_size + body, SAM spec
+ *             4.2) concatenated in `rec_buf`; rec_off[i] is the byte offset of record i
+ *             (n_rec + 1 entries).  rec_buf must be followed by >= 16 readable bytes.
+ *             Records are grouped by contig (ctg_rec_off) and coordinate sorted inside a
+ *             contig, i.e. the order `samtools view <bam> <ctg>` prints.
+ *   sites     het-SNP sites ordered by (contig, position): site_ctg, site_pos (1-based
+ *             position inside the contig, the value the reference writes to files),
+ *             site_cnt[4] depth of A,C,G,T, site_al[2] the two called alleles as base
+ *             indices (0..3 = A,C,G,T) ordered by the string "ACTG" (CPython-2 dict order,
+ *             SURVEY.md B.1), site_top[2] the same two alleles ordered major, minor.
+ *   vmap      variant_map rows in file order: vm_site (index into sites), vm_base
+ *             (0..3), vm_qid (q_id inside the contig).
+ *   atable    association rows ordered by (site1, site2): at_s1, at_s2, at_ct[4] =
+ *             c11 c12 c21 c22 with alleles in site_al order.
+ *   phase     per site: ph_state (0 = (al0,al1), 1 = (al1,al0), 255 = site not in any
+ *             accepted atable row), ph_lext/ph_rext (1-based positions), ph_lscore,
+ *             ph_rscore, ph_block (block id, dense from 1 per contig, 0 = none).
+ *   reads     phased_reads rows ordered by (contig, q_id, block): pr_ctg, pr_qid,
+ *             pr_block, pr_phase, pr_n0, pr_n1.
+ */
+#ifndef FUZ_H_
+#define FUZ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUZ_VERSION 1
+
+enum {
+    FUZ_OK = 0,
+    FUZ_E_CUDA = 1,        /* CUDA runtime error (no device, launch failure, ...)      */
+    FUZ_E_ARG = 2,         /* invalid argument                                          */
+    FUZ_E_CAPACITY = 3,    /* an output / scratch capacity was too small (see status)   */
+    FUZ_E_BADRECORD = 4,   /* a record the reference would crash on (CIGAR '*', SEQ '*',
+                              M/=/X running past SEQ, unknown CIGAR op; phasing.py:72,84) */
+    FUZ_E_UNSORTED = 5,    /* records not coordinate sorted / not grouped by contig      */
+    FUZ_E_DEPTH = 6,       /* more than 65535 reads over one pileup tile                 */
+    FUZ_E_INTERNAL = 7,    /* kernels disagree with each other (a bug)                   */
+    FUZ_E_FORMAT = 8       /* stage input not in the reference-produced format           */
+};
+
+/* thresholds are the reference's literals (phasing.py:72-75,100,112,169,192,205,245,
+ * 394,398,477-479); they are compiled in, not configurable. */
+
+typedef struct fuz_ctx fuz_ctx;
+
+/* One batch of contigs.  Global pileup coordinates: contig c occupies
+ * [ctg_goff[c], ctg_goff[c] + ctg_len[c]); ctg_goff must be multiples of
+ * FUZ_TILE (fuz_tile_size()) so that no pileup tile straddles two contigs. */
+typedef struct {
+    int32_t n_ctg;
+    int32_t n_rec;
+    int64_t rec_bytes;
+    const uint8_t *d_rec_buf;     /* [rec_bytes + 16]                                   */
+    const int64_t *d_rec_off;     /* [n_rec + 1]                                        */
+    const int32_t *d_rec_qid;     /* [n_rec] q_id of the record's QNAME in its contig   */
+    const int32_t *d_ctg_rec_off; /* [n_ctg + 1] record range of each contig            */
+    const int32_t *d_ctg_len;     /* [n_ctg]                                            */
+    const int64_t *d_ctg_goff;    /* [n_ctg + 1] tile-aligned global offsets            */
+    const int32_t *d_ctg_nq;      /* [n_ctg] number of distinct QNAMEs (q_ids) per contig */
+    int64_t total_glen;           /* ctg_goff[n_ctg]                                    */
+    int64_t total_nq;             /* sum of ctg_nq                                      */
+} fuz_batch;
+
+typedef struct {
+    int64_t cap_sites, cap_vmap, cap_atable, cap_reads;
+    /* sites */
+    int32_t *d_site_ctg, *d_site_pos, *d_site_cnt /* [cap_sites*4] */;
+    uint8_t *d_site_al /* [cap_sites*2] */, *d_site_top /* [cap_sites*2] */;
+    /* vmap */
+    int32_t *d_vm_site, *d_vm_qid; uint8_t *d_vm_base;
+    /* atable */
+    int32_t *d_at_s1, *d_at_s2, *d_at_ct /* [cap_atable*4] */;
+    /* phase (per site, capacity cap_sites) */
+    uint8_t *d_ph_state; int32_t *d_ph_lext, *d_ph_rext, *d_ph_lscore, *d_ph_rscore, *d_ph_block;
+    /* reads */
+    int32_t *d_pr_ctg, *d_pr_qid, *d_pr_block, *d_pr_phase, *d_pr_n0, *d_pr_n1;
+    /* optional full pileup (debug / parity): [total_glen*4] depth of A,C,G,T, or NULL   */
+    uint32_t *d_counts;
+} fuz_outputs;
+
+/* Filled on the device, copied to the host by fuz_get_status(). */
+typedef struct {
+    int32_t error;                /* FUZ_OK or the first FUZ_E_* raised by a kernel      */
+    int32_t error_index;          /* record / site / tile index the error refers to      */
+    int64_t n_sites, n_vmap, n_atable, n_reads;
+    int64_t need_sites, need_vmap, need_atable, need_reads, need_pairs;
+    int64_t n_accepted;           /* records passing the filter of phasing.py:72-75      */
+    int64_t aligned_bases;        /* sum of M/=/X lengths over accepted records          */
+    int64_t n_segments;
+    int64_t reserved[4];
+} fuz_status;
+
+/* ---- context ------------------------------------------------------------------ */
+int fuz_version(void);
+int fuz_tile_size(void);
+int fuz_ctx_create(int device, fuz_ctx **out);
+int fuz_ctx_destroy(fuz_ctx *ctx);
+const char *fuz_last_error(fuz_ctx *ctx);      /* ctx may be NULL: create-time error     */
+int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
+/* options: "pileup_impl" 0 = tiled register pileup fused with the het test (default),
+ *          1 = global-atomic pileup + separate het test (cross-check path);
+ *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */
+int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value);
+int fuz_sync(fuz_ctx *ctx);
+/* device -> host copy of the status block of the last call (synchronises the stream) */
+int fuz_get_status(fuz_ctx *ctx, fuz_status *h_status);
+/* number of kernel launches issued by this context since creation */
+int64_t fuz_launch_count(fuz_ctx *ctx);
+/* CUDA-event timing of the dominant (pileup) kernel: enable, then read the accumulated
+ * milliseconds and launch count (synchronises).  Used by bench.py's roofline block.    */
+int fuz_kernel_timing(fuz_ctx *ctx, int enable);
+int fuz_get_kernel_timing(fuz_ctx *ctx, double *h_ms_total, int64_t *h_launches);
+
+/* ---- stages (asynchronous on the context stream; check with fuz_get_status) ---- */
+/* phasing.py:14-134: record scan + filter, pileup, het call, variant_map rows.
+ * Fills sites + vmap of `out`. */
+int fuz_het_call(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
+/* phasing.py:137-206.  Inputs: sites (ctg,pos,al) + vmap of `out` with the given counts;
+ * fills atable. */
+int fuz_association_table(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, int64_t n_vmap,
+                          fuz_outputs *out);
+/* phasing.py:216-421.  Inputs: sites + atable (n_atable rows, ordered by (s1,s2));
+ * fills phase.  */
+int fuz_phased_blocks(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, int64_t n_atable,
+                      fuz_outputs *out);
+/* phasing.py:423-480.  Inputs: sites, vmap, phase; d_ctg_nq [n_ctg] with sum total_nq;
+ * fills reads. */
+int fuz_phased_reads(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq,
+                     int64_t n_sites, int64_t n_vmap, fuz_outputs *out);
+/* phasing.py:482-553: all four stages for the batch, no host synchronisation between
+ * them (counts stay on the device).  This is the timed hot path of bench.py. */
+int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
+
+/* ---- host-buffer entry (the reference-facing call; includes H2D / D2H) ---------- */
+typedef struct {
+    int32_t n_ctg, n_rec;
+    int64_t rec_bytes;
+    const uint8_t *h_rec_buf;     /* [rec_bytes] verbatim BAM records                    */
+    const int64_t *h_rec_off;     /* [n_rec + 1]                                         */
+    const int32_t *h_rec_qid;     /* [n_rec]                                             */
+    const int32_t *h_ctg_rec_off; /* [n_ctg + 1]                                         */
+    const int32_t *h_ctg_len;     /* [n_ctg]                                             */
+    const int32_t *h_ctg_nq;      /* [n_ctg]                                             */
+} fuz_host_batch;
+
+typedef struct {
+    int64_t cap_sites, cap_vmap, cap_atable, cap_reads;
+    int32_t *site_ctg, *site_pos, *site_cnt; uint8_t *site_al, *site_top;
+    int32_t *vm_site, *vm_qid; uint8_t *vm_base;
+    int32_t *at_s1, *at_s2, *at_ct;
+    uint8_t *ph_state; int32_t *ph_lext, *ph_rext, *ph_lscore, *ph_rscore, *ph_block;
+    int32_t *pr_ctg, *pr_qid, *pr_block, *pr_phase, *pr_n0, *pr_n1;
+} fuz_host_outputs;
+
+/* H2D of the batch, fuz_phase_batch, D2H of every row array (only the filled prefix).
+ * Device staging buffers are owned by the context and reused across calls.
+ * h_status receives the final status; bytes moved are reported for bench.py. */
+int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_outputs *out,
+                         fuz_status *h_status, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* ---- host helpers (no CUDA) ------------------------------------------------------ */
+/* Walk the block_size chain of a record buffer.  rec_off needs n_rec+1 slots; returns
+ * the record count through n_rec (call with rec_off = NULL to count only). */
+int fuz_host_index_records(const uint8_t *h_rec_buf, int64_t rec_bytes, int64_t *h_rec_off,
+                           int64_t cap_rec, int64_t *n_rec);
+/* first-seen QNAME -> q_id per contig (phasing.py:47-54).  h_name_first[q] receives the
+ * index of the first record carrying q_id q of its contig, at ctg_q_off[c] + q. */
+int fuz_host_assign_qids(const uint8_t *h_rec_buf, const int64_t *h_rec_off, int64_t n_rec,
+                         const int32_t *h_ctg_rec_off, int32_t n_ctg, int32_t *h_rec_qid,
+                         int32_t *h_ctg_nq, int64_t *h_name_first);
+/* CPython-2.7 dict iteration order of int keys inserted in the given order (B.3). */
+int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUZ_H_ */

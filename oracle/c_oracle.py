@@ -140,6 +140,18 @@ def het_call(records, rec_off: np.ndarray, qid: np.ndarray) -> dict:
     return out
 
 
+def pileup_counts(records, rec_off: np.ndarray, ctg_len: int) -> np.ndarray:
+    """[ctg_len, 4] depth of A,C,G,T over accepted records (phasing.py:63-96)."""
+    recs = np.frombuffer(records, dtype=np.uint8) if not isinstance(records, np.ndarray) else records
+    recs = np.ascontiguousarray(recs)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+    counts = np.zeros((ctg_len, 4), dtype=np.uint32)
+    rc = lib().fo_pileup_counts(_p(recs, C.c_uint8), _p(rec_off, C.c_int64), C.c_int64(len(rec_off) - 1),
+                                C.c_int64(ctg_len), _p(counts, C.c_uint32))
+    _check(rc, "pileup_counts")
+    return counts
+
+
 def association_table(vm_pos, vm_allele, vm_qid) -> dict:
     vm_pos = np.ascontiguousarray(vm_pos, dtype=np.int32)
     vm_allele = np.ascontiguousarray(vm_allele, dtype=np.uint8)

@@ -77,7 +77,7 @@ typedef struct {
 /* pileup[pos][symbol] -> list of q_ids (phasing.py:88-90); 16 BAM symbols */
 typedef struct { ivec sym[16]; uint16_t mask; } cell_t;
 
-static const char SEQ_CODES[] = "=ACMGRSVTWYHKDBN";
+
 
 static void cell_clear(cell_t *c) {
     for (int s = 0; s < 16; s++) { free(c->sym[s].p); c->sym[s].p = NULL; c->sym[s].n = c->sym[s].cap = 0; }
@@ -615,4 +615,43 @@ int fo_phased_reads(const int32_t *vm_pos, const uint8_t *vm_allele, const int32
 
 void fo_free_reads(fo_reads_result *r) {
     free(r->qid); free(r->pid); free(r->phase); free(r->n0); free(r->n1); memset(r, 0, sizeof(*r));
+}
+
+/* ================================================================== full pileup (tests)
+ * Depth of A,C,G,T at every position [0, ctg_len) over the accepted records: the
+ * pileup of phasing.py:77-96 without the streaming flush.  counts[4*pos + b]. */
+int fo_pileup_counts(const uint8_t *recs, const int64_t *rec_off, int64_t n_rec, int64_t ctg_len,
+                     uint32_t *counts) {
+    memset(counts, 0, (size_t)ctg_len * 4 * sizeof(uint32_t));
+    for (int64_t r = 0; r < n_rec; r++) {
+        const uint8_t *rec = recs + rec_off[r];
+        int32_t pos = rd_i32(rec + 8);
+        int l_name = rec[12];
+        int n_cig = rd_u16(rec + 16);
+        const uint8_t *cig = rec + 36 + l_name;
+        const uint8_t *seq = cig + 4 * (int64_t)n_cig;
+        int64_t skip = 0, total = 0;
+        for (int k = 0; k < n_cig; k++) {
+            uint32_t c = rd_u32(cig + 4 * k);
+            total += c >> 4;
+            if ((c & 15) == 4) skip += c >> 4;
+        }
+        if (total == 0) return FO_E_BADRECORD;
+        if (1.0 - 1.0 * (double)skip / (double)total < 0.1) continue;
+        if (total < 2000) continue;
+        int64_t rp = pos, qp = 0;
+        for (int k = 0; k < n_cig; k++) {
+            uint32_t c = rd_u32(cig + 4 * k); int64_t adv = c >> 4; int op = c & 15;
+            if (op == 4 || op == 1) qp += adv;
+            else if (op == 2) rp += adv;
+            else if (op == 0 || op == 7 || op == 8) {
+                for (int64_t i = 0; i < adv; i++, rp++, qp++) {
+                    int sym = (seq[qp >> 1] >> ((qp & 1) ? 0 : 4)) & 15;
+                    int b = sym == 1 ? 0 : sym == 2 ? 1 : sym == 4 ? 2 : sym == 8 ? 3 : -1;
+                    if (b >= 0 && rp >= 0 && rp < ctg_len) counts[4 * rp + b]++;
+                }
+            }
+        }
+    }
+    return FO_OK;
 }

@@ -1,0 +1,130 @@
+"""GPU parity: the CUDA path (through the C ABI of libfuz.so) against the CPU oracle on the
+same seeded inputs -- bit-exact arrays and byte-exact files."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import synth_set
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_files(sset, tmp):
+    from oracle import c_oracle
+    out = {}
+    for c, (name, _l) in enumerate(sset.refs):
+        out[name] = c_oracle.run_phasing_stages(sset.contig_records(c), name, sset.ref_seqs[c], str(tmp))
+    return out
+
+
+def _assert_same_files(a, b):
+    for ctg in a:
+        for k in a[ctg]:
+            ta, tb = open(a[ctg][k]).read(), open(b[ctg][k]).read()
+            if ta != tb:
+                la, lb = ta.splitlines(), tb.splitlines()
+                for i, (x, y) in enumerate(zip(la, lb)):
+                    if x != y:
+                        raise AssertionError("%s/%s differs at line %d: oracle %r | gpu %r (%d vs %d lines)"
+                                             % (ctg, k, i, x, y, len(la), len(lb)))
+                raise AssertionError("%s/%s: %d vs %d lines" % (ctg, k, len(la), len(lb)))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+def test_pileup_counts_match_oracle(eng, cfg, impl):
+    from falcon_unzip_b200 import engine
+    from oracle import c_oracle
+    sset = synth_set(cfg)
+    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+    eng.set_option("pileup_impl", impl)
+    try:
+        res = eng.phase_device(pb, want_counts=True, stage="het")
+    finally:
+        eng.set_option("pileup_impl", 0)
+    goff = res.arrays["goff"]
+    for c, (name, L) in enumerate(sset.refs):
+        recs = sset.contig_records(c)
+        want = c_oracle.pileup_counts(recs, c_oracle.index_records(recs), L)
+        got = res.arrays["counts"][goff[c]:goff[c] + L]
+        bad = np.flatnonzero((want != got).any(axis=1))
+        assert len(bad) == 0, "contig %s: %d positions differ, first %d: want %s got %s" % (
+            name, len(bad), bad[0], want[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+def test_het_call_arrays_match_oracle(eng, cfg, impl):
+    from falcon_unzip_b200 import engine
+    from oracle import c_oracle
+    sset = synth_set(cfg)
+    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+    eng.set_option("pileup_impl", impl)
+    try:
+        res = eng.phase_device(pb, stage="het")
+    finally:
+        eng.set_option("pileup_impl", 0)
+    site_off = np.searchsorted(res.site_ctg, np.arange(pb.n_ctg + 1))
+    vm_off = np.searchsorted(res.vm_site, site_off)
+    aligned = accepted = 0
+    for c in range(pb.n_ctg):
+        recs = sset.contig_records(c)
+        off = c_oracle.index_records(recs)
+        qid, _names = c_oracle.assign_qids(c_oracle.record_names(recs, off))
+        h = c_oracle.het_call(recs, off, qid)
+        aligned += h["aligned_bases"]; accepted += h["n_accepted"]
+        s0, s1 = site_off[c], site_off[c + 1]
+        assert np.array_equal(res.site_pos[s0:s1], h["site_pos"] + 1)
+        # counts in A,C,G,T order vs the oracle's sorted order
+        letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+        for k in range(4):
+            idx = np.argmax(h["site_base"] == letters[k], axis=1)
+            assert np.array_equal(res.site_cnt[s0:s1, k], np.take_along_axis(h["site_count"], idx[:, None], 1)[:, 0])
+        v0, v1 = vm_off[c], vm_off[c + 1]
+        assert np.array_equal(res.site_pos[res.vm_site[v0:v1]], h["vm_pos"] + 1)
+        assert np.array_equal(letters[res.vm_base[v0:v1]], h["vm_allele"])
+        assert np.array_equal(res.vm_qid[v0:v1], h["vm_qid"])
+    assert res.aligned_bases == aligned and res.n_accepted == accepted
+
+
+@pytest.mark.parametrize("host_path", [True, False])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+def test_fused_batch_files_match_oracle(eng, cfg, host_path, tmp_path):
+    from falcon_unzip_b200 import phasing
+    sset = synth_set(cfg)
+    want = _oracle_files(sset, tmp_path / "oracle")
+    _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs,
+                                      str(tmp_path / "gpu"), host_path=host_path)
+    _assert_same_files(want, got)
+
+
+def test_reference_cli_per_stage_files_match_oracle(eng, tmp_path):
+    """fc_phasing-style run: BAM + FASTA on disk, the four stage functions chained through
+    files exactly like reference phasing.py:482-553."""
+    from falcon_unzip_b200 import bam, phasing, synth
+    sset = synth_set("quirks")
+    bam_fn, fa_fn = str(tmp_path / "in.bam"), str(tmp_path / "ref.fa")
+    bam.write_bam(bam_fn, sset.refs, sset.records.tobytes())
+    synth.write_fasta(fa_fn, sset)
+    want = _oracle_files(sset, tmp_path / "oracle")
+    got = {}
+    for name, _l in sset.refs:
+        phasing.main(["fc_phasing.py", "--bam", bam_fn, "--fasta", fa_fn, "--ctg_id", name,
+                      "--base_dir", str(tmp_path / "gpu"), "--samtools", "/nonexistent/samtools"])
+        base = tmp_path / "gpu" / name
+        got[name] = dict(variant_map=str(base / "het_call" / "variant_map"),
+                         variant_pos=str(base / "het_call" / "variant_pos"),
+                         q_id_map=str(base / "het_call" / "q_id_map"),
+                         atable=str(base / "g_atable" / "atable"),
+                         phased_variants=str(base / "get_phased_blocks" / "phased_variants"),
+                         phased_reads=str(base / "phased_reads"))
+    _assert_same_files(want, got)
+
+
+def test_m_style_cigar_and_single_contig(eng, tmp_path):
+    from falcon_unzip_b200 import phasing
+    sset = synth_set("tiny", cigar_style="M", n_contigs=1, seed=99)
+    want = _oracle_files(sset, tmp_path / "oracle")
+    _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs, str(tmp_path / "gpu"))
+    _assert_same_files(want, got)
