@@ -186,10 +186,13 @@ class DeviceOutputs:
         v = torch.from_numpy(np.ascontiguousarray(values).reshape(-1))
         self.t[name][:v.numel()].copy_(v.view(self.t[name].dtype) if v.dtype != self.t[name].dtype else v)
 
-    def fetch(self, st: _lib.Status) -> Dict[str, np.ndarray]:
+    def fetch(self, st: _lib.Status, keys: Sequence[str] = ("sites", "vmap", "atable", "reads")) -> Dict[str, np.ndarray]:
+        """Download the filled prefix of the row arrays of the given groups."""
         out = {}
         for name, dt, key, width in _lib.OUTPUT_ARRAYS:
-            n = int(getattr(st, _CAP_KEY_N[key]))
+            if key not in keys:
+                continue
+            n = min(int(getattr(st, _CAP_KEY_N[key])), self.caps[key])
             a = self.t[name][:n * width].cpu().numpy()
             out[name] = a.reshape(n, width) if width > 1 else a
         return out

@@ -169,7 +169,7 @@ def generate_association_table(self):
         eng.association_async(1, n_sites, n_vmap, do)
     caps = dict(sites=max(n_sites, 16), vmap=max(n_vmap, 16), atable=max(16, 24 * n_sites), reads=16)
     do, st = eng._retry(caps, 0, run)
-    a = do.fetch(st)
+    a = do.fetch(st, ("atable",))
     res = SimpleNamespace(site_pos=pos, site_al=al, at_s1=a["at_s1"], at_s2=a["at_s2"], at_ct=a["at_ct"])
     with _open_out(atable_fn) as f:
         f.write(formats.atable_text(res, 0, int(st.n_atable)))
@@ -215,7 +215,7 @@ def get_phased_blocks(self):
     eng._torch.cuda.synchronize(eng.device)
     eng.blocks_async(1, n_sites, n_at, do)
     st = eng.status()
-    a = do.fetch(st)
+    a = do.fetch(st, ("sites",))
     res = SimpleNamespace(site_pos=pos, site_al=al, **{k: a[k][:n_sites] for k in (
         "ph_state", "ph_lext", "ph_rext", "ph_lscore", "ph_rscore", "ph_block")})
     with _open_out(p_variant_fn) as f:
@@ -266,7 +266,7 @@ def get_phased_reads(self):
         eng.reads_async(1, np.asarray([nq], np.int32), n_sites, n_vmap, do)
     caps = dict(sites=max(n_sites, 16), vmap=max(n_vmap, 16), atable=16, reads=max(16, 2 * nq))
     do, st = eng._retry(caps, 0, run)
-    a = do.fetch(st)
+    a = do.fetch(st, ("reads",))
     res = SimpleNamespace(vm_qid=vm_qid, **{k: a[k] for k in ("pr_qid", "pr_block", "pr_phase", "pr_n0", "pr_n1")})
     with _open_out(phased_read_fn) as f:
         f.write(formats.phased_reads_text(res, 0, int(st.n_reads), 0, n_vmap, ctg_id, rid_map))

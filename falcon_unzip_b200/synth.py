@@ -223,7 +223,6 @@ def _gen_batch(rng: np.random.Generator, cfg: SynthConfig, refid: int, haps: np.
 def generate(cfg: SynthConfig, batch_bases: int = 4_000_000) -> SynthSet:
     """Generate every contig of ``cfg`` (records coordinate-sorted within a contig)."""
     refs, ref_seqs, het_all, chunks, ctg_of = [], [], [], [], []
-    read_serial = 0
     for ci in range(cfg.first_contig, cfg.first_contig + cfg.n_contigs):
         rng = np.random.Generator(np.random.PCG64([cfg.seed, ci]))
         L = cfg.contig_len
@@ -254,11 +253,12 @@ def generate(cfg: SynthConfig, batch_bases: int = 4_000_000) -> SynthSet:
         hv = np.flatnonzero(heavy)
         clip_l[hv] = 9 * lens[hv] + rng.integers(0, 3, len(hv)) - 1
         names = []
+        read_serial = ci * 1_000_000          # unique across contigs, independent of batch composition
         for i in range(n_reads):
             if i > 0 and cfg.frac_dup_name > 0 and rng.random() < cfg.frac_dup_name:
                 names.append(names[-1])
             else:
-                names.append(b"m%06d/%d/0_%d" % (read_serial, read_serial, int(lens[i])))
+                names.append(b"m%08d/%d/0_%d" % (read_serial, read_serial, int(lens[i])))
             read_serial += 1
         # batches bound the working set of the vectorised generator
         b0 = 0
@@ -290,3 +290,31 @@ def write_fasta(path: str, sset: SynthSet, width: int = 80) -> None:
             f.write(">%s\n" % name)
             for o in range(0, len(seq), width):
                 f.write(seq[o:o + width] + "\n")
+
+
+def _gen_one(args):
+    cfg, ci = args
+    return generate(dataclasses.replace(cfg, n_contigs=1, first_contig=ci))
+
+
+def generate_parallel(cfg: SynthConfig, workers: int = 0) -> SynthSet:
+    """generate() with one process per contig (call before CUDA is initialised: fork)."""
+    import multiprocessing as mp
+    import os
+    workers = workers or min(cfg.n_contigs, os.cpu_count() or 1)
+    if workers <= 1 or cfg.n_contigs == 1:
+        return generate(cfg)
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_gen_one, [(cfg, ci) for ci in range(cfg.first_contig, cfg.first_contig + cfg.n_contigs)])
+    refs, ref_seqs, het, recs, offs, ctgs, base = [], [], [], [], [np.zeros(1, np.int64)], [], 0
+    for c, p in enumerate(parts):
+        refs += p.refs; ref_seqs += p.ref_seqs; het += p.het_pos
+        buf = p.records.copy()
+        # refID of the record = contig index inside the merged set
+        idx = p.rec_off[:-1, None] + 4 + np.arange(4)[None, :]
+        buf[idx] = np.frombuffer(np.int32(c).tobytes(), dtype=np.uint8)[None, :]
+        recs.append(buf)
+        offs.append(p.rec_off[1:] + base)
+        base += len(buf)
+        ctgs.append(np.full(len(p.rec_off) - 1, c, dtype=np.int32))
+    return SynthSet(cfg, refs, ref_seqs, het, np.concatenate(recs), np.concatenate(offs), np.concatenate(ctgs))
