@@ -154,27 +154,31 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 }
 
 // ------------------------------------------------------------------ single-CTA scan
-// One CTA of 1024 threads walks the array in chunks of 4096 carrying the running total.
+// One CTA of 1024 threads walks the array in chunks of 16384 carrying the running total.
 // The arrays scanned on this path (records, tiles, sites, q_ids) are at most a few
-// million entries; the scan is never the dominant kernel.
+// million entries; the scan is never the dominant kernel.  The tail of the scan also
+// publishes the total into the status block (row counts + capacity checks), which saves
+// one tiny kernel launch per scan.
+#define SCAN_PER_THREAD 16
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
-                                                   int64_t n_cap, const int64_t *__restrict__ d_n,
-                                                   int64_t *__restrict__ d_total64) {
+                                                   int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
+                                                   int64_t fin_cap, fuz_status *st) {
     __shared__ int warp_tot[32];
     __shared__ long long carry_s;
     int64_t n = d_n ? *d_n : n_cap;
     if (n > n_cap) n = n_cap;
     if (n < 0) n = 0;
+    if (st && st->error) n = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 4096) {
-        int v[4];
+    for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD) {
+        int v[SCAN_PER_THREAD];
         int s = 0;
+        const int64_t i0 = base + (int64_t)tid * SCAN_PER_THREAD;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int64_t i = base + (int64_t)tid * 4 + k;
-            v[k] = i < n ? in[i] : 0;
+        for (int k = 0; k < SCAN_PER_THREAD; k++) {
+            v[k] = i0 + k < n ? in[i0 + k] : 0;
             s += v[k];
         }
         int incl = fuz_warp_incl_scan(s, lane);
@@ -186,12 +190,10 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
             warp_tot[lane] = ti - t;  // exclusive offset of each warp
         }
         __syncthreads();
-        long long carry = carry_s;
-        long long excl = carry + warp_tot[warp] + (incl - s);
+        long long excl = carry_s + warp_tot[warp] + (incl - s);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int64_t i = base + (int64_t)tid * 4 + k;
-            if (i < n) out[i] = (int32_t)excl;
+        for (int k = 0; k < SCAN_PER_THREAD; k++) {
+            if (i0 + k < n) out[i0 + k] = (int32_t)excl;
             excl += v[k];
         }
         __syncthreads();
@@ -199,14 +201,43 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
         __syncthreads();
     }
     if (tid == 0) {
-        out[n] = (int32_t)carry_s;
-        if (d_total64) *d_total64 = carry_s;
+        const long long total = carry_s;
+        out[n] = (int32_t)total;
+        if (st && !st->error) {
+            switch (fin_op) {
+            case FUZ_FIN_SITES:
+                st->need_sites = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 0); else st->n_sites = total;
+                break;
+            case FUZ_FIN_VMAP:
+                st->need_vmap = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 1); else st->n_vmap = total;
+                break;
+            case FUZ_FIN_ATABLE:
+                st->need_atable = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 2); else st->n_atable = total;
+                break;
+            case FUZ_FIN_READS:
+                st->need_reads = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 3); else st->n_reads = total;
+                break;
+            case FUZ_FIN_PAIRS:
+                st->need_pairs = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 4);
+                break;
+            case FUZ_FIN_PROJ:          // alignment spans (deletions) beyond the projection scratch
+                st->reserved[0] = total;
+                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 6);
+                break;
+            default: break;
+            }
+        }
     }
 }
 
-int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n,
-                 int64_t *d_total64) {
-    k_scan_i32<<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n_cap, d_n, d_total64);
+int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n, int fin_op,
+                 int64_t fin_cap) {
+    k_scan_i32<<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n_cap, d_n, fin_op, fin_cap, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_scan_i32");
     return FUZ_OK;
 }

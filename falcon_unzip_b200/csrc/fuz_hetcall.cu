@@ -8,17 +8,17 @@ namespace {
 
 // scratch of the het-call stage (device pointers into the context arena)
 struct HetScratch {
-    int32_t *r_gstart, *r_gend, *r_seg_off, *r_nseg, *r_segcnt;
+    int32_t *r_gstart, *r_gend, *r_nwords, *r_woff;
     int64_t *r_seq;
     uint8_t *r_flags;
-    int32_t *seg_rs, *seg_len, *seg_qs;
-    int32_t *ctg_last_rec, *ctg_maxspan, *ctg_poslast_g;
-    int32_t *tile_ctg, *tile_rlo, *tile_rhi, *tile_site_base, *tile_site_cnt, *tile_site_off;
+    uint32_t *proj;            // reference-aligned 4-bit projection of every accepted record
+    int64_t proj_cap;          // capacity of proj in words
+    int32_t *ctg_last_rec, *ctg_maxspan;
+    int32_t *tile_ctg, *tile_rlo, *tile_rhi, *tile_limit, *tile_site_base, *tile_site_cnt, *tile_site_off;
     int32_t *us_gpos;
     uint32_t *us_cnt;
     int32_t *s_gpos, *site_rows, *site_row_off;
     uint32_t *counts;
-    int64_t seg_cap;
     int32_t n_tiles;
 };
 
@@ -36,19 +36,10 @@ __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_m
     for (; i < n_ctg; i += gridDim.x * blockDim.x) { ctg_last_rec[i] = -1; ctg_maxspan[i] = 0; }
 }
 
-// upper bound of the number of match segments of each record: ceil(n_cigar / 2)
-__global__ void k_rec_segbound(const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off,
-                               int n_rec, int32_t *__restrict__ segcnt) {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-        uint32_t w = fuz_ld_u32_un(rec_buf + rec_off[r] + 16);   // n_cigar_op:u16, flag:u16
-        segcnt[r] = (int)((w & 0xFFFFu) + 1) >> 1;
-    }
-}
-
 // ---------------------------------------------------------------- record scan
-// One warp per record.  Pass 1: totals for the filter (phasing.py:63-75).  Pass 2 (accepted
-// records): ref/query prefix of every CIGAR op and the match segments = maximal runs of
-// M/=/X ops not interrupted by S/I/D (N/H/P advance nothing, phasing.py:77-96 quirk).
+// One warp per record, one pass over the CIGAR: totals for the filter (phasing.py:63-75),
+// reference span (M/=/X/D advance the reference; N/H/P advance nothing, the quirk of
+// phasing.py:77-96), number of 8-position words the record touches on the global grid.
 __global__ void __launch_bounds__(256) k_scan_records(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg,
@@ -56,11 +47,12 @@ __global__ void __launch_bounds__(256) k_scan_records(
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    long long acc_aligned = 0, acc_accepted = 0, acc_segs = 0;
+    long long acc_aligned = 0, acc_accepted = 0;
     for (int r = warp_g; r < n_rec; r += n_warps) {
         const uint8_t *rec = rec_buf + rec_off[r];
         // contig of the record = position of r in ctg_rec_off (records grouped by contig)
         int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
+        const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
         const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
         const uint32_t w12 = fuz_ld_u32_un(rec + 12);     // l_read_name, mapq, bin
         const uint32_t w16 = fuz_ld_u32_un(rec + 16);     // n_cigar_op, flag
@@ -69,26 +61,22 @@ __global__ void __launch_bounds__(256) k_scan_records(
         const int n_cig = w16 & 0xFFFF;
         const uint8_t *cig = rec + 36 + l_name;
         const int64_t seq_off = rec_off[r] + 36 + l_name + 4 * (int64_t)n_cig;
-        const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
-        bool bad = false;
+        if (lane == 0) {
+            S.r_flags[r] = 0; S.r_nwords[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_seq[r] = seq_off;
+        }
         if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 ||
             rec_off[r + 1] - rec_off[r] != (int64_t)block_size + 4 ||
-            36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4)
-            bad = true;
-        if (lane == 0) { S.r_flags[r] = 0; S.r_nseg[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_seq[r] = seq_off; }
-        if (bad) {
+            36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4) {
             if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
             continue;
         }
-        const int64_t goff = ctg_goff[c];
-        const int64_t gstart64 = goff + pos;
+        const int64_t gstart64 = ctg_goff[c] + pos;
         // coordinate order inside the contig
         if (lane == 0 && r > ctg_rec_off[c]) {
             int32_t prev_pos = (int32_t)fuz_ld_u32_un(rec_buf + rec_off[r - 1] + 8);
             if (prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
         }
-        // ---- pass 1: total / soft-clip lengths (phasing.py:63-70)
-        long long total = 0, skip = 0, aligned = 0;
+        long long total = 0, skip = 0, aligned = 0, span = 0;
         bool badop = false;
         for (int k = lane; k < n_cig; k += 32) {
             uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
@@ -96,122 +84,45 @@ __global__ void __launch_bounds__(256) k_scan_records(
             if (op > 8) badop = true;
             total += len;
             if (op == 4) skip += len;
-            if (op_is_match(op)) aligned += len;
+            if (op_is_match(op)) { aligned += len; span += len; }
+            if (op == 2) span += len;
         }
         total = fuz_warp_sum64(total);
         skip = fuz_warp_sum64(skip);
         aligned = fuz_warp_sum64(aligned);
+        span = fuz_warp_sum64(span);
         badop = __any_sync(0xffffffffu, badop);
-        if (badop || total == 0) {           // unknown op / ZeroDivisionError at phasing.py:72
+        if (badop || total == 0 || gstart64 + span > 0x7fffffffLL) {   // unknown op / ZeroDivisionError :72
             if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
             continue;
         }
         // phasing.py:72-75 in IEEE double, same operation order as the reference
-        bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
-        int32_t gstart = (int32_t)gstart64;
-        if (!accept) {
-            if (lane == 0) {
-                S.r_gstart[r] = gstart; S.r_gend[r] = gstart; S.r_flags[r] = 0; S.r_nseg[r] = 0;
-                S.r_seq[r] = seq_off;
-            }
-            continue;
-        }
-        // ---- pass 2: prefix positions + match segments
-        const int seg_base = S.r_seg_off[r];
-        int carry_rp = gstart, carry_qp = 0;
-        bool open = false;
-        int open_rs = 0, open_qs = 0, nseg = 0;
-        bool overrun = false;
-        const uint32_t lt = (1u << lane) - 1u;
-        for (int k0 = 0; k0 < n_cig; k0 += 32) {
-            int k = k0 + lane;
-            bool valid = k < n_cig;
-            uint32_t cw = valid ? fuz_ld_u32_un(cig + 4 * k) : 0u;
-            int len = (int)(cw >> 4);
-            uint32_t op = cw & 15;
-            bool is_m = valid && op_is_match(op) && len > 0;
-            bool brk = valid && (op == 1 || op == 2 || op == 4);          // I D S
-            int radv = (valid && (op_is_match(op) || op == 2)) ? len : 0;  // M = X D
-            int qadv = (valid && (op_is_match(op) || op == 1 || op == 4)) ? len : 0;  // M = X I S
-            int rinc = fuz_warp_incl_scan(radv, lane);
-            int qinc = fuz_warp_incl_scan(qadv, lane);
-            int rp0 = carry_rp + rinc - radv;
-            int qp0 = carry_qp + qinc - qadv;
-            if (is_m && (long long)qp0 + len > (long long)l_seq) overrun = true;  // IndexError :84
-            uint32_t mmask = __ballot_sync(0xffffffffu, is_m);
-            uint32_t bmask = __ballot_sync(0xffffffffu, brk);
-            int last_m = (mmask & lt) ? 31 - __clz(mmask & lt) : -1;
-            int last_b = (bmask & lt) ? 31 - __clz(bmask & lt) : -1;
-            bool open_before = last_m > last_b ? true : (last_b > last_m ? false : open);
-            bool starts = is_m && !open_before;
-            bool ends_here = brk && open_before;
-            uint32_t smask = __ballot_sync(0xffffffffu, starts);
-            uint32_t emask = __ballot_sync(0xffffffffu, ends_here);
-            uint32_t sm = smask & lt;
-            int src = sm ? 31 - __clz(sm) : 0;
-            int rs_s = __shfl_sync(0xffffffffu, rp0, src);
-            int qs_s = __shfl_sync(0xffffffffu, qp0, src);
-            if (ends_here) {
-                int rs = sm ? rs_s : open_rs, qs = sm ? qs_s : open_qs;
-                int idx = seg_base + nseg + __popc(emask & lt);
-                S.seg_rs[idx] = rs; S.seg_len[idx] = rp0 - rs; S.seg_qs[idx] = qs;
-            }
-            nseg += __popc(emask);
-            int last_m_all = mmask ? 31 - __clz(mmask) : -1;
-            int last_b_all = bmask ? 31 - __clz(bmask) : -1;
-            // the group open at the end of the chunk starts at the first start after the last break
-            uint32_t sm2 = last_b_all >= 0 ? (last_b_all == 31 ? 0u : (smask & ~((2u << last_b_all) - 1u))) : smask;
-            int src2 = sm2 ? __ffs(sm2) - 1 : 0;
-            int rs2 = __shfl_sync(0xffffffffu, rp0, src2);
-            int qs2 = __shfl_sync(0xffffffffu, qp0, src2);
-            if (last_m_all > last_b_all) {
-                if (sm2) { open_rs = rs2; open_qs = qs2; }
-                open = true;
-            } else if (last_b_all > last_m_all) {
-                open = false;
-            }
-            carry_rp += __shfl_sync(0xffffffffu, rinc, 31);
-            carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
-        }
-        if (open) {
-            if (lane == 0) {
-                int idx = seg_base + nseg;
-                S.seg_rs[idx] = open_rs; S.seg_len[idx] = carry_rp - open_rs; S.seg_qs[idx] = open_qs;
-            }
-            nseg++;
-        }
-        overrun = __any_sync(0xffffffffu, overrun);
-        if (overrun) {
-            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
-            continue;
-        }
+        const bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
+        const int32_t gstart = (int32_t)gstart64;
         if (lane == 0) {
-            S.r_gstart[r] = gstart; S.r_gend[r] = carry_rp; S.r_flags[r] = 1; S.r_nseg[r] = nseg;
-            S.r_seq[r] = seq_off;
-            atomicMax(&S.ctg_last_rec[c], r);
-            atomicMax(&S.ctg_maxspan[c], carry_rp - gstart);
-            acc_aligned += aligned; acc_accepted += 1; acc_segs += nseg;
+            S.r_gstart[r] = gstart;
+            S.r_gend[r] = accept ? gstart + (int32_t)span : gstart;
+            S.r_flags[r] = accept ? 1 : 0;
+            S.r_nwords[r] = (accept && span > 0) ? (int32_t)(((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 1) : 0;
+            if (accept) {
+                atomicMax(&S.ctg_last_rec[c], r);
+                atomicMax(&S.ctg_maxspan[c], (int32_t)span);
+                acc_aligned += aligned; acc_accepted += 1;
+            }
         }
     }
     if (lane == 0 && acc_accepted) {
         atomicAdd((unsigned long long *)&st->aligned_bases, (unsigned long long)acc_aligned);
         atomicAdd((unsigned long long *)&st->n_accepted, (unsigned long long)acc_accepted);
-        atomicAdd((unsigned long long *)&st->n_segments, (unsigned long long)acc_segs);
     }
 }
 
-// POS_last of each contig in global coordinates: start of the last accepted record in
+// candidate record range, contig and evaluation limit of every pileup tile.  The limit is
+// POS_last of the contig in global coordinates: the start of the last accepted record in
 // file order; positions >= POS_last are never evaluated (no final flush, phasing.py:98-129).
-__global__ void k_ctg_finish(int n_ctg, const int64_t *__restrict__ ctg_goff, HetScratch S) {
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_ctg; c += gridDim.x * blockDim.x) {
-        int lr = S.ctg_last_rec[c];
-        S.ctg_poslast_g[c] = lr >= 0 ? S.r_gstart[lr] : (int32_t)ctg_goff[c];
-    }
-}
-
-// candidate record range of every pileup tile
 __global__ void k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict__ ctg_goff,
-                              const int32_t *__restrict__ ctg_rec_off, HetScratch S) {
+                              const int32_t *__restrict__ ctg_rec_off, HetScratch S, const fuz_status *st) {
+    if (st->error) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
         int64_t t0 = (int64_t)t * FUZ_TILE;
         int lo = 0, hi = n_ctg + 1;                      // last c with ctg_goff[c] <= t0
@@ -221,7 +132,9 @@ __global__ void k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict_
         int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
         int t1 = (int)(t0 + FUZ_TILE);
         int span = S.ctg_maxspan[c];
+        int lr = S.ctg_last_rec[c];
         S.tile_ctg[t] = c;
+        S.tile_limit[t] = lr >= 0 ? S.r_gstart[lr] : (int32_t)ctg_goff[c];
         S.tile_rlo[t] = fuz_lower_bound(S.r_gstart, r0, r1, (int)t0 - span + 1);
         S.tile_rhi[t] = fuz_lower_bound(S.r_gstart, r0, r1, t1);
     }
@@ -289,8 +202,8 @@ __device__ __forceinline__ void emit_tile_sites(const uint32_t (&cnt)[8][4], int
     }
 }
 
-// ---------------------------------------------------------------- tiled pileup (default)
-// 8 nibbles (query bases qn0..qn0+7, BAM 4-bit codes) -> one word, base i at bits 4i.
+// ---------------------------------------------------------------- projection (read major)
+// 8 nibbles (query bases q0..q0+7, BAM 4-bit codes) -> one word, base i at bits 4i.
 __device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {
     const uint8_t *addr = seq + (q0 >> 1);
     uintptr_t a = reinterpret_cast<uintptr_t>(addr);
@@ -311,73 +224,178 @@ __device__ __forceinline__ uint32_t nibble_mask(int lo, int hi) {
     return m & ~((1u << (4 * lo)) - 1u);
 }
 
-// One warp writes the part of record `rec` that falls into tile [t0, t0 + FUZ_TILE) into
-// its staging slot as 4-bit codes in reference coordinates (0 = no base).
-__device__ __forceinline__ void project_record(int rec, int t0, uint32_t *slot, int lane,
-                                               const uint8_t *__restrict__ rec_buf, const HetScratch &S) {
-    const int t1 = t0 + FUZ_TILE;
-    const int sbase = S.r_seg_off[rec];
-    const int nseg = S.r_nseg[rec];
-    const uint8_t *seq = rec_buf + S.r_seq[rec];
-    // 32-ary search: first segment whose end is > t0
-    int first = nseg, lo = 0, hi = nseg;
-    while (lo < hi) {
-        int n = hi - lo, step = (n + 31) >> 5;
-        int sb = lo + lane * step;
-        bool valid = sb < hi;
-        int sl = min(sb + step, hi) - 1;
-        int e = valid ? S.seg_rs[sbase + sl] + S.seg_len[sbase + sl] : 0x7fffffff;
-        uint32_t m = __ballot_sync(0xffffffffu, valid && e > t0);
-        if (!m) break;
-        int b = __ffs(m) - 1;
-        int cand = min(lo + (b + 1) * step, hi) - 1;
-        first = cand;
-        lo = lo + b * step;
-        hi = cand;
+#define FUZ_STRIP 512          // words of the per-warp sliding output window (2 KB)
+
+// flush the window [strip_base, strip_base + FUZ_STRIP) to the record's projection and clear it
+__device__ __forceinline__ void strip_flush(uint32_t *strip, uint32_t *__restrict__ out, int strip_base, int n_words, int lane) {
+    __syncwarp();
+#pragma unroll 4
+    for (int j = lane; j < FUZ_STRIP; j += 32) {
+        int w = strip_base + j;
+        if (w < n_words) out[w] = strip[j];
+        strip[j] = 0;
     }
-    for (int c0 = first; c0 < nseg; c0 += 32) {
-        int si = c0 + lane;
-        bool valid = si < nseg;
-        int rs = valid ? S.seg_rs[sbase + si] : 0x7fffffff;
-        int ln = valid ? S.seg_len[sbase + si] : 0;
-        int qs = valid ? S.seg_qs[sbase + si] : 0;
-        uint32_t act = __ballot_sync(0xffffffffu, valid && rs < t1);
-        int n_act = __popc(act);                        // segments are sorted: a prefix of lanes
-        for (int j = 0; j < n_act; j++) {
-            int rs_j = __shfl_sync(0xffffffffu, rs, j);
-            int ln_j = __shfl_sync(0xffffffffu, ln, j);
-            int qs_j = __shfl_sync(0xffffffffu, qs, j);
-            int a = max(rs_j, t0), b = min(rs_j + ln_j, t1);
-            if (a < b) {
-                int wa = (a - t0) >> 3, wb = (b - 1 - t0) >> 3;
-                for (int W = wa + lane; W <= wb; W += 32) {
-                    int pw = t0 + 8 * W;
-                    uint32_t v = fetch8(seq, qs_j + (pw - rs_j));
-                    v &= nibble_mask(max(a - pw, 0), min(b - pw, 8));
-                    slot[W] |= v;
-                }
-            }
-            __syncwarp();
+    __syncwarp();
+}
+
+// Place the segments held by the lanes (seg_len > 0 marks a lane with a segment: reference
+// start seg_rs, query start seg_qs) into the projection: all (segment, word) pairs of the
+// chunk are flattened over the 32 lanes; the segment of an item is found by a shuffle
+// binary search over the inclusive word-count prefix.
+__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, const uint8_t *seq,
+                                               uint32_t *strip, uint32_t *__restrict__ out, int &strip_base,
+                                               int n_words, int lane) {
+    const int wf = (seg_rs >> 3) - W0;
+    const int nw = seg_len > 0 ? ((seg_rs + seg_len - 1) >> 3) - (seg_rs >> 3) + 1 : 0;
+    const int pinc = fuz_warp_incl_scan(nw, lane);
+    const int pexc = pinc - nw;
+    const int wtot = __shfl_sync(0xffffffffu, pinc, 31);
+    for (int b0 = 0; b0 < wtot; b0 += 32) {
+        const int i = b0 + lane;
+        const bool act = i < wtot;
+        int idx = 0;                                    // first lane with pinc > i
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            int t = __shfl_sync(0xffffffffu, pinc, idx + step - 1);
+            if (t <= i) idx += step;
         }
-        if (n_act < 32) break;
+        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, idx);
+        const int o_len = __shfl_sync(0xffffffffu, seg_len, idx);
+        const int o_qs = __shfl_sync(0xffffffffu, seg_qs, idx);
+        const int o_pe = __shfl_sync(0xffffffffu, pexc, idx);
+        const int o_wf = __shfl_sync(0xffffffffu, wf, idx);
+        const int W = o_wf + (i - o_pe);               // word of the record's projection
+        const int pw = (W0 + W) << 3;                   // first global position of the word
+        const int a = max(o_rs, pw), b = min(o_rs + o_len, pw + 8);
+        uint32_t v = 0;
+        if (act) v = fetch8(seq, o_qs + (pw - o_rs)) & nibble_mask(a - pw, b - pw);
+        const bool full = b - a == 8;
+        bool done = !act;
+        for (;;) {
+            if (!done && W < strip_base + FUZ_STRIP) {
+                // a fully covered word belongs to one segment only; words shared by two
+                // segments (around an insertion / short deletion) are OR-merged
+                if (full) strip[W - strip_base] = v; else atomicOr(&strip[W - strip_base], v);
+                done = true;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            strip_flush(strip, out, strip_base, n_words, lane);
+            strip_base += FUZ_STRIP;
+            // skip windows that no remaining item touches (long deletions): all zero
+            int min_w = __reduce_min_sync(0xffffffffu, done ? 0x7fffffff : W);
+            while (min_w >= strip_base + FUZ_STRIP) {
+                for (int j = lane; j < FUZ_STRIP; j += 32)
+                    if (strip_base + j < n_words) out[strip_base + j] = 0;
+                strip_base += FUZ_STRIP;
+            }
+        }
     }
 }
 
-__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_tile(
-    const uint8_t *__restrict__ rec_buf, HetScratch S, int64_t cap_sites, uint32_t *__restrict__ counts_out,
-    fuz_status *st) {
-    if (st->error) return;   // an earlier kernel rejected the batch: scratch may be undefined
-    __shared__ uint32_t stage[FUZ_NSLOT][FUZ_TILE_THREADS];
-    __shared__ int list[FUZ_TILE_THREADS];
+// One warp per accepted record walks the CIGAR 32 ops at a time (prefix positions by warp
+// scans), merges runs of M/=/X into match segments (S/I/D break a run; N/H/P do nothing)
+// and writes the read in REFERENCE coordinates, aligned to the global 8-position grid:
+// proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as BAM 4-bit codes,
+// 0 where the read has no base (outside the alignment, deletions).
+__global__ void __launch_bounds__(256) k_project(
+    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec, HetScratch S, fuz_status *st) {
+    if (st->error) return;
+    __shared__ uint32_t strips[8][FUZ_STRIP];
+    const int lane = threadIdx.x & 31;
+    uint32_t *strip = strips[threadIdx.x >> 5];
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = lane; j < FUZ_STRIP; j += 32) strip[j] = 0;
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int r = warp_g; r < n_rec; r += n_warps) {
+        const int n_words = S.r_nwords[r];
+        if (!S.r_flags[r] || n_words == 0) continue;
+        const uint8_t *rec = rec_buf + rec_off[r];
+        const int l_name = fuz_ld_u32_un(rec + 12) & 0xFF;
+        const int n_cig = fuz_ld_u32_un(rec + 16) & 0xFFFF;
+        const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
+        const uint8_t *cig = rec + 36 + l_name;
+        const uint8_t *seq = rec_buf + S.r_seq[r];
+        const int gstart = S.r_gstart[r];
+        const int W0 = gstart >> 3;
+        uint32_t *out = S.proj + S.r_woff[r];
+        int strip_base = 0;
+        int carry_rp = gstart, carry_qp = 0;
+        bool open = false, overrun = false;
+        int open_rs = 0, open_qs = 0;
+        for (int k0 = 0; k0 < n_cig; k0 += 32) {
+            const int k = k0 + lane;
+            const bool valid = k < n_cig;
+            const uint32_t cw = valid ? fuz_ld_u32_un(cig + 4 * k) : 0u;
+            const int len = (int)(cw >> 4);
+            const uint32_t op = cw & 15;
+            const bool is_m = valid && op_is_match(op) && len > 0;
+            const bool brk = valid && (op == 1 || op == 2 || op == 4);               // I D S
+            const int radv = (valid && (op_is_match(op) || op == 2)) ? len : 0;        // M = X D
+            const int qadv = (valid && (op_is_match(op) || op == 1 || op == 4)) ? len : 0;  // M = X I S
+            const int rinc = fuz_warp_incl_scan(radv, lane);
+            const int qinc = fuz_warp_incl_scan(qadv, lane);
+            const int rp0 = carry_rp + rinc - radv;
+            const int qp0 = carry_qp + qinc - qadv;
+            if (is_m && (long long)qp0 + len > (long long)l_seq) overrun = true;       // IndexError :84
+            const uint32_t mmask = __ballot_sync(0xffffffffu, is_m);
+            const uint32_t bmask = __ballot_sync(0xffffffffu, brk);
+            const int last_m = (mmask & lt) ? 31 - __clz(mmask & lt) : -1;
+            const int last_b = (bmask & lt) ? 31 - __clz(bmask & lt) : -1;
+            const bool open_before = last_m > last_b ? true : (last_b > last_m ? false : open);
+            const bool starts = is_m && !open_before;
+            const bool ends_here = brk && open_before;      // a breaker closes the run before it
+            const uint32_t smask = __ballot_sync(0xffffffffu, starts);
+            const uint32_t sm = smask & lt;
+            const int src = sm ? 31 - __clz(sm) : 0;
+            const int rs_s = __shfl_sync(0xffffffffu, rp0, src);
+            const int qs_s = __shfl_sync(0xffffffffu, qp0, src);
+            const int seg_rs = sm ? rs_s : open_rs, seg_qs = sm ? qs_s : open_qs;
+            place_segments(seg_rs, ends_here ? rp0 - seg_rs : 0, seg_qs, W0, seq, strip, out, strip_base, n_words, lane);
+            const int last_m_all = mmask ? 31 - __clz(mmask) : -1;
+            const int last_b_all = bmask ? 31 - __clz(bmask) : -1;
+            // the run open at the end of the chunk starts at the first start after the last breaker
+            const uint32_t sm2 = last_b_all >= 0 ? (last_b_all == 31 ? 0u : (smask & ~((2u << last_b_all) - 1u))) : smask;
+            const int src2 = sm2 ? __ffs(sm2) - 1 : 0;
+            const int rs2 = __shfl_sync(0xffffffffu, rp0, src2);
+            const int qs2 = __shfl_sync(0xffffffffu, qp0, src2);
+            if (last_m_all > last_b_all) {
+                if (sm2) { open_rs = rs2; open_qs = qs2; }
+                open = true;
+            } else if (last_b_all > last_m_all) {
+                open = false;
+            }
+            carry_rp += __shfl_sync(0xffffffffu, rinc, 31);
+            carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
+        }
+        // the run still open at the end of the CIGAR
+        place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, seq, strip, out, strip_base,
+                       n_words, lane);
+        strip_flush(strip, out, strip_base, n_words, lane);
+        if (__any_sync(0xffffffffu, overrun)) {
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tiled pileup (default)
+// One CTA per 2048-position tile, one thread per 8-position word.  Every read overlapping
+// the tile contributes one ALIGNED word load per thread (no shifting: the projection is on
+// the global grid); bases are counted bit-sliced: 4-bit lanes for up to 15 reads, widened
+// into 16-bit counters held in registers.  No atomics, no shared-memory histogram.
+__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S, int64_t cap_sites,
+                                                                    uint32_t *__restrict__ counts_out, fuz_status *st) {
+    if (st->error) return;
+    __shared__ int l_off[FUZ_TILE_THREADS], l_w0[FUZ_TILE_THREADS], l_nw[FUZ_TILE_THREADS];
     __shared__ int s_warp_tot[FUZ_NW];
-    __shared__ int s_n, s_base;
+    __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int t0 = tile * FUZ_TILE, t1 = t0 + FUZ_TILE;
-    const int c = S.tile_ctg[tile];
+    const int Wt = (t0 >> 3) + tid;                       // my word on the global grid
     const int rlo = S.tile_rlo[tile], rhi = S.tile_rhi[tile];
-#pragma unroll
-    for (int s = 0; s < FUZ_NSLOT; s++) stage[s][tid] = 0;
+    const uint32_t *__restrict__ proj = S.proj;
     // c16[b][j]: 16-bit counters of base b for positions 2j (low half) and 2j+1 (high half)
     uint32_t c16[4][4];
 #pragma unroll
@@ -385,46 +403,55 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_tile(
 #pragma unroll
         for (int j = 0; j < 4; j++) c16[b][j] = 0;
     int n_reads_seen = 0;
-    __syncthreads();
     for (int cb = rlo; cb < rhi; cb += FUZ_TILE_THREADS) {
         // compact the records overlapping the tile (any order: only counts matter here)
-        int r = cb + tid;
-        bool ok = r < rhi && S.r_flags[r] && S.r_gend[r] > t0 && S.r_gstart[r] < t1;
-        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        const int r = cb + tid;
+        const bool ok = r < rhi && S.r_flags[r] && S.r_gend[r] > t0 && S.r_gstart[r] < t1;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) s_warp_tot[warp] = __popc(m);
         __syncthreads();
         int off = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < FUZ_NW; w++) { int v = s_warp_tot[w]; if (w < warp) off += v; tot += v; }
-        if (ok) list[off + __popc(m & ((1u << lane) - 1u))] = r;
+        if (ok) {
+            int slot = off + __popc(m & ((1u << lane) - 1u));
+            l_off[slot] = S.r_woff[r]; l_w0[slot] = S.r_gstart[r] >> 3; l_nw[slot] = S.r_nwords[r];
+        }
         __syncthreads();
         n_reads_seen += tot;
         for (int g = 0; g < tot; g += FUZ_NSLOT) {
-            int ns = min(FUZ_NSLOT, tot - g);
-            for (int s = warp; s < ns; s += FUZ_NW) project_record(list[g + s], t0, stage[s], lane, rec_buf, S);
-            __syncthreads();
+            const int ns = min(FUZ_NSLOT, tot - g);
+            uint32_t w[FUZ_NSLOT];
+#pragma unroll
+            for (int s = 0; s < FUZ_NSLOT; s++) {
+                w[s] = 0;
+                if (s < ns) {
+                    const int j = Wt - l_w0[g + s];
+                    if ((unsigned)j < (unsigned)l_nw[g + s]) w[s] = __ldg(proj + l_off[g + s] + j);
+                }
+            }
             // count: 4-bit lanes, at most FUZ_NSLOT (<= 15) increments per lane per round
             uint32_t c4[4] = {0, 0, 0, 0};
             const uint32_t M = 0x11111111u;
-            for (int s = 0; s < ns; s++) {
-                uint32_t w = stage[s][tid];
-                stage[s][tid] = 0;
-                uint32_t p0 = w & M, p1 = (w >> 1) & M, p2 = (w >> 2) & M, p3 = (w >> 3) & M;
-                uint32_t sum = p0 + p1 + p2 + p3;
-                uint32_t multi = ((sum >> 1) | (sum >> 2)) & M;   // codes with 2+ bits (M R S V W Y H K D B N)
+#pragma unroll
+            for (int s = 0; s < FUZ_NSLOT; s++) {
+                const uint32_t x = w[s];
+                uint32_t p0 = x & M, p1 = (x >> 1) & M, p2 = (x >> 2) & M, p3 = (x >> 3) & M;
+                const uint32_t sum = p0 + p1 + p2 + p3;
+                const uint32_t multi = ((sum >> 1) | (sum >> 2)) & M;   // codes with 2+ bits (M R S V W Y H K D B N)
                 if (multi) { p0 &= ~multi; p1 &= ~multi; p2 &= ~multi; p3 &= ~multi; }
-                c4[0] += p0; c4[1] += p1; c4[2] += p2; c4[3] += p3;   // A=1 C=2 G=4 T=8
+                c4[0] += p0; c4[1] += p1; c4[2] += p2; c4[3] += p3;     // A=1 C=2 G=4 T=8
             }
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                uint32_t x = c4[b];
+                const uint32_t x = c4[b];
                 c16[b][0] += (x & 0xFu) | ((x & 0xF0u) << 12);
                 c16[b][1] += ((x >> 8) & 0xFu) | ((x & 0xF000u) << 4);
                 c16[b][2] += ((x >> 16) & 0xFu) | ((x >> 4) & 0xF0000u);
                 c16[b][3] += ((x >> 24) & 0xFu) | ((x >> 12) & 0xF0000u);
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
     if (n_reads_seen > 65535 && tid == 0) fuz_raise(st, FUZ_E_DEPTH, tile);
     uint32_t cnt[8][4];
@@ -437,7 +464,7 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_tile(
 #pragma unroll
         for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
     }
-    emit_tile_sites(cnt, tile, t0, S.ctg_poslast_g[c], S, cap_sites, st, s_warp_tot, &s_base);
+    emit_tile_sites(cnt, tile, t0, S.tile_limit[tile], S, cap_sites, st, s_warp_tot, &s_base);
 }
 
 // ---------------------------------------------------------------- cross-check pileup (impl 1)
@@ -498,19 +525,10 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
         uint4 v = in[i];
         cnt[i][0] = v.x; cnt[i][1] = v.y; cnt[i][2] = v.z; cnt[i][3] = v.w;
     }
-    emit_tile_sites(cnt, tile, t0, S.ctg_poslast_g[S.tile_ctg[tile]], S, cap_sites, st, s_warp_tot, &s_base);
+    emit_tile_sites(cnt, tile, t0, S.tile_limit[tile], S, cap_sites, st, s_warp_tot, &s_base);
 }
 
 // ---------------------------------------------------------------- ordered sites + rows
-__global__ void k_sites_count(int n_tiles, HetScratch S, int64_t cap_sites, fuz_status *st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
-        int64_t total = S.tile_site_off[n_tiles];
-        st->need_sites = total;
-        if (total > cap_sites) { fuz_raise(st, FUZ_E_CAPACITY, 0); total = 0; }
-        st->n_sites = total;
-    }
-}
-
 __global__ void k_order_sites(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff, fuz_outputs O,
                               fuz_status *st) {
     if (st->error) return;
@@ -541,21 +559,12 @@ __global__ void k_order_sites(int n_tiles, HetScratch S, const int64_t *__restri
     }
 }
 
-__global__ void k_rows_count(HetScratch S, int64_t cap_vmap, fuz_status *st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
-        int64_t total = S.site_row_off[st->n_sites];
-        st->need_vmap = total;
-        if (total > cap_vmap) { fuz_raise(st, FUZ_E_CAPACITY, 1); total = 0; }
-        st->n_vmap = total;
-    }
-}
-
 // One warp per site: the records covering the site, in record (= file) order, 32 at a
 // time; ballot/popc turn "my read carries the major / minor allele" into ordered row
 // slots (phasing.py:125-128: all major-allele reads, then all minor-allele reads).
 __global__ void __launch_bounds__(256) k_signature(
-    const uint8_t *__restrict__ rec_buf, const int32_t *__restrict__ rec_qid,
-    const int32_t *__restrict__ ctg_rec_off, HetScratch S, fuz_outputs O, fuz_status *st) {
+    const int32_t *__restrict__ rec_qid, const int32_t *__restrict__ ctg_rec_off, HetScratch S, fuz_outputs O,
+    fuz_status *st) {
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -577,18 +586,8 @@ __global__ void __launch_bounds__(256) k_signature(
             int r = rb + lane;
             uint32_t nib = 0;
             if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp) {
-                const int sb = S.r_seg_off[r];
-                int lo = 0, hi = S.r_nseg[r];                 // last segment with rs <= gp
-                while (lo < hi) { int m = (lo + hi) >> 1; if (S.seg_rs[sb + m] <= gp) lo = m + 1; else hi = m; }
-                if (lo > 0) {
-                    int si = sb + lo - 1;
-                    int rs = S.seg_rs[si];
-                    if (gp < rs + S.seg_len[si]) {
-                        int q = S.seg_qs[si] + (gp - rs);
-                        uint32_t byte = rec_buf[S.r_seq[r] + (q >> 1)];
-                        nib = (q & 1) ? (byte & 15u) : (byte >> 4);
-                    }
-                }
+                uint32_t w = S.proj[S.r_woff[r] + ((gp >> 3) - (S.r_gstart[r] >> 3))];
+                nib = (w >> (4 * (gp & 7))) & 15u;
             }
             uint32_t m0 = __ballot_sync(0xffffffffu, nib == code0);
             uint32_t m1 = __ballot_sync(0xffffffffu, nib == code1);
@@ -619,17 +618,21 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     cudaStream_t st = ctx->stream;
     const int n_rec = in->n_rec, n_ctg = in->n_ctg;
     const int n_tiles = (int)(in->total_glen / FUZ_TILE);
-    const int64_t seg_cap = in->rec_bytes / 8 + n_rec + 1;   // sum ceil(n_cigar/2) <= rec_bytes/8 + n_rec
     const int64_t cap_sites = out->cap_sites;
+    // words of the projection: one per 8 aligned reference positions.  SEQ holds 2 bases per
+    // byte, so rec_bytes / 4 words cover every M/=/X base; deletions add to the span and are
+    // checked on the device (FUZ_E_CAPACITY, index 6).
+    const int64_t proj_cap = in->rec_bytes / 4 + 2 * (int64_t)n_rec + 64;
+    if (proj_cap > 0x7fffffffLL) return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (projection exceeds 2^31 words)");
     HetScratch S;
     FuzLayout L;
     size_t o_gstart = L.add(4 * (size_t)(n_rec + 1)), o_gend = L.add(4 * (size_t)(n_rec + 1));
-    size_t o_segoff = L.add(4 * (size_t)(n_rec + 2)), o_nseg = L.add(4 * (size_t)(n_rec + 1));
-    size_t o_segcnt = L.add(4 * (size_t)(n_rec + 2)), o_rseq = L.add(8 * (size_t)(n_rec + 1));
-    size_t o_flags = L.add((size_t)n_rec + 1);
-    size_t o_srs = L.add(4 * (size_t)seg_cap), o_slen = L.add(4 * (size_t)seg_cap), o_sqs = L.add(4 * (size_t)seg_cap);
-    size_t o_clast = L.add(4 * (size_t)n_ctg), o_cspan = L.add(4 * (size_t)n_ctg), o_cpl = L.add(4 * (size_t)n_ctg);
+    size_t o_nw = L.add(4 * (size_t)(n_rec + 2)), o_woff = L.add(4 * (size_t)(n_rec + 2));
+    size_t o_rseq = L.add(8 * (size_t)(n_rec + 1)), o_flags = L.add((size_t)n_rec + 1);
+    size_t o_proj = L.add(4 * (size_t)proj_cap);
+    size_t o_clast = L.add(4 * (size_t)n_ctg), o_cspan = L.add(4 * (size_t)n_ctg);
     size_t o_tctg = L.add(4 * (size_t)n_tiles), o_tlo = L.add(4 * (size_t)n_tiles), o_thi = L.add(4 * (size_t)n_tiles);
+    size_t o_tlim = L.add(4 * (size_t)n_tiles);
     size_t o_tbase = L.add(4 * (size_t)n_tiles), o_tcnt = L.add(4 * (size_t)(n_tiles + 1)),
            o_toff = L.add(4 * (size_t)(n_tiles + 2));
     size_t o_usg = L.add(4 * (size_t)cap_sites), o_usc = L.add(16 * (size_t)cap_sites);
@@ -641,36 +644,29 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
     S.r_gstart = fuz_at<int32_t>(ctx, o_gstart); S.r_gend = fuz_at<int32_t>(ctx, o_gend);
-    S.r_seg_off = fuz_at<int32_t>(ctx, o_segoff); S.r_nseg = fuz_at<int32_t>(ctx, o_nseg);
-    S.r_segcnt = fuz_at<int32_t>(ctx, o_segcnt); S.r_seq = fuz_at<int64_t>(ctx, o_rseq);
-    S.r_flags = fuz_at<uint8_t>(ctx, o_flags);
-    S.seg_rs = fuz_at<int32_t>(ctx, o_srs); S.seg_len = fuz_at<int32_t>(ctx, o_slen); S.seg_qs = fuz_at<int32_t>(ctx, o_sqs);
+    S.r_nwords = fuz_at<int32_t>(ctx, o_nw); S.r_woff = fuz_at<int32_t>(ctx, o_woff);
+    S.r_seq = fuz_at<int64_t>(ctx, o_rseq); S.r_flags = fuz_at<uint8_t>(ctx, o_flags);
+    S.proj = fuz_at<uint32_t>(ctx, o_proj); S.proj_cap = proj_cap;
     S.ctg_last_rec = fuz_at<int32_t>(ctx, o_clast); S.ctg_maxspan = fuz_at<int32_t>(ctx, o_cspan);
-    S.ctg_poslast_g = fuz_at<int32_t>(ctx, o_cpl);
     S.tile_ctg = fuz_at<int32_t>(ctx, o_tctg); S.tile_rlo = fuz_at<int32_t>(ctx, o_tlo); S.tile_rhi = fuz_at<int32_t>(ctx, o_thi);
+    S.tile_limit = fuz_at<int32_t>(ctx, o_tlim);
     S.tile_site_base = fuz_at<int32_t>(ctx, o_tbase); S.tile_site_cnt = fuz_at<int32_t>(ctx, o_tcnt);
     S.tile_site_off = fuz_at<int32_t>(ctx, o_toff);
     S.us_gpos = fuz_at<int32_t>(ctx, o_usg); S.us_cnt = fuz_at<uint32_t>(ctx, o_usc);
     S.s_gpos = fuz_at<int32_t>(ctx, o_sg); S.site_rows = fuz_at<int32_t>(ctx, o_srow);
     S.site_row_off = fuz_at<int32_t>(ctx, o_sroff);
     S.counts = out->d_counts ? out->d_counts : (need_counts ? fuz_at<uint32_t>(ctx, o_counts) : nullptr);
-    S.seg_cap = seg_cap; S.n_tiles = n_tiles;
+    S.n_tiles = n_tiles;
 
     k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, n_ctg);
     FUZ_LAUNCH_CHECK(ctx, "k_het_init");
-    if (n_rec > 0) {
-        k_rec_segbound<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S.r_segcnt);
-        FUZ_LAUNCH_CHECK(ctx, "k_rec_segbound");
-    }
-    if ((rc = fuz_scan_i32(ctx, S.r_segcnt, S.r_seg_off, n_rec, nullptr, nullptr))) return rc;
     if (n_rec > 0) {
         k_scan_records<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
                                                          in->d_ctg_goff, n_ctg, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_scan_records");
     }
-    k_ctg_finish<<<(n_ctg + 255) / 256, 256, 0, st>>>(n_ctg, in->d_ctg_goff, S);
-    FUZ_LAUNCH_CHECK(ctx, "k_ctg_finish");
-    k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S);
+    if ((rc = fuz_scan_i32(ctx, S.r_nwords, S.r_woff, n_rec, nullptr, FUZ_FIN_PROJ, proj_cap))) return rc;
+    k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -687,13 +683,19 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     }
     if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
-        k_pileup_tile<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(in->d_rec_buf, S, cap_sites, out->d_counts, ctx->d_status);
-        FUZ_LAUNCH_CHECK(ctx, "k_pileup_tile");
+        if (n_rec > 0) {
+            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_project");
+        }
+        k_pileup_gather<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S, cap_sites, out->d_counts, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
     } else {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
+            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_project");      // the variant_map rows still come from the projection
             k_pileup_atomic<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
                                                               in->d_ctg_goff, n_ctg, S, S.counts, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_pileup_atomic");
@@ -702,15 +704,12 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         k_het_from_counts<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
-    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, nullptr))) return rc;
-    k_sites_count<<<1, 32, 0, st>>>(n_tiles, S, cap_sites, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_sites_count");
+    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, FUZ_FIN_SITES, cap_sites))) return rc;
     k_order_sites<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_order_sites");
-    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, nullptr))) return rc;
-    k_rows_count<<<1, 32, 0, st>>>(S, out->cap_vmap, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_rows_count");
-    k_signature<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
+    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, FUZ_FIN_VMAP, out->cap_vmap)))
+        return rc;
+    k_signature<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_signature");
     return FUZ_OK;
 }

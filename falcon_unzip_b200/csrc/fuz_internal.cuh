@@ -29,6 +29,7 @@ struct fuz_ctx {
     int64_t launches = 0;
     int pileup_impl = 0;
     int64_t max_pairs_per_site = 96;
+    bool phase_attr_set = false;
     // timing of the dominant kernel
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -122,6 +123,8 @@ __device__ __forceinline__ int fuz_upper_bound(const int32_t *a, int lo, int hi,
 #endif
 
 // exclusive scan of n int32 values (n read from *d_n if d_n != nullptr, clamped to cap);
-// out has n+1 entries (out[n] = total); optionally stores the total as int64.
+// out has n+1 entries (out[n] = total).  fin_op publishes the total into the status block
+// as a row count with a capacity check (FUZ_FIN_NONE: nothing).
+enum { FUZ_FIN_NONE = 0, FUZ_FIN_SITES, FUZ_FIN_VMAP, FUZ_FIN_ATABLE, FUZ_FIN_READS, FUZ_FIN_PAIRS, FUZ_FIN_PROJ };
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap,
-                 const int64_t *d_n, int64_t *d_total64);
+                 const int64_t *d_n, int fin_op, int64_t fin_cap);

@@ -129,14 +129,6 @@ __global__ void k_cand_count(const int32_t *__restrict__ site_ctg, const int32_t
     }
 }
 
-__global__ void k_pairs_check(AssocScratch A, fuz_status *st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
-        int64_t total = A.cand_off[st->n_sites];
-        st->need_pairs = total;
-        if (total > A.max_pairs) fuz_raise(st, FUZ_E_CAPACITY, 4);
-    }
-}
-
 __device__ __forceinline__ int sorted_intersect(const int32_t *__restrict__ a, int na, const int32_t *__restrict__ b, int nb) {
     int i = 0, j = 0, s = 0;
     while (i < na && j < nb) {
@@ -183,15 +175,6 @@ __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *
     }
 }
 
-__global__ void k_atable_count(AssocScratch A, int64_t cap_atable, fuz_status *st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
-        int64_t total = A.at_off[st->n_sites];
-        st->need_atable = total;
-        if (total > cap_atable) { fuz_raise(st, FUZ_E_CAPACITY, 2); total = 0; }
-        st->n_atable = total;
-    }
-}
-
 __global__ void __launch_bounds__(256) k_pair_fill(AssocScratch A, fuz_outputs O, const fuz_status *st) {
     if (st->error) return;
     const int lane = threadIdx.x & 31;
@@ -222,21 +205,26 @@ __global__ void __launch_bounds__(256) k_pair_fill(AssocScratch A, fuz_outputs O
 
 // ================================================================== phased blocks
 struct BlockScratch {
-    int32_t *ctg_site_off, *left_cnt, *left_off, *left_cur, *left_row, *right_off, *minleft_row;
+    int32_t *ctg_site_off, *left_cnt, *left_off, *left_cur, *lq, *ld, *right_off, *min_k;
+    int32_t *bidx, *bsize, *bnew;
     uint32_t *fp;   // forest pointer: parent * 2 + parity bit
 };
+
+#define FUZ_PHASE_THREADS 1024
+#define FUZ_PHASE_SMEM (160 * 1024)      // dynamic shared memory of k_ctg_phase
 
 __device__ __forceinline__ int row_d(const int32_t *__restrict__ at_ct, int row) {       // cis - trans
     int4 c = reinterpret_cast<const int4 *>(at_ct)[row];
     return (c.x + c.w) - (c.y + c.z);
 }
 
-__global__ void k_blk_init(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+__global__ void k_blk_init(BlockScratch B, const fuz_status *st) {
     if (st->error) return;
     const int n_sites = (int)st->n_sites;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
         B.left_cnt[s] = 0;
-        if (s < n_sites) { B.left_cur[s] = 0; B.minleft_row[s] = -1; }
+        B.bsize[s] = 0;
+        if (s < n_sites) B.left_cur[s] = 0;
     }
 }
 
@@ -251,6 +239,8 @@ __global__ void k_edge_count(BlockScratch B, fuz_outputs O, const fuz_status *st
     }
 }
 
+// left adjacency in CSR form: lq = left partner, ld = cis - trans (order inside a site's list
+// is arbitrary: only sums / minima over it are used)
 __global__ void k_edge_fill(BlockScratch B, fuz_outputs O, fuz_status *st) {
     if (st->error) return;
     const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
@@ -261,11 +251,15 @@ __global__ void k_edge_fill(BlockScratch B, fuz_outputs O, fuz_status *st) {
             fuz_raise(st, FUZ_E_FORMAT, r);     // rows must be strictly ordered by (site1, site2)
             continue;
         }
-        if (abs(row_d(O.d_at_ct, r)) >= 6) B.left_row[B.left_off[s2] + atomicAdd(&B.left_cur[s2], 1)] = r;
+        const int d = row_d(O.d_at_ct, r);
+        if (abs(d) >= 6) {
+            int k = B.left_off[s2] + atomicAdd(&B.left_cur[s2], 1);
+            B.lq[k] = s1; B.ld[k] = d;
+        }
     }
 }
 
-// per site: row range as left site; accepted row with the smallest left partner
+// per site: row range as left site; list slot of the smallest left partner
 __global__ void k_site_prep(BlockScratch B, fuz_outputs O, const fuz_status *st) {
     if (st->error) return;
     const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
@@ -274,47 +268,112 @@ __global__ void k_site_prep(BlockScratch B, fuz_outputs O, const fuz_status *st)
         if (s < n_sites) {
             int best = -1, best_s1 = 0x7fffffff;
             for (int k = B.left_off[s]; k < B.left_off[s + 1]; k++) {
-                int row = B.left_row[k], s1 = O.d_at_s1[row];
-                if (s1 < best_s1) { best_s1 = s1; best = row; }
+                int s1 = B.lq[k];
+                if (s1 < best_s1) { best_s1 = s1; best = k; }
             }
-            B.minleft_row[s] = best;
+            B.min_k[s] = best;
         }
     }
 }
 
+// CTA-wide exclusive scans over one value per thread (sum / max); s_tmp has 33 ints.
+__device__ __forceinline__ int cta_excl_sum(int v, int *s_tmp, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = fuz_warp_incl_scan(v, lane);
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nw ? s_tmp[lane] : 0;
+        int ti = fuz_warp_incl_scan(t, lane);
+        s_tmp[lane] = ti - t;
+        if (lane == 31) s_tmp[32] = ti;
+    }
+    __syncthreads();
+    int r = s_tmp[warp] + incl - v;
+    *total = s_tmp[32];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   // values >= 0, identity 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, t);
+    }
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0;
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nw ? s_tmp[lane] : 0, ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti = max(ti, u);
+        }
+        int te = __shfl_up_sync(0xffffffffu, ti, 1);
+        if (lane == 0) te = 0;
+        s_tmp[lane] = te;
+        if (lane == 31) s_tmp[32] = ti;
+    }
+    __syncthreads();
+    int r = max(s_tmp[warp], excl);
+    *total = s_tmp[32];
+    __syncthreads();
+    return r;
+}
+
 // One CTA per contig: pass-1 forest + pointer jumping, pass-2 sweep, pass-3 extents and
 // scores, pass-4 block chaining (phasing.py:240-408; parallel forms of SURVEY.md A.3).
-__global__ void __launch_bounds__(1024) k_ctg_phase(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+// Phase bits of the contig live in shared memory; the left adjacency is staged there too
+// when it fits, so the inherently sequential sweep runs at shared-memory latency.
+__global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B, fuz_outputs O, fuz_status *st) {
     if (st->error) return;
+    extern __shared__ uint32_t smem[];
+    __shared__ int s_tmp[33];
     const int c = blockIdx.x;
     const int cs0 = B.ctg_site_off[c], cs1 = B.ctg_site_off[c + 1];
     const int n = cs1 - cs0;
     if (n <= 0) return;
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int e0 = B.left_off[cs0], n_e = B.left_off[cs1] - e0;
+    const int nbw = (n + 31) >> 5;
+    if ((size_t)nbw * 4 > FUZ_PHASE_SMEM) { if (tid == 0) fuz_raise(st, FUZ_E_CAPACITY, 5); return; }
+    uint32_t *sbits = smem;                                   // [nbw] phase bit per site
+    const bool staged = (size_t)nbw * 4 + (size_t)(n + 1) * 4 + (size_t)n_e * 8 <= FUZ_PHASE_SMEM;
+    int *s_off = reinterpret_cast<int *>(smem + nbw);         // [n + 1] (staged only)
+    int *s_q = s_off + n + 1, *s_d = s_q + n_e;               // [n_e] each (staged only)
     volatile uint32_t *fp = B.fp;
     // ---- pass 1 as a forest (rows are ordered by (site1, site2), ties impossible)
     for (int x = cs0 + tid; x < cs1; x += nt) {
         int parent = x, bit = 0;
         bool in_pos = false;
-        int ml = B.minleft_row[x];
-        if (ml >= 0) {
+        int mk = B.min_k[x];
+        if (mk >= 0) {
             in_pos = true;
-            parent = O.d_at_s1[ml];
-            bit = row_d(O.d_at_ct, ml) < 0;                    // trans > cis flips the state
+            parent = B.lq[mk];
+            bit = B.ld[mk] < 0;                                // trans > cis flips the state
         } else {
             for (int r = B.right_off[x]; r < B.right_off[x + 1]; r++) {
                 int d = row_d(O.d_at_ct, r);
                 if (abs(d) < 6) continue;
                 in_pos = true;                                 // first accepted row = smallest right partner
                 int rm = O.d_at_s2[r];
-                int mlr = B.minleft_row[rm];
+                int mkr = B.min_k[rm];
                 // partner already has a state when x is first touched iff it has a left partner < x
-                if (mlr >= 0 && O.d_at_s1[mlr] < x) { parent = rm; bit = d < 0; }
+                if (mkr >= 0 && B.lq[mkr] < x) { parent = rm; bit = d < 0; }
                 break;
             }
         }
         fp[x] = ((uint32_t)parent << 1) | (uint32_t)bit;
         O.d_ph_state[x] = in_pos ? 0 : 255;
+    }
+    for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
+    if (staged) {
+        for (int i = tid; i <= n; i += nt) s_off[i] = B.left_off[cs0 + i] - e0;
+        for (int k = tid; k < n_e; k += nt) { s_q[k] = B.lq[e0 + k] - cs0; s_d[k] = B.ld[e0 + k]; }
     }
     __syncthreads();
     int rounds = 1;
@@ -332,65 +391,94 @@ __global__ void __launch_bounds__(1024) k_ctg_phase(BlockScratch B, fuz_outputs 
         __syncthreads();
     }
     for (int x = cs0 + tid; x < cs1; x += nt)
-        if (O.d_ph_state[x] != 255) O.d_ph_state[x] = (uint8_t)(fp[x] & 1u);
+        if (O.d_ph_state[x] != 255 && (fp[x] & 1u)) atomicOr(&sbits[(x - cs0) >> 5], 1u << ((x - cs0) & 31));
     __syncthreads();
     // ---- pass 2: one left-to-right sweep (a second sweep never changes anything)
-    if (tid < 32) {
-        volatile uint8_t *state = O.d_ph_state;
-        for (int x = cs0; x < cs1; x++) {
-            const int l0 = B.left_off[x], l1 = B.left_off[x + 1];
+    if (warp == 0) {
+        volatile uint32_t *vb = sbits;
+        for (int i = 0; i < n; i++) {
+            int l0, l1;
+            if (staged) { l0 = s_off[i]; l1 = s_off[i + 1]; } else { l0 = B.left_off[cs0 + i] - e0; l1 = B.left_off[cs0 + i + 1] - e0; }
             if (l0 == l1) continue;
             int s0 = 0;                                         // score(state 0) - score(state 1)
             for (int k = l0 + lane; k < l1; k += 32) {
-                int row = B.left_row[k];
-                int d = row_d(O.d_at_ct, row);
-                s0 += state[O.d_at_s1[row]] == 0 ? d : -d;
+                int q, d;
+                if (staged) { q = s_q[k]; d = s_d[k]; } else { q = B.lq[e0 + k] - cs0; d = B.ld[e0 + k]; }
+                s0 += ((vb[q >> 5] >> (q & 31)) & 1u) ? -d : d;
             }
-            s0 = fuz_warp_sum(s0);
-            if (lane == 0) { if (s0 < 0) state[x] = 1; else if (s0 > 0) state[x] = 0; }
+            s0 = __reduce_add_sync(0xffffffffu, s0);
+            if (lane == 0) {
+                uint32_t w = vb[i >> 5], m = 1u << (i & 31);
+                if (s0 < 0) vb[i >> 5] = w | m; else if (s0 > 0) vb[i >> 5] = w & ~m;
+            }
             __syncwarp();
         }
     }
     __syncthreads();
-    // ---- pass 3: scores and extents (positions are the 1-based file positions)
-    for (int x = cs0 + tid; x < cs1; x += nt) {
-        const uint8_t sx = O.d_ph_state[x];
-        int lscore = 0, rscore = 0, lext = O.d_site_pos[x], rext = O.d_site_pos[x];
-        if (sx != 255) {
-            for (int k = B.left_off[x]; k < B.left_off[x + 1]; k++) {
-                int row = B.left_row[k], q = O.d_at_s1[row];
-                int d = row_d(O.d_at_ct, row);
-                int dd = O.d_ph_state[q] == sx ? d : -d;
+    // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
+    for (int x = cs0 + warp; x < cs1; x += nwarps) {
+        const bool in_pos = O.d_ph_state[x] != 255;
+        const int px = O.d_site_pos[x];
+        int lscore = 0, rscore = 0, lext = px, rext = px;
+        if (in_pos) {
+            const uint32_t sx = (sbits[(x - cs0) >> 5] >> ((x - cs0) & 31)) & 1u;
+            for (int k = B.left_off[x] + lane; k < B.left_off[x + 1]; k += 32) {
+                int q = B.lq[k], d = B.ld[k];
+                uint32_t sq = (sbits[(q - cs0) >> 5] >> ((q - cs0) & 31)) & 1u;
+                int dd = sq == sx ? d : -d;
                 lscore += dd;
                 if (dd > 0) lext = min(lext, O.d_site_pos[q]);
             }
-            for (int r = B.right_off[x]; r < B.right_off[x + 1]; r++) {
+            for (int r = B.right_off[x] + lane; r < B.right_off[x + 1]; r += 32) {
                 int d = row_d(O.d_at_ct, r);
                 if (abs(d) < 6) continue;
                 int q = O.d_at_s2[r];
-                int dd = O.d_ph_state[q] == sx ? d : -d;
+                uint32_t sq = (sbits[(q - cs0) >> 5] >> ((q - cs0) & 31)) & 1u;
+                int dd = sq == sx ? d : -d;
                 rscore += dd;
                 if (dd > 0) rext = max(rext, O.d_site_pos[q]);
             }
+            lscore = __reduce_add_sync(0xffffffffu, lscore); rscore = __reduce_add_sync(0xffffffffu, rscore);
+            lext = __reduce_min_sync(0xffffffffu, lext); rext = __reduce_max_sync(0xffffffffu, rext);
+            if (lane == 0) O.d_ph_state[x] = (uint8_t)sx;
         }
-        O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
-        O.d_ph_block[x] = 0;
+        if (lane == 0) {
+            O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
+        }
     }
     __syncthreads();
-    // ---- pass 4: chain sites into blocks by the running maximum of right extents
-    if (tid == 0) {
-        int block_id = 1, max_right_ext = 0, pb_first = -1, pb_n = 0;
-        for (int x = cs0; x < cs1; x++) {
-            if (O.d_ph_state[x] == 255 || O.d_ph_rscore[x] < 10 || O.d_ph_lscore[x] < 10) continue;
-            if (max_right_ext < O.d_ph_lext[x]) {
-                if (pb_n > 3) block_id++;
-                else for (int y = pb_first; y >= 0 && y < x; y++) O.d_ph_block[y] = 0;
-                pb_first = x; pb_n = 0;
-            }
-            O.d_ph_block[x] = block_id; pb_n++;
-            max_right_ext = max(max_right_ext, O.d_ph_rext[x]);
-        }
-        if (pb_n <= 3) for (int y = pb_first; y >= 0 && y < cs1; y++) O.d_ph_block[y] = 0;
+    // ---- pass 4: chain sites into blocks by the running maximum of right extents (never reset)
+    //      = exclusive prefix max + boundary flags + segment sizes + dense ids of blocks with > 3 sites
+    int carry_max = 0, carry_b = 0;
+    for (int base = 0; base < n; base += nt) {
+        const int x = cs0 + base + tid;
+        const bool valid = base + tid < n;
+        const bool f = valid && O.d_ph_state[x] != 255 && O.d_ph_rscore[x] >= 10 && O.d_ph_lscore[x] >= 10;
+        int tot;
+        int mb = max(carry_max, cta_excl_max(f ? O.d_ph_rext[x] : 0, s_tmp, &tot));
+        carry_max = max(carry_max, tot);
+        const int boundary = f && mb < O.d_ph_lext[x];
+        int bi = carry_b + cta_excl_sum(boundary, s_tmp, &tot) + boundary;   // inclusive: temp block number
+        carry_b += tot;
+        if (valid) B.bidx[x] = f ? bi : 0;
+        if (f) atomicAdd(&B.bsize[cs0 + bi], 1);       // bi <= number of filtered sites <= n
+    }
+    __threadfence_block();
+    __syncthreads();
+    int carry_id = 0;
+    for (int base = 0; base <= n; base += nt) {        // temp block numbers 0..n
+        const int b = base + tid;
+        const int keep = b >= 1 && b <= n && B.bsize[cs0 + b] > 3;
+        int tot;
+        int id = carry_id + cta_excl_sum(keep, s_tmp, &tot);
+        carry_id += tot;
+        if (b <= n) B.bnew[cs0 + c + b] = keep ? id + 1 : 0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (int x = cs0 + tid; x < cs1; x += nt) {
+        int bi = B.bidx[x];
+        O.d_ph_block[x] = bi > 0 ? B.bnew[cs0 + c + bi] : 0;
     }
 }
 
@@ -475,15 +563,6 @@ __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_st
     }
 }
 
-__global__ void k_reads_count(ReadScratch R, int64_t cap_reads, fuz_status *st) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
-        int64_t total = R.pr_off[R.total_nq];
-        st->need_reads = total;
-        if (total > cap_reads) { fuz_raise(st, FUZ_E_CAPACITY, 3); total = 0; }
-        st->n_reads = total;
-    }
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------ host side
@@ -516,14 +595,10 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
     k_cand_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_ctg, out->d_site_pos, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_cand_count");
-    if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, nullptr))) return rc;
-    k_pairs_check<<<1, 32, 0, st>>>(A, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_pairs_check");
+    if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, FUZ_FIN_PAIRS, A.max_pairs))) return rc;
     k_pair_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
-    if ((rc = fuz_scan_i32(ctx, A.at_cnt, A.at_off, cs, d_ns, nullptr))) return rc;
-    k_atable_count<<<1, 32, 0, st>>>(A, out->cap_atable, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_atable_count");
+    if ((rc = fuz_scan_i32(ctx, A.at_cnt, A.at_off, cs, d_ns, FUZ_FIN_ATABLE, out->cap_atable))) return rc;
     k_pair_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_fill");
     return FUZ_OK;
@@ -535,25 +610,31 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
     BlockScratch B;
     FuzLayout L;
     size_t o_cso = L.add(4 * (size_t)(n_ctg + 2)), o_lc = L.add(4 * (size_t)(cs + 2)), o_lo = L.add(4 * (size_t)(cs + 2));
-    size_t o_lcur = L.add(4 * (size_t)(cs + 1)), o_lrow = L.add(4 * (size_t)(ca + 1)), o_ro = L.add(4 * (size_t)(cs + 2));
-    size_t o_ml = L.add(4 * (size_t)(cs + 1)), o_fp = L.add(4 * (size_t)(cs + 1));
+    size_t o_lcur = L.add(4 * (size_t)(cs + 1)), o_lq = L.add(4 * (size_t)(ca + 1)), o_ld = L.add(4 * (size_t)(ca + 1));
+    size_t o_ro = L.add(4 * (size_t)(cs + 2)), o_mk = L.add(4 * (size_t)(cs + 1)), o_fp = L.add(4 * (size_t)(cs + 1));
+    size_t o_bi = L.add(4 * (size_t)(cs + 1)), o_bs = L.add(4 * (size_t)(cs + 2)), o_bn = L.add(4 * (size_t)(cs + n_ctg + 2));
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
     B.ctg_site_off = fuz_at<int32_t>(ctx, o_cso); B.left_cnt = fuz_at<int32_t>(ctx, o_lc); B.left_off = fuz_at<int32_t>(ctx, o_lo);
-    B.left_cur = fuz_at<int32_t>(ctx, o_lcur); B.left_row = fuz_at<int32_t>(ctx, o_lrow); B.right_off = fuz_at<int32_t>(ctx, o_ro);
-    B.minleft_row = fuz_at<int32_t>(ctx, o_ml); B.fp = fuz_at<uint32_t>(ctx, o_fp);
+    B.left_cur = fuz_at<int32_t>(ctx, o_lcur); B.lq = fuz_at<int32_t>(ctx, o_lq); B.ld = fuz_at<int32_t>(ctx, o_ld);
+    B.right_off = fuz_at<int32_t>(ctx, o_ro); B.min_k = fuz_at<int32_t>(ctx, o_mk); B.fp = fuz_at<uint32_t>(ctx, o_fp);
+    B.bidx = fuz_at<int32_t>(ctx, o_bi); B.bsize = fuz_at<int32_t>(ctx, o_bs); B.bnew = fuz_at<int32_t>(ctx, o_bn);
+    if (!ctx->phase_attr_set) {
+        FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
+        ctx->phase_attr_set = true;
+    }
     k_ctg_siteoff<<<(n_ctg + 256) / 256, 256, 0, st>>>(out->d_site_ctg, n_ctg, B.ctg_site_off, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_ctg_siteoff");
-    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
     k_edge_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
-    if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, nullptr))) return rc;
+    if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, FUZ_FIN_NONE, 0))) return rc;
     k_edge_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
     k_site_prep<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_site_prep");
-    k_ctg_phase<<<n_ctg, 1024, 0, st>>>(B, *out, ctx->d_status);
+    k_ctg_phase<<<n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_ctg_phase");
     return FUZ_OK;
 }
@@ -574,7 +655,7 @@ int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t
     R.q_cnt = fuz_at<int32_t>(ctx, o_qc); R.q_off = fuz_at<int32_t>(ctx, o_qo); R.q_cur = fuz_at<int32_t>(ctx, o_qcur);
     R.q_ent = fuz_at<int32_t>(ctx, o_qe); R.pr_cnt = fuz_at<int32_t>(ctx, o_pc); R.pr_off = fuz_at<int32_t>(ctx, o_po);
     R.dup = fuz_at<uint8_t>(ctx, o_dup);
-    if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, nullptr))) return rc;
+    if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, FUZ_FIN_NONE, 0))) return rc;
     k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, R.row_off, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
     k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
@@ -583,14 +664,12 @@ int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t
     FUZ_LAUNCH_CHECK(ctx, "k_rd_init");
     k_q_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_count");
-    if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, nullptr))) return rc;
+    if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, FUZ_FIN_NONE, 0))) return rc;
     k_q_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_fill");
     k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
-    if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, nullptr))) return rc;
-    k_reads_count<<<1, 32, 0, st>>>(R, out->cap_reads, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_reads_count");
+    if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, FUZ_FIN_READS, out->cap_reads))) return rc;
     k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
     return FUZ_OK;

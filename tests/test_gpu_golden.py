@@ -1,0 +1,118 @@
+"""GPU parity against the committed golden vectors and the crafted Appendix-E cases: the
+reference-signature functions of falcon_unzip_b200.phasing (through the C ABI) must write
+byte-identical files."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import cases
+from test_golden_cpu import CASES, FILES, GOLD, STAGE_CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _paths(base, ctg):
+    b = os.path.join(base, ctg)
+    return dict(variant_map=os.path.join(b, "het_call", "variant_map"), variant_pos=os.path.join(b, "het_call", "variant_pos"),
+                q_id_map=os.path.join(b, "het_call", "q_id_map"), atable=os.path.join(b, "g_atable", "atable"),
+                phased_variants=os.path.join(b, "get_phased_blocks", "phased_variants"),
+                phased_reads=os.path.join(b, "phased_reads"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_on_golden_inputs(eng, case, tmp_path):
+    """fc_phasing.py command line on the golden BAM + FASTA (four stages through files)."""
+    from falcon_unzip_b200 import phasing
+    d, _refs, _records, ctg, _ref = load_case(case)
+    phasing.main(["fc_phasing.py", "--bam", os.path.join(d, "in.bam"), "--fasta", os.path.join(d, "ref.fa"),
+                  "--ctg_id", ctg, "--base_dir", str(tmp_path)])
+    got = _paths(str(tmp_path), ctg)
+    for k in FILES:
+        assert open(os.path.join(d, k)).read() == open(got[k]).read(), (case, k)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_batch_on_golden_inputs(eng, case, tmp_path):
+    from falcon_unzip_b200 import phasing
+    d, _refs, records, ctg, ref = load_case(case)
+    _res, got = phasing.phase_contigs(records, [ctg], [ref], str(tmp_path))
+    for k in FILES:
+        assert open(os.path.join(d, k)).read() == open(got[ctg][k]).read(), (case, k)
+
+
+@pytest.mark.parametrize("case", STAGE_CASES)
+def test_stage_functions_on_golden_inputs(eng, case, tmp_path):
+    """generate_association_table / get_phased_blocks / get_phased_reads called one by one
+    with the reference's PypeTask `self` convention, each from the golden input files."""
+    from falcon_unzip_b200 import phasing
+    d = os.path.join(GOLD, case)
+    p = lambda k: os.path.join(d, k)
+    o = lambda k: str(tmp_path / k)
+    phasing.generate_association_table(SimpleNamespace(vmap_file=p("variant_map"), atable_file=o("atable"),
+                                                       parameters=dict(ctg_id="c", base_dir=".")))
+    phasing.get_phased_blocks(SimpleNamespace(vmap_file=p("variant_map"), atable_file=p("atable"),
+                                              phased_variant_file=o("phased_variants"), parameters={}))
+    phasing.get_phased_reads(SimpleNamespace(vmap_file=p("variant_map"), q_id_map_file=p("q_id_map"),
+                                             phased_variant_file=p("phased_variants"), phased_read_file=o("phased_reads"),
+                                             parameters=dict(ctg_id="c")))
+    for k in ("atable", "phased_variants", "phased_reads"):
+        assert open(p(k)).read() == open(o(k)).read(), (case, k)
+
+
+@pytest.mark.parametrize("gap", [65536, 65537])
+def test_window_edge_vs_oracle(eng, gap, tmp_path):
+    from falcon_unzip_b200 import phasing
+    from oracle import c_oracle
+    recs, ref = cases.window_case(gap)
+    records, _refs = cases.build(recs, len(ref))
+    want = c_oracle.run_phasing_stages(records, cases.CTG, ref, str(tmp_path / "oracle"))
+    _res, got = phasing.phase_contigs(records, [cases.CTG], [ref], str(tmp_path / "gpu"))
+    for k in FILES:
+        assert open(want[k]).read() == open(got[cases.CTG][k]).read(), k
+    assert len(open(want["atable"]).read().splitlines()) == (1 if gap == 65536 else 0)
+
+
+@pytest.mark.parametrize("seed", range(6, 30))
+def test_stage_fuzz_vs_oracle(eng, seed, tmp_path):
+    """Random variant_map inputs through the three later stage functions, GPU vs oracle."""
+    from falcon_unzip_b200 import phasing
+    from oracle import c_oracle
+    rng = np.random.default_rng(1000 + seed)
+    n_sites = int(rng.integers(5, 400))
+    _p, _r, rows = cases.random_vmap(rng, n_sites, int(rng.integers(8, 40)), int(rng.integers(30, 600)),
+                                     dup_rate=float(rng.choice([0.0, 0.1, 0.3])))
+    d_g, d_o = tmp_path / "gpu", tmp_path / "oracle"
+    for d in (d_g, d_o):
+        os.makedirs(d)
+        with open(d / "variant_map", "w") as f:
+            f.write("".join("%d %s %s %d\n" % r for r in rows))
+        with open(d / "q_id_map", "w") as f:
+            f.write("".join("%d read%d\n" % (q, q) for q in range(max(r[3] for r in rows) + 1)))
+    g, o = (lambda k: str(d_g / k)), (lambda k: str(d_o / k))
+    c_oracle.generate_association_table_files(o("variant_map"), o("atable"))
+    c_oracle.get_phased_blocks_files(o("variant_map"), o("atable"), o("phased_variants"))
+    c_oracle.get_phased_reads_files(o("variant_map"), o("q_id_map"), o("phased_variants"), "c", o("phased_reads"))
+    phasing.generate_association_table(SimpleNamespace(vmap_file=g("variant_map"), atable_file=g("atable"),
+                                                       parameters=dict(ctg_id="c", base_dir=".")))
+    phasing.get_phased_blocks(SimpleNamespace(vmap_file=g("variant_map"), atable_file=g("atable"),
+                                              phased_variant_file=g("phased_variants"), parameters={}))
+    phasing.get_phased_reads(SimpleNamespace(vmap_file=g("variant_map"), q_id_map_file=g("q_id_map"),
+                                             phased_variant_file=g("phased_variants"), phased_read_file=g("phased_reads"),
+                                             parameters=dict(ctg_id="c")))
+    for k in ("atable", "phased_variants", "phased_reads"):
+        assert open(o(k)).read() == open(g(k)).read(), k
+
+
+def test_c1_scale_contig_vs_oracle(eng, tmp_path):
+    """A 300 kb / 30x contig (C1 shape at reduced length so the oracle finishes in seconds)."""
+    from conftest import synth_set
+    from falcon_unzip_b200 import phasing
+    from oracle import c_oracle
+    sset = synth_set("c1", contig_len=300_000)
+    want = c_oracle.run_phasing_stages(sset.contig_records(0), sset.refs[0][0], sset.ref_seqs[0], str(tmp_path / "oracle"))
+    _res, got = phasing.phase_contigs(sset.records, [sset.refs[0][0]], sset.ref_seqs, str(tmp_path / "gpu"))
+    for k in FILES:
+        assert open(want[k]).read() == open(got[sset.refs[0][0]][k]).read(), k
+    assert len(open(want["phased_reads"]).read().splitlines()) > 500
