@@ -305,11 +305,12 @@ def run_b200(args):
                         "d2h_bytes_per_step": int(r.d2h_bytes), "ms_per_step": e2e_ms_max, "steps": e2e_steps,
                         "api": "fuz_phase_batch_host (pinned host BAM records in, host row arrays out)"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_pileup_tile (pileup + het test)", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": "k_project + k_pileup_gather (pileup + het test, timed as one group)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "algorithmic_bytes_per_launch": alg["total"], "kernel_ms": kern_ms, "peak_source": peak_src,
                              "note": "algorithmic bytes per SURVEY.md 8(d): records once (36+4*n_cigar+ceil(l_seq/2)) + 32 B/position "
-                                     "of pileup counts; the fused kernel keeps the counts in registers, so its DRAM traffic is lower"},
+                                     "of pileup counts; the kernels keep the counts in registers and move a 4-bit reference-aligned projection "
+                                     "(0.5 B/base written + read) instead"},
                 "cpu_baseline": cpu,
                 "clocks": clocks,
                 "rows": {"sites": int(st.n_sites), "variant_map": int(st.n_vmap), "atable": int(st.n_atable),

@@ -84,6 +84,8 @@ SYMBOLS = [
     ("fuz_launch_count", C.c_int64, [C.c_void_p]),
     ("fuz_kernel_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("fuz_get_kernel_timing", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    ("fuz_profile", C.c_int, [C.c_void_p, C.c_int]),
+    ("fuz_profile_report", C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
     ("fuz_het_call", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Outputs)]),
     ("fuz_association_table", C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(Outputs)]),
     ("fuz_phased_blocks", C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(Outputs)]),

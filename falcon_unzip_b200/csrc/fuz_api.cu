@@ -5,17 +5,20 @@
 #include "fuz_internal.cuh"
 
 int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
-int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out);
+int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row_off_valid);
 int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out);
-int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out);
+int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
+                   bool dup_valid);
 
 extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (!ctx || !in || !out) return FUZ_E_ARG;
     int rc = fuz_het_call_impl(ctx, in, out);
     if (rc) return rc;
-    if ((rc = fuz_association_impl(ctx, in->n_ctg, out))) return rc;
+    // the row range of every site (het call) and the duplicate flags (association) stay in
+    // the context's inter-stage buffer and are reused by the later stages
+    if ((rc = fuz_association_impl(ctx, in->n_ctg, out, true))) return rc;
     if ((rc = fuz_blocks_impl(ctx, in->n_ctg, out))) return rc;
-    return fuz_reads_impl(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out);
+    return fuz_reads_impl(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out, true);
 }
 
 static int ensure_stage(fuz_ctx *ctx, size_t dev_bytes, size_t pin_bytes) {

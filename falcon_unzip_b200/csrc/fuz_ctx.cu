@@ -61,7 +61,10 @@ extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->timing_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : ctx->prof_marks) cudaEventDestroy(p.second);
+    if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->keep) cudaFree(ctx->keep);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
     if (ctx->d_status) cudaFree(ctx->d_status);
@@ -140,6 +143,64 @@ extern "C" int fuz_get_kernel_timing(fuz_ctx *ctx, double *h_ms_total, int64_t *
     return FUZ_OK;
 }
 
+int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup) {
+    size_t off_dup = ((size_t)(cap_sites + 2) * 4 + 255) & ~(size_t)255;
+    size_t need = off_dup + (size_t)cap_vmap + 256;
+    if (need > ctx->keep_cap) {
+        FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->keep) FUZ_CUDA(ctx, cudaFree(ctx->keep));
+        ctx->keep = nullptr; ctx->keep_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->keep, need + (need >> 2));
+        if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "inter-stage buffer of %zu bytes: %s", need, cudaGetErrorString(e));
+        ctx->keep_cap = need + (need >> 2);
+    }
+    *row_off = reinterpret_cast<int32_t *>(ctx->keep);
+    *dup = ctx->keep + off_dup;
+    return FUZ_OK;
+}
+
+// ---- per-launch profile: fuz_profile(ctx, 1) starts a capture, fuz_profile_report prints
+// "name ms" for every launch since (device time between consecutive marks on the stream).
+void fuz_profile_mark(fuz_ctx *ctx, const char *name) {
+    if (ctx->prof_used == ctx->prof_marks.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->prof_marks.push_back({name, e});
+    }
+    ctx->prof_marks[ctx->prof_used].first = name;
+    cudaEventRecord(ctx->prof_marks[ctx->prof_used].second, ctx->stream);
+    ctx->prof_used++;
+}
+
+extern "C" int fuz_profile(fuz_ctx *ctx, int enable) {
+    if (!ctx) return FUZ_E_ARG;
+    ctx->profile = enable != 0;
+    ctx->prof_used = 0;
+    if (enable) {
+        if (!ctx->prof_start) FUZ_CUDA(ctx, cudaEventCreate(&ctx->prof_start));
+        FUZ_CUDA(ctx, cudaEventRecord(ctx->prof_start, ctx->stream));
+    }
+    return FUZ_OK;
+}
+
+// Writes "name\tms\n" lines into buf (truncated to cap); returns the number of marks.
+extern "C" int64_t fuz_profile_report(fuz_ctx *ctx, char *buf, int64_t cap) {
+    if (!ctx || !buf || cap < 1) return -1;
+    cudaStreamSynchronize(ctx->stream);
+    int64_t w = 0;
+    buf[0] = 0;
+    cudaEvent_t prev = ctx->prof_start;
+    for (size_t i = 0; i < ctx->prof_used; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, prev, ctx->prof_marks[i].second);
+        prev = ctx->prof_marks[i].second;
+        int n = snprintf(buf + w, (size_t)(cap - w), "%s\t%.4f\n", ctx->prof_marks[i].first, ms);
+        if (n < 0 || w + n >= cap) break;
+        w += n;
+    }
+    return (int64_t)ctx->prof_used;
+}
+
 int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
     if (l.off <= ctx->arena_cap) return FUZ_OK;
     FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -159,46 +220,46 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 // million entries; the scan is never the dominant kernel.  The tail of the scan also
 // publishes the total into the status block (row counts + capacity checks), which saves
 // one tiny kernel launch per scan.
-#define SCAN_PER_THREAD 16
+#define SCAN_PER_THREAD 8
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                    int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
                                                    int64_t fin_cap, fuz_status *st) {
-    __shared__ int warp_tot[32];
-    __shared__ long long carry_s;
+    __shared__ int warp_tot[2][32];               // double buffered: one barrier per chunk
     int64_t n = d_n ? *d_n : n_cap;
     if (n > n_cap) n = n_cap;
     if (n < 0) n = 0;
     if (st && st->error) n = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD) {
+    long long carry_s = 0;                        // replicated in every thread
+    int buf = 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD, buf ^= 1) {
         int v[SCAN_PER_THREAD];
         int s = 0;
         const int64_t i0 = base + (int64_t)tid * SCAN_PER_THREAD;
+        if (vec_ok && i0 + SCAN_PER_THREAD <= n) {
+            const int4 a = *reinterpret_cast<const int4 *>(in + i0), b = *reinterpret_cast<const int4 *>(in + i0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; k++) {
-            v[k] = i0 + k < n ? in[i0 + k] : 0;
-            s += v[k];
+            for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
         }
-        int incl = fuz_warp_incl_scan(s, lane);
-        if (lane == 31) warp_tot[warp] = incl;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; k++) s += v[k];
+        const int incl = fuz_warp_incl_scan(s, lane);
+        if (lane == 31) warp_tot[buf][warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            int t = warp_tot[lane];
-            int ti = fuz_warp_incl_scan(t, lane);
-            warp_tot[lane] = ti - t;  // exclusive offset of each warp
-        }
-        __syncthreads();
-        long long excl = carry_s + warp_tot[warp] + (incl - s);
+        const int t = warp_tot[buf][lane];
+        const int ti = fuz_warp_incl_scan(t, lane);
+        const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
+        const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
+        long long excl = carry_s + wexcl + (incl - s);
 #pragma unroll
         for (int k = 0; k < SCAN_PER_THREAD; k++) {
             if (i0 + k < n) out[i0 + k] = (int32_t)excl;
             excl += v[k];
         }
-        __syncthreads();
-        if (tid == 1023) carry_s = excl;  // excl now = carry + chunk total
-        __syncthreads();
+        carry_s += chunk_total;
     }
     if (tid == 0) {
         const long long total = carry_s;

@@ -2,6 +2,8 @@
 // Reproduces reference falcon_unzip/phasing.py:14-134 (make_het_call) for a batch of
 // contigs; see DESIGN.md for the data layout and the equivalence argument
 // (streaming flush == full pileup evaluated for pos < POS_last).
+#include <algorithm>
+
 #include "fuz_internal.cuh"
 
 namespace {
@@ -49,35 +51,35 @@ __global__ void __launch_bounds__(256) k_scan_records(
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     long long acc_aligned = 0, acc_accepted = 0;
     for (int r = warp_g; r < n_rec; r += n_warps) {
-        const uint8_t *rec = rec_buf + rec_off[r];
-        // contig of the record = position of r in ctg_rec_off (records grouped by contig)
-        int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
+        // issue every independent load first: offsets, then this and the previous header
+        const int64_t off_r = rec_off[r], off_n = rec_off[r + 1], off_p = r > 0 ? rec_off[r - 1] : 0;
+        const uint8_t *rec = rec_buf + off_r;
         const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
         const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
         const uint32_t w12 = fuz_ld_u32_un(rec + 12);     // l_read_name, mapq, bin
         const uint32_t w16 = fuz_ld_u32_un(rec + 16);     // n_cigar_op, flag
         const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
+        const int32_t prev_pos = r > 0 ? (int32_t)fuz_ld_u32_un(rec_buf + off_p + 8) : 0;
+        // contig of the record = position of r in ctg_rec_off (records grouped by contig)
+        const int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
         const int l_name = w12 & 0xFF;
         const int n_cig = w16 & 0xFFFF;
         const uint8_t *cig = rec + 36 + l_name;
-        const int64_t seq_off = rec_off[r] + 36 + l_name + 4 * (int64_t)n_cig;
+        const int64_t seq_off = off_r + 36 + l_name + 4 * (int64_t)n_cig;
         if (lane == 0) {
             S.r_flags[r] = 0; S.r_nwords[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_seq[r] = seq_off;
         }
-        if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 ||
-            rec_off[r + 1] - rec_off[r] != (int64_t)block_size + 4 ||
+        if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 || off_n - off_r != (int64_t)block_size + 4 ||
             36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4) {
             if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
             continue;
         }
         const int64_t gstart64 = ctg_goff[c] + pos;
         // coordinate order inside the contig
-        if (lane == 0 && r > ctg_rec_off[c]) {
-            int32_t prev_pos = (int32_t)fuz_ld_u32_un(rec_buf + rec_off[r - 1] + 8);
-            if (prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
-        }
+        if (lane == 0 && r > ctg_rec_off[c] && prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
         long long total = 0, skip = 0, aligned = 0, span = 0;
         bool badop = false;
+#pragma unroll 4
         for (int k = lane; k < n_cig; k += 32) {
             uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
             uint32_t len = cw >> 4, op = cw & 15;
@@ -103,7 +105,8 @@ __global__ void __launch_bounds__(256) k_scan_records(
             S.r_gstart[r] = gstart;
             S.r_gend[r] = accept ? gstart + (int32_t)span : gstart;
             S.r_flags[r] = accept ? 1 : 0;
-            S.r_nwords[r] = (accept && span > 0) ? (int32_t)(((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 1) : 0;
+            // words of the projection, padded to whole quads (128-bit flushes)
+            S.r_nwords[r] = (accept && span > 0) ? (int32_t)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
             if (accept) {
                 atomicMax(&S.ctg_last_rec[c], r);
                 atomicMax(&S.ctg_maxspan[c], (int32_t)span);
@@ -157,18 +160,13 @@ __device__ __forceinline__ bool het_test(uint32_t cA, uint32_t cC, uint32_t cG, 
 }
 
 // Ordered compaction of the het positions of one tile: every thread owns 8 consecutive
-// positions with counts cnt[i][0..3]; sites of a tile land contiguously (in position
-// order) at an atomically claimed base; tiles are put in order afterwards.
-__device__ __forceinline__ void emit_tile_sites(const uint32_t (&cnt)[8][4], int tile, int t0, int pos_limit,
+// positions (bit i of hetmask: position i is a het site with counts cnt[i][0..3]); sites of
+// a tile land contiguously (in position order) at an atomically claimed base; tiles are put
+// in order afterwards.
+__device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t (&cnt)[8][4], int tile, int t0,
                                                 HetScratch &S, int64_t cap_sites, fuz_status *st,
                                                 int *s_warp_tot, int *s_base) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t hetmask = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int p = t0 + tid * 8 + i;
-        if (p < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
-    }
     int nh = __popc(hetmask);
     int incl = fuz_warp_incl_scan(nh, lane);
     if (lane == 31) s_warp_tot[warp] = incl;
@@ -202,9 +200,32 @@ __device__ __forceinline__ void emit_tile_sites(const uint32_t (&cnt)[8][4], int
     }
 }
 
+__device__ __forceinline__ uint32_t het_mask_of(const uint32_t (&cnt)[8][4], int t0, int pos_limit) {
+    uint32_t hetmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int p = t0 + (int)threadIdx.x * 8 + i;
+        if (p < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
+    }
+    return hetmask;
+}
+
 // ---------------------------------------------------------------- projection (read major)
 // 8 nibbles (query bases q0..q0+7, BAM 4-bit codes) -> one word, base i at bits 4i.
-__device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {
+__device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {      // BAM: first base of a byte in the HIGH nibble
+    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+// zero every nibble that is not one of A=1 C=2 G=4 T=8 (ambiguity codes never count as a
+// base in the pileup, phasing.py:108-111, and never match a called allele)
+__device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
+    uint32_t any = (x & (x >> 1) & 0x77777777u) | (x & (x >> 2) & 0x33333333u) | (x & (x >> 3) & 0x11111111u);
+    if (any) {
+        uint32_t f = (any | (any >> 1) | (any >> 2)) & 0x11111111u;
+        x &= ~(f * 15u);
+    }
+    return x;
+}
+__device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {   // global-memory slow path
     const uint8_t *addr = seq + (q0 >> 1);
     uintptr_t a = reinterpret_cast<uintptr_t>(addr);
     const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
@@ -212,47 +233,70 @@ __device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {
     uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
     uint32_t lo = __funnelshift_r(w0, w1, sh);          // bytes 0..3
     uint32_t b4 = (w1 >> sh) & 0xFFu;                   // byte 4
-    // BAM stores the first base of a byte in the high nibble: swap nibbles inside bytes
-    uint32_t s_lo = ((lo & 0x0F0F0F0Fu) << 4) | ((lo >> 4) & 0x0F0F0F0Fu);
-    uint32_t s_b4 = ((b4 & 0x0Fu) << 4) | (b4 >> 4);
-    return __funnelshift_r(s_lo, s_b4, (uint32_t)(q0 & 1) * 4);
+    return keep_acgt(__funnelshift_r(swap_nibbles(lo), swap_nibbles(b4), (uint32_t)(q0 & 1) * 4));
 }
-
-// nibble mask covering nibble indices [lo, hi), 0 <= lo < hi <= 8
-__device__ __forceinline__ uint32_t nibble_mask(int lo, int hi) {
-    uint32_t m = hi >= 8 ? 0xFFFFFFFFu : ((1u << (4 * hi)) - 1u);
-    return m & ~((1u << (4 * lo)) - 1u);
-}
+// mask of the low n nibbles (n <= 0: none, n >= 8: all)
+__device__ __forceinline__ uint32_t low_nibbles(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(4 * n, 0)); }
 
 #define FUZ_STRIP 512          // words of the per-warp sliding output window (2 KB)
+#define FUZ_QWIN 512           // words of the per-warp SEQ window (2 KB = 4096 bases)
 
-// flush the window [strip_base, strip_base + FUZ_STRIP) to the record's projection and clear it
-__device__ __forceinline__ void strip_flush(uint32_t *strip, uint32_t *__restrict__ out, int strip_base, int n_words, int lane) {
+struct ProjWarp {              // per-warp state of k_project
+    uint32_t *strip;           // [FUZ_STRIP] output window, words strip_base .. strip_base + FUZ_STRIP
+    uint32_t *qwin;            // [FUZ_QWIN + 8] SEQ window: swapped + ACGT-only nibbles, query nibble qw_base + 8 * i at word i
+    uint32_t *out;             // the record's projection
+    const uint8_t *seq;
+    int strip_base, n_words4, qw_base, seq_nib_end, lane;
+};
+
+// flush the output window to the record's projection (128-bit stores) and clear it
+__device__ __forceinline__ void strip_flush(ProjWarp &P) {
     __syncwarp();
-#pragma unroll 4
-    for (int j = lane; j < FUZ_STRIP; j += 32) {
-        int w = strip_base + j;
-        if (w < n_words) out[w] = strip[j];
-        strip[j] = 0;
+    uint4 *s4 = reinterpret_cast<uint4 *>(P.strip);
+    uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
+#pragma unroll
+    for (int j = P.lane; j < FUZ_STRIP / 4; j += 32) {
+        int w = P.strip_base + 4 * j;
+        if (w < P.n_words4) o4[w >> 2] = s4[j];
+        s4[j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+}
+
+// (re)load the SEQ window so that it starts at (the 16-byte line holding) query nibble q_lo
+__device__ __forceinline__ void qwin_load(ProjWarp &P, int q_lo) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(P.seq + (q_lo >> 1)) & ~(uintptr_t)15;
+    const uint8_t *wa = reinterpret_cast<const uint8_t *>(a);
+    P.qw_base = (int)(wa - P.seq) * 2;
+    const uint8_t *seq_end = P.seq + ((P.seq_nib_end + 1) >> 1);
+    __syncwarp();
+#pragma unroll
+    for (int j = P.lane; j < FUZ_QWIN / 4; j += 32) {
+        const uint8_t *src = wa + 16 * j;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src < seq_end) v = __ldg(reinterpret_cast<const uint4 *>(src));
+        v.x = keep_acgt(swap_nibbles(v.x)); v.y = keep_acgt(swap_nibbles(v.y));
+        v.z = keep_acgt(swap_nibbles(v.z)); v.w = keep_acgt(swap_nibbles(v.w));
+        reinterpret_cast<uint4 *>(P.qwin)[j] = v;
     }
     __syncwarp();
 }
 
 // Place the segments held by the lanes (seg_len > 0 marks a lane with a segment: reference
-// start seg_rs, query start seg_qs) into the projection: all (segment, word) pairs of the
-// chunk are flattened over the 32 lanes; the segment of an item is found by a shuffle
-// binary search over the inclusive word-count prefix.
-__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, const uint8_t *seq,
-                                               uint32_t *strip, uint32_t *__restrict__ out, int &strip_base,
-                                               int n_words, int lane) {
-    const int wf = (seg_rs >> 3) - W0;
-    const int nw = seg_len > 0 ? ((seg_rs + seg_len - 1) >> 3) - (seg_rs >> 3) + 1 : 0;
-    const int pinc = fuz_warp_incl_scan(nw, lane);
-    const int pexc = pinc - nw;
-    const int wtot = __shfl_sync(0xffffffffu, pinc, 31);
-    for (int b0 = 0; b0 < wtot; b0 += 32) {
+// start seg_rs, query start seg_qs) into the projection.  Work items are (segment, quad)
+// pairs -- a quad = 4 consecutive projection words = 32 reference positions -- flattened
+// over the 32 lanes; the segment of an item is found by a shuffle binary search over the
+// inclusive quad-count prefix.
+__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
+    const int lane = P.lane;
+    const int qf = ((seg_rs >> 3) - W0) >> 2;
+    const int nq = seg_len > 0 ? ((((seg_rs + seg_len - 1) >> 3) - W0) >> 2) - qf + 1 : 0;
+    const int pinc = fuz_warp_incl_scan(nq, lane);
+    const int pexc = pinc - nq;
+    const int qtot = __shfl_sync(0xffffffffu, pinc, 31);
+    for (int b0 = 0; b0 < qtot; b0 += 32) {
         const int i = b0 + lane;
-        const bool act = i < wtot;
+        const bool act = i < qtot;
         int idx = 0;                                    // first lane with pinc > i
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
@@ -263,30 +307,58 @@ __device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_
         const int o_len = __shfl_sync(0xffffffffu, seg_len, idx);
         const int o_qs = __shfl_sync(0xffffffffu, seg_qs, idx);
         const int o_pe = __shfl_sync(0xffffffffu, pexc, idx);
-        const int o_wf = __shfl_sync(0xffffffffu, wf, idx);
-        const int W = o_wf + (i - o_pe);               // word of the record's projection
-        const int pw = (W0 + W) << 3;                   // first global position of the word
-        const int a = max(o_rs, pw), b = min(o_rs + o_len, pw + 8);
-        uint32_t v = 0;
-        if (act) v = fetch8(seq, o_qs + (pw - o_rs)) & nibble_mask(a - pw, b - pw);
-        const bool full = b - a == 8;
+        const int o_qf = __shfl_sync(0xffffffffu, qf, idx);
+        const int Q = o_qf + (i - o_pe);               // quad of the record's projection
+        const int pq = (W0 + 4 * Q) << 3;              // first global position of the quad
+        const int la = max(o_rs, pq) - pq, lb = min(o_rs + o_len, pq + 32) - pq;   // covered nibbles [la, lb)
+        const int q0 = o_qs + (pq - o_rs);             // query nibble of the quad's first position
+        // SEQ window: the quad reads query nibbles [q0, q0 + 40)
+        const int need_lo = __reduce_min_sync(0xffffffffu, act ? q0 + la : 0x7fffffff);
+        const int need_hi = __reduce_max_sync(0xffffffffu, act ? q0 + lb : -0x7fffffff);
+        if (need_lo - 32 < P.qw_base || need_hi + 8 > P.qw_base + 8 * FUZ_QWIN) qwin_load(P, max(need_lo - 32, -32));
+        uint32_t v[4] = {0, 0, 0, 0};
+        if (act) {
+            const int rel = q0 - P.qw_base;
+            if (rel >= 0 && rel + 40 <= 8 * FUZ_QWIN) {
+                const uint32_t *m = P.qwin + (rel >> 3);
+                const uint32_t sh = (uint32_t)(rel & 7) * 4;
+                uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4];
+                v[0] = __funnelshift_r(m0, m1, sh); v[1] = __funnelshift_r(m1, m2, sh);
+                v[2] = __funnelshift_r(m2, m3, sh); v[3] = __funnelshift_r(m3, m4, sh);
+            } else {                                    // span larger than the window (huge insertion): global path
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (la < 8 * k + 8 && lb > 8 * k) v[k] = fetch8(P.seq, q0 + 8 * k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] &= low_nibbles(lb - 8 * k) & ~low_nibbles(la - 8 * k);
+        }
+        const bool full = la == 0 && lb == 32;
+        const int W = 4 * Q;
         bool done = !act;
         for (;;) {
-            if (!done && W < strip_base + FUZ_STRIP) {
-                // a fully covered word belongs to one segment only; words shared by two
-                // segments (around an insertion / short deletion) are OR-merged
-                if (full) strip[W - strip_base] = v; else atomicOr(&strip[W - strip_base], v);
+            if (!done && W < P.strip_base + FUZ_STRIP) {
+                uint32_t *dst = P.strip + (W - P.strip_base);
+                // a fully covered quad belongs to one segment only; quads shared by two
+                // segments (around an insertion / deletion) are OR-merged
+                if (full) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (v[k]) atomicOr(dst + k, v[k]);
+                }
                 done = true;
             }
             if (__all_sync(0xffffffffu, done)) break;
-            strip_flush(strip, out, strip_base, n_words, lane);
-            strip_base += FUZ_STRIP;
+            strip_flush(P);
+            P.strip_base += FUZ_STRIP;
             // skip windows that no remaining item touches (long deletions): all zero
             int min_w = __reduce_min_sync(0xffffffffu, done ? 0x7fffffff : W);
-            while (min_w >= strip_base + FUZ_STRIP) {
-                for (int j = lane; j < FUZ_STRIP; j += 32)
-                    if (strip_base + j < n_words) out[strip_base + j] = 0;
-                strip_base += FUZ_STRIP;
+            while (min_w >= P.strip_base + FUZ_STRIP) {
+                uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
+                for (int j = lane; j < FUZ_STRIP / 4; j += 32)
+                    if (P.strip_base + 4 * j < P.n_words4) o4[(P.strip_base >> 2) + j] = make_uint4(0, 0, 0, 0);
+                P.strip_base += FUZ_STRIP;
             }
         }
     }
@@ -295,17 +367,25 @@ __device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_
 // One warp per accepted record walks the CIGAR 32 ops at a time (prefix positions by warp
 // scans), merges runs of M/=/X into match segments (S/I/D break a run; N/H/P do nothing)
 // and writes the read in REFERENCE coordinates, aligned to the global 8-position grid:
-// proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as BAM 4-bit codes,
-// 0 where the read has no base (outside the alignment, deletions).
+// proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
+// G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
+// SEQ is staged through a per-warp shared-memory window (coalesced 128-bit loads, nibble
+// swap and ACGT filter once per word); the output goes through a per-warp shared-memory
+// window flushed with 128-bit stores.
 __global__ void __launch_bounds__(256) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec, HetScratch S, fuz_status *st) {
     if (st->error) return;
-    __shared__ uint32_t strips[8][FUZ_STRIP];
-    const int lane = threadIdx.x & 31;
-    uint32_t *strip = strips[threadIdx.x >> 5];
+    __shared__ __align__(16) uint32_t strips[8][FUZ_STRIP];
+    __shared__ __align__(16) uint32_t qwins[8][FUZ_QWIN + 8];
+    ProjWarp P;
+    P.lane = threadIdx.x & 31;
+    P.strip = strips[threadIdx.x >> 5];
+    P.qwin = qwins[threadIdx.x >> 5];
+    const int lane = P.lane;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = lane; j < FUZ_STRIP; j += 32) strip[j] = 0;
+    for (int j = lane; j < FUZ_STRIP; j += 32) P.strip[j] = 0;
+    for (int j = lane; j < FUZ_QWIN + 8; j += 32) P.qwin[j] = 0;
     __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     for (int r = warp_g; r < n_rec; r += n_warps) {
@@ -316,11 +396,14 @@ __global__ void __launch_bounds__(256) k_project(
         const int n_cig = fuz_ld_u32_un(rec + 16) & 0xFFFF;
         const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
         const uint8_t *cig = rec + 36 + l_name;
-        const uint8_t *seq = rec_buf + S.r_seq[r];
         const int gstart = S.r_gstart[r];
         const int W0 = gstart >> 3;
-        uint32_t *out = S.proj + S.r_woff[r];
-        int strip_base = 0;
+        P.seq = rec_buf + S.r_seq[r];
+        P.seq_nib_end = l_seq;
+        P.out = S.proj + S.r_woff[r];
+        P.n_words4 = n_words;                  // padded to a multiple of 4 by the record scan
+        P.strip_base = 0;
+        P.qw_base = -0x40000000;               // nothing staged yet
         int carry_rp = gstart, carry_qp = 0;
         bool open = false, overrun = false;
         int open_rs = 0, open_qs = 0;
@@ -352,7 +435,8 @@ __global__ void __launch_bounds__(256) k_project(
             const int rs_s = __shfl_sync(0xffffffffu, rp0, src);
             const int qs_s = __shfl_sync(0xffffffffu, qp0, src);
             const int seg_rs = sm ? rs_s : open_rs, seg_qs = sm ? qs_s : open_qs;
-            place_segments(seg_rs, ends_here ? rp0 - seg_rs : 0, seg_qs, W0, seq, strip, out, strip_base, n_words, lane);
+            if (__any_sync(0xffffffffu, overrun)) break;     // bad record: stop before reading past SEQ
+            place_segments(seg_rs, ends_here ? rp0 - seg_rs : 0, seg_qs, W0, P);
             const int last_m_all = mmask ? 31 - __clz(mmask) : -1;
             const int last_b_all = bmask ? 31 - __clz(bmask) : -1;
             // the run open at the end of the chunk starts at the first start after the last breaker
@@ -369,25 +453,45 @@ __global__ void __launch_bounds__(256) k_project(
             carry_rp += __shfl_sync(0xffffffffu, rinc, 31);
             carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
         }
+        overrun = __any_sync(0xffffffffu, overrun);
         // the run still open at the end of the CIGAR
-        place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, seq, strip, out, strip_base,
-                       n_words, lane);
-        strip_flush(strip, out, strip_base, n_words, lane);
-        if (__any_sync(0xffffffffu, overrun)) {
-            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
-        }
+        if (!overrun) place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, P);
+        strip_flush(P);
+        if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
     }
 }
 
 // ---------------------------------------------------------------- tiled pileup (default)
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#define FUZ_FA(a, b, c, s, cy) do { s = xor3(a, b, c); cy = maj3(a, b, c); } while (0)
+
+// count of base b at position i from the 8 bit planes of the vertical counters
+__device__ __forceinline__ uint32_t plane_count(const uint32_t (&acc)[8], int bit) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v |= ((acc[k] >> bit) & 1u) << k;
+    return v;
+}
+
 // One CTA per 2048-position tile, one thread per 8-position word.  Every read overlapping
 // the tile contributes one ALIGNED word load per thread (no shifting: the projection is on
-// the global grid); bases are counted bit-sliced: 4-bit lanes for up to 15 reads, widened
-// into 16-bit counters held in registers.  No atomics, no shared-memory histogram.
+// the global grid, one-hot A/C/G/T nibbles).  Counting is bit-sliced *vertically*: 15 words
+// are reduced by a carry-save adder tree (11 full adders = 22 LOP3) to a 4-bit number per
+// (position, base) bit, which is rippled into 8 bit planes held in registers (depth <= 255
+// between spills into 16-bit counters).  No atomics, no shared-memory histogram.
 __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S, int64_t cap_sites,
                                                                     uint32_t *__restrict__ counts_out, fuz_status *st) {
     if (st->error) return;
-    __shared__ int l_off[FUZ_TILE_THREADS], l_w0[FUZ_TILE_THREADS], l_nw[FUZ_TILE_THREADS];
+    __shared__ int4 l_ent[FUZ_TILE_THREADS];             // x = word offset of the projection, y = first word, z = words
     __shared__ int s_warp_tot[FUZ_NW];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -396,13 +500,14 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S
     const int Wt = (t0 >> 3) + tid;                       // my word on the global grid
     const int rlo = S.tile_rlo[tile], rhi = S.tile_rhi[tile];
     const uint32_t *__restrict__ proj = S.proj;
-    // c16[b][j]: 16-bit counters of base b for positions 2j (low half) and 2j+1 (high half)
-    uint32_t c16[4][4];
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};           // bit planes of the per-(position, base) counters
+    uint32_t c16[4][4];                                   // spill: 16-bit counters, base b, positions 2j / 2j+1
 #pragma unroll
     for (int b = 0; b < 4; b++)
 #pragma unroll
         for (int j = 0; j < 4; j++) c16[b][j] = 0;
-    int n_reads_seen = 0;
+    int n_reads_seen = 0, groups_in_acc = 0;
+    bool spilled = false;
     for (int cb = rlo; cb < rhi; cb += FUZ_TILE_THREADS) {
         // compact the records overlapping the tile (any order: only counts matter here)
         const int r = cb + tid;
@@ -413,58 +518,81 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S
         int off = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < FUZ_NW; w++) { int v = s_warp_tot[w]; if (w < warp) off += v; tot += v; }
-        if (ok) {
-            int slot = off + __popc(m & ((1u << lane) - 1u));
-            l_off[slot] = S.r_woff[r]; l_w0[slot] = S.r_gstart[r] >> 3; l_nw[slot] = S.r_nwords[r];
-        }
+        if (ok) l_ent[off + __popc(m & ((1u << lane) - 1u))] = make_int4(S.r_woff[r], S.r_gstart[r] >> 3, S.r_nwords[r], 0);
         __syncthreads();
         n_reads_seen += tot;
-        for (int g = 0; g < tot; g += FUZ_NSLOT) {
-            const int ns = min(FUZ_NSLOT, tot - g);
-            uint32_t w[FUZ_NSLOT];
+        for (int g = 0; g < tot; g += 15) {
+            const int ns = min(15, tot - g);
+            uint32_t x[15];
 #pragma unroll
-            for (int s = 0; s < FUZ_NSLOT; s++) {
-                w[s] = 0;
+            for (int s = 0; s < 15; s++) {
+                x[s] = 0;
                 if (s < ns) {
-                    const int j = Wt - l_w0[g + s];
-                    if ((unsigned)j < (unsigned)l_nw[g + s]) w[s] = __ldg(proj + l_off[g + s] + j);
+                    const int4 e = l_ent[g + s];
+                    const int j = Wt - e.y;
+                    if ((unsigned)j < (unsigned)e.z) x[s] = __ldg(proj + e.x + j);
                 }
             }
-            // count: 4-bit lanes, at most FUZ_NSLOT (<= 15) increments per lane per round
-            uint32_t c4[4] = {0, 0, 0, 0};
-            const uint32_t M = 0x11111111u;
+            // carry-save adder tree: 15 one-bit inputs per bit position -> 4-bit count
+            uint32_t s0, s1, s2, s3, s4, s5, k0, k1, k2, k3, k4, k5, k6, ones, t0_, t1_, d0, d1, d2, twos, fours, eights;
+            FUZ_FA(x[0], x[1], x[2], s0, k0); FUZ_FA(x[3], x[4], x[5], s1, k1); FUZ_FA(x[6], x[7], x[8], s2, k2);
+            FUZ_FA(x[9], x[10], x[11], s3, k3); FUZ_FA(x[12], x[13], x[14], s4, k4);
+            FUZ_FA(s0, s1, s2, s5, k5); FUZ_FA(s3, s4, s5, ones, k6);
+            FUZ_FA(k0, k1, k2, t0_, d0); FUZ_FA(k3, k4, k5, t1_, d1); FUZ_FA(t0_, t1_, k6, twos, d2);
+            FUZ_FA(d0, d1, d2, fours, eights);
+            // ripple the 4-bit number into the 8 planes
+            uint32_t cy = acc[0] & ones; acc[0] ^= ones;
+            uint32_t nc = maj3(acc[1], twos, cy); acc[1] = xor3(acc[1], twos, cy); cy = nc;
+            nc = maj3(acc[2], fours, cy); acc[2] = xor3(acc[2], fours, cy); cy = nc;
+            nc = maj3(acc[3], eights, cy); acc[3] = xor3(acc[3], eights, cy); cy = nc;
 #pragma unroll
-            for (int s = 0; s < FUZ_NSLOT; s++) {
-                const uint32_t x = w[s];
-                uint32_t p0 = x & M, p1 = (x >> 1) & M, p2 = (x >> 2) & M, p3 = (x >> 3) & M;
-                const uint32_t sum = p0 + p1 + p2 + p3;
-                const uint32_t multi = ((sum >> 1) | (sum >> 2)) & M;   // codes with 2+ bits (M R S V W Y H K D B N)
-                if (multi) { p0 &= ~multi; p1 &= ~multi; p2 &= ~multi; p3 &= ~multi; }
-                c4[0] += p0; c4[1] += p1; c4[2] += p2; c4[3] += p3;     // A=1 C=2 G=4 T=8
-            }
+            for (int k = 4; k < 8; k++) { nc = acc[k] & cy; acc[k] ^= cy; cy = nc; }
+            if (++groups_in_acc == 17) {                 // 17 * 15 = 255: planes are full, spill to 16-bit counters
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t x = c4[b];
-                c16[b][0] += (x & 0xFu) | ((x & 0xF0u) << 12);
-                c16[b][1] += ((x >> 8) & 0xFu) | ((x & 0xF000u) << 4);
-                c16[b][2] += ((x >> 16) & 0xFu) | ((x >> 4) & 0xF0000u);
-                c16[b][3] += ((x >> 24) & 0xFu) | ((x >> 12) & 0xF0000u);
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) c16[b][i >> 1] += plane_count(acc, 4 * i + b) << ((i & 1) * 16);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = 0;
+                groups_in_acc = 0;
+                spilled = true;
             }
         }
         __syncthreads();
     }
     if (n_reads_seen > 65535 && tid == 0) fuz_raise(st, FUZ_E_DEPTH, tile);
+    const int pos_limit = S.tile_limit[tile];
     uint32_t cnt[8][4];
+    uint32_t hetmask = 0;
+    if (!spilled && !counts_out) {
+        // a het site needs two bases with count >= 3 (second allele > 25 % of a depth >= 10):
+        // test that on the planes and extract counts only for the few candidate positions
+        const uint32_t ge3 = (acc[0] & acc[1]) | acc[2] | acc[3] | acc[4] | acc[5] | acc[6] | acc[7];
+        const uint32_t two = (ge3 & (ge3 >> 1) & 0x77777777u) | (ge3 & (ge3 >> 2) & 0x33333333u) | (ge3 & (ge3 >> 3) & 0x11111111u);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 8; i++) {
 #pragma unroll
-        for (int b = 0; b < 4; b++) cnt[i][b] = (c16[b][i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
-    if (counts_out) {
-        uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
+            for (int b = 0; b < 4; b++) cnt[i][b] = 0;
+            if ((two >> (4 * i)) & 7u) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+                for (int b = 0; b < 4; b++) cnt[i][b] = plane_count(acc, 4 * i + b);
+                if (t0 + tid * 8 + i < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                cnt[i][b] = ((c16[b][i >> 1] >> ((i & 1) * 16)) & 0xFFFFu) + plane_count(acc, 4 * i + b);
+        if (counts_out) {
+            uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+        }
+        hetmask = het_mask_of(cnt, t0, pos_limit);
     }
-    emit_tile_sites(cnt, tile, t0, S.tile_limit[tile], S, cap_sites, st, s_warp_tot, &s_base);
+    emit_tile_sites(hetmask, cnt, tile, t0, S, cap_sites, st, s_warp_tot, &s_base);
 }
 
 // ---------------------------------------------------------------- cross-check pileup (impl 1)
@@ -525,7 +653,7 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
         uint4 v = in[i];
         cnt[i][0] = v.x; cnt[i][1] = v.y; cnt[i][2] = v.z; cnt[i][3] = v.w;
     }
-    emit_tile_sites(cnt, tile, t0, S.tile_limit[tile], S, cap_sites, st, s_warp_tot, &s_base);
+    emit_tile_sites(het_mask_of(cnt, t0, S.tile_limit[tile]), cnt, tile, t0, S, cap_sites, st, s_warp_tot, &s_base);
 }
 
 // ---------------------------------------------------------------- ordered sites + rows
@@ -622,7 +750,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     // words of the projection: one per 8 aligned reference positions.  SEQ holds 2 bases per
     // byte, so rec_bytes / 4 words cover every M/=/X base; deletions add to the span and are
     // checked on the device (FUZ_E_CAPACITY, index 6).
-    const int64_t proj_cap = in->rec_bytes / 4 + 2 * (int64_t)n_rec + 64;
+    const int64_t proj_cap = in->rec_bytes / 4 + 5 * (int64_t)n_rec + 64;
     if (proj_cap > 0x7fffffffLL) return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (projection exceeds 2^31 words)");
     HetScratch S;
     FuzLayout L;
@@ -643,6 +771,8 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (need_counts) o_counts = L.add(16 * (size_t)in->total_glen);
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
+    int32_t *keep_row_off; uint8_t *keep_dup;
+    if ((rc = fuz_keep_commit(ctx, cap_sites, out->cap_vmap, &keep_row_off, &keep_dup))) return rc;
     S.r_gstart = fuz_at<int32_t>(ctx, o_gstart); S.r_gend = fuz_at<int32_t>(ctx, o_gend);
     S.r_nwords = fuz_at<int32_t>(ctx, o_nw); S.r_woff = fuz_at<int32_t>(ctx, o_woff);
     S.r_seq = fuz_at<int64_t>(ctx, o_rseq); S.r_flags = fuz_at<uint8_t>(ctx, o_flags);
@@ -654,14 +784,16 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.tile_site_off = fuz_at<int32_t>(ctx, o_toff);
     S.us_gpos = fuz_at<int32_t>(ctx, o_usg); S.us_cnt = fuz_at<uint32_t>(ctx, o_usc);
     S.s_gpos = fuz_at<int32_t>(ctx, o_sg); S.site_rows = fuz_at<int32_t>(ctx, o_srow);
-    S.site_row_off = fuz_at<int32_t>(ctx, o_sroff);
+    S.site_row_off = keep_row_off;       // also the first input of the association stage
+    (void)o_sroff;
     S.counts = out->d_counts ? out->d_counts : (need_counts ? fuz_at<uint32_t>(ctx, o_counts) : nullptr);
     S.n_tiles = n_tiles;
 
     k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, n_ctg);
     FUZ_LAUNCH_CHECK(ctx, "k_het_init");
     if (n_rec > 0) {
-        k_scan_records<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
+        const int scan_blocks = std::min((n_rec + 7) / 8, 148 * 32);      // one record per warp in flight
+        k_scan_records<<<scan_blocks, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
                                                          in->d_ctg_goff, n_ctg, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_scan_records");
     }

@@ -23,6 +23,10 @@ struct fuz_ctx {
     // scratch arena (device), grown on demand, reused across calls
     uint8_t *arena = nullptr;
     size_t arena_cap = 0;
+    // small device buffer that survives from one stage to the next inside fuz_phase_batch
+    // (row range of every site, duplicate flags of the variant_map rows)
+    uint8_t *keep = nullptr;
+    size_t keep_cap = 0;
     // status block
     fuz_status *d_status = nullptr;
     fuz_status *h_status = nullptr;   // pinned
@@ -30,6 +34,11 @@ struct fuz_ctx {
     int pileup_impl = 0;
     int64_t max_pairs_per_site = 96;
     bool phase_attr_set = false;
+    // per-launch profile (diagnostics): an event after every kernel launch
+    bool profile = false;
+    cudaEvent_t prof_start = nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> prof_marks;
+    size_t prof_used = 0;
     // timing of the dominant kernel
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -54,7 +63,10 @@ int fuz_fail(fuz_ctx *ctx, int code, const char *fmt, ...);
         cudaError_t e_ = cudaGetLastError();                                             \
         if (e_ != cudaSuccess)                                                           \
             return fuz_fail((ctx), FUZ_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+        if ((ctx)->profile) fuz_profile_mark((ctx), name);                               \
     } while (0)
+
+void fuz_profile_mark(fuz_ctx *ctx, const char *name);
 
 // Bump layout over the context arena: add() all buffers, then commit() (grows the arena
 // if needed; growing synchronises the stream) and resolve pointers with at().
@@ -67,6 +79,8 @@ struct FuzLayout {
     }
 };
 int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l);
+// inter-stage buffer: row_off [cap_sites + 2] int32, dup [cap_vmap + 1] uint8
+int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup);
 template <typename T>
 static inline T *fuz_at(fuz_ctx *ctx, size_t off) { return reinterpret_cast<T *>(ctx->arena + off); }
 

@@ -25,15 +25,6 @@ __global__ void k_site_rowoff(const int32_t *__restrict__ vm_site, int32_t *__re
         row_off[s] = s == n_sites ? n_vmap : fuz_lower_bound(vm_site, 0, n_vmap, s);
 }
 
-// first site index of every contig
-__global__ void k_ctg_siteoff(const int32_t *__restrict__ site_ctg, int n_ctg, int32_t *__restrict__ ctg_site_off,
-                              const fuz_status *st) {
-    if (st->error) return;
-    const int n_sites = (int)st->n_sites;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= n_ctg; c += gridDim.x * blockDim.x)
-        ctg_site_off[c] = c == n_ctg ? n_sites : fuz_lower_bound(site_ctg, 0, n_sites, c);
-}
-
 // One warp per site.  dup[i] = an earlier row of the same (site, allele) carries the same
 // q_id (the reference builds set(qids): phasing.py:189, :448-449).
 __global__ void __launch_bounds__(256) k_dup_flags(const int32_t *__restrict__ row_off, const uint8_t *__restrict__ vm_base,
@@ -59,6 +50,7 @@ __global__ void __launch_bounds__(256) k_dup_flags(const int32_t *__restrict__ r
 // ================================================================== association table
 struct AssocScratch {
     int32_t *row_off, *uq, *uq_n, *na0, *qmin, *qmax, *cand_cnt, *cand_off, *at_cnt, *at_off;
+    const int32_t *site_ctg, *site_pos;
     int4 *pair_ct;
     uint8_t *dup;
     int64_t max_pairs;
@@ -92,7 +84,7 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
         }
         bad = __any_sync(0xffffffffu, bad);
         if (bad || c0 == 0 || c0 == n) {          // a site must carry exactly two alleles
-            if (lane == 0) fuz_raise(st, FUZ_E_FORMAT, s);
+            if (lane == 0) { fuz_raise(st, FUZ_E_FORMAT, s); A.cand_cnt[s] = 0; }
             continue;
         }
         // rank of every non-duplicate q among the non-duplicates of its allele
@@ -107,25 +99,17 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
         }
         if (lane == 0) {
             A.na0[s] = c0; A.uq_n[2 * s] = u0; A.uq_n[2 * s + 1] = u1; A.qmin[s] = mn; A.qmax[s] = mx;
+            // number of later sites of the same contig within 65536 bp (phasing.py:166-170)
+            const int c = A.site_ctg[s];
+            const long long lim = (long long)A.site_pos[s] + (1 << 16);
+            int lo = s + 1, hi = n_sites;                // first index with (ctg,pos) > (c, lim)
+            while (lo < hi) {
+                int m = (lo + hi) >> 1;
+                bool le = A.site_ctg[m] < c || (A.site_ctg[m] == c && (long long)A.site_pos[m] <= lim);
+                if (le) lo = m + 1; else hi = m;
+            }
+            A.cand_cnt[s] = lo - s - 1;
         }
-    }
-}
-
-// number of later sites of the same contig within 65536 bp (phasing.py:166-170)
-__global__ void k_cand_count(const int32_t *__restrict__ site_ctg, const int32_t *__restrict__ site_pos, AssocScratch A,
-                             const fuz_status *st) {
-    if (st->error) return;
-    const int n_sites = (int)st->n_sites;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_sites; s += gridDim.x * blockDim.x) {
-        const int c = site_ctg[s];
-        const long long lim = (long long)site_pos[s] + (1 << 16);
-        int lo = s + 1, hi = n_sites;                // first index with (ctg,pos) > (c, lim)
-        while (lo < hi) {
-            int m = (lo + hi) >> 1;
-            bool le = site_ctg[m] < c || (site_ctg[m] == c && (long long)site_pos[m] <= lim);
-            if (le) lo = m + 1; else hi = m;
-        }
-        A.cand_cnt[s] = lo - s - 1;
     }
 }
 
@@ -218,14 +202,20 @@ __device__ __forceinline__ int row_d(const int32_t *__restrict__ at_ct, int row)
     return (c.x + c.w) - (c.y + c.z);
 }
 
-__global__ void k_blk_init(BlockScratch B, const fuz_status *st) {
+// zero the counters; first site of every contig; row range of every site as left site
+__global__ void k_blk_init(BlockScratch B, fuz_outputs O, int n_ctg, const fuz_status *st) {
     if (st->error) return;
-    const int n_sites = (int)st->n_sites;
+    const int n_sites = (int)st->n_sites, n_at = (int)st->n_atable;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
         B.left_cnt[s] = 0;
         B.bsize[s] = 0;
         if (s < n_sites) B.left_cur[s] = 0;
+        B.right_off[s] = s == n_sites ? n_at : fuz_lower_bound(O.d_at_s1, 0, n_at, s);
+        if (s <= n_ctg) B.ctg_site_off[s] = s == n_ctg ? n_sites : fuz_lower_bound(O.d_site_ctg, 0, n_sites, s);
     }
+    // n_ctg may exceed n_sites + 1
+    for (int c = n_sites + 1 + blockIdx.x * blockDim.x + threadIdx.x; c <= n_ctg; c += gridDim.x * blockDim.x)
+        B.ctg_site_off[c] = c == n_ctg ? n_sites : fuz_lower_bound(O.d_site_ctg, 0, n_sites, c);
 }
 
 // accepted rows |cis - trans| >= 6 (phasing.py:245) -> in-degree of the right site
@@ -255,23 +245,6 @@ __global__ void k_edge_fill(BlockScratch B, fuz_outputs O, fuz_status *st) {
         if (abs(d) >= 6) {
             int k = B.left_off[s2] + atomicAdd(&B.left_cur[s2], 1);
             B.lq[k] = s1; B.ld[k] = d;
-        }
-    }
-}
-
-// per site: row range as left site; list slot of the smallest left partner
-__global__ void k_site_prep(BlockScratch B, fuz_outputs O, const fuz_status *st) {
-    if (st->error) return;
-    const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
-        B.right_off[s] = s == n_sites ? n_at : fuz_lower_bound(O.d_at_s1, 0, n_at, s);
-        if (s < n_sites) {
-            int best = -1, best_s1 = 0x7fffffff;
-            for (int k = B.left_off[s]; k < B.left_off[s + 1]; k++) {
-                int s1 = B.lq[k];
-                if (s1 < best_s1) { best_s1 = s1; best = k; }
-            }
-            B.min_k[s] = best;
         }
     }
 }
@@ -327,8 +300,10 @@ __device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   /
 
 // One CTA per contig: pass-1 forest + pointer jumping, pass-2 sweep, pass-3 extents and
 // scores, pass-4 block chaining (phasing.py:240-408; parallel forms of SURVEY.md A.3).
-// Phase bits of the contig live in shared memory; the left adjacency is staged there too
-// when it fits, so the inherently sequential sweep runs at shared-memory latency.
+// Everything the passes touch (left / right adjacency, positions, forest pointers, phase
+// bits) is staged into shared memory with one parallel load phase when it fits, so the
+// inherently sequential sweep and the pointer chasing run at shared-memory latency.
+// Contigs too large for that (> ~10^4 sites) fall back to global memory for the adjacency.
 __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B, fuz_outputs O, fuz_status *st) {
     if (st->error) return;
     extern __shared__ uint32_t smem[];
@@ -338,72 +313,98 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     const int n = cs1 - cs0;
     if (n <= 0) return;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    const int e0 = B.left_off[cs0], n_e = B.left_off[cs1] - e0;
+    const int e0 = B.left_off[cs0], n_e = B.left_off[cs1] - e0;         // accepted left edges of the contig
+    const int r0 = B.right_off[cs0], n_r = B.right_off[cs1] - r0;       // atable rows of the contig
     const int nbw = (n + 31) >> 5;
     if ((size_t)nbw * 4 > FUZ_PHASE_SMEM) { if (tid == 0) fuz_raise(st, FUZ_E_CAPACITY, 5); return; }
+    // shared-memory layout (words): bits | loff | lq | ld | roff | rq | rd | pos | fp
+    const size_t need = (size_t)nbw + (n + 1) + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + n;
+    const bool staged = need * 4 <= FUZ_PHASE_SMEM;
     uint32_t *sbits = smem;                                   // [nbw] phase bit per site
-    const bool staged = (size_t)nbw * 4 + (size_t)(n + 1) * 4 + (size_t)n_e * 8 <= FUZ_PHASE_SMEM;
-    int *s_off = reinterpret_cast<int *>(smem + nbw);         // [n + 1] (staged only)
-    int *s_q = s_off + n + 1, *s_d = s_q + n_e;               // [n_e] each (staged only)
-    volatile uint32_t *fp = B.fp;
+    int *s_loff = reinterpret_cast<int *>(smem + nbw);        // [n + 1] left CSR offsets (relative to e0)
+    int *s_lq = s_loff + n + 1, *s_ld = s_lq + n_e;           // [n_e] partner (contig-local), cis - trans
+    int *s_roff = s_ld + n_e;                                 // [n + 1] right row offsets (relative to r0)
+    int *s_rq = s_roff + n + 1, *s_rd = s_rq + n_r;           // [n_r] partner (contig-local), cis - trans (0: rejected row)
+    int *s_pos = s_rd + n_r;                                  // [n] 1-based positions
+    volatile uint32_t *s_fp = reinterpret_cast<uint32_t *>(s_pos + n);   // [n] forest pointers (contig-local)
+    for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
+    if (staged) {
+        for (int i = tid; i <= n; i += nt) { s_loff[i] = B.left_off[cs0 + i] - e0; s_roff[i] = B.right_off[cs0 + i] - r0; }
+        for (int k = tid; k < n_e; k += nt) { s_lq[k] = B.lq[e0 + k] - cs0; s_ld[k] = B.ld[e0 + k]; }
+        for (int k = tid; k < n_r; k += nt) {
+            int d = row_d(O.d_at_ct, r0 + k);
+            s_rq[k] = O.d_at_s2[r0 + k] - cs0; s_rd[k] = abs(d) >= 6 ? d : 0;
+        }
+        for (int i = tid; i < n; i += nt) s_pos[i] = O.d_site_pos[cs0 + i];
+    }
+    __syncthreads();
+    // accessors (contig-local indices)
+    auto loff = [&](int i) { return staged ? s_loff[i] : B.left_off[cs0 + i] - e0; };
+    auto lq = [&](int k) { return staged ? s_lq[k] : B.lq[e0 + k] - cs0; };
+    auto ld = [&](int k) { return staged ? s_ld[k] : B.ld[e0 + k]; };
+    auto roff = [&](int i) { return staged ? s_roff[i] : B.right_off[cs0 + i] - r0; };
+    auto rq = [&](int k) { return staged ? s_rq[k] : O.d_at_s2[r0 + k] - cs0; };
+    auto rd = [&](int k) { if (staged) return s_rd[k]; int d = row_d(O.d_at_ct, r0 + k); return abs(d) >= 6 ? d : 0; };
+    auto pos_of = [&](int i) { return staged ? s_pos[i] : O.d_site_pos[cs0 + i]; };
+    volatile uint32_t *fp = staged ? s_fp : reinterpret_cast<volatile uint32_t *>(B.fp + cs0);
+    // smallest left partner of site i (slot in the left list), -1 if none
+    auto min_left = [&](int i, int &d_out) {
+        int best = -1, bq = 0x7fffffff;
+        for (int k = loff(i); k < loff(i + 1); k++) { int q = lq(k); if (q < bq) { bq = q; best = k; } }
+        d_out = best >= 0 ? ld(best) : 0;
+        return best >= 0 ? bq : -1;
+    };
     // ---- pass 1 as a forest (rows are ordered by (site1, site2), ties impossible)
-    for (int x = cs0 + tid; x < cs1; x += nt) {
-        int parent = x, bit = 0;
+    for (int i = tid; i < n; i += nt) {
+        int parent = i, bit = 0, d;
         bool in_pos = false;
-        int mk = B.min_k[x];
-        if (mk >= 0) {
+        int ml = min_left(i, d);
+        if (ml >= 0) {
             in_pos = true;
-            parent = B.lq[mk];
-            bit = B.ld[mk] < 0;                                // trans > cis flips the state
+            parent = ml;
+            bit = d < 0;                                       // trans > cis flips the state
         } else {
-            for (int r = B.right_off[x]; r < B.right_off[x + 1]; r++) {
-                int d = row_d(O.d_at_ct, r);
-                if (abs(d) < 6) continue;
+            for (int k = roff(i); k < roff(i + 1); k++) {
+                int dr = rd(k);
+                if (dr == 0) continue;
                 in_pos = true;                                 // first accepted row = smallest right partner
-                int rm = O.d_at_s2[r];
-                int mkr = B.min_k[rm];
-                // partner already has a state when x is first touched iff it has a left partner < x
-                if (mkr >= 0 && B.lq[mkr] < x) { parent = rm; bit = d < 0; }
+                int rm = rq(k), d2;
+                int mlr = min_left(rm, d2);
+                // partner already has a state when i is first touched iff it has a left partner < i
+                if (mlr >= 0 && mlr < i) { parent = rm; bit = dr < 0; }
                 break;
             }
         }
-        fp[x] = ((uint32_t)parent << 1) | (uint32_t)bit;
-        O.d_ph_state[x] = in_pos ? 0 : 255;
-    }
-    for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
-    if (staged) {
-        for (int i = tid; i <= n; i += nt) s_off[i] = B.left_off[cs0 + i] - e0;
-        for (int k = tid; k < n_e; k += nt) { s_q[k] = B.lq[e0 + k] - cs0; s_d[k] = B.ld[e0 + k]; }
+        fp[i] = ((uint32_t)parent << 1) | (uint32_t)bit;
+        O.d_ph_state[cs0 + i] = in_pos ? 0 : 255;
     }
     __syncthreads();
     int rounds = 1;
     while ((1 << rounds) < n) rounds++;
     rounds++;
     for (int it = 0; it < rounds; it++) {
-        for (int x = cs0 + tid; x < cs1; x += nt) {
-            uint32_t me = fp[x];
+        for (int i = tid; i < n; i += nt) {
+            uint32_t me = fp[i];
             int p = (int)(me >> 1);
-            if (p != x) {
+            if (p != i) {
                 uint32_t pp = fp[p];
-                fp[x] = (pp & ~1u) | ((me ^ pp) & 1u);
+                fp[i] = (pp & ~1u) | ((me ^ pp) & 1u);
             }
         }
         __syncthreads();
     }
-    for (int x = cs0 + tid; x < cs1; x += nt)
-        if (O.d_ph_state[x] != 255 && (fp[x] & 1u)) atomicOr(&sbits[(x - cs0) >> 5], 1u << ((x - cs0) & 31));
+    for (int i = tid; i < n; i += nt)
+        if (O.d_ph_state[cs0 + i] != 255 && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
     __syncthreads();
     // ---- pass 2: one left-to-right sweep (a second sweep never changes anything)
     if (warp == 0) {
         volatile uint32_t *vb = sbits;
         for (int i = 0; i < n; i++) {
-            int l0, l1;
-            if (staged) { l0 = s_off[i]; l1 = s_off[i + 1]; } else { l0 = B.left_off[cs0 + i] - e0; l1 = B.left_off[cs0 + i + 1] - e0; }
+            const int l0 = loff(i), l1 = loff(i + 1);
             if (l0 == l1) continue;
             int s0 = 0;                                         // score(state 0) - score(state 1)
             for (int k = l0 + lane; k < l1; k += 32) {
-                int q, d;
-                if (staged) { q = s_q[k]; d = s_d[k]; } else { q = B.lq[e0 + k] - cs0; d = B.ld[e0 + k]; }
+                int q = lq(k), d = ld(k);
                 s0 += ((vb[q >> 5] >> (q & 31)) & 1u) ? -d : d;
             }
             s0 = __reduce_add_sync(0xffffffffu, s0);
@@ -416,27 +417,28 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     }
     __syncthreads();
     // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
-    for (int x = cs0 + warp; x < cs1; x += nwarps) {
+    for (int i = warp; i < n; i += nwarps) {
+        const int x = cs0 + i;
         const bool in_pos = O.d_ph_state[x] != 255;
-        const int px = O.d_site_pos[x];
+        const int px = pos_of(i);
         int lscore = 0, rscore = 0, lext = px, rext = px;
         if (in_pos) {
-            const uint32_t sx = (sbits[(x - cs0) >> 5] >> ((x - cs0) & 31)) & 1u;
-            for (int k = B.left_off[x] + lane; k < B.left_off[x + 1]; k += 32) {
-                int q = B.lq[k], d = B.ld[k];
-                uint32_t sq = (sbits[(q - cs0) >> 5] >> ((q - cs0) & 31)) & 1u;
+            const uint32_t sx = (sbits[i >> 5] >> (i & 31)) & 1u;
+            for (int k = loff(i) + lane; k < loff(i + 1); k += 32) {
+                int q = lq(k), d = ld(k);
+                uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
                 int dd = sq == sx ? d : -d;
                 lscore += dd;
-                if (dd > 0) lext = min(lext, O.d_site_pos[q]);
+                if (dd > 0) lext = min(lext, pos_of(q));
             }
-            for (int r = B.right_off[x] + lane; r < B.right_off[x + 1]; r += 32) {
-                int d = row_d(O.d_at_ct, r);
-                if (abs(d) < 6) continue;
-                int q = O.d_at_s2[r];
-                uint32_t sq = (sbits[(q - cs0) >> 5] >> ((q - cs0) & 31)) & 1u;
+            for (int k = roff(i) + lane; k < roff(i + 1); k += 32) {
+                int d = rd(k);
+                if (d == 0) continue;
+                int q = rq(k);
+                uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
                 int dd = sq == sx ? d : -d;
                 rscore += dd;
-                if (dd > 0) rext = max(rext, O.d_site_pos[q]);
+                if (dd > 0) rext = max(rext, pos_of(q));
             }
             lscore = __reduce_add_sync(0xffffffffu, lscore); rscore = __reduce_add_sync(0xffffffffu, rscore);
             lext = __reduce_min_sync(0xffffffffu, lext); rext = __reduce_max_sync(0xffffffffu, rext);
@@ -566,35 +568,37 @@ __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_st
 }  // namespace
 
 // ------------------------------------------------------------------ host side
-int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
+int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row_off_valid) {
     (void)n_ctg;
     cudaStream_t st = ctx->stream;
     const int64_t cs = out->cap_sites, cv = out->cap_vmap;
     AssocScratch A;
     A.max_pairs = ctx->max_pairs_per_site * (cs > 0 ? cs : 1);
     FuzLayout L;
-    size_t o_roff = L.add(4 * (size_t)(cs + 2)), o_uq = L.add(4 * (size_t)(cv + 1)), o_uqn = L.add(8 * (size_t)(cs + 1));
+    size_t o_uq = L.add(4 * (size_t)(cv + 1)), o_uqn = L.add(8 * (size_t)(cs + 1));
     size_t o_na0 = L.add(4 * (size_t)(cs + 1)), o_qmin = L.add(4 * (size_t)(cs + 1)), o_qmax = L.add(4 * (size_t)(cs + 1));
     size_t o_cc = L.add(4 * (size_t)(cs + 2)), o_co = L.add(4 * (size_t)(cs + 2));
     size_t o_ac = L.add(4 * (size_t)(cs + 2)), o_ao = L.add(4 * (size_t)(cs + 2));
-    size_t o_pc = L.add(16 * (size_t)(A.max_pairs + 1)), o_dup = L.add((size_t)cv + 1);
+    size_t o_pc = L.add(16 * (size_t)(A.max_pairs + 1));
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
-    A.row_off = fuz_at<int32_t>(ctx, o_roff); A.uq = fuz_at<int32_t>(ctx, o_uq); A.uq_n = fuz_at<int32_t>(ctx, o_uqn);
+    if ((rc = fuz_keep_commit(ctx, cs, cv, &A.row_off, &A.dup))) return rc;
+    A.site_ctg = out->d_site_ctg; A.site_pos = out->d_site_pos;
+    A.uq = fuz_at<int32_t>(ctx, o_uq); A.uq_n = fuz_at<int32_t>(ctx, o_uqn);
     A.na0 = fuz_at<int32_t>(ctx, o_na0); A.qmin = fuz_at<int32_t>(ctx, o_qmin); A.qmax = fuz_at<int32_t>(ctx, o_qmax);
     A.cand_cnt = fuz_at<int32_t>(ctx, o_cc); A.cand_off = fuz_at<int32_t>(ctx, o_co);
     A.at_cnt = fuz_at<int32_t>(ctx, o_ac); A.at_off = fuz_at<int32_t>(ctx, o_ao);
-    A.pair_ct = fuz_at<int4>(ctx, o_pc); A.dup = fuz_at<uint8_t>(ctx, o_dup);
+    A.pair_ct = fuz_at<int4>(ctx, o_pc);
     const int64_t *d_ns = &ctx->d_status->n_sites;
 
-    k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, A.row_off, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
+    if (!row_off_valid) {
+        k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, A.row_off, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
+    }
     k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A.row_off, out->d_vm_base, out->d_vm_qid, A.dup, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
     k_uniq_lists<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
-    k_cand_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_ctg, out->d_site_pos, A, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_cand_count");
     if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, FUZ_FIN_PAIRS, A.max_pairs))) return rc;
     k_pair_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
@@ -623,43 +627,41 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;
     }
-    k_ctg_siteoff<<<(n_ctg + 256) / 256, 256, 0, st>>>(out->d_site_ctg, n_ctg, B.ctg_site_off, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_ctg_siteoff");
-    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, ctx->d_status);
+    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, n_ctg, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
     k_edge_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
     if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, FUZ_FIN_NONE, 0))) return rc;
     k_edge_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
-    k_site_prep<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_site_prep");
     k_ctg_phase<<<n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_ctg_phase");
     return FUZ_OK;
 }
 
-int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out) {
+int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
+                   bool dup_valid) {
     cudaStream_t st = ctx->stream;
     const int64_t cs = out->cap_sites, cv = out->cap_vmap;
     ReadScratch R;
     R.total_nq = total_nq;
     FuzLayout L;
-    size_t o_roff = L.add(4 * (size_t)(cs + 2)), o_cq = L.add(4 * (size_t)(n_ctg + 2));
+    size_t o_cq = L.add(4 * (size_t)(n_ctg + 2));
     size_t o_qc = L.add(4 * (size_t)(total_nq + 2)), o_qo = L.add(4 * (size_t)(total_nq + 2)), o_qcur = L.add(4 * (size_t)(total_nq + 1));
     size_t o_qe = L.add(4 * (size_t)(cv + 1)), o_pc = L.add(4 * (size_t)(total_nq + 2)), o_po = L.add(4 * (size_t)(total_nq + 2));
-    size_t o_dup = L.add((size_t)cv + 1);
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
-    R.row_off = fuz_at<int32_t>(ctx, o_roff); R.ctg_q_off = fuz_at<int32_t>(ctx, o_cq);
+    if ((rc = fuz_keep_commit(ctx, cs, cv, &R.row_off, &R.dup))) return rc;
+    R.ctg_q_off = fuz_at<int32_t>(ctx, o_cq);
     R.q_cnt = fuz_at<int32_t>(ctx, o_qc); R.q_off = fuz_at<int32_t>(ctx, o_qo); R.q_cur = fuz_at<int32_t>(ctx, o_qcur);
     R.q_ent = fuz_at<int32_t>(ctx, o_qe); R.pr_cnt = fuz_at<int32_t>(ctx, o_pc); R.pr_off = fuz_at<int32_t>(ctx, o_po);
-    R.dup = fuz_at<uint8_t>(ctx, o_dup);
     if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, R.row_off, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
-    k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
+    if (!dup_valid) {
+        k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, R.row_off, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
+        k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
+    }
     k_rd_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R);
     FUZ_LAUNCH_CHECK(ctx, "k_rd_init");
     k_q_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
@@ -685,7 +687,7 @@ extern "C" int fuz_association_table(fuz_ctx *ctx, int32_t n_ctg, int64_t n_site
     if (!ctx || !out || n_sites < 0 || n_vmap < 0 || n_sites > out->cap_sites || n_vmap > out->cap_vmap)
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_association_table: bad arguments");
     int rc = set_counts(ctx, n_sites, n_vmap, 0);
-    return rc ? rc : fuz_association_impl(ctx, n_ctg, out);
+    return rc ? rc : fuz_association_impl(ctx, n_ctg, out, false);
 }
 
 extern "C" int fuz_phased_blocks(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, int64_t n_atable, fuz_outputs *out) {
@@ -701,5 +703,5 @@ extern "C" int fuz_phased_reads(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ct
         n_vmap > out->cap_vmap)
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_phased_reads: bad arguments");
     int rc = set_counts(ctx, n_sites, n_vmap, -1);
-    return rc ? rc : fuz_reads_impl(ctx, n_ctg, d_ctg_nq, total_nq, out);
+    return rc ? rc : fuz_reads_impl(ctx, n_ctg, d_ctg_nq, total_nq, out, false);
 }

@@ -281,6 +281,19 @@ class Engine:
         _lib.check(self.ctx, lib().fuz_get_kernel_timing(self.ctx, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile(self, enable: bool) -> None:
+        _lib.check(self.ctx, lib().fuz_profile(self.ctx, int(enable)))
+
+    def profile_report(self):
+        """[(kernel name, ms)] for every launch since profile(True)."""
+        buf = C.create_string_buffer(1 << 20)
+        lib().fuz_profile_report(self.ctx, buf, len(buf))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.split("\t")
+            out.append((name, float(ms)))
+        return out
+
     # ---- device-resident path
     def upload(self, pb: PreparedBatch) -> DeviceBatch:
         db = DeviceBatch(pb, self.device)

@@ -140,6 +140,10 @@ int64_t fuz_launch_count(fuz_ctx *ctx);
  * milliseconds and launch count (synchronises).  Used by bench.py's roofline block.    */
 int fuz_kernel_timing(fuz_ctx *ctx, int enable);
 int fuz_get_kernel_timing(fuz_ctx *ctx, double *h_ms_total, int64_t *h_launches);
+/* Diagnostics: per-launch device time.  fuz_profile(ctx, 1) starts a capture (an event is
+ * recorded after every kernel launch); fuz_profile_report writes "kernel\tms" lines. */
+int fuz_profile(fuz_ctx *ctx, int enable);
+int64_t fuz_profile_report(fuz_ctx *ctx, char *buf, int64_t cap);
 
 /* ---- stages (asynchronous on the context stream; check with fuz_get_status) ---- */
 /* phasing.py:14-134: record scan + filter, pileup, het call, variant_map rows.
