@@ -220,7 +220,7 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 // million entries; the scan is never the dominant kernel.  The tail of the scan also
 // publishes the total into the status block (row counts + capacity checks), which saves
 // one tiny kernel launch per scan.
-#define SCAN_PER_THREAD 8
+#define SCAN_PER_THREAD 32
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                    int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
                                                    int64_t fin_cap, fuz_status *st) {
@@ -233,19 +233,27 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
     long long carry_s = 0;                        // replicated in every thread
     int buf = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    // a chunk = 32768 elements: every thread owns 32 consecutive ones (8 x 128-bit loads in
+    // flight), so arrays up to 32 K entries (sites, tiles, records, reads of a C2-size batch)
+    // need one memory round trip and one barrier
     for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD, buf ^= 1) {
         int v[SCAN_PER_THREAD];
         int s = 0;
         const int64_t i0 = base + (int64_t)tid * SCAN_PER_THREAD;
-        if (vec_ok && i0 + SCAN_PER_THREAD <= n) {
-            const int4 a = *reinterpret_cast<const int4 *>(in + i0), b = *reinterpret_cast<const int4 *>(in + i0 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+        if (i0 < n) {
+            if (vec_ok && i0 + SCAN_PER_THREAD <= n) {
 #pragma unroll
-            for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
+                for (int k = 0; k < SCAN_PER_THREAD; k += 4) {
+                    const int4 a = *reinterpret_cast<const int4 *>(in + i0 + k);
+                    v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < SCAN_PER_THREAD; k++) s += v[k];
         }
-#pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; k++) s += v[k];
         const int incl = fuz_warp_incl_scan(s, lane);
         if (lane == 31) warp_tot[buf][warp] = incl;
         __syncthreads();
@@ -253,11 +261,13 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
         const int ti = fuz_warp_incl_scan(t, lane);
         const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
         const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
-        long long excl = carry_s + wexcl + (incl - s);
+        if (i0 < n) {
+            long long excl = carry_s + wexcl + (incl - s);
 #pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; k++) {
-            if (i0 + k < n) out[i0 + k] = (int32_t)excl;
-            excl += v[k];
+            for (int k = 0; k < SCAN_PER_THREAD; k++) {
+                if (i0 + k < n) out[i0 + k] = (int32_t)excl;
+                excl += v[k];
+            }
         }
         carry_s += chunk_total;
     }

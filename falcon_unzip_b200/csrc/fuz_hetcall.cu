@@ -33,91 +33,9 @@ __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_m
         st->error = 0; st->error_index = 0;
         st->n_sites = st->n_vmap = st->n_atable = st->n_reads = 0;
         st->need_sites = st->need_vmap = st->need_atable = st->need_reads = st->need_pairs = 0;
-        st->n_accepted = 0; st->aligned_bases = 0; st->n_segments = 0;
+        st->n_accepted = 0; st->aligned_bases = 0; st->n_segments = 0; st->reserved[0] = 0;
     }
     for (; i < n_ctg; i += gridDim.x * blockDim.x) { ctg_last_rec[i] = -1; ctg_maxspan[i] = 0; }
-}
-
-// ---------------------------------------------------------------- record scan
-// One warp per record, one pass over the CIGAR: totals for the filter (phasing.py:63-75),
-// reference span (M/=/X/D advance the reference; N/H/P advance nothing, the quirk of
-// phasing.py:77-96), number of 8-position words the record touches on the global grid.
-__global__ void __launch_bounds__(256) k_scan_records(
-    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
-    const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg,
-    HetScratch S, fuz_status *st) {
-    const int lane = threadIdx.x & 31;
-    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    long long acc_aligned = 0, acc_accepted = 0;
-    for (int r = warp_g; r < n_rec; r += n_warps) {
-        // issue every independent load first: offsets, then this and the previous header
-        const int64_t off_r = rec_off[r], off_n = rec_off[r + 1], off_p = r > 0 ? rec_off[r - 1] : 0;
-        const uint8_t *rec = rec_buf + off_r;
-        const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
-        const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
-        const uint32_t w12 = fuz_ld_u32_un(rec + 12);     // l_read_name, mapq, bin
-        const uint32_t w16 = fuz_ld_u32_un(rec + 16);     // n_cigar_op, flag
-        const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
-        const int32_t prev_pos = r > 0 ? (int32_t)fuz_ld_u32_un(rec_buf + off_p + 8) : 0;
-        // contig of the record = position of r in ctg_rec_off (records grouped by contig)
-        const int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
-        const int l_name = w12 & 0xFF;
-        const int n_cig = w16 & 0xFFFF;
-        const uint8_t *cig = rec + 36 + l_name;
-        const int64_t seq_off = off_r + 36 + l_name + 4 * (int64_t)n_cig;
-        if (lane == 0) {
-            S.r_flags[r] = 0; S.r_nwords[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_seq[r] = seq_off;
-        }
-        if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 || off_n - off_r != (int64_t)block_size + 4 ||
-            36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4) {
-            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
-            continue;
-        }
-        const int64_t gstart64 = ctg_goff[c] + pos;
-        // coordinate order inside the contig
-        if (lane == 0 && r > ctg_rec_off[c] && prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
-        long long total = 0, skip = 0, aligned = 0, span = 0;
-        bool badop = false;
-#pragma unroll 4
-        for (int k = lane; k < n_cig; k += 32) {
-            uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
-            uint32_t len = cw >> 4, op = cw & 15;
-            if (op > 8) badop = true;
-            total += len;
-            if (op == 4) skip += len;
-            if (op_is_match(op)) { aligned += len; span += len; }
-            if (op == 2) span += len;
-        }
-        total = fuz_warp_sum64(total);
-        skip = fuz_warp_sum64(skip);
-        aligned = fuz_warp_sum64(aligned);
-        span = fuz_warp_sum64(span);
-        badop = __any_sync(0xffffffffu, badop);
-        if (badop || total == 0 || gstart64 + span > 0x7fffffffLL) {   // unknown op / ZeroDivisionError :72
-            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
-            continue;
-        }
-        // phasing.py:72-75 in IEEE double, same operation order as the reference
-        const bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
-        const int32_t gstart = (int32_t)gstart64;
-        if (lane == 0) {
-            S.r_gstart[r] = gstart;
-            S.r_gend[r] = accept ? gstart + (int32_t)span : gstart;
-            S.r_flags[r] = accept ? 1 : 0;
-            // words of the projection, padded to whole quads (128-bit flushes)
-            S.r_nwords[r] = (accept && span > 0) ? (int32_t)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
-            if (accept) {
-                atomicMax(&S.ctg_last_rec[c], r);
-                atomicMax(&S.ctg_maxspan[c], (int32_t)span);
-                acc_aligned += aligned; acc_accepted += 1;
-            }
-        }
-    }
-    if (lane == 0 && acc_accepted) {
-        atomicAdd((unsigned long long *)&st->aligned_bases, (unsigned long long)acc_aligned);
-        atomicAdd((unsigned long long *)&st->n_accepted, (unsigned long long)acc_accepted);
-    }
 }
 
 // candidate record range, contig and evaluation limit of every pileup tile.  The limit is
@@ -217,8 +135,11 @@ __device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {      // BAM: firs
 }
 // zero every nibble that is not one of A=1 C=2 G=4 T=8 (ambiguity codes never count as a
 // base in the pileup, phasing.py:108-111, and never match a called allele)
+__device__ __forceinline__ uint32_t multi_bits(uint32_t x) {     // non-zero inside nibbles with 2+ bits set
+    return (x & (x >> 1) & 0x77777777u) | (x & (x >> 2) & 0x33333333u) | (x & (x >> 3) & 0x11111111u);
+}
 __device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
-    uint32_t any = (x & (x >> 1) & 0x77777777u) | (x & (x >> 2) & 0x33333333u) | (x & (x >> 3) & 0x11111111u);
+    uint32_t any = multi_bits(x);
     if (any) {
         uint32_t f = (any | (any >> 1) | (any >> 2)) & 0x11111111u;
         x &= ~(f * 15u);
@@ -275,8 +196,10 @@ __device__ __forceinline__ void qwin_load(ProjWarp &P, int q_lo) {
         const uint8_t *src = wa + 16 * j;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (src < seq_end) v = __ldg(reinterpret_cast<const uint4 *>(src));
-        v.x = keep_acgt(swap_nibbles(v.x)); v.y = keep_acgt(swap_nibbles(v.y));
-        v.z = keep_acgt(swap_nibbles(v.z)); v.w = keep_acgt(swap_nibbles(v.w));
+        v.x = swap_nibbles(v.x); v.y = swap_nibbles(v.y); v.z = swap_nibbles(v.z); v.w = swap_nibbles(v.w);
+        if (multi_bits(v.x) | multi_bits(v.y) | multi_bits(v.z) | multi_bits(v.w)) {   // ambiguity codes: rare
+            v.x = keep_acgt(v.x); v.y = keep_acgt(v.y); v.z = keep_acgt(v.z); v.w = keep_acgt(v.w);
+        }
         reinterpret_cast<uint4 *>(P.qwin)[j] = v;
     }
     __syncwarp();
@@ -364,17 +287,31 @@ __device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_
     }
 }
 
-// One warp per accepted record walks the CIGAR 32 ops at a time (prefix positions by warp
-// scans), merges runs of M/=/X into match segments (S/I/D break a run; N/H/P do nothing)
-// and writes the read in REFERENCE coordinates, aligned to the global 8-position grid:
+// sum of a 64-bit quantity (< 2^48) over the warp with three 16-bit-limb REDUX adds
+__device__ __forceinline__ long long warp_sum48(long long v) {
+    unsigned long long u = (unsigned long long)v;
+    unsigned a = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0xFFFFu));
+    unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 16) & 0xFFFFu));
+    unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 32) & 0xFFFFu));
+    return (long long)((unsigned long long)a + ((unsigned long long)b << 16) + ((unsigned long long)c << 32));
+}
+
+// One warp per record.
+// Pass 1 (every record): one sweep over the CIGAR for the filter of phasing.py:63-75 (total
+// and soft-clipped length, IEEE double like the reference) and the reference span (M/=/X/D
+// advance the reference; N/H/P advance nothing, the quirk of phasing.py:77-96); record
+// validation; space for the projection is claimed with one atomic add.
+// Pass 2 (accepted records): walks the CIGAR 32 ops at a time (prefix positions by warp
+// scans), merges runs of M/=/X into match segments (S/I/D break a run) and writes the read
+// in REFERENCE coordinates, aligned to the global 8-position grid:
 // proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
 // G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
 // SEQ is staged through a per-warp shared-memory window (coalesced 128-bit loads, nibble
 // swap and ACGT filter once per word); the output goes through a per-warp shared-memory
 // window flushed with 128-bit stores.
 __global__ void __launch_bounds__(256) k_project(
-    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec, HetScratch S, fuz_status *st) {
-    if (st->error) return;
+    const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
+    const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
     __shared__ __align__(16) uint32_t strips[8][FUZ_STRIP];
     __shared__ __align__(16) uint32_t qwins[8][FUZ_QWIN + 8];
     ProjWarp P;
@@ -388,20 +325,83 @@ __global__ void __launch_bounds__(256) k_project(
     for (int j = lane; j < FUZ_QWIN + 8; j += 32) P.qwin[j] = 0;
     __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
+    long long acc_aligned = 0, acc_accepted = 0;
     for (int r = warp_g; r < n_rec; r += n_warps) {
-        const int n_words = S.r_nwords[r];
-        if (!S.r_flags[r] || n_words == 0) continue;
-        const uint8_t *rec = rec_buf + rec_off[r];
-        const int l_name = fuz_ld_u32_un(rec + 12) & 0xFF;
-        const int n_cig = fuz_ld_u32_un(rec + 16) & 0xFFFF;
+        // ---- pass 1: issue every independent load first: offsets, then this and the previous header
+        const int64_t off_r = rec_off[r], off_n = rec_off[r + 1], off_p = r > 0 ? rec_off[r - 1] : 0;
+        const uint8_t *rec = rec_buf + off_r;
+        const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
+        const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
+        const uint32_t w12 = fuz_ld_u32_un(rec + 12);     // l_read_name, mapq, bin
+        const uint32_t w16 = fuz_ld_u32_un(rec + 16);     // n_cigar_op, flag
         const int32_t l_seq = (int32_t)fuz_ld_u32_un(rec + 20);
+        const int32_t prev_pos = r > 0 ? (int32_t)fuz_ld_u32_un(rec_buf + off_p + 8) : 0;
+        // contig of the record = position of r in ctg_rec_off (records grouped by contig)
+        const int c = fuz_upper_bound(ctg_rec_off, 0, n_ctg + 1, r) - 1;
+        const int l_name = w12 & 0xFF;
+        const int n_cig = w16 & 0xFFFF;
         const uint8_t *cig = rec + 36 + l_name;
-        const int gstart = S.r_gstart[r];
+        const int64_t seq_off = off_r + 36 + l_name + 4 * (int64_t)n_cig;
+        if (lane == 0) {
+            S.r_flags[r] = 0; S.r_nwords[r] = 0; S.r_gstart[r] = 0; S.r_gend[r] = 0; S.r_woff[r] = 0;
+        }
+        if (c < 0 || c >= n_ctg || pos < 0 || l_seq < 0 || off_n - off_r != (int64_t)block_size + 4 ||
+            36 + l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)block_size + 4) {
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+            continue;
+        }
+        const int64_t gstart64 = ctg_goff[c] + pos;
+        // coordinate order inside the contig
+        if (lane == 0 && r > ctg_rec_off[c] && prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
+        long long total = 0, skip = 0, aligned = 0, span = 0;
+        bool badop = false;
+#pragma unroll 4
+        for (int k = lane; k < n_cig; k += 32) {
+            uint32_t cw = fuz_ld_u32_un(cig + 4 * k);
+            uint32_t len = cw >> 4, op = cw & 15;
+            if (op > 8) badop = true;
+            total += len;
+            if (op == 4) skip += len;
+            if (op_is_match(op)) { aligned += len; span += len; }
+            if (op == 2) span += len;
+        }
+        total = warp_sum48(total); skip = warp_sum48(skip); aligned = warp_sum48(aligned); span = warp_sum48(span);
+        badop = __any_sync(0xffffffffu, badop);
+        if (badop || total == 0 || gstart64 + span > 0x7fffffffLL) {   // unknown op / ZeroDivisionError :72
+            if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+            continue;
+        }
+        // phasing.py:72-75 in IEEE double, same operation order as the reference
+        const bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
+        const int gstart = (int)gstart64;
+        // words of the projection, padded to whole quads (128-bit flushes)
+        const int n_words = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
+        int woff = 0;
+        if (lane == 0) {
+            S.r_gstart[r] = gstart;
+            S.r_gend[r] = accept ? gstart + (int32_t)span : gstart;
+            S.r_flags[r] = accept ? 1 : 0;
+            S.r_nwords[r] = n_words;
+            if (accept) {
+                atomicMax(&S.ctg_last_rec[c], r);
+                atomicMax(&S.ctg_maxspan[c], (int32_t)span);
+                acc_aligned += aligned; acc_accepted += 1;
+            }
+            if (n_words) {
+                long long o = (long long)atomicAdd((unsigned long long *)&st->reserved[0], (unsigned long long)n_words);
+                if (o + n_words > S.proj_cap) { fuz_raise(st, FUZ_E_CAPACITY, 6); o = -1; }
+                woff = (int)o;
+                S.r_woff[r] = woff < 0 ? 0 : woff;
+            }
+        }
+        woff = __shfl_sync(0xffffffffu, woff, 0);
+        if (n_words == 0 || woff < 0) continue;
+        // ---- pass 2: projection
         const int W0 = gstart >> 3;
-        P.seq = rec_buf + S.r_seq[r];
+        P.seq = rec_buf + seq_off;
         P.seq_nib_end = l_seq;
-        P.out = S.proj + S.r_woff[r];
-        P.n_words4 = n_words;                  // padded to a multiple of 4 by the record scan
+        P.out = S.proj + woff;
+        P.n_words4 = n_words;
         P.strip_base = 0;
         P.qw_base = -0x40000000;               // nothing staged yet
         int carry_rp = gstart, carry_qp = 0;
@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(256) k_project(
         if (!overrun) place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, P);
         strip_flush(P);
         if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
+    }
+    if (lane == 0 && acc_accepted) {
+        atomicAdd((unsigned long long *)&st->aligned_bases, (unsigned long long)acc_aligned);
+        atomicAdd((unsigned long long *)&st->n_accepted, (unsigned long long)acc_accepted);
     }
 }
 
@@ -791,16 +795,6 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
 
     k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, n_ctg);
     FUZ_LAUNCH_CHECK(ctx, "k_het_init");
-    if (n_rec > 0) {
-        const int scan_blocks = std::min((n_rec + 7) / 8, 148 * 32);      // one record per warp in flight
-        k_scan_records<<<scan_blocks, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
-                                                         in->d_ctg_goff, n_ctg, S, ctx->d_status);
-        FUZ_LAUNCH_CHECK(ctx, "k_scan_records");
-    }
-    if ((rc = fuz_scan_i32(ctx, S.r_nwords, S.r_woff, n_rec, nullptr, FUZ_FIN_PROJ, proj_cap))) return rc;
-    k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
-
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->timing) {
         if (ctx->timing_used == ctx->timing_events.size()) {
@@ -816,9 +810,12 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S, ctx->d_status);
+            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+                                                       n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");
         }
+        k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
         k_pileup_gather<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S, cap_sites, out->d_counts, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
@@ -826,13 +823,16 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, S, ctx->d_status);
-            FUZ_LAUNCH_CHECK(ctx, "k_project");      // the variant_map rows still come from the projection
+            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+                                                       n_ctg, S, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_project");      // filter + the projection the variant_map rows come from
             k_pileup_atomic<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
                                                               in->d_ctg_goff, n_ctg, S, S.counts, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_pileup_atomic");
         }
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
+        k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
         k_het_from_counts<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }

@@ -57,46 +57,76 @@ struct AssocScratch {
 };
 
 // sorted unique q_id lists per (site, allele): uq[row_off[s] ..) for allele al0 and
-// uq[row_off[s] + na0[s] ..) for allele al1, lengths uq_n[2s], uq_n[2s+1].
+// uq[row_off[s] + na0[s] ..) for allele al1, lengths uq_n[2s], uq_n[2s+1]; duplicate flags
+// of the rows (an earlier row of the same (site, allele) carries the same q_id: the
+// reference builds set(qids), phasing.py:189, :448-449).  One warp per site; the rows of a
+// site (depth many, a few dozen) are staged in shared memory and every lane ranks its own
+// rows against all of them.
+#define FUZ_UQ_ROWS 256
 __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ site_al, const uint8_t *__restrict__ vm_base,
                                                     const int32_t *__restrict__ vm_qid, AssocScratch A, fuz_status *st) {
     if (st->error) return;
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_q[8][FUZ_UQ_ROWS];
+    __shared__ uint8_t s_b[8][FUZ_UQ_ROWS], s_d[8][FUZ_UQ_ROWS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_sites = (int)st->n_sites;
+    int *sq = s_q[wib];
+    uint8_t *sb = s_b[wib], *sd = s_d[wib];
     for (int s = warp_g; s < n_sites; s += n_warps) {
         const int off = A.row_off[s], n = A.row_off[s + 1] - off;
         const uint8_t al0 = site_al[2 * s], al1 = site_al[2 * s + 1];
-        int c0 = 0, u0 = 0, u1 = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
+        const bool in_smem = n <= FUZ_UQ_ROWS;
+        int c0 = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
         bool bad = al0 == al1 || al0 > 3 || al1 > 3;
+        __syncwarp();
         for (int i = lane; i < n; i += 32) {
-            uint8_t b = vm_base[off + i];
-            int q = vm_qid[off + i];
+            const uint8_t b = vm_base[off + i];
+            const int q = vm_qid[off + i];
+            if (in_smem) { sq[i] = q; sb[i] = b; }
             if (b != al0 && b != al1) bad = true;
             c0 += b == al0;
-            if (!A.dup[off + i]) { u0 += b == al0; u1 += b == al1; }
             mn = min(mn, q); mx = max(mx, q);
         }
-        c0 = fuz_warp_sum(c0); u0 = fuz_warp_sum(u0); u1 = fuz_warp_sum(u1);
-        for (int d = 16; d > 0; d >>= 1) {
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-        }
+        __syncwarp();
+        c0 = __reduce_add_sync(0xffffffffu, c0);
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
         bad = __any_sync(0xffffffffu, bad);
         if (bad || c0 == 0 || c0 == n) {          // a site must carry exactly two alleles
             if (lane == 0) { fuz_raise(st, FUZ_E_FORMAT, s); A.cand_cnt[s] = 0; }
             continue;
         }
-        // rank of every non-duplicate q among the non-duplicates of its allele
+        // phase A: duplicate flag of every row (kept in shared memory for phase B)
         for (int i = lane; i < n; i += 32) {
-            if (A.dup[off + i]) continue;
-            const uint8_t b = vm_base[off + i];
-            const int q = vm_qid[off + i];
-            int rank = 0;
-            for (int j = 0; j < n; j++)
-                rank += (!A.dup[off + j] && vm_base[off + j] == b && vm_qid[off + j] < q);
-            A.uq[off + (b == al0 ? 0 : c0) + rank] = q;
+            const int q = in_smem ? sq[i] : vm_qid[off + i];
+            const uint8_t b = in_smem ? sb[i] : vm_base[off + i];
+            bool dup = false;
+            for (int j = 0; j < i; j++) {
+                const int qj = in_smem ? sq[j] : vm_qid[off + j];
+                const uint8_t bj = in_smem ? sb[j] : vm_base[off + j];
+                if (qj == q && bj == b) { dup = true; break; }
+            }
+            A.dup[off + i] = dup ? 1 : 0;
+            if (in_smem) sd[i] = dup ? 1 : 0;
         }
+        __syncwarp();
+        // phase B: slot of every first occurrence in the sorted unique list of its allele
+        int u0 = 0, u1 = 0;
+        for (int i = lane; i < n; i += 32) {
+            if (in_smem ? sd[i] : A.dup[off + i]) continue;
+            const int q = in_smem ? sq[i] : vm_qid[off + i];
+            const uint8_t b = in_smem ? sb[i] : vm_base[off + i];
+            int rank = 0;
+            for (int j = 0; j < n; j++) {
+                const int qj = in_smem ? sq[j] : vm_qid[off + j];
+                const uint8_t bj = in_smem ? sb[j] : vm_base[off + j];
+                const uint8_t dj = in_smem ? sd[j] : A.dup[off + j];
+                rank += (!dj && bj == b && qj < q);
+            }
+            A.uq[off + (b == al0 ? 0 : c0) + rank] = q;
+            if (b == al0) u0++; else u1++;
+        }
+        u0 = __reduce_add_sync(0xffffffffu, u0); u1 = __reduce_add_sync(0xffffffffu, u1);
         if (lane == 0) {
             A.na0[s] = c0; A.uq_n[2 * s] = u0; A.uq_n[2 * s + 1] = u1; A.qmin[s] = mn; A.qmax[s] = mx;
             // number of later sites of the same contig within 65536 bp (phasing.py:166-170)
@@ -396,23 +426,46 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     for (int i = tid; i < n; i += nt)
         if (O.d_ph_state[cs0 + i] != 255 && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
     __syncthreads();
-    // ---- pass 2: one left-to-right sweep (a second sweep never changes anything)
+    // ---- pass 2: one left-to-right sweep (a second sweep never changes anything).
+    // Sequential by construction; one warp walks the sites.  The critical path per site is
+    // kept in registers: the states of the last 32 sites live in a warp-uniform bit window
+    // (`recent`), the adjacency of the next site is prefetched, the vote is one REDUX.
     if (warp == 0) {
         volatile uint32_t *vb = sbits;
+        uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
+        int l0n = loff(0), l1n = loff(1);
+        int qn = l0n + lane < l1n ? lq(l0n + lane) : -1, dn = l0n + lane < l1n ? ld(l0n + lane) : 0;
+        uint32_t ownn = (vb[0] >> 0) & 1u;
         for (int i = 0; i < n; i++) {
-            const int l0 = loff(i), l1 = loff(i + 1);
-            if (l0 == l1) continue;
-            int s0 = 0;                                         // score(state 0) - score(state 1)
-            for (int k = l0 + lane; k < l1; k += 32) {
-                int q = lq(k), d = ld(k);
-                s0 += ((vb[q >> 5] >> (q & 31)) & 1u) ? -d : d;
+            const int l0 = l0n, l1 = l1n, q = qn, d = dn;
+            const uint32_t own = ownn;
+            if (i + 1 < n) {                                    // prefetch the next site (independent of the states)
+                l0n = l1; l1n = loff(i + 2);
+                const int k = l0n + lane;
+                qn = k < l1n ? lq(k) : -1; dn = k < l1n ? ld(k) : 0;
+                ownn = (vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u;
             }
-            s0 = __reduce_add_sync(0xffffffffu, s0);
-            if (lane == 0) {
-                uint32_t w = vb[i >> 5], m = 1u << (i & 31);
-                if (s0 < 0) vb[i >> 5] = w | m; else if (s0 > 0) vb[i >> 5] = w & ~m;
+            uint32_t nw = own;
+            if (l0 != l1) {
+                int s0 = 0;                                     // score(state 0) - score(state 1)
+                if (q >= 0) {
+                    const int back = i - 1 - q;
+                    const uint32_t sq = back < 32 ? (recent >> back) & 1u : (vb[q >> 5] >> (q & 31)) & 1u;
+                    s0 = sq ? -d : d;
+                }
+                for (int k = l0 + 32 + lane; k < l1; k += 32) { // more than 32 left partners (rare)
+                    const int q2 = lq(k), d2 = ld(k), back = i - 1 - q2;
+                    const uint32_t sq = back < 32 ? (recent >> back) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
+                    s0 += sq ? -d2 : d2;
+                }
+                s0 = __reduce_add_sync(0xffffffffu, s0);
+                nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
+                if (nw != own) {                                // uniform: publish the flipped bit for far readers
+                    if (lane == 0) { uint32_t w = vb[i >> 5], m = 1u << (i & 31); vb[i >> 5] = nw ? (w | m) : (w & ~m); }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
+            recent = (recent << 1) | nw;
         }
     }
     __syncthreads();
@@ -523,7 +576,13 @@ __global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
     const int n_vmap = (int)st->n_vmap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
         int gq = voting_gq(i, R, O, st);
-        if (gq >= 0) R.q_ent[R.q_off[gq] + atomicAdd(&R.q_cur[gq], 1)] = i;
+        if (gq >= 0) {
+            // entry = (block << 1) | phase of the variant: phase 0 if the row's base is the
+            // hap-0 allele of the site's state (phasing.py:462-463)
+            const int s = O.d_vm_site[i];
+            const uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
+            R.q_ent[R.q_off[gq] + atomicAdd(&R.q_cur[gq], 1)] = (O.d_ph_block[s] << 1) | (O.d_vm_base[i] == h0 ? 0 : 1);
+        }
     }
 }
 
@@ -539,16 +598,14 @@ __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_st
         while (e0 < e1) {
             int cur = 0x7fffffff;
             for (int e = e0; e < e1; e++) {
-                int b = O.d_ph_block[O.d_vm_site[R.q_ent[e]]];
+                int b = R.q_ent[e] >> 1;
                 if (b > last && b < cur) cur = b;
             }
             if (cur == 0x7fffffff) break;
             int n0 = 0, n1 = 0;
             for (int e = e0; e < e1; e++) {
-                int i = R.q_ent[e], s = O.d_vm_site[i];
-                if (O.d_ph_block[s] != cur) continue;
-                uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
-                if (O.d_vm_base[i] == h0) n0++; else n1++;
+                int v = R.q_ent[e];
+                if ((v >> 1) == cur) { if (v & 1) n1++; else n0++; }
             }
             int phase = n0 - n1 > 1 ? 0 : (n1 - n0 > 1 ? 1 : -1);
             if (phase >= 0) {
@@ -595,8 +652,6 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
         k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, A.row_off, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
     }
-    k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A.row_off, out->d_vm_base, out->d_vm_qid, A.dup, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
     k_uniq_lists<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
     if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, FUZ_FIN_PAIRS, A.max_pairs))) return rc;
