@@ -220,11 +220,11 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 // million entries; the scan is never the dominant kernel.  The tail of the scan also
 // publishes the total into the status block (row counts + capacity checks), which saves
 // one tiny kernel launch per scan.
-#define SCAN_PER_THREAD 32
+#define SCAN_PASSES 4
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                    int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
                                                    int64_t fin_cap, fuz_status *st) {
-    __shared__ int warp_tot[2][32];               // double buffered: one barrier per chunk
+    __shared__ int warp_tot[2][32];               // double buffered: one barrier per pass
     int64_t n = d_n ? *d_n : n_cap;
     if (n > n_cap) n = n_cap;
     if (n < 0) n = 0;
@@ -233,43 +233,51 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
     long long carry_s = 0;                        // replicated in every thread
     int buf = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    // a chunk = 32768 elements: every thread owns 32 consecutive ones (8 x 128-bit loads in
-    // flight), so arrays up to 32 K entries (sites, tiles, records, reads of a C2-size batch)
-    // need one memory round trip and one barrier
-    for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD, buf ^= 1) {
-        int v[SCAN_PER_THREAD];
-        int s = 0;
-        const int64_t i0 = base + (int64_t)tid * SCAN_PER_THREAD;
-        if (i0 < n) {
-            if (vec_ok && i0 + SCAN_PER_THREAD <= n) {
+    // a pass = 4096 elements, 4 consecutive ones per thread (one coalesced 128-bit load);
+    // the loads of SCAN_PASSES passes are issued together so that arrays up to 16 K entries
+    // cost one memory round trip
+    for (int64_t base = 0; base < n; base += 4096 * SCAN_PASSES) {
+        int4 v[SCAN_PASSES];
 #pragma unroll
-                for (int k = 0; k < SCAN_PER_THREAD; k += 4) {
-                    const int4 a = *reinterpret_cast<const int4 *>(in + i0 + k);
-                    v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+        for (int p = 0; p < SCAN_PASSES; p++) {
+            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
+            v[p] = make_int4(0, 0, 0, 0);
+            if (i0 < n) {
+                if (vec_ok && i0 + 4 <= n) v[p] = *reinterpret_cast<const int4 *>(in + i0);
+                else {
+                    v[p].x = in[i0];
+                    if (i0 + 1 < n) v[p].y = in[i0 + 1];
+                    if (i0 + 2 < n) v[p].z = in[i0 + 2];
+                    if (i0 + 3 < n) v[p].w = in[i0 + 3];
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < SCAN_PER_THREAD; k++) v[k] = i0 + k < n ? in[i0 + k] : 0;
-            }
-#pragma unroll
-            for (int k = 0; k < SCAN_PER_THREAD; k++) s += v[k];
-        }
-        const int incl = fuz_warp_incl_scan(s, lane);
-        if (lane == 31) warp_tot[buf][warp] = incl;
-        __syncthreads();
-        const int t = warp_tot[buf][lane];
-        const int ti = fuz_warp_incl_scan(t, lane);
-        const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
-        const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
-        if (i0 < n) {
-            long long excl = carry_s + wexcl + (incl - s);
-#pragma unroll
-            for (int k = 0; k < SCAN_PER_THREAD; k++) {
-                if (i0 + k < n) out[i0 + k] = (int32_t)excl;
-                excl += v[k];
             }
         }
-        carry_s += chunk_total;
+#pragma unroll
+        for (int p = 0; p < SCAN_PASSES; p++, buf ^= 1) {
+            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
+            if (base + p * 4096 >= n) break;      // uniform
+            const int s = v[p].x + v[p].y + v[p].z + v[p].w;
+            const int incl = fuz_warp_incl_scan(s, lane);
+            if (lane == 31) warp_tot[buf][warp] = incl;
+            __syncthreads();
+            const int t = warp_tot[buf][lane];
+            const int ti = fuz_warp_incl_scan(t, lane);
+            const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
+            const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
+            const long long excl = carry_s + wexcl + (incl - s);
+            if (i0 < n) {
+                int4 o;
+                o.x = (int)excl; o.y = o.x + v[p].x; o.z = o.y + v[p].y; o.w = o.z + v[p].z;
+                if (i0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) *reinterpret_cast<int4 *>(out + i0) = o;
+                else {
+                    out[i0] = o.x;
+                    if (i0 + 1 < n) out[i0 + 1] = o.y;
+                    if (i0 + 2 < n) out[i0 + 2] = o.z;
+                    if (i0 + 3 < n) out[i0 + 3] = o.w;
+                }
+            }
+            carry_s += chunk_total;
+        }
     }
     if (tid == 0) {
         const long long total = carry_s;

@@ -309,7 +309,7 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 // SEQ is staged through a per-warp shared-memory window (coalesced 128-bit loads, nibble
 // swap and ACGT filter once per word); the output goes through a per-warp shared-memory
 // window flushed with 128-bit stores.
-__global__ void __launch_bounds__(256) k_project(
+__global__ void __launch_bounds__(256, 4) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
     __shared__ __align__(16) uint32_t strips[8][FUZ_STRIP];

@@ -427,45 +427,52 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         if (O.d_ph_state[cs0 + i] != 255 && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
     __syncthreads();
     // ---- pass 2: one left-to-right sweep (a second sweep never changes anything).
-    // Sequential by construction; one warp walks the sites.  The critical path per site is
-    // kept in registers: the states of the last 32 sites live in a warp-uniform bit window
-    // (`recent`), the adjacency of the next site is prefetched, the vote is one REDUX.
+    // Sequential by construction: one warp walks the sites and nothing hides its latency, so
+    // the loop is kept to a few dozen instructions per site: the states of the last 32 sites
+    // live in a warp-uniform bit window (`recent`), the adjacency of the next site is
+    // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
     if (warp == 0) {
         volatile uint32_t *vb = sbits;
         uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
-        int l0n = loff(0), l1n = loff(1);
-        int qn = l0n + lane < l1n ? lq(l0n + lane) : -1, dn = l0n + lane < l1n ? ld(l0n + lane) : 0;
-        uint32_t ownn = (vb[0] >> 0) & 1u;
+        uint32_t word = vb[0];                                  // states of sites 32*(i/32) .. (pass-1 values, updated in place)
+        int l1n = loff(1), l0n = loff(0);
+        int kn = l0n + lane;
+        int qn = kn < l1n ? lq(kn) : 0x40000000, dn = kn < l1n ? ld(kn) : 0;
         for (int i = 0; i < n; i++) {
-            const int l0 = l0n, l1 = l1n, q = qn, d = dn;
-            const uint32_t own = ownn;
+            const int l0 = l0n, l1 = l1n, d = dn;
+            const int back = i - 1 - qn;                        // < 0 for lanes without a partner
             if (i + 1 < n) {                                    // prefetch the next site (independent of the states)
                 l0n = l1; l1n = loff(i + 2);
-                const int k = l0n + lane;
-                qn = k < l1n ? lq(k) : -1; dn = k < l1n ? ld(k) : 0;
-                ownn = (vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u;
+                kn = l0n + lane;
+                qn = kn < l1n ? lq(kn) : 0x40000000; dn = kn < l1n ? ld(kn) : 0;
             }
+            const uint32_t own = (word >> (i & 31)) & 1u;
             uint32_t nw = own;
             if (l0 != l1) {
                 int s0 = 0;                                     // score(state 0) - score(state 1)
-                if (q >= 0) {
-                    const int back = i - 1 - q;
-                    const uint32_t sq = back < 32 ? (recent >> back) & 1u : (vb[q >> 5] >> (q & 31)) & 1u;
+                if (back >= 0) {
+                    uint32_t sq;
+                    if (back < 32) sq = (recent >> back) & 1u;
+                    else { const int q = i - 1 - back; sq = (vb[q >> 5] >> (q & 31)) & 1u; }   // a completed word
                     s0 = sq ? -d : d;
                 }
-                for (int k = l0 + 32 + lane; k < l1; k += 32) { // more than 32 left partners (rare)
-                    const int q2 = lq(k), d2 = ld(k), back = i - 1 - q2;
-                    const uint32_t sq = back < 32 ? (recent >> back) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
-                    s0 += sq ? -d2 : d2;
+                if (l1 - l0 > 32) {                             // more than 32 left partners (rare)
+                    for (int k = l0 + 32 + lane; k < l1; k += 32) {
+                        const int q2 = lq(k), d2 = ld(k), b2 = i - 1 - q2;
+                        const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
+                        s0 += sq ? -d2 : d2;
+                    }
                 }
                 s0 = __reduce_add_sync(0xffffffffu, s0);
                 nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
-                if (nw != own) {                                // uniform: publish the flipped bit for far readers
-                    if (lane == 0) { uint32_t w = vb[i >> 5], m = 1u << (i & 31); vb[i >> 5] = nw ? (w | m) : (w & ~m); }
-                    __syncwarp();
-                }
             }
             recent = (recent << 1) | nw;
+            word = (word & ~(1u << (i & 31))) | (nw << (i & 31));
+            if ((i & 31) == 31 || i == n - 1) {                 // publish the finished word, fetch the next
+                if (lane == 0) vb[i >> 5] = word;
+                __syncwarp();
+                if (i + 1 < n) word = vb[(i + 1) >> 5];
+            }
         }
     }
     __syncthreads();
