@@ -328,6 +328,53 @@ __device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   /
     return r;
 }
 
+// The sweep of pass 2 for one contig, executed by one warp.  STAGED: adjacency in shared
+// memory with contig-local indices; otherwise global arrays (offsets rebased by e0 / cs0).
+template <bool STAGED>
+__device__ __forceinline__ void sweep_sites(int n, int lane, uint32_t *sbits, const int *__restrict__ loff_a,
+                                            const int *__restrict__ lq_a, const int *__restrict__ ld_a, int e0 = 0,
+                                            int cs0 = 0) {
+    volatile uint32_t *vb = sbits;
+    const int NONE = 0x40000000;
+    uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
+    uint32_t word = vb[0];                                  // states of sites 32 * (i / 32) .. (pass-1 values, updated in place)
+    int l0n = loff_a[0] - e0, l1n = loff_a[1] - e0;
+    int kn = l0n + lane;
+    int qn = kn < l1n ? lq_a[kn] - cs0 : NONE, dn = kn < l1n ? ld_a[kn] : 0;
+    for (int i = 0; i < n; i++) {
+        const int l0 = l0n, l1 = l1n, d = dn;
+        const int back = i - 1 - qn;                        // < 0 for lanes without a partner
+        // prefetch the adjacency of the next site (independent of the states)
+        l0n = l1;
+        l1n = loff_a[min(i + 2, n)] - e0;
+        kn = l0n + lane;
+        qn = kn < l1n ? lq_a[kn] - cs0 : NONE;
+        dn = kn < l1n ? ld_a[kn] : 0;
+        const uint32_t own = (word >> (i & 31)) & 1u;
+        uint32_t nw = own;
+        if (l0 != l1) {
+            int s0 = (back >= 0) ? ((((recent >> (back & 31)) & 1u) ? -d : d)) : 0;   // score(state 0) - score(state 1)
+            if (__any_sync(0xffffffffu, back >= 32) || l1 - l0 > 32) {               // far / many partners: rare
+                if (back >= 32) { const int q = i - 1 - back; s0 = ((vb[q >> 5] >> (q & 31)) & 1u) ? -d : d; }
+                for (int k = l0 + 32 + lane; k < l1; k += 32) {
+                    const int q2 = lq_a[k] - cs0, d2 = ld_a[k], b2 = i - 1 - q2;
+                    const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
+                    s0 += sq ? -d2 : d2;
+                }
+            }
+            s0 = __reduce_add_sync(0xffffffffu, s0);
+            nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
+        }
+        recent = (recent << 1) | nw;
+        word = (word & ~(1u << (i & 31))) | (nw << (i & 31));
+        if ((i & 31) == 31 || i == n - 1) {                 // publish the finished word, fetch the next
+            if (lane == 0) vb[i >> 5] = word;
+            __syncwarp();
+            if (i + 1 < n) word = vb[(i + 1) >> 5];
+        }
+    }
+}
+
 // One CTA per contig: pass-1 forest + pointer jumping, pass-2 sweep, pass-3 extents and
 // scores, pass-4 block chaining (phasing.py:240-408; parallel forms of SURVEY.md A.3).
 // Everything the passes touch (left / right adjacency, positions, forest pointers, phase
@@ -432,48 +479,8 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     // live in a warp-uniform bit window (`recent`), the adjacency of the next site is
     // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
     if (warp == 0) {
-        volatile uint32_t *vb = sbits;
-        uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
-        uint32_t word = vb[0];                                  // states of sites 32*(i/32) .. (pass-1 values, updated in place)
-        int l1n = loff(1), l0n = loff(0);
-        int kn = l0n + lane;
-        int qn = kn < l1n ? lq(kn) : 0x40000000, dn = kn < l1n ? ld(kn) : 0;
-        for (int i = 0; i < n; i++) {
-            const int l0 = l0n, l1 = l1n, d = dn;
-            const int back = i - 1 - qn;                        // < 0 for lanes without a partner
-            if (i + 1 < n) {                                    // prefetch the next site (independent of the states)
-                l0n = l1; l1n = loff(i + 2);
-                kn = l0n + lane;
-                qn = kn < l1n ? lq(kn) : 0x40000000; dn = kn < l1n ? ld(kn) : 0;
-            }
-            const uint32_t own = (word >> (i & 31)) & 1u;
-            uint32_t nw = own;
-            if (l0 != l1) {
-                int s0 = 0;                                     // score(state 0) - score(state 1)
-                if (back >= 0) {
-                    uint32_t sq;
-                    if (back < 32) sq = (recent >> back) & 1u;
-                    else { const int q = i - 1 - back; sq = (vb[q >> 5] >> (q & 31)) & 1u; }   // a completed word
-                    s0 = sq ? -d : d;
-                }
-                if (l1 - l0 > 32) {                             // more than 32 left partners (rare)
-                    for (int k = l0 + 32 + lane; k < l1; k += 32) {
-                        const int q2 = lq(k), d2 = ld(k), b2 = i - 1 - q2;
-                        const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
-                        s0 += sq ? -d2 : d2;
-                    }
-                }
-                s0 = __reduce_add_sync(0xffffffffu, s0);
-                nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
-            }
-            recent = (recent << 1) | nw;
-            word = (word & ~(1u << (i & 31))) | (nw << (i & 31));
-            if ((i & 31) == 31 || i == n - 1) {                 // publish the finished word, fetch the next
-                if (lane == 0) vb[i >> 5] = word;
-                __syncwarp();
-                if (i + 1 < n) word = vb[(i + 1) >> 5];
-            }
-        }
+        if (staged) sweep_sites<true>(n, lane, sbits, s_loff, s_lq, s_ld);
+        else sweep_sites<false>(n, lane, sbits, B.left_off + cs0, B.lq + e0, B.ld + e0, e0, cs0);
     }
     __syncthreads();
     // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
