@@ -222,6 +222,7 @@ struct BlockScratch {
     int32_t *ctg_site_off, *left_cnt, *left_off, *left_cur, *lq, *ld, *right_off, *min_k;
     int32_t *bidx, *bsize, *bnew;
     uint32_t *fp;   // forest pointer: parent * 2 + parity bit
+    long long *dbg; // optional: per-contig phase timestamps (16 per contig), diagnostics only
 };
 
 #define FUZ_PHASE_THREADS 1024
@@ -328,6 +329,56 @@ __device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   /
     return r;
 }
 
+// Lean form of the pass-2 sweep for the staged (shared-memory) case.  Per site the loop-carried
+// chain is: window shift -> select +-d -> REDUX -> sign -> window update; everything else
+// (adjacency of the next site) is prefetched off the chain.  Sites whose partners do not fit
+// the fast path (more than 32 of them, or one more than 32 sites back) are flagged by the
+// caller in s_slow and take the generic code.
+__device__ __forceinline__ void sweep_sites_lean(int n, int lane, uint32_t *sbits, const int *__restrict__ s_loff,
+                                                 const int *__restrict__ s_lq, const int *__restrict__ s_ld,
+                                                 const uint8_t *__restrict__ s_slow) {
+    volatile uint32_t *vb = sbits;
+    uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
+    uint32_t word = vb[0];
+    int l1n = s_loff[1];
+    int kn = s_loff[0] + lane;
+    int dn = kn < l1n ? s_ld[kn] : 0;
+    int bn = kn < l1n ? (0 - 1 - s_lq[kn]) & 31 : 0;        // back = i - 1 - q (mod 32: exact on the fast path)
+    uint32_t slown = s_slow[0];
+    for (int i = 0; i < n; i++) {
+        const int d = dn, back = bn, l0 = kn - lane, l1 = l1n;
+        const uint32_t slow = slown & 1u;
+        slown = s_slow[min(i + 1, n - 1)];
+        // prefetch site i + 1
+        const int l1x = s_loff[min(i + 2, n)];
+        kn = l1 + lane;
+        const bool hv = kn < l1x;
+        const int qx = hv ? s_lq[kn] : 0;
+        dn = hv ? s_ld[kn] : 0;
+        bn = (i - qx) & 31;
+        l1n = l1x;
+        const uint32_t own = (word >> (i & 31)) & 1u;
+        int s0 = ((recent >> back) & 1u) ? -d : d;          // lanes without a partner carry d = 0
+        if (slow) {                                         // uniform, rare: far or > 32 partners
+            s0 = 0;
+            for (int k = l0 + lane; k < l1; k += 32) {
+                const int q2 = s_lq[k], d2 = s_ld[k], b2 = i - 1 - q2;
+                const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
+                s0 += sq ? -d2 : d2;
+            }
+        }
+        s0 = __reduce_add_sync(0xffffffffu, s0);
+        const uint32_t nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
+        recent = (recent << 1) | nw;
+        word = (word & ~(1u << (i & 31))) | (nw << (i & 31));
+        if ((i & 31) == 31 || i == n - 1) {                 // publish the finished word, fetch the next
+            if (lane == 0) vb[i >> 5] = word;
+            __syncwarp();
+            if (i + 1 < n) word = vb[(i + 1) >> 5];
+        }
+    }
+}
+
 // The sweep of pass 2 for one contig, executed by one warp.  STAGED: adjacency in shared
 // memory with contig-local indices; otherwise global arrays (offsets rebased by e0 / cs0).
 template <bool STAGED>
@@ -395,7 +446,8 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     const int nbw = (n + 31) >> 5;
     if ((size_t)nbw * 4 > FUZ_PHASE_SMEM) { if (tid == 0) fuz_raise(st, FUZ_E_CAPACITY, 5); return; }
     // shared-memory layout (words): bits | loff | lq | ld | roff | rq | rd | pos | fp
-    const size_t need = (size_t)nbw + (n + 1) + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + n;
+    const size_t need = (size_t)nbw + (n + 1) + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + n + (n + 3) / 4 + 1 +
+                        4 * (size_t)n;
     const bool staged = need * 4 <= FUZ_PHASE_SMEM;
     uint32_t *sbits = smem;                                   // [nbw] phase bit per site
     int *s_loff = reinterpret_cast<int *>(smem + nbw);        // [n + 1] left CSR offsets (relative to e0)
@@ -404,6 +456,9 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     int *s_rq = s_roff + n + 1, *s_rd = s_rq + n_r;           // [n_r] partner (contig-local), cis - trans (0: rejected row)
     int *s_pos = s_rd + n_r;                                  // [n] 1-based positions
     volatile uint32_t *s_fp = reinterpret_cast<uint32_t *>(s_pos + n);   // [n] forest pointers (contig-local)
+    uint8_t *s_slow = reinterpret_cast<uint8_t *>(s_pos + 2 * n);        // [n] site needs the generic sweep step (bit 0), in positions (bit 1)
+    int *s_sc = s_pos + 2 * n + (n + 3) / 4 + 1;                         // [4n] lscore, rscore, lext, rext of pass 3
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 0] = clock64();
     for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
     if (staged) {
         for (int i = tid; i <= n; i += nt) { s_loff[i] = B.left_off[cs0 + i] - e0; s_roff[i] = B.right_off[cs0 + i] - r0; }
@@ -431,11 +486,13 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         d_out = best >= 0 ? ld(best) : 0;
         return best >= 0 ? bq : -1;
     };
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 1] = clock64();
     // ---- pass 1 as a forest (rows are ordered by (site1, site2), ties impossible)
     for (int i = tid; i < n; i += nt) {
         int parent = i, bit = 0, d;
         bool in_pos = false;
         int ml = min_left(i, d);
+        uint8_t slow_flag = (loff(i + 1) - loff(i) > 32) || (ml >= 0 && i - 1 - ml >= 32);
         if (ml >= 0) {
             in_pos = true;
             parent = ml;
@@ -454,8 +511,10 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         }
         fp[i] = ((uint32_t)parent << 1) | (uint32_t)bit;
         O.d_ph_state[cs0 + i] = in_pos ? 0 : 255;
+        if (staged) s_slow[i] = slow_flag | (in_pos ? 2 : 0);
     }
     __syncthreads();
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 2] = clock64();
     int rounds = 1;
     while ((1 << rounds) < n) rounds++;
     rounds++;
@@ -471,22 +530,24 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt)
-        if (O.d_ph_state[cs0 + i] != 255 && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
+        if ((staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[cs0 + i] != 255) && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
     __syncthreads();
     // ---- pass 2: one left-to-right sweep (a second sweep never changes anything).
     // Sequential by construction: one warp walks the sites and nothing hides its latency, so
     // the loop is kept to a few dozen instructions per site: the states of the last 32 sites
     // live in a warp-uniform bit window (`recent`), the adjacency of the next site is
     // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 3] = clock64();
     if (warp == 0) {
-        if (staged) sweep_sites<true>(n, lane, sbits, s_loff, s_lq, s_ld);
+        if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, s_slow);
         else sweep_sites<false>(n, lane, sbits, B.left_off + cs0, B.lq + e0, B.ld + e0, e0, cs0);
     }
     __syncthreads();
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 4] = clock64();
     // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
     for (int i = warp; i < n; i += nwarps) {
         const int x = cs0 + i;
-        const bool in_pos = O.d_ph_state[x] != 255;
+        const bool in_pos = staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255;
         const int px = pos_of(i);
         int lscore = 0, rscore = 0, lext = px, rext = px;
         if (in_pos) {
@@ -513,20 +574,30 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         }
         if (lane == 0) {
             O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
+            if (staged) { s_sc[4 * i] = lscore; s_sc[4 * i + 1] = rscore; s_sc[4 * i + 2] = lext; s_sc[4 * i + 3] = rext; }
         }
     }
     __syncthreads();
     // ---- pass 4: chain sites into blocks by the running maximum of right extents (never reset)
     //      = exclusive prefix max + boundary flags + segment sizes + dense ids of blocks with > 3 sites
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 5] = clock64();
     int carry_max = 0, carry_b = 0;
     for (int base = 0; base < n; base += nt) {
-        const int x = cs0 + base + tid;
-        const bool valid = base + tid < n;
-        const bool f = valid && O.d_ph_state[x] != 255 && O.d_ph_rscore[x] >= 10 && O.d_ph_lscore[x] >= 10;
+        const int x = cs0 + base + tid, il = base + tid;
+        const bool valid = il < n;
+        bool f;
+        int my_rext = 0, my_lext = 0;
+        if (staged) {
+            f = valid && (s_slow[il] & 2) && s_sc[4 * il + 1] >= 10 && s_sc[4 * il] >= 10;
+            if (f) { my_lext = s_sc[4 * il + 2]; my_rext = s_sc[4 * il + 3]; }
+        } else {
+            f = valid && O.d_ph_state[x] != 255 && O.d_ph_rscore[x] >= 10 && O.d_ph_lscore[x] >= 10;
+            if (f) { my_lext = O.d_ph_lext[x]; my_rext = O.d_ph_rext[x]; }
+        }
         int tot;
-        int mb = max(carry_max, cta_excl_max(f ? O.d_ph_rext[x] : 0, s_tmp, &tot));
+        int mb = max(carry_max, cta_excl_max(f ? my_rext : 0, s_tmp, &tot));
         carry_max = max(carry_max, tot);
-        const int boundary = f && mb < O.d_ph_lext[x];
+        const int boundary = f && mb < my_lext;
         int bi = carry_b + cta_excl_sum(boundary, s_tmp, &tot) + boundary;   // inclusive: temp block number
         carry_b += tot;
         if (valid) B.bidx[x] = f ? bi : 0;
@@ -549,6 +620,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         int bi = B.bidx[x];
         O.d_ph_block[x] = bi > 0 ? B.bnew[cs0 + c + bi] : 0;
     }
+    if (B.dbg && tid == 0) B.dbg[c * 16 + 6] = clock64();
 }
 
 // ================================================================== phased reads
@@ -686,12 +758,14 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
     size_t o_lcur = L.add(4 * (size_t)(cs + 1)), o_lq = L.add(4 * (size_t)(ca + 1)), o_ld = L.add(4 * (size_t)(ca + 1));
     size_t o_ro = L.add(4 * (size_t)(cs + 2)), o_mk = L.add(4 * (size_t)(cs + 1)), o_fp = L.add(4 * (size_t)(cs + 1));
     size_t o_bi = L.add(4 * (size_t)(cs + 1)), o_bs = L.add(4 * (size_t)(cs + 2)), o_bn = L.add(4 * (size_t)(cs + n_ctg + 2));
+    size_t o_dbg = L.add(8 * 16 * (size_t)n_ctg);
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
     B.ctg_site_off = fuz_at<int32_t>(ctx, o_cso); B.left_cnt = fuz_at<int32_t>(ctx, o_lc); B.left_off = fuz_at<int32_t>(ctx, o_lo);
     B.left_cur = fuz_at<int32_t>(ctx, o_lcur); B.lq = fuz_at<int32_t>(ctx, o_lq); B.ld = fuz_at<int32_t>(ctx, o_ld);
     B.right_off = fuz_at<int32_t>(ctx, o_ro); B.min_k = fuz_at<int32_t>(ctx, o_mk); B.fp = fuz_at<uint32_t>(ctx, o_fp);
     B.bidx = fuz_at<int32_t>(ctx, o_bi); B.bsize = fuz_at<int32_t>(ctx, o_bs); B.bnew = fuz_at<int32_t>(ctx, o_bn);
+    B.dbg = ctx->profile ? fuz_at<long long>(ctx, o_dbg) : nullptr;
     if (!ctx->phase_attr_set) {
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;
@@ -705,6 +779,13 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
     FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
     k_ctg_phase<<<n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_ctg_phase");
+    if (B.dbg) {            // diagnostics: phase durations (cycles) of contig 0
+        long long h[16];
+        cudaMemcpyAsync(h, B.dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "k_ctg_phase contig 0 cycles: stage %lld pass1 %lld jump %lld sweep %lld pass3 %lld pass4 %lld\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+    }
     return FUZ_OK;
 }
 
