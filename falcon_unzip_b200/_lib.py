@@ -62,6 +62,20 @@ class HostOutputs(C.Structure):
                  ("cap_reads", C.c_int64)] + [(n, C.c_void_p) for n in _OUT_ORDER])
 
 
+class RRInput(C.Structure):
+    _fields_ = [("n_ovl", C.c_int64), ("d_q", C.c_void_p), ("d_t", C.c_void_p), ("d_len", C.c_void_p),
+                ("d_tlen", C.c_void_p), ("d_file", C.c_void_p), ("n_reads", C.c_int32), ("d_in_map", C.c_void_p),
+                ("d_ph_ctg", C.c_void_p), ("d_ph_block", C.c_void_p), ("d_ph_phase", C.c_void_p),
+                ("d_rc_off", C.c_void_p), ("d_rc_ctg", C.c_void_p), ("min_len", C.c_int32), ("bestn", C.c_int32),
+                ("n_ctg", C.c_int32)]
+
+
+class RROutputs(C.Structure):
+    _fields_ = [("d_keep", C.c_void_p), ("d_hp_n", C.c_void_p), ("d_hp_len", C.c_void_p), ("d_hp_q", C.c_void_p),
+                ("cap_votes", C.c_int64), ("d_vt_off", C.c_void_p), ("d_vt_ctg", C.c_void_p),
+                ("d_vt_count", C.c_void_p), ("d_vt_score", C.c_void_p)]
+
+
 class Status(C.Structure):
     _fields_ = [("error", C.c_int32), ("error_index", C.c_int32), ("n_sites", C.c_int64),
                 ("n_vmap", C.c_int64), ("n_atable", C.c_int64), ("n_reads", C.c_int64),
@@ -94,6 +108,9 @@ SYMBOLS = [
     ("fuz_phase_batch", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Outputs)]),
     ("fuz_phase_batch_host", C.c_int, [C.c_void_p, C.POINTER(HostBatch), C.POINTER(HostOutputs),
                                        C.POINTER(Status), _i64p, _i64p]),
+    ("fuz_rr_track", C.c_int, [C.c_void_p, C.POINTER(RRInput), C.POINTER(RROutputs)]),
+    ("fuz_host_parse_la4falcon", C.c_int64, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
     ("fuz_host_index_records", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p]),
     ("fuz_host_assign_qids", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -108,3 +108,44 @@ extern "C" int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int6
         if (e.used) out[w++] = e.key;
     return FUZ_OK;
 }
+
+// LA4Falcon -m lines: "q t -len idt qstrand qs qe ql tstrand ts te tl tag" (rr_hctg_track.py:38-44)
+extern "C" int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t,
+                                            int32_t *len, int32_t *tlen) {
+    if (!text || n_bytes < 0 || !q || !t || !len || !tlen) return -1;
+    int64_t n = 0, i = 0;
+    while (i < n_bytes && n < cap) {
+        // one line
+        long long col[12];
+        int c = 0;
+        bool any = false;
+        while (i < n_bytes && text[i] != '\n') {
+            while (i < n_bytes && (text[i] == ' ' || text[i] == '\t' || text[i] == '\r')) i++;
+            if (i >= n_bytes || text[i] == '\n') break;
+            any = true;
+            // token
+            int64_t s = i;
+            while (i < n_bytes && text[i] != ' ' && text[i] != '\t' && text[i] != '\n' && text[i] != '\r') i++;
+            if (c < 12) {
+                if (c == 3) { col[c] = 0; }            // idt: float, unused (:42)
+                else {
+                    bool neg = false; int64_t k = s; long long v = 0;
+                    if (k < i && (text[k] == '-' || text[k] == '+')) { neg = text[k] == '-'; k++; }
+                    if (k == i) { if (c == 0 || c == 1 || c == 2 || c == 11) return -1; }
+                    for (; k < i; k++) {
+                        if (text[k] < '0' || text[k] > '9') { if (c == 0 || c == 1 || c == 2 || c == 11) return -1; v = 0; break; }
+                        v = v * 10 + (text[k] - '0');
+                    }
+                    col[c] = neg ? -v : v;
+                }
+            }
+            c++;
+        }
+        if (i < n_bytes) i++;                          // newline
+        if (!any) continue;                            // blank line
+        if (c < 12) return -1;
+        q[n] = (int32_t)col[0]; t[n] = (int32_t)col[1]; len[n] = (int32_t)(-col[2]); tlen[n] = (int32_t)col[11];
+        n++;
+    }
+    return n;
+}

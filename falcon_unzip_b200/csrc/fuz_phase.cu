@@ -330,38 +330,36 @@ __device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   /
 }
 
 // Lean form of the pass-2 sweep for the staged (shared-memory) case.  Per site the loop-carried
-// chain is: window shift -> select +-d -> REDUX -> sign -> window update; everything else
-// (adjacency of the next site) is prefetched off the chain.  Sites whose partners do not fit
-// the fast path (more than 32 of them, or one more than 32 sites back) are flagged by the
-// caller in s_slow and take the generic code.
+// chain is: window shift -> select +-d -> REDUX -> sign -> window update.  The adjacency is
+// pre-packed per edge as (d << 6 | back), back = distance to the partner in sites, and is
+// loaded two sites ahead so that no load sits on the chain.  Sites whose partners do not fit
+// the fast path (more than 32 of them, or one more than 32 sites back) are flagged in s_slow
+// and take the generic code.
 __device__ __forceinline__ void sweep_sites_lean(int n, int lane, uint32_t *sbits, const int *__restrict__ s_loff,
                                                  const int *__restrict__ s_lq, const int *__restrict__ s_ld,
-                                                 const uint8_t *__restrict__ s_slow) {
+                                                 const int *__restrict__ s_pk, const uint8_t *__restrict__ s_slow) {
     volatile uint32_t *vb = sbits;
     uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
     uint32_t word = vb[0];
-    int l1n = s_loff[1];
-    int kn = s_loff[0] + lane;
-    int dn = kn < l1n ? s_ld[kn] : 0;
-    int bn = kn < l1n ? (0 - 1 - s_lq[kn]) & 31 : 0;        // back = i - 1 - q (mod 32: exact on the fast path)
-    uint32_t slown = s_slow[0];
+    auto edge = [&](int site) {                             // packed edge of `site` for this lane (0: none)
+        const int s = min(site, n - 1);
+        const int k = s_loff[s] + lane;
+        return (site < n && k < s_loff[s + 1]) ? s_pk[k] : 0;
+    };
+    int pk_cur = edge(0), pk_nxt = edge(1);
+    uint32_t slow_cur = s_slow[0] & 1u, slow_nxt = s_slow[min(1, n - 1)] & 1u;
     for (int i = 0; i < n; i++) {
-        const int d = dn, back = bn, l0 = kn - lane, l1 = l1n;
-        const uint32_t slow = slown & 1u;
-        slown = s_slow[min(i + 1, n - 1)];
-        // prefetch site i + 1
-        const int l1x = s_loff[min(i + 2, n)];
-        kn = l1 + lane;
-        const bool hv = kn < l1x;
-        const int qx = hv ? s_lq[kn] : 0;
-        dn = hv ? s_ld[kn] : 0;
-        bn = (i - qx) & 31;
-        l1n = l1x;
+        const int pk = pk_cur;
+        const uint32_t slow = slow_cur;
+        pk_cur = pk_nxt; slow_cur = slow_nxt;
+        pk_nxt = edge(i + 2);                               // two sites ahead: off the critical chain
+        slow_nxt = s_slow[min(i + 2, n - 1)] & 1u;
+        const int d = pk >> 6;
         const uint32_t own = (word >> (i & 31)) & 1u;
-        int s0 = ((recent >> back) & 1u) ? -d : d;          // lanes without a partner carry d = 0
+        int s0 = ((recent >> (pk & 31)) & 1u) ? -d : d;     // lanes without a partner carry d = 0
         if (slow) {                                         // uniform, rare: far or > 32 partners
             s0 = 0;
-            for (int k = l0 + lane; k < l1; k += 32) {
+            for (int k = s_loff[i] + lane; k < s_loff[i + 1]; k += 32) {
                 const int q2 = s_lq[k], d2 = s_ld[k], b2 = i - 1 - q2;
                 const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
                 s0 += sq ? -d2 : d2;
@@ -447,7 +445,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     if ((size_t)nbw * 4 > FUZ_PHASE_SMEM) { if (tid == 0) fuz_raise(st, FUZ_E_CAPACITY, 5); return; }
     // shared-memory layout (words): bits | loff | lq | ld | roff | rq | rd | pos | fp
     const size_t need = (size_t)nbw + (n + 1) + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + n + (n + 3) / 4 + 1 +
-                        4 * (size_t)n;
+                        4 * (size_t)n + n_e;
     const bool staged = need * 4 <= FUZ_PHASE_SMEM;
     uint32_t *sbits = smem;                                   // [nbw] phase bit per site
     int *s_loff = reinterpret_cast<int *>(smem + nbw);        // [n + 1] left CSR offsets (relative to e0)
@@ -458,6 +456,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     volatile uint32_t *s_fp = reinterpret_cast<uint32_t *>(s_pos + n);   // [n] forest pointers (contig-local)
     uint8_t *s_slow = reinterpret_cast<uint8_t *>(s_pos + 2 * n);        // [n] site needs the generic sweep step (bit 0), in positions (bit 1)
     int *s_sc = s_pos + 2 * n + (n + 3) / 4 + 1;                         // [4n] lscore, rscore, lext, rext of pass 3
+    int *s_pk = s_sc + 4 * n;                                            // [n_e] packed left edges for the sweep
     if (B.dbg && tid == 0) B.dbg[c * 16 + 0] = clock64();
     for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
     if (staged) {
@@ -493,6 +492,8 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         bool in_pos = false;
         int ml = min_left(i, d);
         uint8_t slow_flag = (loff(i + 1) - loff(i) > 32) || (ml >= 0 && i - 1 - ml >= 32);
+        if (staged)
+            for (int k = loff(i); k < loff(i + 1); k++) s_pk[k] = (ld(k) << 6) | ((i - 1 - lq(k)) & 31);
         if (ml >= 0) {
             in_pos = true;
             parent = ml;
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
     if (B.dbg && tid == 0) B.dbg[c * 16 + 3] = clock64();
     if (warp == 0) {
-        if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, s_slow);
+        if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, s_pk, s_slow);
         else sweep_sites<false>(n, lane, sbits, B.left_off + cs0, B.lq + e0, B.ld + e0, e0, cs0);
     }
     __syncthreads();

@@ -10,6 +10,8 @@
  *   fuz_phased_reads        falcon_unzip/phasing.py:423-480  get_phased_reads
  *   fuz_phase_batch         falcon_unzip/phasing.py:482-553  phasing() (the four stages
  *                           chained on the device for a batch of contigs)
+ *   fuz_rr_track            falcon_unzip/rr_hctg_track.py:31-65,97-105,113-123
+ *                           tr_stage1 + heap merge + contig vote of run_track_reads
  *   fuz_host_*              host-side helpers of the same path (record index, QNAME ->
  *                           q_id of phasing.py:47-54)
  *
@@ -192,6 +194,38 @@ typedef struct {
 int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_outputs *out,
                          fuz_status *h_status, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
+/* ---- raw-read -> haplotig tracking (falcon_unzip/rr_hctg_track.py) --------------- */
+/* fuz_rr_track replaces tr_stage1 (:31-65), the heap merge (:97-105) and the contig vote
+ * (:113-123) of run_track_reads for ALL LAS files at once.  The host parses the LA4Falcon
+ * text (fuz_host_parse_la4falcon), builds the tables (:15-23, :72-85) and formats the rows
+ * (:126-138, with the CPython-2 orders of SURVEY.md B.4). */
+typedef struct {
+    int64_t n_ovl;                /* overlap lines, concatenated in (sorted file, line) order */
+    const int32_t *d_q, *d_t;     /* read ids (LA4Falcon columns 0, 1)                    */
+    const int32_t *d_len;         /* overlap length = -int(col 2)                         */
+    const int32_t *d_tlen;        /* col 11                                               */
+    const int32_t *d_file;        /* LAS file index of the line (non-decreasing)          */
+    int32_t n_reads;              /* size of the read-id space (len of rawread_ids list)  */
+    const uint8_t *d_in_map;      /* [n_reads] 1 if rid is a key of rid_to_ctg            */
+    const int32_t *d_ph_ctg, *d_ph_block, *d_ph_phase; /* [n_reads] phase table; ctg -1 = None */
+    const int32_t *d_rc_off;      /* [n_reads + 1] CSR rid -> contigs                     */
+    const int32_t *d_rc_ctg;      /* contig indices, each list in CPython-2 set iteration order */
+    int32_t min_len, bestn, n_ctg;
+} fuz_rr_input;
+
+typedef struct {
+    uint8_t *d_keep;              /* [n_ovl] 1 = the line passed the filter (:45-57)       */
+    int32_t *d_hp_n;              /* [n_reads] entries of the merged heap of every target  */
+    int32_t *d_hp_len, *d_hp_q;   /* [n_reads * bestn] merged heaps in heapq ARRAY order   */
+    int64_t cap_votes;
+    int32_t *d_vt_off;            /* [n_reads + 1] vote rows of every target               */
+    int32_t *d_vt_ctg, *d_vt_count; int64_t *d_vt_score;  /* [cap_votes] in dict insertion order */
+} fuz_rr_outputs;
+
+/* status after the call: reserved[1] = vote rows, reserved[2] = vote rows needed,
+ * reserved[3] = kept overlap lines. */
+int fuz_rr_track(fuz_ctx *ctx, const fuz_rr_input *in, fuz_rr_outputs *out);
+
 /* ---- host helpers (no CUDA) ------------------------------------------------------ */
 /* Walk the block_size chain of a record buffer.  rec_off needs n_rec+1 slots; returns
  * the record count through n_rec (call with rec_off = NULL to count only). */
@@ -202,6 +236,11 @@ int fuz_host_index_records(const uint8_t *h_rec_buf, int64_t rec_bytes, int64_t 
 int fuz_host_assign_qids(const uint8_t *h_rec_buf, const int64_t *h_rec_off, int64_t n_rec,
                          const int32_t *h_ctg_rec_off, int32_t n_ctg, int32_t *h_rec_qid,
                          int32_t *h_ctg_nq, int64_t *h_name_first);
+/* Parse LA4Falcon -m text (rr_hctg_track.py:38-44): columns 0, 1, 2, 11 of every line ->
+ * q, t, len = -int(col 2), tlen.  Returns the number of lines parsed (stops at cap), or -1
+ * on a malformed line (the reference would raise). */
+int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, int64_t cap,
+                                 int32_t *q, int32_t *t, int32_t *len, int32_t *tlen);
 /* CPython-2.7 dict iteration order of int keys inserted in the given order (B.3). */
 int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int64_t *out);
 
