@@ -327,10 +327,11 @@ def write_contig_files(res, sl, c: int, ctg_id: str, ref_seq: str, names: Sequen
 
 
 def phase_contigs(records, ctg_names: Sequence[str], ref_seqs: Sequence[str], base_dir: str,
-                  device: int = 0, host_path: bool = True):
+                  device: int = 0, host_path: bool = True, ctg_rec_off=None):
     """Fused path: every contig of the batch in one device call, then the per-contig files.
-    records: concatenated BAM records grouped by contig (refID = index into ctg_names)."""
-    pb = engine.prepare_batch(records, ctg_names, [len(s) for s in ref_seqs])
+    records: concatenated BAM records grouped by contig, in the order of ctg_names (grouping from
+    the refID fields 0..n-1, or given explicitly as record offsets ctg_rec_off)."""
+    pb = engine.prepare_batch(records, ctg_names, [len(s) for s in ref_seqs], ctg_rec_off=ctg_rec_off)
     eng = engine.get_engine(device)
     res = eng.phase_host(pb) if host_path else eng.phase_device(pb)
     sl = formats.contig_slices(res, pb.n_ctg)

@@ -1,0 +1,70 @@
+"""Contig sharding across the GPUs of one box.  Contigs are independent units of the phasing
+path (the reference runs one fc_phasing.py process per contig, unzip.py:231-281), so the
+steady state needs no collective: every rank phases its own contigs and writes their files;
+only the bookkeeping (who did what) is gathered."""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+def assign_contigs(weights: Sequence[float], world_size: int) -> List[List[int]]:
+    """Longest-processing-time-first: contigs sorted by weight (record bytes / aligned bases),
+    each given to the currently lightest rank.  Deterministic; every rank computes the same."""
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    load = [0.0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += weights[i]
+    return [sorted(x) for x in out]
+
+
+def contig_record_ranges(records: np.ndarray, rec_off: np.ndarray, n_ctg: int):
+    """Record range and byte weight of every contig of a coordinate-sorted record buffer."""
+    from . import engine
+    refid = engine.record_refids(records, rec_off) if len(rec_off) > 1 else np.zeros(0, np.int32)
+    bounds = np.searchsorted(refid, np.arange(n_ctg + 1), side="left")
+    weights = [float(rec_off[bounds[c + 1]] - rec_off[bounds[c]]) for c in range(n_ctg)]
+    return bounds, weights
+
+
+def phase_bam_sharded(bam_fn: str, fasta_fn: str, base_dir: str, rank: int = 0, world_size: int = 1,
+                      device: Optional[int] = None, phase_fn: Optional[Callable] = None) -> Dict[str, object]:
+    """Every rank phases its LPT share of the contigs of `bam_fn` with one fused device call and
+    writes the per-contig files under base_dir.  With torch.distributed initialised the list of
+    finished contigs is gathered on every rank (all_gather_object: host bookkeeping only)."""
+    from . import bam, phasing
+    _text, refs, recs = bam.read_bam(bam_fn)
+    ref_seqs = {name.split()[0]: seq.upper() for name, seq in bam.read_fasta(fasta_fn)}
+    records = np.frombuffer(recs, dtype=np.uint8)
+    from . import engine
+    rec_off = engine.index_records(records)
+    bounds, weights = contig_record_ranges(records, rec_off, len(refs))
+    mine = assign_contigs(weights, world_size)[rank]
+    done = []
+    if mine:
+        sub_names = [refs[c][0] for c in mine]
+        parts, sub_off = [], [0]
+        for c in mine:
+            lo, hi = int(rec_off[bounds[c]]), int(rec_off[bounds[c + 1]])
+            parts.append(records[lo:hi])
+            sub_off.append(sub_off[-1] + (bounds[c + 1] - bounds[c]))
+        sub = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+        seqs = [ref_seqs.get(n, "") for n in sub_names]
+        fn = phase_fn or (lambda rec, names, sq, bd: phasing.phase_contigs(
+            rec, names, sq, bd, device=device if device is not None else 0, ctg_rec_off=np.asarray(sub_off, np.int32)))
+        fn(sub, sub_names, seqs, base_dir)
+        done = sub_names
+    gathered = [done]
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and world_size > 1:
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, done)
+    except ImportError:
+        pass
+    return dict(rank=rank, mine=done, all=[c for part in gathered for c in part], n_contigs=len(refs))
