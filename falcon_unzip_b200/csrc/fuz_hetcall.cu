@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(256, 4) k_project(
             continue;
         }
         // phasing.py:72-75 in IEEE double, same operation order as the reference
-        const bool accept = !(1.0 - 1.0 * (double)skip / (double)total < 0.1) && !(total < 2000);
+        // (skip == 0: 1.0 - 0.0 < 0.1 is false, no division needed)
+        const bool accept = (skip == 0 || !(1.0 - 1.0 * (double)skip / (double)total < 0.1)) && !(total < 2000);
         const int gstart = (int)gstart64;
         // words of the projection, padded to whole quads (128-bit flushes)
         const int n_words = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;

@@ -116,3 +116,52 @@ def test_c1_scale_contig_vs_oracle(eng, tmp_path):
     for k in FILES:
         assert open(want[k]).read() == open(got[sset.refs[0][0]][k]).read(), k
     assert len(open(want["phased_reads"]).read().splitlines()) > 500
+
+
+def test_c1_full_size_contig_vs_oracle(eng, tmp_path):
+    """BASELINE.json config 1 at full size: 1 Mb contig, 0.1 % het, 30x 10 kb reads, 1 % error."""
+    from falcon_unzip_b200 import phasing, synth
+    from oracle import c_oracle
+    sset = synth.generate(synth.CONFIGS["c1"])
+    name = sset.refs[0][0]
+    want = c_oracle.run_phasing_stages(sset.contig_records(0), name, sset.ref_seqs[0], str(tmp_path / "oracle"))
+    res, got = phasing.phase_contigs(sset.records, [name], sset.ref_seqs, str(tmp_path / "gpu"))
+    for k in FILES:
+        assert open(want[k]).read() == open(got[name][k]).read(), k
+    assert res.n_sites > 800 and res.n_reads > 2500
+
+
+def test_c2_shape_batch_vs_oracle_and_batch_independence(eng, tmp_path):
+    """Six contigs of the C2 shape (250 kb, 40x) in ONE fused call: files equal the oracle's, and
+    equal what the same contigs give when phased alone (contigs are independent units)."""
+    import dataclasses
+    import numpy as np
+    from falcon_unzip_b200 import phasing, synth
+    from oracle import c_oracle
+    sset = synth.generate_parallel(dataclasses.replace(synth.CONFIGS["c2"], n_contigs=6))
+    names = [r[0] for r in sset.refs]
+    _res, got = phasing.phase_contigs(sset.records, names, sset.ref_seqs, str(tmp_path / "gpu"), host_path=False)
+    for c, name in enumerate(names):
+        want = c_oracle.run_phasing_stages(sset.contig_records(c), name, sset.ref_seqs[c], str(tmp_path / "oracle"))
+        for k in FILES:
+            assert open(want[k]).read() == open(got[name][k]).read(), (name, k)
+    idx = np.flatnonzero(sset.rec_ctg == 3)
+    sub = sset.records[sset.rec_off[idx[0]]:sset.rec_off[idx[-1] + 1]]
+    _r, alone = phasing.phase_contigs(sub, [names[3]], [sset.ref_seqs[3]], str(tmp_path / "alone"),
+                                      ctg_rec_off=np.asarray([0, len(idx)], np.int32))
+    for k in FILES:
+        assert open(alone[names[3]][k]).read() == open(got[names[3]][k]).read(), k
+
+
+def test_many_small_contigs_c3_shape(eng, tmp_path):
+    """C3 shape: many short contigs (67.5 kb, 50x) batched into one launch; 40 of them here."""
+    import dataclasses
+    from falcon_unzip_b200 import phasing, synth
+    from oracle import c_oracle
+    sset = synth.generate_parallel(dataclasses.replace(synth.CONFIGS["c3"], n_contigs=40))
+    names = [r[0] for r in sset.refs]
+    _res, got = phasing.phase_contigs(sset.records, names, sset.ref_seqs, str(tmp_path / "gpu"))
+    for c in (0, 17, 39):
+        want = c_oracle.run_phasing_stages(sset.contig_records(c), names[c], sset.ref_seqs[c], str(tmp_path / "oracle"))
+        for k in FILES:
+            assert open(want[k]).read() == open(got[names[c]][k]).read(), (names[c], k)
