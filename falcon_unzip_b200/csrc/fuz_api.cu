@@ -6,7 +6,7 @@
 
 int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
 int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row_off_valid);
-int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out);
+int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_valid);
 int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
                    bool dup_valid);
 
@@ -17,7 +17,7 @@ extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *o
     // the row range of every site (het call) and the duplicate flags (association) stay in
     // the context's inter-stage buffer and are reused by the later stages
     if ((rc = fuz_association_impl(ctx, in->n_ctg, out, true))) return rc;
-    if ((rc = fuz_blocks_impl(ctx, in->n_ctg, out))) return rc;
+    if ((rc = fuz_blocks_impl(ctx, in->n_ctg, out, true))) return rc;
     return fuz_reads_impl(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out, true);
 }
 

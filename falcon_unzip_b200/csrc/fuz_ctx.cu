@@ -143,9 +143,9 @@ extern "C" int fuz_get_kernel_timing(fuz_ctx *ctx, double *h_ms_total, int64_t *
     return FUZ_OK;
 }
 
-int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup) {
-    size_t off_dup = ((size_t)(cap_sites + 2) * 4 + 255) & ~(size_t)255;
-    size_t need = off_dup + (size_t)cap_vmap + 256;
+int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup, int32_t **at_off) {
+    const size_t sz_off = ((size_t)(cap_sites + 2) * 4 + 255) & ~(size_t)255;
+    const size_t need = 2 * sz_off + (size_t)cap_vmap + 256;
     if (need > ctx->keep_cap) {
         FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->keep) FUZ_CUDA(ctx, cudaFree(ctx->keep));
@@ -155,7 +155,8 @@ int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t *
         ctx->keep_cap = need + (need >> 2);
     }
     *row_off = reinterpret_cast<int32_t *>(ctx->keep);
-    *dup = ctx->keep + off_dup;
+    if (at_off) *at_off = reinterpret_cast<int32_t *>(ctx->keep + sz_off);
+    *dup = ctx->keep + 2 * sz_off;
     return FUZ_OK;
 }
 
@@ -220,98 +221,15 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 // million entries; the scan is never the dominant kernel.  The tail of the scan also
 // publishes the total into the status block (row counts + capacity checks), which saves
 // one tiny kernel launch per scan.
-#define SCAN_PASSES 4
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                    int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
                                                    int64_t fin_cap, fuz_status *st) {
-    __shared__ int warp_tot[2][32];               // double buffered: one barrier per pass
     int64_t n = d_n ? *d_n : n_cap;
     if (n > n_cap) n = n_cap;
     if (n < 0) n = 0;
     if (st && st->error) n = 0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long carry_s = 0;                        // replicated in every thread
-    int buf = 0;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    // a pass = 4096 elements, 4 consecutive ones per thread (one coalesced 128-bit load);
-    // the loads of SCAN_PASSES passes are issued together so that arrays up to 16 K entries
-    // cost one memory round trip
-    for (int64_t base = 0; base < n; base += 4096 * SCAN_PASSES) {
-        int4 v[SCAN_PASSES];
-#pragma unroll
-        for (int p = 0; p < SCAN_PASSES; p++) {
-            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
-            v[p] = make_int4(0, 0, 0, 0);
-            if (i0 < n) {
-                if (vec_ok && i0 + 4 <= n) v[p] = *reinterpret_cast<const int4 *>(in + i0);
-                else {
-                    v[p].x = in[i0];
-                    if (i0 + 1 < n) v[p].y = in[i0 + 1];
-                    if (i0 + 2 < n) v[p].z = in[i0 + 2];
-                    if (i0 + 3 < n) v[p].w = in[i0 + 3];
-                }
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < SCAN_PASSES; p++, buf ^= 1) {
-            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
-            if (base + p * 4096 >= n) break;      // uniform
-            const int s = v[p].x + v[p].y + v[p].z + v[p].w;
-            const int incl = fuz_warp_incl_scan(s, lane);
-            if (lane == 31) warp_tot[buf][warp] = incl;
-            __syncthreads();
-            const int t = warp_tot[buf][lane];
-            const int ti = fuz_warp_incl_scan(t, lane);
-            const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
-            const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
-            const long long excl = carry_s + wexcl + (incl - s);
-            if (i0 < n) {
-                int4 o;
-                o.x = (int)excl; o.y = o.x + v[p].x; o.z = o.y + v[p].y; o.w = o.z + v[p].z;
-                if (i0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) *reinterpret_cast<int4 *>(out + i0) = o;
-                else {
-                    out[i0] = o.x;
-                    if (i0 + 1 < n) out[i0 + 1] = o.y;
-                    if (i0 + 2 < n) out[i0 + 2] = o.z;
-                    if (i0 + 3 < n) out[i0 + 3] = o.w;
-                }
-            }
-            carry_s += chunk_total;
-        }
-    }
-    if (tid == 0) {
-        const long long total = carry_s;
-        out[n] = (int32_t)total;
-        if (st && !st->error) {
-            switch (fin_op) {
-            case FUZ_FIN_SITES:
-                st->need_sites = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 0); else st->n_sites = total;
-                break;
-            case FUZ_FIN_VMAP:
-                st->need_vmap = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 1); else st->n_vmap = total;
-                break;
-            case FUZ_FIN_ATABLE:
-                st->need_atable = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 2); else st->n_atable = total;
-                break;
-            case FUZ_FIN_READS:
-                st->need_reads = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 3); else st->n_reads = total;
-                break;
-            case FUZ_FIN_PAIRS:
-                st->need_pairs = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 4);
-                break;
-            case FUZ_FIN_PROJ:          // alignment spans (deletions) beyond the projection scratch
-                st->reserved[0] = total;
-                if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 6);
-                break;
-            default: break;
-            }
-        }
-    }
+    const long long total = fuz_cta_scan_i32(in, out, n);
+    if (threadIdx.x == 0) fuz_scan_publish(st, fin_op, fin_cap, total);
 }
 
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n, int fin_op,

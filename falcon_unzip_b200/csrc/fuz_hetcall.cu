@@ -662,10 +662,18 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
 }
 
 // ---------------------------------------------------------------- ordered sites + rows
-__global__ void k_order_sites(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff, fuz_outputs O,
-                              fuz_status *st) {
+// One CTA: exclusive scan of the per-tile site counts (tiles are in position order, so this
+// puts the sites in order), copy of the sites to their ordered slots with the derived fields,
+// exclusive scan of the variant_map rows per site.  Three former launches in one.
+__global__ void __launch_bounds__(1024) k_sites_finalize(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff,
+                                                          fuz_outputs O, fuz_status *st) {
     if (st->error) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    const long long total = fuz_cta_scan_i32(S.tile_site_cnt, S.tile_site_off, n_tiles);
+    if (threadIdx.x == 0) fuz_scan_publish(st, FUZ_FIN_SITES, O.cap_sites, total);
+    __threadfence_block();
+    __syncthreads();
+    if (total > O.cap_sites) return;
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
         int cnt = S.tile_site_cnt[t];
         if (!cnt) continue;
         int src = S.tile_site_base[t], dst = S.tile_site_off[t], c = S.tile_ctg[t];
@@ -690,6 +698,10 @@ __global__ void k_order_sites(int n_tiles, HetScratch S, const int64_t *__restri
             S.site_rows[d] = (int)((m0 >> 2) + (m1 >> 2));
         }
     }
+    __threadfence_block();
+    __syncthreads();
+    const long long rows = fuz_cta_scan_i32(S.site_rows, S.site_row_off, total);
+    if (threadIdx.x == 0) fuz_scan_publish(st, FUZ_FIN_VMAP, O.cap_vmap, rows);
 }
 
 // One warp per site: the records covering the site, in record (= file) order, 32 at a
@@ -706,19 +718,17 @@ __global__ void __launch_bounds__(256) k_signature(
     const uint32_t lt = (1u << lane) - 1u;
     for (int s = warp_g; s < n_sites; s += n_warps) {
         const int gp = S.s_gpos[s];
-        const int c = O.d_site_ctg[s];
         const int b0 = O.d_site_top[2 * s], b1 = O.d_site_top[2 * s + 1];
         const uint32_t code0 = 1u << b0, code1 = 1u << b1;
         const int n0 = O.d_site_cnt[4 * s + b0], n1 = O.d_site_cnt[4 * s + b1];
-        const int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
-        const int rhi = fuz_upper_bound(S.r_gstart, r0, r1, gp);
-        const int rlo = fuz_lower_bound(S.r_gstart, r0, r1, gp - S.ctg_maxspan[c] + 1);
+        // records that can cover the site = candidates of its pileup tile (file order)
+        const int rlo = S.tile_rlo[gp / FUZ_TILE], rhi = S.tile_rhi[gp / FUZ_TILE];
         const int64_t off0 = S.site_row_off[s], off1 = off0 + n0;
         int run0 = 0, run1 = 0;
         for (int rb = rlo; rb < rhi; rb += 32) {
             int r = rb + lane;
             uint32_t nib = 0;
-            if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp) {
+            if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp && S.r_gstart[r] <= gp) {
                 uint32_t w = S.proj[S.r_woff[r] + ((gp >> 3) - (S.r_gstart[r] >> 3))];
                 nib = (w >> (4 * (gp & 7))) & 15u;
             }
@@ -837,11 +847,8 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         k_het_from_counts<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
-    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, FUZ_FIN_SITES, cap_sites))) return rc;
-    k_order_sites<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_order_sites");
-    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, FUZ_FIN_VMAP, out->cap_vmap)))
-        return rc;
+    k_sites_finalize<<<1, 1024, 0, st>>>(n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_sites_finalize");
     k_signature<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_signature");
     return FUZ_OK;

@@ -79,8 +79,9 @@ struct FuzLayout {
     }
 };
 int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l);
-// inter-stage buffer: row_off [cap_sites + 2] int32, dup [cap_vmap + 1] uint8
-int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup);
+// inter-stage buffer: row_off [cap_sites + 2] int32, at_off [cap_sites + 2] int32, dup [cap_vmap + 1] uint8
+int fuz_keep_commit(fuz_ctx *ctx, int64_t cap_sites, int64_t cap_vmap, int32_t **row_off, uint8_t **dup,
+                    int32_t **at_off = nullptr);
 template <typename T>
 static inline T *fuz_at(fuz_ctx *ctx, size_t off) { return reinterpret_cast<T *>(ctx->arena + off); }
 
@@ -134,11 +135,80 @@ __device__ __forceinline__ int fuz_upper_bound(const int32_t *a, int lo, int hi,
     }
     return lo;
 }
+// Exclusive scan of n int32 values by ONE CTA of 1024 threads (every thread of the CTA must
+// call it); out[n] = total, which is also returned (in every thread).  A pass = 4096 elements,
+// 4 consecutive ones per thread (one coalesced 128-bit load); the loads of 4 passes are issued
+// together so that arrays up to 16 K entries cost one memory round trip and one barrier per pass.
+__device__ __forceinline__ long long fuz_cta_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n) {
+    __shared__ int fuz_scan_tot[2][32];            // double buffered: one barrier per pass
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long carry_s = 0;                         // replicated in every thread
+    int buf = 0;
+    const bool vec_in = (reinterpret_cast<uintptr_t>(in) & 15) == 0, vec_out = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int64_t base = 0; base < n; base += 4096 * 4) {
+        int4 v[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
+            v[p] = make_int4(0, 0, 0, 0);
+            if (i0 < n) {
+                if (vec_in && i0 + 4 <= n) v[p] = *reinterpret_cast<const int4 *>(in + i0);
+                else {
+                    v[p].x = in[i0];
+                    if (i0 + 1 < n) v[p].y = in[i0 + 1];
+                    if (i0 + 2 < n) v[p].z = in[i0 + 2];
+                    if (i0 + 3 < n) v[p].w = in[i0 + 3];
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++, buf ^= 1) {
+            const int64_t i0 = base + p * 4096 + (int64_t)tid * 4;
+            if (base + p * 4096 >= n) break;       // uniform
+            const int s = v[p].x + v[p].y + v[p].z + v[p].w;
+            const int incl = fuz_warp_incl_scan(s, lane);
+            if (lane == 31) fuz_scan_tot[buf][warp] = incl;
+            __syncthreads();
+            const int t = fuz_scan_tot[buf][lane];
+            const int ti = fuz_warp_incl_scan(t, lane);
+            const int wexcl = __shfl_sync(0xffffffffu, ti - t, warp);
+            const int chunk_total = __shfl_sync(0xffffffffu, ti, 31);
+            const long long excl = carry_s + wexcl + (incl - s);
+            if (i0 < n) {
+                int4 o;
+                o.x = (int)excl; o.y = o.x + v[p].x; o.z = o.y + v[p].y; o.w = o.z + v[p].z;
+                if (vec_out && i0 + 4 <= n) *reinterpret_cast<int4 *>(out + i0) = o;
+                else {
+                    out[i0] = o.x;
+                    if (i0 + 1 < n) out[i0 + 1] = o.y;
+                    if (i0 + 2 < n) out[i0 + 2] = o.z;
+                    if (i0 + 3 < n) out[i0 + 3] = o.w;
+                }
+            }
+            carry_s += chunk_total;
+        }
+    }
+    if (tid == 0) out[n] = (int32_t)carry_s;
+    return carry_s;
+}
+
+// publish the total of a scan into the status block as a row count with a capacity check
+__device__ __forceinline__ void fuz_scan_publish(fuz_status *st, int fin_op, int64_t fin_cap, long long total) {
+    if (!st || st->error) return;
+    switch (fin_op) {
+    case 1: st->need_sites = total; if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 0); else st->n_sites = total; break;
+    case 2: st->need_vmap = total; if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 1); else st->n_vmap = total; break;
+    case 3: st->need_atable = total; if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 2); else st->n_atable = total; break;
+    case 4: st->need_reads = total; if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 3); else st->n_reads = total; break;
+    case 5: st->need_pairs = total; if (total > fin_cap) fuz_raise(st, FUZ_E_CAPACITY, 4); break;
+    default: break;
+    }
+}
 #endif
 
 // exclusive scan of n int32 values (n read from *d_n if d_n != nullptr, clamped to cap);
 // out has n+1 entries (out[n] = total).  fin_op publishes the total into the status block
 // as a row count with a capacity check (FUZ_FIN_NONE: nothing).
-enum { FUZ_FIN_NONE = 0, FUZ_FIN_SITES, FUZ_FIN_VMAP, FUZ_FIN_ATABLE, FUZ_FIN_READS, FUZ_FIN_PAIRS, FUZ_FIN_PROJ };
+enum { FUZ_FIN_NONE = 0, FUZ_FIN_SITES = 1, FUZ_FIN_VMAP = 2, FUZ_FIN_ATABLE = 3, FUZ_FIN_READS = 4, FUZ_FIN_PAIRS = 5 };
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap,
                  const int64_t *d_n, int fin_op, int64_t fin_cap);

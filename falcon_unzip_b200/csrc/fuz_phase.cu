@@ -59,36 +59,31 @@ struct AssocScratch {
 // sorted unique q_id lists per (site, allele): uq[row_off[s] ..) for allele al0 and
 // uq[row_off[s] + na0[s] ..) for allele al1, lengths uq_n[2s], uq_n[2s+1]; duplicate flags
 // of the rows (an earlier row of the same (site, allele) carries the same q_id: the
-// reference builds set(qids), phasing.py:189, :448-449).  One warp per site; the rows of a
-// site (depth many, a few dozen) are staged in shared memory and every lane ranks its own
-// rows against all of them.
-#define FUZ_UQ_ROWS 256
+// reference builds set(qids), phasing.py:189, :448-449).  One warp per site.  The q_ids of a
+// site span a small range (q_ids are handed out in coordinate order), so the common path
+// is a direct-address table in shared memory: first row per (q_id, allele) by atomicMin,
+// then ballot/popc compaction in q_id order.  Wider sites use all-pairs ranking.
+#define FUZ_UQ_RANGE 512
 __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ site_al, const uint8_t *__restrict__ vm_base,
                                                     const int32_t *__restrict__ vm_qid, AssocScratch A, fuz_status *st) {
     if (st->error) return;
-    __shared__ int s_q[8][FUZ_UQ_ROWS];
-    __shared__ uint8_t s_b[8][FUZ_UQ_ROWS], s_d[8][FUZ_UQ_ROWS];
+    __shared__ int s_first[8][2][FUZ_UQ_RANGE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_sites = (int)st->n_sites;
-    int *sq = s_q[wib];
-    uint8_t *sb = s_b[wib], *sd = s_d[wib];
+    const uint32_t lt = (1u << lane) - 1u;
     for (int s = warp_g; s < n_sites; s += n_warps) {
         const int off = A.row_off[s], n = A.row_off[s + 1] - off;
         const uint8_t al0 = site_al[2 * s], al1 = site_al[2 * s + 1];
-        const bool in_smem = n <= FUZ_UQ_ROWS;
         int c0 = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
         bool bad = al0 == al1 || al0 > 3 || al1 > 3;
-        __syncwarp();
         for (int i = lane; i < n; i += 32) {
             const uint8_t b = vm_base[off + i];
             const int q = vm_qid[off + i];
-            if (in_smem) { sq[i] = q; sb[i] = b; }
             if (b != al0 && b != al1) bad = true;
             c0 += b == al0;
             mn = min(mn, q); mx = max(mx, q);
         }
-        __syncwarp();
         c0 = __reduce_add_sync(0xffffffffu, c0);
         mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
         bad = __any_sync(0xffffffffu, bad);
@@ -96,37 +91,48 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
             if (lane == 0) { fuz_raise(st, FUZ_E_FORMAT, s); A.cand_cnt[s] = 0; }
             continue;
         }
-        // phase A: duplicate flag of every row (kept in shared memory for phase B)
-        for (int i = lane; i < n; i += 32) {
-            const int q = in_smem ? sq[i] : vm_qid[off + i];
-            const uint8_t b = in_smem ? sb[i] : vm_base[off + i];
-            bool dup = false;
-            for (int j = 0; j < i; j++) {
-                const int qj = in_smem ? sq[j] : vm_qid[off + j];
-                const uint8_t bj = in_smem ? sb[j] : vm_base[off + j];
-                if (qj == q && bj == b) { dup = true; break; }
-            }
-            A.dup[off + i] = dup ? 1 : 0;
-            if (in_smem) sd[i] = dup ? 1 : 0;
-        }
-        __syncwarp();
-        // phase B: slot of every first occurrence in the sorted unique list of its allele
         int u0 = 0, u1 = 0;
-        for (int i = lane; i < n; i += 32) {
-            if (in_smem ? sd[i] : A.dup[off + i]) continue;
-            const int q = in_smem ? sq[i] : vm_qid[off + i];
-            const uint8_t b = in_smem ? sb[i] : vm_base[off + i];
-            int rank = 0;
-            for (int j = 0; j < n; j++) {
-                const int qj = in_smem ? sq[j] : vm_qid[off + j];
-                const uint8_t bj = in_smem ? sb[j] : vm_base[off + j];
-                const uint8_t dj = in_smem ? sd[j] : A.dup[off + j];
-                rank += (!dj && bj == b && qj < q);
+        const long long range = (long long)mx - mn + 1;
+        if (range <= FUZ_UQ_RANGE) {
+            int *f0 = s_first[wib][0], *f1 = s_first[wib][1];
+            __syncwarp();
+            for (int x = lane; x < range; x += 32) { f0[x] = 0x7fffffff; f1[x] = 0x7fffffff; }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32)
+                atomicMin((vm_base[off + i] == al0 ? f0 : f1) + (vm_qid[off + i] - mn), i);
+            __syncwarp();
+            for (int i = lane; i < n; i += 32)
+                A.dup[off + i] = (vm_base[off + i] == al0 ? f0 : f1)[vm_qid[off + i] - mn] != i;
+            for (int base = 0; base < range; base += 32) {
+                const int x = base + lane;
+                const bool p0 = x < range && f0[x] != 0x7fffffff, p1 = x < range && f1[x] != 0x7fffffff;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+                if (p0) A.uq[off + u0 + __popc(m0 & lt)] = mn + x;
+                if (p1) A.uq[off + c0 + u1 + __popc(m1 & lt)] = mn + x;
+                u0 += __popc(m0); u1 += __popc(m1);
             }
-            A.uq[off + (b == al0 ? 0 : c0) + rank] = q;
-            if (b == al0) u0++; else u1++;
+        } else {
+            // all-pairs: duplicate flag, then the slot of every first occurrence in its sorted unique list
+            for (int i = lane; i < n; i += 32) {
+                const int q = vm_qid[off + i];
+                const uint8_t b = vm_base[off + i];
+                bool dup = false;
+                for (int j = 0; j < i; j++)
+                    if (vm_qid[off + j] == q && vm_base[off + j] == b) { dup = true; break; }
+                A.dup[off + i] = dup ? 1 : 0;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                if (A.dup[off + i]) continue;
+                const int q = vm_qid[off + i];
+                const uint8_t b = vm_base[off + i];
+                int rank = 0;
+                for (int j = 0; j < n; j++) rank += (!A.dup[off + j] && vm_base[off + j] == b && vm_qid[off + j] < q);
+                A.uq[off + (b == al0 ? 0 : c0) + rank] = q;
+                if (b == al0) u0++; else u1++;
+            }
+            u0 = __reduce_add_sync(0xffffffffu, u0); u1 = __reduce_add_sync(0xffffffffu, u1);
         }
-        u0 = __reduce_add_sync(0xffffffffu, u0); u1 = __reduce_add_sync(0xffffffffu, u1);
         if (lane == 0) {
             A.na0[s] = c0; A.uq_n[2 * s] = u0; A.uq_n[2 * s + 1] = u1; A.qmin[s] = mn; A.qmax[s] = mx;
             // number of later sites of the same contig within 65536 bp (phasing.py:166-170)
@@ -154,18 +160,32 @@ __device__ __forceinline__ int sorted_intersect(const int32_t *__restrict__ a, i
 
 // One warp per left site, one lane per candidate partner: 2x2 set-intersection sizes
 // (phasing.py:187-191), kept for the fill pass; emitted rows are capped at 501 per left
-// site AFTER the total >= 6 filter (phasing.py:192-206).
+// site AFTER the total >= 6 filter (phasing.py:192-206).  The two q_id sets of the left site
+// become bit masks over its (small) q_id range in shared memory; every lane then tests the
+// q_ids of its partner against them.  Left sites with a wide q_id range merge sorted lists.
+#define FUZ_PAIR_WORDS 16            // 512-bit masks
 __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *st) {
     if (st->error) return;
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_mask[8][2][FUZ_PAIR_WORDS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_sites = (int)st->n_sites;
+    uint32_t *m0 = s_mask[wib][0], *m1 = s_mask[wib][1];
     for (int i1 = warp_g; i1 < n_sites; i1 += n_warps) {
         const int nc = A.cand_cnt[i1];
         const int64_t base = A.cand_off[i1];
         const int o1 = A.row_off[i1], n10 = A.uq_n[2 * i1], n11 = A.uq_n[2 * i1 + 1];
         const int32_t *a0 = A.uq + o1, *a1 = A.uq + o1 + A.na0[i1];
         const int mn1 = A.qmin[i1], mx1 = A.qmax[i1];
+        const bool masked = (long long)mx1 - mn1 < 32 * FUZ_PAIR_WORDS;
+        __syncwarp();
+        if (masked && nc > 0) {
+            if (lane < FUZ_PAIR_WORDS) { m0[lane] = 0; m1[lane] = 0; }
+            __syncwarp();
+            for (int e = lane; e < n10; e += 32) { int x = a0[e] - mn1; atomicOr(&m0[x >> 5], 1u << (x & 31)); }
+            for (int e = lane; e < n11; e += 32) { int x = a1[e] - mn1; atomicOr(&m1[x >> 5], 1u << (x & 31)); }
+            __syncwarp();
+        }
         int emitted = 0;
         for (int k0 = 0; k0 < nc && emitted <= 500; k0 += 32) {
             const int k = k0 + lane;
@@ -176,10 +196,21 @@ __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *
                 if (A.qmin[i2] <= mx1 && mn1 <= A.qmax[i2]) {     // q_id ranges overlap
                     const int o2 = A.row_off[i2], n20 = A.uq_n[2 * i2], n21 = A.uq_n[2 * i2 + 1];
                     const int32_t *b0 = A.uq + o2, *b1 = A.uq + o2 + A.na0[i2];
-                    ct.x = sorted_intersect(a0, n10, b0, n20);
-                    ct.y = sorted_intersect(a0, n10, b1, n21);
-                    ct.z = sorted_intersect(a1, n11, b0, n20);
-                    ct.w = sorted_intersect(a1, n11, b1, n21);
+                    if (masked) {
+                        for (int e = 0; e < n20; e++) {
+                            const unsigned x = (unsigned)(b0[e] - mn1);
+                            if (x < 32u * FUZ_PAIR_WORDS) { ct.x += (m0[x >> 5] >> (x & 31)) & 1u; ct.z += (m1[x >> 5] >> (x & 31)) & 1u; }
+                        }
+                        for (int e = 0; e < n21; e++) {
+                            const unsigned x = (unsigned)(b1[e] - mn1);
+                            if (x < 32u * FUZ_PAIR_WORDS) { ct.y += (m0[x >> 5] >> (x & 31)) & 1u; ct.w += (m1[x >> 5] >> (x & 31)) & 1u; }
+                        }
+                    } else {
+                        ct.x = sorted_intersect(a0, n10, b0, n20);
+                        ct.y = sorted_intersect(a0, n10, b1, n21);
+                        ct.z = sorted_intersect(a1, n11, b0, n20);
+                        ct.w = sorted_intersect(a1, n11, b1, n21);
+                    }
                 }
                 A.pair_ct[base + k] = ct;
             }
@@ -234,14 +265,14 @@ __device__ __forceinline__ int row_d(const int32_t *__restrict__ at_ct, int row)
 }
 
 // zero the counters; first site of every contig; row range of every site as left site
-__global__ void k_blk_init(BlockScratch B, fuz_outputs O, int n_ctg, const fuz_status *st) {
+__global__ void k_blk_init(BlockScratch B, fuz_outputs O, int n_ctg, int right_off_valid, const fuz_status *st) {
     if (st->error) return;
     const int n_sites = (int)st->n_sites, n_at = (int)st->n_atable;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
         B.left_cnt[s] = 0;
         B.bsize[s] = 0;
         if (s < n_sites) B.left_cur[s] = 0;
-        B.right_off[s] = s == n_sites ? n_at : fuz_lower_bound(O.d_at_s1, 0, n_at, s);
+        if (!right_off_valid) B.right_off[s] = s == n_sites ? n_at : fuz_lower_bound(O.d_at_s1, 0, n_at, s);
         if (s <= n_ctg) B.ctg_site_off[s] = s == n_ctg ? n_sites : fuz_lower_bound(O.d_site_ctg, 0, n_sites, s);
     }
     // n_ctg may exceed n_sites + 1
@@ -726,12 +757,12 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     size_t o_pc = L.add(16 * (size_t)(A.max_pairs + 1));
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
-    if ((rc = fuz_keep_commit(ctx, cs, cv, &A.row_off, &A.dup))) return rc;
+    if ((rc = fuz_keep_commit(ctx, cs, cv, &A.row_off, &A.dup, &A.at_off))) return rc;   // at_off = row range per left site, reused by the block stage
     A.site_ctg = out->d_site_ctg; A.site_pos = out->d_site_pos;
     A.uq = fuz_at<int32_t>(ctx, o_uq); A.uq_n = fuz_at<int32_t>(ctx, o_uqn);
     A.na0 = fuz_at<int32_t>(ctx, o_na0); A.qmin = fuz_at<int32_t>(ctx, o_qmin); A.qmax = fuz_at<int32_t>(ctx, o_qmax);
     A.cand_cnt = fuz_at<int32_t>(ctx, o_cc); A.cand_off = fuz_at<int32_t>(ctx, o_co);
-    A.at_cnt = fuz_at<int32_t>(ctx, o_ac); A.at_off = fuz_at<int32_t>(ctx, o_ao);
+    A.at_cnt = fuz_at<int32_t>(ctx, o_ac); (void)o_ao;
     A.pair_ct = fuz_at<int4>(ctx, o_pc);
     const int64_t *d_ns = &ctx->d_status->n_sites;
 
@@ -750,7 +781,7 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     return FUZ_OK;
 }
 
-int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
+int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_valid) {
     cudaStream_t st = ctx->stream;
     const int64_t cs = out->cap_sites, ca = out->cap_atable;
     BlockScratch B;
@@ -764,14 +795,19 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out) {
     if (rc) return rc;
     B.ctg_site_off = fuz_at<int32_t>(ctx, o_cso); B.left_cnt = fuz_at<int32_t>(ctx, o_lc); B.left_off = fuz_at<int32_t>(ctx, o_lo);
     B.left_cur = fuz_at<int32_t>(ctx, o_lcur); B.lq = fuz_at<int32_t>(ctx, o_lq); B.ld = fuz_at<int32_t>(ctx, o_ld);
-    B.right_off = fuz_at<int32_t>(ctx, o_ro); B.min_k = fuz_at<int32_t>(ctx, o_mk); B.fp = fuz_at<uint32_t>(ctx, o_fp);
+    B.right_off = fuz_at<int32_t>(ctx, o_ro);
+    if (at_off_valid) {      // the association stage left the row range of every left site in the inter-stage buffer
+        int32_t *ro; uint8_t *dp; int32_t *ao;
+        if ((rc = fuz_keep_commit(ctx, cs, out->cap_vmap, &ro, &dp, &ao))) return rc;
+        B.right_off = ao;
+    } B.min_k = fuz_at<int32_t>(ctx, o_mk); B.fp = fuz_at<uint32_t>(ctx, o_fp);
     B.bidx = fuz_at<int32_t>(ctx, o_bi); B.bsize = fuz_at<int32_t>(ctx, o_bs); B.bnew = fuz_at<int32_t>(ctx, o_bn);
     B.dbg = ctx->profile ? fuz_at<long long>(ctx, o_dbg) : nullptr;
     if (!ctx->phase_attr_set) {
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;
     }
-    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, n_ctg, ctx->d_status);
+    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, n_ctg, at_off_valid ? 1 : 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
     k_edge_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
@@ -845,7 +881,7 @@ extern "C" int fuz_phased_blocks(fuz_ctx *ctx, int32_t n_ctg, int64_t n_sites, i
     if (!ctx || !out || n_ctg < 1 || n_sites < 0 || n_atable < 0 || n_sites > out->cap_sites || n_atable > out->cap_atable)
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_phased_blocks: bad arguments");
     int rc = set_counts(ctx, n_sites, -1, n_atable);
-    return rc ? rc : fuz_blocks_impl(ctx, n_ctg, out);
+    return rc ? rc : fuz_blocks_impl(ctx, n_ctg, out, false);
 }
 
 extern "C" int fuz_phased_reads(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, int64_t n_sites,
