@@ -146,143 +146,185 @@ __device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
     }
     return x;
 }
-__device__ __forceinline__ uint32_t fetch8(const uint8_t *seq, int q0) {   // global-memory slow path
-    const uint8_t *addr = seq + (q0 >> 1);
-    uintptr_t a = reinterpret_cast<uintptr_t>(addr);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
-    uint32_t lo = __funnelshift_r(w0, w1, sh);          // bytes 0..3
-    uint32_t b4 = (w1 >> sh) & 0xFFu;                   // byte 4
-    return keep_acgt(__funnelshift_r(swap_nibbles(lo), swap_nibbles(b4), (uint32_t)(q0 & 1) * 4));
-}
 // mask of the low n nibbles (n <= 0: none, n >= 8: all)
 __device__ __forceinline__ uint32_t low_nibbles(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(4 * n, 0)); }
 
-#define FUZ_STRIP 512          // words of the per-warp sliding output window (2 KB)
-#define FUZ_QWIN 512           // words of the per-warp SEQ window (2 KB = 4096 bases)
+#define FUZ_STRIP 512          // words of the per-warp output ring (2 KB = 4096 reference positions)
+#define FUZ_QWIN 1024          // words of the per-warp SEQ ring (4 KB = 8192 query bases)
+#define FUZ_FIT_Q 6000         // largest query span of a batch of segments served from the SEQ ring
 
 struct ProjWarp {              // per-warp state of k_project
-    uint32_t *strip;           // [FUZ_STRIP] output window, words strip_base .. strip_base + FUZ_STRIP
-    uint32_t *qwin;            // [FUZ_QWIN + 8] SEQ window: swapped + ACGT-only nibbles, query nibble qw_base + 8 * i at word i
+    uint32_t *strip;           // output ring: word w of the record's projection lives at strip[w & (FUZ_STRIP-1)],
+                               // valid for w in [strip_base, strip_base + FUZ_STRIP); words below strip_base are written
+    uint32_t *qwin;            // SEQ ring: 16-byte lines of SEQ (nibbles swapped, ACGT only); line L at words 4L & (FUZ_QWIN-1)
     uint32_t *out;             // the record's projection
-    const uint8_t *seq;
-    int strip_base, n_words4, qw_base, seq_nib_end, lane;
+    const uint8_t *qbase;      // address of line 0 (= 16 bytes before the 16-byte line holding SEQ[0])
+    const uint8_t *seq_end;    // end of SEQ
+    int qphase;                // nibble index of SEQ[0] inside the ring coordinates (32 .. 62)
+    int q_lines;               // lines [0, q_lines) have been staged; the ring keeps the last FUZ_QWIN / 4
+    int strip_base, n_words4, lane;
 };
 
-// flush the output window to the record's projection (128-bit stores) and clear it
-__device__ __forceinline__ void strip_flush(ProjWarp &P) {
+// write words [a, b) (multiples of 4) of the output ring to the projection and clear them
+__device__ __forceinline__ void strip_flush(ProjWarp &P, int a, int b) {
     __syncwarp();
-    uint4 *s4 = reinterpret_cast<uint4 *>(P.strip);
     uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
-#pragma unroll
-    for (int j = P.lane; j < FUZ_STRIP / 4; j += 32) {
-        int w = P.strip_base + 4 * j;
-        if (w < P.n_words4) o4[w >> 2] = s4[j];
-        s4[j] = make_uint4(0, 0, 0, 0);
+    for (int w = a + 4 * P.lane; w < b; w += 128) {
+        uint4 *s4 = reinterpret_cast<uint4 *>(P.strip + (w & (FUZ_STRIP - 1)));
+        if (w < P.n_words4) o4[w >> 2] = *s4;
+        *s4 = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
 }
 
-// (re)load the SEQ window so that it starts at (the 16-byte line holding) query nibble q_lo
-__device__ __forceinline__ void qwin_load(ProjWarp &P, int q_lo) {
-    uintptr_t a = reinterpret_cast<uintptr_t>(P.seq + (q_lo >> 1)) & ~(uintptr_t)15;
-    const uint8_t *wa = reinterpret_cast<const uint8_t *>(a);
-    P.qw_base = (int)(wa - P.seq) * 2;
-    const uint8_t *seq_end = P.seq + ((P.seq_nib_end + 1) >> 1);
+// make the output ring cover words [wlo, whi]; false if they span more than the ring
+__device__ __forceinline__ bool strip_cover(ProjWarp &P, int wlo, int whi) {
+    if (whi < P.strip_base + FUZ_STRIP) return true;
+    const int nb = wlo & ~3;
+    if (whi - nb >= FUZ_STRIP) return false;
+    strip_flush(P, P.strip_base, min(nb, P.strip_base + FUZ_STRIP));
+    if (nb > P.strip_base + FUZ_STRIP) {                  // nothing lands in between (long deletion): zeros
+        uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
+        for (int w = P.strip_base + FUZ_STRIP + 4 * P.lane; w < nb; w += 128)
+            if (w < P.n_words4) o4[w >> 2] = make_uint4(0, 0, 0, 0);
+    }
+    P.strip_base = nb;
+    return true;
+}
+
+// stage SEQ lines until ring coordinate y_hi is covered (the ring then still holds y_lo if the
+// caller respected FUZ_FIT_Q); each 16-byte line is loaded, nibble-swapped and filtered once
+__device__ __forceinline__ void qwin_cover(ProjWarp &P, int y_hi) {
+    if (y_hi <= 32 * P.q_lines) return;
     __syncwarp();
+    while (32 * P.q_lines < y_hi) {
 #pragma unroll
-    for (int j = P.lane; j < FUZ_QWIN / 4; j += 32) {
-        const uint8_t *src = wa + 16 * j;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (src < seq_end) v = __ldg(reinterpret_cast<const uint4 *>(src));
-        v.x = swap_nibbles(v.x); v.y = swap_nibbles(v.y); v.z = swap_nibbles(v.z); v.w = swap_nibbles(v.w);
-        if (multi_bits(v.x) | multi_bits(v.y) | multi_bits(v.z) | multi_bits(v.w)) {   // ambiguity codes: rare
-            v.x = keep_acgt(v.x); v.y = keep_acgt(v.y); v.z = keep_acgt(v.z); v.w = keep_acgt(v.w);
+        for (int k = 0; k < 2; k++) {
+            const int line = P.q_lines + 32 * k + P.lane;
+            const uint8_t *src = P.qbase + 16 * (int64_t)line;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (src < P.seq_end) v = __ldg(reinterpret_cast<const uint4 *>(src));
+            v.x = swap_nibbles(v.x); v.y = swap_nibbles(v.y); v.z = swap_nibbles(v.z); v.w = swap_nibbles(v.w);
+            if (multi_bits(v.x) | multi_bits(v.y) | multi_bits(v.z) | multi_bits(v.w)) {   // ambiguity codes: rare
+                v.x = keep_acgt(v.x); v.y = keep_acgt(v.y); v.z = keep_acgt(v.z); v.w = keep_acgt(v.w);
+            }
+            *reinterpret_cast<uint4 *>(P.qwin + ((4 * line) & (FUZ_QWIN - 1))) = v;
         }
-        reinterpret_cast<uint4 *>(P.qwin)[j] = v;
+        P.q_lines += 64;
     }
     __syncwarp();
 }
 
-// Place the segments held by the lanes (seg_len > 0 marks a lane with a segment: reference
-// start seg_rs, query start seg_qs) into the projection.  Work items are (segment, quad)
-// pairs -- a quad = 4 consecutive projection words = 32 reference positions -- flattened
-// over the 32 lanes; the segment of an item is found by a shuffle binary search over the
-// inclusive quad-count prefix.
-__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
+// the 32 positions of a quad whose first position is query nibble q0 (ring resident)
+__device__ __forceinline__ void fetch_quad(const ProjWarp &P, int q0, uint32_t (&v)[4]) {
+    const int y = q0 + P.qphase;
+    const int idx = y >> 3;
+    const uint32_t sh = (uint32_t)(y & 7) * 4;
+    const uint32_t m0 = P.qwin[idx & (FUZ_QWIN - 1)], m1 = P.qwin[(idx + 1) & (FUZ_QWIN - 1)],
+                   m2 = P.qwin[(idx + 2) & (FUZ_QWIN - 1)], m3 = P.qwin[(idx + 3) & (FUZ_QWIN - 1)],
+                   m4 = P.qwin[(idx + 4) & (FUZ_QWIN - 1)];
+    v[0] = __funnelshift_r(m0, m1, sh); v[1] = __funnelshift_r(m1, m2, sh);
+    v[2] = __funnelshift_r(m2, m3, sh); v[3] = __funnelshift_r(m3, m4, sh);
+}
+
+// A batch of match segments (one per lane; seg_len > 0 marks a lane with a segment: reference
+// start seg_rs, query start seg_qs) whose projection words fit the output ring and whose query
+// span fits the SEQ ring.  Work is split by quads (4 projection words = 32 positions):
+//   boundary quads (first / last quad of a segment, partially covered or shared with a
+//   neighbouring segment): masked and OR-merged into the ring, two per segment, spread over
+//   the lanes;
+//   interior quads (fully covered by one segment): flattened over all 32 lanes, no masks, one
+//   128-bit shared-memory store each.
+__device__ __forceinline__ void place_fit(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
     const int lane = P.lane;
+    const bool has = seg_len > 0;
+    const uint32_t hmask = __ballot_sync(0xffffffffu, has);
+    if (!hmask) return;
     const int qf = ((seg_rs >> 3) - W0) >> 2;
-    const int nq = seg_len > 0 ? ((((seg_rs + seg_len - 1) >> 3) - W0) >> 2) - qf + 1 : 0;
-    const int pinc = fuz_warp_incl_scan(nq, lane);
-    const int pexc = pinc - nq;
-    const int qtot = __shfl_sync(0xffffffffu, pinc, 31);
-    for (int b0 = 0; b0 < qtot; b0 += 32) {
+    const int ql = has ? ((((seg_rs + seg_len - 1) >> 3) - W0) >> 2) : qf;
+    // ---- boundary quads: lane 2r handles the first quad of the r-th segment, lane 2r+1 its last
+    const int n_seg = __popc(hmask);
+    for (int r0 = 0; r0 < n_seg; r0 += 16) {
+        const int r = r0 + (lane >> 1);
+        const bool act0 = r < n_seg;
+        const int src = act0 ? __fns(hmask, 0, r + 1) : 0;
+        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, src), o_len = __shfl_sync(0xffffffffu, seg_len, src);
+        const int o_qs = __shfl_sync(0xffffffffu, seg_qs, src);
+        const int o_qf = __shfl_sync(0xffffffffu, qf, src), o_ql = __shfl_sync(0xffffffffu, ql, src);
+        const bool act = act0 && ((lane & 1) == 0 || o_ql > o_qf);
+        if (act) {
+            const int Q = (lane & 1) ? o_ql : o_qf;
+            const int pq = (W0 + 4 * Q) << 3;
+            const int la = max(o_rs, pq) - pq, lb = min(o_rs + o_len, pq + 32) - pq;      // covered nibbles [la, lb)
+            uint32_t v[4];
+            fetch_quad(P, o_qs + (pq - o_rs), v);
+            uint32_t *dst = P.strip + ((4 * Q) & (FUZ_STRIP - 1));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t x = v[k] & low_nibbles(lb - 8 * k) & ~low_nibbles(la - 8 * k);
+                if (x) atomicOr(dst + k, x);
+            }
+        }
+    }
+    // ---- interior quads, flattened over the lanes
+    const int ni = has ? max(ql - qf - 1, 0) : 0;
+    const int pinc = fuz_warp_incl_scan(ni, lane);
+    const int pexc = pinc - ni;
+    const int itot = __shfl_sync(0xffffffffu, pinc, 31);
+    for (int b0 = 0; b0 < itot; b0 += 32) {
         const int i = b0 + lane;
-        const bool act = i < qtot;
         int idx = 0;                                    // first lane with pinc > i
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
             int t = __shfl_sync(0xffffffffu, pinc, idx + step - 1);
             if (t <= i) idx += step;
         }
-        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, idx);
-        const int o_len = __shfl_sync(0xffffffffu, seg_len, idx);
-        const int o_qs = __shfl_sync(0xffffffffu, seg_qs, idx);
-        const int o_pe = __shfl_sync(0xffffffffu, pexc, idx);
-        const int o_qf = __shfl_sync(0xffffffffu, qf, idx);
-        const int Q = o_qf + (i - o_pe);               // quad of the record's projection
-        const int pq = (W0 + 4 * Q) << 3;              // first global position of the quad
-        const int la = max(o_rs, pq) - pq, lb = min(o_rs + o_len, pq + 32) - pq;   // covered nibbles [la, lb)
-        const int q0 = o_qs + (pq - o_rs);             // query nibble of the quad's first position
-        // SEQ window: the quad reads query nibbles [q0, q0 + 40)
-        const int need_lo = __reduce_min_sync(0xffffffffu, act ? q0 + la : 0x7fffffff);
-        const int need_hi = __reduce_max_sync(0xffffffffu, act ? q0 + lb : -0x7fffffff);
-        if (need_lo - 32 < P.qw_base || need_hi + 8 > P.qw_base + 8 * FUZ_QWIN) qwin_load(P, max(need_lo - 32, -32));
-        uint32_t v[4] = {0, 0, 0, 0};
-        if (act) {
-            const int rel = q0 - P.qw_base;
-            if (rel >= 0 && rel + 40 <= 8 * FUZ_QWIN) {
-                const uint32_t *m = P.qwin + (rel >> 3);
-                const uint32_t sh = (uint32_t)(rel & 7) * 4;
-                uint32_t m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4];
-                v[0] = __funnelshift_r(m0, m1, sh); v[1] = __funnelshift_r(m1, m2, sh);
-                v[2] = __funnelshift_r(m2, m3, sh); v[3] = __funnelshift_r(m3, m4, sh);
-            } else {                                    // span larger than the window (huge insertion): global path
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (la < 8 * k + 8 && lb > 8 * k) v[k] = fetch8(P.seq, q0 + 8 * k);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) v[k] &= low_nibbles(lb - 8 * k) & ~low_nibbles(la - 8 * k);
+        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, idx), o_qs = __shfl_sync(0xffffffffu, seg_qs, idx);
+        const int o_qf = __shfl_sync(0xffffffffu, qf, idx), o_pe = __shfl_sync(0xffffffffu, pexc, idx);
+        if (i < itot) {
+            const int Q = o_qf + 1 + (i - o_pe);
+            const int pq = (W0 + 4 * Q) << 3;
+            uint32_t v[4];
+            fetch_quad(P, o_qs + (pq - o_rs), v);
+            *reinterpret_cast<uint4 *>(P.strip + ((4 * Q) & (FUZ_STRIP - 1))) = make_uint4(v[0], v[1], v[2], v[3]);
         }
-        const bool full = la == 0 && lb == 32;
-        const int W = 4 * Q;
-        bool done = !act;
-        for (;;) {
-            if (!done && W < P.strip_base + FUZ_STRIP) {
-                uint32_t *dst = P.strip + (W - P.strip_base);
-                // a fully covered quad belongs to one segment only; quads shared by two
-                // segments (around an insertion / deletion) are OR-merged
-                if (full) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) if (v[k]) atomicOr(dst + k, v[k]);
-                }
-                done = true;
-            }
-            if (__all_sync(0xffffffffu, done)) break;
-            strip_flush(P);
-            P.strip_base += FUZ_STRIP;
-            // skip windows that no remaining item touches (long deletions): all zero
-            int min_w = __reduce_min_sync(0xffffffffu, done ? 0x7fffffff : W);
-            while (min_w >= P.strip_base + FUZ_STRIP) {
-                uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
-                for (int j = lane; j < FUZ_STRIP / 4; j += 32)
-                    if (P.strip_base + 4 * j < P.n_words4) o4[(P.strip_base >> 2) + j] = make_uint4(0, 0, 0, 0);
-                P.strip_base += FUZ_STRIP;
-            }
+    }
+}
+
+// Place the segments held by the lanes into the projection.  The common case (a 32-op CIGAR
+// chunk spans ~2-3 kb) goes to place_fit in one piece; batches that are too wide for the rings
+// (long M operations, long deletions, long insertions) are fed to it one <= 2048-base piece of
+// one segment at a time.
+__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
+    const int lane = P.lane;
+    const bool has = seg_len > 0;
+    const uint32_t hmask = __ballot_sync(0xffffffffu, has);
+    if (!hmask) return;
+    const int wlo = __reduce_min_sync(0xffffffffu, has ? (seg_rs >> 3) - W0 : 0x7fffffff);
+    const int whi = __reduce_max_sync(0xffffffffu, has ? (((seg_rs + seg_len - 1) >> 3) - W0) | 3 : -1);
+    const int qlo = __reduce_min_sync(0xffffffffu, has ? seg_qs : 0x7fffffff);
+    const int qhi = __reduce_max_sync(0xffffffffu, has ? seg_qs + seg_len : -0x7fffffff);
+    if (qhi - qlo <= FUZ_FIT_Q && whi - (wlo & ~3) < FUZ_STRIP) {
+        strip_cover(P, wlo, whi);
+        const int y_lo = qlo - 32 + P.qphase;                // a long soft clip / insertion: skip, do not stage it
+        if (y_lo >= 32 * P.q_lines) P.q_lines = (y_lo >> 5) & ~63;
+        qwin_cover(P, qhi + 40 + P.qphase);
+        place_fit(seg_rs, seg_len, seg_qs, W0, P);
+        return;
+    }
+    for (uint32_t m = hmask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const int rs = __shfl_sync(0xffffffffu, seg_rs, j), ln = __shfl_sync(0xffffffffu, seg_len, j);
+        const int qs = __shfl_sync(0xffffffffu, seg_qs, j);
+        for (int o = 0; o < ln; o += 2048) {
+            const int pl = min(2048, ln - o);
+            const int pwlo = ((rs + o) >> 3) - W0, pwhi = (((rs + o + pl - 1) >> 3) - W0) | 3;
+            strip_cover(P, pwlo, pwhi);                 // a 2048-base piece always fits
+            // a query jump between pieces (long insertion) may leave the ring behind: restart it
+            const int y_lo = qs + o - 32 + P.qphase;
+            if (y_lo >= 32 * P.q_lines) P.q_lines = (y_lo >> 5) & ~63;
+            qwin_cover(P, qs + o + pl + 40 + P.qphase);
+            place_fit(rs + o, lane == 0 ? pl : 0, qs + o, W0, P);
         }
     }
 }
@@ -313,7 +355,7 @@ __global__ void __launch_bounds__(256, 4) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
     __shared__ __align__(16) uint32_t strips[8][FUZ_STRIP];
-    __shared__ __align__(16) uint32_t qwins[8][FUZ_QWIN + 8];
+    __shared__ __align__(16) uint32_t qwins[8][FUZ_QWIN];
     ProjWarp P;
     P.lane = threadIdx.x & 31;
     P.strip = strips[threadIdx.x >> 5];
@@ -322,7 +364,7 @@ __global__ void __launch_bounds__(256, 4) k_project(
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int j = lane; j < FUZ_STRIP; j += 32) P.strip[j] = 0;
-    for (int j = lane; j < FUZ_QWIN + 8; j += 32) P.qwin[j] = 0;
+    for (int j = lane; j < FUZ_QWIN; j += 32) P.qwin[j] = 0;
     __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     long long acc_aligned = 0, acc_accepted = 0;
@@ -399,12 +441,17 @@ __global__ void __launch_bounds__(256, 4) k_project(
         if (n_words == 0 || woff < 0) continue;
         // ---- pass 2: projection
         const int W0 = gstart >> 3;
-        P.seq = rec_buf + seq_off;
-        P.seq_nib_end = l_seq;
+        {
+            const uint8_t *seq = rec_buf + seq_off;
+            const uintptr_t a16 = reinterpret_cast<uintptr_t>(seq) & ~(uintptr_t)15;
+            P.qbase = reinterpret_cast<const uint8_t *>(a16) - 16;         // inside the record (>= 36 header bytes)
+            P.qphase = (int)(reinterpret_cast<uintptr_t>(seq) - a16) * 2 + 32;
+            P.seq_end = seq + ((l_seq + 1) >> 1);
+        }
+        P.q_lines = 0;
         P.out = S.proj + woff;
         P.n_words4 = n_words;
         P.strip_base = 0;
-        P.qw_base = -0x40000000;               // nothing staged yet
         int carry_rp = gstart, carry_qp = 0;
         bool open = false, overrun = false;
         int open_rs = 0, open_qs = 0;
@@ -457,7 +504,9 @@ __global__ void __launch_bounds__(256, 4) k_project(
         overrun = __any_sync(0xffffffffu, overrun);
         // the run still open at the end of the CIGAR
         if (!overrun) place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, P);
-        strip_flush(P);
+        strip_flush(P, P.strip_base, min(P.strip_base + FUZ_STRIP, n_words));
+        for (int w = P.strip_base + FUZ_STRIP + 4 * lane; w < n_words; w += 128)      // trailing deletion: no bases
+            reinterpret_cast<uint4 *>(P.out)[w >> 2] = make_uint4(0, 0, 0, 0);
         if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
     }
     if (lane == 0 && acc_accepted) {
@@ -493,10 +542,11 @@ __device__ __forceinline__ uint32_t plane_count(const uint32_t (&acc)[8], int bi
 // are reduced by a carry-save adder tree (11 full adders = 22 LOP3) to a 4-bit number per
 // (position, base) bit, which is rippled into 8 bit planes held in registers (depth <= 255
 // between spills into 16-bit counters).  No atomics, no shared-memory histogram.
-__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S, int64_t cap_sites,
-                                                                    uint32_t *__restrict__ counts_out, fuz_status *st) {
+__global__ void __launch_bounds__(FUZ_TILE_THREADS, 5) k_pileup_gather(HetScratch S, int64_t cap_sites,
+                                                                       uint32_t *__restrict__ counts_out, fuz_status *st) {
     if (st->error) return;
     __shared__ int4 l_ent[FUZ_TILE_THREADS];             // x = word offset of the projection, y = first word, z = words
+    __shared__ uint32_t c16s[16][FUZ_TILE_THREADS];      // spill counters (depth > 255 only): [4 * base + j][thread]
     __shared__ int s_warp_tot[FUZ_NW];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -506,11 +556,9 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S
     const int rlo = S.tile_rlo[tile], rhi = S.tile_rhi[tile];
     const uint32_t *__restrict__ proj = S.proj;
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};           // bit planes of the per-(position, base) counters
-    uint32_t c16[4][4];                                   // spill: 16-bit counters, base b, positions 2j / 2j+1
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) c16[b][j] = 0;
+    // spill: 16-bit counters, base b, positions 2j (low half) / 2j+1 (high half); kept in shared
+    // memory because they are touched only when more than 255 reads cover a tile
+#define C16(b, j) c16s[4 * (b) + (j)][tid]
     int n_reads_seen = 0, groups_in_acc = 0;
     bool spilled = false;
     for (int cb = rlo; cb < rhi; cb += FUZ_TILE_THREADS) {
@@ -556,7 +604,10 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S
 #pragma unroll
                 for (int b = 0; b < 4; b++)
 #pragma unroll
-                    for (int i = 0; i < 8; i++) c16[b][i >> 1] += plane_count(acc, 4 * i + b) << ((i & 1) * 16);
+                    for (int i = 0; i < 8; i++) {
+                        if (!spilled && (i & 1) == 0) C16(b, i >> 1) = 0;
+                        C16(b, i >> 1) += plane_count(acc, 4 * i + b) << ((i & 1) * 16);
+                    }
 #pragma unroll
                 for (int k = 0; k < 8; k++) acc[k] = 0;
                 groups_in_acc = 0;
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_pileup_gather(HetScratch S
         for (int i = 0; i < 8; i++)
 #pragma unroll
             for (int b = 0; b < 4; b++)
-                cnt[i][b] = ((c16[b][i >> 1] >> ((i & 1) * 16)) & 0xFFFFu) + plane_count(acc, 4 * i + b);
+                cnt[i][b] = (spilled ? (C16(b, i >> 1) >> ((i & 1) * 16)) & 0xFFFFu : 0u) + plane_count(acc, 4 * i + b);
         if (counts_out) {
             uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
 #pragma unroll
