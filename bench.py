@@ -43,12 +43,15 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicate", type=int, default=1, help="repeat the workload's contigs (named in config)")
+    ap.add_argument("--contigs", type=int, default=0, help="use only the first N contigs of the config (named in config)")
     return ap.parse_args()
 
 
-def make_workload(name: str, rank: int, replicate: int = 1):
+def make_workload(name: str, rank: int, replicate: int = 1, contigs: int = 0):
     from falcon_unzip_b200 import synth
     cfg = synth.CONFIGS[name]
+    if contigs:
+        cfg = dataclasses.replace(cfg, n_contigs=contigs)
     cfg = dataclasses.replace(cfg, first_contig=rank * cfg.n_contigs * replicate, n_contigs=cfg.n_contigs * replicate)
     return cfg, synth.generate_parallel(cfg)
 
@@ -165,7 +168,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg, sset = make_workload(args.config, 0, args.replicate)
+    cfg, sset = make_workload(args.config, 0, args.replicate, args.contigs)
     cores = os.cpu_count() or 1
     threads = min(cores, len(sset.refs))
     for _ in range(min(args.warmup, 1)):
@@ -192,7 +195,7 @@ def workload_config(cfg, sset, args, aligned_bases):
     return {"workload": "BASELINE.json configs[1]: synthetic E. coli-scale diploid, %d contigs x %d bp, %.0fx %d bp reads, "
                         "%.1f%% het, %.0f%% error" % (cfg.n_contigs, cfg.contig_len, cfg.coverage, cfg.mean_read_len,
                                                       100 * cfg.het_rate, 100 * cfg.error_rate)
-            if args.config == "c2" and args.replicate == 1 else
+            if args.config == "c2" and args.replicate == 1 and not args.contigs else
             "synthetic %s x%d: %d contigs x %d bp, %.0fx" % (args.config, args.replicate, cfg.n_contigs, cfg.contig_len, cfg.coverage),
             "contigs_per_gpu": cfg.n_contigs, "records_per_gpu": int(len(sset.rec_off) - 1),
             "aligned_bases_per_gpu_step": int(aligned_bases), "record_bytes_per_gpu": int(len(sset.records)),
@@ -206,7 +209,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg, sset = make_workload(args.config, rank, args.replicate)      # before CUDA init (fork)
+    cfg, sset = make_workload(args.config, rank, args.replicate, args.contigs)      # before CUDA init (fork)
     alg = algorithmic_bytes(sset)
 
     import torch

@@ -254,6 +254,7 @@ struct BlockScratch {
     int32_t *bidx, *bsize, *bnew;
     uint32_t *fp;   // forest pointer: parent * 2 + parity bit
     long long *dbg; // optional: per-contig phase timestamps (16 per contig), diagnostics only
+    int staging;    // ctx option "phase_staging"
 };
 
 #define FUZ_PHASE_THREADS 1024
@@ -362,40 +363,43 @@ __device__ __forceinline__ int cta_excl_max(int v, int *s_tmp, int *total) {   /
 
 // Lean form of the pass-2 sweep for the staged (shared-memory) case.  Per site the loop-carried
 // chain is: window shift -> select +-d -> REDUX -> sign -> window update.  The adjacency is
-// pre-packed per edge as (d << 6 | back), back = distance to the partner in sites, and is
-// loaded two sites ahead so that no load sits on the chain.  Sites whose partners do not fit
-// the fast path (more than 32 of them, or one more than 32 sites back) are flagged in s_slow
-// and take the generic code.
-__device__ __forceinline__ void sweep_sites_lean(int n, int lane, uint32_t *sbits, const int *__restrict__ s_loff,
-                                                 const int *__restrict__ s_lq, const int *__restrict__ s_ld,
+// pre-packed per edge as (d << 6 | back), back = distance to the partner in sites; list offsets
+// are read four sites ahead and edges two sites ahead into registers, so no load (and no
+// address computation depending on a load) sits on the chain.  Sites whose partners do not
+// fit the fast path (more than 32 of them, or one more than 32 sites back) are flagged in
+// s_slow and take the generic code.
+__device__ __noinline__ void sweep_sites_lean(int n, int lane, uint32_t *sbits, const int *__restrict__ s_loff,
+                                                 const int *__restrict__ s_lq, const int *__restrict__ s_ld, int q_base,
                                                  const int *__restrict__ s_pk, const uint8_t *__restrict__ s_slow) {
     volatile uint32_t *vb = sbits;
     uint32_t recent = 0;                                    // bit j = state of site i - 1 - j
     uint32_t word = vb[0];
-    auto edge = [&](int site) {                             // packed edge of `site` for this lane (0: none)
-        const int s = min(site, n - 1);
-        const int k = s_loff[s] + lane;
-        return (site < n && k < s_loff[s + 1]) ? s_pk[k] : 0;
-    };
-    int pk_cur = edge(0), pk_nxt = edge(1);
+    auto off_at = [&](int site) { return s_loff[min(site, n)]; };
+    auto edge_at = [&](int lo, int hi) { const int k = lo + lane; return k < hi ? s_pk[k] : 0; };
+    // register pipeline: offsets of sites i+2 .. i+4, packed edges of sites i, i+1
+    int o2 = off_at(2), o3 = off_at(3), o4 = off_at(4);
+    int pk_cur = edge_at(off_at(0), off_at(1)), pk_nxt = edge_at(off_at(1), o2);
     uint32_t slow_cur = s_slow[0] & 1u, slow_nxt = s_slow[min(1, n - 1)] & 1u;
+    int d = pk_cur >> 6, back = pk_cur & 31;
     for (int i = 0; i < n; i++) {
-        const int pk = pk_cur;
-        const uint32_t slow = slow_cur;
-        pk_cur = pk_nxt; slow_cur = slow_nxt;
-        pk_nxt = edge(i + 2);                               // two sites ahead: off the critical chain
-        slow_nxt = s_slow[min(i + 2, n - 1)] & 1u;
-        const int d = pk >> 6;
+        // ---- chain of site i (everything it needs is already in registers)
         const uint32_t own = (word >> (i & 31)) & 1u;
-        int s0 = ((recent >> (pk & 31)) & 1u) ? -d : d;     // lanes without a partner carry d = 0
-        if (slow) {                                         // uniform, rare: far or > 32 partners
+        const uint32_t sq = (recent >> back) & 1u;
+        int s0 = (d ^ -(int)sq) + (int)sq;                  // sq ? -d : d ; lanes without a partner carry d = 0
+        if (slow_cur) {                                     // uniform, rare: far or > 32 partners
             s0 = 0;
+#pragma unroll 1
             for (int k = s_loff[i] + lane; k < s_loff[i + 1]; k += 32) {
-                const int q2 = s_lq[k], d2 = s_ld[k], b2 = i - 1 - q2;
-                const uint32_t sq = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
-                s0 += sq ? -d2 : d2;
+                const int q2 = s_lq[k] - q_base, d2 = s_ld[k], b2 = i - 1 - q2;
+                const uint32_t sq2 = b2 < 32 ? (recent >> b2) & 1u : (vb[q2 >> 5] >> (q2 & 31)) & 1u;
+                s0 += sq2 ? -d2 : d2;
             }
         }
+        // ---- off the chain: edges of site i + 2, offsets of site i + 5, unpack site i + 1
+        const int pk_new = edge_at(o2, o3);
+        const uint32_t slow_new = s_slow[min(i + 2, n - 1)] & 1u;
+        o2 = o3; o3 = o4; o4 = off_at(i + 5);
+        const int d_n = pk_nxt >> 6, back_n = pk_nxt & 31;
         s0 = __reduce_add_sync(0xffffffffu, s0);
         const uint32_t nw = s0 < 0 ? 1u : (s0 > 0 ? 0u : own);
         recent = (recent << 1) | nw;
@@ -405,6 +409,7 @@ __device__ __forceinline__ void sweep_sites_lean(int n, int lane, uint32_t *sbit
             __syncwarp();
             if (i + 1 < n) word = vb[(i + 1) >> 5];
         }
+        pk_nxt = pk_new; slow_cur = slow_nxt; slow_nxt = slow_new; d = d_n; back = back_n;
     }
 }
 
@@ -474,24 +479,30 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     const int r0 = B.right_off[cs0], n_r = B.right_off[cs1] - r0;       // atable rows of the contig
     const int nbw = (n + 31) >> 5;
     if ((size_t)nbw * 4 > FUZ_PHASE_SMEM) { if (tid == 0) fuz_raise(st, FUZ_E_CAPACITY, 5); return; }
-    // shared-memory layout (words): bits | loff | lq | ld | roff | rq | rd | pos | fp
-    const size_t need = (size_t)nbw + (n + 1) + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + n + (n + 3) / 4 + 1 +
-                        4 * (size_t)n + n_e;
-    const bool staged = need * 4 <= FUZ_PHASE_SMEM;
+    // shared-memory layout (words).  Tier "sweep" (what the sequential sweep and the pointer
+    // jumping touch): bits | loff | pk | slow | fp.  Tier "full" adds what the parallel passes
+    // read: lq | ld | roff | rq | rd | pos | sc.  Large contigs that do not fit "full" still run
+    // the sweep from shared memory; the parallel passes then read global memory.
+    const size_t need_sweep = (size_t)nbw + (n + 1) + n_e + ((n + 3) / 4 + 1) + n;
+    const size_t need = need_sweep + 2 * (size_t)n_e + (n + 1) + 2 * (size_t)n_r + n + 4 * (size_t)n;
+    const bool staged = need * 4 <= FUZ_PHASE_SMEM && B.staging == 0;
+    const bool sweep_staged = need_sweep * 4 <= FUZ_PHASE_SMEM && B.staging <= 1;
     uint32_t *sbits = smem;                                   // [nbw] phase bit per site
     int *s_loff = reinterpret_cast<int *>(smem + nbw);        // [n + 1] left CSR offsets (relative to e0)
-    int *s_lq = s_loff + n + 1, *s_ld = s_lq + n_e;           // [n_e] partner (contig-local), cis - trans
+    int *s_pk = s_loff + n + 1;                               // [n_e] packed left edges for the sweep
+    uint8_t *s_slow = reinterpret_cast<uint8_t *>(s_pk + n_e);    // [n] site needs the generic sweep step (bit 0), in positions (bit 1)
+    volatile uint32_t *s_fp = reinterpret_cast<uint32_t *>(s_pk + n_e + (n + 3) / 4 + 1);   // [n] forest pointers (contig-local)
+    int *s_lq = s_pk + n_e + (n + 3) / 4 + 1 + n, *s_ld = s_lq + n_e;   // [n_e] partner (contig-local), cis - trans
     int *s_roff = s_ld + n_e;                                 // [n + 1] right row offsets (relative to r0)
     int *s_rq = s_roff + n + 1, *s_rd = s_rq + n_r;           // [n_r] partner (contig-local), cis - trans (0: rejected row)
     int *s_pos = s_rd + n_r;                                  // [n] 1-based positions
-    volatile uint32_t *s_fp = reinterpret_cast<uint32_t *>(s_pos + n);   // [n] forest pointers (contig-local)
-    uint8_t *s_slow = reinterpret_cast<uint8_t *>(s_pos + 2 * n);        // [n] site needs the generic sweep step (bit 0), in positions (bit 1)
-    int *s_sc = s_pos + 2 * n + (n + 3) / 4 + 1;                         // [4n] lscore, rscore, lext, rext of pass 3
-    int *s_pk = s_sc + 4 * n;                                            // [n_e] packed left edges for the sweep
+    int *s_sc = s_pos + n;                                    // [4n] lscore, rscore, lext, rext of pass 3
     if (B.dbg && tid == 0) B.dbg[c * 16 + 0] = clock64();
     for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
+    if (sweep_staged)
+        for (int i = tid; i <= n; i += nt) s_loff[i] = B.left_off[cs0 + i] - e0;
     if (staged) {
-        for (int i = tid; i <= n; i += nt) { s_loff[i] = B.left_off[cs0 + i] - e0; s_roff[i] = B.right_off[cs0 + i] - r0; }
+        for (int i = tid; i <= n; i += nt) s_roff[i] = B.right_off[cs0 + i] - r0;
         for (int k = tid; k < n_e; k += nt) { s_lq[k] = B.lq[e0 + k] - cs0; s_ld[k] = B.ld[e0 + k]; }
         for (int k = tid; k < n_r; k += nt) {
             int d = row_d(O.d_at_ct, r0 + k);
@@ -501,14 +512,14 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     }
     __syncthreads();
     // accessors (contig-local indices)
-    auto loff = [&](int i) { return staged ? s_loff[i] : B.left_off[cs0 + i] - e0; };
+    auto loff = [&](int i) { return sweep_staged ? s_loff[i] : B.left_off[cs0 + i] - e0; };
     auto lq = [&](int k) { return staged ? s_lq[k] : B.lq[e0 + k] - cs0; };
     auto ld = [&](int k) { return staged ? s_ld[k] : B.ld[e0 + k]; };
     auto roff = [&](int i) { return staged ? s_roff[i] : B.right_off[cs0 + i] - r0; };
     auto rq = [&](int k) { return staged ? s_rq[k] : O.d_at_s2[r0 + k] - cs0; };
     auto rd = [&](int k) { if (staged) return s_rd[k]; int d = row_d(O.d_at_ct, r0 + k); return abs(d) >= 6 ? d : 0; };
     auto pos_of = [&](int i) { return staged ? s_pos[i] : O.d_site_pos[cs0 + i]; };
-    volatile uint32_t *fp = staged ? s_fp : reinterpret_cast<volatile uint32_t *>(B.fp + cs0);
+    volatile uint32_t *fp = sweep_staged ? s_fp : reinterpret_cast<volatile uint32_t *>(B.fp + cs0);
     // smallest left partner of site i (slot in the left list), -1 if none
     auto min_left = [&](int i, int &d_out) {
         int best = -1, bq = 0x7fffffff;
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         bool in_pos = false;
         int ml = min_left(i, d);
         uint8_t slow_flag = (loff(i + 1) - loff(i) > 32) || (ml >= 0 && i - 1 - ml >= 32);
-        if (staged)
+        if (sweep_staged)
             for (int k = loff(i); k < loff(i + 1); k++) s_pk[k] = (ld(k) << 6) | ((i - 1 - lq(k)) & 31);
         if (ml >= 0) {
             in_pos = true;
@@ -543,7 +554,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         }
         fp[i] = ((uint32_t)parent << 1) | (uint32_t)bit;
         O.d_ph_state[cs0 + i] = in_pos ? 0 : 255;
-        if (staged) s_slow[i] = slow_flag | (in_pos ? 2 : 0);
+        if (sweep_staged) s_slow[i] = slow_flag | (in_pos ? 2 : 0);
     }
     __syncthreads();
     if (B.dbg && tid == 0) B.dbg[c * 16 + 2] = clock64();
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt)
-        if ((staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[cs0 + i] != 255) && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
+        if ((sweep_staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[cs0 + i] != 255) && (fp[i] & 1u)) atomicOr(&sbits[i >> 5], 1u << (i & 31));
     __syncthreads();
     // ---- pass 2: one left-to-right sweep (a second sweep never changes anything).
     // Sequential by construction: one warp walks the sites and nothing hides its latency, so
@@ -571,7 +582,8 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
     if (B.dbg && tid == 0) B.dbg[c * 16 + 3] = clock64();
     if (warp == 0) {
-        if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, s_pk, s_slow);
+        if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, 0, s_pk, s_slow);
+        else if (sweep_staged) sweep_sites_lean(n, lane, sbits, s_loff, B.lq + e0, B.ld + e0, cs0, s_pk, s_slow);
         else sweep_sites<false>(n, lane, sbits, B.left_off + cs0, B.lq + e0, B.ld + e0, e0, cs0);
     }
     __syncthreads();
@@ -579,7 +591,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
     for (int i = warp; i < n; i += nwarps) {
         const int x = cs0 + i;
-        const bool in_pos = staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255;
+        const bool in_pos = sweep_staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255;
         const int px = pos_of(i);
         int lscore = 0, rscore = 0, lext = px, rext = px;
         if (in_pos) {
@@ -803,6 +815,7 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_v
     } B.min_k = fuz_at<int32_t>(ctx, o_mk); B.fp = fuz_at<uint32_t>(ctx, o_fp);
     B.bidx = fuz_at<int32_t>(ctx, o_bi); B.bsize = fuz_at<int32_t>(ctx, o_bs); B.bnew = fuz_at<int32_t>(ctx, o_bn);
     B.dbg = ctx->profile ? fuz_at<long long>(ctx, o_dbg) : nullptr;
+    B.staging = ctx->phase_staging;
     if (!ctx->phase_attr_set) {
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;

@@ -131,6 +131,8 @@ const char *fuz_last_error(fuz_ctx *ctx);      /* ctx may be NULL: create-time e
 int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
 /* options: "pileup_impl" 0 = tiled register pileup fused with the het test (default),
  *          1 = global-atomic pileup + separate het test (cross-check path);
+ *          "phase_staging" 0 = stage as much of a contig as fits in shared memory (default),
+ *                          1 = at most the sweep tier, 2 = global memory only (both for tests),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */
 int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value);
 int fuz_sync(fuz_ctx *ctx);

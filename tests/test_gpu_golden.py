@@ -118,6 +118,25 @@ def test_c1_scale_contig_vs_oracle(eng, tmp_path):
     assert len(open(want["phased_reads"]).read().splitlines()) > 500
 
 
+@pytest.mark.parametrize("staging", [1, 2])
+def test_phase_staging_tiers_vs_oracle(eng, staging, tmp_path):
+    """k_ctg_phase keeps a contig in shared memory in full, for the sweep only, or not at all
+    (large contigs); the two smaller tiers are forced here on a contig that would fit in full."""
+    from conftest import synth_set
+    from falcon_unzip_b200 import phasing
+    from oracle import c_oracle
+    sset = synth_set("c1", contig_len=300_000)
+    name = sset.refs[0][0]
+    want = c_oracle.run_phasing_stages(sset.contig_records(0), name, sset.ref_seqs[0], str(tmp_path / "oracle"))
+    eng.set_option("phase_staging", staging)
+    try:
+        _res, got = phasing.phase_contigs(sset.records, [name], sset.ref_seqs, str(tmp_path / "gpu"))
+    finally:
+        eng.set_option("phase_staging", 0)
+    for k in FILES:
+        assert open(want[k]).read() == open(got[name][k]).read(), k
+
+
 def test_c1_full_size_contig_vs_oracle(eng, tmp_path):
     """BASELINE.json config 1 at full size: 1 Mb contig, 0.1 % het, 30x 10 kb reads, 1 % error."""
     from falcon_unzip_b200 import phasing, synth
