@@ -306,7 +306,7 @@ def run_b200(args):
                 "config": workload_config(cfg, sset, args, aligned),
                 "e2e": {"value": total_units / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(r.h2d_bytes),
                         "d2h_bytes_per_step": int(r.d2h_bytes), "ms_per_step": e2e_ms_max, "steps": e2e_steps,
-                        "api": "fuz_phase_batch_host (pinned host BAM records in, host row arrays out)"},
+                        "api": "fuz_phase_batch_host (pinned host BAM records in, host row arrays out; header/name/CIGAR/SEQ of each record cross PCIe, QUAL and tags do not)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_project + k_pileup_gather (pileup + het test, timed as one group)", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),

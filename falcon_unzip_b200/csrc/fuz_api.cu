@@ -43,6 +43,69 @@ static int ensure_stage(fuz_ctx *ctx, size_t dev_bytes, size_t pin_bytes) {
     return FUZ_OK;
 }
 
+// ---------------------------------------------------------------- selective record fetch
+// Host-buffer entry, records in page-locked host memory: the kernels need the fixed header,
+// read name, CIGAR and SEQ of a BAM record -- not QUAL (one byte per base, ~2/3 of a PacBio
+// record) or the tags.  Instead of a cudaMemcpy of the whole buffer, one warp per record
+// reads exactly those bytes through the host mapping (128-bit loads, 16-byte lines) and writes
+// them at the SAME offsets of the device buffer, so every later kernel sees an ordinary
+// record buffer whose unread parts are simply not populated.
+// The first 512 bytes from the 16-byte line holding the record start are always fetched (they
+// carry the header, from which the needed length follows); the rest up to the end of SEQ.
+#define FUZ_FETCH_SLAB 512
+__global__ void __launch_bounds__(256) k_fetch_records(const uint8_t *__restrict__ h_src, uint8_t *__restrict__ d_dst,
+                                                       const int64_t *__restrict__ rec_off, int n_rec, int64_t rec_bytes,
+                                                       unsigned long long *fetched) {
+    __shared__ __align__(16) uint8_t head[8][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int64_t whole = rec_bytes & ~(int64_t)15;               // 16-byte lines fully inside the buffer
+    unsigned long long bytes = 0;
+    for (int r = warp_g; r < n_rec; r += n_warps) {
+        const int64_t off_r = rec_off[r], off_n = rec_off[r + 1];
+        if (off_r < 0 || off_n < off_r || off_n > rec_bytes) continue;      // the record kernels report it
+        const int64_t a0 = off_r & ~(int64_t)15;
+        // slab: 32 lines from a0
+        const int64_t s_off = a0 + 16 * lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const bool s_in = s_off + 16 <= whole;
+        if (s_in) {
+            v = __ldcs(reinterpret_cast<const uint4 *>(h_src + s_off));
+            *reinterpret_cast<uint4 *>(d_dst + s_off) = v;
+        }
+        if (lane < 4) *reinterpret_cast<uint4 *>(&head[wib][16 * lane]) = v;
+        __syncwarp();
+        // header fields (record-relative offsets 12, 16, 20; the record start is not aligned)
+        const int sh = (int)(off_r - a0);
+        auto u32_at = [&](int o) {
+            const uint8_t *b = &head[wib][sh + o];
+            return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+        };
+        const int64_t l_name = u32_at(12) & 0xFF, n_cig = u32_at(16) & 0xFFFF;
+        const int64_t l_seq = (int32_t)u32_at(20);
+        __syncwarp();
+        int64_t need = 36 + l_name + 4 * n_cig + (l_seq > 0 ? (l_seq + 1) / 2 : 0);
+        need = min(max(need, (int64_t)36), off_n - off_r);         // a bad header: the validation sees the record as it is
+        int64_t end = min((off_r + need + 15) & ~(int64_t)15, whole);
+        const int64_t body = a0 + FUZ_FETCH_SLAB;
+        // body: 4 lines per lane in flight
+        for (int64_t o = body + 16 * lane; o < end; o += 4 * 512) {
+            uint4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (o + 512 * j < end) w[j] = __ldcs(reinterpret_cast<const uint4 *>(h_src + o + 512 * j));
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (o + 512 * j < end) *reinterpret_cast<uint4 *>(d_dst + o + 512 * j) = w[j];
+        }
+        if (lane == 0) bytes += (unsigned long long)(max(end, min(body, whole)) - a0);
+        // tail of the buffer that is not a whole line (last record only)
+        if (off_r + need > whole && lane == 0)
+            for (int64_t o = max(whole, a0); o < min(off_r + need, rec_bytes); o++) { d_dst[o] = h_src[o]; bytes++; }
+    }
+    if (lane == 0 && bytes) atomicAdd(fetched, bytes);
+}
+
 extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_outputs *out, fuz_status *h_status,
                                     int64_t *h2d_bytes, int64_t *d2h_bytes) {
     if (!ctx || !in || !out || !h_status) return FUZ_E_ARG;
@@ -52,11 +115,11 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     // tile-aligned global offsets (host, tiny)
     int64_t total_nq = 0;
     FuzLayout P;   // pinned
-    size_t p_goff = P.add(8 * (size_t)(n_ctg + 1));
+    size_t p_goff = P.add(8 * (size_t)(n_ctg + 1)), p_fetched = P.add(8);
     FuzLayout D;   // device
     size_t d_rec = D.add((size_t)in->rec_bytes + 16), d_off = D.add(8 * (size_t)(n_rec + 1)), d_qid = D.add(4 * (size_t)(n_rec + 1));
     size_t d_cro = D.add(4 * (size_t)(n_ctg + 1)), d_clen = D.add(4 * (size_t)n_ctg), d_goff = D.add(8 * (size_t)(n_ctg + 1));
-    size_t d_cnq = D.add(4 * (size_t)n_ctg);
+    size_t d_cnq = D.add(4 * (size_t)n_ctg), d_fetched = D.add(8);
     const int64_t cs = out->cap_sites, cv = out->cap_vmap, ca = out->cap_atable, cr = out->cap_reads;
     size_t o_sctg = D.add(4 * (size_t)cs), o_spos = D.add(4 * (size_t)cs), o_scnt = D.add(16 * (size_t)cs);
     size_t o_sal = D.add(2 * (size_t)cs), o_stop = D.add(2 * (size_t)cs);
@@ -83,9 +146,27 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
         up += (int64_t)bytes;
         return bytes ? cudaMemcpyAsync(dv + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
     };
-    FUZ_CUDA(ctx, h2d(d_rec, in->h_rec_buf, (size_t)in->rec_bytes));
-    FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 16, st));
+    // records in page-locked memory that the device can address: fetch only what the kernels read
+    const uint8_t *mapped = nullptr;
+    if (ctx->host_fetch && in->rec_bytes > 0 && n_rec > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, in->h_rec_buf) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            mapped = static_cast<const uint8_t *>(pa.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
     FUZ_CUDA(ctx, h2d(d_off, in->h_rec_off, 8 * (size_t)(n_rec + 1)));
+    if (mapped) {
+        FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_fetched, 0, 8, st));
+        k_fetch_records<<<FUZ_GRID_BLOCKS * 2, 256, 0, st>>>(mapped, dv + d_rec, reinterpret_cast<const int64_t *>(dv + d_off),
+                                                             n_rec, in->rec_bytes,
+                                                             reinterpret_cast<unsigned long long *>(dv + d_fetched));
+        FUZ_LAUNCH_CHECK(ctx, "k_fetch_records");
+        FUZ_CUDA(ctx, cudaMemcpyAsync(ctx->stage_pin + p_fetched, dv + d_fetched, 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        FUZ_CUDA(ctx, h2d(d_rec, in->h_rec_buf, (size_t)in->rec_bytes));
+    }
+    FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 16, st));
     FUZ_CUDA(ctx, h2d(d_qid, in->h_rec_qid, 4 * (size_t)n_rec));
     FUZ_CUDA(ctx, h2d(d_cro, in->h_ctg_rec_off, 4 * (size_t)(n_ctg + 1)));
     FUZ_CUDA(ctx, h2d(d_clen, in->h_ctg_len, 4 * (size_t)n_ctg));
@@ -115,6 +196,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     o.d_counts = nullptr;
     if ((rc = fuz_phase_batch(ctx, &b, &o))) return rc;
     rc = fuz_get_status(ctx, h_status);          // synchronises; row counts now known
+    if (mapped) up += *reinterpret_cast<const int64_t *>(ctx->stage_pin + p_fetched);
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = (int64_t)sizeof(fuz_status);
     if (rc) return rc;

@@ -131,6 +131,8 @@ const char *fuz_last_error(fuz_ctx *ctx);      /* ctx may be NULL: create-time e
 int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
 /* options: "pileup_impl" 0 = tiled register pileup fused with the het test (default),
  *          1 = global-atomic pileup + separate het test (cross-check path);
+ *          "host_fetch" 1 = fuz_phase_batch_host reads page-locked records through the host mapping and
+ *                       moves only header/name/CIGAR/SEQ (default), 0 = always copy the whole buffer,
  *          "phase_staging" 0 = stage as much of a contig as fits in shared memory (default),
  *                          1 = at most the sweep tier, 2 = global memory only (both for tests),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */

@@ -128,3 +128,32 @@ def test_m_style_cigar_and_single_contig(eng, tmp_path):
     want = _oracle_files(sset, tmp_path / "oracle")
     _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs, str(tmp_path / "gpu"))
     _assert_same_files(want, got)
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+def test_selective_fetch_of_pinned_records_equals_full_copy(eng, cfg):
+    """Host entry with page-locked records: only header/name/CIGAR/SEQ cross PCIe
+    (k_fetch_records); results equal the whole-buffer copy and the pageable-memory path."""
+    from falcon_unzip_b200 import engine
+
+    def run(s, fetch, pin):
+        eng.set_option("host_fetch", fetch)
+        pb = engine.prepare_batch(s.records, [r[0] for r in s.refs], [r[1] for r in s.refs], pin=pin)
+        return eng.phase_host(pb)
+
+    other, sset = synth_set("quirks" if cfg == "tiny" else "tiny"), synth_set(cfg)
+    try:
+        run(other, 1, True)                 # leaves another batch's bytes in the device staging
+        got = run(sset, 1, True)
+        full = run(sset, 0, True)
+        run(other, 1, True)
+        pageable = run(sset, 1, False)
+    finally:
+        eng.set_option("host_fetch", 1)
+    assert got.h2d_bytes < 0.6 * full.h2d_bytes and pageable.h2d_bytes == full.h2d_bytes
+    for res in (got, pageable):
+        assert (res.n_sites, res.n_vmap, res.n_atable, res.n_reads, res.aligned_bases) == \
+               (full.n_sites, full.n_vmap, full.n_atable, full.n_reads, full.aligned_bases)
+        for k, a in full.arrays.items():
+            assert np.array_equal(res.arrays[k], a), k
+    assert full.n_sites > 0 and full.n_reads > 0
