@@ -146,186 +146,106 @@ __device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
     }
     return x;
 }
-// mask of the low n nibbles (n <= 0: none, n >= 8: all)
-__device__ __forceinline__ uint32_t low_nibbles(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(4 * n, 0)); }
 
-#define FUZ_STRIP 512          // words of the per-warp output ring (2 KB = 4096 reference positions)
-#define FUZ_QWIN 1024          // words of the per-warp SEQ ring (4 KB = 8192 query bases)
-#define FUZ_FIT_Q 6000         // largest query span of a batch of segments served from the SEQ ring
+#define FUZ_SEGCAP 256         // match segments buffered per warp before their quads are emitted
 
-struct ProjWarp {              // per-warp state of k_project
-    uint32_t *strip;           // output ring: word w of the record's projection lives at strip[w & (FUZ_STRIP-1)],
-                               // valid for w in [strip_base, strip_base + FUZ_STRIP); words below strip_base are written
-    uint32_t *qwin;            // SEQ ring: 16-byte lines of SEQ (nibbles swapped, ACGT only); line L at words 4L & (FUZ_QWIN-1)
+// The match segments of a record (maximal runs of M/=/X; reference [rs, re), query offset
+// dq = query position - reference position) sit in a per-warp shared-memory list ordered by
+// rs.  The projection is produced in quads (4 words = 32 reference positions, one 128-bit
+// store).  Every quad has at most one OWNER, the first segment that intersects it; a segment
+// is a non-owner only in the quad it starts in (when an earlier segment ends there).  So:
+//   phase 1: one lane per quad, rows of 32 consecutive quads: look up the owner, cut its 32
+//            query nibbles out of SEQ (five aligned 32-bit loads, nibble swap, funnel shift),
+//            mask to the segment, store the quad (zeros where nothing lands: deletions, padding);
+//   phase 2: one lane per segment that starts in a quad it does not own: same cut, OR-merged
+//            into the stored quad (atomicOr; the words are still in L2).
+struct ProjRec {
+    const uint32_t *base4;     // SEQ address rounded down to 4 bytes
+    int nphase;                // nibble index of SEQ[0] relative to base4 (0, 2, 4, 6)
+    int W0;                    // first word of the record on the global 8-position grid
     uint32_t *out;             // the record's projection
-    const uint8_t *qbase;      // address of line 0 (= 16 bytes before the 16-byte line holding SEQ[0])
-    const uint8_t *seq_end;    // end of SEQ
-    int qphase;                // nibble index of SEQ[0] inside the ring coordinates (32 .. 62)
-    int q_lines;               // lines [0, q_lines) have been staged; the ring keeps the last FUZ_QWIN / 4
-    int strip_base, n_words4, lane;
 };
 
-// write words [a, b) (multiples of 4) of the output ring to the projection and clear them
-__device__ __forceinline__ void strip_flush(ProjWarp &P, int a, int b) {
-    __syncwarp();
-    uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
-    for (int w = a + 4 * P.lane; w < b; w += 128) {
-        uint4 *s4 = reinterpret_cast<uint4 *>(P.strip + (w & (FUZ_STRIP - 1)));
-        if (w < P.n_words4) o4[w >> 2] = *s4;
-        *s4 = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-}
-
-// make the output ring cover words [wlo, whi]; false if they span more than the ring
-__device__ __forceinline__ bool strip_cover(ProjWarp &P, int wlo, int whi) {
-    if (whi < P.strip_base + FUZ_STRIP) return true;
-    const int nb = wlo & ~3;
-    if (whi - nb >= FUZ_STRIP) return false;
-    strip_flush(P, P.strip_base, min(nb, P.strip_base + FUZ_STRIP));
-    if (nb > P.strip_base + FUZ_STRIP) {                  // nothing lands in between (long deletion): zeros
-        uint4 *o4 = reinterpret_cast<uint4 *>(P.out);
-        for (int w = P.strip_base + FUZ_STRIP + 4 * P.lane; w < nb; w += 128)
-            if (w < P.n_words4) o4[w >> 2] = make_uint4(0, 0, 0, 0);
-    }
-    P.strip_base = nb;
-    return true;
-}
-
-// stage SEQ lines until ring coordinate y_hi is covered (the ring then still holds y_lo if the
-// caller respected FUZ_FIT_Q); each 16-byte line is loaded, nibble-swapped and filtered once
-__device__ __forceinline__ void qwin_cover(ProjWarp &P, int y_hi) {
-    if (y_hi <= 32 * P.q_lines) return;
-    __syncwarp();
-    while (32 * P.q_lines < y_hi) {
+// the piece of segment (a, b, dq) inside the quad starting at reference position Q0:
+// positions [lo, hi) of the quad (hi <= lo: nothing), ambiguity codes removed
+__device__ __forceinline__ void quad_piece(const ProjRec &R, int Q0, int a, int b, int dq, uint32_t (&v)[4]) {
+    const int lo4 = 4 * max(a - Q0, 0), hi4 = 4 * min(b - Q0, 32);
+    const int n = Q0 + dq + R.nphase;                     // nibble of position Q0 relative to base4 (>= -31)
+    const uint32_t *src = R.base4 + (n >> 3);
+    const uint32_t sh = (uint32_t)(n & 7) * 4;
+    uint32_t m[5];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int line = P.q_lines + 32 * k + P.lane;
-            const uint8_t *src = P.qbase + 16 * (int64_t)line;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (src < P.seq_end) v = __ldg(reinterpret_cast<const uint4 *>(src));
-            v.x = swap_nibbles(v.x); v.y = swap_nibbles(v.y); v.z = swap_nibbles(v.z); v.w = swap_nibbles(v.w);
-            if (multi_bits(v.x) | multi_bits(v.y) | multi_bits(v.z) | multi_bits(v.w)) {   // ambiguity codes: rare
-                v.x = keep_acgt(v.x); v.y = keep_acgt(v.y); v.z = keep_acgt(v.z); v.w = keep_acgt(v.w);
-            }
-            *reinterpret_cast<uint4 *>(P.qwin + ((4 * line) & (FUZ_QWIN - 1))) = v;
-        }
-        P.q_lines += 64;
-    }
-    __syncwarp();
-}
-
-// the 32 positions of a quad whose first position is query nibble q0 (ring resident)
-__device__ __forceinline__ void fetch_quad(const ProjWarp &P, int q0, uint32_t (&v)[4]) {
-    const int y = q0 + P.qphase;
-    const int idx = y >> 3;
-    const uint32_t sh = (uint32_t)(y & 7) * 4;
-    const uint32_t m0 = P.qwin[idx & (FUZ_QWIN - 1)], m1 = P.qwin[(idx + 1) & (FUZ_QWIN - 1)],
-                   m2 = P.qwin[(idx + 2) & (FUZ_QWIN - 1)], m3 = P.qwin[(idx + 3) & (FUZ_QWIN - 1)],
-                   m4 = P.qwin[(idx + 4) & (FUZ_QWIN - 1)];
-    v[0] = __funnelshift_r(m0, m1, sh); v[1] = __funnelshift_r(m1, m2, sh);
-    v[2] = __funnelshift_r(m2, m3, sh); v[3] = __funnelshift_r(m3, m4, sh);
-}
-
-// A batch of match segments (one per lane; seg_len > 0 marks a lane with a segment: reference
-// start seg_rs, query start seg_qs) whose projection words fit the output ring and whose query
-// span fits the SEQ ring.  Work is split by quads (4 projection words = 32 positions):
-//   boundary quads (first / last quad of a segment, partially covered or shared with a
-//   neighbouring segment): masked and OR-merged into the ring, two per segment, spread over
-//   the lanes;
-//   interior quads (fully covered by one segment): flattened over all 32 lanes, no masks, one
-//   128-bit shared-memory store each.
-__device__ __forceinline__ void place_fit(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
-    const int lane = P.lane;
-    const bool has = seg_len > 0;
-    const uint32_t hmask = __ballot_sync(0xffffffffu, has);
-    if (!hmask) return;
-    const int qf = ((seg_rs >> 3) - W0) >> 2;
-    const int ql = has ? ((((seg_rs + seg_len - 1) >> 3) - W0) >> 2) : qf;
-    // ---- boundary quads: lane 2r handles the first quad of the r-th segment, lane 2r+1 its last
-    const int n_seg = __popc(hmask);
-    for (int r0 = 0; r0 < n_seg; r0 += 16) {
-        const int r = r0 + (lane >> 1);
-        const bool act0 = r < n_seg;
-        const int src = act0 ? __fns(hmask, 0, r + 1) : 0;
-        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, src), o_len = __shfl_sync(0xffffffffu, seg_len, src);
-        const int o_qs = __shfl_sync(0xffffffffu, seg_qs, src);
-        const int o_qf = __shfl_sync(0xffffffffu, qf, src), o_ql = __shfl_sync(0xffffffffu, ql, src);
-        const bool act = act0 && ((lane & 1) == 0 || o_ql > o_qf);
-        if (act) {
-            const int Q = (lane & 1) ? o_ql : o_qf;
-            const int pq = (W0 + 4 * Q) << 3;
-            const int la = max(o_rs, pq) - pq, lb = min(o_rs + o_len, pq + 32) - pq;      // covered nibbles [la, lb)
-            uint32_t v[4];
-            fetch_quad(P, o_qs + (pq - o_rs), v);
-            uint32_t *dst = P.strip + ((4 * Q) & (FUZ_STRIP - 1));
+    for (int k = 0; k < 5; k++) m[k] = __ldg(src + k);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t x = v[k] & low_nibbles(lb - 8 * k) & ~low_nibbles(la - 8 * k);
-                if (x) atomicOr(dst + k, x);
-            }
-        }
+    for (int k = 0; k < 5; k++) m[k] = swap_nibbles(m[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t mh = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(hi4 - 32 * k, 0));
+        const uint32_t ml = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(lo4 - 32 * k, 0));
+        v[k] = __funnelshift_r(m[k], m[k + 1], sh) & mh & ~ml;
     }
-    // ---- interior quads, flattened over the lanes
-    const int ni = has ? max(ql - qf - 1, 0) : 0;
-    const int pinc = fuz_warp_incl_scan(ni, lane);
-    const int pexc = pinc - ni;
-    const int itot = __shfl_sync(0xffffffffu, pinc, 31);
-    for (int b0 = 0; b0 < itot; b0 += 32) {
-        const int i = b0 + lane;
-        int idx = 0;                                    // first lane with pinc > i
+    if (multi_bits(v[0]) | multi_bits(v[1]) | multi_bits(v[2]) | multi_bits(v[3])) {        // ambiguity codes: rare
+        v[0] = keep_acgt(v[0]); v[1] = keep_acgt(v[1]); v[2] = keep_acgt(v[2]); v[3] = keep_acgt(v[3]);
+    }
+}
+
+// quads [q_from, q_to) of the record from the segment list (see above)
+__device__ __forceinline__ void emit_quads(const int *__restrict__ s_rs, const int *__restrict__ s_re,
+                                           const int *__restrict__ s_dq, int n_seg, int q_from, int q_to,
+                                           const ProjRec &R, int lane) {
+    if (q_from >= q_to) return;
+    auto quad_pos = [&](int q) { return (R.W0 + 4 * q) << 3; };
+    // ---- phase 1
+    int row_sp = 0;                                        // first segment with re > first position of the row
+    for (int q_row = q_from; q_row < q_to; q_row += 32) {
+        const int Qr = quad_pos(q_row);
+        int re_l;                                          // ends of segments row_sp .. row_sp + 31, one per lane
+        for (;;) {
+            re_l = row_sp + lane < n_seg ? s_re[row_sp + lane] : 0x7fffffff;
+            const int adv = __popc(__ballot_sync(0xffffffffu, re_l <= Qr));
+            if (adv == 0) break;
+            row_sp += adv;
+        }
+        const int q = q_row + lane;
+        const int Q0 = Qr + 32 * lane;
+        // owner = first segment with re > Q0: binary search over the 32 ends held by the lanes
+        int idx = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
-            int t = __shfl_sync(0xffffffffu, pinc, idx + step - 1);
-            if (t <= i) idx += step;
+            const int t = __shfl_sync(0xffffffffu, re_l, idx + step - 1);
+            if (t <= Q0) idx += step;
         }
-        const int o_rs = __shfl_sync(0xffffffffu, seg_rs, idx), o_qs = __shfl_sync(0xffffffffu, seg_qs, idx);
-        const int o_qf = __shfl_sync(0xffffffffu, qf, idx), o_pe = __shfl_sync(0xffffffffu, pexc, idx);
-        if (i < itot) {
-            const int Q = o_qf + 1 + (i - o_pe);
-            const int pq = (W0 + 4 * Q) << 3;
-            uint32_t v[4];
-            fetch_quad(P, o_qs + (pq - o_rs), v);
-            *reinterpret_cast<uint4 *>(P.strip + ((4 * Q) & (FUZ_STRIP - 1))) = make_uint4(v[0], v[1], v[2], v[3]);
+        int s = row_sp + idx;
+        const int re_31 = __shfl_sync(0xffffffffu, re_l, 31);
+        if (idx == 31 && re_31 <= Q0) {      // more than 32 segments in the row: rare
+            int lo = s + 1, hi = n_seg;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_re[mid] <= Q0) lo = mid + 1; else hi = mid;
+            }
+            s = lo;
+        }
+        if (q < q_to) {
+            const bool has = s < n_seg;
+            const int a = has ? s_rs[s] : 0x7fffffff, b = has ? s_re[s] : 0x7fffffff, dq = has ? s_dq[s] : 0;
+            uint32_t v[4] = {0u, 0u, 0u, 0u};
+            if (a < Q0 + 32) quad_piece(R, Q0, a, b, dq, v);
+            *reinterpret_cast<uint4 *>(R.out + 4 * q) = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
-}
-
-// Place the segments held by the lanes into the projection.  The common case (a 32-op CIGAR
-// chunk spans ~2-3 kb) goes to place_fit in one piece; batches that are too wide for the rings
-// (long M operations, long deletions, long insertions) are fed to it one <= 2048-base piece of
-// one segment at a time.
-__device__ __forceinline__ void place_segments(int seg_rs, int seg_len, int seg_qs, int W0, ProjWarp &P) {
-    const int lane = P.lane;
-    const bool has = seg_len > 0;
-    const uint32_t hmask = __ballot_sync(0xffffffffu, has);
-    if (!hmask) return;
-    const int wlo = __reduce_min_sync(0xffffffffu, has ? (seg_rs >> 3) - W0 : 0x7fffffff);
-    const int whi = __reduce_max_sync(0xffffffffu, has ? (((seg_rs + seg_len - 1) >> 3) - W0) | 3 : -1);
-    const int qlo = __reduce_min_sync(0xffffffffu, has ? seg_qs : 0x7fffffff);
-    const int qhi = __reduce_max_sync(0xffffffffu, has ? seg_qs + seg_len : -0x7fffffff);
-    if (qhi - qlo <= FUZ_FIT_Q && whi - (wlo & ~3) < FUZ_STRIP) {
-        strip_cover(P, wlo, whi);
-        const int y_lo = qlo - 32 + P.qphase;                // a long soft clip / insertion: skip, do not stage it
-        if (y_lo >= 32 * P.q_lines) P.q_lines = (y_lo >> 5) & ~63;
-        qwin_cover(P, qhi + 40 + P.qphase);
-        place_fit(seg_rs, seg_len, seg_qs, W0, P);
-        return;
-    }
-    for (uint32_t m = hmask; m; m &= m - 1) {
-        const int j = __ffs(m) - 1;
-        const int rs = __shfl_sync(0xffffffffu, seg_rs, j), ln = __shfl_sync(0xffffffffu, seg_len, j);
-        const int qs = __shfl_sync(0xffffffffu, seg_qs, j);
-        for (int o = 0; o < ln; o += 2048) {
-            const int pl = min(2048, ln - o);
-            const int pwlo = ((rs + o) >> 3) - W0, pwhi = (((rs + o + pl - 1) >> 3) - W0) | 3;
-            strip_cover(P, pwlo, pwhi);                 // a 2048-base piece always fits
-            // a query jump between pieces (long insertion) may leave the ring behind: restart it
-            const int y_lo = qs + o - 32 + P.qphase;
-            if (y_lo >= 32 * P.q_lines) P.q_lines = (y_lo >> 5) & ~63;
-            qwin_cover(P, qs + o + pl + 40 + P.qphase);
-            place_fit(rs + o, lane == 0 ? pl : 0, qs + o, W0, P);
-        }
+    __syncwarp();
+    // ---- phase 2
+    for (int s = 1 + lane; s < n_seg; s += 32) {
+        const int a = s_rs[s];
+        const int q = ((a >> 3) - R.W0) >> 2;
+        if (q < q_from || q >= q_to) continue;
+        const int Q0 = quad_pos(q);
+        if (s_re[s - 1] <= Q0) continue;                   // no earlier segment in this quad: s owns it
+        uint32_t v[4];
+        quad_piece(R, Q0, a, s_re[s], s_dq[s], v);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (v[k]) atomicOr(R.out + 4 * q + k, v[k]);
     }
 }
 
@@ -348,24 +268,16 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 // in REFERENCE coordinates, aligned to the global 8-position grid:
 // proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
 // G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
-// SEQ is staged through a per-warp shared-memory window (coalesced 128-bit loads, nibble
-// swap and ACGT filter once per word); the output goes through a per-warp shared-memory
-// window flushed with 128-bit stores.
+// Closed segments are appended to the warp's shared-memory list; the list is turned into
+// quads of the projection (emit_quads) when it fills up and at the end of the CIGAR.
 __global__ void __launch_bounds__(256, 4) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
-    __shared__ __align__(16) uint32_t strips[8][FUZ_STRIP];
-    __shared__ __align__(16) uint32_t qwins[8][FUZ_QWIN];
-    ProjWarp P;
-    P.lane = threadIdx.x & 31;
-    P.strip = strips[threadIdx.x >> 5];
-    P.qwin = qwins[threadIdx.x >> 5];
-    const int lane = P.lane;
+    __shared__ int segs[8][3][FUZ_SEGCAP];
+    const int lane = threadIdx.x & 31;
+    int *s_rs = segs[threadIdx.x >> 5][0], *s_re = segs[threadIdx.x >> 5][1], *s_dq = segs[threadIdx.x >> 5][2];
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int j = lane; j < FUZ_STRIP; j += 32) P.strip[j] = 0;
-    for (int j = lane; j < FUZ_QWIN; j += 32) P.qwin[j] = 0;
-    __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     long long acc_aligned = 0, acc_accepted = 0;
     for (int r = warp_g; r < n_rec; r += n_warps) {
@@ -440,18 +352,15 @@ __global__ void __launch_bounds__(256, 4) k_project(
         woff = __shfl_sync(0xffffffffu, woff, 0);
         if (n_words == 0 || woff < 0) continue;
         // ---- pass 2: projection
-        const int W0 = gstart >> 3;
+        ProjRec R;
         {
-            const uint8_t *seq = rec_buf + seq_off;
-            const uintptr_t a16 = reinterpret_cast<uintptr_t>(seq) & ~(uintptr_t)15;
-            P.qbase = reinterpret_cast<const uint8_t *>(a16) - 16;         // inside the record (>= 36 header bytes)
-            P.qphase = (int)(reinterpret_cast<uintptr_t>(seq) - a16) * 2 + 32;
-            P.seq_end = seq + ((l_seq + 1) >> 1);
+            const uintptr_t sa = reinterpret_cast<uintptr_t>(rec_buf + seq_off);
+            R.base4 = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
+            R.nphase = (int)(sa & 3) * 2;
+            R.W0 = gstart >> 3;
+            R.out = S.proj + woff;
         }
-        P.q_lines = 0;
-        P.out = S.proj + woff;
-        P.n_words4 = n_words;
-        P.strip_base = 0;
+        int n_seg = 0, q_next = 0;
         int carry_rp = gstart, carry_qp = 0;
         bool open = false, overrun = false;
         int open_rs = 0, open_qs = 0;
@@ -484,7 +393,31 @@ __global__ void __launch_bounds__(256, 4) k_project(
             const int qs_s = __shfl_sync(0xffffffffu, qp0, src);
             const int seg_rs = sm ? rs_s : open_rs, seg_qs = sm ? qs_s : open_qs;
             if (__any_sync(0xffffffffu, overrun)) break;     // bad record: stop before reading past SEQ
-            place_segments(seg_rs, ends_here ? rp0 - seg_rs : 0, seg_qs, W0, P);
+            // append the runs closed in this chunk (in CIGAR order = reference order)
+            const uint32_t emask = __ballot_sync(0xffffffffu, ends_here);
+            if (ends_here) {
+                const int idx = n_seg + __popc(emask & lt);
+                s_rs[idx] = seg_rs; s_re[idx] = rp0; s_dq[idx] = seg_qs - seg_rs;
+            }
+            n_seg += __popc(emask);
+            __syncwarp();
+            if (n_seg > FUZ_SEGCAP - 32) {
+                // emit every quad that no later segment can touch: those before the quad holding
+                // the end of the last segment; keep the (<= 32) segments that reach into that quad
+                const int q_lim = (((s_re[n_seg - 1] - 1) >> 3) - R.W0) >> 2;
+                emit_quads(s_rs, s_re, s_dq, n_seg, q_next, q_lim, R, lane);
+                q_next = max(q_next, q_lim);
+                const int P = (R.W0 + 4 * q_lim) << 3;
+                const int s = n_seg - 32 + lane;
+                const bool keep = s >= 0 && s_re[s] > P;
+                const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
+                int t_rs = 0, t_re = 0, t_dq = 0;
+                if (keep) { t_rs = s_rs[s]; t_re = s_re[s]; t_dq = s_dq[s]; }
+                __syncwarp();
+                if (keep) { const int d = __popc(kmask & lt); s_rs[d] = t_rs; s_re[d] = t_re; s_dq[d] = t_dq; }
+                n_seg = __popc(kmask);
+                __syncwarp();
+            }
             const int last_m_all = mmask ? 31 - __clz(mmask) : -1;
             const int last_b_all = bmask ? 31 - __clz(bmask) : -1;
             // the run open at the end of the chunk starts at the first start after the last breaker
@@ -502,11 +435,15 @@ __global__ void __launch_bounds__(256, 4) k_project(
             carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
         }
         overrun = __any_sync(0xffffffffu, overrun);
-        // the run still open at the end of the CIGAR
-        if (!overrun) place_segments(open_rs, (open && lane == 0) ? carry_rp - open_rs : 0, open_qs, W0, P);
-        strip_flush(P, P.strip_base, min(P.strip_base + FUZ_STRIP, n_words));
-        for (int w = P.strip_base + FUZ_STRIP + 4 * lane; w < n_words; w += 128)      // trailing deletion: no bases
-            reinterpret_cast<uint4 *>(P.out)[w >> 2] = make_uint4(0, 0, 0, 0);
+        if (!overrun) {
+            if (open && carry_rp > open_rs) {               // the run still open at the end of the CIGAR
+                if (lane == 0) { s_rs[n_seg] = open_rs; s_re[n_seg] = carry_rp; s_dq[n_seg] = open_qs - open_rs; }
+                n_seg++;
+                __syncwarp();
+            }
+            emit_quads(s_rs, s_re, s_dq, n_seg, q_next, n_words >> 2, R, lane);
+        }
+        __syncwarp();
         if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
     }
     if (lane == 0 && acc_accepted) {

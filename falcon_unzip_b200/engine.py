@@ -213,7 +213,7 @@ class DeviceBatch:
                 d[:t.numel()].copy_(t, non_blocking=True)
                 return d
             return t.to(device, non_blocking=True)
-        self.rec_buf = up(pb.records, pad=16)
+        self.rec_buf = up(pb.records, pad=32)
         self.rec_off = up(pb.rec_off)
         self.rec_qid = up(pb.rec_qid) if pb.n_rec else torch.zeros(1, dtype=torch.int32, device=device)
         self.ctg_rec_off = up(pb.ctg_rec_off)

@@ -28,7 +28,7 @@
  * Device data model (struct-of-arrays, all little endian)
  *   records   verbatim uncompressed BAM alignment records (block_size + body, SAM spec
  *             4.2) concatenated in `rec_buf`; rec_off[i] is the byte offset of record i
- *             (n_rec + 1 entries).  rec_buf must be followed by >= 16 readable bytes.
+ *             (n_rec + 1 entries).  rec_buf must be followed by >= 32 readable bytes.
  *             Records are grouped by contig (ctg_rec_off) and coordinate sorted inside a
  *             contig, i.e. the order `samtools view <bam> <ctg>` prints.
  *   sites     het-SNP sites ordered by (contig, position): site_ctg, site_pos (1-based
@@ -82,7 +82,7 @@ typedef struct {
     int32_t n_ctg;
     int32_t n_rec;
     int64_t rec_bytes;
-    const uint8_t *d_rec_buf;     /* [rec_bytes + 16]                                   */
+    const uint8_t *d_rec_buf;     /* [rec_bytes + 32]                                   */
     const int64_t *d_rec_off;     /* [n_rec + 1]                                        */
     const int32_t *d_rec_qid;     /* [n_rec] q_id of the record's QNAME in its contig   */
     const int32_t *d_ctg_rec_off; /* [n_ctg + 1] record range of each contig            */
