@@ -16,6 +16,7 @@ struct HetScratch {
     uint32_t *proj;            // reference-aligned 4-bit projection of every accepted record
     int64_t proj_cap;          // capacity of proj in words
     int32_t *ctg_last_rec, *ctg_maxspan;
+    int32_t *rec_cursor;       // next record to hand to a warp of k_project
     int32_t *tile_ctg, *tile_rlo, *tile_rhi, *tile_limit, *tile_site_base, *tile_site_cnt, *tile_site_off;
     int32_t *us_gpos;
     uint32_t *us_cnt;
@@ -27,9 +28,10 @@ struct HetScratch {
 __device__ __forceinline__ bool op_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 
 // ---------------------------------------------------------------- init
-__global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_maxspan, int n_ctg) {
+__global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_maxspan, int32_t *rec_cursor, int n_ctg) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
+        *rec_cursor = 0;
         st->error = 0; st->error_index = 0;
         st->n_sites = st->n_vmap = st->n_atable = st->n_reads = 0;
         st->need_sites = st->need_vmap = st->need_atable = st->need_reads = st->need_pairs = 0;
@@ -138,6 +140,14 @@ __device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {      // BAM: firs
 __device__ __forceinline__ uint32_t multi_bits(uint32_t x) {     // non-zero inside nibbles with 2+ bits set
     return (x & (x >> 1) & 0x77777777u) | (x & (x >> 2) & 0x33333333u) | (x & (x >> 3) & 0x11111111u);
 }
+// bit 0 of byte i set iff nibble i of the low 16 bits of x is not 0 or a one-hot code: one
+// PRMT as a 16-entry table (selector bit 3 = replicate the sign of the selected byte)
+__device__ __forceinline__ uint32_t bad_nibbles4(uint32_t x) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0x81808000u), "r"(0x81818180u), "r"(x));
+    return d;
+}
+__device__ __forceinline__ uint32_t bad_nibbles(uint32_t x) { return bad_nibbles4(x) | bad_nibbles4(x >> 16); }
 __device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
     uint32_t any = multi_bits(x);
     if (any) {
@@ -184,7 +194,7 @@ __device__ __forceinline__ void quad_piece(const ProjRec &R, int Q0, int a, int 
         const uint32_t ml = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(lo4 - 32 * k, 0));
         v[k] = __funnelshift_r(m[k], m[k + 1], sh) & mh & ~ml;
     }
-    if (multi_bits(v[0]) | multi_bits(v[1]) | multi_bits(v[2]) | multi_bits(v[3])) {        // ambiguity codes: rare
+    if ((bad_nibbles(v[0]) | bad_nibbles(v[1]) | bad_nibbles(v[2]) | bad_nibbles(v[3])) & 0x01010101u) {   // ambiguity codes: rare
         v[0] = keep_acgt(v[0]); v[1] = keep_acgt(v[1]); v[2] = keep_acgt(v[2]); v[3] = keep_acgt(v[3]);
     }
 }
@@ -264,13 +274,13 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 // advance the reference; N/H/P advance nothing, the quirk of phasing.py:77-96); record
 // validation; space for the projection is claimed with one atomic add.
 // Pass 2 (accepted records): walks the CIGAR 32 ops at a time (prefix positions by warp
-// scans), merges runs of M/=/X into match segments (S/I/D break a run) and writes the read
+// scans), turns runs of adjacent M/=/X ops into match segments and writes the read
 // in REFERENCE coordinates, aligned to the global 8-position grid:
 // proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
 // G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
 // Closed segments are appended to the warp's shared-memory list; the list is turned into
 // quads of the projection (emit_quads) when it fills up and at the end of the CIGAR.
-__global__ void __launch_bounds__(256, 4) k_project(
+__global__ void __launch_bounds__(256, 6) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
     __shared__ int segs[8][3][FUZ_SEGCAP];
@@ -280,9 +290,15 @@ __global__ void __launch_bounds__(256, 4) k_project(
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     long long acc_aligned = 0, acc_accepted = 0;
-    for (int r = warp_g; r < n_rec; r += n_warps) {
+    // records are handed out dynamically (their cost varies with length and CIGAR): the first
+    // one per warp statically, the rest from a global cursor
+    int r_next = 0;
+    for (int r = warp_g; r < n_rec; r = r_next) {
+        if (lane == 0) r_next = n_warps + atomicAdd(S.rec_cursor, 1);
+        r_next = __shfl_sync(0xffffffffu, r_next, 0);
         // ---- pass 1: issue every independent load first: offsets, then this and the previous header
         const int64_t off_r = rec_off[r], off_n = rec_off[r + 1], off_p = r > 0 ? rec_off[r - 1] : 0;
+        const int64_t off_x = rec_off[min(r_next, n_rec - 1)];      // the warp's next record: header + CIGAR into L2
         const uint8_t *rec = rec_buf + off_r;
         const int32_t block_size = (int32_t)fuz_ld_u32_un(rec);
         const int32_t pos = (int32_t)fuz_ld_u32_un(rec + 8);
@@ -304,6 +320,10 @@ __global__ void __launch_bounds__(256, 4) k_project(
             if (lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
             continue;
         }
+        // SEQ is needed after the CIGAR has been walked: start moving it to L2 now
+        for (int64_t o = seq_off + 128 * lane; o < seq_off + ((l_seq + 1) >> 1); o += 128 * 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_buf + o));
+        if (lane < 8 && r_next < n_rec) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_buf + off_x + 128 * lane));
         const int64_t gstart64 = ctg_goff[c] + pos;
         // coordinate order inside the contig
         if (lane == 0 && r > ctg_rec_off[c] && prev_pos > pos) fuz_raise(st, FUZ_E_UNSORTED, r);
@@ -362,44 +382,35 @@ __global__ void __launch_bounds__(256, 4) k_project(
         }
         int n_seg = 0, q_next = 0;
         int carry_rp = gstart, carry_qp = 0;
-        bool open = false, overrun = false;
-        int open_rs = 0, open_qs = 0;
+        bool overrun = false;
         for (int k0 = 0; k0 < n_cig; k0 += 32) {
             const int k = k0 + lane;
             const bool valid = k < n_cig;
             const uint32_t cw = valid ? fuz_ld_u32_un(cig + 4 * k) : 0u;
             const int len = (int)(cw >> 4);
             const uint32_t op = cw & 15;
-            const bool is_m = valid && op_is_match(op) && len > 0;
-            const bool brk = valid && (op == 1 || op == 2 || op == 4);               // I D S
-            const int radv = (valid && (op_is_match(op) || op == 2)) ? len : 0;        // M = X D
-            const int qadv = (valid && (op_is_match(op) || op == 1 || op == 4)) ? len : 0;  // M = X I S
+            const bool mt = valid && op_is_match(op);                                  // M = X
+            const bool is_m = mt && len > 0;
+            const int radv = (mt || (valid && op == 2)) ? len : 0;                      // M = X D
+            const int qadv = (mt || (valid && (op == 1 || op == 4))) ? len : 0;         // M = X I S
             const int rinc = fuz_warp_incl_scan(radv, lane);
             const int qinc = fuz_warp_incl_scan(qadv, lane);
             const int rp0 = carry_rp + rinc - radv;
             const int qp0 = carry_qp + qinc - qadv;
             if (is_m && (long long)qp0 + len > (long long)l_seq) overrun = true;       // IndexError :84
             const uint32_t mmask = __ballot_sync(0xffffffffu, is_m);
-            const uint32_t bmask = __ballot_sync(0xffffffffu, brk);
-            const int last_m = (mmask & lt) ? 31 - __clz(mmask & lt) : -1;
-            const int last_b = (bmask & lt) ? 31 - __clz(bmask & lt) : -1;
-            const bool open_before = last_m > last_b ? true : (last_b > last_m ? false : open);
-            const bool starts = is_m && !open_before;
-            const bool ends_here = brk && open_before;      // a breaker closes the run before it
-            const uint32_t smask = __ballot_sync(0xffffffffu, starts);
-            const uint32_t sm = smask & lt;
-            const int src = sm ? 31 - __clz(sm) : 0;
-            const int rs_s = __shfl_sync(0xffffffffu, rp0, src);
-            const int qs_s = __shfl_sync(0xffffffffu, qp0, src);
-            const int seg_rs = sm ? rs_s : open_rs, seg_qs = sm ? qs_s : open_qs;
             if (__any_sync(0xffffffffu, overrun)) break;     // bad record: stop before reading past SEQ
-            // append the runs closed in this chunk (in CIGAR order = reference order)
-            const uint32_t emask = __ballot_sync(0xffffffffu, ends_here);
-            if (ends_here) {
-                const int idx = n_seg + __popc(emask & lt);
-                s_rs[idx] = seg_rs; s_re[idx] = rp0; s_dq[idx] = seg_qs - seg_rs;
+            // runs of adjacent match ops inside the chunk become one segment each (a run that
+            // crosses the chunk border, or is interrupted by N/H/P, gives touching segments:
+            // same projection); appended in CIGAR order = reference order
+            const uint32_t smask = mmask & ~(mmask << 1), emask = mmask & ~(mmask >> 1);
+            const int e = lane + __ffs(emask >> lane) - 1;                             // last op of the run starting here
+            const int run_end = __shfl_sync(0xffffffffu, rp0 + len, e & 31);
+            if ((smask >> lane) & 1u) {
+                const int idx = n_seg + __popc(smask & lt);
+                s_rs[idx] = rp0; s_re[idx] = run_end; s_dq[idx] = qp0 - rp0;
             }
-            n_seg += __popc(emask);
+            n_seg += __popc(smask);
             __syncwarp();
             if (n_seg > FUZ_SEGCAP - 32) {
                 // emit every quad that no later segment can touch: those before the quad holding
@@ -418,31 +429,11 @@ __global__ void __launch_bounds__(256, 4) k_project(
                 n_seg = __popc(kmask);
                 __syncwarp();
             }
-            const int last_m_all = mmask ? 31 - __clz(mmask) : -1;
-            const int last_b_all = bmask ? 31 - __clz(bmask) : -1;
-            // the run open at the end of the chunk starts at the first start after the last breaker
-            const uint32_t sm2 = last_b_all >= 0 ? (last_b_all == 31 ? 0u : (smask & ~((2u << last_b_all) - 1u))) : smask;
-            const int src2 = sm2 ? __ffs(sm2) - 1 : 0;
-            const int rs2 = __shfl_sync(0xffffffffu, rp0, src2);
-            const int qs2 = __shfl_sync(0xffffffffu, qp0, src2);
-            if (last_m_all > last_b_all) {
-                if (sm2) { open_rs = rs2; open_qs = qs2; }
-                open = true;
-            } else if (last_b_all > last_m_all) {
-                open = false;
-            }
             carry_rp += __shfl_sync(0xffffffffu, rinc, 31);
             carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
         }
         overrun = __any_sync(0xffffffffu, overrun);
-        if (!overrun) {
-            if (open && carry_rp > open_rs) {               // the run still open at the end of the CIGAR
-                if (lane == 0) { s_rs[n_seg] = open_rs; s_re[n_seg] = carry_rp; s_dq[n_seg] = open_qs - open_rs; }
-                n_seg++;
-                __syncwarp();
-            }
-            emit_quads(s_rs, s_re, s_dq, n_seg, q_next, n_words >> 2, R, lane);
-        }
+        if (!overrun) emit_quads(s_rs, s_re, s_dq, n_seg, q_next, n_words >> 2, R, lane);
         __syncwarp();
         if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
     }
@@ -769,6 +760,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     size_t o_usg = L.add(4 * (size_t)cap_sites), o_usc = L.add(16 * (size_t)cap_sites);
     size_t o_sg = L.add(4 * (size_t)cap_sites), o_srow = L.add(4 * (size_t)(cap_sites + 1)),
            o_sroff = L.add(4 * (size_t)(cap_sites + 2));
+    size_t o_cursor = L.add(16);
     size_t o_counts = 0;
     const bool need_counts = ctx->pileup_impl == 1 && !out->d_counts;
     if (need_counts) o_counts = L.add(16 * (size_t)in->total_glen);
@@ -781,6 +773,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.r_seq = fuz_at<int64_t>(ctx, o_rseq); S.r_flags = fuz_at<uint8_t>(ctx, o_flags);
     S.proj = fuz_at<uint32_t>(ctx, o_proj); S.proj_cap = proj_cap;
     S.ctg_last_rec = fuz_at<int32_t>(ctx, o_clast); S.ctg_maxspan = fuz_at<int32_t>(ctx, o_cspan);
+    S.rec_cursor = fuz_at<int32_t>(ctx, o_cursor);
     S.tile_ctg = fuz_at<int32_t>(ctx, o_tctg); S.tile_rlo = fuz_at<int32_t>(ctx, o_tlo); S.tile_rhi = fuz_at<int32_t>(ctx, o_thi);
     S.tile_limit = fuz_at<int32_t>(ctx, o_tlim);
     S.tile_site_base = fuz_at<int32_t>(ctx, o_tbase); S.tile_site_cnt = fuz_at<int32_t>(ctx, o_tcnt);
@@ -792,7 +785,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.counts = out->d_counts ? out->d_counts : (need_counts ? fuz_at<uint32_t>(ctx, o_counts) : nullptr);
     S.n_tiles = n_tiles;
 
-    k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, n_ctg);
+    k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, S.rec_cursor, n_ctg);
     FUZ_LAUNCH_CHECK(ctx, "k_het_init");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->timing) {
@@ -809,7 +802,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            k_project<<<148 * 6, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");
         }
@@ -822,7 +815,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            k_project<<<148 * 6, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");      // filter + the projection the variant_map rows come from
             k_pileup_atomic<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
