@@ -93,6 +93,9 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "host_fetch")) {
         if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "host_fetch must be 0 or 1");
         ctx->host_fetch = (int)value;
+    } else if (!strcmp(key, "rr_filter_only")) {
+        if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "rr_filter_only must be 0 or 1");
+        ctx->rr_filter_only = (int)value;
     } else if (!strcmp(key, "phase_staging")) {
         if (value < 0 || value > 2) return fuz_fail(ctx, FUZ_E_ARG, "phase_staging must be 0, 1 or 2");
         ctx->phase_staging = (int)value;

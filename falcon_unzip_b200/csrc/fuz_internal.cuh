@@ -33,6 +33,7 @@ struct fuz_ctx {
     int64_t launches = 0;
     int pileup_impl = 0;
     int host_fetch = 1;                // host entry: fetch only header/name/CIGAR/SEQ from page-locked records
+    int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int64_t max_pairs_per_site = 96;
     bool phase_attr_set = false;

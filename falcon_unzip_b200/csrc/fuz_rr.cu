@@ -205,6 +205,7 @@ extern "C" int fuz_rr_track(fuz_ctx *ctx, const fuz_rr_input *in, fuz_rr_outputs
     FUZ_LAUNCH_CHECK(ctx, "k_rr_init");
     k_rr_filter<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(*in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_filter");
+    if (ctx->rr_filter_only) return FUZ_OK;      // map step of the multi-GPU run: d_keep (and reserved[3]) only
     if ((rc = fuz_scan_i32(ctx, R.t_cnt, R.t_off, n_reads, nullptr, FUZ_FIN_NONE, 0))) return rc;
     k_rr_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(*in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_fill");

@@ -408,8 +408,12 @@ def alloc_host_outputs(caps: Dict[str, int], pin: bool = False) -> Dict[str, np.
 _engines: Dict[int, Engine] = {}
 
 
-def get_engine(device: int = 0) -> Engine:
-    """Process-wide engine per device (contexts are cheap to keep, costly to create)."""
+def get_engine(device: Optional[int] = None) -> Engine:
+    """Process-wide engine per device (contexts are cheap to keep, costly to create).
+    device None = torch's current CUDA device (rank-local GPU in multi-process runs)."""
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     e = _engines.get(device)
     if e is None or not e.ctx:
         e = Engine(device)

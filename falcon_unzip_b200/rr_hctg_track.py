@@ -118,7 +118,7 @@ class _Tables:
             self.ph_block[r], self.ph_phase[r] = ph[1], ph[2]
 
 
-def _track_device(q, t, ln, tl, file_idx, tab: _Tables, min_len: int, bestn: int):
+def _track_device(q, t, ln, tl, file_idx, tab: _Tables, min_len: int, bestn: int, filter_only: bool = False):
     """fuz_rr_track on the arrays -> (keep, hp_n, hp_len, hp_q, vt_off, vt_ctg, vt_count, vt_score)."""
     import torch
     eng = engine.get_engine()
@@ -153,7 +153,11 @@ def _track_device(q, t, ln, tl, file_idx, tab: _Tables, min_len: int, bestn: int
         ro.cap_votes = cap_votes
         for k in o:
             setattr(ro, "d_" + k, o[k].data_ptr())
-        _lib.check(eng.ctx, lib().fuz_rr_track(eng.ctx, C.byref(ri), C.byref(ro)))
+        eng.set_option("rr_filter_only", 1 if filter_only else 0)
+        try:
+            _lib.check(eng.ctx, lib().fuz_rr_track(eng.ctx, C.byref(ri), C.byref(ro)))
+        finally:
+            eng.set_option("rr_filter_only", 0)
         st = eng.status(raise_on_error=False)
         if st.error == _lib.FUZ_OK:
             n_votes = int(st.reserved[1])
@@ -189,11 +193,8 @@ def tr_stage1(readlines: Callable[[], Iterable[str]], min_len: int, bestn: int, 
     return rtn
 
 
-def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn, file_list, min_len, bestn, db_fn,
-                    rawread_to_contigs_fn):
-    """reference rr_hctg_track.py:67-138.  `exe_pool` is accepted for signature compatibility:
-    every LAS file goes through ONE device call (the per-file heaps and their merge, :97-105,
-    are replayed inside the kernel)."""
+def _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn):
+    """the id tables of reference rr_hctg_track.py:70-85."""
     rid_to_ctg = get_rid_to_ctg(read_to_contig_map_fn)
     oid_to_phase = {}
     with open(phased_read_file_fn) as f:
@@ -206,40 +207,127 @@ def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawrea
     with open(rawread_ids_fn) as f:
         rid_to_oid = f.read().split("\n")
     rid_to_phase = [oid_to_phase.get(oid) for oid in rid_to_oid]
-    tab = _Tables(rid_to_ctg, rid_to_phase, len(rid_to_phase))
-    files = sorted(file_list)
+    return rid_to_ctg, _Tables(rid_to_ctg, rid_to_phase, len(rid_to_phase))
+
+
+def _parse_files(db_fn, files: Sequence[str], file_ids: Sequence[int]):
+    """LA4Falcon lines of `files` -> (q, t, len, tlen, file_idx) in (file, line) order."""
     parts = [_parse_lines(read_las_lines(db_fn, fn)) for fn in files]
     q, t, ln, tl = (np.concatenate([p[k] for p in parts]) if parts else np.zeros(0, np.int32) for k in range(4))
-    file_idx = np.concatenate([np.full(len(p[0]), i, np.int32) for i, p in enumerate(parts)]) if parts else np.zeros(0, np.int32)
-    keep, hp_n, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn)
-    # row order of the b-reads: dict insertion = per file, the file's targets in CPython-2
-    # order of ITS dict (keys inserted at their first kept line), first sight wins (:97-100,113)
+    file_idx = (np.concatenate([np.full(len(p[0]), i, np.int32) for i, p in zip(file_ids, parts)])
+                if parts else np.zeros(0, np.int32))
+    return q, t, ln, tl, file_idx
+
+
+def _bread_order(t_kept: np.ndarray, file_kept: np.ndarray) -> List[str]:
+    """b-reads in the iteration order of the reference's `bread_to_areads` dict: keys are
+    inserted per file (ascending), the file's targets in the CPython-2 order of ITS dict (keys
+    inserted at their first kept line), first sight wins (:97-100); iteration = CPython-2 order
+    of the merged dict (:113).  Inputs: target and file index of every KEPT line, (file, line) order."""
     inserted: Dict[str, None] = {}
-    bounds = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])]).astype(np.int64)
-    for i in range(len(files)):
-        sl = slice(int(bounds[i]), int(bounds[i + 1]))
-        keys = ["%09d" % x for x in _first_kept_order(t[sl], keep[sl]).tolist()]
-        for k in py2compat.str_dict_order(keys):
-            inserted.setdefault(k, None)
-    out = []
+    if len(t_kept):
+        cut = np.flatnonzero(np.diff(file_kept)) + 1
+        for seg in np.split(t_kept, cut):
+            _, first = np.unique(seg, return_index=True)
+            keys = ["%09d" % x for x in seg[np.sort(first)].tolist()]
+            for k in py2compat.str_dict_order(keys):
+                inserted.setdefault(k, None)
+    return py2compat.str_dict_order(inserted)
+
+
+def _format_bread(bread: str, tab: _Tables, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score) -> str:
+    """rows of one b-read (reference rr_hctg_track.py:126-138)."""
+    tid = int(bread)
+    lo, hi = int(vt_off[tid]), int(vt_off[tid + 1])
+    if lo == hi:
+        return ""
     names = tab.ctg_names
-    for bread in py2compat.str_dict_order(inserted):
-        tid = int(bread)
-        lo, hi = int(vt_off[tid]), int(vt_off[tid + 1])
-        if lo == hi:
-            continue
-        ctgs = [names[c] for c in vt_ctg[lo:hi].tolist()]              # dict insertion order
-        score = dict(zip(ctgs, zip(vt_score[lo:hi].tolist(), vt_count[lo:hi].tolist())))
-        items = [(k, score[k]) for k in py2compat.str_dict_order(ctgs)]   # ctg_score.items() (:126)
-        items.sort(key=lambda kv: kv[1][0])                            # stable sort by score (:127)
-        own = rid_to_ctg.get(bread)
-        for rank, (ctg, (sc, cnt)) in enumerate(items):
-            in_ctg = 1 if own is not None and ctg in own else 0
-            out.append("%s %s %d %d %d %d\n" % (bread, ctg, cnt, rank, sc, in_ctg))
-    os.makedirs(os.path.dirname(rawread_to_contigs_fn) or ".", exist_ok=True)
-    with open(rawread_to_contigs_fn + ".tmp", "w") as f:
-        f.write("".join(out))
-    os.replace(rawread_to_contigs_fn + ".tmp", rawread_to_contigs_fn)
+    ctgs = [names[c] for c in vt_ctg[lo:hi].tolist()]              # dict insertion order
+    score = dict(zip(ctgs, zip(vt_score[lo:hi].tolist(), vt_count[lo:hi].tolist())))
+    items = [(k, score[k]) for k in py2compat.str_dict_order(ctgs)]   # ctg_score.items() (:126)
+    items.sort(key=lambda kv: kv[1][0])                            # stable sort by score (:127)
+    own = rid_to_ctg.get(bread)
+    out = []
+    for rank, (ctg, (sc, cnt)) in enumerate(items):
+        in_ctg = 1 if own is not None and ctg in own else 0
+        out.append("%s %s %d %d %d %d\n" % (bread, ctg, cnt, rank, sc, in_ctg))
+    return "".join(out)
+
+
+def _write_rows(fn: str, text: str) -> None:
+    os.makedirs(os.path.dirname(fn) or ".", exist_ok=True)
+    with open(fn + ".tmp", "w") as f:
+        f.write(text)
+    os.replace(fn + ".tmp", fn)
+
+
+def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn, file_list, min_len, bestn, db_fn,
+                    rawread_to_contigs_fn):
+    """reference rr_hctg_track.py:67-138.  `exe_pool` is accepted for signature compatibility:
+    every LAS file goes through ONE device call (the per-file heaps and their merge, :97-105,
+    are replayed inside the kernel)."""
+    rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
+    files = sorted(file_list)
+    q, t, ln, tl, file_idx = _parse_files(db_fn, files, range(len(files)))
+    keep, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn)
+    kept = keep.astype(bool)
+    rows = [_format_bread(b, tab, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score) for b in _bread_order(t[kept], file_idx[kept])]
+    _write_rows(rawread_to_contigs_fn, "".join(rows))
+
+
+def run_track_reads_sharded(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn, file_list, min_len, bestn, db_fn,
+                            rawread_to_contigs_fn, rank: int, world_size: int, group=None):
+    """run_track_reads over `world_size` processes (one per GPU; torch.distributed initialised
+    by the caller).  It mirrors the reference's map + merge (rr_hctg_track.py:88-105):
+
+      map       LAS files are dealt round-robin to the ranks; a rank parses its files and
+                runs the overlap filter (:45-57) on its GPU;
+      exchange  ONE all-gather of the kept overlap lines (q, t, len, tlen, file: int32 x 5);
+      merge     every rank replays the per-file heaps and their merge and takes the contig vote
+                for the targets t with t % world_size == rank (a target's result depends only on
+                its own kept lines in (file, line) order, so the shard is exact);
+      rows      formatted per rank, collected by rank 0, written in the reference's row order.
+
+    The id tables are replicated (every rank reads the three table files)."""
+    import torch
+    import torch.distributed as dist
+    rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
+    files = sorted(file_list)
+    mine = list(range(rank, len(files), world_size))
+    q, t, ln, tl, file_idx = _parse_files(db_fn, [files[i] for i in mine], mine)
+    keep = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn, filter_only=True)[0].astype(bool)
+    local = np.stack([q[keep], t[keep], ln[keep], tl[keep], file_idx[keep]], axis=1).astype(np.int32)
+    backend = dist.get_backend(group)
+    dev = engine.get_engine().device if backend == "nccl" else torch.device("cpu")
+    # exchange: sizes, then the padded line blocks
+    n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world_size)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    pad = max(max(sizes), 1)
+    send = torch.zeros((pad, 5), dtype=torch.int32, device=dev)
+    if len(local):
+        send[:len(local)] = torch.from_numpy(local).to(dev)
+    recv = [torch.zeros((pad, 5), dtype=torch.int32, device=dev) for _ in range(world_size)]
+    dist.all_gather(recv, send, group=group)
+    lines = np.concatenate([r[:n].cpu().numpy() for r, n in zip(recv, sizes)], axis=0)
+    lines = lines[np.argsort(lines[:, 4], kind="stable")]          # (file, line) order: files are disjoint across ranks
+    # merge + vote for this rank's targets
+    own = lines[lines[:, 1] % world_size == rank]
+    _k, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(
+        own[:, 0], own[:, 1], own[:, 2], own[:, 3], own[:, 4], tab, min_len, bestn)
+    order = _bread_order(lines[:, 1], lines[:, 4])
+    blocks = {b: _format_bread(b, tab, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score)
+              for b in order if int(b) % world_size == rank}
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, blocks, group=group)
+    if rank == 0:
+        merged = {}
+        for g in gathered:
+            merged.update(g)
+        _write_rows(rawread_to_contigs_fn, "".join(merged[b] for b in order))
+    dist.barrier(group=group)
+    return dict(lines_local=int(len(q)), kept_local=int(len(local)), kept_total=int(len(lines)), targets_local=len(blocks))
 
 
 def try_run_track_reads(n_core, phased_read_file, read_to_contig_map, rawread_ids, min_len, bestn, output):
