@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicate", type=int, default=1, help="repeat the workload's contigs (named in config)")
     ap.add_argument("--contigs", type=int, default=0, help="use only the first N contigs of the config (named in config)")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="library option for experiments (fuz_set_option), e.g. pdl=0; recorded in config")
     return ap.parse_args()
 
 
@@ -201,7 +203,8 @@ def workload_config(cfg, sset, args, aligned_bases):
             "aligned_bases_per_gpu_step": int(aligned_bases), "record_bytes_per_gpu": int(len(sset.records)),
             "seed": cfg.seed, "parallelism": "contig-sharded x%d, no collective" % args.gpus,
             "l2": "inputs (%.0f MB of records per GPU) exceed the 126 MB L2 and a 256 MiB buffer is overwritten between timed steps"
-                  % (len(sset.records) / 1e6)}
+                  % (len(sset.records) / 1e6),
+            **({"options": list(args.opt)} if args.opt else {})}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -221,6 +224,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     eng = engine.Engine(local_rank)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        eng.set_option(key, int(val))
     stream = torch.cuda.Stream(device=dev)
     from falcon_unzip_b200._lib import lib
     lib().fuz_set_stream(eng.ctx, stream.cuda_stream)

@@ -56,6 +56,7 @@ static int ensure_stage(fuz_ctx *ctx, size_t dev_bytes, size_t pin_bytes) {
 __global__ void __launch_bounds__(256) k_fetch_records(const uint8_t *__restrict__ h_src, uint8_t *__restrict__ d_dst,
                                                        const int64_t *__restrict__ rec_off, int n_rec, int64_t rec_bytes,
                                                        unsigned long long *fetched) {
+    fuz_pdl_enter();
     __shared__ __align__(16) uint8_t head[8][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -158,7 +159,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     FUZ_CUDA(ctx, h2d(d_off, in->h_rec_off, 8 * (size_t)(n_rec + 1)));
     if (mapped) {
         FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_fetched, 0, 8, st));
-        k_fetch_records<<<FUZ_GRID_BLOCKS * 2, 256, 0, st>>>(mapped, dv + d_rec, reinterpret_cast<const int64_t *>(dv + d_off),
+        fuz_launch(ctx, k_fetch_records, FUZ_GRID_BLOCKS * 2, 256, 0, st, mapped, dv + d_rec, reinterpret_cast<const int64_t *>(dv + d_off),
                                                              n_rec, in->rec_bytes,
                                                              reinterpret_cast<unsigned long long *>(dv + d_fetched));
         FUZ_LAUNCH_CHECK(ctx, "k_fetch_records");

@@ -93,6 +93,9 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "host_fetch")) {
         if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "host_fetch must be 0 or 1");
         ctx->host_fetch = (int)value;
+    } else if (!strcmp(key, "pdl")) {
+        if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "pdl must be 0 or 1");
+        ctx->pdl = (int)value;
     } else if (!strcmp(key, "rr_filter_only")) {
         if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "rr_filter_only must be 0 or 1");
         ctx->rr_filter_only = (int)value;
@@ -233,6 +236,7 @@ int fuz_arena_commit(fuz_ctx *ctx, const FuzLayout &l) {
 __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                    int64_t n_cap, const int64_t *__restrict__ d_n, int fin_op,
                                                    int64_t fin_cap, fuz_status *st) {
+    fuz_pdl_enter();
     int64_t n = d_n ? *d_n : n_cap;
     if (n > n_cap) n = n_cap;
     if (n < 0) n = 0;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
 
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n, int fin_op,
                  int64_t fin_cap) {
-    k_scan_i32<<<1, 1024, 0, ctx->stream>>>(d_in, d_out, n_cap, d_n, fin_op, fin_cap, ctx->d_status);
+    fuz_launch(ctx, k_scan_i32, 1, 1024, 0, ctx->stream, d_in, d_out, n_cap, d_n, fin_op, fin_cap, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_scan_i32");
     return FUZ_OK;
 }

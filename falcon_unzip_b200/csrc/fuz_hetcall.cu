@@ -29,6 +29,7 @@ __device__ __forceinline__ bool op_is_match(uint32_t op) { return op == 0 || op 
 
 // ---------------------------------------------------------------- init
 __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_maxspan, int32_t *rec_cursor, int n_ctg) {
+    fuz_pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         *rec_cursor = 0;
@@ -45,6 +46,7 @@ __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_m
 // file order; positions >= POS_last are never evaluated (no final flush, phasing.py:98-129).
 __global__ void k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict__ ctg_goff,
                               const int32_t *__restrict__ ctg_rec_off, HetScratch S, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
         int64_t t0 = (int64_t)t * FUZ_TILE;
@@ -283,6 +285,7 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 __global__ void __launch_bounds__(256, 6) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
+    fuz_pdl_enter();
     __shared__ int segs[8][3][FUZ_SEGCAP];
     const int lane = threadIdx.x & 31;
     int *s_rs = segs[threadIdx.x >> 5][0], *s_re = segs[threadIdx.x >> 5][1], *s_dq = segs[threadIdx.x >> 5][2];
@@ -472,6 +475,7 @@ __device__ __forceinline__ uint32_t plane_count(const uint32_t (&acc)[8], int bi
 // between spills into 16-bit counters).  No atomics, no shared-memory histogram.
 __global__ void __launch_bounds__(FUZ_TILE_THREADS, 5) k_pileup_gather(HetScratch S, int64_t cap_sites,
                                                                        uint32_t *__restrict__ counts_out, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     __shared__ int4 l_ent[FUZ_TILE_THREADS];             // x = word offset of the projection, y = first word, z = words
     __shared__ uint32_t c16s[16][FUZ_TILE_THREADS];      // spill counters (depth > 255 only): [4 * base + j][thread]
@@ -587,6 +591,7 @@ __global__ void __launch_bounds__(256) k_pileup_atomic(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S,
     uint32_t *__restrict__ counts, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -625,6 +630,7 @@ __global__ void __launch_bounds__(256) k_pileup_atomic(
 
 __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
     const uint32_t *__restrict__ counts, HetScratch S, int64_t cap_sites, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     __shared__ int s_warp_tot[FUZ_NW];
     __shared__ int s_base;
@@ -646,6 +652,7 @@ __global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
 // exclusive scan of the variant_map rows per site.  Three former launches in one.
 __global__ void __launch_bounds__(1024) k_sites_finalize(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff,
                                                           fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const long long total = fuz_cta_scan_i32(S.tile_site_cnt, S.tile_site_off, n_tiles);
     if (threadIdx.x == 0) fuz_scan_publish(st, FUZ_FIN_SITES, O.cap_sites, total);
@@ -689,6 +696,7 @@ __global__ void __launch_bounds__(1024) k_sites_finalize(int n_tiles, HetScratch
 __global__ void __launch_bounds__(256) k_signature(
     const int32_t *__restrict__ rec_qid, const int32_t *__restrict__ ctg_rec_off, HetScratch S, fuz_outputs O,
     fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -785,7 +793,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.counts = out->d_counts ? out->d_counts : (need_counts ? fuz_at<uint32_t>(ctx, o_counts) : nullptr);
     S.n_tiles = n_tiles;
 
-    k_het_init<<<1, 256, 0, st>>>(ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, S.rec_cursor, n_ctg);
+    fuz_launch(ctx, k_het_init, 1, 256, 0, st, ctx->d_status, S.ctg_last_rec, S.ctg_maxspan, S.rec_cursor, n_ctg);
     FUZ_LAUNCH_CHECK(ctx, "k_het_init");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->timing) {
@@ -802,35 +810,35 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<148 * 6, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            fuz_launch(ctx, k_project, 148 * 6, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");
         }
-        k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 255) / 256, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
-        k_pileup_gather<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S, cap_sites, out->d_counts, ctx->d_status);
+        fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_TILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
     } else {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            k_project<<<148 * 6, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            fuz_launch(ctx, k_project, 148 * 6, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");      // filter + the projection the variant_map rows come from
-            k_pileup_atomic<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
+            fuz_launch(ctx, k_pileup_atomic, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,
                                                               in->d_ctg_goff, n_ctg, S, S.counts, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_pileup_atomic");
         }
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
-        k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 255) / 256, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
-        k_het_from_counts<<<n_tiles, FUZ_TILE_THREADS, 0, st>>>(S.counts, S, cap_sites, ctx->d_status);
+        fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_TILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
-    k_sites_finalize<<<1, 1024, 0, st>>>(n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
+    fuz_launch(ctx, k_sites_finalize, 1, 1024, 0, st, n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_sites_finalize");
-    k_signature<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
+    fuz_launch(ctx, k_signature, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_signature");
     return FUZ_OK;
 }

@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <utility>
+
 #include "fuz.h"
 
 #define FUZ_TILE 2048              // reference positions per pileup tile (one CTA)
@@ -33,6 +35,7 @@ struct fuz_ctx {
     int64_t launches = 0;
     int pileup_impl = 0;
     int host_fetch = 1;                // host entry: fetch only header/name/CIGAR/SEQ from page-locked records
+    int pdl = 1;                       // programmatic dependent launch between the kernels of a call
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int64_t max_pairs_per_site = 96;
@@ -68,6 +71,29 @@ int fuz_fail(fuz_ctx *ctx, int code, const char *fmt, ...);
             return fuz_fail((ctx), FUZ_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
         if ((ctx)->profile) fuz_profile_mark((ctx), name);                               \
     } while (0)
+
+// Programmatic dependent launch: every kernel of the library starts with fuz_pdl_enter()
+// (let the next kernel of the stream start launching, then wait until everything before this
+// kernel has completed and is visible), and is launched through fuz_launch(), which allows the
+// overlap of its launch with the tail of its predecessor.  Profile mode launches serialised.
+#ifdef __CUDACC__
+__device__ __forceinline__ void fuz_pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void fuz_launch(fuz_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->profile || !ctx->pdl) ? 0 : 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);   // errors: FUZ_LAUNCH_CHECK
+}
+#endif
 
 void fuz_profile_mark(fuz_ctx *ctx, const char *name);
 

@@ -9,6 +9,7 @@ namespace {
 
 // ------------------------------------------------------------------ shared helpers
 __global__ void k_set_counts(fuz_status *st, int64_t n_sites, int64_t n_vmap, int64_t n_atable, int reset_error) {
+    fuz_pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (reset_error) { st->error = 0; st->error_index = 0; }
         if (n_sites >= 0) st->n_sites = n_sites;
@@ -19,6 +20,7 @@ __global__ void k_set_counts(fuz_status *st, int64_t n_sites, int64_t n_vmap, in
 
 // row range of every site inside the (site-grouped) vmap rows
 __global__ void k_site_rowoff(const int32_t *__restrict__ vm_site, int32_t *__restrict__ row_off, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_sites = (int)st->n_sites, n_vmap = (int)st->n_vmap;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x)
@@ -30,6 +32,7 @@ __global__ void k_site_rowoff(const int32_t *__restrict__ vm_site, int32_t *__re
 __global__ void __launch_bounds__(256) k_dup_flags(const int32_t *__restrict__ row_off, const uint8_t *__restrict__ vm_base,
                                                    const int32_t *__restrict__ vm_qid, uint8_t *__restrict__ dup,
                                                    const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -66,6 +69,7 @@ struct AssocScratch {
 #define FUZ_UQ_RANGE 512
 __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ site_al, const uint8_t *__restrict__ vm_base,
                                                     const int32_t *__restrict__ vm_qid, AssocScratch A, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     __shared__ int s_first[8][2][FUZ_UQ_RANGE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -165,6 +169,7 @@ __device__ __forceinline__ int sorted_intersect(const int32_t *__restrict__ a, i
 // q_ids of its partner against them.  Left sites with a wide q_id range merge sorted lists.
 #define FUZ_PAIR_WORDS 16            // 512-bit masks
 __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     __shared__ uint32_t s_mask[8][2][FUZ_PAIR_WORDS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *
 }
 
 __global__ void __launch_bounds__(256) k_pair_fill(AssocScratch A, fuz_outputs O, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -267,6 +273,7 @@ __device__ __forceinline__ int row_d(const int32_t *__restrict__ at_ct, int row)
 
 // zero the counters; first site of every contig; row range of every site as left site
 __global__ void k_blk_init(BlockScratch B, fuz_outputs O, int n_ctg, int right_off_valid, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_sites = (int)st->n_sites, n_at = (int)st->n_atable;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_sites; s += gridDim.x * blockDim.x) {
@@ -283,6 +290,7 @@ __global__ void k_blk_init(BlockScratch B, fuz_outputs O, int n_ctg, int right_o
 
 // accepted rows |cis - trans| >= 6 (phasing.py:245) -> in-degree of the right site
 __global__ void k_edge_count(BlockScratch B, fuz_outputs O, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_at = (int)st->n_atable;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_at; r += gridDim.x * blockDim.x) {
@@ -295,6 +303,7 @@ __global__ void k_edge_count(BlockScratch B, fuz_outputs O, const fuz_status *st
 // left adjacency in CSR form: lq = left partner, ld = cis - trans (order inside a site's list
 // is arbitrary: only sums / minima over it are used)
 __global__ void k_edge_fill(BlockScratch B, fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_at = (int)st->n_atable, n_sites = (int)st->n_sites;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_at; r += gridDim.x * blockDim.x) {
@@ -467,6 +476,7 @@ __device__ __forceinline__ void sweep_sites(int n, int lane, uint32_t *sbits, co
 // inherently sequential sweep and the pointer chasing run at shared-memory latency.
 // Contigs too large for that (> ~10^4 sites) fall back to global memory for the adjacency.
 __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B, fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     extern __shared__ uint32_t smem[];
     __shared__ int s_tmp[33];
@@ -675,6 +685,7 @@ struct ReadScratch {
 };
 
 __global__ void k_rd_init(ReadScratch R) {
+    fuz_pdl_enter();
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= R.total_nq; q += (int64_t)gridDim.x * blockDim.x) {
         R.q_cnt[q] = 0;
         if (q < R.total_nq) R.q_cur[q] = 0;
@@ -693,6 +704,7 @@ __device__ __forceinline__ int voting_gq(int i, const ReadScratch &R, const fuz_
 }
 
 __global__ void k_q_count(ReadScratch R, fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_vmap = (int)st->n_vmap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
@@ -702,6 +714,7 @@ __global__ void k_q_count(ReadScratch R, fuz_outputs O, fuz_status *st) {
 }
 
 __global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     const int n_vmap = (int)st->n_vmap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
@@ -719,6 +732,7 @@ __global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
 // One thread per read: distinct phased variants -> (block, phase) counts; blocks in
 // ascending id; a row when |n0 - n1| > 1 (phasing.py:465-480).  fill = 0 counts rows.
 __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     for (int64_t gq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gq < R.total_nq; gq += (int64_t)gridDim.x * blockDim.x) {
         const int e0 = R.q_off[gq], e1 = R.q_off[gq + 1];
@@ -779,16 +793,16 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     const int64_t *d_ns = &ctx->d_status->n_sites;
 
     if (!row_off_valid) {
-        k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, A.row_off, ctx->d_status);
+        fuz_launch(ctx, k_site_rowoff, FUZ_GRID_BLOCKS, 256, 0, st, out->d_vm_site, A.row_off, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
     }
-    k_uniq_lists<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
+    fuz_launch(ctx, k_uniq_lists, FUZ_GRID_BLOCKS, 256, 0, st, out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
     if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, FUZ_FIN_PAIRS, A.max_pairs))) return rc;
-    k_pair_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, ctx->d_status);
+    fuz_launch(ctx, k_pair_count, FUZ_GRID_BLOCKS, 256, 0, st, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
     if ((rc = fuz_scan_i32(ctx, A.at_cnt, A.at_off, cs, d_ns, FUZ_FIN_ATABLE, out->cap_atable))) return rc;
-    k_pair_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(A, *out, ctx->d_status);
+    fuz_launch(ctx, k_pair_fill, FUZ_GRID_BLOCKS, 256, 0, st, A, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_fill");
     return FUZ_OK;
 }
@@ -820,14 +834,14 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_v
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;
     }
-    k_blk_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, n_ctg, at_off_valid ? 1 : 0, ctx->d_status);
+    fuz_launch(ctx, k_blk_init, FUZ_GRID_BLOCKS, 256, 0, st, B, *out, n_ctg, at_off_valid ? 1 : 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
-    k_edge_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    fuz_launch(ctx, k_edge_count, FUZ_GRID_BLOCKS, 256, 0, st, B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
     if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, FUZ_FIN_NONE, 0))) return rc;
-    k_edge_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(B, *out, ctx->d_status);
+    fuz_launch(ctx, k_edge_fill, FUZ_GRID_BLOCKS, 256, 0, st, B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
-    k_ctg_phase<<<n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st>>>(B, *out, ctx->d_status);
+    fuz_launch(ctx, k_ctg_phase, n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st, B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_ctg_phase");
     if (B.dbg) {            // diagnostics: phase durations (cycles) of contig 0
         long long h[16];
@@ -857,28 +871,28 @@ int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t
     R.q_ent = fuz_at<int32_t>(ctx, o_qe); R.pr_cnt = fuz_at<int32_t>(ctx, o_pc); R.pr_off = fuz_at<int32_t>(ctx, o_po);
     if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, FUZ_FIN_NONE, 0))) return rc;
     if (!dup_valid) {
-        k_site_rowoff<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(out->d_vm_site, R.row_off, ctx->d_status);
+        fuz_launch(ctx, k_site_rowoff, FUZ_GRID_BLOCKS, 256, 0, st, out->d_vm_site, R.row_off, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
-        k_dup_flags<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
+        fuz_launch(ctx, k_dup_flags, FUZ_GRID_BLOCKS, 256, 0, st, R.row_off, out->d_vm_base, out->d_vm_qid, R.dup, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_dup_flags");
     }
-    k_rd_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R);
+    fuz_launch(ctx, k_rd_init, FUZ_GRID_BLOCKS, 256, 0, st, R);
     FUZ_LAUNCH_CHECK(ctx, "k_rd_init");
-    k_q_count<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
+    fuz_launch(ctx, k_q_count, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_count");
     if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    k_q_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, ctx->d_status);
+    fuz_launch(ctx, k_q_fill, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_fill");
-    k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 0, ctx->d_status);
+    fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
     if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, FUZ_FIN_READS, out->cap_reads))) return rc;
-    k_vote<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(R, *out, n_ctg, 1, ctx->d_status);
+    fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
     return FUZ_OK;
 }
 
 static int set_counts(fuz_ctx *ctx, int64_t n_sites, int64_t n_vmap, int64_t n_atable) {
-    k_set_counts<<<1, 32, 0, ctx->stream>>>(ctx->d_status, n_sites, n_vmap, n_atable, 1);
+    fuz_launch(ctx, k_set_counts, 1, 32, 0, ctx->stream, ctx->d_status, n_sites, n_vmap, n_atable, 1);
     FUZ_LAUNCH_CHECK(ctx, "k_set_counts");
     return FUZ_OK;
 }

@@ -15,6 +15,7 @@ struct RRScratch {
 };
 
 __global__ void k_rr_init(fuz_status *st, RRScratch R, int n_reads) {
+    fuz_pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { st->error = 0; st->error_index = 0; st->reserved[1] = st->reserved[2] = st->reserved[3] = 0; }
     for (; i <= n_reads; i += gridDim.x * blockDim.x) { R.t_cnt[i] = 0; if (i < n_reads) R.t_cur[i] = 0; }
@@ -22,6 +23,7 @@ __global__ void k_rr_init(fuz_status *st, RRScratch R, int n_reads) {
 
 // R1: rr_hctg_track.py:45-57
 __global__ void k_rr_filter(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, fuz_status *st) {
+    fuz_pdl_enter();
     long long kept = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < in.n_ovl; i += (int64_t)gridDim.x * blockDim.x) {
         const int q = in.d_q[i], t = in.d_t[i];
@@ -44,6 +46,7 @@ __global__ void k_rr_filter(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, fu
 }
 
 __global__ void k_rr_fill(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < in.n_ovl; i += (int64_t)gridDim.x * blockDim.x) {
         if (!out.d_keep[i]) continue;
@@ -118,6 +121,7 @@ __device__ void sort_lines(int *a, int n) {
 
 // R2: one thread per target read
 __global__ void k_rr_replay(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, const fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < in.n_reads; t += gridDim.x * blockDim.x) {
         const int n = R.t_cnt[t];
@@ -145,6 +149,7 @@ __global__ void k_rr_replay(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, co
 // R3: contigs voted by the kept a-reads of a target, in insertion order (:113-123).
 #define FUZ_RR_MAXC 64
 __global__ void k_rr_vote(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, int fill, fuz_status *st) {
+    fuz_pdl_enter();
     if (st->error) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < in.n_reads; t += gridDim.x * blockDim.x) {
         const int ng = out.d_hp_n[t];
@@ -175,6 +180,7 @@ __global__ void k_rr_vote(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, int 
 }
 
 __global__ void k_rr_votes_total(fuz_rr_outputs out, int n_reads, fuz_status *st) {
+    fuz_pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0 && !st->error) {
         int64_t total = out.d_vt_off[n_reads];
         st->reserved[2] = total;
@@ -201,22 +207,22 @@ extern "C" int fuz_rr_track(fuz_ctx *ctx, const fuz_rr_input *in, fuz_rr_outputs
     R.t_cnt = fuz_at<int32_t>(ctx, o_cnt); R.t_off = fuz_at<int32_t>(ctx, o_off); R.t_cur = fuz_at<int32_t>(ctx, o_cur);
     R.grp = fuz_at<int32_t>(ctx, o_grp); R.a_len = fuz_at<int32_t>(ctx, o_al); R.a_q = fuz_at<int32_t>(ctx, o_aq);
     R.vt_cnt = fuz_at<int32_t>(ctx, o_vc);
-    k_rr_init<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(ctx->d_status, R, (int)n_reads);
+    fuz_launch(ctx, k_rr_init, FUZ_GRID_BLOCKS, 256, 0, st, ctx->d_status, R, (int)n_reads);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_init");
-    k_rr_filter<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(*in, *out, R, ctx->d_status);
+    fuz_launch(ctx, k_rr_filter, FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_filter");
     if (ctx->rr_filter_only) return FUZ_OK;      // map step of the multi-GPU run: d_keep (and reserved[3]) only
     if ((rc = fuz_scan_i32(ctx, R.t_cnt, R.t_off, n_reads, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    k_rr_fill<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(*in, *out, R, ctx->d_status);
+    fuz_launch(ctx, k_rr_fill, FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_fill");
-    k_rr_replay<<<FUZ_GRID_BLOCKS, 256, 0, st>>>(*in, *out, R, ctx->d_status);
+    fuz_launch(ctx, k_rr_replay, FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_replay");
-    k_rr_vote<<<FUZ_GRID_BLOCKS, 128, 0, st>>>(*in, *out, R, 0, ctx->d_status);
+    fuz_launch(ctx, k_rr_vote, FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_vote(count)");
     if ((rc = fuz_scan_i32(ctx, R.vt_cnt, out->d_vt_off, n_reads, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    k_rr_votes_total<<<1, 32, 0, st>>>(*out, (int)n_reads, ctx->d_status);
+    fuz_launch(ctx, k_rr_votes_total, 1, 32, 0, st, *out, (int)n_reads, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_votes_total");
-    k_rr_vote<<<FUZ_GRID_BLOCKS, 128, 0, st>>>(*in, *out, R, 1, ctx->d_status);
+    fuz_launch(ctx, k_rr_vote, FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_vote(fill)");
     return FUZ_OK;
 }

@@ -133,6 +133,8 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *          1 = global-atomic pileup + separate het test (cross-check path);
  *          "host_fetch" 1 = fuz_phase_batch_host reads page-locked records through the host mapping and
  *                       moves only header/name/CIGAR/SEQ (default), 0 = always copy the whole buffer,
+ *          "pdl" 1 = kernels of a call are launched with programmatic stream serialisation, i.e. the
+ *                launch of a kernel overlaps the tail of its predecessor (default), 0 = plain launches,
  *          "rr_filter_only" 1 = fuz_rr_track runs the overlap filter only (d_keep; the map step of the
  *                           multi-GPU run, the merge then runs on the gathered kept lines), 0 = default,
  *          "phase_staging" 0 = stage as much of a contig as fits in shared memory (default),
