@@ -18,7 +18,7 @@ struct HetScratch {
     int32_t *ctg_last_rec, *ctg_maxspan;
     int32_t *rec_cursor;       // next record to hand to a warp of k_project
     int32_t *tile_ctg, *tile_rlo, *tile_rhi, *tile_limit, *tile_site_base, *tile_site_cnt, *tile_site_off;
-    int32_t *us_gpos;
+    int32_t *us_gpos, *us_tile;
     uint32_t *us_cnt;
     int32_t *s_gpos, *site_rows, *site_row_off;
     uint32_t *counts;
@@ -114,6 +114,7 @@ __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t
             if (hetmask & (1u << i)) {
                 if (o < cap_sites) {
                     S.us_gpos[o] = t0 + tid * 8 + i;
+                    S.us_tile[o] = tile;
                     reinterpret_cast<uint4 *>(S.us_cnt)[o] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
                 }
                 o++;
@@ -659,29 +660,45 @@ __global__ void __launch_bounds__(1024) k_sites_finalize(int n_tiles, HetScratch
     __threadfence_block();
     __syncthreads();
     if (total > O.cap_sites) return;
-    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
-        int cnt = S.tile_site_cnt[t];
-        if (!cnt) continue;
-        int src = S.tile_site_base[t], dst = S.tile_site_off[t], c = S.tile_ctg[t];
-        for (int j = 0; j < cnt; j++) {
-            int gp = S.us_gpos[src + j];
-            uint4 v = reinterpret_cast<const uint4 *>(S.us_cnt)[src + j];
-            uint32_t k[4] = {v.x << 2, (v.y << 2) | 1, (v.z << 2) | 2, (v.w << 2) | 3};
+    // one thread per site (claimed slot u of its tile -> ordered slot d), four sites per thread
+    // and round so that the dependent loads (tile -> offsets -> contig origin) of a round overlap
+    for (int u0 = threadIdx.x; u0 < (int)total; u0 += 4 * blockDim.x) {
+        int t[4], d[4], c[4], gp[4];
+        uint4 v[4];
+        int64_t org[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int u = u0 + j * blockDim.x;
+            t[j] = u < (int)total ? S.us_tile[u] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int u = min(u0 + j * (int)blockDim.x, (int)total - 1);
+            d[j] = S.tile_site_off[t[j]] + (u - S.tile_site_base[t[j]]);
+            c[j] = S.tile_ctg[t[j]];
+            gp[j] = S.us_gpos[u];
+            v[j] = reinterpret_cast<const uint4 *>(S.us_cnt)[u];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) org[j] = ctg_goff[c[j]];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (u0 + j * blockDim.x >= (int)total) break;
+            const uint32_t k[4] = {v[j].x << 2, (v[j].y << 2) | 1, (v[j].z << 2) | 2, (v[j].w << 2) | 3};
             uint32_t m0 = max(max(k[0], k[1]), max(k[2], k[3])), m1 = 0;
+#pragma unroll
             for (int b = 0; b < 4; b++) if (k[b] != m0) m1 = max(m1, k[b]);
-            int b0 = m0 & 3, b1 = m1 & 3;
-            int d = dst + j;
-            S.s_gpos[d] = gp;
-            O.d_site_ctg[d] = c;
-            O.d_site_pos[d] = (int32_t)(gp - ctg_goff[c]) + 1;
-            reinterpret_cast<uint4 *>(O.d_site_cnt)[d] = v;
-            O.d_site_top[2 * d] = (uint8_t)b0; O.d_site_top[2 * d + 1] = (uint8_t)b1;
+            const int b0 = m0 & 3, b1 = m1 & 3, dd = d[j];
+            S.s_gpos[dd] = gp[j];
+            O.d_site_ctg[dd] = c[j];
+            O.d_site_pos[dd] = (int32_t)(gp[j] - org[j]) + 1;
+            reinterpret_cast<uint4 *>(O.d_site_cnt)[dd] = v[j];
             // allele order of the association table = order by "ACTG" (SURVEY.md B.1):
-            // rank A=0 C=1 T=2 G=3
-            const int rank[4] = {0, 1, 3, 2};
-            bool sw = rank[b0] > rank[b1];
-            O.d_site_al[2 * d] = (uint8_t)(sw ? b1 : b0); O.d_site_al[2 * d + 1] = (uint8_t)(sw ? b0 : b1);
-            S.site_rows[d] = (int)((m0 >> 2) + (m1 >> 2));
+            // rank A=0 C=1 T=2 G=3 (two bits each in 0xB4)
+            const bool sw = ((0xB4 >> (2 * b0)) & 3) > ((0xB4 >> (2 * b1)) & 3);
+            reinterpret_cast<uchar2 *>(O.d_site_top)[dd] = make_uchar2((uint8_t)b0, (uint8_t)b1);
+            reinterpret_cast<uchar2 *>(O.d_site_al)[dd] = make_uchar2((uint8_t)(sw ? b1 : b0), (uint8_t)(sw ? b0 : b1));
+            S.site_rows[dd] = (int)((m0 >> 2) + (m1 >> 2));
         }
     }
     __threadfence_block();
@@ -765,7 +782,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     size_t o_tlim = L.add(4 * (size_t)n_tiles);
     size_t o_tbase = L.add(4 * (size_t)n_tiles), o_tcnt = L.add(4 * (size_t)(n_tiles + 1)),
            o_toff = L.add(4 * (size_t)(n_tiles + 2));
-    size_t o_usg = L.add(4 * (size_t)cap_sites), o_usc = L.add(16 * (size_t)cap_sites);
+    size_t o_usg = L.add(4 * (size_t)cap_sites), o_usc = L.add(16 * (size_t)cap_sites), o_ust = L.add(4 * (size_t)cap_sites);
     size_t o_sg = L.add(4 * (size_t)cap_sites), o_srow = L.add(4 * (size_t)(cap_sites + 1)),
            o_sroff = L.add(4 * (size_t)(cap_sites + 2));
     size_t o_cursor = L.add(16);
@@ -787,6 +804,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.tile_site_base = fuz_at<int32_t>(ctx, o_tbase); S.tile_site_cnt = fuz_at<int32_t>(ctx, o_tcnt);
     S.tile_site_off = fuz_at<int32_t>(ctx, o_toff);
     S.us_gpos = fuz_at<int32_t>(ctx, o_usg); S.us_cnt = fuz_at<uint32_t>(ctx, o_usc);
+    S.us_tile = fuz_at<int32_t>(ctx, o_ust);
     S.s_gpos = fuz_at<int32_t>(ctx, o_sg); S.site_rows = fuz_at<int32_t>(ctx, o_srow);
     S.site_row_off = keep_row_off;       // also the first input of the association stage
     (void)o_sroff;
