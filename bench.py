@@ -70,12 +70,45 @@ def algorithmic_bytes(sset) -> dict:
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every
+    millisecond or so (the timed region is a few milliseconds long; nvidia-smi's own loop mode
+    cannot sample that fast and is only the fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.p = None
+        self.thread = None
+        self.sm, self.smax, self.reasons, self.run = [], [], set(), True
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+
+            def poll():
+                while self.run:
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = int(reasons_fn(h))
+                        for nm, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        break
+                    time.sleep(0.0005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,6 +117,11 @@ class ClockSampler:
             pass
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.run = False
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.smax) if self.smax else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -94,7 +132,6 @@ class ClockSampler:
             self.p.kill()
             out = ""
         sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -103,11 +140,11 @@ class ClockSampler:
                 sm.append(float(f[0])); smax.append(float(f[1]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def measured_peak():
@@ -267,7 +304,6 @@ def run_b200(args):
     evs = [one_step(True) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = eng.launch_count() - launches0
     st = eng.status()
     step_ms = [a.elapsed_time(b) for a, b in evs]
@@ -285,6 +321,7 @@ def run_b200(args):
         r = eng.phase_host(pb, caps, host_out)
     torch.cuda.synchronize(dev)
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()                                     # sampled over both timed regions (device-resident + e2e)
     barrier()
 
     # ---- aggregate over ranks: units summed, time = max over ranks

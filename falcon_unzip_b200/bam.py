@@ -19,6 +19,7 @@ codes into ``=ACMGRSVTWYHKDBN`` (high nibble first).
 """
 from __future__ import annotations
 
+import os
 import struct
 import zlib
 from typing import Iterable, Iterator, List, Sequence, Tuple
@@ -200,11 +201,9 @@ def write_bam(path: str, refs: Sequence[Tuple[str, int]], records: bytes,
         f.write(_BGZF_EOF)
 
 
-def bgzf_inflate(path: str) -> bytes:
-    """Concatenated payload of every BGZF block of ``path``."""
-    with open(path, "rb") as f:
-        raw = f.read()
-    out = []
+def _bgzf_blocks(raw, path: str):
+    """(compressed start, compressed end, isize, crc) of every BGZF block of the file image."""
+    blocks = []
     o, n = 0, len(raw)
     while o < n:
         if raw[o:o + 4] != b"\x1f\x8b\x08\x04":
@@ -218,30 +217,58 @@ def bgzf_inflate(path: str) -> bytes:
             x += 4 + slen
         if bsize is None:
             raise ValueError("%s: BGZF block without BC subfield" % path)
-        cdata = raw[xend:o + bsize - 8]
         crc, isize = struct.unpack_from("<II", raw, o + bsize - 8)
-        data = zlib.decompress(cdata, -15) if isize else b""
-        if len(data) != isize or (zlib.crc32(data) & 0xFFFFFFFF) != crc:
-            raise ValueError("%s: BGZF block CRC/size mismatch at byte %d" % (path, o))
-        out.append(data)
+        blocks.append((xend, o + bsize - 8, isize, crc, o))
         o += bsize
-    return b"".join(out)
+    return blocks
+
+
+def bgzf_inflate(path: str, threads: int = 0) -> memoryview:
+    """Concatenated payload of every BGZF block of ``path``.  Blocks are independent deflate
+    streams (<= 64 KiB each), so they are inflated by a thread pool straight into one buffer
+    (zlib releases the GIL); threads = 0: all host cores (at most 32)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    blocks = _bgzf_blocks(raw, path)
+    offs = [0]
+    for b in blocks:
+        offs.append(offs[-1] + b[2])
+    out = bytearray(offs[-1])
+    view = memoryview(out)
+
+    def work(lo: int, hi: int) -> None:
+        for i in range(lo, hi):
+            c0, c1, isize, crc, o = blocks[i]
+            data = zlib.decompress(raw[c0:c1], -15) if isize else b""
+            if len(data) != isize or (zlib.crc32(data) & 0xFFFFFFFF) != crc:
+                raise ValueError("%s: BGZF block CRC/size mismatch at byte %d" % (path, o))
+            view[offs[i]:offs[i] + isize] = data
+    n_thr = threads or min(32, os.cpu_count() or 1)
+    step = 32
+    if n_thr <= 1 or len(blocks) <= step:
+        work(0, len(blocks))
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(n_thr) as pool:
+            for fut in [pool.submit(work, lo, min(lo + step, len(blocks))) for lo in range(0, len(blocks), step)]:
+                fut.result()
+    return view
 
 
 def read_bam(path: str):
-    """-> (header_text, refs [(name, length)], records buffer (bytes))."""
+    """-> (header_text, refs [(name, length)], records buffer (memoryview, no copy))."""
     data = bgzf_inflate(path)
-    if data[:4] != b"BAM\1":
+    if bytes(data[:4]) != b"BAM\1":
         raise ValueError("%s: missing BAM magic" % path)
     (l_text,) = struct.unpack_from("<i", data, 4)
-    text = data[8:8 + l_text].split(b"\0", 1)[0].decode("ascii", "replace")
+    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("ascii", "replace")
     o = 8 + l_text
     (n_ref,) = struct.unpack_from("<i", data, o)
     o += 4
     refs = []
     for _ in range(n_ref):
         (l_name,) = struct.unpack_from("<i", data, o)
-        name = data[o + 4:o + 4 + l_name - 1].decode("ascii")
+        name = bytes(data[o + 4:o + 4 + l_name - 1]).decode("ascii")
         (l_ref,) = struct.unpack_from("<i", data, o + 4 + l_name)
         refs.append((name, l_ref))
         o += 8 + l_name
