@@ -268,8 +268,9 @@ def run_b200(args):
     from falcon_unzip_b200._lib import lib
     lib().fuz_set_stream(eng.ctx, stream.cuda_stream)
 
+    # q_ids (phasing.py:47-54) are NOT precomputed: both timed legs assign them on the device
     pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs], rec_off=sset.rec_off,
-                              pin=True)
+                              pin=True, assign_qids=False)
     db = eng.upload(pb)
     caps = engine.default_caps(int(pb.ctg_len.sum()), pb.n_rec)
     # size the outputs once (capacity retry outside the timed region)

@@ -48,7 +48,7 @@ _OUT_ORDER = ["site_ctg", "site_pos", "site_cnt", "site_al", "site_top", "vm_sit
 class Outputs(C.Structure):
     _fields_ = ([("cap_sites", C.c_int64), ("cap_vmap", C.c_int64), ("cap_atable", C.c_int64),
                  ("cap_reads", C.c_int64)] + [("d_" + n, C.c_void_p) for n in _OUT_ORDER]
-                + [("d_counts", C.c_void_p)])
+                + [("d_counts", C.c_void_p), ("d_ctg_nq", C.c_void_p), ("d_name_first", C.c_void_p)])
 
 
 class HostBatch(C.Structure):
@@ -59,7 +59,8 @@ class HostBatch(C.Structure):
 
 class HostOutputs(C.Structure):
     _fields_ = ([("cap_sites", C.c_int64), ("cap_vmap", C.c_int64), ("cap_atable", C.c_int64),
-                 ("cap_reads", C.c_int64)] + [(n, C.c_void_p) for n in _OUT_ORDER])
+                 ("cap_reads", C.c_int64)] + [(n, C.c_void_p) for n in _OUT_ORDER] +
+                [("ctg_nq", C.c_void_p), ("name_first", C.c_void_p)])
 
 
 class RRInput(C.Structure):
@@ -108,6 +109,8 @@ SYMBOLS = [
     ("fuz_phase_batch", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Outputs)]),
     ("fuz_phase_batch_host", C.c_int, [C.c_void_p, C.POINTER(HostBatch), C.POINTER(HostOutputs),
                                        C.POINTER(Status), _i64p, _i64p]),
+    ("fuz_assign_qids", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     ("fuz_rr_track", C.c_int, [C.c_void_p, C.POINTER(RRInput), C.POINTER(RROutputs)]),
     ("fuz_host_parse_la4falcon", C.c_int64, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),

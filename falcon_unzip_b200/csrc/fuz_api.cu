@@ -9,10 +9,38 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
 int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_valid);
 int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
                    bool dup_valid);
+int fuz_assign_qids_impl(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec, int64_t rec_bytes,
+                         const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid, int32_t *d_ctg_nq,
+                         int64_t *d_name_first, int32_t *d_ctg_slots);
 
-extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
-    if (!ctx || !in || !out) return FUZ_E_ARG;
-    int rc = fuz_het_call_impl(ctx, in, out);
+extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in_, fuz_outputs *out) {
+    if (!ctx || !in_ || !out) return FUZ_E_ARG;
+    fuz_batch b = *in_;
+    const fuz_batch *in = &b;
+    int rc;
+    if (!b.d_rec_qid) {
+        // q_ids assigned here (phasing.py:47-54).  The read stage then indexes its per-read tables by
+        // (first record of the contig + q_id): one slot per record, so no count has to come back to
+        // the host before the later stages are launched.
+        if (b.n_rec < 0 || b.n_ctg < 1 || !b.d_ctg_rec_off) return fuz_fail(ctx, FUZ_E_ARG, "fuz_phase_batch: empty batch");
+        const size_t sz_q = ((size_t)(b.n_rec + 1) * 4 + 255) & ~(size_t)255, sz_c = ((size_t)b.n_ctg * 4 + 255) & ~(size_t)255;
+        const size_t need = sz_q + 2 * sz_c;
+        if (need > ctx->qid_cap) {
+            FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->qid_buf) FUZ_CUDA(ctx, cudaFree(ctx->qid_buf));
+            ctx->qid_buf = nullptr; ctx->qid_cap = 0;
+            cudaError_t e = cudaMalloc(&ctx->qid_buf, need + (need >> 2));
+            if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "q_id buffer of %zu bytes: %s", need, cudaGetErrorString(e));
+            ctx->qid_cap = need + (need >> 2);
+        }
+        int32_t *qid = reinterpret_cast<int32_t *>(ctx->qid_buf), *slots = reinterpret_cast<int32_t *>(ctx->qid_buf + sz_q);
+        int32_t *nq = out->d_ctg_nq ? out->d_ctg_nq : reinterpret_cast<int32_t *>(ctx->qid_buf + sz_q + sz_c);
+        if ((rc = fuz_assign_qids_impl(ctx, b.d_rec_buf, b.d_rec_off, b.n_rec, b.rec_bytes, b.d_ctg_rec_off, b.n_ctg, qid, nq,
+                                       out->d_name_first, slots)))
+            return rc;
+        b.d_rec_qid = qid; b.d_ctg_nq = slots; b.total_nq = b.n_rec;
+    }
+    rc = fuz_het_call_impl(ctx, in, out);
     if (rc) return rc;
     // the row range of every site (het call) and the duplicate flags (association) stay in
     // the context's inter-stage buffer and are reused by the later stages
@@ -117,10 +145,12 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     int64_t total_nq = 0;
     FuzLayout P;   // pinned
     size_t p_goff = P.add(8 * (size_t)(n_ctg + 1)), p_fetched = P.add(8);
+    const bool dev_qid = in->h_rec_qid == nullptr;
     FuzLayout D;   // device
     size_t d_rec = D.add((size_t)in->rec_bytes + 32), d_off = D.add(8 * (size_t)(n_rec + 1)), d_qid = D.add(4 * (size_t)(n_rec + 1));
     size_t d_cro = D.add(4 * (size_t)(n_ctg + 1)), d_clen = D.add(4 * (size_t)n_ctg), d_goff = D.add(8 * (size_t)(n_ctg + 1));
     size_t d_cnq = D.add(4 * (size_t)n_ctg), d_fetched = D.add(8);
+    size_t d_nfirst = D.add(8 * (size_t)(n_rec + 1));
     const int64_t cs = out->cap_sites, cv = out->cap_vmap, ca = out->cap_atable, cr = out->cap_reads;
     size_t o_sctg = D.add(4 * (size_t)cs), o_spos = D.add(4 * (size_t)cs), o_scnt = D.add(16 * (size_t)cs);
     size_t o_sal = D.add(2 * (size_t)cs), o_stop = D.add(2 * (size_t)cs);
@@ -139,7 +169,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
         int64_t padded = ((int64_t)in->h_ctg_len[c] + FUZ_TILE - 1) / FUZ_TILE * FUZ_TILE;
         if (padded == 0) padded = FUZ_TILE;
         goff[c + 1] = goff[c] + padded;
-        total_nq += in->h_ctg_nq[c];
+        if (!dev_qid) total_nq += in->h_ctg_nq[c];
     }
     uint8_t *dv = ctx->stage_dev;
     int64_t up = 0;
@@ -168,11 +198,11 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
         FUZ_CUDA(ctx, h2d(d_rec, in->h_rec_buf, (size_t)in->rec_bytes));
     }
     FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 32, st));
-    FUZ_CUDA(ctx, h2d(d_qid, in->h_rec_qid, 4 * (size_t)n_rec));
+    if (!dev_qid) FUZ_CUDA(ctx, h2d(d_qid, in->h_rec_qid, 4 * (size_t)n_rec));
     FUZ_CUDA(ctx, h2d(d_cro, in->h_ctg_rec_off, 4 * (size_t)(n_ctg + 1)));
     FUZ_CUDA(ctx, h2d(d_clen, in->h_ctg_len, 4 * (size_t)n_ctg));
     FUZ_CUDA(ctx, h2d(d_goff, goff, 8 * (size_t)(n_ctg + 1)));
-    FUZ_CUDA(ctx, h2d(d_cnq, in->h_ctg_nq, 4 * (size_t)n_ctg));
+    if (!dev_qid) FUZ_CUDA(ctx, h2d(d_cnq, in->h_ctg_nq, 4 * (size_t)n_ctg));
     fuz_batch b;
     memset(&b, 0, sizeof(b));
     b.n_ctg = n_ctg; b.n_rec = n_rec; b.rec_bytes = in->rec_bytes;
@@ -181,6 +211,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     b.d_ctg_len = reinterpret_cast<int32_t *>(dv + d_clen); b.d_ctg_goff = reinterpret_cast<int64_t *>(dv + d_goff);
     b.d_ctg_nq = reinterpret_cast<int32_t *>(dv + d_cnq);
     b.total_glen = goff[n_ctg]; b.total_nq = total_nq;
+    if (dev_qid) b.d_rec_qid = nullptr;       // fuz_phase_batch assigns the q_ids on the device
     fuz_outputs o;
     memset(&o, 0, sizeof(o));
     o.cap_sites = cs; o.cap_vmap = cv; o.cap_atable = ca; o.cap_reads = cr;
@@ -195,6 +226,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     o.d_pr_phase = DP(int32_t, o_rp); o.d_pr_n0 = DP(int32_t, o_r0); o.d_pr_n1 = DP(int32_t, o_r1);
 #undef DP
     o.d_counts = nullptr;
+    if (dev_qid) { o.d_ctg_nq = reinterpret_cast<int32_t *>(dv + d_cnq); o.d_name_first = reinterpret_cast<int64_t *>(dv + d_nfirst); }
     if ((rc = fuz_phase_batch(ctx, &b, &o))) return rc;
     rc = fuz_get_status(ctx, h_status);          // synchronises; row counts now known
     if (mapped) up += *reinterpret_cast<const int64_t *>(ctx->stage_pin + p_fetched);
@@ -221,6 +253,10 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     FUZ_CUDA(ctx, d2h(out->pr_ctg, o_rc, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_qid, o_rq, 4 * nr));
     FUZ_CUDA(ctx, d2h(out->pr_block, o_rb, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_phase, o_rp, 4 * nr));
     FUZ_CUDA(ctx, d2h(out->pr_n0, o_r0, 4 * nr)); FUZ_CUDA(ctx, d2h(out->pr_n1, o_r1, 4 * nr));
+    if (dev_qid) {
+        FUZ_CUDA(ctx, d2h(out->ctg_nq, d_cnq, 4 * (size_t)n_ctg));
+        FUZ_CUDA(ctx, d2h(out->name_first, d_nfirst, 8 * (size_t)n_rec));
+    }
     FUZ_CUDA(ctx, cudaStreamSynchronize(st));
     if (d2h_bytes) *d2h_bytes = down;
     return FUZ_OK;

@@ -65,6 +65,7 @@ extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->keep) cudaFree(ctx->keep);
+    if (ctx->qid_buf) cudaFree(ctx->qid_buf);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
     if (ctx->d_status) cudaFree(ctx->d_status);

@@ -862,5 +862,6 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
 }
 
 extern "C" int fuz_het_call(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
+    if (ctx && in && !in->d_rec_qid) return fuz_fail(ctx, FUZ_E_ARG, "fuz_het_call needs d_rec_qid (fuz_assign_qids or fuz_phase_batch)");
     return fuz_het_call_impl(ctx, in, out);
 }

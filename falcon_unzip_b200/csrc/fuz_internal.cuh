@@ -29,6 +29,9 @@ struct fuz_ctx {
     // (row range of every site, duplicate flags of the variant_map rows)
     uint8_t *keep = nullptr;
     size_t keep_cap = 0;
+    // q_ids assigned by the library (fuz_phase_batch with d_rec_qid == NULL): live for the whole call
+    uint8_t *qid_buf = nullptr;
+    size_t qid_cap = 0;
     // status block
     fuz_status *d_status = nullptr;
     fuz_status *h_status = nullptr;   // pinned

@@ -26,7 +26,7 @@ class PreparedBatch:
     """Host arrays of one batch of contigs (see include/fuz.h, fuz_host_batch)."""
     records: np.ndarray          # uint8 [rec_bytes] verbatim BAM records
     rec_off: np.ndarray          # int64 [n_rec + 1]
-    rec_qid: np.ndarray          # int32 [n_rec]
+    rec_qid: Optional[np.ndarray]  # int32 [n_rec]; None: assigned on the device by phase_host
     ctg_rec_off: np.ndarray      # int32 [n_ctg + 1]
     ctg_len: np.ndarray          # int32 [n_ctg]
     ctg_nq: np.ndarray           # int32 [n_ctg]
@@ -82,10 +82,12 @@ def record_refids(records: np.ndarray, rec_off: np.ndarray) -> np.ndarray:
 
 def prepare_batch(records, ctg_names: Sequence[str], ctg_lens: Sequence[int],
                   rec_off: Optional[np.ndarray] = None, ctg_rec_off: Optional[np.ndarray] = None,
-                  pin: bool = False) -> PreparedBatch:
+                  pin: bool = False, assign_qids: bool = True) -> PreparedBatch:
     """records: concatenated BAM records grouped by contig in the order of ctg_names (refID
     ascending, i.e. a coordinate-sorted BAM).  If ctg_rec_off is None the grouping is read
-    from the refID fields, which must be 0..n_ctg-1 in order."""
+    from the refID fields, which must be 0..n_ctg-1 in order.  assign_qids=False leaves the
+    QNAME -> q_id assignment (phasing.py:47-54) to the device (Engine.phase_host fills ctg_nq
+    and name_first of the batch)."""
     if not isinstance(records, np.ndarray):
         records = np.frombuffer(records, dtype=np.uint8)
     records = np.ascontiguousarray(records, dtype=np.uint8)
@@ -99,6 +101,12 @@ def prepare_batch(records, ctg_names: Sequence[str], ctg_lens: Sequence[int],
             raise FuzError(_lib.FUZ_E_UNSORTED, "records are not grouped by reference id 0..%d" % (n_ctg - 1))
         ctg_rec_off = np.searchsorted(refid, np.arange(n_ctg + 1), side="left")
     ctg_rec_off = np.ascontiguousarray(ctg_rec_off, dtype=np.int32)
+    if not assign_qids:
+        pb = PreparedBatch(records, rec_off, None, ctg_rec_off, np.asarray(ctg_lens, dtype=np.int32),
+                           np.zeros(n_ctg, dtype=np.int32), np.zeros(0, np.int64), list(ctg_names))
+        if pin:
+            pin_batch(pb)
+        return pb
     rec_qid = np.empty(n_rec, dtype=np.int32)
     ctg_nq = np.zeros(n_ctg, dtype=np.int32)
     name_first = np.empty(max(n_rec, 1), dtype=np.int64)
@@ -118,6 +126,8 @@ def pin_batch(pb: PreparedBatch) -> None:
     import torch
     for name in ("records", "rec_off", "rec_qid", "ctg_rec_off", "ctg_len", "ctg_nq"):
         a = getattr(pb, name)
+        if a is None:
+            continue
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         pb.pinned[name] = t
         setattr(pb, name, t.numpy())
@@ -215,7 +225,10 @@ class DeviceBatch:
             return t.to(device, non_blocking=True)
         self.rec_buf = up(pb.records, pad=32)
         self.rec_off = up(pb.rec_off)
-        self.rec_qid = up(pb.rec_qid) if pb.n_rec else torch.zeros(1, dtype=torch.int32, device=device)
+        self.dev_qid = pb.rec_qid is None                # q_ids assigned by fuz_phase_batch
+        self.rec_qid = up(pb.rec_qid) if pb.n_rec and not self.dev_qid else torch.zeros(1, dtype=torch.int32, device=device)
+        self.qid_nq = torch.zeros(max(pb.n_ctg, 1), dtype=torch.int32, device=device)
+        self.qid_first = torch.zeros(max(pb.n_rec, 1), dtype=torch.int64, device=device)
         self.ctg_rec_off = up(pb.ctg_rec_off)
         self.ctg_len = up(pb.ctg_len)
         self.ctg_goff = up(goff)
@@ -223,7 +236,8 @@ class DeviceBatch:
         self.total_glen = int(goff[-1])
         b = _lib.Batch()
         b.n_ctg, b.n_rec, b.rec_bytes = pb.n_ctg, pb.n_rec, len(pb.records)
-        b.d_rec_buf, b.d_rec_off, b.d_rec_qid = self.rec_buf.data_ptr(), self.rec_off.data_ptr(), self.rec_qid.data_ptr()
+        b.d_rec_buf, b.d_rec_off = self.rec_buf.data_ptr(), self.rec_off.data_ptr()
+        b.d_rec_qid = None if self.dev_qid else self.rec_qid.data_ptr()
         b.d_ctg_rec_off, b.d_ctg_len = self.ctg_rec_off.data_ptr(), self.ctg_len.data_ptr()
         b.d_ctg_goff, b.d_ctg_nq = self.ctg_goff.data_ptr(), self.ctg_nq.data_ptr()
         b.total_glen, b.total_nq = self.total_glen, int(pb.ctg_nq.sum())
@@ -306,7 +320,21 @@ class Engine:
         return do
 
     def phase_batch_async(self, db: DeviceBatch, do: DeviceOutputs) -> None:
+        if db.dev_qid:                                   # library assigns the q_ids: tables come back here
+            do.c.d_ctg_nq, do.c.d_name_first = db.qid_nq.data_ptr(), db.qid_first.data_ptr()
         _lib.check(self.ctx, lib().fuz_phase_batch(self.ctx, C.byref(db.c), C.byref(do.c)))
+
+    def assign_qids(self, db: DeviceBatch):
+        """fuz_assign_qids on an uploaded batch -> (rec_qid, ctg_nq, name_first) as numpy arrays."""
+        torch = self._torch
+        pb = db.pb
+        qid = torch.zeros(max(pb.n_rec, 1), dtype=torch.int32, device=self.device)
+        _lib.check(self.ctx, lib().fuz_assign_qids(self.ctx, db.rec_buf.data_ptr(), db.rec_off.data_ptr(), pb.n_rec, len(pb.records),
+                                                   db.ctg_rec_off.data_ptr(), pb.n_ctg, qid.data_ptr(), db.qid_nq.data_ptr(),
+                                                   db.qid_first.data_ptr()))
+        self.sync()
+        nq = db.qid_nq.cpu().numpy()[:pb.n_ctg]
+        return qid.cpu().numpy()[:pb.n_rec], nq, db.qid_first.cpu().numpy()[:int(nq.sum())]
 
     def het_call_async(self, db: DeviceBatch, do: DeviceOutputs) -> None:
         _lib.check(self.ctx, lib().fuz_het_call(self.ctx, C.byref(db.c), C.byref(do.c)))
@@ -348,6 +376,9 @@ class Engine:
         run = (lambda do: self.phase_batch_async(db, do)) if stage == "all" else (lambda do: self.het_call_async(db, do))
         do, st = self._retry(caps, db.total_glen if want_counts else 0, run)
         arrays = do.fetch(st)
+        if db.dev_qid and stage == "all":
+            pb.ctg_nq = db.qid_nq.cpu().numpy()[:pb.n_ctg]
+            pb.name_first = db.qid_first.cpu().numpy()[:int(pb.ctg_nq.sum())].copy()
         if want_counts:
             arrays["counts"] = do.counts.cpu().numpy().view(np.uint32).reshape(-1, 4)
             arrays["goff"] = pb.goff()
@@ -360,8 +391,11 @@ class Engine:
         caps = caps or default_caps(int(pb.ctg_len.sum()), pb.n_rec)
         hb = _lib.HostBatch()
         hb.n_ctg, hb.n_rec, hb.rec_bytes = pb.n_ctg, pb.n_rec, len(pb.records)
-        hb.h_rec_buf, hb.h_rec_off, hb.h_rec_qid = _np_ptr(pb.records), _np_ptr(pb.rec_off), _np_ptr(pb.rec_qid)
+        dev_qid = pb.rec_qid is None
+        hb.h_rec_buf, hb.h_rec_off = _np_ptr(pb.records), _np_ptr(pb.rec_off)
+        hb.h_rec_qid = None if dev_qid else _np_ptr(pb.rec_qid)
         hb.h_ctg_rec_off, hb.h_ctg_len, hb.h_ctg_nq = _np_ptr(pb.ctg_rec_off), _np_ptr(pb.ctg_len), _np_ptr(pb.ctg_nq)
+        q_nq, q_first = np.zeros(pb.n_ctg, np.int32), np.zeros(max(pb.n_rec, 1), np.int64)
         for _ in range(8):
             bufs = host_out if host_out is not None and host_out.get("_caps") == caps else alloc_host_outputs(caps)
             ho = _lib.HostOutputs()
@@ -369,10 +403,15 @@ class Engine:
                 setattr(ho, "cap_" + key, caps[key])
             for name, _dt, _key, _w in _lib.OUTPUT_ARRAYS:
                 setattr(ho, name, _np_ptr(bufs[name]))
+            if dev_qid:
+                ho.ctg_nq, ho.name_first = _np_ptr(q_nq), _np_ptr(q_first)
             st = _lib.Status()
             up, down = C.c_int64(0), C.c_int64(0)
             rc = lib().fuz_phase_batch_host(self.ctx, C.byref(hb), C.byref(ho), C.byref(st), C.byref(up), C.byref(down))
             if rc == _lib.FUZ_OK:
+                if dev_qid:
+                    pb.ctg_nq = q_nq
+                    pb.name_first = q_first[:int(q_nq.sum())].copy()
                 arrays = {}
                 for name, _dt, key, width in _lib.OUTPUT_ARRAYS:
                     n = int(getattr(st, _CAP_KEY_N[key]))

@@ -331,7 +331,8 @@ def phase_contigs(records, ctg_names: Sequence[str], ref_seqs: Sequence[str], ba
     """Fused path: every contig of the batch in one device call, then the per-contig files.
     records: concatenated BAM records grouped by contig, in the order of ctg_names (grouping from
     the refID fields 0..n-1, or given explicitly as record offsets ctg_rec_off)."""
-    pb = engine.prepare_batch(records, ctg_names, [len(s) for s in ref_seqs], ctg_rec_off=ctg_rec_off)
+    pb = engine.prepare_batch(records, ctg_names, [len(s) for s in ref_seqs], ctg_rec_off=ctg_rec_off,
+                              assign_qids=not host_path)       # host entry: q_ids are assigned on the device
     eng = engine.get_engine(device)
     res = eng.phase_host(pb) if host_path else eng.phase_device(pb)
     sl = formats.contig_slices(res, pb.n_ctg)

@@ -84,7 +84,8 @@ typedef struct {
     int64_t rec_bytes;
     const uint8_t *d_rec_buf;     /* [rec_bytes + 32]                                   */
     const int64_t *d_rec_off;     /* [n_rec + 1]                                        */
-    const int32_t *d_rec_qid;     /* [n_rec] q_id of the record's QNAME in its contig   */
+    const int32_t *d_rec_qid;     /* [n_rec] q_id of the record's QNAME in its contig, or NULL:
+                                   * fuz_phase_batch assigns them (d_ctg_nq / total_nq ignored) */
     const int32_t *d_ctg_rec_off; /* [n_ctg + 1] record range of each contig            */
     const int32_t *d_ctg_len;     /* [n_ctg]                                            */
     const int64_t *d_ctg_goff;    /* [n_ctg + 1] tile-aligned global offsets            */
@@ -108,6 +109,10 @@ typedef struct {
     int32_t *d_pr_ctg, *d_pr_qid, *d_pr_block, *d_pr_phase, *d_pr_n0, *d_pr_n1;
     /* optional full pileup (debug / parity): [total_glen*4] depth of A,C,G,T, or NULL   */
     uint32_t *d_counts;
+    /* optional, filled when fuz_phase_batch assigns the q_ids (fuz_batch.d_rec_qid == NULL):
+     * distinct QNAMEs per contig [n_ctg]; first record of every q_id [n_rec]            */
+    int32_t *d_ctg_nq;
+    int64_t *d_name_first;
 } fuz_outputs;
 
 /* Filled on the device, copied to the host by fuz_get_status(). */
@@ -181,10 +186,10 @@ typedef struct {
     int64_t rec_bytes;
     const uint8_t *h_rec_buf;     /* [rec_bytes] verbatim BAM records                    */
     const int64_t *h_rec_off;     /* [n_rec + 1]                                         */
-    const int32_t *h_rec_qid;     /* [n_rec]                                             */
+    const int32_t *h_rec_qid;     /* [n_rec], or NULL: q_ids are assigned on the device  */
     const int32_t *h_ctg_rec_off; /* [n_ctg + 1]                                         */
     const int32_t *h_ctg_len;     /* [n_ctg]                                             */
-    const int32_t *h_ctg_nq;      /* [n_ctg]                                             */
+    const int32_t *h_ctg_nq;      /* [n_ctg] (ignored when h_rec_qid is NULL)            */
 } fuz_host_batch;
 
 typedef struct {
@@ -194,6 +199,9 @@ typedef struct {
     int32_t *at_s1, *at_s2, *at_ct;
     uint8_t *ph_state; int32_t *ph_lext, *ph_rext, *ph_lscore, *ph_rscore, *ph_block;
     int32_t *pr_ctg, *pr_qid, *pr_block, *pr_phase, *pr_n0, *pr_n1;
+    /* filled when the q_ids are assigned on the device (h_rec_qid == NULL); may be NULL   */
+    int32_t *ctg_nq;              /* [n_ctg] distinct QNAMEs per contig                   */
+    int64_t *name_first;          /* [n_rec] first record of every q_id, contig after contig */
 } fuz_host_outputs;
 
 /* H2D of the batch, fuz_phase_batch, D2H of every row array (only the filled prefix).
@@ -201,6 +209,14 @@ typedef struct {
  * h_status receives the final status; bytes moved are reported for bench.py. */
 int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_outputs *out,
                          fuz_status *h_status, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* ---- q_id assignment on the device (falcon_unzip/phasing.py:47-54) ------------------ */
+/* First-seen QNAME -> q_id per contig, before any filtering: the device form of
+ * fuz_host_assign_qids.  d_rec_qid [n_rec], d_ctg_nq [n_ctg], d_name_first [n_rec] (record
+ * index of the first record of every q_id, contig after contig; may be NULL). */
+int fuz_assign_qids(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec,
+                    int64_t rec_bytes, const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid,
+                    int32_t *d_ctg_nq, int64_t *d_name_first);
 
 /* ---- raw-read -> haplotig tracking (falcon_unzip/rr_hctg_track.py) --------------- */
 /* fuz_rr_track replaces tr_stage1 (:31-65), the heap merge (:97-105) and the contig vote

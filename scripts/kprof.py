@@ -22,7 +22,8 @@ def main():
     import torch
     from falcon_unzip_b200 import engine
     eng = engine.Engine(0)
-    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs], rec_off=sset.rec_off)
+    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs], rec_off=sset.rec_off,
+                              assign_qids=False)
     db = eng.upload(pb)
     do, st = eng._retry(engine.default_caps(int(pb.ctg_len.sum()), pb.n_rec), 0, lambda d: eng.phase_batch_async(db, d))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)

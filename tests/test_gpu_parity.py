@@ -157,3 +157,45 @@ def test_selective_fetch_of_pinned_records_equals_full_copy(eng, cfg):
         for k, a in full.arrays.items():
             assert np.array_equal(res.arrays[k], a), k
     assert full.n_sites > 0 and full.n_reads > 0
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+def test_device_qid_assignment_equals_host_helper(eng, cfg):
+    """QNAME -> q_id in first-seen order per contig (phasing.py:47-54): hash-table kernels against
+    the host helper (itself pinned to the oracle in test_host_formats), duplicated names included."""
+    from falcon_unzip_b200 import engine
+    sset = synth_set(cfg)
+    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+    qid, nq, first = eng.assign_qids(eng.upload(pb))
+    assert np.array_equal(qid, pb.rec_qid) and np.array_equal(nq, pb.ctg_nq) and np.array_equal(first, pb.name_first)
+    if cfg == "quirks":
+        assert int(nq.sum()) < pb.n_rec                      # the set carries duplicated QNAMEs
+
+
+def test_same_qname_in_two_contigs_and_library_assigned_qids(eng):
+    """A name seen in two contigs gets an id in each; fuz_phase_batch with d_rec_qid = NULL gives the
+    same rows as with q_ids assigned on the host."""
+    from falcon_unzip_b200 import bam, engine
+    sset = synth_set("tiny")
+    off = engine.index_records(sset.records)
+    rec = sset.records.copy()
+    pb0 = engine.prepare_batch(rec, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+    # rebuild one record of contig 1 with the name of the first record of contig 0
+    a, r1 = int(off[0]), int(pb0.ctg_rec_off[1]) + 3
+    name = rec[a + 36:a + 36 + int(rec[a + 12])].tobytes()
+    o0, o1 = int(off[r1]), int(off[r1 + 1])
+    body = bytearray(rec[o0:o1].tobytes())
+    body[36:36 + body[12]] = name
+    body[12] = len(name)
+    body[0:4] = (len(body) - 4).to_bytes(4, "little")
+    rec = np.frombuffer(rec[:o0].tobytes() + bytes(body) + rec[o1:].tobytes(), dtype=np.uint8).copy()
+    want = engine.prepare_batch(rec, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+    qid, nq, first = eng.assign_qids(eng.upload(want))
+    assert np.array_equal(qid, want.rec_qid) and np.array_equal(nq, want.ctg_nq) and np.array_equal(first, want.name_first)
+    host_q = eng.phase_device(want)
+    pb = engine.prepare_batch(rec, [r[0] for r in sset.refs], [r[1] for r in sset.refs], assign_qids=False)
+    dev_q = eng.phase_device(pb)
+    assert np.array_equal(pb.ctg_nq, want.ctg_nq) and np.array_equal(pb.name_first, want.name_first)
+    for k, v in host_q.arrays.items():
+        assert np.array_equal(dev_q.arrays[k], v), k
+    assert host_q.n_reads > 0
