@@ -11,7 +11,8 @@ int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t
                    bool dup_valid);
 int fuz_assign_qids_impl(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec, int64_t rec_bytes,
                          const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid, int32_t *d_ctg_nq,
-                         int64_t *d_name_first, int32_t *d_ctg_slots);
+                         int64_t *d_name_first, int32_t *d_ctg_slots, uint8_t *scratch);
+size_t fuz_qid_scratch_bytes(int32_t n_rec);
 
 extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in_, fuz_outputs *out) {
     if (!ctx || !in_ || !out) return FUZ_E_ARG;
@@ -24,7 +25,7 @@ extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in_, fuz_outputs *
         // the host before the later stages are launched.
         if (b.n_rec < 0 || b.n_ctg < 1 || !b.d_ctg_rec_off) return fuz_fail(ctx, FUZ_E_ARG, "fuz_phase_batch: empty batch");
         const size_t sz_q = ((size_t)(b.n_rec + 1) * 4 + 255) & ~(size_t)255, sz_c = ((size_t)b.n_ctg * 4 + 255) & ~(size_t)255;
-        const size_t need = sz_q + 2 * sz_c;
+        const size_t need = sz_q + 2 * sz_c + fuz_qid_scratch_bytes(b.n_rec);
         if (need > ctx->qid_cap) {
             FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->qid_buf) FUZ_CUDA(ctx, cudaFree(ctx->qid_buf));
@@ -35,12 +36,35 @@ extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in_, fuz_outputs *
         }
         int32_t *qid = reinterpret_cast<int32_t *>(ctx->qid_buf), *slots = reinterpret_cast<int32_t *>(ctx->qid_buf + sz_q);
         int32_t *nq = out->d_ctg_nq ? out->d_ctg_nq : reinterpret_cast<int32_t *>(ctx->qid_buf + sz_q + sz_c);
-        if ((rc = fuz_assign_qids_impl(ctx, b.d_rec_buf, b.d_rec_off, b.n_rec, b.rec_bytes, b.d_ctg_rec_off, b.n_ctg, qid, nq,
-                                       out->d_name_first, slots)))
-            return rc;
+        uint8_t *scratch = ctx->qid_buf + sz_q + 2 * sz_c;
+        // independent of the projection and the pileup: run on the side stream, join before k_signature
+        const bool side = !ctx->profile;
+        cudaStream_t main_stream = ctx->stream;
+        if (side) {
+            if (!ctx->aux_stream) {
+                FUZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+                FUZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                FUZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            }
+            FUZ_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+            FUZ_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            ctx->stream = ctx->aux_stream;
+        }
+        rc = fuz_assign_qids_impl(ctx, b.d_rec_buf, b.d_rec_off, b.n_rec, b.rec_bytes, b.d_ctg_rec_off, b.n_ctg, qid, nq,
+                                  out->d_name_first, slots, scratch);
+        ctx->stream = main_stream;
+        if (rc) return rc;
+        if (side) {
+            FUZ_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+            ctx->join_pending = true;
+        }
         b.d_rec_qid = qid; b.d_ctg_nq = slots; b.total_nq = b.n_rec;
     }
     rc = fuz_het_call_impl(ctx, in, out);
+    if (ctx->join_pending) {                  // het_call_impl joins before k_signature; error paths join here
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        ctx->join_pending = false;
+    }
     if (rc) return rc;
     // the row range of every site (het call) and the duplicate flags (association) stay in
     // the context's inter-stage buffer and are reused by the later stages

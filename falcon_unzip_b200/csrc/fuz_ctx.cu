@@ -66,6 +66,9 @@ extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->keep) cudaFree(ctx->keep);
     if (ctx->qid_buf) cudaFree(ctx->qid_buf);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
     if (ctx->d_status) cudaFree(ctx->d_status);

@@ -856,6 +856,10 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     }
     fuz_launch(ctx, k_sites_finalize, 1, 1024, 0, st, n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_sites_finalize");
+    if (ctx->join_pending) {                  // q_ids assigned on the side stream (fuz_phase_batch)
+        FUZ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        ctx->join_pending = false;
+    }
     fuz_launch(ctx, k_signature, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_signature");
     return FUZ_OK;

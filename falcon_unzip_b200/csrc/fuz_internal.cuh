@@ -32,6 +32,10 @@ struct fuz_ctx {
     // q_ids assigned by the library (fuz_phase_batch with d_rec_qid == NULL): live for the whole call
     uint8_t *qid_buf = nullptr;
     size_t qid_cap = 0;
+    // the q_id kernels run on a side stream next to the projection; joined before k_signature
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool join_pending = false;
     // status block
     fuz_status *d_status = nullptr;
     fuz_status *h_status = nullptr;   // pinned

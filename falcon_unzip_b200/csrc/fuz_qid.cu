@@ -115,20 +115,35 @@ __global__ void k_qid_assign(int n_rec, const int32_t *__restrict__ ctg_rec_off,
 
 }  // namespace
 
+// scratch bytes of fuz_assign_qids_impl for n_rec records
+size_t fuz_qid_scratch_bytes(int32_t n_rec) {
+    uint32_t cap = 64;
+    while (cap < 2u * (uint32_t)n_rec) cap <<= 1;
+    return 4 * (size_t)cap + 3 * (((size_t)(n_rec + 2) * 4 + 255) & ~(size_t)255) + 256;
+}
+
+// scratch = nullptr: the context arena (stand-alone call); otherwise a caller-owned buffer of
+// fuz_qid_scratch_bytes(n_rec), which lets the kernels run next to a stage that uses the arena
 int fuz_assign_qids_impl(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec, int64_t rec_bytes,
                          const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid, int32_t *d_ctg_nq,
-                         int64_t *d_name_first, int32_t *d_ctg_slots) {
+                         int64_t *d_name_first, int32_t *d_ctg_slots, uint8_t *scratch) {
     cudaStream_t st = ctx->stream;
     uint32_t cap = 64;
     while (cap < 2u * (uint32_t)n_rec) cap <<= 1;
-    FuzLayout L;
-    size_t o_slots = L.add(4 * (size_t)cap), o_rep = L.add(4 * (size_t)(n_rec + 1)), o_first = L.add(4 * (size_t)(n_rec + 2));
-    size_t o_rank = L.add(4 * (size_t)(n_rec + 2));
-    int rc = fuz_arena_commit(ctx, L);
-    if (rc) return rc;
+    const size_t sz = ((size_t)(n_rec + 2) * 4 + 255) & ~(size_t)255;
+    if (!scratch) {
+        FuzLayout L;
+        size_t o = L.add(fuz_qid_scratch_bytes(n_rec));
+        int rc = fuz_arena_commit(ctx, L);
+        if (rc) return rc;
+        scratch = fuz_at<uint8_t>(ctx, o);
+    }
     QidScratch Q;
-    Q.slots = fuz_at<int32_t>(ctx, o_slots); Q.mask = cap - 1; Q.rep = fuz_at<int32_t>(ctx, o_rep);
-    Q.first = fuz_at<int32_t>(ctx, o_first); Q.rank = fuz_at<int32_t>(ctx, o_rank);
+    Q.slots = reinterpret_cast<int32_t *>(scratch); Q.mask = cap - 1;
+    Q.rep = reinterpret_cast<int32_t *>(scratch + 4 * (size_t)cap);
+    Q.first = reinterpret_cast<int32_t *>(scratch + 4 * (size_t)cap + sz);
+    Q.rank = reinterpret_cast<int32_t *>(scratch + 4 * (size_t)cap + 2 * sz);
+    int rc;
     FUZ_CUDA(ctx, cudaMemsetAsync(Q.slots, 0xFF, 4 * (size_t)cap, st));
     fuz_launch(ctx, k_qid_insert, FUZ_GRID_BLOCKS, 256, 0, st, d_rec_buf, d_rec_off, (int)n_rec, rec_bytes, d_ctg_rec_off, (int)n_ctg, Q);
     FUZ_LAUNCH_CHECK(ctx, "k_qid_insert");
@@ -148,5 +163,5 @@ extern "C" int fuz_assign_qids(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_assign_qids: bad arguments");
     if (n_rec > 0x3fffffff) return fuz_fail(ctx, FUZ_E_ARG, "fuz_assign_qids: too many records");
     return fuz_assign_qids_impl(ctx, d_rec_buf, d_rec_off, n_rec, rec_bytes, d_ctg_rec_off, n_ctg, d_rec_qid, d_ctg_nq,
-                                d_name_first, nullptr);
+                                d_name_first, nullptr, nullptr);
 }
