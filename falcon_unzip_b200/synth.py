@@ -62,6 +62,11 @@ CONFIGS = {
     "quirks": SynthConfig("quirks", 3, 40_000, 30.0, 6_000, seed=11, frac_softclip=0.05,
                           frac_heavy_clip=0.02, frac_short=0.03, frac_dup_name=0.03,
                           n_base_rate=0.002),
+    # raw-read error rates: CIGARs of ~1000 operations per read, match segments of a few bases
+    "noisy": SynthConfig("noisy", 2, 30_000, 30.0, 6_000, seed=13, error_rate=0.12, n_base_rate=0.001),
+    "noisy_m": SynthConfig("noisy_m", 2, 30_000, 30.0, 6_000, seed=17, error_rate=0.15, cigar_style="M"),
+    # ultra-long, accurate reads: match segments of several kb, reads of ~100 kb
+    "long": SynthConfig("long", 1, 400_000, 20.0, 100_000, seed=19, error_rate=0.002, cigar_style="M", min_read_len=20_000),
 }
 
 

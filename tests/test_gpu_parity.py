@@ -32,7 +32,7 @@ def _assert_same_files(a, b):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_pileup_counts_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
     from oracle import c_oracle
@@ -54,7 +54,7 @@ def test_pileup_counts_match_oracle(eng, cfg, impl):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_het_call_arrays_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
     from oracle import c_oracle
@@ -89,7 +89,7 @@ def test_het_call_arrays_match_oracle(eng, cfg, impl):
 
 
 @pytest.mark.parametrize("host_path", [True, False])
-@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m", "long"])
 def test_fused_batch_files_match_oracle(eng, cfg, host_path, tmp_path):
     from falcon_unzip_b200 import phasing
     sset = synth_set(cfg)

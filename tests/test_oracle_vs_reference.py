@@ -57,7 +57,7 @@ def test_window_edge(gap, tmp_path):
     assert n_rows == (1 if gap == 65536 else 0)
 
 
-@pytest.mark.parametrize("cfg", ["tiny", "quirks"])
+@pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_synthetic_sets(cfg, tmp_path):
     sset = synth_set(cfg)
     for c, (name, _l) in enumerate(sset.refs):
