@@ -1,4 +1,5 @@
 // Context, scratch arena, status block, scan primitive.
+#include <stdlib.h>
 #include <string.h>
 
 #include "fuz_internal.cuh"
@@ -41,6 +42,7 @@ extern "C" int fuz_ctx_create(int device, fuz_ctx **out) {
                         device, prop.major, prop.minor);
     fuz_ctx *ctx = new fuz_ctx();
     ctx->device = device;
+    if (const char *v = getenv("FUZ_PDL")) ctx->pdl = atoi(v) != 0;      // experiments: FUZ_PDL=0 -> plain launches
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return fuz_fail(nullptr, FUZ_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));

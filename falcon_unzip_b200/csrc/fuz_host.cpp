@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -110,9 +112,8 @@ extern "C" int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int6
 }
 
 // LA4Falcon -m lines: "q t -len idt qstrand qs qe ql tstrand ts te tl tag" (rr_hctg_track.py:38-44)
-extern "C" int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t,
-                                            int32_t *len, int32_t *tlen) {
-    if (!text || n_bytes < 0 || !q || !t || !len || !tlen) return -1;
+static int64_t parse_la4falcon_range(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t, int32_t *len,
+                                     int32_t *tlen) {
     int64_t n = 0, i = 0;
     while (i < n_bytes && n < cap) {
         // one line
@@ -148,4 +149,56 @@ extern "C" int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, i
         n++;
     }
     return n;
+}
+
+// Large inputs are cut at line ends into one piece per host thread; every piece is parsed
+// into its own vectors, which are then copied to their place in the output (line order kept).
+extern "C" int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t,
+                                            int32_t *len, int32_t *tlen) {
+    if (!text || n_bytes < 0 || !q || !t || !len || !tlen) return -1;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 32), n_bytes / (1 << 20));
+    if (n_thr <= 1) return parse_la4falcon_range(text, n_bytes, cap, q, t, len, tlen);
+    std::vector<int64_t> cut(n_thr + 1, n_bytes);
+    cut[0] = 0;
+    for (int k = 1; k < n_thr; k++) {
+        int64_t p = std::max(cut[k - 1], n_bytes / n_thr * k);
+        const void *nl = p < n_bytes ? memchr(text + p, '\n', (size_t)(n_bytes - p)) : nullptr;
+        cut[k] = nl ? (const char *)nl - text + 1 : n_bytes;
+    }
+    struct Piece { std::vector<int32_t> q, t, len, tlen; int64_t n = 0; };
+    std::vector<Piece> pieces(n_thr);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_thr; k++)
+        pool.emplace_back([&, k] {
+            Piece &pc = pieces[k];
+            const int64_t bytes = cut[k + 1] - cut[k];
+            int64_t lines = 1;
+            for (const char *s = text + cut[k], *e = s + bytes; s < e;) {
+                const void *nl = memchr(s, '\n', (size_t)(e - s));
+                if (!nl) break;
+                lines++;
+                s = (const char *)nl + 1;
+            }
+            pc.q.resize(lines); pc.t.resize(lines); pc.len.resize(lines); pc.tlen.resize(lines);
+            pc.n = parse_la4falcon_range(text + cut[k], bytes, lines, pc.q.data(), pc.t.data(), pc.len.data(), pc.tlen.data());
+        });
+    for (auto &th : pool) th.join();
+    int64_t total = 0;
+    for (auto &pc : pieces) {
+        if (pc.n < 0) return -1;
+        total += pc.n;
+    }
+    std::vector<int64_t> at(n_thr + 1, 0);
+    for (int k = 0; k < n_thr; k++) at[k + 1] = at[k] + pieces[k].n;
+    pool.clear();
+    for (int k = 0; k < n_thr; k++)
+        pool.emplace_back([&, k] {
+            const Piece &pc = pieces[k];
+            const int64_t room = std::max<int64_t>(0, std::min(pc.n, cap - at[k]));     // stops at cap like the serial parser
+            memcpy(q + at[k], pc.q.data(), (size_t)room * 4); memcpy(t + at[k], pc.t.data(), (size_t)room * 4);
+            memcpy(len + at[k], pc.len.data(), (size_t)room * 4); memcpy(tlen + at[k], pc.tlen.data(), (size_t)room * 4);
+        });
+    for (auto &th : pool) th.join();
+    return std::min(total, cap);
 }

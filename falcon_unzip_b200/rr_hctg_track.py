@@ -57,21 +57,21 @@ def get_rid_to_ctg(fn: str) -> Dict[str, OrderedStrSet]:
     return rid_to_ctg
 
 
-def read_las_lines(db_fn: str, fn: str) -> Iterable[str]:
-    """Lines of ``LA4Falcon -m <db> <las>`` (reference run_tr_stage1, :25-29).  Tests replace
-    this function; nothing else of the module touches LA4Falcon."""
-    p = subprocess.Popen(shlex.split("LA4Falcon -m %s %s" % (db_fn, fn)), stdout=subprocess.PIPE, universal_newlines=True)
-    try:
-        for line in p.stdout:
-            yield line
-    finally:
-        p.stdout.close()
-        if p.wait() != 0:
-            raise RuntimeError("LA4Falcon failed on %s" % fn)
+def read_las_lines(db_fn: str, fn: str):
+    """Output of ``LA4Falcon -m <db> <las>`` (reference run_tr_stage1, :25-29) as one bytes object
+    (the C++ parser splits it over the host threads; an iterable of text lines works too).  Tests
+    replace this function; nothing else of the module touches LA4Falcon."""
+    p = subprocess.run(shlex.split("LA4Falcon -m %s %s" % (db_fn, fn)), stdout=subprocess.PIPE)
+    if p.returncode != 0:
+        raise RuntimeError("LA4Falcon failed on %s" % fn)
+    return p.stdout
 
 
-def _parse_lines(lines: Iterable[str]):
-    blob = "".join(l if l.endswith("\n") else l + "\n" for l in lines).encode("ascii")
+def _parse_lines(lines):
+    if isinstance(lines, (bytes, bytearray, memoryview)):
+        blob = bytes(lines)
+    else:
+        blob = "".join(l if l.endswith("\n") else l + "\n" for l in lines).encode("ascii")
     cap = blob.count(b"\n") + 1
     q, t, ln, tl = (np.empty(cap, np.int32) for _ in range(4))
     n = lib().fuz_host_parse_la4falcon(blob, len(blob), cap, q.ctypes.data, t.ctypes.data, ln.ctypes.data, tl.ctypes.data)

@@ -37,8 +37,9 @@ def main():
     rid_to_phase = rr_oracle.phase_table(rr.phased_reads, rr.rawread_ids)
     tab = rrm._Tables(rid_to_ctg, rid_to_phase, len(rid_to_phase))
     files = sorted(rr.las_lines)
+    blobs = ["".join(l + "\n" for l in rr.las_lines[f]).encode("ascii") for f in files]   # what LA4Falcon -m prints
     t0 = time.perf_counter()
-    parts = [rrm._parse_lines(rr.las_lines[f]) for f in files]
+    parts = [rrm._parse_lines(b) for b in blobs]
     parse_s = time.perf_counter() - t0
     q, t, ln, tl = (np.concatenate([p[k] for p in parts]) for k in range(4))
     fidx = np.concatenate([np.full(len(p[0]), i, np.int32) for i, p in enumerate(parts)])
