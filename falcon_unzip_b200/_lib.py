@@ -111,6 +111,11 @@ SYMBOLS = [
                                        C.POINTER(Status), _i64p, _i64p]),
     ("fuz_assign_qids", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    ("fuz_host_bgzf_index", C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fuz_bgzf_inflate", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_int64]),
+    ("fuz_bam_index_records", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                        _i64p, _i64p]),
     ("fuz_rr_track", C.c_int, [C.c_void_p, C.POINTER(RRInput), C.POINTER(RROutputs)]),
     ("fuz_host_parse_la4falcon", C.c_int64, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),

@@ -255,6 +255,44 @@ def bgzf_inflate(path: str, threads: int = 0) -> memoryview:
     return view
 
 
+def parse_bam_header(data) -> Tuple[str, List[Tuple[str, int]], int]:
+    """-> (header text, refs [(name, length)], offset of the first alignment record) from the
+    start of an inflated BAM stream; raises IndexError/struct.error when `data` is too short."""
+    if bytes(data[:4]) != b"BAM\1":
+        raise ValueError("missing BAM magic")
+    (l_text,) = struct.unpack_from("<i", data, 4)
+    if 8 + l_text + 4 > len(data):
+        raise IndexError("header text incomplete")
+    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("ascii", "replace")
+    o = 8 + l_text
+    (n_ref,) = struct.unpack_from("<i", data, o)
+    o += 4
+    refs = []
+    for _ in range(n_ref):
+        (l_name,) = struct.unpack_from("<i", data, o)
+        if o + 8 + l_name > len(data):
+            raise IndexError("reference list incomplete")
+        name = bytes(data[o + 4:o + 4 + l_name - 1]).decode("ascii")
+        (l_ref,) = struct.unpack_from("<i", data, o + 4 + l_name)
+        refs.append((name, l_ref))
+        o += 8 + l_name
+    return text, refs, o
+
+
+def read_bam_header(raw, coff, csize) -> Tuple[str, List[Tuple[str, int]], int]:
+    """Header of a BAM file image: inflates only as many leading BGZF blocks as the header
+    spans (coff / csize: the block table of fuz_host_bgzf_index)."""
+    data = b""
+    for i in range(len(coff)):
+        c0 = int(coff[i])
+        data += zlib.decompress(bytes(raw[c0:c0 + int(csize[i])]), -15)
+        try:
+            return parse_bam_header(data)
+        except (IndexError, struct.error):
+            continue
+    raise ValueError("BAM header is incomplete")
+
+
 def read_bam(path: str):
     """-> (header_text, refs [(name, length)], records buffer (memoryview, no copy))."""
     data = bgzf_inflate(path)

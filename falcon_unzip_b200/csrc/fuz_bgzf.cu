@@ -1,0 +1,430 @@
+// BAM ingest on the device: BGZF block inflate (RFC 1951), CRC32 check, record index and the
+// record range of every contig.  Replaces the `samtools view <bam> <ctg>` pipe of reference
+// falcon_unzip/phasing.py:27: the compressed file image crosses PCIe,
+// everything after that stays in HBM.
+//
+//   k_bgzf_inflate   one warp per BGZF block (<= 64 KiB of payload).  All 32 lanes run the decode
+//                    loop of fuz_inflate_core.h redundantly on identical bit buffers (uniform
+//                    control flow, nothing to broadcast).  The compressed words reach the lanes as
+//                    a 32-word register ring (one coalesced load per 128 B, fetched one ring ahead,
+//                    handed out by shuffle); literals are staged one byte per lane and leave as
+//                    32-byte sector stores; a match is copied by all lanes at once, sources taken
+//                    modulo the distance so that overlapping matches need no ordering.  Then the
+//                    warp re-reads its payload and checks the CRC32 of the BGZF trailer (32 partial
+//                    CRCs combined with the GF(2) operators x^(8 * length)).
+//   k_bam_anchor / k_bam_resolve / k_bam_fill
+//                    the block_size chain of the record stream is sequential; it is cut into
+//                    64 KiB regions: every region finds its first offset that looks like a record
+//                    header (strong test) and walks the chain from there; one thread then threads
+//                    the regions together starting from offset 0 (a region whose guess is not the
+//                    point where the true chain enters it is re-walked), and the regions write
+//                    their slice of rec_off.
+//   k_bam_ctg_ranges record range of every reference id (records are sorted by refID).
+#include <string.h>
+
+#include "fuz_inflate_core.h"
+#include "fuz_internal.cuh"
+
+namespace {
+
+#define FUZ_INF_WARPS 4            // warps (= BGZF blocks) per CTA
+#define FUZ_BAM_REGION (1 << 16)   // bytes of record stream per chain region
+
+struct CrcTables {
+    uint32_t byte_tab[256];        // reflected CRC-32 (poly 0xEDB88320), one byte per step
+    uint32_t x2n[32];              // x^(2^k) mod P
+};
+
+struct DevIO {
+    const uint32_t *words; int64_t n_words;
+    int64_t cbase, widx;
+    uint32_t cur, nxt;
+    uint8_t *out;
+    int64_t o0, opos, olimit, pstart;
+    uint32_t pend;
+    int ln;
+
+    __device__ __forceinline__ uint32_t ldw(int64_t i) const { return i < n_words ? __ldg(words + i) : 0u; }
+    __device__ __forceinline__ int seek(int64_t b) {
+        cbase = widx = b >> 2;
+        cur = ldw(cbase + ln);
+        nxt = ldw(cbase + 32 + ln);
+        return (int)(b & 3);
+    }
+    __device__ __forceinline__ uint32_t next_word() {
+        const int i = (int)(widx - cbase);
+        const uint32_t w = __shfl_sync(0xffffffffu, cur, i);
+        widx++;
+        if (i == 31) { cur = nxt; cbase += 32; nxt = ldw(cbase + 32 + ln); }
+        return w;
+    }
+    __device__ __forceinline__ int64_t word_pos() const { return widx; }
+    // staged literals [pstart, opos) lie inside one aligned 32-byte window; lane = position & 31
+    __device__ __forceinline__ void flush() {
+        const int64_t p = (pstart & ~31LL) + ln;
+        if (p >= pstart && p < opos) out[p] = (uint8_t)pend;
+        pstart = opos;
+    }
+    __device__ __forceinline__ bool put(uint8_t b) {
+        if (opos >= olimit) return false;
+        if (((int)opos & 31) == ln) pend = b;
+        opos++;
+        if (((int)opos & 31) == 0) flush();
+        return true;
+    }
+    __device__ __forceinline__ bool copy(int len, int dist) {
+        if ((int64_t)dist > opos - o0 || opos + len > olimit) return false;
+        flush();
+        __syncwarp();
+        const uint8_t *src = out + opos - dist;
+        uint8_t *dst = out + opos;
+        if (dist >= len) {
+            for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + i);
+        } else {                                   // overlapping: the pattern repeats with period dist
+            for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + (i % dist));
+        }
+        opos += len;
+        pstart = opos;
+        return true;
+    }
+    __device__ __forceinline__ bool copy_in(int64_t src_byte, int len) {
+        if (opos + len > olimit) return false;
+        flush();
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(words) + src_byte;
+        for (int i = ln; i < len; i += 32) out[opos + i] = __ldg(src + i);
+        opos += len;
+        pstart = opos;
+        return true;
+    }
+    __device__ __forceinline__ int lane() const { return ln; }
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+// a(x) * b(x) mod P, reflected representation (zlib crc32.c multmodp)
+__host__ __device__ inline uint32_t crc_mul(uint32_t a, uint32_t b) {
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
+    const uint8_t *__restrict__ comp, int64_t comp_bytes, const int64_t *__restrict__ coff, const int32_t *__restrict__ csize,
+    const int64_t *__restrict__ uoff, const uint32_t *__restrict__ crc, int64_t n_blk, uint8_t *out, int64_t out_bytes,
+    const __grid_constant__ CrcTables ctab, fuz_status *st) {
+    fuz_pdl_enter();
+    __shared__ FuzInfTables tabs[FUZ_INF_WARPS];
+    __shared__ uint32_t s_crc[256], s_x2n[32];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = ctab.byte_tab[i];
+    if (threadIdx.x < 32) s_x2n[threadIdx.x] = ctab.x2n[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * FUZ_INF_WARPS + warp;
+    if (b >= n_blk) return;
+    const int64_t c0 = coff[b], u0 = uoff[b], u1 = uoff[b + 1];
+    const int32_t cs = csize[b];
+    if (c0 < 0 || cs < 0 || c0 + cs > comp_bytes || u0 < 0 || u1 < u0 || u1 > out_bytes || u1 - u0 > 65536) {
+        if (lane == 0) fuz_raise(st, FUZ_E_ARG, (int)b);
+        return;
+    }
+    if (u1 == u0) return;                          // empty block (the BGZF EOF marker)
+    DevIO io;
+    io.words = reinterpret_cast<const uint32_t *>(comp);
+    io.n_words = (comp_bytes + 3) >> 2;
+    io.out = out; io.o0 = io.opos = io.pstart = u0; io.olimit = u1; io.pend = 0; io.ln = lane;
+    io.cbase = io.widx = 0; io.cur = io.nxt = 0;
+    FuzInflate<DevIO> inf(io, tabs[warp]);
+    int rc = inf.run(c0, cs);
+    io.flush();
+    if (rc == FUZ_INF_OK && io.opos != u1) rc = FUZ_INF_SIZE;
+    __syncwarp();
+    if (rc == FUZ_INF_OK && crc) {
+        // CRC-32 of the payload: 32 contiguous pieces, then log2(32) combine steps
+        const int n = (int)(u1 - u0);
+        const int piece = (n + 31) >> 5;
+        const int lo = min(lane * piece, n), hi = min(lo + piece, n);
+        uint32_t c = 0xFFFFFFFFu;
+        for (int i = lo; i < hi; i++) c = s_crc[(c ^ __ldcg(out + u0 + i)) & 0xFFu] ^ (c >> 8);
+        c ^= 0xFFFFFFFFu;
+        int len = hi - lo;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t c2 = __shfl_down_sync(0xffffffffu, c, d);
+            const int len2 = __shfl_down_sync(0xffffffffu, len, d);
+            // crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
+            uint32_t op = 1u << 31;
+            for (int k = 3, m = len2; m; m >>= 1, k++)
+                if (m & 1) op = crc_mul(s_x2n[k & 31], op);
+            c = crc_mul(op, c) ^ c2;
+            len += len2;
+        }
+        if (lane == 0 && c != crc[b]) rc = FUZ_INF_CRC;
+        rc = __shfl_sync(0xffffffffu, rc, 0);
+    }
+    if (rc != FUZ_INF_OK && lane == 0) {
+        fuz_raise(st, FUZ_E_FORMAT, (int)b);
+        atomicMax((int *)&st->reserved[3], rc);     // which FUZ_INF_* (diagnostics)
+    }
+}
+
+// ---------------------------------------------------------------- record index
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return fuz_ld_u32_un(p); }
+
+// weak test: enough to follow the chain (what fuz_host_index_records checks)
+__device__ __forceinline__ bool rec_chain_ok(const uint8_t *rec, int64_t o, int64_t n, int64_t *next) {
+    if (o + 4 > n) return false;
+    const int32_t bs = (int32_t)ld_u32(rec + o);
+    if (bs < 32 || o + 4 + (int64_t)bs > n) return false;
+    *next = o + 4 + (int64_t)bs;
+    return true;
+}
+// strong test: the fixed core of an alignment record is consistent (SAM spec 4.2)
+__device__ __forceinline__ bool rec_header_ok(const uint8_t *rec, int64_t o, int64_t n, int n_ref) {
+    if (o + 36 > n) return false;
+    const int32_t bs = (int32_t)ld_u32(rec + o);
+    if (bs < 32 || o + 4 + (int64_t)bs > n) return false;
+    const int32_t ref = (int32_t)ld_u32(rec + o + 4), pos = (int32_t)ld_u32(rec + o + 8);
+    if (ref < -1 || ref >= n_ref || pos < -1) return false;
+    const uint32_t w12 = ld_u32(rec + o + 12), w16 = ld_u32(rec + o + 16);
+    const int l_name = w12 & 0xFF, n_cig = w16 & 0xFFFF;
+    const int32_t l_seq = (int32_t)ld_u32(rec + o + 20);
+    const int32_t nref = (int32_t)ld_u32(rec + o + 24), npos = (int32_t)ld_u32(rec + o + 28);
+    if (l_name < 1 || l_seq < 0 || nref < -1 || nref >= n_ref || npos < -1) return false;
+    if (32 + (int64_t)l_name + 4 * (int64_t)n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > (int64_t)bs) return false;
+    if (rec[o + 36 + l_name - 1] != 0) return false;                // read_name is NUL terminated
+    if (l_name > 1 && (rec[o + 36] < 33 || rec[o + 36] > 126)) return false;
+    return true;
+}
+
+struct BamIndexScratch {
+    int64_t *first, *land, *entry;   // per region: first header-like offset, where its chain leaves the region
+    int32_t *cnt, *base;             // records starting in the region (guess), index of the region's first record
+    int64_t *n_rec;                  // [0] record count, [1] needed capacity
+};
+
+__global__ void __launch_bounds__(256) k_bam_anchor(const uint8_t *__restrict__ rec, int64_t n, int n_ref, int64_t n_reg,
+                                                    BamIndexScratch S, const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_reg) return;
+    const int64_t a = k * FUZ_BAM_REGION, e = min(a + FUZ_BAM_REGION, n);
+    int64_t c = -1;
+    if (k == 0) c = 0;
+    for (int64_t base = a; c < 0 && base < e; base += 32) {
+        const int64_t o = base + lane;
+        int64_t nx;
+        bool ok = o < e && rec_header_ok(rec, o, n, n_ref);
+        if (ok) ok = rec_chain_ok(rec, o, n, &nx) && (nx == n || rec_header_ok(rec, nx, n, n_ref));
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) c = base + __ffs(m) - 1;
+    }
+    if (lane) return;
+    int64_t o = c, cnt = 0;
+    if (c >= 0) {
+        while (o < e) {
+            int64_t nx;
+            if (!rec_chain_ok(rec, o, n, &nx)) { o = -2; break; }
+            cnt++;
+            o = nx;
+        }
+    }
+    S.first[k] = c; S.land[k] = o; S.cnt[k] = (int32_t)cnt;
+}
+
+__global__ void __launch_bounds__(1024) k_bam_resolve(const uint8_t *__restrict__ rec, int64_t n, int64_t n_reg, int64_t cap_rec,
+                                                      BamIndexScratch S, fuz_status *st) {
+    fuz_pdl_enter();
+    __shared__ int64_t s_first[1024], s_land[1024];
+    __shared__ int32_t s_cnt[1024];
+    __shared__ int64_t s_E, s_N;
+    __shared__ int s_bad;
+    if (st->error) return;                         // e.g. a corrupt BGZF block: nothing to index
+    if (threadIdx.x == 0) { s_E = 0; s_N = 0; s_bad = 0; }
+    for (int64_t k0 = 0; k0 < n_reg; k0 += 1024) {
+        const int64_t k = k0 + threadIdx.x;
+        __syncthreads();
+        if (k < n_reg) { s_first[threadIdx.x] = S.first[k]; s_land[threadIdx.x] = S.land[k]; s_cnt[threadIdx.x] = S.cnt[k]; }
+        __syncthreads();
+        if (threadIdx.x == 0 && !s_bad) {
+            int64_t E = s_E, N = s_N;
+            const int m = (int)min((int64_t)1024, n_reg - k0);
+            for (int i = 0; i < m; i++) {
+                const int64_t end = min((k0 + i + 1) * FUZ_BAM_REGION, n);
+                if (E >= end) { S.entry[k0 + i] = -1; S.base[k0 + i] = (int32_t)N; continue; }
+                S.entry[k0 + i] = E; S.base[k0 + i] = (int32_t)N;
+                if (s_first[i] == E && s_land[i] >= 0) { N += s_cnt[i]; E = s_land[i]; continue; }
+                while (E < end) {                      // the region guessed wrong (or its chain broke): walk it here
+                    int64_t nx;
+                    if (!rec_chain_ok(rec, E, n, &nx)) { s_bad = 1; break; }
+                    N++;
+                    E = nx;
+                }
+                if (s_bad) break;
+            }
+            s_E = E; s_N = N;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_bad || s_E != n) { fuz_raise(st, FUZ_E_BADRECORD, (int)min(s_N, (int64_t)0x7fffffff)); S.n_rec[0] = 0; S.n_rec[1] = 0; }
+        else {
+            S.n_rec[1] = s_N;
+            if (s_N > cap_rec || s_N > 0x7fffffff) { fuz_raise(st, FUZ_E_CAPACITY, 7); S.n_rec[0] = 0; }
+            else S.n_rec[0] = s_N;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bam_fill(const uint8_t *__restrict__ rec, int64_t n, int64_t n_reg, BamIndexScratch S,
+                                                  int64_t *__restrict__ rec_off, const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) rec_off[S.n_rec[0]] = n;
+    if (k >= n_reg) return;
+    int64_t o = S.entry[k], i = S.base[k];
+    const int64_t end = min((k + 1) * FUZ_BAM_REGION, n);
+    while (o >= 0 && o < end) {
+        rec_off[i++] = o;
+        o += 4 + (int64_t)(int32_t)ld_u32(rec + o);
+    }
+}
+
+// ctg_rec_off[c] = first record with refID >= c (unmapped records, refID -1, sort last and count as n_ref)
+__global__ void __launch_bounds__(256) k_bam_ctg_ranges(const uint8_t *__restrict__ rec, const int64_t *__restrict__ rec_off,
+                                                        const int64_t *__restrict__ n_rec_p, int n_ref, int32_t *__restrict__ ctg_rec_off,
+                                                        fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t n_rec = *n_rec_p;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_rec == 0) {
+        for (int64_t c = t0; c <= n_ref; c += (int64_t)gridDim.x * blockDim.x) ctg_rec_off[c] = 0;
+        return;
+    }
+    for (int64_t r = t0; r < n_rec; r += (int64_t)gridDim.x * blockDim.x) {
+        int ref = (int32_t)ld_u32(rec + rec_off[r] + 4);
+        if (ref < -1 || ref >= n_ref) { fuz_raise(st, FUZ_E_BADRECORD, (int)r); continue; }
+        if (ref < 0) ref = n_ref;
+        int prev = -1;
+        if (r > 0) {
+            prev = (int32_t)ld_u32(rec + rec_off[r - 1] + 4);
+            if (prev < 0 || prev > n_ref) prev = n_ref;
+            if (prev > ref) { fuz_raise(st, FUZ_E_UNSORTED, (int)r); continue; }
+        }
+        for (int c = prev + 1; c <= ref; c++) ctg_rec_off[c] = (int32_t)r;
+        if (r == n_rec - 1)
+            for (int c = ref + 1; c <= n_ref; c++) ctg_rec_off[c] = (int32_t)n_rec;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side
+extern "C" int64_t fuz_host_bgzf_index(const uint8_t *h_file, int64_t n_bytes, int64_t cap, int64_t *h_coff, int32_t *h_csize,
+                                       int64_t *h_uoff, uint32_t *h_crc) {
+    if (!h_file || n_bytes < 0) return -1;
+    int64_t o = 0, n = 0, u = 0;
+    while (o < n_bytes) {
+        if (o + 18 > n_bytes || h_file[o] != 0x1f || h_file[o + 1] != 0x8b || h_file[o + 2] != 8 || !(h_file[o + 3] & 4)) return -1;
+        const int xlen = h_file[o + 10] | (h_file[o + 11] << 8);
+        int64_t x = o + 12;
+        const int64_t xend = x + xlen;
+        if (xend > n_bytes) return -1;
+        int64_t bsize = -1;
+        while (x + 4 <= xend) {
+            const int slen = h_file[x + 2] | (h_file[x + 3] << 8);
+            if (h_file[x] == 66 && h_file[x + 1] == 67 && slen == 2 && x + 6 <= xend) bsize = (h_file[x + 4] | (h_file[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 0 || o + bsize > n_bytes || xend + 8 > o + bsize) return -1;
+        uint32_t crc, isize;
+        memcpy(&crc, h_file + o + bsize - 8, 4);
+        memcpy(&isize, h_file + o + bsize - 4, 4);
+        if (isize > 65536) return -1;
+        if (h_coff) {
+            if (n >= cap) return -1;
+            h_coff[n] = xend; h_csize[n] = (int32_t)(o + bsize - 8 - xend); h_uoff[n] = u;
+            if (h_crc) h_crc[n] = crc;
+        }
+        u += isize;
+        n++;
+        o += bsize;
+    }
+    if (h_uoff && n <= cap) h_uoff[n] = u;
+    return n;
+}
+
+static CrcTables make_crc_tables() {
+    CrcTables t;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+        t.byte_tab[i] = c;
+    }
+    uint32_t p = 1u << 30;                         // x^1
+    t.x2n[0] = p;
+    for (int k = 1; k < 32; k++) t.x2n[k] = p = crc_mul(p, p);
+    return t;
+}
+
+extern "C" int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t comp_bytes, const int64_t *d_coff,
+                                const int32_t *d_csize, const int64_t *d_uoff, const uint32_t *d_crc, int64_t n_blk,
+                                uint8_t *d_out, int64_t out_bytes) {
+    if (!ctx || !d_comp || !d_coff || !d_csize || !d_uoff || !d_out || n_blk < 0 || comp_bytes < 0 || out_bytes < 0)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_bgzf_inflate: bad argument");
+    if (reinterpret_cast<uintptr_t>(d_comp) & 3) return fuz_fail(ctx, FUZ_E_ARG, "fuz_bgzf_inflate: d_comp must be 4-byte aligned");
+    static const CrcTables tabs = make_crc_tables();
+    FUZ_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(fuz_status), ctx->stream));
+    ctx->ingest_pending = true;                    // fuz_bam_index_records reports an error raised here
+    if (n_blk == 0) return FUZ_OK;
+    const unsigned grid = (unsigned)((n_blk + FUZ_INF_WARPS - 1) / FUZ_INF_WARPS);
+    fuz_launch(ctx, k_bgzf_inflate, grid, FUZ_INF_WARPS * 32, 0, ctx->stream, d_comp, comp_bytes, d_coff, d_csize, d_uoff, d_crc, n_blk,
+               d_out, out_bytes, tabs, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bgzf_inflate");
+    return FUZ_OK;
+}
+
+extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                                     int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec) {
+    if (!ctx || !d_rec || rec_bytes < 0 || n_ref < 0 || cap_rec < 0 || !d_rec_off || !d_ctg_rec_off || !h_n_rec)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_records: bad argument");
+    cudaStream_t st = ctx->stream;
+    const int64_t n_reg = (rec_bytes + FUZ_BAM_REGION - 1) / FUZ_BAM_REGION;
+    FuzLayout L;
+    const size_t o_first = L.add(8 * (size_t)(n_reg + 1)), o_land = L.add(8 * (size_t)(n_reg + 1)), o_entry = L.add(8 * (size_t)(n_reg + 1));
+    const size_t o_cnt = L.add(4 * (size_t)(n_reg + 1)), o_base = L.add(4 * (size_t)(n_reg + 1)), o_n = L.add(16);
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    BamIndexScratch S;
+    S.first = fuz_at<int64_t>(ctx, o_first); S.land = fuz_at<int64_t>(ctx, o_land); S.entry = fuz_at<int64_t>(ctx, o_entry);
+    S.cnt = fuz_at<int32_t>(ctx, o_cnt); S.base = fuz_at<int32_t>(ctx, o_base); S.n_rec = fuz_at<int64_t>(ctx, o_n);
+    if (!ctx->ingest_pending) FUZ_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(fuz_status), st));
+    ctx->ingest_pending = false;
+    FUZ_CUDA(ctx, cudaMemsetAsync(S.n_rec, 0, 16, st));
+    if (n_reg > 0) {
+        fuz_launch(ctx, k_bam_anchor, (unsigned)((n_reg * 32 + 255) / 256), 256, 0, st, d_rec, rec_bytes, (int)n_ref, n_reg, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_bam_anchor");
+    }
+    fuz_launch(ctx, k_bam_resolve, 1, 1024, 0, st, d_rec, rec_bytes, n_reg, cap_rec, S, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bam_resolve");
+    fuz_launch(ctx, k_bam_fill, (unsigned)((n_reg + 256) / 256), 256, 0, st, d_rec, rec_bytes, n_reg, S, d_rec_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bam_fill");
+    fuz_launch(ctx, k_bam_ctg_ranges, FUZ_GRID_BLOCKS, 256, 0, st, d_rec, d_rec_off, S.n_rec, (int)n_ref, d_ctg_rec_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bam_ctg_ranges");
+    int64_t h[2] = {0, 0};
+    FUZ_CUDA(ctx, cudaMemcpyAsync(h, S.n_rec, 16, cudaMemcpyDeviceToHost, st));
+    fuz_status hs;
+    rc = fuz_get_status(ctx, &hs);                 // synchronises
+    *h_n_rec = h[0];
+    if (h_need_rec) *h_need_rec = h[1];
+    return rc;
+}

@@ -46,6 +46,7 @@ struct fuz_ctx {
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int64_t max_pairs_per_site = 96;
+    bool ingest_pending = false;       // fuz_bgzf_inflate ran; the next fuz_bam_index_records keeps its status
     bool phase_attr_set = false;
     // per-launch profile (diagnostics): an event after every kernel launch
     bool profile = false;

@@ -244,6 +244,46 @@ class DeviceBatch:
         self.c = b
 
 
+@dataclasses.dataclass
+class DeviceBam:
+    """A BAM file decoded on the device (Engine.ingest_bam): the inflated stream, the record
+    index and the record range of every reference, all in HBM."""
+    refs: List                   # [(name, length)] from the BAM header
+    raw: object                  # torch uint8: padding + inflated stream + slack
+    rec_ptr: int                 # device address of the first alignment record (256-byte aligned)
+    rec_bytes: int
+    rec_off: object              # torch int64 [>= n_rec + 1]
+    ctg_rec_off: object          # torch int32 [n_ref + 1]
+    n_rec: int                   # all records; the mapped ones are the first n_mapped
+    n_mapped: int
+    h2d_bytes: int
+    keep: tuple = ()             # tensors that must outlive the asynchronous copies
+
+    def records(self) -> np.ndarray:
+        """Inflated alignment records on the host (tests / diagnostics)."""
+        a = self.raw.cpu().numpy()
+        o = self.rec_ptr - self.raw.data_ptr()
+        return a[o:o + self.rec_bytes]
+
+
+class BamBatchInfo:
+    """What the file writers need from a batch that only exists on the device: contig names
+    and the QNAME of every q_id (gathered on the device, a few bytes per read)."""
+
+    def __init__(self, ctg_names, ctg_lens, ctg_nq, names):
+        self.ctg_names, self.ctg_len = list(ctg_names), np.asarray(ctg_lens, np.int32)
+        self.ctg_nq = np.asarray(ctg_nq, np.int32)
+        self._names = names
+        self._q_off = np.concatenate([[0], np.cumsum(self.ctg_nq)]).astype(np.int64)
+
+    @property
+    def n_ctg(self) -> int:
+        return len(self.ctg_names)
+
+    def qnames(self, c: int) -> List[str]:
+        return self._names[int(self._q_off[c]):int(self._q_off[c + 1])]
+
+
 class Engine:
     """One libfuz context = one GPU = one stream (not thread safe; include/fuz.h)."""
 
@@ -384,6 +424,98 @@ class Engine:
             arrays["goff"] = pb.goff()
         return PhaseResult(arrays, int(st.n_sites), int(st.n_vmap), int(st.n_atable), int(st.n_reads),
                            int(st.n_accepted), int(st.aligned_bases))
+
+    # ---- BAM ingest on the device (BGZF inflate + record index)
+    def ingest_bam(self, image, verify_crc: bool = True) -> DeviceBam:
+        """image: the bytes of a coordinate-sorted BAM file (numpy uint8, ideally pinned).  The
+        compressed image crosses PCIe; inflate, record index and grouping by reference run on
+        the device.  Only the header blocks are inflated on the host (names and lengths)."""
+        torch = self._torch
+        from . import bam
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        n_blk = int(lib().fuz_host_bgzf_index(_np_ptr(image), len(image), 0, None, None, None, None))
+        if n_blk < 0:
+            raise FuzError(_lib.FUZ_E_FORMAT, "not a BGZF file")
+        coff, csize = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32)
+        uoff, crc = np.empty(n_blk + 1, np.int64), np.empty(n_blk, np.uint32)
+        lib().fuz_host_bgzf_index(_np_ptr(image), len(image), n_blk, _np_ptr(coff), _np_ptr(csize), _np_ptr(uoff), _np_ptr(crc))
+        _text, refs, hdr_bytes = bam.read_bam_header(image, coff, csize)
+        total = int(uoff[-1])
+        pad = (-hdr_bytes) % 256
+        dev = self.device
+        d_comp = torch.empty((len(image) + 3) // 4 * 4 + 16, dtype=torch.uint8, device=dev)
+        d_comp[:len(image)].copy_(torch.from_numpy(image), non_blocking=True)
+        d_coff, d_csize = torch.from_numpy(coff).to(dev, non_blocking=True), torch.from_numpy(csize).to(dev, non_blocking=True)
+        d_uoff = torch.from_numpy(uoff).to(dev, non_blocking=True)
+        d_crc = torch.from_numpy(crc.view(np.int32)).to(dev, non_blocking=True) if verify_crc else None
+        raw = torch.empty(pad + total + 64, dtype=torch.uint8, device=dev)
+        raw[pad + total:].zero_()
+        torch.cuda.synchronize(dev)                      # torch's stream -> the context's stream
+        _lib.check(self.ctx, lib().fuz_bgzf_inflate(self.ctx, d_comp.data_ptr(), len(image), d_coff.data_ptr(), d_csize.data_ptr(),
+                                                    d_uoff.data_ptr(), d_crc.data_ptr() if verify_crc else None, n_blk,
+                                                    raw.data_ptr() + pad, total))
+        rec_ptr, rec_bytes = raw.data_ptr() + pad + hdr_bytes, total - hdr_bytes
+        ctg_rec_off = torch.zeros(len(refs) + 1, dtype=torch.int32, device=dev)
+        cap = rec_bytes // 2048 + 1024
+        n_rec, need = C.c_int64(0), C.c_int64(0)
+        for _ in range(2):
+            rec_off = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize(dev)
+            rc = lib().fuz_bam_index_records(self.ctx, rec_ptr, rec_bytes, len(refs), cap, rec_off.data_ptr(),
+                                             ctg_rec_off.data_ptr(), C.byref(n_rec), C.byref(need))
+            if rc != _lib.FUZ_E_CAPACITY:
+                break
+            cap = int(need.value)
+        _lib.check(self.ctx, rc)
+        n_mapped = int(ctg_rec_off[-1].item()) if len(refs) else 0
+        h2d = len(image) + coff.nbytes + csize.nbytes + uoff.nbytes + (crc.nbytes if verify_crc else 0)
+        return DeviceBam(refs, raw, rec_ptr, rec_bytes, rec_off, ctg_rec_off, int(n_rec.value), n_mapped, h2d,
+                         keep=(d_comp, d_coff, d_csize, d_uoff, d_crc))
+
+    def phase_bam(self, image, caps: Optional[Dict[str, int]] = None, verify_crc: bool = True):
+        """BAM file image -> (PhaseResult, BamBatchInfo): ingest_bam, then the four stages for every
+        reference of the BAM in one device call (q_ids assigned on the device)."""
+        torch = self._torch
+        db = self.ingest_bam(image, verify_crc)
+        n_ctg = len(db.refs)
+        if n_ctg < 1:
+            raise FuzError(_lib.FUZ_E_ARG, "the BAM header lists no reference sequence")
+        ctg_len = np.asarray([r[1] for r in db.refs], np.int32)
+        t = lib().fuz_tile_size()
+        goff = np.concatenate([[0], np.cumsum(np.maximum((ctg_len.astype(np.int64) + t - 1) // t * t, t))]).astype(np.int64)
+        dev = self.device
+        d_len, d_goff = torch.from_numpy(ctg_len).to(dev), torch.from_numpy(goff).to(dev)
+        qid_nq = torch.zeros(n_ctg, dtype=torch.int32, device=dev)
+        qid_first = torch.zeros(max(db.n_mapped, 1), dtype=torch.int64, device=dev)
+        b = _lib.Batch()
+        b.n_ctg, b.n_rec, b.rec_bytes = n_ctg, db.n_mapped, db.rec_bytes
+        b.d_rec_buf, b.d_rec_off, b.d_rec_qid = db.rec_ptr, db.rec_off.data_ptr(), None
+        b.d_ctg_rec_off, b.d_ctg_len, b.d_ctg_goff = db.ctg_rec_off.data_ptr(), d_len.data_ptr(), d_goff.data_ptr()
+        b.d_ctg_nq, b.total_glen, b.total_nq = qid_nq.data_ptr(), int(goff[-1]), 0
+        caps = caps or default_caps(int(ctg_len.sum()), db.n_mapped)
+
+        def run(do):
+            do.c.d_ctg_nq, do.c.d_name_first = qid_nq.data_ptr(), qid_first.data_ptr()
+            _lib.check(self.ctx, lib().fuz_phase_batch(self.ctx, C.byref(b), C.byref(do.c)))
+        do, st = self._retry(caps, 0, run)
+        arrays = do.fetch(st)
+        res = PhaseResult(arrays, int(st.n_sites), int(st.n_vmap), int(st.n_atable), int(st.n_reads),
+                          int(st.n_accepted), int(st.aligned_bases), db.h2d_bytes, sum(a.nbytes for a in arrays.values()))
+        # QNAME of every q_id: gathered on the device from the first record of each name
+        nq = qid_nq.cpu().numpy()
+        total_nq = int(nq.sum())
+        names: List[str] = []
+        if total_nq:
+            o = db.rec_ptr - db.raw.data_ptr()
+            first_off = db.rec_off[qid_first[:total_nq]] + o
+            l_name = db.raw[first_off + 12].to(torch.int64)
+            width = int(l_name.max().item())
+            idx = first_off[:, None] + 36 + torch.arange(width, device=dev)[None, :]
+            chars = db.raw[idx.clamp_(max=db.raw.numel() - 1)].cpu().numpy()
+            ln = l_name.cpu().numpy()
+            names = [chars[i, :ln[i] - 1].tobytes().decode("ascii") for i in range(total_nq)]
+            res.d2h_bytes += chars.nbytes
+        return res, BamBatchInfo([r[0] for r in db.refs], ctg_len, nq, names)
 
     # ---- host-buffer path (what the reference-facing functions and bench e2e use)
     def phase_host(self, pb: PreparedBatch, caps: Optional[Dict[str, int]] = None,

@@ -342,6 +342,21 @@ def phase_contigs(records, ctg_names: Sequence[str], ref_seqs: Sequence[str], ba
     return res, out
 
 
+def phase_bam(bam_fn: str, fasta_fn: str, base_dir: str, device: int = 0, verify_crc: bool = True):
+    """Every contig of a coordinate-sorted BAM in one go, decoded on the device: the file image is
+    uploaded as it is, BGZF inflate + record split (the `samtools view` pipe of phasing.py:27), the
+    QNAME -> q_id table and the four stages run in HBM; the same six files per contig come out."""
+    image = np.fromfile(bam_fn, dtype=np.uint8)
+    ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fasta_fn)}
+    eng = engine.get_engine(device)
+    res, info = eng.phase_bam(image, verify_crc=verify_crc)
+    sl = formats.contig_slices(res, info.n_ctg)
+    out = {}
+    for c, name in enumerate(info.ctg_names):
+        out[name] = write_contig_files(res, sl, c, name, ref_seqs.get(name, ""), info.qnames(c), base_dir)
+    return res, out
+
+
 def parse_args(argv):
     parser = argparse.ArgumentParser(description="phasing variants and reads from a bam file")
     parser.add_argument("--bam", type=str, help="path to sorted bam file", required=True)

@@ -12,6 +12,9 @@
  *                           chained on the device for a batch of contigs)
  *   fuz_rr_track            falcon_unzip/rr_hctg_track.py:31-65,97-105,113-123
  *                           tr_stage1 + heap merge + contig vote of run_track_reads
+ *   fuz_bgzf_inflate, fuz_bam_index_records
+ *                           falcon_unzip/phasing.py:27        the `samtools view` pipe: BGZF
+ *                           inflate + record split, on the device
  *   fuz_host_*              host-side helpers of the same path (record index, QNAME ->
  *                           q_id of phasing.py:47-54)
  *
@@ -217,6 +220,30 @@ int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_host_output
 int fuz_assign_qids(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec,
                     int64_t rec_bytes, const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid,
                     int32_t *d_ctg_nq, int64_t *d_name_first);
+
+/* ---- BAM ingest on the device (replaces the `samtools view <bam> <ctg>` pipe of
+ *      falcon_unzip/phasing.py:27) ------------------------------- */
+/* Host: walk the BGZF block chain of a BAM file image (SAM spec 4.1).  Per block: offset and
+ * size of the raw deflate stream, offset of its payload in the inflated stream (h_uoff has
+ * cap + 1 slots, h_uoff[n] = inflated size), CRC32 of the payload (h_crc may be NULL).
+ * Returns the number of blocks (call with h_coff = NULL to count), -1 on a malformed file. */
+int64_t fuz_host_bgzf_index(const uint8_t *h_file, int64_t n_bytes, int64_t cap, int64_t *h_coff,
+                            int32_t *h_csize, int64_t *h_uoff, uint32_t *h_crc);
+/* Device: inflate n_blk raw deflate streams (RFC 1951), block i = d_comp[d_coff[i], +d_csize[i])
+ * -> d_out[d_uoff[i], d_uoff[i+1]), one warp per block; when d_crc is not NULL the CRC32 of every
+ * payload is checked.  d_comp must be 4-byte aligned.  Asynchronous; a corrupt block raises
+ * FUZ_E_FORMAT (error_index = block, status.reserved[3] = reason) in the status block. */
+int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t comp_bytes, const int64_t *d_coff,
+                     const int32_t *d_csize, const int64_t *d_uoff, const uint32_t *d_crc, int64_t n_blk,
+                     uint8_t *d_out, int64_t out_bytes);
+/* Device form of fuz_host_index_records plus the grouping by reference id: d_rec = the alignment
+ * records of a coordinate-sorted BAM (everything after the header), followed by >= 32 readable
+ * bytes.  Fills d_rec_off [cap_rec + 1] and d_ctg_rec_off [n_ref + 1] (records of reference c =
+ * [d_ctg_rec_off[c], d_ctg_rec_off[c+1]); unmapped records, refID -1, lie behind d_ctg_rec_off[n_ref]).
+ * Synchronises; *h_n_rec = record count.  FUZ_E_CAPACITY: *h_need_rec says how many slots are needed;
+ * FUZ_E_BADRECORD: broken block_size chain; FUZ_E_UNSORTED: refIDs not ascending. */
+int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                          int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec);
 
 /* ---- raw-read -> haplotig tracking (falcon_unzip/rr_hctg_track.py) --------------- */
 /* fuz_rr_track replaces tr_stage1 (:31-65), the heap merge (:97-105) and the contig vote

@@ -1,0 +1,213 @@
+"""BAM ingest on the device, through the C ABI: k_bgzf_inflate against zlib on every
+block type / table shape / stream alignment, CRC32 check, corrupt streams; the parallel record index
+against the sequential host walk (records longer than a region, tiny records, header-like bytes inside
+aux data at region starts, unmapped tail, broken chains); whole files: inflated stream, index and the
+six output files identical to the host-decoded path and to the oracle."""
+import ctypes as C
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import deflate_cases
+from conftest import synth_set
+
+pytestmark = pytest.mark.gpu
+
+
+def _inflate_blocks(eng, blocks, crcs=None, sizes=None):
+    """blocks: list of (payload or None, raw deflate stream).  Returns (status, list of outputs)."""
+    import torch
+    from falcon_unzip_b200 import _lib
+    L = _lib.lib()
+    comp, coff = bytearray(), []
+    for i, (_p, c) in enumerate(blocks):
+        comp += b"\x99" * (i % 4)                       # every stream alignment
+        coff.append(len(comp))
+        comp += c
+    csize = [len(c) for _p, c in blocks]
+    sizes = sizes or [len(p) for p, _c in blocks]
+    uoff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    dev = eng.device
+    d_comp = torch.zeros(len(comp) + 16, dtype=torch.uint8, device=dev)
+    d_comp[:len(comp)] = torch.frombuffer(bytes(comp) or b"\0", dtype=torch.uint8)[:len(comp)].to(dev)
+    d_coff = torch.tensor(coff, dtype=torch.int64, device=dev)
+    d_cs = torch.tensor(csize, dtype=torch.int32, device=dev)
+    d_uoff = torch.from_numpy(uoff).to(dev)
+    d_crc = None
+    if crcs is not None:
+        d_crc = torch.from_numpy(np.asarray(crcs, np.uint32).view(np.int32)).to(dev)
+    out = torch.full((int(uoff[-1]) + 64,), 0xEE, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    rc = L.fuz_bgzf_inflate(eng.ctx, d_comp.data_ptr(), len(comp), d_coff.data_ptr(), d_cs.data_ptr(), d_uoff.data_ptr(),
+                            d_crc.data_ptr() if d_crc is not None else None, len(blocks), out.data_ptr(), int(uoff[-1]))
+    assert rc == 0
+    st = eng.status(raise_on_error=False)
+    host = out.cpu().numpy()
+    assert np.all(host[int(uoff[-1]):] == 0xEE), "wrote past the inflated size"
+    return st, [host[uoff[i]:uoff[i + 1]].tobytes() for i in range(len(blocks))]
+
+
+def test_inflate_matches_zlib(eng):
+    streams = deflate_cases.streams()
+    blocks = [(d, c) for _n, d, c in streams]
+    crcs = [zlib.crc32(d) & 0xFFFFFFFF for d, _c in blocks]
+    st, outs = _inflate_blocks(eng, blocks, crcs)
+    assert st.error == 0, (st.error, st.error_index, st.reserved[3], streams[st.error_index][0])
+    for (name, d, _c), got in zip(streams, outs):
+        assert got == d, name
+    st, outs = _inflate_blocks(eng, blocks)                 # without the CRC check
+    assert st.error == 0 and all(g == d for g, (d, _c) in zip(outs, blocks))
+
+
+def test_inflate_rejects_corrupt_blocks(eng):
+    from falcon_unzip_b200 import _lib
+    for name, comp, size in deflate_cases.corrupt_streams():
+        try:
+            want = zlib.decompress(comp, -15)
+        except zlib.error:
+            want = None
+        st, outs = _inflate_blocks(eng, [(None, comp)], sizes=[size])
+        if want is not None and len(want) == size:
+            assert st.error == 0 and outs[0] == want, name
+        else:
+            assert st.error == _lib.FUZ_E_FORMAT and st.error_index == 0, name
+    data = b"payload whose CRC does not match" * 100
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = c.compress(data) + c.flush()
+    st, _ = _inflate_blocks(eng, [(data, comp), (data, comp)], [zlib.crc32(data), zlib.crc32(data) ^ 1])
+    assert st.error == _lib.FUZ_E_FORMAT and st.error_index == 1 and st.reserved[3] == 8
+    st, _ = _inflate_blocks(eng, [(data, comp)] * 3, [zlib.crc32(data)] * 3)
+    assert st.error == 0
+
+
+def _index_device(eng, records: bytes, n_ref: int, cap=None):
+    import torch
+    from falcon_unzip_b200 import _lib
+    L = _lib.lib()
+    dev = eng.device
+    n = len(records)
+    d = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    if n:
+        d[:n] = torch.frombuffer(records, dtype=torch.uint8).to(dev)
+    cap = n // 36 + 2 if cap is None else cap
+    off = torch.full((cap + 1,), -7, dtype=torch.int64, device=dev)
+    cro = torch.full((n_ref + 1,), -7, dtype=torch.int32, device=dev)
+    n_rec, need = C.c_int64(-1), C.c_int64(-1)
+    torch.cuda.synchronize(dev)
+    rc = L.fuz_bam_index_records(eng.ctx, d.data_ptr(), n, n_ref, cap, off.data_ptr(), cro.data_ptr(), C.byref(n_rec), C.byref(need))
+    return rc, n_rec.value, need.value, off.cpu().numpy(), cro.cpu().numpy()
+
+
+def _host_index(records: bytes, n_ref: int):
+    from falcon_unzip_b200 import bam, engine
+    off = bam.index_records(records)
+    a = np.frombuffer(records, np.uint8)
+    ref = engine.record_refids(a, off) if len(off) > 1 else np.zeros(0, np.int32)
+    key = np.where(ref < 0, n_ref, ref)
+    return off, np.searchsorted(key, np.arange(n_ref + 1), side="left").astype(np.int32)
+
+
+def _rec(refid, pos, name, l_seq, aux=b"", rng=None):
+    from falcon_unzip_b200 import bam
+    seq = "".join("ACGT"[i] for i in (rng.integers(0, 4, l_seq) if rng is not None else np.zeros(l_seq, int)))
+    return bam.encode_record(refid, pos, name, 0, 254, [(l_seq, "=")] if l_seq else [], seq or "*", aux=aux)
+
+
+def _fake_header(block_size: int) -> bytes:
+    body = struct.pack("<iiBBHHHiiii", 0, 5, 2, 0, 0, 0, 0, 0, -1, -1, 0) + b"x\0"
+    return struct.pack("<i", block_size) + body
+
+
+def test_record_index_matches_host_walk(eng):
+    rng = np.random.default_rng(5)
+    cases = {}
+    cases["empty"] = (b"", 3)
+    cases["one"] = (_rec(0, 0, "r0", 10, rng=rng), 1)
+    cases["tiny_records"] = (b"".join(_rec(i // 2000, i, "t%d" % i, int(rng.integers(0, 3)), rng=rng) for i in range(6000)), 3)
+    cases["long_records"] = (b"".join(_rec(0, 10 * i, "m/%d/0_1" % i, int(rng.integers(90000, 140000)), rng=rng) for i in range(12)), 1)
+    mixed = [_rec(int(i >= 150), i * 7 % 1000 + (i >= 150) * 0, "m/%d/0_%d" % (i, i), int(rng.integers(1, 30000)), rng=rng) for i in range(300)]
+    mixed += [_rec(-1, -1, "unmapped%d" % i, 100, rng=rng) for i in range(5)]
+    cases["mixed_unmapped_tail"] = (b"".join(mixed), 4)
+    # header-like bytes inside aux data, exactly at the start of regions 1 and 2, whose own chain
+    # (two fake records) lands on a true record start: the guess of those regions must be discarded
+    head = b"".join(_rec(0, i, "h%d" % i, 5000, rng=rng) for i in range(5))
+    for target in (65536, 131072):
+        aux_start = len(head) + 36 + 4          # core + name "big\0" (no CIGAR, no SEQ)
+        aux_len = 200000
+        aux = bytearray(rng.integers(0, 256, aux_len, dtype=np.uint8).tobytes())
+        p1 = target - aux_start
+        bs1 = 1000
+        p2 = p1 + 4 + bs1
+        bs2 = aux_len - p2 - 4
+        aux[p1:p1 + len(_fake_header(bs1))] = _fake_header(bs1)
+        aux[p2:p2 + len(_fake_header(bs2))] = _fake_header(bs2)
+        big = _rec(0, 9, "big", 0, aux=b"XYB" + bytes([255]) + bytes(aux[4:]))   # keep offsets: overwrite first 4 aux bytes
+        tail = b"".join(_rec(0, 10 + i, "t%d" % i, 3000, rng=rng) for i in range(40))
+        cases["fake_headers_%d" % target] = (head + big + tail, 2)
+    for name, (records, n_ref) in cases.items():
+        want_off, want_cro = _host_index(records, n_ref)
+        rc, n_rec, need, off, cro = _index_device(eng, records, n_ref)
+        assert rc == 0, (name, rc)
+        assert n_rec == len(want_off) - 1 == need, name
+        assert np.array_equal(off[:n_rec + 1], want_off), name
+        assert np.array_equal(cro, want_cro), name
+    # capacity protocol
+    from falcon_unzip_b200 import _lib
+    records, n_ref = cases["tiny_records"]
+    rc, n_rec, need, _off, _cro = _index_device(eng, records, n_ref, cap=100)
+    assert rc == _lib.FUZ_E_CAPACITY and need == 6000
+    # broken chain / unsorted reference ids
+    records = cases["mixed_unmapped_tail"][0]
+    rc, *_ = _index_device(eng, records[:-3], 4)
+    assert rc == _lib.FUZ_E_BADRECORD
+    bad = bytearray(records); bad[0:4] = struct.pack("<i", 20)
+    rc, *_ = _index_device(eng, bytes(bad), 4)
+    assert rc == _lib.FUZ_E_BADRECORD
+    swapped = _rec(1, 0, "a", 50, rng=rng) + _rec(0, 0, "b", 50, rng=rng)
+    rc, *_ = _index_device(eng, swapped, 2)
+    assert rc == _lib.FUZ_E_UNSORTED
+
+
+@pytest.mark.parametrize("cfg,level", [("quirks", 1), ("quirks", 6), ("long", 1)])
+def test_ingest_bam_file(eng, tmp_path, cfg, level):
+    from falcon_unzip_b200 import bam
+    sset = synth_set(cfg)
+    fn = str(tmp_path / "in.bam")
+    bam.write_bam(fn, sset.refs, sset.records.tobytes(), level=level)
+    db = eng.ingest_bam(np.fromfile(fn, dtype=np.uint8))
+    assert [tuple(r) for r in db.refs] == [tuple(r) for r in sset.refs]
+    assert np.array_equal(db.records(), np.asarray(sset.records))
+    want_off, want_cro = _host_index(sset.records.tobytes(), len(sset.refs))
+    assert db.n_rec == len(want_off) - 1 == db.n_mapped
+    assert np.array_equal(db.rec_off.cpu().numpy()[:db.n_rec + 1], want_off)
+    assert np.array_equal(db.ctg_rec_off.cpu().numpy(), want_cro)
+    # a flipped payload bit is caught by the CRC check
+    img = np.fromfile(fn, dtype=np.uint8)
+    img[len(img) // 2] ^= 0x10
+    from falcon_unzip_b200 import _lib
+    with pytest.raises(_lib.FuzError):
+        eng.ingest_bam(img)
+
+
+@pytest.mark.parametrize("cfg", ["quirks", "tiny"])
+def test_phase_bam_equals_host_decoded_path_and_oracle(eng, tmp_path, cfg):
+    from falcon_unzip_b200 import bam, phasing, synth
+    from oracle import c_oracle
+    sset = synth_set(cfg)
+    fn, fa = str(tmp_path / "in.bam"), str(tmp_path / "ref.fa")
+    bam.write_bam(fn, sset.refs, sset.records.tobytes())
+    synth.write_fasta(fa, sset)
+    res_b, files_b = phasing.phase_bam(fn, fa, str(tmp_path / "dev"))
+    names = [r[0] for r in sset.refs]
+    res_h, files_h = phasing.phase_contigs(sset.records, names, sset.ref_seqs, str(tmp_path / "host"))
+    assert (res_b.n_sites, res_b.n_vmap, res_b.n_atable, res_b.n_reads) == (res_h.n_sites, res_h.n_vmap, res_h.n_atable, res_h.n_reads)
+    assert res_b.aligned_bases == res_h.aligned_bases and res_b.n_sites > 0
+    for c, name in enumerate(names):
+        want = c_oracle.run_phasing_stages(sset.contig_records(c), name, sset.ref_seqs[c], str(tmp_path / "oracle"))
+        for k in want:
+            a = open(want[k]).read()
+            assert open(files_b[name][k]).read() == a, (name, k)
+            assert open(files_h[name][k]).read() == a, (name, k)
