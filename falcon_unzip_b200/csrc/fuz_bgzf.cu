@@ -37,63 +37,66 @@ struct CrcTables {
 
 struct DevIO {
     const uint32_t *words; int64_t n_words;
-    int64_t cbase, widx;
-    uint32_t cur, nxt;
-    uint8_t *out;
-    int64_t o0, opos, olimit, pstart;
+    int64_t cbase;                 // absolute word index of cur[lane 0]
+    uint32_t cur, nxt;             // words cbase + lane, cbase + 32 + lane
+    int wi;                        // next word to hand out = cbase + wi
+    uint8_t *ob;                   // 32-byte aligned address at or below the first payload byte
+    int p0, pos, lim, pstart;      // positions relative to ob: payload start, next byte, payload end, first staged byte
     uint32_t pend;
     int ln;
 
     __device__ __forceinline__ uint32_t ldw(int64_t i) const { return i < n_words ? __ldg(words + i) : 0u; }
     __device__ __forceinline__ int seek(int64_t b) {
-        cbase = widx = b >> 2;
+        cbase = b >> 2;
+        wi = 0;
         cur = ldw(cbase + ln);
         nxt = ldw(cbase + 32 + ln);
         return (int)(b & 3);
     }
     __device__ __forceinline__ uint32_t next_word() {
-        const int i = (int)(widx - cbase);
-        const uint32_t w = __shfl_sync(0xffffffffu, cur, i);
-        widx++;
-        if (i == 31) { cur = nxt; cbase += 32; nxt = ldw(cbase + 32 + ln); }
+        const uint32_t w = __shfl_sync(0xffffffffu, cur, wi);
+        if (++wi == 32) { wi = 0; cur = nxt; cbase += 32; nxt = ldw(cbase + 32 + ln); }
         return w;
     }
-    __device__ __forceinline__ int64_t word_pos() const { return widx; }
-    // staged literals [pstart, opos) lie inside one aligned 32-byte window; lane = position & 31
+    __device__ __forceinline__ int64_t word_pos() const { return cbase + wi; }
+    // staged literals [pstart, pos) lie inside one aligned 32-byte window; lane = position & 31.
+    // Literals past the expected size are never stored; the caller sees pos != lim in the end.
     __device__ __forceinline__ void flush() {
-        const int64_t p = (pstart & ~31LL) + ln;
-        if (p >= pstart && p < opos) out[p] = (uint8_t)pend;
-        pstart = opos;
+        const int p = (pstart & ~31) + ln;
+        if (p >= pstart && p < min(pos, lim)) ob[p] = (uint8_t)pend;
+        pstart = pos;
     }
     __device__ __forceinline__ bool put(uint8_t b) {
-        if (opos >= olimit) return false;
-        if (((int)opos & 31) == ln) pend = b;
-        opos++;
-        if (((int)opos & 31) == 0) flush();
+        if ((pos & 31) == ln) pend = b;
+        pos++;
+        if ((pos & 31) == 0) { flush(); return pos <= lim; }
         return true;
     }
     __device__ __forceinline__ bool copy(int len, int dist) {
-        if ((int64_t)dist > opos - o0 || opos + len > olimit) return false;
+        if (dist > pos - p0 || pos + len > lim) return false;
         flush();
         __syncwarp();
-        const uint8_t *src = out + opos - dist;
-        uint8_t *dst = out + opos;
+        const uint8_t *src = ob + pos - dist;
+        uint8_t *dst = ob + pos;
         if (dist >= len) {
             for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + i);
+        } else if (dist == 1) {                    // a run of one byte (the 0xFF QUAL of PacBio BAMs)
+            const uint8_t v = __ldcg(src);
+            for (int i = ln; i < len; i += 32) dst[i] = v;
         } else {                                   // overlapping: the pattern repeats with period dist
             for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + (i % dist));
         }
-        opos += len;
-        pstart = opos;
+        pos += len;
+        pstart = pos;
         return true;
     }
     __device__ __forceinline__ bool copy_in(int64_t src_byte, int len) {
-        if (opos + len > olimit) return false;
+        if (pos + len > lim) return false;
         flush();
         const uint8_t *src = reinterpret_cast<const uint8_t *>(words) + src_byte;
-        for (int i = ln; i < len; i += 32) out[opos + i] = __ldg(src + i);
-        opos += len;
-        pstart = opos;
+        for (int i = ln; i < len; i += 32) ob[pos + i] = __ldg(src + i);
+        pos += len;
+        pstart = pos;
         return true;
     }
     __device__ __forceinline__ int lane() const { return ln; }
@@ -138,12 +141,14 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
     DevIO io;
     io.words = reinterpret_cast<const uint32_t *>(comp);
     io.n_words = (comp_bytes + 3) >> 2;
-    io.out = out; io.o0 = io.opos = io.pstart = u0; io.olimit = u1; io.pend = 0; io.ln = lane;
-    io.cbase = io.widx = 0; io.cur = io.nxt = 0;
+    const int omis = (int)(reinterpret_cast<uintptr_t>(out + u0) & 31);
+    io.ob = out + u0 - omis;
+    io.p0 = io.pos = io.pstart = omis; io.lim = omis + (int)(u1 - u0); io.pend = 0; io.ln = lane;
+    io.cbase = 0; io.wi = 0; io.cur = io.nxt = 0;
     FuzInflate<DevIO> inf(io, tabs[warp]);
     int rc = inf.run(c0, cs);
     io.flush();
-    if (rc == FUZ_INF_OK && io.opos != u1) rc = FUZ_INF_SIZE;
+    if (rc == FUZ_INF_OK && io.pos != io.lim) rc = FUZ_INF_SIZE;
     __syncwarp();
     if (rc == FUZ_INF_OK && crc) {
         // CRC-32 of the payload: 32 contiguous pieces, then log2(32) combine steps
@@ -239,46 +244,66 @@ __global__ void __launch_bounds__(256) k_bam_anchor(const uint8_t *__restrict__ 
     S.first[k] = c; S.land[k] = o; S.cnt[k] = (int32_t)cnt;
 }
 
-__global__ void __launch_bounds__(1024) k_bam_resolve(const uint8_t *__restrict__ rec, int64_t n, int64_t n_reg, int64_t cap_rec,
-                                                      BamIndexScratch S, fuz_status *st) {
+// One warp threads the regions together, 32 at a time: if every region of a group either is
+// entered exactly where it guessed or holds no record start at all, the group is accepted with
+// two warp scans; otherwise lane 0 walks it region by region.
+__global__ void __launch_bounds__(32) k_bam_resolve(const uint8_t *__restrict__ rec, int64_t n, int64_t n_reg, int64_t cap_rec,
+                                                     BamIndexScratch S, fuz_status *st) {
     fuz_pdl_enter();
-    __shared__ int64_t s_first[1024], s_land[1024];
-    __shared__ int32_t s_cnt[1024];
-    __shared__ int64_t s_E, s_N;
-    __shared__ int s_bad;
     if (st->error) return;                         // e.g. a corrupt BGZF block: nothing to index
-    if (threadIdx.x == 0) { s_E = 0; s_N = 0; s_bad = 0; }
-    for (int64_t k0 = 0; k0 < n_reg; k0 += 1024) {
-        const int64_t k = k0 + threadIdx.x;
-        __syncthreads();
-        if (k < n_reg) { s_first[threadIdx.x] = S.first[k]; s_land[threadIdx.x] = S.land[k]; s_cnt[threadIdx.x] = S.cnt[k]; }
-        __syncthreads();
-        if (threadIdx.x == 0 && !s_bad) {
-            int64_t E = s_E, N = s_N;
-            const int m = (int)min((int64_t)1024, n_reg - k0);
-            for (int i = 0; i < m; i++) {
-                const int64_t end = min((k0 + i + 1) * FUZ_BAM_REGION, n);
-                if (E >= end) { S.entry[k0 + i] = -1; S.base[k0 + i] = (int32_t)N; continue; }
-                S.entry[k0 + i] = E; S.base[k0 + i] = (int32_t)N;
-                if (s_first[i] == E && s_land[i] >= 0) { N += s_cnt[i]; E = s_land[i]; continue; }
-                while (E < end) {                      // the region guessed wrong (or its chain broke): walk it here
+    const int lane = threadIdx.x;
+    int64_t E = 0, N = 0;                          // where the true chain enters the next group; records so far
+    bool bad = false;
+    for (int64_t k0 = 0; k0 < n_reg && !bad; k0 += 32) {
+        const int64_t k = k0 + lane;
+        const bool in = k < n_reg;
+        const int64_t first = in ? S.first[k] : -1, land = in ? S.land[k] : -1;
+        const int cnt = in ? S.cnt[k] : 0;
+        const int64_t end = min((k + 1) * FUZ_BAM_REGION, n);
+        // speculation: every region with a guess is entered at its guess and left at its landing point
+        const bool has = in && first >= 0 && land >= 0;
+        int64_t lmax = has ? land : -1;            // inclusive max-scan of the landing points
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, lmax, d);
+            if (lane >= d) lmax = max(lmax, t);
+        }
+        int64_t e_in = __shfl_up_sync(0xffffffffu, lmax, 1);
+        if (lane == 0) e_in = -1;
+        e_in = max(e_in, E);                       // entry point of this region under the speculation
+        const bool ok = !in || (has ? first == e_in : e_in >= end);
+        if (__all_sync(0xffffffffu, ok)) {
+            const int c = has ? cnt : 0;
+            const int incl = fuz_warp_incl_scan(c, lane);
+            if (in) { S.entry[k] = has ? e_in : -1; S.base[k] = (int32_t)(N + incl - c); }
+            N += __shfl_sync(0xffffffffu, incl, 31);
+            E = max(E, __shfl_sync(0xffffffffu, lmax, 31));
+            continue;
+        }
+        if (lane == 0) {
+            const int m = (int)min((int64_t)32, n_reg - k0);
+            for (int i = 0; i < m && !bad; i++) {
+                const int64_t kk = k0 + i, e2 = min((kk + 1) * FUZ_BAM_REGION, n);
+                if (E >= e2) { S.entry[kk] = -1; S.base[kk] = (int32_t)N; continue; }
+                S.entry[kk] = E; S.base[kk] = (int32_t)N;
+                if (S.first[kk] == E && S.land[kk] >= 0) { N += S.cnt[kk]; E = S.land[kk]; continue; }
+                while (E < e2) {                   // the region guessed wrong (or its chain broke): walk it here
                     int64_t nx;
-                    if (!rec_chain_ok(rec, E, n, &nx)) { s_bad = 1; break; }
+                    if (!rec_chain_ok(rec, E, n, &nx)) { bad = true; break; }
                     N++;
                     E = nx;
                 }
-                if (s_bad) break;
             }
-            s_E = E; s_N = N;
         }
+        E = __shfl_sync(0xffffffffu, E, 0); N = __shfl_sync(0xffffffffu, N, 0);
+        bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_bad || s_E != n) { fuz_raise(st, FUZ_E_BADRECORD, (int)min(s_N, (int64_t)0x7fffffff)); S.n_rec[0] = 0; S.n_rec[1] = 0; }
+    if (lane == 0) {
+        if (bad || E != n) { fuz_raise(st, FUZ_E_BADRECORD, (int)min(N, (int64_t)0x7fffffff)); S.n_rec[0] = 0; S.n_rec[1] = 0; }
         else {
-            S.n_rec[1] = s_N;
-            if (s_N > cap_rec || s_N > 0x7fffffff) { fuz_raise(st, FUZ_E_CAPACITY, 7); S.n_rec[0] = 0; }
-            else S.n_rec[0] = s_N;
+            S.n_rec[1] = N;
+            if (N > cap_rec || N > 0x7fffffff) { fuz_raise(st, FUZ_E_CAPACITY, 7); S.n_rec[0] = 0; }
+            else S.n_rec[0] = N;
         }
     }
 }
@@ -414,7 +439,7 @@ extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t
         fuz_launch(ctx, k_bam_anchor, (unsigned)((n_reg * 32 + 255) / 256), 256, 0, st, d_rec, rec_bytes, (int)n_ref, n_reg, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_bam_anchor");
     }
-    fuz_launch(ctx, k_bam_resolve, 1, 1024, 0, st, d_rec, rec_bytes, n_reg, cap_rec, S, ctx->d_status);
+    fuz_launch(ctx, k_bam_resolve, 1, 32, 0, st, d_rec, rec_bytes, n_reg, cap_rec, S, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_bam_resolve");
     fuz_launch(ctx, k_bam_fill, (unsigned)((n_reg + 256) / 256), 256, 0, st, d_rec, rec_bytes, n_reg, S, d_rec_off, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_bam_fill");

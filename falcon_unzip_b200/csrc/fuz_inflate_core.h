@@ -25,8 +25,10 @@
 enum { FUZ_INF_OK = 0, FUZ_INF_BADBLOCK = 1, FUZ_INF_BADTABLE = 2, FUZ_INF_BADCODE = 3, FUZ_INF_BADDIST = 4,
        FUZ_INF_OVERRUN = 5, FUZ_INF_INPUT = 6, FUZ_INF_SIZE = 7, FUZ_INF_CRC = 8 };
 
-// Table entry: [3:0] code length (0: not in the table, take the canonical search), [5:4] kind
-// (0 literal, 1 match length, 2 end of block), [11:8] extra bits, [31:16] literal / base value.
+// Table entry.  Literal: bit 31 clear, [3:0] code length (>= 1), [23:16] the byte.  Everything
+// else has bit 31 set: [3:0] code length (0: not in the table, take the canonical search), [5:4]
+// kind (1 match length, 2 end of block), [11:8] extra bits, [30:16] base value.  Distance and
+// code-length tables use the same fields without bit 31.
 struct FuzInfTables {
     uint32_t lit[1 << FUZ_INF_LBITS];
     uint32_t dist[1 << FUZ_INF_DBITS];
@@ -35,16 +37,17 @@ struct FuzInfTables {
     uint16_t lcount[16], dcount[16];     // codes per length
     uint8_t lens[FUZ_INF_MAXL + FUZ_INF_MAXD];
 };
+#define FUZ_INF_SPECIAL 0x80000000u
 
 FUZ_HD uint32_t fuz_inf_lit_entry(int sym, int nbits) {
     if (sym < 256) return ((uint32_t)sym << 16) | (uint32_t)nbits;
-    if (sym == 256) return (2u << 4) | (uint32_t)nbits;
-    if (sym > 285) return 0;                                     // 286, 287: never valid in a stream
+    if (sym == 256) return FUZ_INF_SPECIAL | (2u << 4) | (uint32_t)nbits;
+    if (sym > 285) return FUZ_INF_SPECIAL;                       // 286, 287: never valid in a stream (length 0 = reject)
     int base, eb;
     if (sym < 265) { base = sym - 254; eb = 0; }
     else if (sym == 285) { base = 258; eb = 0; }
     else { eb = (sym - 261) >> 2; base = 3 + ((4 + ((sym - 261) & 3)) << eb); }
-    return ((uint32_t)base << 16) | ((uint32_t)eb << 8) | (1u << 4) | (uint32_t)nbits;
+    return FUZ_INF_SPECIAL | ((uint32_t)base << 16) | ((uint32_t)eb << 8) | (1u << 4) | (uint32_t)nbits;
 }
 FUZ_HD uint32_t fuz_inf_dist_entry(int sym, int nbits) {
     if (sym > 29) return 0;
@@ -65,7 +68,8 @@ FUZ_HD uint32_t fuz_inf_rev(uint32_t code, int n) {            // reverse the lo
 //   int seek(int64 byte)        position the reader on the aligned word holding `byte`, return byte & 3
 //   uint32 next_word()          next 32 input bits
 //   int64 word_pos()            words handed out so far, as an absolute word index
-//   bool put(uint8)             append a literal (false: past the expected size)
+//   bool put(uint8)             append a literal (false: past the expected size; may be reported late,
+//                               but never later than 32 literals and never after writing out of bounds)
 //   bool copy(int len,int dist) append a match (false: distance too far back / past the expected size)
 //   bool copy_in(int64 byte, int len)   append len input bytes starting at `byte` (stored block)
 //   int lane(), int lanes(), void sync()
@@ -73,30 +77,40 @@ template <class IO>
 struct FuzInflate {
     IO &io;
     FuzInfTables &T;
-    uint64_t bb = 0;
-    int nb = 0;
+    // bit reader: the stream bits [32 W + bp, 32 W + 64) sit in (lo, hi), W = io.word_pos() - 2.
+    // refill() keeps bp < 32, so peek() always returns 32 valid bits with one funnel shift.
+    uint32_t lo = 0, hi = 0;
+    int bp = 0;
     int64_t end_byte = 0;
 
     FUZ_HD FuzInflate(IO &io_, FuzInfTables &t_) : io(io_), T(t_) {}
 
     FUZ_HD void start(int64_t first_byte, int64_t n_bytes) {
         const int mis = io.seek(first_byte);
-        bb = (uint64_t)(io.next_word() >> (8 * mis));
-        nb = 32 - 8 * mis;
+        lo = io.next_word();
+        hi = io.next_word();
+        bp = 8 * mis;
         end_byte = first_byte + n_bytes;
     }
-    FUZ_HD void need32() {
-        if (nb <= 32) { bb |= (uint64_t)io.next_word() << nb; nb += 32; }
+    FUZ_HD void refill() {
+        if (bp >= 32) { lo = hi; hi = io.next_word(); bp -= 32; }
     }
-    FUZ_HD void drop(int n) { bb >>= n; nb -= n; }
-    FUZ_HD uint32_t take(int n) {
-        const uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
-        drop(n);
+    FUZ_HD uint32_t peek() const {                               // needs bp < 32
+#ifdef __CUDA_ARCH__
+        return __funnelshift_r(lo, hi, (uint32_t)bp);
+#else
+        return (uint32_t)((((uint64_t)hi << 32) | lo) >> bp);
+#endif
+    }
+    FUZ_HD uint32_t take(int n) {                                // n <= 16
+        refill();
+        const uint32_t v = peek() & ((1u << n) - 1u);
+        bp += n;
         return v;
     }
-    // first input byte no bit of which has been consumed (bits are consumed in whole bytes at call sites)
-    FUZ_HD int64_t byte_pos() const { return io.word_pos() * 4 - (nb >> 3); }
-    FUZ_HD bool input_ok() const { return io.word_pos() * 4 - (nb >> 3) <= end_byte; }
+    // first input byte no bit of which has been consumed (call with bp on a byte boundary)
+    FUZ_HD int64_t byte_pos() const { return (io.word_pos() - 2) * 4 + (bp >> 3); }
+    FUZ_HD bool input_ok() const { return (io.word_pos() - 2) * 4 + ((bp + 7) >> 3) <= end_byte; }
 
     // Canonical Huffman decode tables from code lengths lens[0..n): the lookup table of 1 << tbits
     // entries for codes up to tbits long, plus count[] and sorted[] for the canonical search.
@@ -125,7 +139,7 @@ struct FuzInflate {
         }
         io.sync();
         err = count[0];
-        for (int i = io.lane(); i < (1 << tbits); i += io.lanes()) table[i] = 0;
+        for (int i = io.lane(); i < (1 << tbits); i += io.lanes()) table[i] = kind == 1 ? FUZ_INF_SPECIAL : 0u;
         io.sync();
         if (err) return err;
         int n_used = 0;
@@ -147,7 +161,7 @@ struct FuzInflate {
     // canonical search (codes longer than the table, and invalid codes): bit by bit like puff.c
     FUZ_HD uint32_t search(const uint16_t *count, const uint16_t *sorted, int kind) const {
         uint32_t code = 0, first = 0, index = 0;
-        uint64_t b = bb;
+        uint32_t b = peek();
         for (int l = 1; l < 16; l++) {
             code |= (uint32_t)b & 1u;
             b >>= 1;
@@ -173,16 +187,12 @@ struct FuzInflate {
     }
 
     FUZ_HD int dynamic_tables() {
-        need32();
         const int nlen = (int)take(5) + 257, ndist = (int)take(5) + 1, ncode = (int)take(4) + 4;
         if (nlen > 286 || ndist > 30) return FUZ_INF_BADTABLE;
         const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
         // every lane writes the same values to the same places: no hand-over needed before the build
         for (int i = 0; i < 19; i++) T.lens[i] = 0;
-        for (int i = 0; i < ncode; i++) {
-            need32();
-            T.lens[order[i]] = (uint8_t)take(3);
-        }
+        for (int i = 0; i < ncode; i++) T.lens[order[i]] = (uint8_t)take(3);
         io.sync();
         int e = build(T.lens, 19, T.dist, FUZ_INF_DBITS, T.dcount, T.dsorted, 0);
         if (e) return e;
@@ -190,10 +200,10 @@ struct FuzInflate {
         // distance table is built afterwards
         int i = 0, prev = 0;
         while (i < nlen + ndist) {
-            need32();
-            const uint32_t ent = T.dist[(uint32_t)bb & ((1u << FUZ_INF_DBITS) - 1u)];
+            refill();
+            const uint32_t ent = T.dist[peek() & ((1u << FUZ_INF_DBITS) - 1u)];
             if ((ent & 15u) == 0) return FUZ_INF_BADCODE;
-            drop((int)(ent & 15u));
+            bp += (int)(ent & 15u);
             const int sym = (int)(ent >> 16);
             int rep, val;
             if (sym < 16) { rep = 1; val = sym; prev = sym; }
@@ -212,27 +222,32 @@ struct FuzInflate {
 
     FUZ_HD int codes() {
         for (;;) {
-            need32();
-            uint32_t e = T.lit[(uint32_t)bb & ((1u << FUZ_INF_LBITS) - 1u)];
-            if ((e & 15u) == 0) {
-                e = search(T.lcount, T.lsorted, 1);
-                if (e == 0) return FUZ_INF_BADCODE;
-            }
-            drop((int)(e & 15u));
-            const uint32_t kind = (e >> 4) & 3u;
-            if (kind == 0) {
+            refill();
+            uint32_t e = T.lit[peek() & ((1u << FUZ_INF_LBITS) - 1u)];
+            if ((int32_t)e >= 0) {                               // literal straight from the table
+                bp += (int)(e & 15u);
                 if (!io.put((uint8_t)(e >> 16))) return FUZ_INF_OVERRUN;
                 continue;
             }
-            if (kind == 2) return FUZ_INF_OK;
-            const int len = (int)(e >> 16) + (int)take((int)((e >> 8) & 15u));
-            need32();
-            uint32_t d = T.dist[(uint32_t)bb & ((1u << FUZ_INF_DBITS) - 1u)];
+            if ((e & 15u) == 0) {
+                e = search(T.lcount, T.lsorted, 1);
+                if ((e & 15u) == 0) return FUZ_INF_BADCODE;
+                if ((int32_t)e >= 0) {
+                    bp += (int)(e & 15u);
+                    if (!io.put((uint8_t)(e >> 16))) return FUZ_INF_OVERRUN;
+                    continue;
+                }
+            }
+            bp += (int)(e & 15u);
+            if (((e >> 4) & 3u) == 2) return FUZ_INF_OK;
+            const int len = (int)((e >> 16) & 0x7FFFu) + (int)take((int)((e >> 8) & 15u));
+            refill();
+            uint32_t d = T.dist[peek() & ((1u << FUZ_INF_DBITS) - 1u)];
             if ((d & 15u) == 0) {
                 d = search(T.dcount, T.dsorted, 2);
-                if (d == 0) return FUZ_INF_BADCODE;
+                if ((d & 15u) == 0) return FUZ_INF_BADCODE;
             }
-            drop((int)(d & 15u));
+            bp += (int)(d & 15u);
             const int dist = (int)(d >> 16) + (int)take((int)((d >> 8) & 15u));
             if (!io.copy(len, dist)) return FUZ_INF_BADDIST;
             if (!input_ok()) return FUZ_INF_INPUT;
@@ -243,13 +258,12 @@ struct FuzInflate {
     FUZ_HD int run(int64_t first_byte, int64_t n_bytes) {
         start(first_byte, n_bytes);
         for (;;) {
-            need32();
             const uint32_t last = take(1), type = take(2);
             int e;
             if (type == 0) {
-                drop(nb & 7);
-                need32();
+                bp = (bp + 7) & ~7;
                 const uint32_t len = take(16), nlen = take(16);
+                refill();
                 if ((len ^ 0xFFFFu) != nlen) return FUZ_INF_BADBLOCK;
                 const int64_t src = byte_pos();
                 if (src + (int64_t)len > end_byte) return FUZ_INF_INPUT;

@@ -32,7 +32,7 @@ def _inflate_blocks(eng, blocks, crcs=None, sizes=None):
     uoff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     dev = eng.device
     d_comp = torch.zeros(len(comp) + 16, dtype=torch.uint8, device=dev)
-    d_comp[:len(comp)] = torch.frombuffer(bytes(comp) or b"\0", dtype=torch.uint8)[:len(comp)].to(dev)
+    d_comp[:len(comp)] = torch.from_numpy(np.frombuffer(bytes(comp) or b"\0", dtype=np.uint8).copy())[:len(comp)].to(dev)
     d_coff = torch.tensor(coff, dtype=torch.int64, device=dev)
     d_cs = torch.tensor(csize, dtype=torch.int32, device=dev)
     d_uoff = torch.from_numpy(uoff).to(dev)
@@ -91,7 +91,7 @@ def _index_device(eng, records: bytes, n_ref: int, cap=None):
     n = len(records)
     d = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
     if n:
-        d[:n] = torch.frombuffer(records, dtype=torch.uint8).to(dev)
+        d[:n] = torch.from_numpy(np.frombuffer(records, dtype=np.uint8).copy()).to(dev)
     cap = n // 36 + 2 if cap is None else cap
     off = torch.full((cap + 1,), -7, dtype=torch.int64, device=dev)
     cro = torch.full((n_ref + 1,), -7, dtype=torch.int32, device=dev)
@@ -185,9 +185,13 @@ def test_ingest_bam_file(eng, tmp_path, cfg, level):
     assert np.array_equal(db.rec_off.cpu().numpy()[:db.n_rec + 1], want_off)
     assert np.array_equal(db.ctg_rec_off.cpu().numpy(), want_cro)
     # a flipped payload bit is caught by the CRC check
-    img = np.fromfile(fn, dtype=np.uint8)
-    img[len(img) // 2] ^= 0x10
     from falcon_unzip_b200 import _lib
+    img = np.fromfile(fn, dtype=np.uint8)
+    n_blk = _lib.lib().fuz_host_bgzf_index(img.ctypes.data, len(img), 0, None, None, None, None)
+    coff, csize, uoff = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32), np.empty(n_blk + 1, np.int64)
+    _lib.lib().fuz_host_bgzf_index(img.ctypes.data, len(img), n_blk, coff.ctypes.data, csize.ctypes.data, uoff.ctypes.data, None)
+    b = n_blk // 2
+    img[coff[b] + csize[b] // 2] ^= 0x10                 # inside the deflate stream of a middle block
     with pytest.raises(_lib.FuzError):
         eng.ingest_bam(img)
 
