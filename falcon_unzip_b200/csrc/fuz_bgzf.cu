@@ -41,8 +41,13 @@ struct DevIO {
     uint32_t cur, nxt;             // words cbase + lane, cbase + 32 + lane
     int wi;                        // next word to hand out = cbase + wi
     uint8_t *ob;                   // 32-byte aligned address at or below the first payload byte
-    int p0, pos, lim, pstart;      // positions relative to ob: payload start, next byte, payload end, first staged byte
-    uint32_t pend;
+    int p0, pos, lim;              // positions relative to ob: payload start, next byte, payload end
+    // Output is staged in registers, one byte per lane (lane = position & 31): `pend` holds the
+    // window being filled, [pstart, pos); `pendA` the previous, complete window [a0, next multiple
+    // of 32), which is stored only when the current one completes -- by then the loads that feed
+    // it (match bytes fetched from earlier output) have had a whole window of decoding to return.
+    int pstart, a0;
+    uint32_t pend, pendA;
     int ln;
 
     __device__ __forceinline__ uint32_t ldw(int64_t i) const { return i < n_words ? __ldg(words + i) : 0u; }
@@ -59,9 +64,21 @@ struct DevIO {
         return w;
     }
     __device__ __forceinline__ int64_t word_pos() const { return cbase + wi; }
-    // staged literals [pstart, pos) lie inside one aligned 32-byte window; lane = position & 31.
-    // Literals past the expected size are never stored; the caller sees pos != lim in the end.
+    // bytes past the expected size are never stored; the caller sees pos != lim in the end
+    __device__ __forceinline__ void store_a() {
+        if (a0 >= 0) {
+            const int p = (a0 & ~31) + ln;
+            if (p >= a0 && p < lim) ob[p] = (uint8_t)pendA;
+            a0 = -1;
+        }
+    }
+    __device__ __forceinline__ bool rotate() {                 // the current window is complete
+        store_a();
+        pendA = pend; a0 = pstart; pstart = pos;
+        return pos <= lim;
+    }
     __device__ __forceinline__ void flush() {
+        store_a();
         const int p = (pstart & ~31) + ln;
         if (p >= pstart && p < min(pos, lim)) ob[p] = (uint8_t)pend;
         pstart = pos;
@@ -69,20 +86,43 @@ struct DevIO {
     __device__ __forceinline__ bool put(uint8_t b) {
         if ((pos & 31) == ln) pend = b;
         pos++;
-        if ((pos & 31) == 0) { flush(); return pos <= lim; }
+        if ((pos & 31) == 0) return rotate();
         return true;
     }
     __device__ __forceinline__ bool copy(int len, int dist) {
         if (dist > pos - p0 || pos + len > lim) return false;
+        if (dist == 1) {                           // a run of one byte (the 0xFF QUAL of PacBio BAMs)
+            uint32_t v;
+            if (pstart < pos) v = __shfl_sync(0xffffffffu, pend, (pos - 1) & 31);
+            else if (a0 >= 0) v = __shfl_sync(0xffffffffu, pendA, 31);
+            else { __syncwarp(); v = __ldcg(ob + pos - 1); }
+            while (len > 0) {
+                const int w = pos & 31, n = min(len, 32 - w);
+                if (ln >= w && ln < w + n) pend = v;
+                pos += n; len -= n;
+                if ((pos & 31) == 0) rotate();
+            }
+            return true;
+        }
+        const int unstored = pos - (a0 >= 0 ? a0 : pstart);
+        if (dist >= unstored + len) {              // every source byte is in memory already
+            __syncwarp();
+            const uint8_t *src = ob - dist;
+            while (len > 0) {
+                const int w = pos & 31, n = min(len, 32 - w);
+                if (ln >= w && ln < w + n) pend = __ldcg(src + (pos - w + ln));
+                pos += n; len -= n;
+                if ((pos & 31) == 0) rotate();
+            }
+            return true;
+        }
+        // near match: sources among the staged bytes or inside the match itself
         flush();
         __syncwarp();
         const uint8_t *src = ob + pos - dist;
         uint8_t *dst = ob + pos;
         if (dist >= len) {
             for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + i);
-        } else if (dist == 1) {                    // a run of one byte (the 0xFF QUAL of PacBio BAMs)
-            const uint8_t v = __ldcg(src);
-            for (int i = ln; i < len; i += 32) dst[i] = v;
         } else {                                   // overlapping: the pattern repeats with period dist
             for (int i = ln; i < len; i += 32) dst[i] = __ldcg(src + (i % dist));
         }
@@ -143,7 +183,7 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
     io.n_words = (comp_bytes + 3) >> 2;
     const int omis = (int)(reinterpret_cast<uintptr_t>(out + u0) & 31);
     io.ob = out + u0 - omis;
-    io.p0 = io.pos = io.pstart = omis; io.lim = omis + (int)(u1 - u0); io.pend = 0; io.ln = lane;
+    io.p0 = io.pos = io.pstart = omis; io.lim = omis + (int)(u1 - u0); io.pend = io.pendA = 0; io.a0 = -1; io.ln = lane;
     io.cbase = 0; io.wi = 0; io.cur = io.nxt = 0;
     FuzInflate<DevIO> inf(io, tabs[warp]);
     int rc = inf.run(c0, cs);
@@ -156,7 +196,17 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
         const int piece = (n + 31) >> 5;
         const int lo = min(lane * piece, n), hi = min(lo + piece, n);
         uint32_t c = 0xFFFFFFFFu;
-        for (int i = lo; i < hi; i++) c = s_crc[(c ^ __ldcg(out + u0 + i)) & 0xFFu] ^ (c >> 8);
+        const uint8_t *q = out + u0 + lo, *qe = out + u0 + hi;
+        while (q < qe && (reinterpret_cast<uintptr_t>(q) & 3)) c = s_crc[(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
+#pragma unroll 4
+        for (; q + 4 <= qe; q += 4) {                // aligned words: four table steps per load
+            const uint32_t w = __ldcg(reinterpret_cast<const uint32_t *>(q));
+            c = s_crc[(c ^ w) & 0xFFu] ^ (c >> 8);
+            c = s_crc[(c ^ (w >> 8)) & 0xFFu] ^ (c >> 8);
+            c = s_crc[(c ^ (w >> 16)) & 0xFFu] ^ (c >> 8);
+            c = s_crc[(c ^ (w >> 24)) & 0xFFu] ^ (c >> 8);
+        }
+        while (q < qe) c = s_crc[(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
         c ^= 0xFFFFFFFFu;
         int len = hi - lo;
         for (int d = 1; d < 32; d <<= 1) {

@@ -238,19 +238,25 @@ struct FuzInflate {
                     continue;
                 }
             }
-            bp += (int)(e & 15u);
-            if (((e >> 4) & 3u) == 2) return FUZ_INF_OK;
-            const int len = (int)((e >> 16) & 0x7FFFu) + (int)take((int)((e >> 8) & 15u));
+            // code + extra bits come out of one 32-bit peek (<= 15 + 5 and <= 15 + 13 bits)
+            if (((e >> 4) & 3u) == 2) { bp += (int)(e & 15u); return FUZ_INF_OK; }
+            uint32_t w = peek();
+            int nc = (int)(e & 15u), ne = (int)((e >> 8) & 15u);
+            const int len = (int)((e >> 16) & 0x7FFFu) + (int)((w >> nc) & ((1u << ne) - 1u));
+            bp += nc + ne;
             refill();
-            uint32_t d = T.dist[peek() & ((1u << FUZ_INF_DBITS) - 1u)];
+            w = peek();
+            uint32_t d = T.dist[w & ((1u << FUZ_INF_DBITS) - 1u)];
             if ((d & 15u) == 0) {
                 d = search(T.dcount, T.dsorted, 2);
                 if ((d & 15u) == 0) return FUZ_INF_BADCODE;
             }
-            bp += (int)(d & 15u);
-            const int dist = (int)(d >> 16) + (int)take((int)((d >> 8) & 15u));
+            nc = (int)(d & 15u); ne = (int)((d >> 8) & 15u);
+            const int dist = (int)(d >> 16) + (int)((w >> nc) & ((1u << ne) - 1u));
+            bp += nc + ne;
+            // (no input check here: every match produces output, which is bounded; the input
+            // position is checked at the end of every deflate block)
             if (!io.copy(len, dist)) return FUZ_INF_BADDIST;
-            if (!input_ok()) return FUZ_INF_INPUT;
         }
     }
 
