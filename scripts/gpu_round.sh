@@ -13,9 +13,9 @@ timeout 300 python scripts/kprof.py > gpurun_out/${TAG}_kprof.txt 2>&1; cat gpur
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 cat gpurun_out/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-bam --e2e-steps 1 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_project|k_pileup_gather|k_ctg_phase|k_scan_records" -s 8 -c 4 -f -o gpurun_out/${TAG}_prof4 \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-bam --e2e-steps 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out | tail -15
