@@ -77,6 +77,21 @@ class RROutputs(C.Structure):
                 ("d_vt_count", C.c_void_p), ("d_vt_score", C.c_void_p)]
 
 
+class OvlpInput(C.Structure):
+    _fields_ = ([("n_ovl", C.c_int64)] + [("d_" + k, C.c_void_p) for k in ("q", "t", "len", "qs", "qe", "ql", "ts", "te", "tl",
+                                                                          "flags", "file")] +
+                [("n_reads", C.c_int32), ("d_in_map", C.c_void_p), ("d_ph_ctg", C.c_void_p), ("d_ph_block", C.c_void_p),
+                 ("d_ph_phase", C.c_void_p), ("max_diff", C.c_int32), ("max_ovlp", C.c_int32), ("min_ovlp", C.c_int32),
+                 ("min_len", C.c_int32), ("bestn", C.c_int32), ("stage", C.c_int32), ("d_ignore_in", C.c_void_p),
+                 ("d_contained_in", C.c_void_p)])
+
+
+class OvlpOutputs(C.Structure):
+    _fields_ = [("d_ignore", C.c_void_p), ("d_contained", C.c_void_p), ("cap_groups", C.c_int64), ("d_grp_q", C.c_void_p),
+                ("d_grp_ignore", C.c_void_p), ("d_grp_tie", C.c_void_p), ("d_grp_off", C.c_void_p), ("cap_out", C.c_int64),
+                ("d_out_line", C.c_void_p)]
+
+
 class Status(C.Structure):
     _fields_ = [("error", C.c_int32), ("error_index", C.c_int32), ("n_sites", C.c_int64),
                 ("n_vmap", C.c_int64), ("n_atable", C.c_int64), ("n_reads", C.c_int64),
@@ -117,6 +132,10 @@ SYMBOLS = [
     ("fuz_bam_index_records", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         _i64p, _i64p]),
     ("fuz_rr_track", C.c_int, [C.c_void_p, C.POINTER(RRInput), C.POINTER(RROutputs)]),
+    ("fuz_ovlp_filter", C.c_int, [C.c_void_p, C.POINTER(OvlpInput), C.POINTER(OvlpOutputs)]),
+    ("fuz_host_parse_la4falcon_mo", C.c_int64, [C.c_char_p, C.c_int64, C.c_int64] + [C.c_void_p] * 12),
+    ("fuz_host_format_ovlp", C.c_int64, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64]),
     ("fuz_host_parse_la4falcon", C.c_int64, [C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p]),
     ("fuz_host_index_records", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p]),

@@ -202,3 +202,177 @@ extern "C" int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, i
     for (auto &th : pool) th.join();
     return std::min(total, cap);
 }
+
+// ---------------------------------------------------------------- LA4Falcon -mo (overlap filter)
+// "q t -len idt qstrand qs qe ql tstrand ts te tl tag" (reference ovlp_filter_with_phase.py:60-62,
+// 95-99): every column the three filter stages read, plus where the line sits in the text (the
+// selected lines are printed again, :352).  flags: bit 0 = float(col 3) >= 90 (i.e. not `idt < 90`),
+// bits 1-2 = last token: 1 "overlap", 2 "contains", 3 "contained", 0 anything else.
+// q / t must be %09d ids (9 digits): the reference compares and sorts them as strings.
+#include <charconv>
+#include <stdlib.h>
+
+struct MoCols {
+    int32_t *q, *t, *len, *qs, *qe, *ql, *ts, *te, *tl;
+    uint8_t *flags;
+    int64_t *off;
+    int32_t *llen;
+};
+
+static int64_t parse_mo_range(const char *text, int64_t base, int64_t n_bytes, int64_t cap, const MoCols &c, int64_t at) {
+    int64_t n = 0, i = 0;
+    while (i < n_bytes && n < cap) {
+        const int64_t line0 = i;
+        long long col[12];
+        int nc = 0;
+        bool idt_ok = false, any = false;
+        int64_t last_s = 0, last_e = 0;
+        while (i < n_bytes && text[i] != '\n') {
+            while (i < n_bytes && (text[i] == ' ' || text[i] == '\t' || text[i] == '\r' || text[i] == '\f' || text[i] == '\v')) i++;
+            if (i >= n_bytes || text[i] == '\n') break;
+            any = true;
+            const int64_t s = i;
+            while (i < n_bytes && text[i] != ' ' && text[i] != '\t' && text[i] != '\n' && text[i] != '\r' && text[i] != '\f' && text[i] != '\v') i++;
+            last_s = s; last_e = i;
+            if (nc < 12) {
+                if (nc == 3) {                          // idt: float(l[3]) < 90 (:97,:100)
+                    double v = 0;
+                    auto r = std::from_chars(text + s + (text[s] == '+' ? 1 : 0), text + i, v);
+                    if (r.ec != std::errc() || r.ptr != text + i) return -1;
+                    idt_ok = !(v < 90.0);
+                    col[nc] = 0;
+                } else if (nc == 4 || nc == 8) {
+                    col[nc] = 0;                        // strands: never read
+                } else {
+                    bool neg = false;
+                    int64_t k = s;
+                    long long v = 0;
+                    if (k < i && (text[k] == '-' || text[k] == '+')) { neg = text[k] == '-'; k++; }
+                    if (k == i) return -1;
+                    for (; k < i; k++) {
+                        if (text[k] < '0' || text[k] > '9') return -1;
+                        v = v * 10 + (text[k] - '0');
+                        if (v > 0x7fffffffLL) return -1;
+                    }
+                    if ((nc == 0 || nc == 1) && (i - s != 9 || neg || text[s] == '+')) return -2;   // not a %09d id
+                    col[nc] = neg ? -v : v;
+                }
+            }
+            nc++;
+        }
+        const int64_t line1 = i;
+        if (i < n_bytes) i++;
+        if (!any) continue;
+        if (nc < 12) return -1;
+        int tag = 0;
+        const int64_t tl_ = last_e - last_s;
+        if (tl_ == 7 && !memcmp(text + last_s, "overlap", 7)) tag = 1;
+        else if (tl_ == 8 && !memcmp(text + last_s, "contains", 8)) tag = 2;
+        else if (tl_ == 9 && !memcmp(text + last_s, "contained", 9)) tag = 3;
+        const int64_t w = at + n;
+        c.q[w] = (int32_t)col[0]; c.t[w] = (int32_t)col[1]; c.len[w] = (int32_t)(-col[2]);
+        c.qs[w] = (int32_t)col[5]; c.qe[w] = (int32_t)col[6]; c.ql[w] = (int32_t)col[7];
+        c.ts[w] = (int32_t)col[9]; c.te[w] = (int32_t)col[10]; c.tl[w] = (int32_t)col[11];
+        c.flags[w] = (uint8_t)((idt_ok ? 1 : 0) | (tag << 1));
+        c.off[w] = base + line0; c.llen[w] = (int32_t)(line1 - line0);
+        n++;
+    }
+    return n;
+}
+
+// Returns the number of lines parsed, -1 on a malformed line (the reference would raise), -2 when a
+// read id is not a 9-digit %09d id.  Lines are split over the host threads at line ends.
+extern "C" int64_t fuz_host_parse_la4falcon_mo(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t, int32_t *len,
+                                               int32_t *qs, int32_t *qe, int32_t *ql, int32_t *ts, int32_t *te, int32_t *tl,
+                                               uint8_t *flags, int64_t *line_off, int32_t *line_len) {
+    if (!text || n_bytes < 0 || !q || !t || !len || !qs || !qe || !ql || !ts || !te || !tl || !flags || !line_off || !line_len) return -1;
+    const MoCols c{q, t, len, qs, qe, ql, ts, te, tl, flags, line_off, line_len};
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 32), n_bytes / (1 << 20));
+    if (n_thr <= 1) return parse_mo_range(text, 0, n_bytes, cap, c, 0);
+    std::vector<int64_t> cut(n_thr + 1, n_bytes), lines(n_thr, 0), at(n_thr + 1, 0), got(n_thr, 0);
+    cut[0] = 0;
+    for (int k = 1; k < n_thr; k++) {
+        int64_t p = std::max(cut[k - 1], n_bytes / n_thr * k);
+        const void *nl = p < n_bytes ? memchr(text + p, '\n', (size_t)(n_bytes - p)) : nullptr;
+        cut[k] = nl ? (const char *)nl - text + 1 : n_bytes;
+    }
+    // pass 1: non-blank lines per piece (so that every piece knows where its rows go)
+    auto count_lines = [&](int k) {
+        int64_t n = 0;
+        bool any = false;
+        for (int64_t i = cut[k]; i < cut[k + 1]; i++) {
+            const char ch = text[i];
+            if (ch == '\n') { n += any; any = false; }
+            else if (ch != ' ' && ch != '\t' && ch != '\r' && ch != '\f' && ch != '\v') any = true;
+        }
+        lines[k] = n + (any ? 1 : 0);
+    };
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_thr; k++) pool.emplace_back(count_lines, k);
+    for (auto &th : pool) th.join();
+    for (int k = 0; k < n_thr; k++) at[k + 1] = at[k] + lines[k];
+    if (at[n_thr] > cap) return -1;
+    pool.clear();
+    for (int k = 0; k < n_thr; k++)
+        pool.emplace_back([&, k] { got[k] = parse_mo_range(text + cut[k], cut[k], cut[k + 1] - cut[k], lines[k], c, at[k]); });
+    for (auto &th : pool) th.join();
+    for (int k = 0; k < n_thr; k++) {
+        if (got[k] < 0) return got[k];
+        if (got[k] != lines[k]) return -1;
+    }
+    return at[n_thr];
+}
+
+// Output text of the overlap filter (reference ovlp_filter_with_phase.py:266-275, 352): for every
+// selected line its whitespace-split tokens joined by single blanks, then the phase strings
+// ("ctg.block.phase") of its q and t read.  phase_text / phase_off: one string per read id.
+// Call with out = NULL to get the size.
+extern "C" int64_t fuz_host_format_ovlp(const char *text, const int64_t *line_off, const int32_t *line_len, const int32_t *q,
+                                        const int32_t *t, const int64_t *sel, int64_t n_sel, const char *phase_text,
+                                        const int64_t *phase_off, char *out, int64_t cap) {
+    if (!text || !line_off || !line_len || !q || !t || (!sel && n_sel) || !phase_text || !phase_off) return -1;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 32), n_sel / 4096));
+    std::vector<int64_t> sizes(n_thr, 0), start(n_thr + 1, 0);
+    auto emit = [&](int k, char *dst) -> int64_t {
+        int64_t w = 0;
+        const int64_t lo = n_sel * k / n_thr, hi = n_sel * (k + 1) / n_thr;
+        for (int64_t s = lo; s < hi; s++) {
+            const int64_t li = sel[s];
+            const char *p = text + line_off[li], *e = p + line_len[li];
+            bool first = true;
+            while (p < e) {
+                while (p < e && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\f' || *p == '\v')) p++;
+                if (p >= e) break;
+                const char *s0 = p;
+                while (p < e && *p != ' ' && *p != '\t' && *p != '\r' && *p != '\f' && *p != '\v') p++;
+                if (!first) { if (dst) dst[w] = ' '; w++; }
+                if (dst) memcpy(dst + w, s0, (size_t)(p - s0));
+                w += p - s0;
+                first = false;
+            }
+            for (int side = 0; side < 2; side++) {
+                const int32_t r = side ? t[li] : q[li];
+                const int64_t a = phase_off[r], b = phase_off[r + 1];
+                if (dst) dst[w] = ' ';
+                w++;
+                if (dst) memcpy(dst + w, phase_text + a, (size_t)(b - a));
+                w += b - a;
+            }
+            if (dst) dst[w] = '\n';
+            w++;
+        }
+        return w;
+    };
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_thr; k++) pool.emplace_back([&, k] { sizes[k] = emit(k, nullptr); });
+    for (auto &th : pool) th.join();
+    for (int k = 0; k < n_thr; k++) start[k + 1] = start[k] + sizes[k];
+    if (!out) return start[n_thr];
+    if (start[n_thr] > cap) return -1;
+    pool.clear();
+    for (int k = 0; k < n_thr; k++) pool.emplace_back([&, k] { emit(k, out + start[k]); });
+    for (auto &th : pool) th.join();
+    return start[n_thr];
+}

@@ -15,6 +15,7 @@
  *   fuz_bgzf_inflate, fuz_bam_index_records
  *                           falcon_unzip/phasing.py:27        the `samtools view` pipe: BGZF
  *                           inflate + record split, on the device
+ *   fuz_ovlp_filter         falcon_unzip/ovlp_filter_with_phase.py:49-290  filter_stage1-3
  *   fuz_host_*              host-side helpers of the same path (record index, QNAME ->
  *                           q_id of phasing.py:47-54)
  *
@@ -277,6 +278,46 @@ typedef struct {
  * reserved[3] = kept overlap lines. */
 int fuz_rr_track(fuz_ctx *ctx, const fuz_rr_input *in, fuz_rr_outputs *out);
 
+/* ---- overlap filter with phase (falcon_unzip/ovlp_filter_with_phase.py) ---- */
+/* fuz_ovlp_filter replaces filter_stage1 (:49-143), filter_stage2 (:145-186) and filter_stage3
+ * (:188-290) for ALL LAS files at once.  The host parses the `LA4Falcon -mo` text
+ * (fuz_host_parse_la4falcon_mo), interns the strings of the rid -> (ctg, block, phase) table
+ * (:319-322) and prints the selected lines (fuz_host_format_ovlp, :352). */
+typedef struct {
+    int64_t n_ovl;                /* overlap lines, concatenated in (file, line) order            */
+    const int32_t *d_q, *d_t;     /* read ids (columns 0, 1; %09d ids)                            */
+    const int32_t *d_len;         /* overlap length = -int(col 2)                                 */
+    const int32_t *d_qs, *d_qe, *d_ql, *d_ts, *d_te, *d_tl;   /* columns 5, 6, 7, 9, 10, 11       */
+    const uint8_t *d_flags;       /* bit 0: float(col 3) >= 90; bits 1-2: last column, 1 "overlap",
+                                   * 2 "contains", 3 "contained", 0 anything else                  */
+    const int32_t *d_file;        /* LAS file index of the line (non-decreasing)                  */
+    int32_t n_reads;              /* size of the read-id space                                    */
+    const uint8_t *d_in_map;      /* [n_reads] 1 if the id is a key of arid2phase                 */
+    const int32_t *d_ph_ctg, *d_ph_block, *d_ph_phase;   /* [n_reads] interned strings of the row  */
+    int32_t max_diff, max_ovlp, min_ovlp, min_len, bestn;
+    int32_t stage;                /* 1, 2, 3: stop after that stage (3 = the whole filter)        */
+    const uint8_t *d_ignore_in;   /* [n_reads] or NULL: the ignore set is given (per-file stage 2/3 calls) */
+    const uint8_t *d_contained_in;/* [n_reads] or NULL: the contained set is given                */
+} fuz_ovlp_input;
+
+typedef struct {
+    uint8_t *d_ignore;            /* [n_reads] stage 1: reads to ignore                            */
+    uint8_t *d_contained;         /* [n_reads] stage 2: contained reads                            */
+    int64_t cap_groups;           /* a group = a run of one q among the lines passing the phase filter */
+    int32_t *d_grp_q;             /* [cap_groups] q of the group                                   */
+    uint8_t *d_grp_ignore;        /* [cap_groups] stage-1 verdict of the run (:80-87)              */
+    uint8_t *d_grp_tie;           /* [cap_groups] 1: two candidates tie on (inphase, len, range, t):
+                                   * the host re-sorts the group with the full string comparison   */
+    int32_t *d_grp_off;           /* [cap_groups + 1] slice of d_out_line of every group           */
+    int64_t cap_out;
+    int32_t *d_out_line;          /* [cap_out] stage 3: selected lines (index into the input) in output order */
+} fuz_ovlp_outputs;
+
+/* status after the call: reserved[0] = groups, reserved[1] = selected lines, reserved[2] = selected
+ * lines needed.  FUZ_E_CAPACITY: error_index 10 = cap_groups, 11 = cap_out, 9 = more than 512
+ * candidates on one side of a read (max_cov beyond what the kernel holds in shared memory). */
+int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_outputs *out);
+
 /* ---- host helpers (no CUDA) ------------------------------------------------------ */
 /* Walk the block_size chain of a record buffer.  rec_off needs n_rec+1 slots; returns
  * the record count through n_rec (call with rec_off = NULL to count only). */
@@ -292,6 +333,18 @@ int fuz_host_assign_qids(const uint8_t *h_rec_buf, const int64_t *h_rec_off, int
  * on a malformed line (the reference would raise). */
 int64_t fuz_host_parse_la4falcon(const char *text, int64_t n_bytes, int64_t cap,
                                  int32_t *q, int32_t *t, int32_t *len, int32_t *tlen);
+/* Parse LA4Falcon -mo text (ovlp_filter_with_phase.py:60-62,95-99): every column the three stages
+ * read, the flags of fuz_ovlp_input.d_flags and the place of the line in `text`.  Returns the number
+ * of lines, -1 on a malformed line (the reference would raise), -2 when a read id is not a %09d id. */
+int64_t fuz_host_parse_la4falcon_mo(const char *text, int64_t n_bytes, int64_t cap, int32_t *q, int32_t *t, int32_t *len,
+                                    int32_t *qs, int32_t *qe, int32_t *ql, int32_t *ts, int32_t *te, int32_t *tl,
+                                    uint8_t *flags, int64_t *line_off, int32_t *line_len);
+/* Output text of the filter (:266-275, :352): tokens of every selected line joined by blanks plus the
+ * phase strings of q and t (phase_text[phase_off[r] .. phase_off[r+1]) = "ctg.block.phase").  Returns
+ * the size (call with out = NULL first), -1 if cap is too small. */
+int64_t fuz_host_format_ovlp(const char *text, const int64_t *line_off, const int32_t *line_len, const int32_t *q,
+                             const int32_t *t, const int64_t *sel, int64_t n_sel, const char *phase_text,
+                             const int64_t *phase_off, char *out, int64_t cap);
 /* CPython-2.7 dict iteration order of int keys inserted in the given order (B.3). */
 int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int64_t *out);
 

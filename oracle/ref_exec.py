@@ -204,3 +204,42 @@ def run_rr_track(las_lines: Dict[str, List[str]], phased_read_file: str, read_to
     mod.run_track_reads(FakePool(), phased_read_file, read_to_contig_map, rawread_ids,
                         sorted(las_lines), min_len, bestn, "raw_reads.db", out_path)
     return out_path
+
+
+def load_ovlp_filter(las_lines: Dict[str, List[str]]) -> types.ModuleType:
+    """falcon_unzip/ovlp_filter_with_phase.py: the print statement of main() (:352) and xrange are
+    patched, the LA4Falcon pipe (`sp.check_output`, :60,:150,:195) is replaced by in-memory text.
+    ``las_lines`` maps a LAS file name to its ``LA4Falcon -mo`` lines."""
+    with open(os.path.join(REF_ROOT, "falcon_unzip", "ovlp_filter_with_phase.py")) as f:
+        src = f.read()
+    src = _sub(r'print " "\.join\(l\)', 'print(" ".join(l))', src, 1)
+    src = _sub(r"\bxrange\b", "range", src, 4)
+    mod = _exec_patched(src, "ref_ovlp_filter", {})
+
+    def check_output(cmd):
+        return "".join(x if x.endswith("\n") else x + "\n" for x in las_lines[cmd[-1]])
+    mod.sp = types.SimpleNamespace(check_output=check_output)
+    return mod
+
+
+def run_ovlp_filter(las_lines: Dict[str, List[str]], rid_phase_rows: Iterable[str], max_diff: int, max_cov: int,
+                    min_cov: int, min_len: int, bestn: int) -> str:
+    """main() of the (patched) reference (:309-352) without the process pool -> the text it prints."""
+    mod = load_ovlp_filter(las_lines)
+    mod.arid2phase.clear()
+    for row in rid_phase_rows:
+        row = row.strip().split()
+        mod.arid2phase[row[0]] = (row[1], row[2], row[3])
+    files = list(las_lines)
+    ignore_all: List = []
+    for fn in files:
+        ignore_all.extend(mod.filter_stage1(("db", fn, max_diff, max_cov, min_cov, min_len))[1])
+    ignore_all = set(ignore_all)
+    contained = set()
+    for fn in files:
+        contained.update(mod.filter_stage2(("db", fn, max_diff, max_cov, min_cov, min_len, ignore_all))[1])
+    out = []
+    for fn in files:
+        for l in mod.filter_stage3(("db", fn, max_diff, max_cov, min_cov, min_len, ignore_all, contained, bestn))[1]:
+            out.append(" ".join(l) + "\n")
+    return "".join(out)
