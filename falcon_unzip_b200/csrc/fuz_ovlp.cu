@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(256) k_of_stage1(fuz_ovlp_input in, OvlpScratc
             const int q = in.d_q[S.P[j0]];
             const bool ig = of_ignored(left, right, in);
             out.d_grp_q[g] = q;
+            out.d_grp_line[g] = S.P[j0];
             out.d_grp_ignore[g] = ig ? 1 : 0;
             if (ig && !in.d_ignore_in) out.d_ignore[q] = 1;
         }
@@ -254,7 +255,7 @@ extern "C" int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_
     if (!ctx || !in || !out) return FUZ_E_ARG;
     if (in->n_ovl < 0 || in->n_ovl > 0x7ffffff0LL || in->n_reads < 0) return fuz_fail(ctx, FUZ_E_ARG, "fuz_ovlp_filter: bad sizes");
     if (in->stage < 1 || in->stage > 3) return fuz_fail(ctx, FUZ_E_ARG, "fuz_ovlp_filter: stage must be 1, 2 or 3");
-    if (!out->d_ignore || !out->d_contained || !out->d_grp_q || !out->d_grp_ignore || !out->d_grp_tie || !out->d_grp_off ||
+    if (!out->d_ignore || !out->d_contained || !out->d_grp_q || !out->d_grp_line || !out->d_grp_ignore || !out->d_grp_tie || !out->d_grp_off ||
         (!out->d_out_line && out->cap_out > 0))
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_ovlp_filter: missing output buffer");
     cudaStream_t st = ctx->stream;

@@ -305,6 +305,7 @@ typedef struct {
     uint8_t *d_contained;         /* [n_reads] stage 2: contained reads                            */
     int64_t cap_groups;           /* a group = a run of one q among the lines passing the phase filter */
     int32_t *d_grp_q;             /* [cap_groups] q of the group                                   */
+    int32_t *d_grp_line;          /* [cap_groups] input line that opens the group                  */
     uint8_t *d_grp_ignore;        /* [cap_groups] stage-1 verdict of the run (:80-87)              */
     uint8_t *d_grp_tie;           /* [cap_groups] 1: two candidates tie on (inphase, len, range, t):
                                    * the host re-sorts the group with the full string comparison   */
