@@ -68,6 +68,7 @@ extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->keep) cudaFree(ctx->keep);
     if (ctx->qid_buf) cudaFree(ctx->qid_buf);
+    if (ctx->scan_state) cudaFree(ctx->scan_state);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -251,9 +252,100 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
     if (threadIdx.x == 0) fuz_scan_publish(st, fin_op, fin_cap, total);
 }
 
+// ------------------------------------------------------------------ multi-CTA scan
+// Arrays of millions of entries with a host-known length (overlap lines): single pass with
+// decoupled look-back.  Tiles of 4096 entries are handed out by an atomic counter (a tile only
+// waits for tiles that already run); a tile publishes its aggregate, then its inclusive prefix,
+// flag and value packed in one 64-bit word; warp 0 looks back 32 tiles at a time.
+#define FUZ_SCAN_TILE 4096
+__global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n,
+                                                    unsigned long long *state, unsigned int *counter) {
+    fuz_pdl_enter();
+    __shared__ int s_tile;
+    __shared__ int s_warp[32];
+    __shared__ int s_prefix, s_agg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t i0 = (int64_t)tile * FUZ_SCAN_TILE + (int64_t)tid * 4;
+    int4 v = make_int4(0, 0, 0, 0);
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (i0 + 4 <= n && vec) v = *reinterpret_cast<const int4 *>(in + i0);
+    else if (i0 < n) {
+        v.x = in[i0];
+        if (i0 + 1 < n) v.y = in[i0 + 1];
+        if (i0 + 2 < n) v.z = in[i0 + 2];
+        if (i0 + 3 < n) v.w = in[i0 + 3];
+    }
+    const int s = v.x + v.y + v.z + v.w;
+    const int incl = fuz_warp_incl_scan(s, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int t = s_warp[lane];
+        const int ti = fuz_warp_incl_scan(t, lane);
+        s_warp[lane] = ti - t;
+        const int agg = __shfl_sync(0xffffffffu, ti, 31);
+        int prefix = 0;
+        if (tile > 0) {
+            volatile unsigned long long *vs = state;
+            if (lane == 0) vs[tile] = (1ull << 32) | (unsigned int)agg;
+            for (int base = tile - 1;; base -= 32) {
+                const int idx = base - lane;
+                unsigned long long w;
+                do {
+                    w = idx >= 0 ? vs[idx] : (2ull << 32);
+                } while (__any_sync(0xffffffffu, (w >> 32) == 0));
+                const uint32_t done = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+                const int first = done ? __ffs(done) - 1 : 31;
+                prefix += fuz_warp_sum(lane <= first ? (int)(unsigned int)w : 0);
+                if (done) break;
+            }
+        }
+        if (lane == 0) {
+            reinterpret_cast<volatile unsigned long long *>(state)[tile] = (2ull << 32) | (unsigned int)(prefix + agg);
+            s_prefix = prefix;
+            s_agg = agg;
+        }
+    }
+    __syncthreads();
+    const int excl = s_prefix + s_warp[warp] + (incl - s);
+    if (i0 + 4 <= n && vec) {
+        *reinterpret_cast<int4 *>(out + i0) = make_int4(excl, excl + v.x, excl + v.x + v.y, excl + v.x + v.y + v.z);
+    } else if (i0 < n) {
+        out[i0] = excl;
+        if (i0 + 1 < n) out[i0 + 1] = excl + v.x;
+        if (i0 + 2 < n) out[i0 + 2] = excl + v.x + v.y;
+        if (i0 + 3 < n) out[i0 + 3] = excl + v.x + v.y + v.z;
+    }
+    if (tid == 0 && (int64_t)(tile + 1) * FUZ_SCAN_TILE >= n) out[n] = s_prefix + s_agg;
+}
+
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n, int fin_op,
                  int64_t fin_cap) {
     fuz_launch(ctx, k_scan_i32, 1, 1024, 0, ctx->stream, d_in, d_out, n_cap, d_n, fin_op, fin_cap, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_scan_i32");
+    return FUZ_OK;
+}
+
+// exclusive scan of n entries (host-known n), out[n] = total; uses the context's tile-state buffer:
+// main stream only, one scan at a time
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n) {
+    if (n <= 65536) return fuz_scan_i32(ctx, d_in, d_out, n, nullptr, FUZ_FIN_NONE, 0);
+    const int64_t tiles = (n + FUZ_SCAN_TILE - 1) / FUZ_SCAN_TILE;
+    const size_t need = 8 * (size_t)tiles + 64;
+    if (need > ctx->scan_state_cap) {
+        FUZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->scan_state) FUZ_CUDA(ctx, cudaFree(ctx->scan_state));
+        ctx->scan_state = nullptr; ctx->scan_state_cap = 0;
+        FUZ_CUDA(ctx, cudaMalloc(&ctx->scan_state, need * 2));
+        ctx->scan_state_cap = need * 2;
+    }
+    FUZ_CUDA(ctx, cudaMemsetAsync(ctx->scan_state, 0, need, ctx->stream));
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->scan_state) + 1;
+    fuz_launch(ctx, k_scan_wide, (unsigned)tiles, 1024, 0, ctx->stream, d_in, d_out, n, state,
+               reinterpret_cast<unsigned int *>(ctx->scan_state));
+    FUZ_LAUNCH_CHECK(ctx, "k_scan_wide");
     return FUZ_OK;
 }

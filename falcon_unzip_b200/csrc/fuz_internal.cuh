@@ -46,6 +46,7 @@ struct fuz_ctx {
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int64_t max_pairs_per_site = 96;
+    uint8_t *scan_state = nullptr; size_t scan_state_cap = 0;   // tile states of the multi-CTA scan
     bool ingest_pending = false;       // fuz_bgzf_inflate ran; the next fuz_bam_index_records keeps its status
     bool phase_attr_set = false;
     // per-launch profile (diagnostics): an event after every kernel launch
@@ -249,3 +250,6 @@ __device__ __forceinline__ void fuz_scan_publish(fuz_status *st, int fin_op, int
 enum { FUZ_FIN_NONE = 0, FUZ_FIN_SITES = 1, FUZ_FIN_VMAP = 2, FUZ_FIN_ATABLE = 3, FUZ_FIN_READS = 4, FUZ_FIN_PAIRS = 5 };
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap,
                  const int64_t *d_n, int fin_op, int64_t fin_cap);
+// the same for a host-known n of millions of entries: multi-CTA single-pass scan (decoupled
+// look-back); main stream only
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n);

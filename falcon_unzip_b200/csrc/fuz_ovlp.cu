@@ -281,13 +281,13 @@ extern "C" int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_
     if (!in->d_contained_in) FUZ_CUDA(ctx, cudaMemsetAsync(out->d_contained, 0, (size_t)in->n_reads, st));
     fuz_launch(ctx, k_of_pass, FUZ_GRID_BLOCKS, 256, 0, st, *in, S);
     FUZ_LAUNCH_CHECK(ctx, "k_of_pass");
-    if ((rc = fuz_scan_i32(ctx, S.flag, S.pos, n, nullptr, FUZ_FIN_NONE, 0))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, S.flag, S.pos, n))) return rc;
     fuz_launch(ctx, k_of_compact, FUZ_GRID_BLOCKS, 256, 0, st, n, S);
     FUZ_LAUNCH_CHECK(ctx, "k_of_compact");
     fuz_launch(ctx, k_of_heads, FUZ_GRID_BLOCKS, 256, 0, st, *in, S);
     FUZ_LAUNCH_CHECK(ctx, "k_of_heads");
     // heads beyond n_pass stay 0 (memset), so scanning all n entries gives gscan[n_pass] = groups
-    if ((rc = fuz_scan_i32(ctx, S.head, S.gscan, n, nullptr, FUZ_FIN_NONE, 0))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, S.head, S.gscan, n))) return rc;
     fuz_launch(ctx, k_of_gstart, FUZ_GRID_BLOCKS, 256, 0, st, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_of_gstart");
     fuz_launch(ctx, k_of_stage1, FUZ_GRID_BLOCKS, 256, 0, st, *in, S, *out, ctx->d_status);
@@ -306,7 +306,7 @@ extern "C" int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_
     fuz_launch(ctx, k_of_stage3, 148 * 8, 128, 0, st, *in, S, *out, ignore, contained, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_of_stage3");
     // counts beyond 2 * n_groups are 0 (memset): scanning 2 * cap_groups entries leaves ooff[2 n_groups] = total
-    if ((rc = fuz_scan_i32(ctx, S.ocnt, S.ooff, 2 * out->cap_groups, nullptr, FUZ_FIN_NONE, 0))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, S.ocnt, S.ooff, 2 * out->cap_groups))) return rc;
     fuz_launch(ctx, k_of_emit, FUZ_GRID_BLOCKS, 256, 0, st, *in, S, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_of_emit");
     return FUZ_OK;

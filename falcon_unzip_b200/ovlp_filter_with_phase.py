@@ -105,11 +105,10 @@ class PhaseTable:
         return f
 
 
-def _device_filter(L: Lines, tab: PhaseTable, max_diff: int, max_ovlp: int, min_ovlp: int, min_len: int, bestn: int, stage: int,
-                   ignore_in: Optional[np.ndarray] = None, contained_in: Optional[np.ndarray] = None) -> dict:
+def _upload(L: Lines, tab: PhaseTable, ignore_in: Optional[np.ndarray] = None, contained_in: Optional[np.ndarray] = None) -> dict:
+    """Columns and tables as device tensors (PyTorch owns the memory)."""
     import torch
-    eng = engine.get_engine()
-    dev = eng.device
+    dev = engine.get_engine().device
 
     def up(a):
         a = np.ascontiguousarray(a)
@@ -121,6 +120,18 @@ def _device_filter(L: Lines, tab: PhaseTable, max_diff: int, max_ovlp: int, min_
         d["ignore_in"] = up(ignore_in)
     if contained_in is not None:
         d["contained_in"] = up(contained_in)
+    return d
+
+
+def _device_filter(L: Lines, tab: PhaseTable, max_diff: int, max_ovlp: int, min_ovlp: int, min_len: int, bestn: int, stage: int,
+                   ignore_in: Optional[np.ndarray] = None, contained_in: Optional[np.ndarray] = None, d: Optional[dict] = None) -> dict:
+    import torch
+    eng = engine.get_engine()
+    dev = eng.device
+    if d is None:
+        d = _upload(L, tab, ignore_in, contained_in)
+    ignore_in = d.get("ignore_in")
+    contained_in = d.get("contained_in")
     n, nr = L.n, tab.n_reads
     cap_groups, cap_out = max(16, min(n, 2 * nr) + 16), max(1024, n // 2)
     for _ in range(4):

@@ -45,6 +45,19 @@ def test_fused_filter_matches_oracle(ofp, seed, pi):
     assert got == want and len(want) > 1000
 
 
+def test_fused_filter_large(ofp):
+    """~280 k lines: the multi-CTA scan (k_scan_wide) and reads with ~100 candidates per end."""
+    from falcon_unzip_b200 import synth_rr
+    from oracle import ovlp_oracle
+    s = synth_rr.generate_ovlp(n_reads=2500, seed=8)
+    assert sum(len(v) for v in s.las_lines.values()) > 200000
+    _load(ofp, s.las_lines, s.rid_phase_rows)
+    for p in (PARAMS[0], dict(max_diff=30, max_cov=70, min_cov=3, min_len=2500, bestn=5)):
+        want = ovlp_oracle.run_filter(list(s.las_lines.items()), _a2p(s.rid_phase_rows), **p)
+        got = ofp.run_ovlp_filter(list(s.las_lines), "db", p["max_diff"], p["max_cov"], p["min_cov"], p["min_len"], p["bestn"]).decode()
+        assert got == want and len(want) > 10000, p
+
+
 def test_golden_fixture(ofp):
     from falcon_unzip_b200 import synth_rr
     s = synth_rr.generate_ovlp(n_reads=700, seed=21)
