@@ -64,3 +64,20 @@ def table_order(keys: Iterable, hashes: Iterable[int]) -> List:
 def str_dict_order(keys: Iterable[str]) -> List[str]:
     keys = list(keys)
     return table_order(keys, [str_hash(k) for k in keys])
+
+
+def int_hash(i: int) -> int:
+    return -2 if i == -1 else i
+
+
+def tuple_hash(item_hashes) -> int:
+    """Objects/tupleobject.c:tuplehash (CPython 2.7, 64-bit long) from the hashes of the items."""
+    x, mult, n = 0x345678, 1000003, len(item_hashes)
+    for h in item_hashes:
+        n -= 1
+        x = ((x ^ (h & _M64)) * mult) & _M64
+        mult = (mult + 82520 + n + n) & _M64
+    x = (x + 97531) & _M64
+    if x >= 1 << 63:
+        x -= 1 << 64
+    return -2 if x == -1 else x

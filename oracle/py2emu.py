@@ -131,3 +131,21 @@ class Py27Float(float):
         return py27_float_str(float(self))
 
     __repr__ = __str__
+
+
+def py27_tuple_hash(t) -> int:
+    """Objects/tupleobject.c:tuplehash for tuples of int / str items."""
+    x, mult, n = 0x345678, 1000003, len(t)
+    for it in t:
+        n -= 1
+        h = py27_str_hash(it) if isinstance(it, str) else py27_int_hash(it)
+        x = ((x ^ (h & _M64)) * mult) & _M64
+        mult = (mult + 82520 + n + n) & _M64
+    x = (x + 97531) & _M64
+    if x >= 1 << 63:
+        x -= 1 << 64
+    return -2 if x == -1 else x
+
+
+def py27_tuple_dict_order(keys):
+    return py27_order(keys, py27_tuple_hash)

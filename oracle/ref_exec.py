@@ -243,3 +243,37 @@ def run_ovlp_filter(las_lines: Dict[str, List[str]], rid_phase_rows: Iterable[st
         for l in mod.filter_stage3(("db", fn, max_diff, max_cov, min_cov, min_len, ignore_all, contained, bestn))[1]:
             out.append(" ".join(l) + "\n")
     return "".join(out)
+
+
+def load_phasing_readmap() -> types.ModuleType:
+    """falcon_unzip/phasing_readmap.py: print chevron (:50), py2 int division (:23) and the dict order
+    of the output loop (:48) patched."""
+    with open(os.path.join(REF_ROOT, "falcon_unzip", "phasing_readmap.py")) as f:
+        src = f.read()
+    src = _sub(r"print >>\s*(\w+),\s*(.*)", r"print(\2, file=\1)", src, 1)
+    src = _sub(r"rid = int\(fid\.split\('/'\)\[1\]\)/10", "rid = int(fid.split('/')[1])//10", src, 1)
+    src = _sub(r"for arid, phase in arid_to_phase\.items\(\):",
+               "for arid, phase in [(k, arid_to_phase[k]) for k in py27_str_dict_order(arid_to_phase)]:", src, 1)
+    return _exec_patched(src, "ref_phasing_readmap", dict(py27_str_dict_order=py2emu.py27_str_dict_order))
+
+
+def load_get_read_hctg_map() -> types.ModuleType:
+    """falcon_unzip/get_read_hctg_map.py: print chevron (:59) and the dict / set orders (:55-57) patched."""
+    with open(os.path.join(REF_ROOT, "falcon_unzip", "get_read_hctg_map.py")) as f:
+        src = f.read()
+    src = _sub(r"print >>\s*(\w+),\s*(.*)", r"print(\2, file=\1)", src, 1)
+    src = _sub(r"for k in pread_to_contigs:", "for k in py27_tuple_dict_order(pread_to_contigs):", src, 1)
+    src = _sub(r"pread_to_contigs\.setdefault\( (k[12]), set\(\) \)", r"pread_to_contigs.setdefault( \1, Py27StrSet() )", src, 2)
+    return _exec_patched(src, "ref_get_read_hctg_map", dict(py27_tuple_dict_order=py2emu.py27_tuple_dict_order,
+                                                           Py27StrSet=py2emu.Py27StrSet))
+
+
+def get_rid_to_phase_all_source() -> types.ModuleType:
+    """The module-level task get_rid_to_phase_all of falcon_unzip/unzip.py:303-314, cut out of the file
+    (the rest of unzip.py needs pypeflow / ConfigParser and is not on the path)."""
+    with open(os.path.join(REF_ROOT, "falcon_unzip", "unzip.py")) as f:
+        src = f.read()
+    m = re.search(r"^def get_rid_to_phase_all\(self\):\n(?:(?:[ \t]+.*)?\n)+", src, flags=re.M)
+    if not m:
+        raise RuntimeError("get_rid_to_phase_all not found in unzip.py")
+    return _exec_patched(m.group(0), "ref_get_rid_to_phase_all", dict(fn=lambda p: p))
