@@ -272,6 +272,51 @@ def run_ovlp_filter(file_list: Sequence[str], db_fn: str, max_diff: int, max_cov
     return _format(L, tab, sel)
 
 
+def run_ovlp_filter_sharded(file_list: Sequence[str], db_fn: str, max_diff: int, max_cov: int, min_cov: int, min_len: int, bestn: int,
+                            rank: int, world_size: int, group=None) -> Optional[bytes]:
+    """run_ovlp_filter over `world_size` processes (one per GPU; torch.distributed initialised by the caller).
+    It mirrors the reference's three pool passes (:324-352), whose only cross-file products are two SETS:
+
+      stage 1   LAS files are dealt round-robin to the ranks; every rank judges the reads of its files
+      exchange  ignore set = union over files (:327-330): ONE all-reduce (max) of n_reads flag bytes
+      stage 2   contained reads of the rank's files, given the global ignore set
+      exchange  contained set = union over files (:337-339): ONE all-reduce (max) of n_reads flag bytes
+      stage 3   selection for the rank's files with both global sets; the text of every file is collected by
+                rank 0 and returned in fofn order (other ranks return None).
+
+    The rid -> phase table is replicated (every rank reads rid_phase_map)."""
+    import torch
+    import torch.distributed as dist
+    mine = list(range(rank, len(file_list), world_size))
+    L, tab = Lines([read_las_lines(db_fn, file_list[i]) for i in mine]), PhaseTable(arid2phase)
+    backend = dist.get_backend(group)
+    dev = engine.get_engine().device if backend == "nccl" else torch.device("cpu")
+
+    def union(flags: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(flags, dtype=np.uint8)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return t.cpu().numpy()
+    r1 = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, 0, 1)
+    ignore = union(r1["ignore"])
+    r2 = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, 0, 2, ignore_in=ignore)
+    contained = union(r2["contained"])
+    r3 = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, bestn, 3, ignore_in=ignore, contained_in=contained)
+    sel = _resolve_ties(L, tab, r3, ignore, contained, min_len, bestn)
+    # text per file (selected lines are in (file, line-group) order already)
+    per_file = {}
+    f_of = L.file[sel] if len(sel) else np.zeros(0, np.int32)
+    for k, i in enumerate(mine):
+        per_file[i] = _format(L, tab, sel[f_of == k])
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, per_file, group=group)
+    if rank != 0:
+        return None
+    merged = {}
+    for g in gathered:
+        merged.update(g)
+    return b"".join(merged[i] for i in range(len(file_list)))
+
+
 def parse_args(argv):
     parser = argparse.ArgumentParser(description="a simple multi-processes LAS ovelap data filter")
     parser.add_argument("--n_core", type=int, default=4, help="accepted for compatibility (the work runs on the GPU)")
