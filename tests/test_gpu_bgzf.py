@@ -215,3 +215,37 @@ def test_phase_bam_equals_host_decoded_path_and_oracle(eng, tmp_path, cfg):
             a = open(want[k]).read()
             assert open(files_b[name][k]).read() == a, (name, k)
             assert open(files_h[name][k]).read() == a, (name, k)
+
+
+def test_phase_bam_with_empty_contig_and_unmapped_tail(eng, tmp_path):
+    """A reference without reads in the middle, unmapped records (refID -1) behind the last contig, and a BAM
+    that holds no record at all: the device-decoded path must agree with the host-decoded one."""
+    import struct
+    from falcon_unzip_b200 import bam, engine, phasing, synth
+    sset = synth_set("tiny")
+    names = [sset.refs[0][0], "empty_ctg", sset.refs[1][0]]
+    refs = [sset.refs[0], ("empty_ctg", 5000), sset.refs[1]]
+    recs = np.asarray(sset.records).copy()
+    off = np.asarray(sset.rec_off)
+    for r in np.flatnonzero(np.asarray(sset.rec_ctg) == 1):          # second contig becomes refID 2
+        recs[off[r] + 4:off[r] + 8] = np.frombuffer(struct.pack("<i", 2), np.uint8)
+    tail = b"".join(bam.encode_record(-1, -1, "unmapped/%d" % i, 4, 0, [], "ACGT" * 50) for i in range(7))
+    fn, fa = str(tmp_path / "in.bam"), str(tmp_path / "ref.fa")
+    bam.write_bam(fn, refs, recs.tobytes() + tail)
+    with open(fa, "w") as f:
+        for (n, _l), seq in zip(refs, [sset.ref_seqs[0], "A" * 5000, sset.ref_seqs[1]]):
+            f.write(">%s\n%s\n" % (n, seq))
+    db = eng.ingest_bam(np.fromfile(fn, dtype=np.uint8))
+    assert db.n_rec == len(off) - 1 + 7 and db.n_mapped == len(off) - 1
+    cro = db.ctg_rec_off.cpu().numpy()
+    assert cro[1] == cro[2] and cro[3] == db.n_mapped
+    res_b, files_b = phasing.phase_bam(fn, fa, str(tmp_path / "dev"))
+    res_h, files_h = phasing.phase_contigs(recs, names, [sset.ref_seqs[0], "A" * 5000, sset.ref_seqs[1]], str(tmp_path / "host"))
+    assert res_b.n_sites == res_h.n_sites > 0 and res_b.n_reads == res_h.n_reads
+    for n in names:
+        for k in files_h[n]:
+            assert open(files_b[n][k]).read() == open(files_h[n][k]).read(), (n, k)
+    # no records at all
+    bam.write_bam(fn, refs, b"")
+    res_e, _ = phasing.phase_bam(fn, fa, str(tmp_path / "none"))
+    assert (res_e.n_sites, res_e.n_vmap, res_e.n_reads) == (0, 0, 0)
