@@ -267,8 +267,7 @@ def bam_ingest_leg(eng, sset, aligned, torch, reps: int = 3):
         return best, r
     t_ing, dbam = wall(lambda: eng.ingest_bam(image))
     n_rec = dbam.n_rec
-    eng.profile(True)
-    eng.ingest_bam(image)
+    eng.ingest_bam(image, profile=True)
     eng.sync()
     k = {name: ms for name, ms in eng.profile_report()}
     eng.profile(False)

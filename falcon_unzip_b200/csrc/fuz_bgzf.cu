@@ -164,10 +164,6 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
     const __grid_constant__ CrcTables ctab, fuz_status *st) {
     fuz_pdl_enter();
     __shared__ FuzInfTables tabs[FUZ_INF_WARPS];
-    __shared__ uint32_t s_crc[256], s_x2n[32];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = ctab.byte_tab[i];
-    if (threadIdx.x < 32) s_x2n[threadIdx.x] = ctab.x2n[threadIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * FUZ_INF_WARPS + warp;
     if (b >= n_blk) return;
@@ -191,22 +187,27 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
     if (rc == FUZ_INF_OK && io.pos != io.lim) rc = FUZ_INF_SIZE;
     __syncwarp();
     if (rc == FUZ_INF_OK && crc) {
-        // CRC-32 of the payload: 32 contiguous pieces, then log2(32) combine steps
+        // CRC-32 of the payload: 32 contiguous pieces, then log2(32) combine steps.  The decode tables of the
+        // warp are free now: their 4 KB hold the slicing-by-4 tables (one dependent lookup per word).
+        uint32_t (*s_crc)[256] = reinterpret_cast<uint32_t (*)[256]>(tabs[warp].lit);
+        for (int i = lane; i < 256; i += 32) {
+            uint32_t c = ctab.byte_tab[i];
+            s_crc[0][i] = c;
+            for (int k = 1; k < 4; k++) { c = (c >> 8) ^ ctab.byte_tab[c & 0xFFu]; s_crc[k][i] = c; }
+        }
+        __syncwarp();
         const int n = (int)(u1 - u0);
         const int piece = (n + 31) >> 5;
         const int lo = min(lane * piece, n), hi = min(lo + piece, n);
         uint32_t c = 0xFFFFFFFFu;
         const uint8_t *q = out + u0 + lo, *qe = out + u0 + hi;
-        while (q < qe && (reinterpret_cast<uintptr_t>(q) & 3)) c = s_crc[(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
+        while (q < qe && (reinterpret_cast<uintptr_t>(q) & 3)) c = s_crc[0][(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
 #pragma unroll 4
-        for (; q + 4 <= qe; q += 4) {                // aligned words: four table steps per load
-            const uint32_t w = __ldcg(reinterpret_cast<const uint32_t *>(q));
-            c = s_crc[(c ^ w) & 0xFFu] ^ (c >> 8);
-            c = s_crc[(c ^ (w >> 8)) & 0xFFu] ^ (c >> 8);
-            c = s_crc[(c ^ (w >> 16)) & 0xFFu] ^ (c >> 8);
-            c = s_crc[(c ^ (w >> 24)) & 0xFFu] ^ (c >> 8);
+        for (; q + 4 <= qe; q += 4) {                // aligned words
+            c ^= __ldcg(reinterpret_cast<const uint32_t *>(q));
+            c = s_crc[3][c & 0xFFu] ^ s_crc[2][(c >> 8) & 0xFFu] ^ s_crc[1][(c >> 16) & 0xFFu] ^ s_crc[0][c >> 24];
         }
-        while (q < qe) c = s_crc[(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
+        while (q < qe) c = s_crc[0][(c ^ __ldcg(q++)) & 0xFFu] ^ (c >> 8);
         c ^= 0xFFFFFFFFu;
         int len = hi - lo;
         for (int d = 1; d < 32; d <<= 1) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(FUZ_INF_WARPS * 32) k_bgzf_inflate(
             // crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
             uint32_t op = 1u << 31;
             for (int k = 3, m = len2; m; m >>= 1, k++)
-                if (m & 1) op = crc_mul(s_x2n[k & 31], op);
+                if (m & 1) op = crc_mul(ctab.x2n[k & 31], op);
             c = crc_mul(op, c) ^ c2;
             len += len2;
         }

@@ -77,9 +77,11 @@ template <class IO>
 struct FuzInflate {
     IO &io;
     FuzInfTables &T;
-    // bit reader: the stream bits [32 W + bp, 32 W + 64) sit in (lo, hi), W = io.word_pos() - 2.
-    // refill() keeps bp < 32, so peek() always returns 32 valid bits with one funnel shift.
-    uint32_t lo = 0, hi = 0;
+    // bit reader: the stream bits [32 W + bp, 32 W + 64) sit in (lo, hi), the following word in `ahead`,
+    // W = io.word_pos() - 3.  refill() keeps bp < 32, so peek() always returns 32 valid bits with one
+    // funnel shift; the word a refill fetches is not needed before the NEXT refill (its latency -- a
+    // shuffle on the device -- stays off the decode chain).
+    uint32_t lo = 0, hi = 0, ahead = 0;
     int bp = 0;
     int64_t end_byte = 0;
 
@@ -89,11 +91,12 @@ struct FuzInflate {
         const int mis = io.seek(first_byte);
         lo = io.next_word();
         hi = io.next_word();
+        ahead = io.next_word();
         bp = 8 * mis;
         end_byte = first_byte + n_bytes;
     }
     FUZ_HD void refill() {
-        if (bp >= 32) { lo = hi; hi = io.next_word(); bp -= 32; }
+        if (bp >= 32) { lo = hi; hi = ahead; ahead = io.next_word(); bp -= 32; }
     }
     FUZ_HD uint32_t peek() const {                               // needs bp < 32
 #ifdef __CUDA_ARCH__
@@ -109,8 +112,8 @@ struct FuzInflate {
         return v;
     }
     // first input byte no bit of which has been consumed (call with bp on a byte boundary)
-    FUZ_HD int64_t byte_pos() const { return (io.word_pos() - 2) * 4 + (bp >> 3); }
-    FUZ_HD bool input_ok() const { return (io.word_pos() - 2) * 4 + ((bp + 7) >> 3) <= end_byte; }
+    FUZ_HD int64_t byte_pos() const { return (io.word_pos() - 3) * 4 + (bp >> 3); }
+    FUZ_HD bool input_ok() const { return (io.word_pos() - 3) * 4 + ((bp + 7) >> 3) <= end_byte; }
 
     // Canonical Huffman decode tables from code lengths lens[0..n): the lookup table of 1 << tbits
     // entries for codes up to tbits long, plus count[] and sorted[] for the canonical search.

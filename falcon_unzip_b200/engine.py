@@ -426,7 +426,7 @@ class Engine:
                            int(st.n_accepted), int(st.aligned_bases))
 
     # ---- BAM ingest on the device (BGZF inflate + record index)
-    def ingest_bam(self, image, verify_crc: bool = True) -> DeviceBam:
+    def ingest_bam(self, image, verify_crc: bool = True, profile: bool = False) -> DeviceBam:
         """image: the bytes of a coordinate-sorted BAM file (numpy uint8, ideally pinned).  The
         compressed image crosses PCIe; inflate, record index and grouping by reference run on
         the device.  Only the header blocks are inflated on the host (names and lengths)."""
@@ -451,6 +451,8 @@ class Engine:
         raw = torch.empty(pad + total + 64, dtype=torch.uint8, device=dev)
         raw[pad + total:].zero_()
         torch.cuda.synchronize(dev)                      # torch's stream -> the context's stream
+        if profile:                                      # per-kernel times without the uploads above (bench legs)
+            self.profile(True)
         _lib.check(self.ctx, lib().fuz_bgzf_inflate(self.ctx, d_comp.data_ptr(), len(image), d_coff.data_ptr(), d_csize.data_ptr(),
                                                     d_uoff.data_ptr(), d_crc.data_ptr() if verify_crc else None, n_blk,
                                                     raw.data_ptr() + pad, total))
@@ -511,9 +513,10 @@ class Engine:
             l_name = db.raw[first_off + 12].to(torch.int64)
             width = int(l_name.max().item())
             idx = first_off[:, None] + 36 + torch.arange(width, device=dev)[None, :]
-            chars = db.raw[idx.clamp_(max=db.raw.numel() - 1)].cpu().numpy()
+            chars = np.ascontiguousarray(db.raw[idx.clamp_(max=db.raw.numel() - 1)].cpu().numpy())
             ln = l_name.cpu().numpy()
-            names = [chars[i, :ln[i] - 1].tobytes().decode("ascii") for i in range(total_nq)]
+            chars[np.arange(width)[None, :] >= (ln - 1)[:, None]] = 0          # NUL and everything behind it
+            names = chars.view("S%d" % width).ravel().astype("U").tolist()
             res.d2h_bytes += chars.nbytes
         return res, BamBatchInfo([r[0] for r in db.refs], ctg_len, nq, names)
 

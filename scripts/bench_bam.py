@@ -43,8 +43,7 @@ def main():
     out["ingest_ms"] = t * 1e3
     out["n_rec"] = db.n_rec
     assert np.array_equal(db.records(), np.asarray(sset.records)), "inflated stream differs"
-    eng.profile(True)
-    eng.ingest_bam(image)
+    eng.ingest_bam(image, profile=True)
     eng.sync()
     out["kernels_us"] = {k: round(v * 1e3, 1) for k, v in eng.profile_report()}
     eng.profile(False)
