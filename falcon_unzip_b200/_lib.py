@@ -89,7 +89,7 @@ class OvlpInput(C.Structure):
 class OvlpOutputs(C.Structure):
     _fields_ = [("d_ignore", C.c_void_p), ("d_contained", C.c_void_p), ("cap_groups", C.c_int64), ("d_grp_q", C.c_void_p),
                 ("d_grp_line", C.c_void_p), ("d_grp_ignore", C.c_void_p), ("d_grp_tie", C.c_void_p), ("d_grp_off", C.c_void_p), ("cap_out", C.c_int64),
-                ("d_out_line", C.c_void_p)]
+                ("d_out_line", C.c_void_p), ("d_cand", C.c_void_p)]
 
 
 class Status(C.Structure):

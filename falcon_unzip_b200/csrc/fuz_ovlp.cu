@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(128) k_of_stage3(fuz_ovlp_input in, OvlpScratc
                     cand = (b & 2) && (side == 0 ? s5 : s3) && !ignore[t] && !contained[t];
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, cand);
+                if (cand && out.d_cand) out.d_cand[i] = (uint8_t)(side + 1);
                 if (cand) {
                     const int k = n + __popc(m & ((1u << lane) - 1u));
                     if (k < OF_CAP) {
@@ -303,6 +304,7 @@ extern "C" int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_
     fuz_launch(ctx, k_of_fill_i32, FUZ_GRID_BLOCKS, 256, 0, st, S.rank, n, -1);
     FUZ_LAUNCH_CHECK(ctx, "k_of_fill_i32");
     FUZ_CUDA(ctx, cudaMemsetAsync(S.ocnt, 0, 4 * (size_t)(2 * out->cap_groups + 2), st));
+    if (out->d_cand && n) FUZ_CUDA(ctx, cudaMemsetAsync(out->d_cand, 0, (size_t)n, st));
     fuz_launch(ctx, k_of_stage3, 148 * 8, 128, 0, st, *in, S, *out, ignore, contained, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_of_stage3");
     // counts beyond 2 * n_groups are 0 (memset): scanning 2 * cap_groups entries leaves ooff[2 n_groups] = total

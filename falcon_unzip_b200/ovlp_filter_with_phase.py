@@ -138,7 +138,8 @@ def _device_filter(L: Lines, tab: PhaseTable, max_diff: int, max_ovlp: int, min_
         o = dict(ignore=torch.zeros(nr, dtype=torch.uint8, device=dev), contained=torch.zeros(nr, dtype=torch.uint8, device=dev),
                  grp_q=torch.zeros(cap_groups, dtype=torch.int32, device=dev), grp_line=torch.zeros(cap_groups, dtype=torch.int32, device=dev),
                  grp_ignore=torch.zeros(cap_groups, dtype=torch.uint8, device=dev), grp_tie=torch.zeros(cap_groups, dtype=torch.uint8, device=dev),
-                 grp_off=torch.zeros(cap_groups + 1, dtype=torch.int32, device=dev), out_line=torch.zeros(cap_out, dtype=torch.int32, device=dev))
+                 grp_off=torch.zeros(cap_groups + 1, dtype=torch.int32, device=dev), out_line=torch.zeros(cap_out, dtype=torch.int32, device=dev),
+                 cand=torch.zeros(max(n, 1), dtype=torch.uint8, device=dev))
         torch.cuda.synchronize(dev)
         fi = _lib.OvlpInput()
         fi.n_ovl, fi.n_reads = n, nr
@@ -161,6 +162,7 @@ def _device_filter(L: Lines, tab: PhaseTable, max_diff: int, max_ovlp: int, min_
             if stage == 3:
                 r.update(grp_tie=o["grp_tie"][:ng].cpu().numpy(), grp_off=o["grp_off"][:ng + 1].cpu().numpy(),
                          out_line=o["out_line"][:n_out].cpu().numpy())
+                r["cand"] = o["cand"][:n].cpu().numpy() if r["grp_tie"].any() else None
             return r
         if st.error == _lib.FUZ_E_CAPACITY and st.error_index == 10:
             cap_groups = int(st.reserved[0]) + 16
@@ -178,39 +180,28 @@ def _verdict(left: int, right: int, max_diff: int, max_ovlp: int, min_ovlp: int)
     return abs(left - right) > max_diff or left > max_ovlp or right > max_ovlp or left < min_ovlp or right < min_ovlp
 
 
-def _resolve_ties(L: Lines, tab: PhaseTable, r: dict, ignore: np.ndarray, contained: np.ndarray, min_len: int, bestn: int) -> np.ndarray:
-    """Selected lines with the groups flagged by the kernel re-sorted the way the reference sorts them:
-    tuples (-inphase, -len, range, token list) -- the token list decides among candidates that tie on
-    every number (:234,:275).  Groups without such ties come straight from the device."""
+def _resolve_ties(L: Lines, tab: PhaseTable, r: dict, bestn: int) -> np.ndarray:
+    """Selected lines, with the groups the kernel flagged re-sorted the way the reference sorts them: tuples
+    (-inphase, -len, range, token list) -- the token list decides among candidates that tie on every number
+    (:234,:275).  The candidates of both ends come from the device (d_cand); only their order is settled here.
+    Groups without such ties come straight from the device."""
     tie = np.flatnonzero(r["grp_tie"])
     if len(tie) == 0:
         return r["out_line"].astype(np.int64)
-    a, out, parts, at = L.a, r["out_line"], [], 0
+    a, out, cand, parts, at = L.a, r["out_line"], r["cand"], [], 0
     for g in tie.tolist():
         lo = int(r["grp_line"][g])
         hi = int(r["grp_line"][g + 1]) if g + 1 < r["n_groups"] else L.n      # passing lines in [lo, hi) all belong to g
         q = int(r["grp_q"][g])
-        ends: Tuple[list, list] = ([], [])
-        for i in range(lo, hi):
-            t = int(a["t"][i])
-            if int(a["q"][i]) != q or not (0 <= t < tab.n_reads) or not tab.in_map[t]:
-                continue
-            if tab.ctg[t] != tab.ctg[q] or (tab.blk[t] == tab.blk[q] and tab.ph[t] != tab.ph[q]):
-                continue
-            if contained[q] or contained[t] or ignore[q] or ignore[t]:
-                continue
-            if not (a["flags"][i] & 1) or a["ql"][i] < min_len or a["tl"][i] < min_len:
-                continue
-            five = a["qs"][i] == 0
-            if not five and a["qe"][i] != a["ql"][i]:
-                continue
-            inphase = 1 if (tab.ctg[t], tab.blk[t], tab.ph[t]) == (tab.ctg[q], tab.blk[q], tab.ph[q]) else 0
-            ends[0 if five else 1].append((-inphase, -int(a["len"][i]), int(a["tl"][i]) - (int(a["te"][i]) - int(a["ts"][i])),
-                                           L.tokens(i), i))
         sel = []
-        for cands in ends:
-            cands.sort(key=lambda c: c[:4])
-            for k, c in enumerate(cands):
+        for side in (1, 2):
+            rows = []
+            for i in (lo + np.flatnonzero(cand[lo:hi] == side)).tolist():
+                t = int(a["t"][i])
+                inphase = 1 if (tab.ctg[t], tab.blk[t], tab.ph[t]) == (tab.ctg[q], tab.blk[q], tab.ph[q]) else 0
+                rows.append((-inphase, -int(a["len"][i]), int(a["tl"][i]) - (int(a["te"][i]) - int(a["ts"][i])), L.tokens(i), i))
+            rows.sort(key=lambda c: c[:4])
+            for k, c in enumerate(rows):
                 sel.append(c[4])
                 if k >= bestn and c[2] > 1000:
                     break
@@ -260,7 +251,7 @@ def filter_stage3(input_):
     L, tab = Lines([read_las_lines(db_fn, fn)]), PhaseTable(arid2phase)
     ig, ct = tab.flags_of(ignore_set), tab.flags_of(contained_set)
     r = _device_filter(L, tab, max_diff, max_ovlp, min_ovlp, min_len, bestn, 3, ignore_in=ig, contained_in=ct)
-    sel = _resolve_ties(L, tab, r, ig, ct, min_len, bestn)
+    sel = _resolve_ties(L, tab, r, bestn)
     return fn, [x.split(" ") for x in _format(L, tab, sel).decode("ascii").splitlines()]
 
 
@@ -268,7 +259,7 @@ def run_ovlp_filter(file_list: Sequence[str], db_fn: str, max_diff: int, max_cov
     """main() (:324-352) for all LAS files in one device call -> the text the reference prints."""
     L, tab = Lines([read_las_lines(db_fn, fn) for fn in file_list]), PhaseTable(arid2phase)
     r = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, bestn, 3)
-    sel = _resolve_ties(L, tab, r, r["ignore"], r["contained"], min_len, bestn)
+    sel = _resolve_ties(L, tab, r, bestn)
     return _format(L, tab, sel)
 
 
@@ -301,7 +292,7 @@ def run_ovlp_filter_sharded(file_list: Sequence[str], db_fn: str, max_diff: int,
     r2 = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, 0, 2, ignore_in=ignore)
     contained = union(r2["contained"])
     r3 = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, bestn, 3, ignore_in=ignore, contained_in=contained)
-    sel = _resolve_ties(L, tab, r3, ignore, contained, min_len, bestn)
+    sel = _resolve_ties(L, tab, r3, bestn)
     # text per file (selected lines are in (file, line-group) order already)
     per_file = {}
     f_of = L.file[sel] if len(sel) else np.zeros(0, np.int32)

@@ -312,6 +312,8 @@ typedef struct {
     int32_t *d_grp_off;           /* [cap_groups + 1] slice of d_out_line of every group           */
     int64_t cap_out;
     int32_t *d_out_line;          /* [cap_out] stage 3: selected lines (index into the input) in output order */
+    uint8_t *d_cand;              /* [n_ovl] or NULL: stage-3 candidates, 1 = 5' list, 2 = 3' list (:265-273);
+                                   * what the host needs to re-sort a group flagged in d_grp_tie      */
 } fuz_ovlp_outputs;
 
 /* status after the call: reserved[0] = groups, reserved[1] = selected lines, reserved[2] = selected

@@ -53,7 +53,7 @@ def main():
         r = run()
     torch.cuda.synchronize()
     call_ms = 1e3 * (time.perf_counter() - t0) / a.steps      # device-resident columns; includes output allocation and D2H of the results
-    sel = ofp._resolve_ties(L, tab, r, r["ignore"], r["contained"], p["min_len"], p["bestn"])
+    sel = ofp._resolve_ties(L, tab, r, p["bestn"])
     t0 = time.perf_counter()
     text = ofp._format(L, tab, sel)
     fmt_s = time.perf_counter() - t0

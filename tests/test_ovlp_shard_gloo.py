@@ -25,7 +25,7 @@ def _fake_device_filter(L, tab, max_diff, max_ovlp, min_ovlp, min_len, bestn, st
                     ignore[int(x)] = 1
     out = dict(n_groups=0, ignore=ignore, contained=np.zeros(tab.n_reads, np.uint8), grp_q=np.zeros(0, np.int32),
                grp_line=np.zeros(0, np.int32), grp_ignore=np.zeros(0, np.uint8), grp_tie=np.zeros(0, np.uint8),
-               grp_off=np.zeros(1, np.int32), out_line=np.zeros(0, np.int32))
+               grp_off=np.zeros(1, np.int32), out_line=np.zeros(0, np.int32), cand=None)
     if stage == 1:
         return out
     contained = out["contained"] if contained_in is None else np.asarray(contained_in)
