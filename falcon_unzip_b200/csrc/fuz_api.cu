@@ -7,8 +7,8 @@
 int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out);
 int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row_off_valid);
 int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_valid);
-int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
-                   bool dup_valid);
+int fuz_reads_csr(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out, bool dup_valid);
+int fuz_reads_vote(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *out);
 int fuz_assign_qids_impl(fuz_ctx *ctx, const uint8_t *d_rec_buf, const int64_t *d_rec_off, int32_t n_rec, int64_t rec_bytes,
                          const int32_t *d_ctg_rec_off, int32_t n_ctg, int32_t *d_rec_qid, int32_t *d_ctg_nq,
                          int64_t *d_name_first, int32_t *d_ctg_slots, uint8_t *scratch);
@@ -69,8 +69,27 @@ extern "C" int fuz_phase_batch(fuz_ctx *ctx, const fuz_batch *in_, fuz_outputs *
     // the row range of every site (het call) and the duplicate flags (association) stay in
     // the context's inter-stage buffer and are reused by the later stages
     if ((rc = fuz_association_impl(ctx, in->n_ctg, out, true))) return rc;
-    if ((rc = fuz_blocks_impl(ctx, in->n_ctg, out, true))) return rc;
-    return fuz_reads_impl(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out, true);
+    // The per-read lists of the read stage need the variant_map rows and the duplicate flags only: they are
+    // built on the side stream while the block stage (one CTA per contig, most SMs idle) runs on the main one.
+    const bool side = !ctx->profile;
+    cudaStream_t main_stream = ctx->stream;
+    if (side) {
+        if (!ctx->aux_stream) {
+            FUZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            FUZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            FUZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        FUZ_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+        FUZ_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        ctx->stream = ctx->aux_stream;
+    }
+    rc = fuz_reads_csr(ctx, in->n_ctg, in->d_ctg_nq, in->total_nq, out, true);
+    ctx->stream = main_stream;
+    if (side) cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+    const int rc_blocks = rc ? rc : fuz_blocks_impl(ctx, in->n_ctg, out, true);
+    if (side) cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
+    if (rc_blocks) return rc_blocks;
+    return fuz_reads_vote(ctx, in->n_ctg, in->total_nq, out);
 }
 
 static int ensure_stage(fuz_ctx *ctx, size_t dev_bytes, size_t pin_bytes) {

@@ -69,6 +69,7 @@ extern "C" int fuz_ctx_destroy(fuz_ctx *ctx) {
     if (ctx->keep) cudaFree(ctx->keep);
     if (ctx->qid_buf) cudaFree(ctx->qid_buf);
     if (ctx->scan_state) cudaFree(ctx->scan_state);
+    if (ctx->reads_buf) cudaFree(ctx->reads_buf);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

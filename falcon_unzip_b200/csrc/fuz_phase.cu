@@ -692,11 +692,12 @@ __global__ void k_rd_init(ReadScratch R) {
     }
 }
 
-// rows that can vote: first occurrence of (site, allele, q_id), site inside a block
+// rows that can vote: first occurrence of (site, allele, q_id).  Whether the site lies inside a block is
+// decided later (k_vote): the per-read lists do not depend on the phasing result, so they can be built
+// while the block stage runs.
 __device__ __forceinline__ int voting_gq(int i, const ReadScratch &R, const fuz_outputs &O, fuz_status *st) {
     if (R.dup[i]) return -1;
     const int s = O.d_vm_site[i];
-    if (O.d_ph_block[s] <= 0) return -1;
     const int c = O.d_site_ctg[s];
     const int q = O.d_vm_qid[i];
     if (q < 0 || q >= R.ctg_q_off[c + 1] - R.ctg_q_off[c]) { fuz_raise(st, FUZ_E_FORMAT, i); return -1; }
@@ -719,13 +720,8 @@ __global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
     const int n_vmap = (int)st->n_vmap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vmap; i += gridDim.x * blockDim.x) {
         int gq = voting_gq(i, R, O, st);
-        if (gq >= 0) {
-            // entry = (block << 1) | phase of the variant: phase 0 if the row's base is the
-            // hap-0 allele of the site's state (phasing.py:462-463)
-            const int s = O.d_vm_site[i];
-            const uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
-            R.q_ent[R.q_off[gq] + atomicAdd(&R.q_cur[gq], 1)] = (O.d_ph_block[s] << 1) | (O.d_vm_base[i] == h0 ? 0 : 1);
-        }
+        if (gq >= 0)       // entry = (site << 2) | base; k_vote turns it into (block << 1) | phase
+            R.q_ent[R.q_off[gq] + atomicAdd(&R.q_cur[gq], 1)] = (O.d_vm_site[i] << 2) | (int)O.d_vm_base[i];
     }
 }
 
@@ -736,6 +732,20 @@ __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_st
     if (st->error) return;
     for (int64_t gq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gq < R.total_nq; gq += (int64_t)gridDim.x * blockDim.x) {
         const int e0 = R.q_off[gq], e1 = R.q_off[gq + 1];
+        if (!fill) {
+            // first pass: entries become (block << 1) | phase of the variant -- phase 0 if the row's base is
+            // the hap-0 allele of the site's state (phasing.py:462-463); 0 for a site outside every block
+            for (int e = e0; e < e1; e++) {
+                const int v = R.q_ent[e], s = v >> 2;
+                const int blk = O.d_ph_block[s];
+                int packed = 0;
+                if (blk > 0) {
+                    const uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
+                    packed = (blk << 1) | ((uint8_t)(v & 3) == h0 ? 0 : 1);
+                }
+                R.q_ent[e] = packed;
+            }
+        }
         int rows = 0, last = 0;
         int64_t out = fill ? R.pr_off[gq] : 0;
         int c = -1;
@@ -853,22 +863,40 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_v
     return FUZ_OK;
 }
 
-int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
-                   bool dup_valid) {
-    cudaStream_t st = ctx->stream;
+// The read stage in two halves.  fuz_reads_csr builds the per-read lists of voting rows; it needs the
+// variant_map rows and the duplicate flags only, so fuz_phase_batch runs it on the side stream while the
+// block stage runs.  fuz_reads_vote needs the blocks.  Scratch comes from a buffer of its own (the arena
+// belongs to the stage running on the main stream).
+static int reads_scratch(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *out, ReadScratch &R) {
     const int64_t cs = out->cap_sites, cv = out->cap_vmap;
-    ReadScratch R;
     R.total_nq = total_nq;
     FuzLayout L;
-    size_t o_cq = L.add(4 * (size_t)(n_ctg + 2));
-    size_t o_qc = L.add(4 * (size_t)(total_nq + 2)), o_qo = L.add(4 * (size_t)(total_nq + 2)), o_qcur = L.add(4 * (size_t)(total_nq + 1));
-    size_t o_qe = L.add(4 * (size_t)(cv + 1)), o_pc = L.add(4 * (size_t)(total_nq + 2)), o_po = L.add(4 * (size_t)(total_nq + 2));
-    int rc = fuz_arena_commit(ctx, L);
+    const size_t o_cq = L.add(4 * (size_t)(n_ctg + 2));
+    const size_t o_qc = L.add(4 * (size_t)(total_nq + 2)), o_qo = L.add(4 * (size_t)(total_nq + 2)), o_qcur = L.add(4 * (size_t)(total_nq + 1));
+    const size_t o_qe = L.add(4 * (size_t)(cv + 1)), o_pc = L.add(4 * (size_t)(total_nq + 2)), o_po = L.add(4 * (size_t)(total_nq + 2));
+    if (L.off > ctx->reads_cap) {
+        FUZ_CUDA(ctx, cudaDeviceSynchronize());
+        if (ctx->reads_buf) FUZ_CUDA(ctx, cudaFree(ctx->reads_buf));
+        ctx->reads_buf = nullptr; ctx->reads_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->reads_buf, L.off + (L.off >> 2));
+        if (e != cudaSuccess) return fuz_fail(ctx, FUZ_E_CUDA, "read-stage buffer of %zu bytes: %s", L.off, cudaGetErrorString(e));
+        ctx->reads_cap = L.off + (L.off >> 2);
+    }
+    int rc = fuz_keep_commit(ctx, cs, cv, &R.row_off, &R.dup);
     if (rc) return rc;
-    if ((rc = fuz_keep_commit(ctx, cs, cv, &R.row_off, &R.dup))) return rc;
-    R.ctg_q_off = fuz_at<int32_t>(ctx, o_cq);
-    R.q_cnt = fuz_at<int32_t>(ctx, o_qc); R.q_off = fuz_at<int32_t>(ctx, o_qo); R.q_cur = fuz_at<int32_t>(ctx, o_qcur);
-    R.q_ent = fuz_at<int32_t>(ctx, o_qe); R.pr_cnt = fuz_at<int32_t>(ctx, o_pc); R.pr_off = fuz_at<int32_t>(ctx, o_po);
+    uint8_t *base = ctx->reads_buf;
+    R.ctg_q_off = reinterpret_cast<int32_t *>(base + o_cq);
+    R.q_cnt = reinterpret_cast<int32_t *>(base + o_qc); R.q_off = reinterpret_cast<int32_t *>(base + o_qo);
+    R.q_cur = reinterpret_cast<int32_t *>(base + o_qcur); R.q_ent = reinterpret_cast<int32_t *>(base + o_qe);
+    R.pr_cnt = reinterpret_cast<int32_t *>(base + o_pc); R.pr_off = reinterpret_cast<int32_t *>(base + o_po);
+    return FUZ_OK;
+}
+
+int fuz_reads_csr(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out, bool dup_valid) {
+    cudaStream_t st = ctx->stream;
+    ReadScratch R;
+    int rc = reads_scratch(ctx, n_ctg, total_nq, out, R);
+    if (rc) return rc;
     if ((rc = fuz_scan_i32(ctx, d_ctg_nq, R.ctg_q_off, n_ctg, nullptr, FUZ_FIN_NONE, 0))) return rc;
     if (!dup_valid) {
         fuz_launch(ctx, k_site_rowoff, FUZ_GRID_BLOCKS, 256, 0, st, out->d_vm_site, R.row_off, ctx->d_status);
@@ -883,12 +911,26 @@ int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t
     if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, FUZ_FIN_NONE, 0))) return rc;
     fuz_launch(ctx, k_q_fill, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_fill");
+    return FUZ_OK;
+}
+
+int fuz_reads_vote(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *out) {
+    cudaStream_t st = ctx->stream;
+    ReadScratch R;
+    int rc = reads_scratch(ctx, n_ctg, total_nq, out, R);
+    if (rc) return rc;
     fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
     if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, FUZ_FIN_READS, out->cap_reads))) return rc;
     fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
     return FUZ_OK;
+}
+
+int fuz_reads_impl(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t total_nq, fuz_outputs *out,
+                   bool dup_valid) {
+    int rc = fuz_reads_csr(ctx, n_ctg, d_ctg_nq, total_nq, out, dup_valid);
+    return rc ? rc : fuz_reads_vote(ctx, n_ctg, total_nq, out);
 }
 
 static int set_counts(fuz_ctx *ctx, int64_t n_sites, int64_t n_vmap, int64_t n_atable) {
