@@ -725,6 +725,25 @@ __global__ void k_q_fill(ReadScratch R, fuz_outputs O, fuz_status *st) {
     }
 }
 
+// One thread per entry of the per-read lists: (site << 2) | base becomes (block << 1) | phase of the
+// variant -- phase 0 if the row's base is the hap-0 allele of the site's state (phasing.py:462-463); 0 for a
+// site outside every block.  Runs after the block stage (the lists themselves are built beside it).
+__global__ void k_q_pack(ReadScratch R, fuz_outputs O, fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int n_ent = R.q_off[R.total_nq];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += gridDim.x * blockDim.x) {
+        const int v = R.q_ent[e], s = v >> 2;
+        const int blk = O.d_ph_block[s];
+        int packed = 0;
+        if (blk > 0) {
+            const uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
+            packed = (blk << 1) | ((uint8_t)(v & 3) == h0 ? 0 : 1);
+        }
+        R.q_ent[e] = packed;
+    }
+}
+
 // One thread per read: distinct phased variants -> (block, phase) counts; blocks in
 // ascending id; a row when |n0 - n1| > 1 (phasing.py:465-480).  fill = 0 counts rows.
 __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_status *st) {
@@ -732,20 +751,6 @@ __global__ void k_vote(ReadScratch R, fuz_outputs O, int n_ctg, int fill, fuz_st
     if (st->error) return;
     for (int64_t gq = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gq < R.total_nq; gq += (int64_t)gridDim.x * blockDim.x) {
         const int e0 = R.q_off[gq], e1 = R.q_off[gq + 1];
-        if (!fill) {
-            // first pass: entries become (block << 1) | phase of the variant -- phase 0 if the row's base is
-            // the hap-0 allele of the site's state (phasing.py:462-463); 0 for a site outside every block
-            for (int e = e0; e < e1; e++) {
-                const int v = R.q_ent[e], s = v >> 2;
-                const int blk = O.d_ph_block[s];
-                int packed = 0;
-                if (blk > 0) {
-                    const uint8_t h0 = O.d_ph_state[s] == 0 ? O.d_site_al[2 * s] : O.d_site_al[2 * s + 1];
-                    packed = (blk << 1) | ((uint8_t)(v & 3) == h0 ? 0 : 1);
-                }
-                R.q_ent[e] = packed;
-            }
-        }
         int rows = 0, last = 0;
         int64_t out = fill ? R.pr_off[gq] : 0;
         int c = -1;
@@ -919,6 +924,8 @@ int fuz_reads_vote(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *o
     ReadScratch R;
     int rc = reads_scratch(ctx, n_ctg, total_nq, out, R);
     if (rc) return rc;
+    fuz_launch(ctx, k_q_pack, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_q_pack");
     fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
     if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, FUZ_FIN_READS, out->cap_reads))) return rc;
