@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import _lib, engine
+from . import _lib, engine, la4falcon
 from ._lib import FuzError, lib
 
 arid2phase: Dict[str, Tuple[str, str, str]] = {}
@@ -113,8 +113,11 @@ def _upload(L: Lines, tab: PhaseTable, ignore_in: Optional[np.ndarray] = None, c
     def up(a):
         a = np.ascontiguousarray(a)
         return torch.from_numpy(a).to(dev) if a.size else torch.zeros(1, dtype=getattr(torch, a.dtype.name), device=dev)
-    d = {k: up(L.a[k]) for k in _COLS + ("flags",)}
-    d["file"] = up(L.file)
+    if hasattr(L, "d"):                                   # parsed on the device: the columns are there already
+        d = {k: L.d[k] for k in _COLS + ("flags", "file")}
+    else:
+        d = {k: up(L.a[k]) for k in _COLS + ("flags",)}
+        d["file"] = up(L.file)
     d.update(in_map=up(tab.in_map), ph_ctg=up(tab.ctg), ph_block=up(tab.blk), ph_phase=up(tab.ph))
     if ignore_in is not None:
         d["ignore_in"] = up(ignore_in)
@@ -212,9 +215,14 @@ def _resolve_ties(L: Lines, tab: PhaseTable, r: dict, bestn: int) -> np.ndarray:
     return np.concatenate([p.astype(np.int64) for p in parts])
 
 
-def _format(L: Lines, tab: PhaseTable, sel: np.ndarray) -> bytes:
+def _format(L, tab: PhaseTable, sel: np.ndarray) -> bytes:
     sel = np.ascontiguousarray(sel, dtype=np.int64)
-    args = (L.text, L.a["off"].ctypes.data, L.a["llen"].ctypes.data, L.a["q"].ctypes.data, L.a["t"].ctypes.data, sel.ctypes.data,
+    if hasattr(L, "gather"):                              # columns live on the device: fetch the selected lines only
+        g = L.gather(("off", "llen", "q", "t"), sel)
+    else:
+        g = {k: np.ascontiguousarray(L.a[k][sel]) for k in ("off", "llen", "q", "t")}
+    idx = np.arange(len(sel), dtype=np.int64)
+    args = (L.text, g["off"].ctypes.data, g["llen"].ctypes.data, g["q"].ctypes.data, g["t"].ctypes.data, idx.ctypes.data,
             len(sel), tab.phase_text, tab.phase_off.ctypes.data)
     size = lib().fuz_host_format_ovlp(*args, None, 0)
     if size < 0:
@@ -255,9 +263,13 @@ def filter_stage3(input_):
     return fn, [x.split(" ") for x in _format(L, tab, sel).decode("ascii").splitlines()]
 
 
-def run_ovlp_filter(file_list: Sequence[str], db_fn: str, max_diff: int, max_cov: int, min_cov: int, min_len: int, bestn: int) -> bytes:
-    """main() (:324-352) for all LAS files in one device call -> the text the reference prints."""
-    L, tab = Lines([read_las_lines(db_fn, fn) for fn in file_list]), PhaseTable(arid2phase)
+def run_ovlp_filter(file_list: Sequence[str], db_fn: str, max_diff: int, max_cov: int, min_cov: int, min_len: int, bestn: int,
+                    device_parse: bool = True) -> bytes:
+    """main() (:324-352) for all LAS files in one device call -> the text the reference prints.  The LA4Falcon
+    text is parsed on the device (fuz_parse_la4falcon); device_parse=False takes the host parser."""
+    blobs = [read_las_lines(db_fn, fn) for fn in file_list]
+    L = la4falcon.DeviceLines(blobs, require_id9=True) if device_parse else Lines(blobs)
+    tab = PhaseTable(arid2phase)
     r = _device_filter(L, tab, max_diff, max_cov, min_cov, min_len, bestn, 3)
     sel = _resolve_ties(L, tab, r, bestn)
     return _format(L, tab, sel)
@@ -279,8 +291,10 @@ def run_ovlp_filter_sharded(file_list: Sequence[str], db_fn: str, max_diff: int,
     import torch
     import torch.distributed as dist
     mine = list(range(rank, len(file_list), world_size))
-    L, tab = Lines([read_las_lines(db_fn, file_list[i]) for i in mine]), PhaseTable(arid2phase)
     backend = dist.get_backend(group)
+    blobs = [read_las_lines(db_fn, file_list[i]) for i in mine]
+    L = la4falcon.DeviceLines(blobs, require_id9=True) if backend == "nccl" else Lines(blobs)
+    tab = PhaseTable(arid2phase)
     dev = engine.get_engine().device if backend == "nccl" else torch.device("cpu")
 
     def union(flags: np.ndarray) -> np.ndarray:
@@ -295,7 +309,7 @@ def run_ovlp_filter_sharded(file_list: Sequence[str], db_fn: str, max_diff: int,
     sel = _resolve_ties(L, tab, r3, bestn)
     # text per file (selected lines are in (file, line-group) order already)
     per_file = {}
-    f_of = L.file[sel] if len(sel) else np.zeros(0, np.int32)
+    f_of = (L.gather(("file",), sel)["file"] if hasattr(L, "gather") else L.file[sel]) if len(sel) else np.zeros(0, np.int32)
     for k, i in enumerate(mine):
         per_file[i] = _format(L, tab, sel[f_of == k])
     gathered = [None] * world_size

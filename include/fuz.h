@@ -321,6 +321,19 @@ typedef struct {
  * candidates on one side of a read (max_cov beyond what the kernel holds in shared memory). */
 int fuz_ovlp_filter(fuz_ctx *ctx, const fuz_ovlp_input *in, fuz_ovlp_outputs *out);
 
+/* ---- LA4Falcon text -> columns on the device (rr_hctg_track.py:38-44, ovlp_filter_with_phase.py:60-62,95-99) ---- */
+/* Device form of fuz_host_parse_la4falcon(_mo): d_text = the concatenated output of `LA4Falcon -m / -mo`.
+ * Fills the columns of fuz_rr_input / fuz_ovlp_input (same meaning as the host parsers), d_line_off / d_line_len =
+ * place of every line in the text; blank lines are skipped.  d_flags bit 7: the identity column of that line is
+ * not a plain decimal of at most 15 significant digits and has to be evaluated by the host (float(col 3) < 90).
+ * Asynchronous; status.reserved[0] = lines, reserved[1] = lines flagged for the host.  FUZ_E_CAPACITY (index 12):
+ * more than `cap` lines; FUZ_E_FORMAT: a line the reference would raise on (error_index = line, reserved[3] =
+ * 1 fewer than 12 columns, 2 not an integer, 3 id not a %09d id (require_id9), 4 identity column). */
+int fuz_parse_la4falcon(fuz_ctx *ctx, const uint8_t *d_text, int64_t n_bytes, int64_t cap, int32_t require_id9,
+                        int32_t *d_q, int32_t *d_t, int32_t *d_len, int32_t *d_qs, int32_t *d_qe, int32_t *d_ql,
+                        int32_t *d_ts, int32_t *d_te, int32_t *d_tl, uint8_t *d_flags, int64_t *d_line_off,
+                        int32_t *d_line_len);
+
 /* ---- host helpers (no CUDA) ------------------------------------------------------ */
 /* Walk the block_size chain of a record buffer.  rec_off needs n_rec+1 slots; returns
  * the record count through n_rec (call with rec_off = NULL to count only). */
