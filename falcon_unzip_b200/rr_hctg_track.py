@@ -21,7 +21,7 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from . import _lib, engine, py2compat
+from . import _lib, engine, la4falcon, py2compat
 from ._lib import FuzError, lib
 
 
@@ -118,20 +118,31 @@ class _Tables:
             self.ph_block[r], self.ph_phase[r] = ph[1], ph[2]
 
 
-def _track_device(q, t, ln, tl, file_idx, tab: _Tables, min_len: int, bestn: int, filter_only: bool = False):
-    """fuz_rr_track on the arrays -> (keep, hp_n, hp_len, hp_q, vt_off, vt_ctg, vt_count, vt_score)."""
+def _track_device(q, t, ln, tl, file_idx, tab: _Tables, min_len: int, bestn: int, filter_only: bool = False, lines=None):
+    """fuz_rr_track on the arrays -> (keep, hp_n, hp_len, hp_q, vt_off, vt_ctg, vt_count, vt_score).
+    lines: a la4falcon.DeviceLines whose columns are on the device already (q, t, ln, tl, file_idx ignored)."""
     import torch
     eng = engine.get_engine()
     dev = eng.device
-    n_ovl, n_reads = len(q), tab.n_reads
-    if len(q) and (int(q.min()) < 0 or int(t.min()) < 0 or int(max(q.max(), t.max())) >= n_reads):
-        raise IndexError("list index out of range (read id beyond rawread_ids; rr_hctg_track.py:50,54)")
+    n_reads = tab.n_reads
 
     def up(a, dt):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev) if len(a) else torch.zeros(1, dtype=getattr(
             torch, np.dtype(dt).name), device=dev)
-    d = dict(q=up(q, np.int32), t=up(t, np.int32), len=up(ln, np.int32), tlen=up(tl, np.int32), file=up(file_idx, np.int32),
-             in_map=up(tab.in_map, np.uint8), ph_ctg=up(tab.ph_ctg, np.int32), ph_block=up(tab.ph_block, np.int32),
+    if lines is not None:
+        n_ovl = lines.n
+        d = dict(q=lines.d["q"], t=lines.d["t"], len=lines.d["len"], tlen=lines.d["tl"], file=lines.d["file"])
+        if n_ovl:
+            lo = int(torch.minimum(d["q"][:n_ovl].min(), d["t"][:n_ovl].min()).item())
+            hi = int(torch.maximum(d["q"][:n_ovl].max(), d["t"][:n_ovl].max()).item())
+            if lo < 0 or hi >= n_reads:
+                raise IndexError("list index out of range (read id beyond rawread_ids; rr_hctg_track.py:50,54)")
+    else:
+        n_ovl = len(q)
+        if len(q) and (int(q.min()) < 0 or int(t.min()) < 0 or int(max(q.max(), t.max())) >= n_reads):
+            raise IndexError("list index out of range (read id beyond rawread_ids; rr_hctg_track.py:50,54)")
+        d = dict(q=up(q, np.int32), t=up(t, np.int32), len=up(ln, np.int32), tlen=up(tl, np.int32), file=up(file_idx, np.int32))
+    d.update(in_map=up(tab.in_map, np.uint8), ph_ctg=up(tab.ph_ctg, np.int32), ph_block=up(tab.ph_block, np.int32),
              ph_phase=up(tab.ph_phase, np.int32), rc_off=up(tab.rc_off, np.int32), rc_ctg=up(tab.rc_ctg, np.int32))
     b = max(bestn, 1)
     cap_votes = max(1024, 4 * n_reads)
@@ -268,10 +279,12 @@ def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawrea
     are replayed inside the kernel)."""
     rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
     files = sorted(file_list)
-    q, t, ln, tl, file_idx = _parse_files(db_fn, files, range(len(files)))
-    keep, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn)
-    kept = keep.astype(bool)
-    rows = [_format_bread(b, tab, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score) for b in _bread_order(t[kept], file_idx[kept])]
+    # the LA4Falcon text of all files is parsed on the device; the columns stay there for fuz_rr_track
+    lines = la4falcon.DeviceLines([read_las_lines(db_fn, fn) for fn in files], require_id9=False)
+    keep, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(None, None, None, None, None, tab, min_len, bestn,
+                                                                             lines=lines)
+    kept = lines.gather(("t", "file"), np.flatnonzero(keep[:lines.n]))
+    rows = [_format_bread(b, tab, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score) for b in _bread_order(kept["t"], kept["file"])]
     _write_rows(rawread_to_contigs_fn, "".join(rows))
 
 

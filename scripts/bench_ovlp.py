@@ -32,6 +32,15 @@ def main():
     t0 = time.perf_counter()
     L = ofp.Lines(blobs)
     parse_s = time.perf_counter() - t0
+    from falcon_unzip_b200 import la4falcon
+    la4falcon.DeviceLines(blobs[:1], True)                       # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    DL = la4falcon.DeviceLines(blobs, True)                      # upload + fuz_parse_la4falcon (what run_ovlp_filter does)
+    torch.cuda.synchronize()
+    dev_parse_s = time.perf_counter() - t0
+    assert DL.n == L.n
+    del DL
     tab = ofp.PhaseTable(a2p, n_reads=s.n_reads)
     eng = engine.get_engine()
     t0 = time.perf_counter()
@@ -67,7 +76,8 @@ def main():
                       "groups": int(r["n_groups"]), "selected_lines": int(len(sel)), "tie_groups": int(r["grp_tie"].sum()),
                       "ignored_reads": int(r["ignore"].sum()), "contained_reads": int(r["contained"].sum()),
                       "kernels_us": kern, "params": p,
-                      "host_parse_lines_per_sec": n_lines / parse_s, "host_format_lines_per_sec": len(sel) / max(fmt_s, 1e-9),
+                      "host_parse_lines_per_sec": n_lines / parse_s, "device_parse_lines_per_sec_incl_upload": n_lines / dev_parse_s,
+                      "text_bytes": sum(len(b) for b in blobs), "host_format_lines_per_sec": len(sel) / max(fmt_s, 1e-9),
                       "output_bytes": len(text),
                       "cpu_baseline": {"value": len(s.las_lines[f0]) / cpu_s, "unit": "overlap lines/s", "cores": 1, "kind": "port",
                                        "sample": "all three stages of oracle/ovlp_oracle.py on 1 of 8 LAS files (%d lines, %.1f s)" % (

@@ -41,6 +41,16 @@ def main():
     t0 = time.perf_counter()
     parts = [rrm._parse_lines(b) for b in blobs]
     parse_s = time.perf_counter() - t0
+    # the same text parsed on the device (what run_track_reads does): upload + fuz_parse_la4falcon
+    from falcon_unzip_b200 import la4falcon
+    la4falcon.DeviceLines(blobs[:1], False)                      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dl = la4falcon.DeviceLines(blobs, False)
+    torch.cuda.synchronize()
+    dev_parse_s = time.perf_counter() - t0
+    assert dl.n == sum(len(p[0]) for p in parts)
+    del dl
     q, t, ln, tl = (np.concatenate([p[k] for p in parts]) for k in range(4))
     fidx = np.concatenate([np.full(len(p[0]), i, np.int32) for i, p in enumerate(parts)])
     # one warm call through the product path (allocations, correctness of sizes)
@@ -88,7 +98,8 @@ def main():
     print(json.dumps({"metric": "overlap_lines_per_sec_rr_hctg_track", "value": n_lines / (ms / 1e3), "unit": "overlap lines/s",
                       "ms_per_step": ms, "n_lines": n_lines, "n_reads": n_reads, "kept_lines": int(st.reserved[3]),
                       "vote_rows": int(st.reserved[1]), "bestn": b, "kernels_us": {k: round(1e3 * v, 1) for k, v in prof},
-                      "host_parse_lines_per_sec": n_lines / parse_s,
+                      "host_parse_lines_per_sec": n_lines / parse_s, "device_parse_lines_per_sec_incl_upload": n_lines / dev_parse_s,
+                      "text_bytes": sum(len(b) for b in blobs),
                       "cpu_baseline": {"value": len(rr.las_lines[f0]) / cpu_s, "unit": "overlap lines/s", "cores": 1, "kind": "port",
                                        "sample": "tr_stage1 of oracle/rr_oracle.py on 1 of 8 LAS files (%d lines, %.1f s)" % (
                                            len(rr.las_lines[f0]), cpu_s)},
