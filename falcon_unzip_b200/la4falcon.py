@@ -34,27 +34,36 @@ class DeviceLines:
 
     def __init__(self, blobs: Sequence, require_id9: bool):
         import torch
-        blobs = normalise_blobs(blobs)
-        self.text = b"".join(blobs)
+        import warnings
+        self.blobs = normalise_blobs(blobs)
+        self._text: Optional[bytes] = None
         eng = engine.get_engine()
         dev = eng.device
-        n_bytes = len(self.text)
-        cap = self.text.count(b"\n") + 1
+        sizes = [len(b) for b in self.blobs]
+        n_bytes = sum(sizes)
         d_text = torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev)
-        if n_bytes:
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")              # read-only source buffer: it is only read
-                d_text[:n_bytes].copy_(torch.from_numpy(np.frombuffer(self.text, dtype=np.uint8)))
-        self.d: Dict[str, "torch.Tensor"] = {k: torch.empty(cap, dtype=torch.int32, device=dev) for k in COLS}
-        self.d["flags"] = torch.empty(cap, dtype=torch.uint8, device=dev)
-        self.d["off"] = torch.empty(cap, dtype=torch.int64, device=dev)
-        self.d["llen"] = torch.empty(cap, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize(dev)
-        _lib.check(eng.ctx, lib().fuz_parse_la4falcon(eng.ctx, d_text.data_ptr(), n_bytes, cap, 1 if require_id9 else 0,
-                                                       *[self.d[k].data_ptr() for k in COLS], self.d["flags"].data_ptr(),
-                                                       self.d["off"].data_ptr(), self.d["llen"].data_ptr()))
-        st = eng.status(raise_on_error=False)
+        at = 0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                  # read-only source buffers: they are only read
+            for b in self.blobs:                             # every file goes up on its own: no host-side concatenation
+                if b:
+                    d_text[at:at + len(b)].copy_(torch.from_numpy(np.frombuffer(b, dtype=np.uint8)))
+                at += len(b)
+        cap = n_bytes // 48 + 1024                           # LA4Falcon lines are ~75 bytes; grown on demand
+        for _ in range(2):
+            self.d: Dict[str, "torch.Tensor"] = {k: torch.empty(cap, dtype=torch.int32, device=dev) for k in COLS}
+            self.d["flags"] = torch.empty(cap, dtype=torch.uint8, device=dev)
+            self.d["off"] = torch.empty(cap, dtype=torch.int64, device=dev)
+            self.d["llen"] = torch.empty(cap, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize(dev)
+            _lib.check(eng.ctx, lib().fuz_parse_la4falcon(eng.ctx, d_text.data_ptr(), n_bytes, cap, 1 if require_id9 else 0,
+                                                           *[self.d[k].data_ptr() for k in COLS], self.d["flags"].data_ptr(),
+                                                           self.d["off"].data_ptr(), self.d["llen"].data_ptr()))
+            st = eng.status(raise_on_error=False)
+            if st.error == _lib.FUZ_E_CAPACITY and st.error_index == 12:
+                cap = int(st.reserved[0]) + 16
+                continue
+            break
         if st.error == _lib.FUZ_E_FORMAT:
             if int(st.reserved[3]) == 3:
                 raise FuzError(st.error, "read ids of the overlap lines must be %09d ids (the reference compares them as strings)")
@@ -64,14 +73,21 @@ class DeviceLines:
             eng.status()
         self.n = int(st.reserved[0])
         for k in self.d:
-            self.d[k] = self.d[k][:max(self.n, 1)] if self.n else self.d[k][:1]
+            self.d[k] = self.d[k][:max(self.n, 1)]
         if int(st.reserved[1]):
             self._host_identity()
-        ends = torch.from_numpy(np.cumsum([len(b) for b in blobs]).astype(np.int64)).to(dev)
+        ends = torch.from_numpy(np.cumsum(sizes).astype(np.int64)).to(dev)
         self.d["file"] = torch.bucketize(self.d["off"][:self.n], ends, right=True).to(torch.int32) if self.n else torch.zeros(
             1, dtype=torch.int32, device=dev)
         self._a: Optional[Dict[str, np.ndarray]] = None
         del d_text
+
+    @property
+    def text(self) -> bytes:
+        """The concatenated text (made when the first selected line has to be printed)."""
+        if self._text is None:
+            self._text = b"".join(self.blobs)
+        return self._text
 
     def _host_identity(self) -> None:
         """float(l[3]) < 90 for the lines the kernel left open (flags bit 7)."""
