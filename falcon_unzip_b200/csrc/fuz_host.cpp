@@ -376,3 +376,147 @@ extern "C" int64_t fuz_host_format_ovlp(const char *text, const int64_t *line_of
     for (auto &th : pool) th.join();
     return start[n_thr];
 }
+
+// ---------------------------------------------------------------- CPython-2.7 orders for the tracking rows
+// rawread_to_contigs is printed in the iteration order of CPython-2 dicts (rr_hctg_track.py:97-100,113,126;
+// SURVEY.md B.4).  The emulation of Objects/stringobject.c:string_hash and of the insert-only table of
+// dictobject.c below is the C++ twin of falcon_unzip_b200/py2compat.py (which tests compare it with): the
+// Python version costs 0.6 s per 1.5 M overlap lines, more than everything on the device together.
+#include <stdio.h>
+
+static int64_t py27_str_hash(const char *s, size_t n) {
+    if (n == 0) return 0;
+    uint64_t x = (uint64_t)(unsigned char)s[0] << 7;
+    for (size_t i = 0; i < n; i++) x = (1000003ULL * x) ^ (unsigned char)s[i];
+    x ^= (uint64_t)n;
+    int64_t h = (int64_t)x;
+    return h == -1 ? -2 : h;
+}
+
+struct Py27Table {
+    struct Entry { int64_t hash; int64_t key; };
+    std::vector<Entry> slots;
+    std::vector<uint8_t> used;
+    uint64_t mask = 7;
+    int64_t n_used = 0;
+    Py27Table() : slots(8), used(8, 0) {}
+    template <class Eq>
+    bool insert(int64_t hash, int64_t key, Eq eq) {                 // false: an equal key is there already
+        uint64_t i = (uint64_t)hash & mask, perturb = (uint64_t)hash;
+        for (;;) {
+            const uint64_t s = i & mask;
+            if (!used[s]) { slots[s] = Entry{hash, key}; used[s] = 1; break; }
+            if (slots[s].hash == hash && eq(slots[s].key, key)) return false;
+            i = i * 5 + perturb + 1;
+            perturb >>= 5;
+        }
+        n_used++;
+        if ((uint64_t)n_used * 3 >= (mask + 1) * 2) {
+            const uint64_t minused = (uint64_t)(n_used > 50000 ? 2 : 4) * (uint64_t)n_used;
+            uint64_t newsize = 8;
+            while (newsize <= minused) newsize <<= 1;
+            std::vector<Entry> ns(newsize);
+            std::vector<uint8_t> nu(newsize, 0);
+            const uint64_t nm = newsize - 1;
+            for (uint64_t k = 0; k <= mask; k++) {
+                if (!used[k]) continue;
+                uint64_t j = (uint64_t)slots[k].hash & nm, p = (uint64_t)slots[k].hash;
+                while (nu[j & nm]) { j = j * 5 + p + 1; p >>= 5; }
+                ns[j & nm] = slots[k]; nu[j & nm] = 1;
+            }
+            slots.swap(ns); used.swap(nu); mask = nm;
+        }
+        return true;
+    }
+    template <class F>
+    void each(F f) const {
+        for (uint64_t k = 0; k <= mask; k++)
+            if (used[k]) f(slots[k].key);
+    }
+};
+
+// keys[i] = blob[off[i], off[i+1]) inserted in order (duplicates ignored); out = index of every distinct key in
+// dict iteration order.  Returns the number of distinct keys.
+extern "C" int64_t fuz_host_py27_str_dict_order(const char *blob, const int64_t *off, int64_t n, int64_t *out) {
+    if ((!blob || !off || !out) && n > 0) return -1;
+    Py27Table tab;
+    auto eq = [&](int64_t a, int64_t b) {
+        const int64_t la = off[a + 1] - off[a], lb = off[b + 1] - off[b];
+        return la == lb && !memcmp(blob + off[a], blob + off[b], (size_t)la);
+    };
+    for (int64_t i = 0; i < n; i++) tab.insert(py27_str_hash(blob + off[i], (size_t)(off[i + 1] - off[i])), i, eq);
+    int64_t w = 0;
+    tab.each([&](int64_t k) { out[w++] = k; });
+    return w;
+}
+
+static int64_t id9_hash(int32_t id) {
+    char buf[16];
+    const int n = snprintf(buf, sizeof(buf), "%09d", id);
+    return py27_str_hash(buf, (size_t)n);
+}
+
+// b-reads in the iteration order of the reference's bread_to_areads dict (rr_hctg_track.py:97-100,113): per LAS
+// file the targets of its kept lines are inserted at their first kept line into the file's dict, whose iteration
+// order feeds the merged dict (first sight wins); the result is the iteration order of the merged dict.  Keys are
+// the "%09d" strings of the ids.  t_kept / file_kept: target and file of every KEPT line in (file, line) order.
+extern "C" int64_t fuz_host_rr_bread_order(const int32_t *t_kept, const int32_t *file_kept, int64_t n, int32_t *out) {
+    if ((!t_kept || !file_kept || !out) && n > 0) return -1;
+    auto eq = [](int64_t a, int64_t b) { return a == b; };
+    Py27Table merged;
+    for (int64_t i = 0; i < n;) {
+        int64_t j = i;
+        Py27Table per_file;
+        while (j < n && file_kept[j] == file_kept[i]) { per_file.insert(id9_hash(t_kept[j]), t_kept[j], eq); j++; }
+        per_file.each([&](int64_t k) { merged.insert(id9_hash((int32_t)k), k, eq); });
+        i = j;
+    }
+    int64_t w = 0;
+    merged.each([&](int64_t k) { out[w++] = (int32_t)k; });
+    return w;
+}
+
+// Rows of rawread_to_contigs (rr_hctg_track.py:126-138) for the given b-reads, in the given order: the contigs a
+// b-read voted for in dict order of their names, stably sorted by score, "bread ctg count rank score in_ctg".
+// Returns the size of the text (call with out = NULL first), -1 if cap is too small.
+extern "C" int64_t fuz_host_rr_format_rows(const int32_t *breads, int64_t n_breads, const int32_t *vt_off, const int32_t *vt_ctg,
+                                           const int32_t *vt_count, const int64_t *vt_score, const char *ctg_blob,
+                                           const int64_t *ctg_off, const uint8_t *in_map, const int32_t *rc_off,
+                                           const int32_t *rc_ctg, char *out, int64_t cap) {
+    if ((!breads && n_breads) || !vt_off || !vt_ctg || !vt_count || !vt_score || !ctg_blob || !ctg_off || !in_map || !rc_off || !rc_ctg)
+        return -1;
+    int64_t w = 0;
+    std::vector<std::pair<int64_t, int>> items;        // (score, vote row), in dict order first
+    char line[512];
+    for (int64_t b = 0; b < n_breads; b++) {
+        const int32_t tid = breads[b];
+        const int lo = vt_off[tid], hi = vt_off[tid + 1];
+        if (lo == hi) continue;
+        Py27Table tab;
+        auto eq = [&](int64_t x, int64_t y) { return vt_ctg[x] == vt_ctg[y]; };
+        for (int r = lo; r < hi; r++) {
+            const int c = vt_ctg[r];
+            tab.insert(py27_str_hash(ctg_blob + ctg_off[c], (size_t)(ctg_off[c + 1] - ctg_off[c])), r, eq);
+        }
+        items.clear();
+        tab.each([&](int64_t r) { items.emplace_back(vt_score[r], (int)r); });
+        std::stable_sort(items.begin(), items.end(), [](const std::pair<int64_t, int> &x, const std::pair<int64_t, int> &y) { return x.first < y.first; });
+        int rank = 0;
+        for (const auto &it : items) {
+            const int r = it.second, c = vt_ctg[r];
+            int in_ctg = 0;
+            if (in_map[tid])
+                for (int k = rc_off[tid]; k < rc_off[tid + 1]; k++) in_ctg |= rc_ctg[k] == c;
+            const int nn = snprintf(line, sizeof(line), "%09d %.*s %d %d %lld %d\n", tid, (int)(ctg_off[c + 1] - ctg_off[c]),
+                                    ctg_blob + ctg_off[c], vt_count[r], rank, (long long)it.first, in_ctg);
+            if (nn < 0 || nn >= (int)sizeof(line)) return -1;
+            if (out) {
+                if (w + nn > cap) return -1;
+                memcpy(out + w, line, (size_t)nn);
+            }
+            w += nn;
+            rank++;
+        }
+    }
+    return w;
+}

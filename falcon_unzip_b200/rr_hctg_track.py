@@ -265,9 +265,39 @@ def _format_bread(bread: str, tab: _Tables, rid_to_ctg, vt_off, vt_ctg, vt_count
     return "".join(out)
 
 
-def _write_rows(fn: str, text: str) -> None:
+def _bread_order_native(t_kept: np.ndarray, file_kept: np.ndarray) -> np.ndarray:
+    """_bread_order through libfuz (fuz_host_rr_bread_order): int ids instead of "%09d" strings."""
+    t_kept = np.ascontiguousarray(t_kept, dtype=np.int32)
+    file_kept = np.ascontiguousarray(file_kept, dtype=np.int32)
+    out = np.empty(max(len(t_kept), 1), np.int32)
+    n = lib().fuz_host_rr_bread_order(t_kept.ctypes.data, file_kept.ctypes.data, len(t_kept), out.ctypes.data)
+    if n < 0:
+        raise FuzError(_lib.FUZ_E_ARG, "fuz_host_rr_bread_order failed")
+    return out[:n]
+
+
+def _format_rows_native(breads: np.ndarray, tab: _Tables, vt_off, vt_ctg, vt_count, vt_score) -> bytes:
+    """All rows of rawread_to_contigs through libfuz (fuz_host_rr_format_rows)."""
+    names = [c.encode("ascii") for c in tab.ctg_names]
+    ctg_off = np.concatenate([[0], np.cumsum([len(c) for c in names])]).astype(np.int64)
+    blob = b"".join(names) + b"\0"
+    arrs = [np.ascontiguousarray(a, dtype=dt) for a, dt in ((breads, np.int32), (vt_off, np.int32), (vt_ctg, np.int32),
+                                                           (vt_count, np.int32), (vt_score, np.int64))]
+    if len(arrs[2]) == 0:
+        arrs[2], arrs[3], arrs[4] = np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.int64)
+    args = (arrs[0].ctypes.data, len(arrs[0]), arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data,
+            blob, ctg_off.ctypes.data, tab.in_map.ctypes.data, tab.rc_off.ctypes.data, tab.rc_ctg.ctypes.data)
+    size = lib().fuz_host_rr_format_rows(*args, None, 0)
+    if size < 0:
+        raise FuzError(_lib.FUZ_E_ARG, "fuz_host_rr_format_rows failed")
+    buf = C.create_string_buffer(int(size) + 1)
+    lib().fuz_host_rr_format_rows(*args, buf, size)
+    return buf.raw[:size]
+
+
+def _write_rows(fn: str, text) -> None:
     os.makedirs(os.path.dirname(fn) or ".", exist_ok=True)
-    with open(fn + ".tmp", "w") as f:
+    with open(fn + ".tmp", "wb" if isinstance(text, bytes) else "w") as f:
         f.write(text)
     os.replace(fn + ".tmp", fn)
 
@@ -284,8 +314,9 @@ def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawrea
     keep, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(None, None, None, None, None, tab, min_len, bestn,
                                                                              lines=lines)
     kept = lines.gather(("t", "file"), np.flatnonzero(keep[:lines.n]))
-    rows = [_format_bread(b, tab, rid_to_ctg, vt_off, vt_ctg, vt_count, vt_score) for b in _bread_order(kept["t"], kept["file"])]
-    _write_rows(rawread_to_contigs_fn, "".join(rows))
+    # row order (CPython-2 dict orders) and text: C++ twins of _bread_order / _format_bread
+    breads = _bread_order_native(kept["t"], kept["file"])
+    _write_rows(rawread_to_contigs_fn, _format_rows_native(breads, tab, vt_off, vt_ctg, vt_count, vt_score))
 
 
 def run_track_reads_sharded(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn, file_list, min_len, bestn, db_fn,

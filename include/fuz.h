@@ -361,6 +361,20 @@ int64_t fuz_host_parse_la4falcon_mo(const char *text, int64_t n_bytes, int64_t c
 int64_t fuz_host_format_ovlp(const char *text, const int64_t *line_off, const int32_t *line_len, const int32_t *q,
                              const int32_t *t, const int64_t *sel, int64_t n_sel, const char *phase_text,
                              const int64_t *phase_off, char *out, int64_t cap);
+/* CPython-2.7 dict / set iteration order of str keys (Objects/stringobject.c string_hash + the insert-only table
+ * of dictobject.c): keys[i] = blob[off[i], off[i+1]) inserted in order, duplicates ignored;
+ * out = index of every distinct key in iteration order.  Returns the number of distinct keys. */
+int64_t fuz_host_py27_str_dict_order(const char *blob, const int64_t *off, int64_t n, int64_t *out);
+/* b-reads in the iteration order of the reference's bread_to_areads dict (rr_hctg_track.py:97-100,113) from the
+ * target / LAS file of every KEPT overlap line in (file, line) order.  Returns the number of b-reads. */
+int64_t fuz_host_rr_bread_order(const int32_t *t_kept, const int32_t *file_kept, int64_t n, int32_t *out);
+/* Text of rawread_to_contigs (rr_hctg_track.py:126-138) for the given b-reads from the vote rows of fuz_rr_track,
+ * the contig names (ctg_blob / ctg_off) and the rid -> contigs table of fuz_rr_input.  Returns the size (call with
+ * out = NULL first), -1 if cap is too small. */
+int64_t fuz_host_rr_format_rows(const int32_t *breads, int64_t n_breads, const int32_t *vt_off, const int32_t *vt_ctg,
+                                const int32_t *vt_count, const int64_t *vt_score, const char *ctg_blob,
+                                const int64_t *ctg_off, const uint8_t *in_map, const int32_t *rc_off,
+                                const int32_t *rc_ctg, char *out, int64_t cap);
 /* CPython-2.7 dict iteration order of int keys inserted in the given order (B.3). */
 int fuz_host_py27_int_dict_order(const int64_t *keys, int64_t n, int64_t *out);
 
