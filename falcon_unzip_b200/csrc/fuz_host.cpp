@@ -450,10 +450,12 @@ extern "C" int64_t fuz_host_py27_str_dict_order(const char *blob, const int64_t 
     return w;
 }
 
-static int64_t id9_hash(int32_t id) {
+static int64_t id9_hash(int32_t id) {                  // hash of the string "%09d" % id
     char buf[16];
-    const int n = snprintf(buf, sizeof(buf), "%09d", id);
-    return py27_str_hash(buf, (size_t)n);
+    if (id < 0 || id > 999999999) return py27_str_hash(buf, (size_t)snprintf(buf, sizeof(buf), "%09d", id));
+    uint32_t v = (uint32_t)id;
+    for (int k = 8; k >= 0; k--) { buf[k] = (char)('0' + v % 10); v /= 10; }
+    return py27_str_hash(buf, 9);
 }
 
 // b-reads in the iteration order of the reference's bread_to_areads dict (rr_hctg_track.py:97-100,113): per LAS
@@ -464,10 +466,20 @@ extern "C" int64_t fuz_host_rr_bread_order(const int32_t *t_kept, const int32_t 
     if ((!t_kept || !file_kept || !out) && n > 0) return -1;
     auto eq = [](int64_t a, int64_t b) { return a == b; };
     Py27Table merged;
+    int32_t t_max = -1;
+    for (int64_t i = 0; i < n; i++) {
+        if (t_kept[i] < 0) return -1;
+        t_max = std::max(t_max, t_kept[i]);
+    }
+    std::vector<int64_t> stamp((size_t)t_max + 1, -1);     // last segment in which the target was inserted
     for (int64_t i = 0; i < n;) {
         int64_t j = i;
         Py27Table per_file;
-        while (j < n && file_kept[j] == file_kept[i]) { per_file.insert(id9_hash(t_kept[j]), t_kept[j], eq); j++; }
+        while (j < n && file_kept[j] == file_kept[i]) {
+            const int32_t t = t_kept[j];
+            if (stamp[t] != i) { stamp[t] = i; per_file.insert(id9_hash(t), t, eq); }
+            j++;
+        }
         per_file.each([&](int64_t k) { merged.insert(id9_hash((int32_t)k), k, eq); });
         i = j;
     }
