@@ -321,16 +321,10 @@ def is_bgzf(path: str) -> bool:
 # --------------------------------------------------------------------------- FASTA
 def read_fasta(path: str) -> Iterator[Tuple[str, str]]:
     """Minimal stand-in for falcon_kit.FastaReader (reference phasing.py:3,490-494):
-    yields (header line without '>', sequence)."""
-    name, chunks = None, []
+    yields (header line without '>', sequence).  A record starts at a line that begins with '>'; sequence
+    lines are stripped and joined; anything before the first header is ignored."""
     with open(path) as f:
-        for line in f:
-            line = line.rstrip("\r\n")
-            if line.startswith(">"):
-                if name is not None:
-                    yield name, "".join(chunks)
-                name, chunks = line[1:], []
-            elif name is not None:
-                chunks.append(line.strip())
-    if name is not None:
-        yield name, "".join(chunks)
+        text = f.read()
+    for rec in ("\n" + text).split("\n>")[1:]:
+        header, _, body = rec.partition("\n")
+        yield header.rstrip("\r\n"), "".join(map(str.strip, body.split("\n")))

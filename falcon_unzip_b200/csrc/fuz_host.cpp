@@ -532,3 +532,51 @@ extern "C" int64_t fuz_host_rr_format_rows(const int32_t *breads, int64_t n_brea
     }
     return w;
 }
+
+// ---------------------------------------------------------------- text of the two large per-contig files
+// het_call/variant_map ("pos ref allele q_id", phasing.py:126,128) and g_atable/atable ("pos1 b11 b12 pos2 b21 b22
+// c11 c12 c21 c22", phasing.py:199) hold ~depth x sites and ~10 x sites rows; formatting them row by row in Python
+// took two thirds of the file-level call.  Both return the size of the text, -1 if cap is too small, -2 if a
+// position lies outside ref_seq (the reference raises IndexError, phasing.py:123).
+static inline char *put_int(char *p, long long v) {
+    char tmp[24];
+    int n = 0;
+    unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+extern "C" int64_t fuz_host_format_variant_map(const int32_t *site_pos, const int32_t *vm_site, const uint8_t *vm_base,
+                                               const int32_t *vm_qid, int64_t v0, int64_t v1, const char *ref_seq, int64_t ref_len,
+                                               char *out, int64_t cap) {
+    if (!site_pos || !vm_site || !vm_base || !vm_qid || !ref_seq || !out || v0 > v1) return -1;
+    if ((v1 - v0) * 32 > cap) return -1;
+    static const char B[] = "ACGT";
+    char *p = out;
+    for (int64_t i = v0; i < v1; i++) {
+        const int32_t pos = site_pos[vm_site[i]];
+        if (pos < 1 || pos > ref_len || vm_base[i] > 3) return -2;
+        p = put_int(p, pos); *p++ = ' '; *p++ = ref_seq[pos - 1]; *p++ = ' '; *p++ = B[vm_base[i]]; *p++ = ' ';
+        p = put_int(p, vm_qid[i]); *p++ = '\n';
+    }
+    return p - out;
+}
+
+extern "C" int64_t fuz_host_format_atable(const int32_t *site_pos, const uint8_t *site_al, const int32_t *at_s1, const int32_t *at_s2,
+                                          const int32_t *at_ct, int64_t a0, int64_t a1, char *out, int64_t cap) {
+    if (!site_pos || !site_al || !at_s1 || !at_s2 || !at_ct || !out || a0 > a1) return -1;
+    if ((a1 - a0) * 96 > cap) return -1;
+    static const char B[] = "ACGT";
+    char *p = out;
+    for (int64_t i = a0; i < a1; i++) {
+        const int32_t s1 = at_s1[i], s2 = at_s2[i];
+        if (site_al[2 * s1] > 3 || site_al[2 * s1 + 1] > 3 || site_al[2 * s2] > 3 || site_al[2 * s2 + 1] > 3) return -2;
+        p = put_int(p, site_pos[s1]); *p++ = ' '; *p++ = B[site_al[2 * s1]]; *p++ = ' '; *p++ = B[site_al[2 * s1 + 1]]; *p++ = ' ';
+        p = put_int(p, site_pos[s2]); *p++ = ' '; *p++ = B[site_al[2 * s2]]; *p++ = ' '; *p++ = B[site_al[2 * s2 + 1]];
+        for (int k = 0; k < 4; k++) { *p++ = ' '; p = put_int(p, at_ct[4 * i + k]); }
+        *p++ = '\n';
+    }
+    return p - out;
+}

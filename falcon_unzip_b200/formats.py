@@ -56,11 +56,24 @@ def variant_pos_text(res, s0: int, s1: int, ref_seq: str) -> str:
         for p, t, o, c in zip(pos, tot, so, sc))
 
 
+def _c32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
 def variant_map_text(res, s0: int, v0: int, v1: int, ref_seq: str) -> str:
-    """het_call/variant_map: ``pos ref allele q_id`` (phasing.py:126,128)."""
-    pos = res.site_pos[res.vm_site[v0:v1]].tolist()
-    return "".join("%d %s %s %d\n" % (p, ref_seq[p - 1], BASES[b], q)
-                   for p, b, q in zip(pos, res.vm_base[v0:v1].tolist(), res.vm_qid[v0:v1].tolist()))
+    """het_call/variant_map: ``pos ref allele q_id`` (phasing.py:126,128); rows formatted in libfuz."""
+    site_pos, vm_site, vm_qid = _c32(res.site_pos), _c32(res.vm_site), _c32(res.vm_qid)
+    vm_base = np.ascontiguousarray(res.vm_base, dtype=np.uint8)
+    ref = ref_seq.encode("latin-1")
+    cap = 32 * (v1 - v0) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib().fuz_host_format_variant_map(site_pos.ctypes.data, vm_site.ctypes.data, vm_base.ctypes.data, vm_qid.ctypes.data,
+                                          v0, v1, ref, len(ref), buf, cap)
+    if n == -2:
+        raise IndexError("string index out of range (ref_seq shorter than a het position; phasing.py:123)")
+    if n < 0:
+        raise RuntimeError("fuz_host_format_variant_map failed")
+    return buf.raw[:n].decode("latin-1")
 
 
 def q_id_map_text(names: Sequence[str]) -> str:
@@ -69,13 +82,16 @@ def q_id_map_text(names: Sequence[str]) -> str:
 
 
 def atable_text(res, a0: int, a1: int) -> str:
-    """g_atable/atable: ``pos1 b11 b12 pos2 b21 b22 c11 c12 c21 c22`` (phasing.py:199)."""
-    s1, s2 = res.at_s1[a0:a1], res.at_s2[a0:a1]
-    p1, p2 = res.site_pos[s1].tolist(), res.site_pos[s2].tolist()
-    al1, al2 = res.site_al[s1].tolist(), res.site_al[s2].tolist()
-    return "".join("%d %s %s %d %s %s %d %d %d %d\n" % (
-        x, BASES[a[0]], BASES[a[1]], y, BASES[b[0]], BASES[b[1]], c[0], c[1], c[2], c[3])
-        for x, a, y, b, c in zip(p1, al1, p2, al2, res.at_ct[a0:a1].tolist()))
+    """g_atable/atable: ``pos1 b11 b12 pos2 b21 b22 c11 c12 c21 c22`` (phasing.py:199); rows formatted in libfuz."""
+    site_pos, at_s1, at_s2, at_ct = _c32(res.site_pos), _c32(res.at_s1), _c32(res.at_s2), _c32(res.at_ct)
+    site_al = np.ascontiguousarray(res.site_al, dtype=np.uint8)
+    cap = 96 * (a1 - a0) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib().fuz_host_format_atable(site_pos.ctypes.data, site_al.ctypes.data, at_s1.ctypes.data, at_s2.ctypes.data,
+                                     at_ct.ctypes.data, a0, a1, buf, cap)
+    if n < 0:
+        raise RuntimeError("fuz_host_format_atable failed")
+    return buf.raw[:n].decode("ascii")
 
 
 def phased_variants_text(res, s0: int, s1: int, ref_base) -> str:

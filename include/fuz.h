@@ -361,6 +361,15 @@ int64_t fuz_host_parse_la4falcon_mo(const char *text, int64_t n_bytes, int64_t c
 int64_t fuz_host_format_ovlp(const char *text, const int64_t *line_off, const int32_t *line_len, const int32_t *q,
                              const int32_t *t, const int64_t *sel, int64_t n_sel, const char *phase_text,
                              const int64_t *phase_off, char *out, int64_t cap);
+/* Text of het_call/variant_map (phasing.py:126,128) for the rows [v0, v1) and of g_atable/atable (phasing.py:199) for
+ * the rows [a0, a1) of the row arrays (fuz_outputs layout).  Return the size of the text; -1 if cap is too small
+ * (32 bytes per variant_map row, 96 per atable row suffice), -2 if a position lies outside ref_seq (the reference
+ * raises IndexError, phasing.py:123) or an allele is not one of A, C, G, T. */
+int64_t fuz_host_format_variant_map(const int32_t *site_pos, const int32_t *vm_site, const uint8_t *vm_base,
+                                    const int32_t *vm_qid, int64_t v0, int64_t v1, const char *ref_seq, int64_t ref_len,
+                                    char *out, int64_t cap);
+int64_t fuz_host_format_atable(const int32_t *site_pos, const uint8_t *site_al, const int32_t *at_s1, const int32_t *at_s2,
+                               const int32_t *at_ct, int64_t a0, int64_t a1, char *out, int64_t cap);
 /* CPython-2.7 dict / set iteration order of str keys (Objects/stringobject.c string_hash + the insert-only table
  * of dictobject.c): keys[i] = blob[off[i], off[i+1]) inserted in order, duplicates ignored;
  * out = index of every distinct key in iteration order.  Returns the number of distinct keys. */
