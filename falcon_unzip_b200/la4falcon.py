@@ -122,6 +122,13 @@ class DeviceLines:
         idx = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int64)).to(self.d["q"].device)
         return {k: self.d[k][idx].cpu().numpy() if len(sel) else np.zeros(0, dtype=self.d[k].cpu().numpy().dtype) for k in keys}
 
+    @property
+    def starts(self) -> np.ndarray:
+        """Offset of every file's text in the concatenated stream (line offsets refer to that stream)."""
+        return np.concatenate([[0], np.cumsum([len(b) for b in self.blobs])]).astype(np.int64)
+
     def tokens(self, i: int) -> List[str]:
         o, l = int(self.a["off"][i]), int(self.a["llen"][i])
-        return self.text[o:o + l].decode("ascii").split()
+        k = int(np.searchsorted(self.starts, o, side="right")) - 1
+        o -= int(self.starts[k])
+        return self.blobs[k][o:o + l].decode("ascii").split()

@@ -215,21 +215,37 @@ def _resolve_ties(L: Lines, tab: PhaseTable, r: dict, bestn: int) -> np.ndarray:
     return np.concatenate([p.astype(np.int64) for p in parts])
 
 
-def _format(L, tab: PhaseTable, sel: np.ndarray) -> bytes:
-    sel = np.ascontiguousarray(sel, dtype=np.int64)
-    if hasattr(L, "gather"):                              # columns live on the device: fetch the selected lines only
-        g = L.gather(("off", "llen", "q", "t"), sel)
-    else:
-        g = {k: np.ascontiguousarray(L.a[k][sel]) for k in ("off", "llen", "q", "t")}
-    idx = np.arange(len(sel), dtype=np.int64)
-    args = (L.text, g["off"].ctypes.data, g["llen"].ctypes.data, g["q"].ctypes.data, g["t"].ctypes.data, idx.ctypes.data,
-            len(sel), tab.phase_text, tab.phase_off.ctypes.data)
+def _format_piece(text: bytes, g: dict, tab: PhaseTable) -> bytes:
+    n = len(g["off"])
+    idx = np.arange(n, dtype=np.int64)
+    off, llen, q, t = (np.ascontiguousarray(g[k]) for k in ("off", "llen", "q", "t"))
+    args = (text, off.ctypes.data, llen.ctypes.data, q.ctypes.data, t.ctypes.data, idx.ctypes.data, n, tab.phase_text,
+            tab.phase_off.ctypes.data)
     size = lib().fuz_host_format_ovlp(*args, None, 0)
     if size < 0:
         raise FuzError(_lib.FUZ_E_ARG, "fuz_host_format_ovlp failed")
     buf = C.create_string_buffer(int(size) + 1)
     lib().fuz_host_format_ovlp(*args, buf, size)
     return buf.raw[:size]
+
+
+def _format(L, tab: PhaseTable, sel: np.ndarray) -> bytes:
+    """Output text of the selected lines (fuz_host_format_ovlp)."""
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    if not hasattr(L, "gather"):
+        return _format_piece(L.text, {k: L.a[k][sel] for k in ("off", "llen", "q", "t")}, tab)
+    # columns live on the device: fetch the selected lines only; the text of every file is formatted from its own
+    # buffer (no concatenation of the files on the host) -- selected lines come file after file
+    g = L.gather(("off", "llen", "q", "t"), sel)
+    starts = L.starts
+    k_of = np.searchsorted(starts, g["off"], side="right") - 1
+    out = []
+    for k in np.unique(k_of).tolist():
+        m = k_of == k
+        piece = {key: g[key][m] for key in ("llen", "q", "t")}
+        piece["off"] = g["off"][m] - starts[k]
+        out.append(_format_piece(L.blobs[k], piece, tab))
+    return b"".join(out)
 
 
 # --------------------------------------------------------------------------- the reference's functions
