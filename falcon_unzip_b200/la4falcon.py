@@ -6,6 +6,7 @@ the identity column of lines the kernel flags (exponent / inf / nan notation, mo
 is evaluated with Python's float(), as the reference does for every line."""
 from __future__ import annotations
 
+import bisect
 import ctypes as C
 import re
 from typing import Dict, List, Optional, Sequence
@@ -41,6 +42,9 @@ class DeviceLines:
         dev = eng.device
         sizes = [len(b) for b in self.blobs]
         n_bytes = sum(sizes)
+        # offset of every file's text in the concatenated stream (line offsets refer to that stream)
+        self.starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self._starts_list = self.starts.tolist()
         d_text = torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev)
         at = 0
         with warnings.catch_warnings():
@@ -122,13 +126,9 @@ class DeviceLines:
         idx = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int64)).to(self.d["q"].device)
         return {k: self.d[k][idx].cpu().numpy() if len(sel) else np.zeros(0, dtype=self.d[k].cpu().numpy().dtype) for k in keys}
 
-    @property
-    def starts(self) -> np.ndarray:
-        """Offset of every file's text in the concatenated stream (line offsets refer to that stream)."""
-        return np.concatenate([[0], np.cumsum([len(b) for b in self.blobs])]).astype(np.int64)
 
     def tokens(self, i: int) -> List[str]:
         o, l = int(self.a["off"][i]), int(self.a["llen"][i])
-        k = int(np.searchsorted(self.starts, o, side="right")) - 1
-        o -= int(self.starts[k])
+        k = bisect.bisect_right(self._starts_list, o) - 1
+        o -= self._starts_list[k]
         return self.blobs[k][o:o + l].decode("ascii").split()
