@@ -252,7 +252,7 @@ def _format(L, tab: PhaseTable, sel: np.ndarray) -> bytes:
 def filter_stage1(input_):
     """reference :49-143 -> (fn, ids to ignore in the order the reference appends them)."""
     db_fn, fn, max_diff, max_ovlp, min_ovlp, min_len = input_
-    L, tab = Lines([read_las_lines(db_fn, fn)]), PhaseTable(arid2phase)
+    L, tab = la4falcon.DeviceLines([read_las_lines(db_fn, fn)], require_id9=True), PhaseTable(arid2phase)
     r = _device_filter(L, tab, max_diff, max_ovlp, min_ovlp, min_len, 0, 1)
     rtn: List[Optional[str]] = []
     if r["n_groups"] and _verdict(0, 0, max_diff, max_ovlp, min_ovlp):
@@ -264,7 +264,7 @@ def filter_stage1(input_):
 def filter_stage2(input_):
     """reference :145-186 -> (fn, set of contained read ids)."""
     db_fn, fn, max_diff, max_ovlp, min_ovlp, min_len, ignore_set = input_
-    L, tab = Lines([read_las_lines(db_fn, fn)]), PhaseTable(arid2phase)
+    L, tab = la4falcon.DeviceLines([read_las_lines(db_fn, fn)], require_id9=True), PhaseTable(arid2phase)
     r = _device_filter(L, tab, max_diff, max_ovlp, min_ovlp, min_len, 0, 2, ignore_in=tab.flags_of(ignore_set))
     return fn, set("%09d" % x for x in np.flatnonzero(r["contained"]).tolist())
 
@@ -272,7 +272,7 @@ def filter_stage2(input_):
 def filter_stage3(input_):
     """reference :188-290 -> (fn, selected overlaps as token lists, phase strings appended)."""
     db_fn, fn, max_diff, max_ovlp, min_ovlp, min_len, ignore_set, contained_set, bestn = input_
-    L, tab = Lines([read_las_lines(db_fn, fn)]), PhaseTable(arid2phase)
+    L, tab = la4falcon.DeviceLines([read_las_lines(db_fn, fn)], require_id9=True), PhaseTable(arid2phase)
     ig, ct = tab.flags_of(ignore_set), tab.flags_of(contained_set)
     r = _device_filter(L, tab, max_diff, max_ovlp, min_ovlp, min_len, bestn, 3, ignore_in=ig, contained_in=ct)
     sel = _resolve_ties(L, tab, r, bestn)

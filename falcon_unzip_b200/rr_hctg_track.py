@@ -194,9 +194,11 @@ def _first_kept_order(t: np.ndarray, keep: np.ndarray) -> np.ndarray:
 def tr_stage1(readlines: Callable[[], Iterable[str]], min_len: int, bestn: int, rid_to_ctg, rid_to_phase):
     """reference rr_hctg_track.py:31-65: {t_id: heapq array of (overlap_len, q_id)} for one LAS
     file; targets in first-kept-appearance order."""
-    q, t, ln, tl = _parse_lines(readlines())
+    lines = la4falcon.DeviceLines([readlines()], require_id9=False)
     tab = _Tables(rid_to_ctg, rid_to_phase, len(rid_to_phase))
-    keep, hp_n, hp_len, hp_q, *_ = _track_device(q, t, ln, tl, np.zeros(len(q), np.int32), tab, min_len, bestn)
+    keep, hp_n, hp_len, hp_q, *_ = _track_device(None, None, None, None, None, tab, min_len, bestn, lines=lines)
+    keep = keep[:lines.n]
+    t = lines.a["t"]
     rtn = {}
     for tid in _first_kept_order(t, keep).tolist():
         n = int(hp_n[tid])
@@ -338,10 +340,18 @@ def run_track_reads_sharded(phased_read_file_fn, read_to_contig_map_fn, rawread_
     rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
     files = sorted(file_list)
     mine = list(range(rank, len(files), world_size))
-    q, t, ln, tl, file_idx = _parse_files(db_fn, [files[i] for i in mine], mine)
-    keep = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn, filter_only=True)[0].astype(bool)
-    local = np.stack([q[keep], t[keep], ln[keep], tl[keep], file_idx[keep]], axis=1).astype(np.int32)
     backend = dist.get_backend(group)
+    if backend == "nccl":                                  # text parsed on the device, only the kept lines come back
+        lines = la4falcon.DeviceLines([read_las_lines(db_fn, files[i]) for i in mine], require_id9=False)
+        keep = _track_device(None, None, None, None, None, tab, min_len, bestn, filter_only=True, lines=lines)[0][:lines.n].astype(bool)
+        g = lines.gather(("q", "t", "len", "tl", "file"), np.flatnonzero(keep))
+        file_of = np.asarray(mine, np.int32)[g["file"]] if len(mine) else g["file"]
+        local = np.stack([g["q"], g["t"], g["len"], g["tl"], file_of], axis=1).astype(np.int32)
+        q = np.zeros(lines.n, np.int8)                     # only its length is reported below
+    else:
+        q, t, ln, tl, file_idx = _parse_files(db_fn, [files[i] for i in mine], mine)
+        keep = _track_device(q, t, ln, tl, file_idx, tab, min_len, bestn, filter_only=True)[0].astype(bool)
+        local = np.stack([q[keep], t[keep], ln[keep], tl[keep], file_idx[keep]], axis=1).astype(np.int32)
     dev = engine.get_engine().device if backend == "nccl" else torch.device("cpu")
     # exchange: sizes, then the padded line blocks
     n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
