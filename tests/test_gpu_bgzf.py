@@ -249,3 +249,49 @@ def test_phase_bam_with_empty_contig_and_unmapped_tail(eng, tmp_path):
     bam.write_bam(fn, refs, b"")
     res_e, _ = phasing.phase_bam(fn, fa, str(tmp_path / "none"))
     assert (res_e.n_sites, res_e.n_vmap, res_e.n_reads) == (0, 0, 0)
+
+
+def test_inflate_fuzz(eng):
+    """Random payload mixtures (runs, repeats at random distances, random bytes, small alphabets) x random zlib
+    parameters, 300 blocks in one launch, against zlib; sizes from 0 to 65536."""
+    rng = np.random.default_rng(2024)
+    blocks = []
+    for k in range(300):
+        n = int(rng.choice([0, 1, 2, 31, 32, 33, 255, 4096, 65535, 65536, int(rng.integers(0, 65537))]))
+        parts, size = [], 0
+        while size < n:
+            kind = int(rng.integers(0, 5))
+            m = int(min(n - size, rng.integers(1, 3000)))
+            if kind == 0:
+                piece = bytes([int(rng.integers(0, 256))]) * m
+            elif kind == 1:
+                piece = bytes(rng.integers(0, 256, m, dtype=np.uint8))
+            elif kind == 2:
+                piece = bytes(rng.integers(0, int(rng.integers(2, 20)), m, dtype=np.uint8))
+            elif kind == 3 and size > 0:
+                joined = b"".join(parts)
+                d = int(rng.integers(1, min(size, 32768) + 1))
+                src = joined[size - d:size - d + m]
+                piece = (src * (m // max(len(src), 1) + 1))[:m]
+            else:
+                piece = (b"ACGT" * (m // 4 + 1))[:m]
+            parts.append(piece)
+            size += len(piece)
+        data = b"".join(parts)[:n]
+        level = int(rng.choice([0, 1, 1, 6, 9]))
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, int(rng.integers(1, 10)), strat)
+        comp = c.compress(data)
+        if rng.random() < 0.3 and len(data) > 10:          # several deflate blocks inside one stream
+            comp += c.flush(zlib.Z_FULL_FLUSH)
+            extra = bytes(rng.integers(0, 256, int(rng.integers(0, 50)), dtype=np.uint8))
+            if len(data) + len(extra) <= 65536:
+                comp += c.compress(extra)
+                data += extra
+        comp += c.flush()
+        assert zlib.decompress(comp, -15) == data
+        blocks.append((data, comp))
+    st, outs = _inflate_blocks(eng, blocks, [zlib.crc32(d) & 0xFFFFFFFF for d, _c in blocks])
+    assert st.error == 0, (st.error, st.error_index, st.reserved[3])
+    for k, ((d, _c), got) in enumerate(zip(blocks, outs)):
+        assert got == d, k

@@ -76,3 +76,28 @@ def test_large_text(eng):
     blobs = _blobs(seed=8, n=2500)
     assert sum(len(b) for b in blobs) > 15_000_000
     _same(la4falcon.DeviceLines(blobs, True), ofp.Lines(blobs))
+
+
+def test_parser_fuzz(eng):
+    """Random lines: signs, leading zeros, 1-4 blanks of several kinds between tokens, extra columns, CRLF, random
+    identity notations -- the device columns must equal the host parser's (which is checked against Python)."""
+    from falcon_unzip_b200 import la4falcon, ovlp_filter_with_phase as ofp
+    rng = np.random.default_rng(99)
+    blanks = [" ", "  ", "\t", " \t ", "\v", "\f "]
+    tags = ["overlap", "contains", "contained", "none", "overlapx", "c"]
+    lines = []
+    for _ in range(20000):
+        num = lambda lo, hi: ("%+d" if rng.random() < 0.05 else "%d") % int(rng.integers(lo, hi))
+        idt = rng.choice(["%.2f" % (80 + 20 * rng.random()), "%d" % int(rng.integers(85, 101)), "0%.3f" % (89.5 + rng.random()),
+                          "9.%de1" % int(rng.integers(0, 10)), "%.17f" % (89.9999 + 0.0002 * rng.random())])
+        tok = ["%09d" % int(rng.integers(0, 5000)), "%09d" % int(rng.integers(0, 5000)), num(-30000, 1), idt, num(0, 2), num(0, 100),
+               num(0, 20000), num(0, 20000), num(0, 2), num(0, 100), num(0, 20000), num(0, 20000), str(rng.choice(tags))]
+        if rng.random() < 0.05:
+            tok += ["extra", str(rng.choice(tags))]
+        line = (str(rng.choice(blanks)) if rng.random() < 0.1 else "") + "".join(t + str(rng.choice(blanks)) for t in tok[:-1]) + tok[-1]
+        lines.append(line + ("\r" if rng.random() < 0.05 else "") + ("\n\n" if rng.random() < 0.03 else "\n"))
+    blob = "".join(lines).encode("ascii")
+    DL, HL = la4falcon.DeviceLines([blob[:len(blob) // 2], blob[len(blob) // 2:]], True), ofp.Lines([blob[:len(blob) // 2], blob[len(blob) // 2:]])
+    assert DL.n == HL.n >= 20000
+    for k in ("q", "t", "len", "qs", "qe", "ql", "ts", "te", "tl", "flags", "off", "llen"):
+        assert np.array_equal(DL.a[k], HL.a[k]), k
