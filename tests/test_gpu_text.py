@@ -96,8 +96,8 @@ def test_parser_fuzz(eng):
             tok += ["extra", str(rng.choice(tags))]
         line = (str(rng.choice(blanks)) if rng.random() < 0.1 else "") + "".join(t + str(rng.choice(blanks)) for t in tok[:-1]) + tok[-1]
         lines.append(line + ("\r" if rng.random() < 0.05 else "") + ("\n\n" if rng.random() < 0.03 else "\n"))
-    blob = "".join(lines).encode("ascii")
-    DL, HL = la4falcon.DeviceLines([blob[:len(blob) // 2], blob[len(blob) // 2:]], True), ofp.Lines([blob[:len(blob) // 2], blob[len(blob) // 2:]])
+    blobs = ["".join(lines[:9000]).encode("ascii"), "".join(lines[9000:]).encode("ascii")]
+    DL, HL = la4falcon.DeviceLines(blobs, True), ofp.Lines(blobs)
     assert DL.n == HL.n >= 20000
     for k in ("q", "t", "len", "qs", "qe", "ql", "ts", "te", "tl", "flags", "off", "llen"):
         assert np.array_equal(DL.a[k], HL.a[k]), k
