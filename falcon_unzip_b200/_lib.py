@@ -147,6 +147,8 @@ SYMBOLS = [
                                                 C.c_int64, C.c_char_p, C.c_int64]),
     ("fuz_host_format_atable", C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                            C.c_char_p, C.c_int64]),
+    ("fuz_host_format_phased_reads", C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_int64, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]),
     ("fuz_host_py27_str_dict_order", C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fuz_host_rr_bread_order", C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fuz_host_rr_format_rows", C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,

@@ -580,3 +580,46 @@ extern "C" int64_t fuz_host_format_atable(const int32_t *site_pos, const uint8_t
     }
     return p - out;
 }
+
+// phased_reads of one contig ("q_id ctg block phase n0 n1 qname", phasing.py:478,480): reads in the iteration
+// order of the reference's read_to_variants dict -- a CPython-2 dict with int keys inserted in order of first
+// appearance in variant_map.  vm_qid: the contig's variant_map rows; pr_*: the contig's
+// phased_reads rows, sorted by q_id; names: blob / offsets of the QNAME of every q_id.  Returns the size of the
+// text (call with out = NULL first), -1 if cap is too small or a q_id has no name.
+extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                                const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                                const char *ctg_id, const char *name_blob, const int64_t *name_off, int64_t n_names,
+                                                char *out, int64_t cap) {
+    if ((!vm_qid && n_vm) || (n_pr && (!pr_qid || !pr_block || !pr_phase || !pr_n0 || !pr_n1)) || !ctg_id || !name_blob || !name_off) return -1;
+    Py27Table tab;
+    auto eq = [](int64_t a, int64_t b) { return a == b; };
+    for (int64_t i = 0; i < n_vm; i++) {
+        const int64_t k = vm_qid[i];
+        tab.insert(k == -1 ? -2 : k, k, eq);                // hash(int) = the int (-1 -> -2); duplicates are ignored
+    }
+    const size_t ctg_len = strlen(ctg_id);
+    int64_t w = 0;
+    bool bad = false;
+    tab.each([&](int64_t q) {
+        const int32_t *lo = std::lower_bound(pr_qid, pr_qid + n_pr, (int32_t)q);
+        for (const int32_t *p = lo; p < pr_qid + n_pr && *p == (int32_t)q; p++) {
+            const int64_t i = p - pr_qid;
+            if (q < 0 || q >= n_names) { bad = true; return; }
+            const int64_t nl = name_off[q + 1] - name_off[q];
+            const int64_t need = 5 * 12 + (int64_t)ctg_len + nl + 8;
+            if (out) {
+                if (w + need > cap) { bad = true; return; }
+                char *s = out + w;
+                s = put_int(s, q); *s++ = ' ';
+                memcpy(s, ctg_id, ctg_len); s += ctg_len; *s++ = ' ';
+                s = put_int(s, pr_block[i]); *s++ = ' '; s = put_int(s, pr_phase[i]); *s++ = ' ';
+                s = put_int(s, pr_n0[i]); *s++ = ' '; s = put_int(s, pr_n1[i]); *s++ = ' ';
+                memcpy(s, name_blob + name_off[q], (size_t)nl); s += nl; *s++ = '\n';
+                w = s - out;
+            } else {
+                w += need;                                   // upper bound for the size query
+            }
+        }
+    });
+    return bad ? -1 : w;
+}

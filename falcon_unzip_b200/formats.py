@@ -126,20 +126,31 @@ def phased_variants_text(res, s0: int, s1: int, ref_base) -> str:
 def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, names) -> str:
     """phased_reads: ``q_id ctg block phase n0 n1 qname`` (phasing.py:478,480), reads in the
     iteration order of the reference's ``read_to_variants`` dict (Python-2 int dict, keys
-    inserted in order of first appearance in variant_map)."""
-    vq = res.vm_qid[v0:v1]
+    inserted in order of first appearance in variant_map).  Rows formatted in libfuz.
+    names: list of QNAMEs indexed by q_id, or a dict q_id -> QNAME (file-level stage)."""
+    vq = _c32(res.vm_qid[v0:v1])
     if len(vq) == 0:
         return ""
-    _, first = np.unique(vq, return_index=True)
-    order = py27_int_dict_order(vq[np.sort(first)])
-    q = res.pr_qid[r0:r1]
-    lo = np.searchsorted(q, order, side="left")
-    hi = np.searchsorted(q, order, side="right")
-    blk, ph = res.pr_block[r0:r1].tolist(), res.pr_phase[r0:r1].tolist()
-    n0, n1 = res.pr_n0[r0:r1].tolist(), res.pr_n1[r0:r1].tolist()
-    out: List[str] = []
-    for qq, a, b in zip(order.tolist(), lo.tolist(), hi.tolist()):
-        for i in range(a, b):
-            nm = names[qq] if not isinstance(names, dict) else names[qq]
-            out.append("%d %s %d %d %d %d %s\n" % (qq, ctg_id, blk[i], ph[i], n0[i], n1[i], nm))
-    return "".join(out)
+    if isinstance(names, dict):
+        n_names = max(names) + 1 if names else 0
+        get = names.get
+        name_list = [get(i, "") for i in range(n_names)]
+        missing = [int(q) for q in np.unique(res.pr_qid[r0:r1]).tolist() if q not in names]
+        if missing:
+            raise KeyError(missing[0])                     # rid_map[q_id] of the reference (phasing.py:478)
+    else:
+        name_list = names
+    enc = [n.encode("latin-1") for n in name_list]
+    name_off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+    blob = b"".join(enc) + b"\0"
+    cols = [_c32(getattr(res, k)[r0:r1]) for k in ("pr_qid", "pr_block", "pr_phase", "pr_n0", "pr_n1")]
+    args = (vq.ctypes.data, len(vq), *[c.ctypes.data for c in cols], r1 - r0, ctg_id.encode("latin-1"), blob, name_off.ctypes.data,
+            len(enc))
+    cap = lib().fuz_host_format_phased_reads(*args, None, 0)
+    if cap < 0:
+        raise IndexError("phased_reads row with a q_id that has no QNAME")
+    buf = C.create_string_buffer(int(cap) + 16)
+    n = lib().fuz_host_format_phased_reads(*args, buf, int(cap) + 16)
+    if n < 0:
+        raise RuntimeError("fuz_host_format_phased_reads failed")
+    return buf.raw[:n].decode("latin-1")

@@ -370,6 +370,13 @@ int64_t fuz_host_format_variant_map(const int32_t *site_pos, const int32_t *vm_s
                                     char *out, int64_t cap);
 int64_t fuz_host_format_atable(const int32_t *site_pos, const uint8_t *site_al, const int32_t *at_s1, const int32_t *at_s2,
                                const int32_t *at_ct, int64_t a0, int64_t a1, char *out, int64_t cap);
+/* Text of phased_reads of one contig (phasing.py:465-480): vm_qid = the contig's variant_map rows (they fix the row
+ * order: CPython-2 dict of int keys inserted at first appearance), pr_* = its phased_reads rows sorted
+ * by q_id, names = QNAME of every q_id.  With out = NULL returns an upper bound of the size; else the size, or -1. */
+int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                     const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                     const char *ctg_id, const char *name_blob, const int64_t *name_off, int64_t n_names,
+                                     char *out, int64_t cap);
 /* CPython-2.7 dict / set iteration order of str keys (Objects/stringobject.c string_hash + the insert-only table
  * of dictobject.c): keys[i] = blob[off[i], off[i+1]) inserted in order, duplicates ignored;
  * out = index of every distinct key in iteration order.  Returns the number of distinct keys. */
