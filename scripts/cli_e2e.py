@@ -1,6 +1,7 @@
-"""Whole user path for one configuration: BAM (BGZF) + FASTA on disk -> the six files per contig.
-Prints where the time goes (inflate, record index / q_ids, GPU call, text formatting + writing).
-Usage: cli_e2e.py [config] [contigs]"""
+"""Whole user path for one configuration: BAM (BGZF) + FASTA on disk -> the six files per contig, once with the BAM
+decoded on the device (phasing.phase_bam) and once with the host decoder (bam.read_bam + phasing.phase_contigs).
+Prints one JSON line.   Usage: cli_e2e.py [config] [contigs]"""
+import json
 import os
 import sys
 import tempfile
@@ -9,7 +10,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from falcon_unzip_b200 import bam, engine, formats, phasing, synth  # noqa: E402
+from falcon_unzip_b200 import bam, engine, phasing, synth  # noqa: E402
 
 
 def main():
@@ -23,41 +24,30 @@ def main():
     bam_fn, fa_fn = os.path.join(d, "in.bam"), os.path.join(d, "ref.fa")
     bam.write_bam(bam_fn, sset.refs, sset.records.tobytes())
     synth.write_fasta(fa_fn, sset)
-    print("BAM %.1f MB (%.1f MB of records), %d contigs" % (os.path.getsize(bam_fn) / 1e6, len(sset.records) / 1e6, len(sset.refs)))
     engine.get_engine(0)
-    acc = {}
+    out = {"config": cfg.name, "contigs": cfg.n_contigs, "bam_bytes": os.path.getsize(bam_fn), "record_bytes": int(len(sset.records))}
 
-    def timed(mod, name):
-        f = getattr(mod, name)
-
-        def w(*a, **k):
+    def best(f, n=3):
+        ts, r = [], None
+        for k in range(n):
             t0 = time.perf_counter()
-            try:
-                return f(*a, **k)
-            finally:
-                acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
-        setattr(mod, name, w)
-    timed(engine, "prepare_batch")
-    timed(engine.Engine, "phase_host")
-    timed(phasing, "write_contig_files")
-    timed(formats, "contig_slices")
-    for rep in range(2):
-        t = [time.perf_counter()]
-        _text, refs, recs = bam.read_bam(bam_fn); t.append(time.perf_counter())
-        ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fa_fn)}; t.append(time.perf_counter())
-        records = np.frombuffer(recs, dtype=np.uint8)
+            r = f(k)
+            ts.append(time.perf_counter() - t0)
+        return min(ts), r
+    t_dev, (res, files) = best(lambda k: phasing.phase_bam(bam_fn, fa_fn, os.path.join(d, "dev%d" % k)))
+
+    def host_path(k):
+        _text, refs, recs = bam.read_bam(bam_fn)
+        ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fa_fn)}
         names = [r[0] for r in refs]
-        out = os.path.join(d, "out%d" % rep)
-        t0 = time.perf_counter()
-        res, files = phasing.phase_contigs(records, names, [ref_seqs[n] for n in names], out)
-        t.append(time.perf_counter())
-        print("run %d: inflate+split %.3f s | fasta %.3f s | phase_contigs (index, q_ids, GPU, format, write) %.3f s | total %.3f s"
-              % (rep, t[1] - t[0], t[2] - t[1], t[3] - t0, t[3] - t[0]))
-        print("   inside phase_contigs: " + ", ".join("%s %.3f s" % kv for kv in acc.items()))
-        acc.clear()
-        print("   rows: sites %d vmap %d atable %d reads %d; aligned bases %.1f M -> %.2f G bases/s end to end"
-              % (res.n_sites, res.n_vmap, res.n_atable, res.n_reads, res.aligned_bases / 1e6,
-                 res.aligned_bases / (t[3] - t[0]) / 1e9))
+        return phasing.phase_contigs(np.frombuffer(recs, dtype=np.uint8), names, [ref_seqs[n] for n in names], os.path.join(d, "host%d" % k))
+    t_host, (res_h, files_h) = best(host_path, 2)
+    same = all(open(files[n][k]).read() == open(files_h[n][k]).read() for n in files for k in files[n])
+    out.update(aligned_bases=int(res.aligned_bases), files=sum(len(v) for v in files.values()), identical_to_host_decoded_path=bool(same),
+               device_decode_s=t_dev, device_decode_bases_per_s=res.aligned_bases / t_dev,
+               host_decode_s=t_host, host_decode_bases_per_s=res.aligned_bases / t_host, host_threads=min(32, os.cpu_count() or 1),
+               rows={"sites": res.n_sites, "variant_map": res.n_vmap, "atable": res.n_atable, "phased_reads": res.n_reads})
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
