@@ -474,11 +474,41 @@ class Engine:
         return DeviceBam(refs, raw, rec_ptr, rec_bytes, rec_off, ctg_rec_off, int(n_rec.value), n_mapped, h2d,
                          keep=(d_comp, d_coff, d_csize, d_uoff, d_crc))
 
-    def phase_bam(self, image, caps: Optional[Dict[str, int]] = None, verify_crc: bool = True):
-        """BAM file image -> (PhaseResult, BamBatchInfo): ingest_bam, then the four stages for every
-        reference of the BAM in one device call (q_ids assigned on the device)."""
+    def ingest_bams(self, images: Sequence, verify_crc: bool = True) -> DeviceBam:
+        """Several BAM files (the reference makes one sorted BAM per contig, unzip.py:90) as ONE device batch: every
+        file is decoded on the device (ingest_bam), the mapped records of all files are laid out back to back and
+        the reference lists are concatenated (names must be unique across the files)."""
         torch = self._torch
-        db = self.ingest_bam(image, verify_crc)
+        parts = [self.ingest_bam(im, verify_crc) for im in images]
+        if len(parts) == 1:
+            return parts[0]
+        dev = self.device
+        names = [r[0] for p in parts for r in p.refs]
+        if len(set(names)) != len(names):
+            raise FuzError(_lib.FUZ_E_ARG, "the BAM files list the same reference name more than once")
+        used = [int(p.rec_off[p.n_mapped].item()) if p.n_mapped else 0 for p in parts]     # bytes of the mapped records
+        total = sum(used)
+        raw = torch.empty(total + 64, dtype=torch.uint8, device=dev)
+        raw[total:].zero_()
+        rec_off, ctg_rec_off, at, rec_base = [], [], 0, 0
+        for p, u in zip(parts, used):
+            o = p.rec_ptr - p.raw.data_ptr()
+            raw[at:at + u].copy_(p.raw[o:o + u])
+            rec_off.append(p.rec_off[:p.n_mapped] + at)
+            ctg_rec_off.append(p.ctg_rec_off[:len(p.refs)] + rec_base)
+            at += u
+            rec_base += p.n_mapped
+        rec_off.append(torch.tensor([total], dtype=torch.int64, device=dev))
+        ctg_rec_off.append(torch.tensor([rec_base], dtype=torch.int32, device=dev))
+        torch.cuda.synchronize(dev)
+        return DeviceBam([r for p in parts for r in p.refs], raw, raw.data_ptr(), total, torch.cat(rec_off), torch.cat(ctg_rec_off),
+                         rec_base, rec_base, sum(p.h2d_bytes for p in parts))
+
+    def phase_bam(self, image, caps: Optional[Dict[str, int]] = None, verify_crc: bool = True):
+        """BAM file image (or a list of images, see ingest_bams) -> (PhaseResult, BamBatchInfo): the BAM is decoded
+        on the device, then the four stages run for every reference in one device call (q_ids assigned on the device)."""
+        torch = self._torch
+        db = self.ingest_bams(image, verify_crc) if isinstance(image, (list, tuple)) else self.ingest_bam(image, verify_crc)
         n_ctg = len(db.refs)
         if n_ctg < 1:
             raise FuzError(_lib.FUZ_E_ARG, "the BAM header lists no reference sequence")

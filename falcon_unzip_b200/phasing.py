@@ -342,11 +342,14 @@ def phase_contigs(records, ctg_names: Sequence[str], ref_seqs: Sequence[str], ba
     return res, out
 
 
-def phase_bam(bam_fn: str, fasta_fn: str, base_dir: str, device: int = 0, verify_crc: bool = True):
-    """Every contig of a coordinate-sorted BAM in one go, decoded on the device: the file image is
+def phase_bam(bam_fn, fasta_fn: str, base_dir: str, device: int = 0, verify_crc: bool = True):
+    """Every contig of a coordinate-sorted BAM (or of a list of BAMs, e.g. one per contig) in one go, decoded on the device: the file image is
     uploaded as it is, BGZF inflate + record split (the `samtools view` pipe of phasing.py:27), the
     QNAME -> q_id table and the four stages run in HBM; the same six files per contig come out."""
-    image = np.fromfile(bam_fn, dtype=np.uint8)
+    if isinstance(bam_fn, (list, tuple)):                 # one sorted BAM per contig, as unzip.py:90 leaves them
+        image = [np.fromfile(fn_, dtype=np.uint8) for fn_ in bam_fn]
+    else:
+        image = np.fromfile(bam_fn, dtype=np.uint8)
     ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fasta_fn)}
     eng = engine.get_engine(device)
     res, info = eng.phase_bam(image, verify_crc=verify_crc)

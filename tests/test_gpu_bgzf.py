@@ -295,3 +295,32 @@ def test_inflate_fuzz(eng):
     assert st.error == 0, (st.error, st.error_index, st.reserved[3])
     for k, ((d, _c), got) in enumerate(zip(blocks, outs)):
         assert got == d, k
+
+
+def test_phase_bam_from_one_file_per_contig(eng, tmp_path):
+    """The reference leaves one sorted BAM per contig (unzip.py:90), each with its own one-entry header and refID 0:
+    a list of such files goes through one device batch and gives the files of the single-BAM run."""
+    import struct
+    from falcon_unzip_b200 import bam, phasing, synth
+    sset = synth_set("quirks")
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, sset)
+    fns = []
+    for c, (name, ln) in enumerate(sset.refs):
+        rec = np.frombuffer(sset.contig_records(c), np.uint8).copy()
+        off = bam.index_records(rec.tobytes())
+        for o in off[:-1].tolist():
+            rec[o + 4:o + 8] = np.frombuffer(struct.pack("<i", 0), np.uint8)          # refID 0 inside its own file
+        tail = bam.encode_record(-1, -1, "unmapped/%d" % c, 4, 0, [], "ACGT" * 10) if c % 2 == 0 else b""
+        fn = str(tmp_path / ("%s_sorted.bam" % name))
+        bam.write_bam(fn, [(name, ln)], rec.tobytes() + tail)
+        fns.append(fn)
+    one = str(tmp_path / "all.bam")
+    bam.write_bam(one, sset.refs, sset.records.tobytes())
+    res_m, files_m = phasing.phase_bam(fns, fa, str(tmp_path / "many"))
+    res_1, files_1 = phasing.phase_bam(one, fa, str(tmp_path / "one"))
+    assert (res_m.n_sites, res_m.n_vmap, res_m.n_atable, res_m.n_reads) == (res_1.n_sites, res_1.n_vmap, res_1.n_atable, res_1.n_reads)
+    assert res_m.n_sites > 0
+    for n in files_1:
+        for k in files_1[n]:
+            assert open(files_m[n][k]).read() == open(files_1[n][k]).read(), (n, k)
