@@ -68,3 +68,26 @@ def phase_bam_sharded(bam_fn: str, fasta_fn: str, base_dir: str, rank: int = 0, 
     except ImportError:
         pass
     return dict(rank=rank, mine=done, all=[c for part in gathered for c in part], n_contigs=len(refs))
+
+
+def phase_bam_files_sharded(bam_fns: Sequence[str], fasta_fn: str, base_dir: str, rank: int = 0, world_size: int = 1,
+                            device: Optional[int] = None, phase_fn: Optional[Callable] = None) -> Dict[str, object]:
+    """The reference's layout -- one sorted BAM per contig (unzip.py:90) -- over the GPUs of a box: the files are
+    dealt to the ranks by size (longest-processing-time first), every rank decodes and phases ITS files in one device
+    batch (phasing.phase_bam with a list) and writes their per-contig files.  No collective on the data path; the
+    list of finished files is gathered when torch.distributed is initialised."""
+    from . import phasing
+    fns = list(bam_fns)
+    mine = [fns[i] for i in assign_contigs([float(os.path.getsize(f)) for f in fns], world_size)[rank]]
+    if mine:
+        fn = phase_fn or (lambda files, fa, bd: phasing.phase_bam(files, fa, bd, device=device if device is not None else 0))
+        fn(mine, fasta_fn, base_dir)
+    gathered = [mine]
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and world_size > 1:
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, mine)
+    except ImportError:
+        pass
+    return dict(rank=rank, mine=mine, all=[f for part in gathered for f in part], n_files=len(fns))

@@ -54,3 +54,36 @@ def test_world_size_2_gloo(tmp_path):
     mp.spawn(_worker, args=(2, bam_fn, fa_fn, str(tmp_path / "out"), port), nprocs=2, join=True)
     ranks = {n: open(tmp_path / "out" / n / "rank").read().split()[0] for n, _l in sset.refs}
     assert set(ranks.values()) == {"0", "1"}
+
+
+def _worker_files(rank, world, fns, fa_fn, out_dir, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seen = []
+
+    def fake_phase(files, fa, base_dir):
+        for f in files:
+            os.makedirs(base_dir, exist_ok=True)
+            with open(os.path.join(base_dir, os.path.basename(f) + ".rank"), "w") as g:
+                g.write("%d\n" % rank)
+        seen.extend(files)
+    res = shard.phase_bam_files_sharded(fns, fa_fn, out_dir, rank, world, phase_fn=fake_phase)
+    assert res["mine"] == seen and sorted(res["all"]) == sorted(fns) and res["n_files"] == len(fns)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_files_world_size_2_gloo(tmp_path):
+    """One BAM per contig dealt to two ranks by size: every file is phased exactly once, both ranks work."""
+    fns = []
+    for i, size in enumerate([5000, 100, 3000, 2500, 50, 4000]):
+        fn = str(tmp_path / ("%06dF_sorted.bam" % i))
+        open(fn, "wb").write(b"\0" * size)
+        fns.append(fn)
+    port = 30500 + os.getpid() % 2000
+    mp.spawn(_worker_files, args=(2, fns, str(tmp_path / "ref.fa"), str(tmp_path / "out"), port), nprocs=2, join=True)
+    ranks = [open(tmp_path / "out" / (os.path.basename(f) + ".rank")).read().strip() for f in fns]
+    assert set(ranks) == {"0", "1"}
+    sizes = [5000, 100, 3000, 2500, 50, 4000]
+    loads = [sum(s for s, r in zip(sizes, ranks) if r == k) for k in ("0", "1")]
+    assert abs(loads[0] - loads[1]) <= max(sizes)
