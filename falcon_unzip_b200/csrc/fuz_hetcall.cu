@@ -44,24 +44,48 @@ __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_m
 // candidate record range, contig and evaluation limit of every pileup tile.  The limit is
 // POS_last of the contig in global coordinates: the start of the last accepted record in
 // file order; positions >= POS_last are never evaluated (no final flush, phasing.py:98-129).
-__global__ void k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict__ ctg_goff,
-                              const int32_t *__restrict__ ctg_rec_off, HetScratch S, const fuz_status *st) {
+// One WARP per tile: the searches are 32-ary (every lane probes one pivot, a ballot picks the interval), so a tile
+// costs ~7 dependent memory round trips instead of ~25 with one thread and binary searches.
+// first index in [lo, hi) with a[i] >= key (a ascending), all lanes of the warp cooperate
+template <typename T>
+__device__ __forceinline__ int fuz_warp_lower_bound(const T *__restrict__ a, int lo, int hi, T key, int lane) {
+    while (hi - lo > 32) {
+        const int n = hi - lo, step = (n + 31) >> 5;                 // 32 pivots: lo + (k + 1) * step - 1
+        const int p = min(lo + (lane + 1) * step - 1, hi - 1);
+        const uint32_t ge = __ballot_sync(0xffffffffu, a[p] >= key);   // monotone: a suffix of the lanes
+        const int k = ge ? __ffs(ge) - 1 : 32;                         // first pivot >= key
+        const int nlo = lo + k * step;                                 // everything before pivot k-1 (inclusive) is < key
+        if (k < 32) hi = min(lo + (k + 1) * step - 1, hi - 1) + 1;
+        lo = min(nlo, hi);
+        if (k == 32) break;                                            // every pivot < key: the answer is hi
+    }
+    const int i = lo + lane;
+    const uint32_t ge = __ballot_sync(0xffffffffu, i < hi && a[i] >= key);
+    return ge ? lo + __ffs(ge) - 1 : hi;
+}
+
+__global__ void __launch_bounds__(256) k_tile_ranges(int n_tiles, int n_ctg, const int64_t *__restrict__ ctg_goff,
+                                                     const int32_t *__restrict__ ctg_rec_off, HetScratch S, const fuz_status *st) {
     fuz_pdl_enter();
     if (st->error) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
-        int64_t t0 = (int64_t)t * FUZ_TILE;
-        int lo = 0, hi = n_ctg + 1;                      // last c with ctg_goff[c] <= t0
-        while (lo < hi) { int m = (lo + hi) >> 1; if (ctg_goff[m] <= t0) lo = m + 1; else hi = m; }
-        int c = lo - 1;
+    const int lane = threadIdx.x & 31;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += (gridDim.x * blockDim.x) >> 5) {
+        const int64_t t0 = (int64_t)t * FUZ_TILE;
+        // last c with ctg_goff[c] <= t0  =  (first c with ctg_goff[c] >= t0 + 1) - 1
+        int c = fuz_warp_lower_bound<int64_t>(ctg_goff, 0, n_ctg + 1, t0 + 1, lane) - 1;
         if (c >= n_ctg) c = n_ctg - 1;
-        int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
-        int t1 = (int)(t0 + FUZ_TILE);
-        int span = S.ctg_maxspan[c];
-        int lr = S.ctg_last_rec[c];
-        S.tile_ctg[t] = c;
-        S.tile_limit[t] = lr >= 0 ? S.r_gstart[lr] : (int32_t)ctg_goff[c];
-        S.tile_rlo[t] = fuz_lower_bound(S.r_gstart, r0, r1, (int)t0 - span + 1);
-        S.tile_rhi[t] = fuz_lower_bound(S.r_gstart, r0, r1, t1);
+        const int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
+        const int t1 = (int)(t0 + FUZ_TILE);
+        const int span = S.ctg_maxspan[c];
+        const int lr = S.ctg_last_rec[c];
+        const int rlo = fuz_warp_lower_bound<int32_t>(S.r_gstart, r0, r1, (int)t0 - span + 1, lane);
+        const int rhi = fuz_warp_lower_bound<int32_t>(S.r_gstart, r0, r1, t1, lane);
+        if (lane == 0) {
+            S.tile_ctg[t] = c;
+            S.tile_limit[t] = lr >= 0 ? S.r_gstart[lr] : (int32_t)ctg_goff[c];
+            S.tile_rlo[t] = rlo;
+            S.tile_rhi[t] = rhi;
+        }
     }
 }
 
@@ -832,7 +856,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");
         }
-        fuz_launch(ctx, k_tile_ranges, (n_tiles + 255) / 256, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
         fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_TILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
@@ -849,7 +873,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
             FUZ_LAUNCH_CHECK(ctx, "k_pileup_atomic");
         }
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
-        fuz_launch(ctx, k_tile_ranges, (n_tiles + 255) / 256, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
         fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_TILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
