@@ -101,3 +101,17 @@ def test_parser_fuzz(eng):
     assert DL.n == HL.n >= 20000
     for k in ("q", "t", "len", "qs", "qe", "ql", "ts", "te", "tl", "flags", "off", "llen"):
         assert np.array_equal(DL.a[k], HL.a[k]), k
+
+
+def test_capacity_retry_and_empty_filter_input(eng, monkeypatch):
+    """Short lines exceed the line-count estimate (capacity retry inside DeviceLines); an overlap filter call whose
+    files are all empty returns no text."""
+    from falcon_unzip_b200 import la4falcon, ovlp_filter_with_phase as ofp
+    blob = b"1 2 -3 9 0 0 1 1 0 0 1 1 x\n" * 5000
+    DL = la4falcon.DeviceLines([blob], False)
+    assert DL.n == 5000 and DL.a["q"].tolist() == [1] * 5000 and DL.a["len"][0] == 3 and DL.a["flags"][4999] == 0
+    monkeypatch.setattr(ofp, "read_las_lines", lambda db, fn: b"")
+    ofp.arid2phase.clear()
+    ofp.arid2phase.update({"000000001": ("c", "1", "0")})
+    assert ofp.run_ovlp_filter(["a.las", "b.las"], "db", 120, 120, 1, 2500, 10) == b""
+    assert ofp.filter_stage1(("db", "a.las", 120, 120, 1, 2500)) == ("a.las", [])
