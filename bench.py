@@ -45,16 +45,19 @@ def parse_args():
     ap.add_argument("--no-bam", action="store_true", help="skip the BAM-ingest leg (BGZF file image -> rows, N=1 only)")
     ap.add_argument("--replicate", type=int, default=1, help="repeat the workload's contigs (named in config)")
     ap.add_argument("--contigs", type=int, default=0, help="use only the first N contigs of the config (named in config)")
+    ap.add_argument("--contig-len", type=int, default=0, help="override the contig length of the config (stress cases; named in config)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library option for experiments (fuz_set_option), e.g. pdl=0; recorded in config")
     return ap.parse_args()
 
 
-def make_workload(name: str, rank: int, replicate: int = 1, contigs: int = 0):
+def make_workload(name: str, rank: int, replicate: int = 1, contigs: int = 0, contig_len: int = 0):
     from falcon_unzip_b200 import synth
     cfg = synth.CONFIGS[name]
     if contigs:
         cfg = dataclasses.replace(cfg, n_contigs=contigs)
+    if contig_len:
+        cfg = dataclasses.replace(cfg, contig_len=contig_len)
     cfg = dataclasses.replace(cfg, first_contig=rank * cfg.n_contigs * replicate, n_contigs=cfg.n_contigs * replicate)
     return cfg, synth.generate_parallel(cfg)
 
@@ -208,7 +211,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg, sset = make_workload(args.config, 0, args.replicate, args.contigs)
+    cfg, sset = make_workload(args.config, 0, args.replicate, args.contigs, args.contig_len)
     cores = os.cpu_count() or 1
     threads = min(cores, len(sset.refs))
     for _ in range(min(args.warmup, 1)):
@@ -235,7 +238,7 @@ def workload_config(cfg, sset, args, aligned_bases):
     return {"workload": "BASELINE.json configs[1]: synthetic E. coli-scale diploid, %d contigs x %d bp, %.0fx %d bp reads, "
                         "%.1f%% het, %.0f%% error" % (cfg.n_contigs, cfg.contig_len, cfg.coverage, cfg.mean_read_len,
                                                       100 * cfg.het_rate, 100 * cfg.error_rate)
-            if args.config == "c2" and args.replicate == 1 and not args.contigs else
+            if args.config == "c2" and args.replicate == 1 and not args.contigs and not args.contig_len else
             "synthetic %s x%d: %d contigs x %d bp, %.0fx" % (args.config, args.replicate, cfg.n_contigs, cfg.contig_len, cfg.coverage),
             "contigs_per_gpu": cfg.n_contigs, "records_per_gpu": int(len(sset.rec_off) - 1),
             "aligned_bases_per_gpu_step": int(aligned_bases), "record_bytes_per_gpu": int(len(sset.records)),
@@ -288,7 +291,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg, sset = make_workload(args.config, rank, args.replicate, args.contigs)      # before CUDA init (fork)
+    cfg, sset = make_workload(args.config, rank, args.replicate, args.contigs, args.contig_len)      # before CUDA init (fork)
     alg = algorithmic_bytes(sset)
 
     import torch
