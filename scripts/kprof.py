@@ -17,8 +17,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--replicate", type=int, default=1)
     ap.add_argument("--contigs", type=int, default=0)
+    ap.add_argument("--contig-len", type=int, default=0)
     a = ap.parse_args()
-    cfg, sset = bench.make_workload(a.config, 0, a.replicate, a.contigs)
+    cfg, sset = bench.make_workload(a.config, 0, a.replicate, a.contigs, a.contig_len)
     import torch
     from falcon_unzip_b200 import engine
     eng = engine.Engine(0)
