@@ -7,7 +7,6 @@ is evaluated with Python's float(), as the reference does for every line."""
 from __future__ import annotations
 
 import bisect
-import ctypes as C
 import re
 from typing import Dict, List, Optional, Sequence
 

@@ -15,7 +15,7 @@ import argparse
 import logging
 import os
 import sys
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 from . import py2compat
 
