@@ -402,6 +402,246 @@ __global__ void __launch_bounds__(256) k_bam_ctg_ranges(const uint8_t *__restric
     }
 }
 
+// ---------------------------------------------------------------- record index of SEVERAL files in one buffer
+// fuz_bam_index_files: the reference leaves one sorted BAM per contig (unzip.py:90).  All files are inflated by ONE
+// launch of k_bgzf_inflate into one buffer; file s ("segment") has its records at raw[seg_start[s], seg_end[s]).  The
+// chain regions of all segments are anchored in one launch, one warp per segment threads its regions together, and the
+// mapped records of all segments are written back to back (their unmapped tails and the headers between them dropped).
+struct BamFilesScratch {
+    const int64_t *seg_start, *seg_end, *seg_reg0;   // [n_seg], [n_seg], [n_seg + 1] first region of the segment
+    const int32_t *seg_nref, *seg_ctg0, *reg_seg;    // [n_seg], [n_seg + 1] first contig of the segment, [n_reg] segment of a region
+    int32_t *seg_cnt, *seg_base;                     // records of the segment; exclusive scan [n_seg + 1]
+    int32_t *loc;                                    // [n_ctg + n_seg] per segment: n_ref + 1 LOCAL record offsets of its references
+    int32_t *mbase;                                  // [n_seg + 1] first mapped record of the segment in the output
+    int64_t *bbase, *mbytes;                         // [n_seg + 1] its first output byte; [n_seg] bytes of its mapped records
+    int64_t *tmp_off;                                // [cap_rec + 1] offsets of ALL records in raw
+    int64_t *totals;                                 // [0] mapped records, [1] all records (capacity needed), [2] mapped bytes
+};
+
+__global__ void __launch_bounds__(256) k_bamf_anchor(const uint8_t *__restrict__ raw, int64_t n_reg, BamIndexScratch S, BamFilesScratch F,
+                                                     const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_reg) return;
+    const int s = F.reg_seg[k];
+    const int64_t n = F.seg_end[s], lk = k - F.seg_reg0[s];
+    const int n_ref = F.seg_nref[s];
+    const int64_t a = F.seg_start[s] + lk * FUZ_BAM_REGION, e = min(a + FUZ_BAM_REGION, n);
+    int64_t c = -1;
+    if (lk == 0) c = a;
+    for (int64_t base = a; c < 0 && base < e; base += 32) {
+        const int64_t o = base + lane;
+        int64_t nx;
+        bool ok = o < e && rec_header_ok(raw, o, n, n_ref);
+        if (ok) ok = rec_chain_ok(raw, o, n, &nx) && (nx == n || rec_header_ok(raw, nx, n, n_ref));
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) c = base + __ffs(m) - 1;
+    }
+    if (lane) return;
+    int64_t o = c, cnt = 0;
+    if (c >= 0) {
+        while (o < e) {
+            int64_t nx;
+            if (!rec_chain_ok(raw, o, n, &nx)) { o = -2; break; }
+            cnt++;
+            o = nx;
+        }
+    }
+    S.first[k] = c; S.land[k] = o; S.cnt[k] = (int32_t)cnt;
+}
+
+// one warp per segment; the algorithm of k_bam_resolve on the regions of that segment (S.base = LOCAL record index)
+__global__ void __launch_bounds__(128) k_bamf_resolve(const uint8_t *__restrict__ raw, int n_seg, BamIndexScratch S, BamFilesScratch F,
+                                                      fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (s >= n_seg) return;
+    const int64_t s0 = F.seg_start[s], n = F.seg_end[s], r0 = F.seg_reg0[s], n_reg = F.seg_reg0[s + 1] - r0;
+    int64_t E = s0, N = 0;
+    bool bad = false;
+    for (int64_t k0 = 0; k0 < n_reg && !bad; k0 += 32) {
+        const int64_t k = k0 + lane;
+        const bool in = k < n_reg;
+        const int64_t first = in ? S.first[r0 + k] : -1, land = in ? S.land[r0 + k] : -1;
+        const int cnt = in ? S.cnt[r0 + k] : 0;
+        const int64_t end = min(s0 + (k + 1) * FUZ_BAM_REGION, n);
+        const bool has = in && first >= 0 && land >= 0;
+        int64_t lmax = has ? land : -1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, lmax, d);
+            if (lane >= d) lmax = max(lmax, t);
+        }
+        int64_t e_in = __shfl_up_sync(0xffffffffu, lmax, 1);
+        if (lane == 0) e_in = -1;
+        e_in = max(e_in, E);
+        const bool ok = !in || (has ? first == e_in : e_in >= end);
+        if (__all_sync(0xffffffffu, ok)) {
+            const int c = has ? cnt : 0;
+            const int incl = fuz_warp_incl_scan(c, lane);
+            if (in) { S.entry[r0 + k] = has ? e_in : -1; S.base[r0 + k] = (int32_t)(N + incl - c); }
+            N += __shfl_sync(0xffffffffu, incl, 31);
+            E = max(E, __shfl_sync(0xffffffffu, lmax, 31));
+            continue;
+        }
+        if (lane == 0) {
+            const int m = (int)min((int64_t)32, n_reg - k0);
+            for (int i = 0; i < m && !bad; i++) {
+                const int64_t kk = k0 + i, e2 = min(s0 + (kk + 1) * FUZ_BAM_REGION, n);
+                if (E >= e2) { S.entry[r0 + kk] = -1; S.base[r0 + kk] = (int32_t)N; continue; }
+                S.entry[r0 + kk] = E; S.base[r0 + kk] = (int32_t)N;
+                if (S.first[r0 + kk] == E && S.land[r0 + kk] >= 0) { N += S.cnt[r0 + kk]; E = S.land[r0 + kk]; continue; }
+                while (E < e2) {
+                    int64_t nx;
+                    if (!rec_chain_ok(raw, E, n, &nx)) { bad = true; break; }
+                    N++;
+                    E = nx;
+                }
+            }
+        }
+        E = __shfl_sync(0xffffffffu, E, 0); N = __shfl_sync(0xffffffffu, N, 0);
+        bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
+    }
+    if (lane == 0) {
+        if (bad || E != n || N > 0x7fffffff) { fuz_raise(st, FUZ_E_BADRECORD, s); F.seg_cnt[s] = 0; }
+        else F.seg_cnt[s] = (int32_t)N;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_bamf_scan_seg(int n_seg, int64_t cap_rec, BamFilesScratch F, fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;                         // uniform: read before any thread of this kernel can raise
+    const long long total = fuz_cta_scan_i32(F.seg_cnt, F.seg_base, n_seg);
+    if (threadIdx.x == 0) {
+        F.totals[1] = total;
+        if (total > cap_rec || total > 0x7fffffff) fuz_raise(st, FUZ_E_CAPACITY, 7);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bamf_fill(const uint8_t *__restrict__ raw, int64_t n_reg, BamIndexScratch S, BamFilesScratch F,
+                                                   const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_reg) return;
+    const int s = F.reg_seg[k];
+    int64_t o = S.entry[k], i = (int64_t)F.seg_base[s] + S.base[k];
+    const int64_t end = min(F.seg_start[s] + (k - F.seg_reg0[s] + 1) * FUZ_BAM_REGION, F.seg_end[s]);
+    while (o >= 0 && o < end) {
+        F.tmp_off[i++] = o;
+        o += 4 + (int64_t)(int32_t)ld_u32(raw + o);
+    }
+}
+
+// per segment what k_bam_ctg_ranges does for one file, with LOCAL record indices: loc[c] = first record of the segment with
+// refID >= c; loc[n_ref] = its mapped records
+__global__ void __launch_bounds__(256) k_bamf_ranges(const uint8_t *__restrict__ raw, int n_seg, BamFilesScratch F, fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t n_all = F.seg_base[n_seg];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_all; r += (int64_t)gridDim.x * blockDim.x) {
+        const int s = fuz_upper_bound(F.seg_base, 0, n_seg + 1, (int)r) - 1;     // the last segment starting at or before r
+        const int j = (int)(r - F.seg_base[s]), n_ref = F.seg_nref[s], cnt = F.seg_cnt[s];
+        int32_t *loc = F.loc + F.seg_ctg0[s] + s;
+        int ref = (int32_t)ld_u32(raw + F.tmp_off[r] + 4);
+        if (ref < -1 || ref >= n_ref) { fuz_raise(st, FUZ_E_BADRECORD, (int)r); continue; }
+        if (ref < 0) ref = n_ref;
+        int prev = -1;
+        if (j > 0) {
+            prev = (int32_t)ld_u32(raw + F.tmp_off[r - 1] + 4);
+            if (prev < 0 || prev > n_ref) prev = n_ref;
+            if (prev > ref) { fuz_raise(st, FUZ_E_UNSORTED, (int)r); continue; }
+        }
+        for (int c = prev + 1; c <= ref; c++) loc[c] = j;
+        if (j == cnt - 1)
+            for (int c = ref + 1; c <= n_ref; c++) loc[c] = cnt;
+    }
+}
+
+// one warp: where the mapped records of every segment go (records and bytes), totals, closing entries of the outputs
+__global__ void __launch_bounds__(32) k_bamf_scan_mapped(int n_seg, int n_ctg, int64_t cap_bytes, BamFilesScratch F,
+                                                         int64_t *__restrict__ rec_off, int32_t *__restrict__ ctg_rec_off, fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int lane = threadIdx.x;
+    long long R = 0, B = 0;
+    for (int s0 = 0; s0 < n_seg; s0 += 32) {
+        const int s = s0 + lane;
+        long long m = 0, b = 0;
+        if (s < n_seg) {
+            const int cnt = F.seg_cnt[s];
+            m = F.loc[F.seg_ctg0[s] + s + F.seg_nref[s]];
+            b = (m < cnt ? F.tmp_off[F.seg_base[s] + m] : F.seg_end[s]) - F.seg_start[s];
+            F.mbytes[s] = b;
+        }
+        long long mi = m, bi = b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, mi, d), u = __shfl_up_sync(0xffffffffu, bi, d);
+            if (lane >= d) { mi += t; bi += u; }
+        }
+        if (s < n_seg) { F.mbase[s] = (int32_t)(R + mi - m); F.bbase[s] = B + bi - b; }
+        R += __shfl_sync(0xffffffffu, mi, 31);
+        B += __shfl_sync(0xffffffffu, bi, 31);
+    }
+    if (lane == 0) {
+        F.mbase[n_seg] = (int32_t)R; F.bbase[n_seg] = B;
+        F.totals[0] = R; F.totals[2] = B;
+        if (B > cap_bytes) fuz_raise(st, FUZ_E_CAPACITY, 8);
+        else { rec_off[R] = B; ctg_rec_off[n_ctg] = (int32_t)R; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bamf_finalize(int n_seg, int n_ctg, BamFilesScratch F, int64_t *__restrict__ rec_off,
+                                                       int32_t *__restrict__ ctg_rec_off, const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t n_all = F.seg_base[n_seg], t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = t0; r < n_all; r += nt) {
+        const int s = fuz_upper_bound(F.seg_base, 0, n_seg + 1, (int)r) - 1;
+        const int j = (int)(r - F.seg_base[s]);
+        if (j < F.loc[F.seg_ctg0[s] + s + F.seg_nref[s]]) rec_off[F.mbase[s] + j] = F.bbase[s] + (F.tmp_off[r] - F.seg_start[s]);
+    }
+    for (int64_t g = t0; g < n_ctg; g += nt) {
+        const int s = fuz_upper_bound(F.seg_ctg0, 0, n_seg + 1, (int)g) - 1;
+        ctg_rec_off[g] = F.mbase[s] + F.loc[F.seg_ctg0[s] + s + ((int)g - F.seg_ctg0[s])];
+    }
+}
+
+// one CTA per region: its share of the segment's mapped bytes to their place in the output (128-bit stores; the source
+// is realigned from 32-bit words)
+__global__ void __launch_bounds__(256) k_bamf_copy(const uint8_t *__restrict__ raw, uint8_t *__restrict__ out, BamFilesScratch F,
+                                                   const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    const int64_t k = blockIdx.x;
+    const int s = F.reg_seg[k];
+    const int64_t s0 = F.seg_start[s];
+    const int64_t a = s0 + (k - F.seg_reg0[s]) * FUZ_BAM_REGION, e = min(a + FUZ_BAM_REGION, s0 + F.mbytes[s]);
+    if (a >= e) return;
+    const uint8_t *src = raw + a;
+    uint8_t *dst = out + F.bbase[s] + (a - s0);
+    const int64_t n = e - a;
+    const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    const int64_t body = (n - head) >> 4;
+    for (int64_t t = threadIdx.x; t < head; t += blockDim.x) dst[t] = src[t];
+    for (int64_t q = threadIdx.x; q < body; q += blockDim.x) {
+        const uintptr_t p = reinterpret_cast<uintptr_t>(src + head + 16 * q);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(p & 3) * 8;
+        const uint32_t x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3), x4 = __ldg(w + 4);   // raw has slack
+        uint4 v;
+        v.x = __funnelshift_r(x0, x1, sh); v.y = __funnelshift_r(x1, x2, sh);
+        v.z = __funnelshift_r(x2, x3, sh); v.w = __funnelshift_r(x3, x4, sh);
+        *reinterpret_cast<uint4 *>(dst + head + 16 * q) = v;
+    }
+    for (int64_t t = head + 16 * body + threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- host side
@@ -502,5 +742,102 @@ extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t
     rc = fuz_get_status(ctx, &hs);                 // synchronises
     *h_n_rec = h[0];
     if (h_need_rec) *h_need_rec = h[1];
+    return rc;
+}
+
+extern "C" int fuz_bam_index_files(fuz_ctx *ctx, const uint8_t *d_raw, int64_t raw_bytes, int32_t n_seg, const int64_t *h_seg_start,
+                                   const int64_t *h_seg_end, const int32_t *h_seg_nref, int64_t cap_rec, uint8_t *d_rec_out,
+                                   int64_t cap_bytes, int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec,
+                                   int64_t *h_need_rec, int64_t *h_rec_bytes) {
+    if (!ctx || !d_raw || raw_bytes < 0 || n_seg < 1 || !h_seg_start || !h_seg_end || !h_seg_nref || cap_rec < 0 || !d_rec_out ||
+        cap_bytes < 0 || !d_rec_off || !d_ctg_rec_off || !h_n_rec)
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_files: bad argument");
+    if (raw_bytes / 36 > 0x7fffffff) return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_files: more than 2^31 records possible; split the batch");
+    // host tables: segments, their regions and contigs
+    std::vector<int64_t> reg0((size_t)n_seg + 1, 0);
+    std::vector<int32_t> ctg0((size_t)n_seg + 1, 0);
+    int64_t prev_end = 0;
+    for (int32_t s = 0; s < n_seg; s++) {
+        if (h_seg_start[s] < prev_end || h_seg_end[s] < h_seg_start[s] || h_seg_end[s] > raw_bytes || h_seg_nref[s] < 0)
+            return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_files: segment %d is not inside the buffer / not in ascending order", (int)s);
+        prev_end = h_seg_end[s];
+        reg0[s + 1] = reg0[s] + (h_seg_end[s] - h_seg_start[s] + FUZ_BAM_REGION - 1) / FUZ_BAM_REGION;
+        const int64_t c = (int64_t)ctg0[s] + h_seg_nref[s];
+        if (c > 0x7fffffff - n_seg) return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_files: too many references");
+        ctg0[s + 1] = (int32_t)c;
+    }
+    const int64_t n_reg = reg0[n_seg];
+    const int32_t n_ctg = ctg0[n_seg];
+    std::vector<int32_t> reg_seg((size_t)n_reg);
+    for (int32_t s = 0; s < n_seg; s++)
+        for (int64_t k = reg0[s]; k < reg0[s + 1]; k++) reg_seg[(size_t)k] = s;
+
+    cudaStream_t st = ctx->stream;
+    FuzLayout L;
+    const size_t ns = (size_t)n_seg, nr = (size_t)n_reg;
+    // uploaded tables first (one copy)
+    const size_t o_start = L.add(8 * ns), o_end = L.add(8 * ns), o_reg0 = L.add(8 * (ns + 1));
+    const size_t o_nref = L.add(4 * ns), o_ctg0 = L.add(4 * (ns + 1)), o_regseg = L.add(4 * (nr + 1));
+    const size_t tab_bytes = L.off;
+    const size_t o_first = L.add(8 * (nr + 1)), o_land = L.add(8 * (nr + 1)), o_entry = L.add(8 * (nr + 1));
+    const size_t o_cnt = L.add(4 * (nr + 1)), o_base = L.add(4 * (nr + 1));
+    const size_t o_scnt = L.add(4 * (ns + 4)), o_sbase = L.add(4 * (ns + 4));
+    const size_t o_loc = L.add(4 * ((size_t)n_ctg + ns)), o_mbase = L.add(4 * (ns + 1));
+    const size_t o_bbase = L.add(8 * (ns + 1)), o_mbytes = L.add(8 * ns), o_tmp = L.add(8 * ((size_t)cap_rec + 1)), o_tot = L.add(32);
+    int rc = fuz_arena_commit(ctx, L);
+    if (rc) return rc;
+    std::vector<uint8_t> tab(tab_bytes, 0);
+    memcpy(tab.data() + o_start, h_seg_start, 8 * ns);
+    memcpy(tab.data() + o_end, h_seg_end, 8 * ns);
+    memcpy(tab.data() + o_reg0, reg0.data(), 8 * (ns + 1));
+    memcpy(tab.data() + o_nref, h_seg_nref, 4 * ns);
+    memcpy(tab.data() + o_ctg0, ctg0.data(), 4 * (ns + 1));
+    if (nr) memcpy(tab.data() + o_regseg, reg_seg.data(), 4 * nr);
+    FUZ_CUDA(ctx, cudaMemcpyAsync(ctx->arena, tab.data(), tab_bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+
+    BamIndexScratch S;
+    S.first = fuz_at<int64_t>(ctx, o_first); S.land = fuz_at<int64_t>(ctx, o_land); S.entry = fuz_at<int64_t>(ctx, o_entry);
+    S.cnt = fuz_at<int32_t>(ctx, o_cnt); S.base = fuz_at<int32_t>(ctx, o_base); S.n_rec = fuz_at<int64_t>(ctx, o_tot);
+    BamFilesScratch F;
+    F.seg_start = fuz_at<int64_t>(ctx, o_start); F.seg_end = fuz_at<int64_t>(ctx, o_end); F.seg_reg0 = fuz_at<int64_t>(ctx, o_reg0);
+    F.seg_nref = fuz_at<int32_t>(ctx, o_nref); F.seg_ctg0 = fuz_at<int32_t>(ctx, o_ctg0); F.reg_seg = fuz_at<int32_t>(ctx, o_regseg);
+    F.seg_cnt = fuz_at<int32_t>(ctx, o_scnt); F.seg_base = fuz_at<int32_t>(ctx, o_sbase);
+    F.loc = fuz_at<int32_t>(ctx, o_loc); F.mbase = fuz_at<int32_t>(ctx, o_mbase);
+    F.bbase = fuz_at<int64_t>(ctx, o_bbase); F.mbytes = fuz_at<int64_t>(ctx, o_mbytes);
+    F.tmp_off = fuz_at<int64_t>(ctx, o_tmp); F.totals = fuz_at<int64_t>(ctx, o_tot);
+    if (!ctx->ingest_pending) FUZ_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(fuz_status), st));
+    ctx->ingest_pending = false;
+    FUZ_CUDA(ctx, cudaMemsetAsync(F.totals, 0, 32, st));
+    FUZ_CUDA(ctx, cudaMemsetAsync(F.loc, 0, 4 * ((size_t)n_ctg + ns), st));
+    FUZ_CUDA(ctx, cudaMemsetAsync(F.seg_cnt, 0, 4 * (ns + 4), st));
+    if (n_reg > 0) {
+        fuz_launch(ctx, k_bamf_anchor, (unsigned)((n_reg * 32 + 255) / 256), 256, 0, st, d_raw, n_reg, S, F, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_bamf_anchor");
+    }
+    fuz_launch(ctx, k_bamf_resolve, (unsigned)(((int64_t)n_seg * 32 + 127) / 128), 128, 0, st, d_raw, (int)n_seg, S, F, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bamf_resolve");
+    fuz_launch(ctx, k_bamf_scan_seg, 1, 1024, 0, st, (int)n_seg, cap_rec, F, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bamf_scan_seg");
+    if (n_reg > 0) {
+        fuz_launch(ctx, k_bamf_fill, (unsigned)((n_reg + 255) / 256), 256, 0, st, d_raw, n_reg, S, F, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_bamf_fill");
+    }
+    fuz_launch(ctx, k_bamf_ranges, FUZ_GRID_BLOCKS, 256, 0, st, d_raw, (int)n_seg, F, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bamf_ranges");
+    fuz_launch(ctx, k_bamf_scan_mapped, 1, 32, 0, st, (int)n_seg, (int)n_ctg, cap_bytes, F, d_rec_off, d_ctg_rec_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bamf_scan_mapped");
+    fuz_launch(ctx, k_bamf_finalize, FUZ_GRID_BLOCKS, 256, 0, st, (int)n_seg, (int)n_ctg, F, d_rec_off, d_ctg_rec_off, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_bamf_finalize");
+    if (n_reg > 0) {
+        fuz_launch(ctx, k_bamf_copy, (unsigned)n_reg, 256, 0, st, d_raw, d_rec_out, F, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_bamf_copy");
+    }
+    int64_t h[4] = {0, 0, 0, 0};
+    FUZ_CUDA(ctx, cudaMemcpyAsync(h, F.totals, 32, cudaMemcpyDeviceToHost, st));
+    fuz_status hs;
+    rc = fuz_get_status(ctx, &hs);                 // synchronises
+    *h_n_rec = h[0];
+    if (h_need_rec) *h_need_rec = h[1];
+    if (h_rec_bytes) *h_rec_bytes = h[2];
     return rc;
 }

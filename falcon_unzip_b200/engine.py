@@ -475,34 +475,79 @@ class Engine:
                          keep=(d_comp, d_coff, d_csize, d_uoff, d_crc))
 
     def ingest_bams(self, images: Sequence, verify_crc: bool = True) -> DeviceBam:
-        """Several BAM files (the reference makes one sorted BAM per contig, unzip.py:90) as ONE device batch: every
-        file is decoded on the device (ingest_bam), the mapped records of all files are laid out back to back and
-        the reference lists are concatenated (names must be unique across the files)."""
+        """Several BAM files (the reference makes one sorted BAM per contig, unzip.py:90) as ONE device batch.  The
+        block tables of all files are joined: one upload buffer, ONE launch of the inflate kernel over the blocks of
+        every file (a small file alone would leave the GPU idle behind a few serial block decodes), one record index
+        over all files (fuz_bam_index_files), which also lays the mapped records of all files out back to back.  The
+        reference lists are concatenated (names must be unique across the files)."""
         torch = self._torch
-        parts = [self.ingest_bam(im, verify_crc) for im in images]
-        if len(parts) == 1:
-            return parts[0]
+        from . import bam
+        if len(images) == 0:
+            raise FuzError(_lib.FUZ_E_ARG, "empty list of BAM files")
+        if len(images) == 1:
+            return self.ingest_bam(images[0], verify_crc)
         dev = self.device
-        names = [r[0] for p in parts for r in p.refs]
+        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        tabs, refs_all, seg_start, seg_end, seg_nref = [], [], [], [], []
+        cbase, ubase = 0, 0
+        for k, im in enumerate(images):
+            n_blk = int(lib().fuz_host_bgzf_index(_np_ptr(im), len(im), 0, None, None, None, None))
+            if n_blk < 0:
+                raise FuzError(_lib.FUZ_E_FORMAT, "file %d of the list is not a BGZF file" % k)
+            coff, csize = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32)
+            uoff, crc = np.empty(n_blk + 1, np.int64), np.empty(n_blk, np.uint32)
+            lib().fuz_host_bgzf_index(_np_ptr(im), len(im), n_blk, _np_ptr(coff), _np_ptr(csize), _np_ptr(uoff), _np_ptr(crc))
+            _text, refs, hdr_bytes = bam.read_bam_header(im, coff, csize)
+            total = int(uoff[-1])
+            tabs.append((cbase, coff + cbase, csize, uoff[:-1] + ubase, crc))
+            refs_all.extend(refs)
+            seg_start.append(ubase + hdr_bytes)
+            seg_end.append(ubase + total)
+            seg_nref.append(len(refs))
+            cbase += (len(im) + 15) // 16 * 16
+            ubase += total
+        names = [r[0] for r in refs_all]
         if len(set(names)) != len(names):
             raise FuzError(_lib.FUZ_E_ARG, "the BAM files list the same reference name more than once")
-        used = [int(p.rec_off[p.n_mapped].item()) if p.n_mapped else 0 for p in parts]     # bytes of the mapped records
-        total = sum(used)
-        raw = torch.empty(total + 64, dtype=torch.uint8, device=dev)
-        raw[total:].zero_()
-        rec_off, ctg_rec_off, at, rec_base = [], [], 0, 0
-        for p, u in zip(parts, used):
-            o = p.rec_ptr - p.raw.data_ptr()
-            raw[at:at + u].copy_(p.raw[o:o + u])
-            rec_off.append(p.rec_off[:p.n_mapped] + at)
-            ctg_rec_off.append(p.ctg_rec_off[:len(p.refs)] + rec_base)
-            at += u
-            rec_base += p.n_mapped
-        rec_off.append(torch.tensor([total], dtype=torch.int64, device=dev))
-        ctg_rec_off.append(torch.tensor([rec_base], dtype=torch.int32, device=dev))
+        coff = np.concatenate([t[1] for t in tabs])
+        csize = np.concatenate([t[2] for t in tabs])
+        uoff = np.concatenate([t[3] for t in tabs] + [np.asarray([ubase], np.int64)])
+        crc = np.concatenate([t[4] for t in tabs])
+        n_blk = len(coff)
+        d_comp = torch.empty(cbase + 16, dtype=torch.uint8, device=dev)
+        for t, im in zip(tabs, images):
+            d_comp[t[0]:t[0] + len(im)].copy_(torch.from_numpy(im), non_blocking=True)
+        d_coff, d_csize = torch.from_numpy(coff).to(dev, non_blocking=True), torch.from_numpy(csize).to(dev, non_blocking=True)
+        d_uoff = torch.from_numpy(uoff).to(dev, non_blocking=True)
+        d_crc = torch.from_numpy(crc.view(np.int32)).to(dev, non_blocking=True) if verify_crc else None
+        raw = torch.empty(ubase + 64, dtype=torch.uint8, device=dev)
+        raw[ubase:].zero_()
+        seg_start, seg_end = np.asarray(seg_start, np.int64), np.asarray(seg_end, np.int64)
+        seg_nref = np.asarray(seg_nref, np.int32)
+        cap_bytes = int((seg_end - seg_start).sum())
+        rec_out = torch.empty(cap_bytes + 64, dtype=torch.uint8, device=dev)
+        ctg_rec_off = torch.zeros(len(refs_all) + 1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)                      # torch's stream -> the context's stream
+        _lib.check(self.ctx, lib().fuz_bgzf_inflate(self.ctx, d_comp.data_ptr(), cbase, d_coff.data_ptr(), d_csize.data_ptr(),
+                                                    d_uoff.data_ptr(), d_crc.data_ptr() if verify_crc else None, n_blk,
+                                                    raw.data_ptr(), ubase))
+        cap = cap_bytes // 2048 + 1024
+        n_rec, need, nbytes = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        for _ in range(2):
+            rec_off = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize(dev)
+            rc = lib().fuz_bam_index_files(self.ctx, raw.data_ptr(), ubase, len(images), _np_ptr(seg_start), _np_ptr(seg_end),
+                                           _np_ptr(seg_nref), cap, rec_out.data_ptr(), cap_bytes, rec_off.data_ptr(),
+                                           ctg_rec_off.data_ptr(), C.byref(n_rec), C.byref(need), C.byref(nbytes))
+            if rc != _lib.FUZ_E_CAPACITY:
+                break
+            cap = int(need.value)
+        _lib.check(self.ctx, rc)
+        total = int(nbytes.value)
+        rec_out[total:total + 64].zero_()
         torch.cuda.synchronize(dev)
-        return DeviceBam([r for p in parts for r in p.refs], raw, raw.data_ptr(), total, torch.cat(rec_off), torch.cat(ctg_rec_off),
-                         rec_base, rec_base, sum(p.h2d_bytes for p in parts))
+        h2d = sum(len(im) for im in images) + coff.nbytes + csize.nbytes + uoff.nbytes + (crc.nbytes if verify_crc else 0)
+        return DeviceBam(refs_all, rec_out, rec_out.data_ptr(), total, rec_off, ctg_rec_off, int(n_rec.value), int(n_rec.value), h2d)
 
     def phase_bam(self, image, caps: Optional[Dict[str, int]] = None, verify_crc: bool = True):
         """BAM file image (or a list of images, see ingest_bams) -> (PhaseResult, BamBatchInfo): the BAM is decoded

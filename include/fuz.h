@@ -12,7 +12,7 @@
  *                           chained on the device for a batch of contigs)
  *   fuz_rr_track            falcon_unzip/rr_hctg_track.py:31-65,97-105,113-123
  *                           tr_stage1 + heap merge + contig vote of run_track_reads
- *   fuz_bgzf_inflate, fuz_bam_index_records
+ *   fuz_bgzf_inflate, fuz_bam_index_records, fuz_bam_index_files
  *                           falcon_unzip/phasing.py:27        the `samtools view` pipe: BGZF
  *                           inflate + record split, on the device
  *   fuz_ovlp_filter         falcon_unzip/ovlp_filter_with_phase.py:49-290  filter_stage1-3
@@ -245,6 +245,19 @@ int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t comp_bytes, co
  * FUZ_E_BADRECORD: broken block_size chain; FUZ_E_UNSORTED: refIDs not ascending. */
 int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
                           int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec);
+/* The same for SEVERAL BAM files inflated into one device buffer (one fuz_bgzf_inflate over the blocks of all
+ * files) -- the reference leaves one sorted BAM per contig (falcon_unzip/unzip.py:90-91) and runs fc_phasing.py
+ * once per file (unzip.py:124).  File s has its alignment records at d_raw[h_seg_start[s], h_seg_end[s])
+ * (ascending, not overlapping; the headers lie between them) and h_seg_nref[s] references; d_raw is followed by
+ * >= 32 readable bytes.  All files are indexed in one pass; the MAPPED records of all files are written back to
+ * back into d_rec_out [cap_bytes + 32] (unmapped tails dropped), d_rec_off [cap_rec + 1] are their offsets in
+ * d_rec_out, d_ctg_rec_off [sum(n_ref) + 1] the record range of every reference, file after file.  cap_rec
+ * counts ALL records of the files.  Synchronises; *h_n_rec = mapped records, *h_rec_bytes = their bytes.
+ * Errors as fuz_bam_index_records (FUZ_E_BADRECORD: error_index = file or record). */
+int fuz_bam_index_files(fuz_ctx *ctx, const uint8_t *d_raw, int64_t raw_bytes, int32_t n_seg, const int64_t *h_seg_start,
+                        const int64_t *h_seg_end, const int32_t *h_seg_nref, int64_t cap_rec, uint8_t *d_rec_out,
+                        int64_t cap_bytes, int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec,
+                        int64_t *h_need_rec, int64_t *h_rec_bytes);
 
 /* ---- raw-read -> haplotig tracking (falcon_unzip/rr_hctg_track.py) --------------- */
 /* fuz_rr_track replaces tr_stage1 (:31-65), the heap merge (:97-105) and the contig vote

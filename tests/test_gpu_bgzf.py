@@ -324,3 +324,89 @@ def test_phase_bam_from_one_file_per_contig(eng, tmp_path):
     for n in files_1:
         for k in files_1[n]:
             assert open(files_m[n][k]).read() == open(files_1[n][k]).read(), (n, k)
+
+
+def _bam_image(tmp_path, tag, refs, records: bytes, level=1):
+    from falcon_unzip_b200 import bam
+    fn = str(tmp_path / ("%s.bam" % tag))
+    bam.write_bam(fn, refs, records, level=level)
+    return np.fromfile(fn, dtype=np.uint8)
+
+
+def test_ingest_bams_many_files_one_batch(eng, tmp_path):
+    """fuz_bam_index_files: a list of BAM files (one inflate launch, one record index over all of them) gives the mapped
+    records of the files back to back, with the offsets and per-reference ranges of the sequential host walk."""
+    from falcon_unzip_b200 import _lib
+    rng = np.random.default_rng(11)
+    files = []                                           # (refs, mapped records, unmapped tail)
+    # tiny records: hundreds per region, several regions
+    files.append(([("a0", 9000), ("a1", 9000), ("a2", 9000)],
+                  b"".join(_rec(i // 2000, i % 2000, "t%d" % i, int(rng.integers(0, 3)), rng=rng) for i in range(6000)), b""))
+    files.append(([("none", 500)], b"", b""))                                            # header only
+    files.append(([("only_unmapped", 500)], b"", b"".join(_rec(-1, -1, "u%d" % i, 40, rng=rng) for i in range(7))))
+    # records longer than a region, and an unmapped tail
+    files.append(([("long", 200000)], b"".join(_rec(0, 10 * i, "m/%d/0_1" % i, int(rng.integers(90000, 140000)), rng=rng) for i in range(9)),
+                  _rec(-1, -1, "ux", 100, rng=rng)))
+    # two references, the first one empty; PacBio-like sizes
+    files.append(([("e0", 1000), ("e1", 50000)], b"".join(_rec(1, 3 * i, "p/%d/0_%d" % (i, i), int(rng.integers(1, 30000)), rng=rng) for i in range(150)),
+                  b"".join(_rec(-1, -1, "uy%d" % i, 3000, rng=rng) for i in range(3))))
+    files.append(([], b"", b""))                                                          # no reference at all
+    # header-like bytes inside aux data at the start of a region of THIS file's record stream
+    head = b"".join(_rec(0, i, "h%d" % i, 5000, rng=rng) for i in range(5))
+    aux_start, aux_len = len(head) + 36 + 4, 200000
+    aux = bytearray(rng.integers(0, 256, aux_len, dtype=np.uint8).tobytes())
+    p1 = 65536 - aux_start
+    p2 = p1 + 4 + 1000
+    aux[p1:p1 + len(_fake_header(1000))] = _fake_header(1000)
+    aux[p2:p2 + len(_fake_header(aux_len - p2 - 4))] = _fake_header(aux_len - p2 - 4)
+    big = _rec(0, 9, "big", 0, aux=b"XYB" + bytes([255]) + bytes(aux[4:]))
+    files.append(([("fake", 9999), ("fake2", 10)], head + big + b"".join(_rec(0, 10 + i, "t%d" % i, 3000, rng=rng) for i in range(40)), b""))
+    images = [_bam_image(tmp_path, "f%d" % k, refs, rec + tail, level=(1 if k % 2 else 6)) for k, (refs, rec, tail) in enumerate(files)]
+    db = eng.ingest_bams(images)
+    want = b"".join(rec for _r, rec, _t in files)
+    assert [tuple(r) for r in db.refs] == [tuple(r) for refs, _r, _t in files for r in refs]
+    assert db.rec_bytes == len(want)
+    assert db.records().tobytes() == want
+    want_off, want_cro, base = [], [], 0
+    at = 0
+    for refs, rec, _t in files:
+        off, cro = _host_index(rec, len(refs))
+        want_off.append(off[:-1] + at)
+        want_cro.append(cro[:-1] + base)
+        at += len(rec)
+        base += len(off) - 1
+    want_off = np.concatenate(want_off + [np.asarray([at])])
+    want_cro = np.concatenate(want_cro + [np.asarray([base])])
+    assert db.n_rec == db.n_mapped == base
+    assert np.array_equal(db.rec_off.cpu().numpy()[:base + 1], want_off)
+    assert np.array_equal(db.ctg_rec_off.cpu().numpy(), want_cro)
+    # every file alone through the single-file path gives the same pieces
+    for k in (0, 3, 4):
+        one = eng.ingest_bam(images[k])
+        rec = files[k][1]
+        assert one.records()[:len(rec)].tobytes() == rec and one.n_mapped == len(_host_index(rec, len(files[k][0]))[0]) - 1
+    # errors: unsorted reference ids inside one file, a broken chain in one file, a flipped bit, a repeated reference name
+    swapped = _rec(1, 0, "a", 50, rng=rng) + _rec(0, 0, "b", 50, rng=rng)
+    with pytest.raises(_lib.FuzError) as ei:
+        eng.ingest_bams([images[4], _bam_image(tmp_path, "sw", [("s0", 100), ("s1", 100)], swapped)])
+    assert ei.value.code == _lib.FUZ_E_UNSORTED
+    good = _rec(0, 0, "a", 50, rng=rng) * 3
+    with pytest.raises(_lib.FuzError) as ei:
+        eng.ingest_bams([_bam_image(tmp_path, "br", [("b0", 100)], good[:-3]), images[4]])
+    assert ei.value.code == _lib.FUZ_E_BADRECORD
+    with pytest.raises(_lib.FuzError) as ei:                      # refID 1 in a file that lists one reference
+        eng.ingest_bams([images[3], _bam_image(tmp_path, "rf", [("r0", 100)], _rec(1, 0, "a", 50, rng=rng))])
+    assert ei.value.code == _lib.FUZ_E_BADRECORD
+    img = images[4].copy()
+    n_blk = _lib.lib().fuz_host_bgzf_index(img.ctypes.data, len(img), 0, None, None, None, None)
+    coff, csize, uoff = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32), np.empty(n_blk + 1, np.int64)
+    _lib.lib().fuz_host_bgzf_index(img.ctypes.data, len(img), n_blk, coff.ctypes.data, csize.ctypes.data, uoff.ctypes.data, None)
+    img[coff[n_blk // 2] + csize[n_blk // 2] // 2] ^= 0x10           # inside the deflate stream of a middle block
+    with pytest.raises(_lib.FuzError):
+        eng.ingest_bams([images[3], img])
+    with pytest.raises(_lib.FuzError) as ei:
+        eng.ingest_bams([images[3], images[3]])
+    assert ei.value.code == _lib.FUZ_E_ARG
+    # the engine is usable afterwards
+    db2 = eng.ingest_bams(images[3:5])
+    assert db2.records().tobytes() == files[3][1] + files[4][1]
