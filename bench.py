@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--replicate", type=int, default=1, help="repeat the workload's contigs (named in config)")
     ap.add_argument("--contigs", type=int, default=0, help="use only the first N contigs of the config (named in config)")
     ap.add_argument("--contig-len", type=int, default=0, help="override the contig length of the config (stress cases; named in config)")
+    ap.add_argument("--no-bind", action="store_true", help="N>1: do not bind the rank to the CPUs next to its GPU")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library option for experiments (fuz_set_option), e.g. pdl=0; recorded in config")
     return ap.parse_args()
@@ -296,7 +297,9 @@ def run_b200(args):
 
     import torch
     import torch.distributed as dist
-    from falcon_unzip_b200 import engine
+    from falcon_unzip_b200 import engine, shard
+    # one process per GPU: stay on the CPUs next to the GPU so that the page-locked records land in that socket's memory
+    binding = shard.bind_to_gpu_cpus(local_rank) if world > 1 and not args.no_bind else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
@@ -381,6 +384,13 @@ def run_b200(args):
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max, kern_ms = [float(x) for x in vals.tolist()]
+    per_rank = None
+    if world > 1:                                               # diagnostics: e2e time and CPU binding of every rank
+        mine = torch.tensor([e2e_ms, float(binding["first_cpu"]) if binding and binding.get("bound") else -1.0],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"e2e_ms": [round(float(t[0]), 3) for t in allr], "first_cpu": [int(t[1]) for t in allr]}
     total_units = float(units.item())
 
     cpu = None
@@ -410,6 +420,7 @@ def run_b200(args):
                 "cpu_baseline": cpu,
                 "clocks": clocks,
                 **({"bam_ingest": bam_leg} if bam_leg else {}),
+                **({"host_binding": {**(binding or {"bound": False, "why": "--no-bind"}), "per_rank": per_rank}} if world > 1 else {}),
                 "rows": {"sites": int(st.n_sites), "variant_map": int(st.n_vmap), "atable": int(st.n_atable),
                          "phased_reads": int(st.n_reads), "accepted_records": int(st.n_accepted)},
                 "wall_ms_per_step_incl_l2_flush": 1e3 * t_wall / max(args.steps, 1)}

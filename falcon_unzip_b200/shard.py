@@ -23,6 +23,30 @@ def assign_contigs(weights: Sequence[float], world_size: int) -> List[List[int]]
     return [sorted(x) for x in out]
 
 
+def bind_to_gpu_cpus(device_index: int) -> Dict[str, object]:
+    """One process per GPU: run this process on the CPUs next to its GPU (NVML's CPU affinity of the device, cut to what
+    the process may use), BEFORE any page-locked buffer is allocated.  Page-locked host memory is placed by first touch,
+    so the records a rank uploads then sit in the memory of the socket its GPU hangs off; without it all ranks of a box
+    may read through one socket's memory controllers and the inter-socket link.  Best effort: returns what was done."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device_index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        allowed = os.sched_getaffinity(0)
+        n_words = (max(max(allowed) + 1, os.cpu_count() or 1) + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        near = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus = near & allowed
+        if not cpus:
+            return {"bound": False, "why": "no allowed CPU next to the device", "allowed": len(allowed), "near": len(near)}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "first_cpu": min(cpus), "allowed": len(allowed)}
+    except Exception as e:                                  # noqa: BLE001 -- no NVML / no permission: run unbound
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def contig_record_ranges(records: np.ndarray, rec_off: np.ndarray, n_ctg: int):
     """Record range and byte weight of every contig of a coordinate-sorted record buffer."""
     from . import engine
