@@ -268,7 +268,7 @@ class DeviceBam:
 
 class BamBatchInfo:
     """What the file writers need from a batch that only exists on the device: contig names
-    and the QNAME of every q_id (gathered on the device, a few bytes per read)."""
+    and the QNAME of every q_id (gathered on the device, a few bytes per read; a list of str or a numpy "S" array)."""
 
     def __init__(self, ctg_names, ctg_lens, ctg_nq, names):
         self.ctg_names, self.ctg_len = list(ctg_names), np.asarray(ctg_lens, np.int32)
@@ -281,7 +281,12 @@ class BamBatchInfo:
         return len(self.ctg_names)
 
     def qnames(self, c: int) -> List[str]:
-        return self._names[int(self._q_off[c]):int(self._q_off[c + 1])]
+        """QNAME of every q_id of contig c.  The batch keeps the names as fixed-width byte rows (numpy "S"); the str
+        objects are made here, for the contig that is being written."""
+        part = self._names[int(self._q_off[c]):int(self._q_off[c + 1])]
+        if isinstance(part, np.ndarray):
+            return [b.decode("latin-1") for b in part.tolist()]
+        return part
 
 
 class Engine:
@@ -581,17 +586,17 @@ class Engine:
         # QNAME of every q_id: gathered on the device from the first record of each name
         nq = qid_nq.cpu().numpy()
         total_nq = int(nq.sum())
-        names: List[str] = []
+        names = []
         if total_nq:
             o = db.rec_ptr - db.raw.data_ptr()
             first_off = db.rec_off[qid_first[:total_nq]] + o
             l_name = db.raw[first_off + 12].to(torch.int64)
             width = int(l_name.max().item())
-            idx = first_off[:, None] + 36 + torch.arange(width, device=dev)[None, :]
-            chars = np.ascontiguousarray(db.raw[idx.clamp_(max=db.raw.numel() - 1)].cpu().numpy())
-            ln = l_name.cpu().numpy()
-            chars[np.arange(width)[None, :] >= (ln - 1)[:, None]] = 0          # NUL and everything behind it
-            names = chars.view("S%d" % width).ravel().astype("U").tolist()
+            col = torch.arange(width, device=dev)[None, :]
+            chars_d = db.raw[(first_off[:, None] + 36 + col).clamp_(max=db.raw.numel() - 1)]
+            chars_d.masked_fill_(col >= (l_name - 1)[:, None], 0)              # NUL and everything behind it
+            chars = np.ascontiguousarray(chars_d.cpu().numpy())
+            names = chars.view("S%d" % width).ravel()                          # fixed-width byte rows; str on demand (BamBatchInfo.qnames)
             res.d2h_bytes += chars.nbytes
         return res, BamBatchInfo([r[0] for r in db.refs], ctg_len, nq, names)
 
