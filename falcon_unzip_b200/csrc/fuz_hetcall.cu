@@ -852,7 +852,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            fuz_launch(ctx, k_project, 148 * 6, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            fuz_launch(ctx, k_project, ctx->project_ctas, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");
         }
@@ -865,7 +865,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
         if (n_rec > 0) {
-            fuz_launch(ctx, k_project, 148 * 6, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+            fuz_launch(ctx, k_project, ctx->project_ctas, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
                                                        n_ctg, S, ctx->d_status);
             FUZ_LAUNCH_CHECK(ctx, "k_project");      // filter + the projection the variant_map rows come from
             fuz_launch(ctx, k_pileup_atomic, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off,

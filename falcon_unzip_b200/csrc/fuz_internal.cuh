@@ -44,6 +44,7 @@ struct fuz_ctx {
     int host_fetch = 1;                // host entry: fetch only header/name/CIGAR/SEQ from page-locked records
     int pdl = 1;                       // programmatic dependent launch between the kernels of a call
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
+    int project_ctas = 148 * 6;        // CTAs of k_project (persistent warps, records from a global cursor)
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int64_t max_pairs_per_site = 96;
     uint8_t *reads_buf = nullptr; size_t reads_cap = 0;           // scratch of the read stage (runs beside the block stage)
