@@ -430,7 +430,7 @@ def run_b200(args):
                         "api": "fuz_phase_batch_host (pinned host BAM records in, host row arrays out; header/name/CIGAR/SEQ of each record cross PCIe, QUAL and tags do not)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "k_project + k_pileup_gather (pileup + het test, timed as one group)", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                             "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": ncu_traffic(),
                              "algorithmic_bytes_per_launch": alg["total"], "kernel_ms": kern_ms, "peak_source": peak_src,
                              "note": "algorithmic bytes per SURVEY.md 8(d): records once (36+4*n_cigar+ceil(l_seq/2)) + 32 B/position "
                                      "of pileup counts; the kernels keep the counts in registers and move a 4-bit reference-aligned projection "
