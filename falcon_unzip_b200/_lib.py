@@ -133,6 +133,8 @@ SYMBOLS = [
                                         _i64p, _i64p]),
     ("fuz_bam_index_files", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _i64p, _i64p, _i64p]),
+    ("fuz_gather_records", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_int64]),
     ("fuz_rr_track", C.c_int, [C.c_void_p, C.POINTER(RRInput), C.POINTER(RROutputs)]),
     ("fuz_ovlp_filter", C.c_int, [C.c_void_p, C.POINTER(OvlpInput), C.POINTER(OvlpOutputs)]),
     ("fuz_parse_la4falcon", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 12),

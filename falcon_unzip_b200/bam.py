@@ -201,6 +201,44 @@ def write_bam(path: str, refs: Sequence[Tuple[str, int]], records: bytes,
         f.write(_BGZF_EOF)
 
 
+def bam_header_bytes(header_text: str, refs: Sequence[Tuple[str, int]]) -> bytes:
+    ht = header_text.encode("latin-1")
+    hdr = b"BAM\1" + struct.pack("<i", len(ht)) + ht + struct.pack("<i", len(refs))
+    for name, ln in refs:
+        nb = name.encode("ascii") + b"\0"
+        hdr += struct.pack("<i", len(nb)) + nb + struct.pack("<i", ln)
+    return hdr
+
+
+class BamWriter:
+    """Incremental BAM writer: header in its own BGZF block, then the record bytes handed to write() cut into blocks of
+    at most 65280 payload bytes, EOF marker on close()."""
+
+    def __init__(self, path: str, header_text: str, refs: Sequence[Tuple[str, int]] = (), level: int = 6):
+        self.path, self.level = path, level
+        self._f = open(path, "wb")
+        self._f.write(_bgzf_block(bam_header_bytes(header_text, refs), level))
+        self._pending = bytearray()
+
+    def write(self, records) -> None:
+        self._pending += memoryview(records)
+        n_full = len(self._pending) // _BGZF_MAX_PAYLOAD * _BGZF_MAX_PAYLOAD
+        mv = memoryview(self._pending)
+        for o in range(0, n_full, _BGZF_MAX_PAYLOAD):
+            self._f.write(_bgzf_block(bytes(mv[o:o + _BGZF_MAX_PAYLOAD]), self.level))
+        del mv
+        del self._pending[:n_full]
+
+    def close(self) -> None:
+        if self._f is None:
+            return
+        if self._pending:
+            self._f.write(_bgzf_block(bytes(self._pending), self.level))
+        self._f.write(_BGZF_EOF)
+        self._f.close()
+        self._f = None
+
+
 def _bgzf_blocks(raw, path: str):
     """(compressed start, compressed end, isize, crc) of every BGZF block of the file image."""
     blocks = []

@@ -612,8 +612,26 @@ __global__ void __launch_bounds__(256) k_bamf_finalize(int n_seg, int n_ctg, Bam
     }
 }
 
-// one CTA per region: its share of the segment's mapped bytes to their place in the output (128-bit stores; the source
-// is realigned from 32-bit words)
+// n bytes src -> dst by nt cooperating threads (t = my index): 128-bit stores, the source realigned from 32-bit words;
+// reads up to 7 bytes past src + n (callers keep slack behind their buffers)
+__device__ __forceinline__ void copy_bytes(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n, int t, int nt) {
+    const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    const int64_t body = (n - head) >> 4;
+    for (int64_t i = t; i < head; i += nt) dst[i] = src[i];
+    for (int64_t q = t; q < body; q += nt) {
+        const uintptr_t p = reinterpret_cast<uintptr_t>(src + head + 16 * q);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(p & 3) * 8;
+        const uint32_t x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3), x4 = __ldg(w + 4);
+        uint4 v;
+        v.x = __funnelshift_r(x0, x1, sh); v.y = __funnelshift_r(x1, x2, sh);
+        v.z = __funnelshift_r(x2, x3, sh); v.w = __funnelshift_r(x3, x4, sh);
+        *reinterpret_cast<uint4 *>(dst + head + 16 * q) = v;
+    }
+    for (int64_t i = head + 16 * body + t; i < n; i += nt) dst[i] = src[i];
+}
+
+// one CTA per region: its share of the segment's mapped bytes to their place in the output
 __global__ void __launch_bounds__(256) k_bamf_copy(const uint8_t *__restrict__ raw, uint8_t *__restrict__ out, BamFilesScratch F,
                                                    const fuz_status *st) {
     fuz_pdl_enter();
@@ -623,23 +641,27 @@ __global__ void __launch_bounds__(256) k_bamf_copy(const uint8_t *__restrict__ r
     const int64_t s0 = F.seg_start[s];
     const int64_t a = s0 + (k - F.seg_reg0[s]) * FUZ_BAM_REGION, e = min(a + FUZ_BAM_REGION, s0 + F.mbytes[s]);
     if (a >= e) return;
-    const uint8_t *src = raw + a;
-    uint8_t *dst = out + F.bbase[s] + (a - s0);
-    const int64_t n = e - a;
-    const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
-    const int64_t body = (n - head) >> 4;
-    for (int64_t t = threadIdx.x; t < head; t += blockDim.x) dst[t] = src[t];
-    for (int64_t q = threadIdx.x; q < body; q += blockDim.x) {
-        const uintptr_t p = reinterpret_cast<uintptr_t>(src + head + 16 * q);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
-        const uint32_t sh = (uint32_t)(p & 3) * 8;
-        const uint32_t x0 = __ldg(w), x1 = __ldg(w + 1), x2 = __ldg(w + 2), x3 = __ldg(w + 3), x4 = __ldg(w + 4);   // raw has slack
-        uint4 v;
-        v.x = __funnelshift_r(x0, x1, sh); v.y = __funnelshift_r(x1, x2, sh);
-        v.z = __funnelshift_r(x2, x3, sh); v.w = __funnelshift_r(x3, x4, sh);
-        *reinterpret_cast<uint4 *>(dst + head + 16 * q) = v;
+    copy_bytes(out + F.bbase[s] + (a - s0), raw + a, e - a, threadIdx.x, blockDim.x);
+}
+
+// fuz_gather_records: output record i = source record sel[i], one warp per record (a stable selection of whole records by
+// any key: the per-contig partition of reference falcon_unzip/select_reads_from_bam.py:70-86)
+__global__ void __launch_bounds__(256) k_gather_records(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_off, int64_t n_src,
+                                                        int64_t src_bytes, const int64_t *__restrict__ sel, const int64_t *__restrict__ dst_off,
+                                                        int64_t m, uint8_t *__restrict__ dst, int64_t dst_bytes, fuz_status *st) {
+    fuz_pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += n_warps) {
+        const int64_t r = sel[i];
+        if (r < 0 || r >= n_src) { if (lane == 0) fuz_raise(st, FUZ_E_ARG, (int)min(i, (int64_t)0x7fffffff)); continue; }
+        const int64_t a = src_off[r], n = src_off[r + 1] - a, d = dst_off[i];
+        if (a < 0 || n < 0 || a + n > src_bytes || d < 0 || d + n > dst_bytes || dst_off[i + 1] - d != n) {
+            if (lane == 0) fuz_raise(st, FUZ_E_ARG, (int)min(i, (int64_t)0x7fffffff));
+            continue;
+        }
+        copy_bytes(dst + d, src + a, n, lane, 32);
     }
-    for (int64_t t = head + 16 * body + threadIdx.x; t < n; t += blockDim.x) dst[t] = src[t];
 }
 
 }  // namespace
@@ -840,4 +862,17 @@ extern "C" int fuz_bam_index_files(fuz_ctx *ctx, const uint8_t *d_raw, int64_t r
     if (h_need_rec) *h_need_rec = h[1];
     if (h_rec_bytes) *h_rec_bytes = h[2];
     return rc;
+}
+
+extern "C" int fuz_gather_records(fuz_ctx *ctx, const uint8_t *d_src, const int64_t *d_src_off, int64_t n_src, int64_t src_bytes,
+                                  const int64_t *d_sel, const int64_t *d_dst_off, int64_t m, uint8_t *d_dst, int64_t dst_bytes) {
+    if (!ctx || !d_src || !d_src_off || n_src < 0 || src_bytes < 0 || m < 0 || dst_bytes < 0 || (m > 0 && (!d_sel || !d_dst_off || !d_dst)))
+        return fuz_fail(ctx, FUZ_E_ARG, "fuz_gather_records: bad argument");
+    FUZ_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(fuz_status), ctx->stream));
+    if (m == 0) return FUZ_OK;
+    const unsigned grid = (unsigned)min((int64_t)FUZ_GRID_BLOCKS * 2, (m + 7) / 8);
+    fuz_launch(ctx, k_gather_records, grid, 256, 0, ctx->stream, d_src, d_src_off, n_src, src_bytes, d_sel, d_dst_off, m, d_dst, dst_bytes,
+               ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_gather_records");
+    return FUZ_OK;
 }

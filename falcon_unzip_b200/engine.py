@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -588,17 +588,50 @@ class Engine:
         total_nq = int(nq.sum())
         names = []
         if total_nq:
-            o = db.rec_ptr - db.raw.data_ptr()
-            first_off = db.rec_off[qid_first[:total_nq]] + o
-            l_name = db.raw[first_off + 12].to(torch.int64)
-            width = int(l_name.max().item())
-            col = torch.arange(width, device=dev)[None, :]
-            chars_d = db.raw[(first_off[:, None] + 36 + col).clamp_(max=db.raw.numel() - 1)]
-            chars_d.masked_fill_(col >= (l_name - 1)[:, None], 0)              # NUL and everything behind it
-            chars = np.ascontiguousarray(chars_d.cpu().numpy())
-            names = chars.view("S%d" % width).ravel()                          # fixed-width byte rows; str on demand (BamBatchInfo.qnames)
-            res.d2h_bytes += chars.nbytes
+            names = self.name_rows(db, qid_first[:total_nq])                   # fixed-width byte rows; str on demand (BamBatchInfo.qnames)
+            res.d2h_bytes += names.nbytes
         return res, BamBatchInfo([r[0] for r in db.refs], ctg_len, nq, names)
+
+    def name_rows(self, db: DeviceBam, rec_index=None) -> np.ndarray:
+        """QNAME of the given records (torch int64 indices on the device; None = every record) of a device BAM as a numpy
+        "S" array: gathered on the device into fixed-width rows (NUL and everything behind it zeroed), a few bytes per read
+        over PCIe."""
+        torch = self._torch
+        dev = self.device
+        idx = torch.arange(db.n_rec, device=dev) if rec_index is None else rec_index
+        if idx.numel() == 0:
+            return np.zeros(0, "S1")
+        o = db.rec_ptr - db.raw.data_ptr()
+        first_off = db.rec_off[idx] + o
+        l_name = db.raw[first_off + 12].to(torch.int64)
+        width = max(int(l_name.max().item()) - 1, 1)
+        col = torch.arange(width, device=dev)[None, :]
+        chars_d = db.raw[(first_off[:, None] + 36 + col).clamp_(max=db.raw.numel() - 1)]
+        chars_d.masked_fill_(col >= (l_name - 1)[:, None], 0)
+        chars = np.ascontiguousarray(chars_d.cpu().numpy())
+        return chars.view("S%d" % width).ravel()
+
+    def gather_records(self, db: DeviceBam, sel: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Records sel[0], sel[1], ... of a device BAM back to back (fuz_gather_records) -> (bytes on the host, offsets
+        [len(sel) + 1])."""
+        torch = self._torch
+        dev = self.device
+        sel_d = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int64)).to(dev)
+        m = int(sel_d.numel())
+        if m == 0:
+            return np.zeros(0, np.uint8), np.zeros(1, np.int64)
+        if int(sel_d.min().item()) < 0 or int(sel_d.max().item()) >= db.n_rec:
+            raise FuzError(_lib.FUZ_E_ARG, "record index out of range")
+        sizes = db.rec_off[sel_d + 1] - db.rec_off[sel_d]
+        dst_off = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(sizes, 0, out=dst_off[1:])
+        total = int(dst_off[-1].item())
+        dst = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)                      # torch's stream -> the context's stream
+        _lib.check(self.ctx, lib().fuz_gather_records(self.ctx, db.rec_ptr, db.rec_off.data_ptr(), db.n_rec, db.rec_bytes,
+                                                      sel_d.data_ptr(), dst_off.data_ptr(), m, dst.data_ptr(), total))
+        self.status()                                    # synchronises; raises on a device-side error
+        return dst[:total].cpu().numpy(), dst_off.cpu().numpy()
 
     # ---- host-buffer path (what the reference-facing functions and bench e2e use)
     def phase_host(self, pb: PreparedBatch, caps: Optional[Dict[str, int]] = None,

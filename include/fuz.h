@@ -16,6 +16,8 @@
  *                           falcon_unzip/phasing.py:27        the `samtools view` pipe: BGZF
  *                           inflate + record split, on the device
  *   fuz_ovlp_filter         falcon_unzip/ovlp_filter_with_phase.py:49-290  filter_stage1-3
+ *   fuz_gather_records      falcon_unzip/select_reads_from_bam.py:70-86    per-contig partition of the
+ *                           raw-read BAM records (with the BAM ingest entries above)
  *   fuz_host_*              host-side helpers of the same path (record index, QNAME ->
  *                           q_id of phasing.py:47-54)
  *
@@ -258,6 +260,15 @@ int fuz_bam_index_files(fuz_ctx *ctx, const uint8_t *d_raw, int64_t raw_bytes, i
                         const int64_t *h_seg_end, const int32_t *h_seg_nref, int64_t cap_rec, uint8_t *d_rec_out,
                         int64_t cap_bytes, int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec,
                         int64_t *h_need_rec, int64_t *h_rec_bytes);
+
+/* Device: whole records picked out of a record buffer, in the given order: output record i = source record
+ * d_sel[i] (source record r = d_src[d_src_off[r], d_src_off[r+1])), written at d_dst[d_dst_off[i], d_dst_off[i+1])
+ * (the caller scans the sizes; a size mismatch or an index out of range raises FUZ_E_ARG, error_index = i).
+ * One warp per record.  This is the per-contig partition of the raw-read BAMs in
+ * falcon_unzip/select_reads_from_bam.py:70-86 (d_sel = the records of one contig after another, file order
+ * kept inside a contig).  d_src is followed by >= 8 readable bytes.  Asynchronous. */
+int fuz_gather_records(fuz_ctx *ctx, const uint8_t *d_src, const int64_t *d_src_off, int64_t n_src, int64_t src_bytes,
+                       const int64_t *d_sel, const int64_t *d_dst_off, int64_t m, uint8_t *d_dst, int64_t dst_bytes);
 
 /* ---- raw-read -> haplotig tracking (falcon_unzip/rr_hctg_track.py) --------------- */
 /* fuz_rr_track replaces tr_stage1 (:31-65), the heap merge (:97-105) and the contig vote

@@ -277,3 +277,70 @@ def get_rid_to_phase_all_source() -> types.ModuleType:
     if not m:
         raise RuntimeError("get_rid_to_phase_all not found in unzip.py")
     return _exec_patched(m.group(0), "ref_get_rid_to_phase_all", dict(fn=lambda p: p))
+
+
+# ---------------------------------------------------------------- select_reads_from_bam.py
+class _FakeRead:
+    def __init__(self, raw: bytes):
+        self.raw = raw
+        self.query_name = raw[36:36 + raw[12] - 1].decode("latin-1")
+
+
+def _fake_pysam(outputs: dict) -> types.ModuleType:
+    """Stand-in for the three things the reference uses of pysam (select_reads_from_bam.py:44-88): AlignmentFile(fn, 'rb',
+    check_sq=False) with .header (a dict of the parsed header) and .fetch(until_eof=True); AlignmentFile(fn, 'wb',
+    header=...) with .write(read); .close().  Written files are not BAMs: outputs[fn] = (header dict at open time,
+    [record bytes...])."""
+    import copy
+    from falcon_unzip_b200 import bam
+    from . import select_oracle
+    mod = types.ModuleType("pysam")
+
+    class AlignmentFile:
+        def __init__(self, fn, mode, check_sq=True, header=None):
+            self.mode = mode
+            if mode == "rb":
+                text, _refs, recs = bam.read_bam(fn)
+                self.header = select_oracle.parse_header(text)
+                self._buf = bytes(recs)
+            else:
+                outputs[fn] = (copy.deepcopy(header), [])
+                self._out = outputs[fn][1]
+
+        def fetch(self, until_eof=False):
+            off = bam.index_records(self._buf)
+            for i in range(len(off) - 1):
+                yield _FakeRead(self._buf[off[i]:off[i + 1]])
+
+        def write(self, r):
+            self._out.append(r.raw)
+
+        def close(self):
+            pass
+    mod.AlignmentFile = AlignmentFile
+    return mod
+
+
+def run_select_reads(input_bam_fofn_fn: str, rawread_to_contigs_fn: str, rawread_ids_fn: str, sam_dir: str) -> dict:
+    """The reference's select_reads_from_bam() on real files, pysam replaced by the stand-in above.
+    -> {output path: (header dict, [record bytes, ...])}."""
+    import contextlib
+    import io as _io
+    with open(os.path.join(REF_ROOT, "falcon_unzip", "select_reads_from_bam.py")) as f:
+        src = f.read()
+    src = _sub(r'^(\s*)print "([^\n#]*?)\s*(#[^\n]*)?$', r'\1print("\2)', src, 5, re.M)
+    src = _sub(r"print >>\s*([\w.]+),\s*(.*)", r"print(\2, file=\1)", src, 1)
+    src = _sub(r"ctgs = read_partition\.keys\(\)\n(\s*)ctgs\.sort\(\)", r"ctgs = sorted(read_partition.keys())", src, 1)
+    outputs: dict = {}
+    saved = sys.modules.get("pysam")
+    sys.modules["pysam"] = _fake_pysam(outputs)
+    try:
+        mod = _exec_patched(src, "ref_select_reads_from_bam", {})
+        with contextlib.redirect_stdout(_io.StringIO()), contextlib.redirect_stderr(_io.StringIO()):
+            mod.select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_fn, sam_dir)
+    finally:
+        if saved is None:
+            sys.modules.pop("pysam", None)
+        else:
+            sys.modules["pysam"] = saved
+    return outputs

@@ -1,0 +1,62 @@
+"""oracle/select_oracle.py against the reference's own select_reads_from_bam.py (executed through oracle/ref_exec.py
+with a pysam stand-in; build container only), and the host-side tables of the product module against both."""
+import os
+
+import pytest
+
+import select_cases
+from oracle import ref_exec, select_oracle
+
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(ref_exec.REF_ROOT, "falcon_unzip", "select_reads_from_bam.py")),
+                               reason="reference tree not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [7, 8])
+def test_oracle_matches_reference(tmp_path, seed):
+    fofn, r2c, ids = select_cases.make_case(str(tmp_path), seed=seed)
+    sam_dir = str(tmp_path / "ref_out")
+    ref = ref_exec.run_select_reads(fofn, r2c, ids, sam_dir)
+    header, out = select_oracle.select(fofn, r2c, ids)
+    assert sorted(ref) == sorted(os.path.join(sam_dir, "%s.bam" % c) for c in out)
+    assert set(out) == {"000000F", "000001F", "000004F"}
+    for ctg, recs in out.items():
+        ref_header, ref_recs = ref[os.path.join(sam_dir, "%s.bam" % ctg)]
+        assert ref_recs == recs, ctg
+        assert ref_header == header, ctg
+    assert "PG" not in header and [d["ID"] for d in header["RG"]] == ["rg0", "rg1", "rg1b", "rg2"]
+
+
+def test_product_tables_match_oracle(tmp_path):
+    """read -> contig table and merged header text of the product module (host code, no device) against the oracle."""
+    from falcon_unzip_b200 import bam, select_reads_from_bam as srb
+    fofn, r2c, ids = select_cases.make_case(str(tmp_path), seed=9)
+    header, out = select_oracle.select(fofn, r2c, ids)
+    part, r2ctgs = srb.read_tables(r2c, ids)
+    target = srb.read_to_selected_ctg(part, r2ctgs)
+    assert set(target.values()) == set(out)
+    names_written = {rec[36:36 + rec[12] - 1].decode() for recs in out.values() for rec in recs}
+    assert names_written <= set(target) and all(target[n] in out for n in names_written)
+    base = os.path.dirname(fofn)
+    texts = [bam.read_bam(os.path.join(base, "movie%d.subreads.bam" % k))[0] for k in range(3)]
+    assert select_oracle.parse_header(srb.merged_header_text(texts)) == header
+    with pytest.raises(KeyError):
+        srb.merged_header_text([texts[0], "@HD\tVN:1.5\n"])
+    with pytest.raises(KeyError):
+        srb.merged_header_text(["@HD\tVN:1.5\n", texts[1]])
+    assert srb.merged_header_text(["@HD\tVN:1.5\n@PG\tID:x\n"]) == "@HD\tVN:1.5\n"
+
+
+def test_bam_writer_round_trip(tmp_path):
+    from falcon_unzip_b200 import bam
+    import numpy as np
+    rng = np.random.default_rng(3)
+    recs = [bam.encode_record(-1, -1, "r%d" % i, 4, 255, [], "ACGT" * int(rng.integers(1, 9000))) for i in range(40)]
+    fn = str(tmp_path / "w.bam")
+    w = bam.BamWriter(fn, "@HD\tVN:1.5\n", [], level=1)
+    for i in range(0, 40, 7):
+        w.write(b"".join(recs[i:i + 7]))
+    w.close()
+    w.close()
+    text, refs, got = bam.read_bam(fn)
+    assert text == "@HD\tVN:1.5\n" and refs == [] and bytes(got) == b"".join(recs)
