@@ -17,7 +17,7 @@ import os
 import shlex
 import subprocess
 import sys
-from typing import Callable, Dict, Iterable, List, Optional, Sequence
+from typing import Callable, Dict, Iterable, List, Sequence
 
 import numpy as np
 

@@ -14,7 +14,7 @@ concatenated *uncompressed BAM alignment records* (see bam.py) that both the CUD
 from __future__ import annotations
 
 import dataclasses
-from typing import List, Sequence, Tuple
+from typing import List, Tuple
 
 import numpy as np
 

@@ -17,7 +17,6 @@ import os
 import re
 import stat
 import sys
-import tempfile
 import types
 from typing import Dict, Iterable, List
 
