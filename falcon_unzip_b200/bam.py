@@ -210,9 +210,21 @@ def bam_header_bytes(header_text: str, refs: Sequence[Tuple[str, int]]) -> bytes
     return hdr
 
 
+_compress_pool = None
+
+
+def _pool():
+    """Threads for BGZF block compression (zlib releases the GIL; the blocks of a file are independent)."""
+    global _compress_pool
+    if _compress_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _compress_pool = ThreadPoolExecutor(max(1, min(16, len(os.sched_getaffinity(0)))))
+    return _compress_pool
+
+
 class BamWriter:
     """Incremental BAM writer: header in its own BGZF block, then the record bytes handed to write() cut into blocks of
-    at most 65280 payload bytes, EOF marker on close()."""
+    at most 65280 payload bytes (compressed on a thread pool, written in order), EOF marker on close()."""
 
     def __init__(self, path: str, header_text: str, refs: Sequence[Tuple[str, int]] = (), level: int = 6):
         self.path, self.level = path, level
@@ -223,11 +235,19 @@ class BamWriter:
     def write(self, records) -> None:
         self._pending += memoryview(records)
         n_full = len(self._pending) // _BGZF_MAX_PAYLOAD * _BGZF_MAX_PAYLOAD
+        if n_full == 0:
+            return
         mv = memoryview(self._pending)
-        for o in range(0, n_full, _BGZF_MAX_PAYLOAD):
-            self._f.write(_bgzf_block(bytes(mv[o:o + _BGZF_MAX_PAYLOAD]), self.level))
+        payloads = [bytes(mv[o:o + _BGZF_MAX_PAYLOAD]) for o in range(0, n_full, _BGZF_MAX_PAYLOAD)]
         del mv
         del self._pending[:n_full]
+        level = self.level
+        if len(payloads) > 2:
+            blocks = _pool().map(lambda p: _bgzf_block(p, level), payloads)
+        else:
+            blocks = (_bgzf_block(p, level) for p in payloads)
+        for b in blocks:
+            self._f.write(b)
 
     def close(self) -> None:
         if self._f is None:
