@@ -60,3 +60,11 @@ def test_bam_writer_round_trip(tmp_path):
     w.close()
     text, refs, got = bam.read_bam(fn)
     assert text == "@HD\tVN:1.5\n" and refs == [] and bytes(got) == b"".join(recs)
+    # one large write (blocks compressed on the thread pool) gives the bytes of the serial writer
+    big = b"".join(recs) * 3
+    fn2, fn3 = str(tmp_path / "big.bam"), str(tmp_path / "serial.bam")
+    w = bam.BamWriter(fn2, "@HD\tVN:1.5\n", [("c", 9)], level=6)
+    w.write(big)
+    w.close()
+    bam.write_bam(fn3, [("c", 9)], big, header_text="@HD\tVN:1.5\n", level=6)
+    assert open(fn2, "rb").read() == open(fn3, "rb").read()
