@@ -110,8 +110,15 @@ def partition_file(eng, image: np.ndarray, keys: np.ndarray, key_ctg: np.ndarray
     return data, off[bounds]
 
 
-def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_fn, sam_dir, device: int = 0, level: int = 6):
-    """Write <sam_dir>/<ctg>.bam for every selected contig from the reads of the input BAMs (`:8-89`)."""
+def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_fn, sam_dir, device: int = 0, level: int = 6,
+                          rank: int = 0, world_size: int = 1, partition_fn=None):
+    """Write <sam_dir>/<ctg>.bam for every selected contig from the reads of the input BAMs (`:8-89`).
+
+    One process per GPU (world_size > 1): the selected contigs are dealt to the ranks by their number of reads
+    (longest-processing-time first); every rank decodes every input BAM on its GPU but gathers, compresses and writes
+    only ITS contigs -- the output side (host BGZF compression) is what takes the time, and it divides by contig with
+    no exchange between the ranks; a contig's BAM keeps the order of the input files.  partition_fn replaces the
+    device call in the CPU tests."""
     print("rawread_ids_fn:", repr(rawread_ids_fn))
     print("rawread_to_contigs_fn:", repr(rawread_to_contigs_fn))
     read_partition, read_to_ctgs = read_tables(rawread_to_contigs_fn, rawread_ids_fn)
@@ -127,6 +134,12 @@ def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_
         print("ctg, len:", ctg, len(read_partition[ctg]))
     target = read_to_selected_ctg(read_partition, read_to_ctgs)
     ctgs = sorted(set(target.values()))
+    if world_size > 1:
+        from . import shard
+        mine = shard.assign_contigs([float(len(read_partition[c])) for c in ctgs], world_size)[rank]
+        ctgs = [ctgs[i] for i in mine]
+        keep = set(ctgs)
+        target = {o: c for o, c in target.items() if c in keep}
     ctg_index = {c: i for i, c in enumerate(ctgs)}
     by_name = sorted((o.encode("latin-1"), ctg_index[c]) for o, c in target.items())
     keys = np.array([b for b, _c in by_name], dtype="S") if by_name else np.zeros(0, "S1")
@@ -137,11 +150,12 @@ def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_
     header_text = merged_header_text([h[0] for h in headers]) if headers else ""
     refs = headers[0][1] if headers else []
     os.makedirs(sam_dir, exist_ok=True)
-    eng = engine.get_engine(device)
+    eng = engine.get_engine(device) if partition_fn is None else None
+    part = partition_fn or partition_file
     outfile: Dict[str, bam.BamWriter] = {}
     try:
         for image in images:
-            data, bounds = partition_file(eng, image, keys, key_ctg, len(ctgs))
+            data, bounds = part(eng, image, keys, key_ctg, len(ctgs))
             for i, ctg in enumerate(ctgs):
                 a, b = int(bounds[i]), int(bounds[i + 1])
                 if a == b:
