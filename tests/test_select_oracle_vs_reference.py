@@ -68,3 +68,47 @@ def test_bam_writer_round_trip(tmp_path):
     w.close()
     bam.write_bam(fn3, [("c", 9)], big, header_text="@HD\tVN:1.5\n", level=6)
     assert open(fn2, "rb").read() == open(fn3, "rb").read()
+
+
+@needs_ref
+def test_oracle_matches_reference_on_random_tables(tmp_path):
+    """Random rawread_to_contigs tables over fixed BAMs: contig sizes around the > 20 threshold, score ties between contigs,
+    several rank-0 rows per read, NA rows."""
+    import numpy as np
+    from falcon_unzip_b200 import bam
+    rng = np.random.default_rng(123)
+    root = str(tmp_path)
+    names = ["mv/%d/0_%d" % (i, 100 + i) for i in range(90)]
+    with open(os.path.join(root, "ids"), "w") as f:
+        f.write("\n".join(names))                               # no trailing newline here
+    fns = []
+    for k in range(2):
+        recs = [bam.encode_record(-1, -1, names[int(j)], 4, 255, [], "ACGT" * int(rng.integers(1, 50)))
+                for j in rng.integers(0, 90, 120)]
+        fn = os.path.join(root, "f%d.bam" % k)
+        bam.write_bam(fn, [], b"".join(recs), header_text="@HD\tVN:1.5\n@RG\tID:r%d\n@PG\tID:p\n" % k)
+        fns.append(fn)
+    fofn = os.path.join(root, "fofn")
+    with open(fofn, "w") as f:
+        f.write("\n".join(os.path.basename(x) for x in fns) + "\n")
+    ctgs = ["000000F", "000000F_001", "000001F", "NA"]
+    n_nonempty, sizes = 0, set()
+    for trial in range(25):
+        rows = []
+        for i in range(90):
+            for _ in range(int(rng.integers(0, 4))):
+                rows.append("%09d %s 3 %d %d 1" % (i, ctgs[int(rng.choice(4, p=[0.35, 0.3, 0.25, 0.1]))],
+                                                 int(rng.choice(3, p=[0.6, 0.2, 0.2])), -100 * int(rng.integers(1, 4))))
+        r2c = os.path.join(root, "r2c_%d" % trial)
+        with open(r2c, "w") as f:
+            f.write("".join(r + "\n" for r in rows))
+        sam_dir = os.path.join(root, "out_%d" % trial)
+        ref = ref_exec.run_select_reads(fofn, r2c, os.path.join(root, "ids"), sam_dir)
+        header, out = select_oracle.select(fofn, r2c, os.path.join(root, "ids"))
+        assert sorted(ref) == sorted(os.path.join(sam_dir, "%s.bam" % c) for c in out), trial
+        for ctg, recs in out.items():
+            assert ref[os.path.join(sam_dir, "%s.bam" % ctg)] == (header, recs), (trial, ctg)
+        n_nonempty += bool(out)
+        sizes.add(len(out))
+    n_sizes = len(sizes)
+    assert n_nonempty >= 10 and n_sizes > 1                 # the > 20 rule cuts both ways in the sample
