@@ -351,6 +351,39 @@ def read_bam_header(raw, coff, csize) -> Tuple[str, List[Tuple[str, int]], int]:
     raise ValueError("BAM header is incomplete")
 
 
+def read_bam_header_of_file(path: str, first: int = 1 << 20) -> Tuple[str, List[Tuple[str, int]]]:
+    """(header text, refs) of a BAM file from its first bytes only: the leading BGZF blocks are inflated until the
+    header parses; the prefix read grows when the header is longer than it (raw-read BAMs run to hundreds of GB)."""
+    size = os.path.getsize(path)
+    n = min(size, first)
+    while True:
+        with open(path, "rb") as f:
+            raw = f.read(n)
+        data, o = b"", 0
+        while o + 18 <= len(raw):
+            if raw[o:o + 4] != b"\x1f\x8b\x08\x04":
+                raise ValueError("%s: not a BGZF block at byte %d" % (path, o))
+            (xlen,) = struct.unpack_from("<H", raw, o + 10)
+            x, xend, bsize = o + 12, o + 12 + xlen, None
+            while x + 4 <= xend <= len(raw):
+                slen = struct.unpack_from("<H", raw, x + 2)[0]
+                if raw[x] == 66 and raw[x + 1] == 67:
+                    bsize = struct.unpack_from("<H", raw, x + 4)[0] + 1
+                x += 4 + slen
+            if bsize is None or o + bsize > len(raw):
+                break                                           # block cut by the prefix
+            data += zlib.decompress(raw[xend:o + bsize - 8], -15)
+            try:
+                text, refs, _o = parse_bam_header(data)
+                return text, refs
+            except (IndexError, struct.error):
+                pass
+            o += bsize
+        if n >= size:
+            raise ValueError("%s: BAM header is incomplete" % path)
+        n = min(size, n * 8)
+
+
 def read_bam(path: str):
     """-> (header_text, refs [(name, length)], records buffer (memoryview, no copy))."""
     data = bgzf_inflate(path)

@@ -22,7 +22,6 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 from . import bam, engine
-from ._lib import lib
 
 MIN_READS = 20                      # a contig is written when MORE than this many reads pick it (:64)
 
@@ -80,17 +79,6 @@ def merged_header_text(texts: Sequence[str]) -> str:
     return "".join(ln + "\n" for ln in hd + sq + rg + rest)
 
 
-def _bam_header(image: np.ndarray):
-    n_blk = int(lib().fuz_host_bgzf_index(image.ctypes.data, len(image), 0, None, None, None, None))
-    if n_blk < 0:
-        raise ValueError("not a BGZF file")
-    coff, csize = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32)
-    uoff = np.empty(n_blk + 1, np.int64)
-    lib().fuz_host_bgzf_index(image.ctypes.data, len(image), n_blk, coff.ctypes.data, csize.ctypes.data, uoff.ctypes.data, None)
-    text, refs, _n = bam.read_bam_header(image, coff, csize)
-    return text, refs
-
-
 def partition_file(eng, image: np.ndarray, keys: np.ndarray, key_ctg: np.ndarray, n_ctg: int):
     """One input BAM -> (record bytes grouped by contig, file order inside a contig; byte range [n_ctg + 1] of every
     contig).  keys: sorted "S" array of read names, key_ctg: their contig index."""
@@ -145,8 +133,7 @@ def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_
     keys = np.array([b for b, _c in by_name], dtype="S") if by_name else np.zeros(0, "S1")
     key_ctg = np.array([c for _b, c in by_name], dtype=np.int64)
 
-    images = [np.fromfile(fn, dtype=np.uint8) for fn in fns]
-    headers = [_bam_header(im) for im in images]
+    headers = [bam.read_bam_header_of_file(fn) for fn in fns]          # first bytes of every input only
     header_text = merged_header_text([h[0] for h in headers]) if headers else ""
     refs = headers[0][1] if headers else []
     os.makedirs(sam_dir, exist_ok=True)
@@ -154,8 +141,8 @@ def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_
     part = partition_fn or partition_file
     outfile: Dict[str, bam.BamWriter] = {}
     try:
-        for image in images:
-            data, bounds = part(eng, image, keys, key_ctg, len(ctgs))
+        for fn in fns:                                                   # one input in memory at a time
+            data, bounds = part(eng, np.fromfile(fn, dtype=np.uint8), keys, key_ctg, len(ctgs))
             for i, ctg in enumerate(ctgs):
                 a, b = int(bounds[i]), int(bounds[i + 1])
                 if a == b:

@@ -35,3 +35,32 @@ def test_bind_to_gpu_cpus_is_best_effort():
     if not r["bound"]:
         assert after == before and r.get("why")
     os.sched_setaffinity(0, before)
+
+
+def test_bam_header_from_file_prefix(tmp_path):
+    """bam.read_bam_header_of_file: a header spread over several BGZF blocks, read from growing prefixes of the file."""
+    import pytest
+    from falcon_unzip_b200 import bam
+    refs = [("ctg%05d" % i, 1000 + i) for i in range(6000)]
+    text = "@HD\tVN:1.5\n" + "".join("@RG\tID:r%d\n" % i for i in range(3000))
+    hdr = bam.bam_header_bytes(text, refs)
+    rec = bam.encode_record(0, 5, "r", 0, 254, [(4, "=")], "ACGT")
+    fn = str(tmp_path / "h.bam")
+    with open(fn, "wb") as f:
+        for o in range(0, len(hdr), 40000):
+            f.write(bam._bgzf_block(hdr[o:o + 40000], 1))
+        f.write(bam._bgzf_block(rec * 1000, 1))
+        f.write(bam._BGZF_EOF)
+    want_text, want_refs, _recs = bam.read_bam(fn)
+    for first in (100, 5000, 1 << 20):
+        got_text, got_refs = bam.read_bam_header_of_file(fn, first=first)
+        assert got_text == want_text and list(got_refs) == list(want_refs), first
+    cut = str(tmp_path / "cut.bam")
+    with open(cut, "wb") as f:
+        f.write(open(fn, "rb").read()[:3000])
+    with pytest.raises(ValueError):
+        bam.read_bam_header_of_file(cut)
+    with open(cut, "wb") as f:
+        f.write(b"not a bam file at all, just text" * 10)
+    with pytest.raises(ValueError):
+        bam.read_bam_header_of_file(cut)
