@@ -121,6 +121,97 @@ def prepare_batch(records, ctg_names: Sequence[str], ctg_lens: Sequence[int],
     return pb
 
 
+# --------------------------------------------------------------------------- batch splitting
+# One device call takes at most 2^31 - 64 Ki global positions (tile-padded contig lengths; positions are int32 on the
+# device) and 2^31 - 1 records; max_bytes bounds the record bytes of a batch (device staging of the host entry, scratch
+# that scales with the records).  The reference has no such limit because it runs one process per contig
+# (unzip.py:231-281); here an arbitrary contig list is cut into consecutive batches and the batches run back to back.
+MAX_BATCH_GLEN = 0x7fff0000
+MAX_BATCH_RECORDS = 0x7fffffff - 1
+
+
+class BatchPacker:
+    """Running totals of the batch being filled; fits() says whether one more contig stays inside the limits."""
+
+    def __init__(self, max_bytes: int = 6 << 30):
+        self.max_bytes, self.tile = int(max_bytes), lib().fuz_tile_size()
+        self.reset()
+
+    def reset(self) -> None:
+        self.n = self.bytes = self.nrec = self.glen = 0
+
+    def _pad(self, ctg_len: int) -> int:
+        return max((int(ctg_len) + self.tile - 1) // self.tile * self.tile, self.tile)
+
+    def fits(self, nbytes: int, nrec: int, ctg_len: int) -> bool:
+        return self.n == 0 or not (self.bytes + nbytes > self.max_bytes or self.nrec + nrec > MAX_BATCH_RECORDS or
+                                   self.glen + self._pad(ctg_len) > MAX_BATCH_GLEN)
+
+    def add(self, nbytes: int, nrec: int, ctg_len: int) -> None:
+        self.n += 1; self.bytes += int(nbytes); self.nrec += int(nrec); self.glen += self._pad(ctg_len)
+
+
+def plan_batches(ctg_bytes: Sequence[int], ctg_nrec: Sequence[int], ctg_len: Sequence[int],
+                 max_bytes: int = 6 << 30) -> List[Tuple[int, int]]:
+    """Greedy cut of a contig list (kept in order) into batches [(first contig, one past the last)].  A contig never
+    straddles two batches; a single contig beyond max_bytes gets a batch of its own (the device limits still apply and
+    are reported by the library)."""
+    pk = BatchPacker(max_bytes)
+    out, lo = [], 0
+    for c, (cb, cn, cl) in enumerate(zip(ctg_bytes, ctg_nrec, ctg_len)):
+        if not pk.fits(cb, cn, cl):
+            out.append((lo, c))
+            lo = c
+            pk.reset()
+        pk.add(cb, cn, cl)
+    if lo < len(ctg_len):
+        out.append((lo, len(ctg_len)))
+    return out
+
+
+def build_batch(parts: Sequence[Tuple[np.ndarray, np.ndarray]], ctg_names: Sequence[str], ctg_lens: Sequence[int],
+                pin: bool = False, assign_qids: bool = False) -> PreparedBatch:
+    """One batch from per-contig (records, rec_off) pieces: the records are copied ONCE, straight into the (optionally
+    page-locked) buffer of the batch.  The contig of a record comes from ctg_rec_off (the refID fields are not read)."""
+    total = int(sum(len(r) for r, _o in parts))
+    n_rec = int(sum(len(o) - 1 for _r, o in parts))
+    if pin:
+        import torch
+        t_rec = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        records = t_rec.numpy()[:total]
+    else:
+        t_rec, records = None, np.empty(total, np.uint8)
+    rec_off = np.empty(n_rec + 1, np.int64)
+    ctg_rec_off = np.zeros(len(parts) + 1, np.int32)
+    b = r = 0
+    for c, (rec, off) in enumerate(parts):
+        records[b:b + len(rec)] = rec
+        rec_off[r:r + len(off) - 1] = off[:-1] + b
+        b += len(rec); r += len(off) - 1
+        ctg_rec_off[c + 1] = r
+    rec_off[n_rec] = b
+    pb = prepare_batch(records, ctg_names, ctg_lens, rec_off=rec_off, ctg_rec_off=ctg_rec_off, pin=False,
+                       assign_qids=assign_qids)
+    if pin:
+        pb.pinned["records"] = t_rec
+        pb.records = records
+        for name in ("rec_off", "rec_qid", "ctg_rec_off", "ctg_len", "ctg_nq"):
+            a = getattr(pb, name)
+            if a is not None:
+                import torch
+                t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                pb.pinned[name] = t
+                setattr(pb, name, t.numpy())
+    return pb
+
+
+def sub_batch(pb_records: np.ndarray, rec_off: np.ndarray, ctg_rec_off: np.ndarray, lo: int, hi: int):
+    """Records, offsets and contig ranges of contigs [lo, hi) of a larger grouped record buffer (views, no copy)."""
+    r0, r1 = int(ctg_rec_off[lo]), int(ctg_rec_off[hi])
+    b0, b1 = int(rec_off[r0]), int(rec_off[r1])
+    return pb_records[b0:b1], rec_off[r0:r1 + 1] - b0, (np.asarray(ctg_rec_off[lo:hi + 1]) - r0).astype(np.int32)
+
+
 def pin_batch(pb: PreparedBatch) -> None:
     """Move the batch's arrays into pinned host memory (torch owns it)."""
     import torch

@@ -327,19 +327,37 @@ def write_contig_files(res, sl, c: int, ctg_id: str, ref_seq: str, names: Sequen
 
 
 def phase_contigs(records, ctg_names: Sequence[str], ref_seqs: Sequence[str], base_dir: str,
-                  device: int = 0, host_path: bool = True, ctg_rec_off=None):
-    """Fused path: every contig of the batch in one device call, then the per-contig files.
+                  device: int = 0, host_path: bool = True, ctg_rec_off=None, max_batch_bytes: int = 6 << 30):
+    """Fused path: every contig of the list in one device call (or, for lists beyond the limits of one call --
+    engine.plan_batches -- in consecutive batches), then the per-contig files.
     records: concatenated BAM records grouped by contig, in the order of ctg_names (grouping from
-    the refID fields 0..n-1, or given explicitly as record offsets ctg_rec_off)."""
-    pb = engine.prepare_batch(records, ctg_names, [len(s) for s in ref_seqs], ctg_rec_off=ctg_rec_off,
-                              assign_qids=not host_path)       # host entry: q_ids are assigned on the device
+    the refID fields 0..n-1, or given explicitly as record offsets ctg_rec_off).
+    Returns (PhaseResult of the batch -- a list of them when the contigs were split --, {contig: {file kind: path}})."""
+    if not isinstance(records, np.ndarray):
+        records = np.frombuffer(records, dtype=np.uint8)
+    lens = [len(s) for s in ref_seqs]
     eng = engine.get_engine(device)
-    res = eng.phase_host(pb) if host_path else eng.phase_device(pb)
-    sl = formats.contig_slices(res, pb.n_ctg)
-    out = {}
-    for c, name in enumerate(ctg_names):
-        out[name] = write_contig_files(res, sl, c, name, ref_seqs[c], pb.qnames(c), base_dir)
-    return res, out
+    rec_off = engine.index_records(records)
+    if ctg_rec_off is None:
+        refid = engine.record_refids(records, rec_off) if len(rec_off) > 1 else np.zeros(0, np.int32)
+        if len(refid) and (np.any(np.diff(refid) < 0) or refid.min() < 0 or refid.max() >= len(ctg_names)):
+            raise FuzError(5, "records are not grouped by reference id 0..%d" % (len(ctg_names) - 1))
+        ctg_rec_off = np.searchsorted(refid, np.arange(len(ctg_names) + 1), side="left")
+    ctg_rec_off = np.asarray(ctg_rec_off, np.int64)
+    ctg_bytes = rec_off[ctg_rec_off[1:]] - rec_off[ctg_rec_off[:-1]]
+    plan = engine.plan_batches(ctg_bytes, np.diff(ctg_rec_off), lens, max_batch_bytes)
+    out, results = {}, []
+    for lo, hi in plan:
+        sub_rec, sub_off, sub_cro = engine.sub_batch(records, rec_off, ctg_rec_off, lo, hi)
+        pb = engine.prepare_batch(sub_rec, ctg_names[lo:hi], lens[lo:hi], rec_off=sub_off, ctg_rec_off=sub_cro,
+                                  assign_qids=not host_path)   # host entry: q_ids are assigned on the device
+        res = eng.phase_host(pb) if host_path else eng.phase_device(pb)
+        sl = formats.contig_slices(res, pb.n_ctg)
+        for c in range(pb.n_ctg):
+            name = ctg_names[lo + c]
+            out[name] = write_contig_files(res, sl, c, name, ref_seqs[lo + c], pb.qnames(c), base_dir)
+        results.append(res)
+    return (results[0] if len(results) == 1 else results), out
 
 
 def phase_bam(bam_fn, fasta_fn: str, base_dir: str, device: int = 0, verify_crc: bool = True):

@@ -323,3 +323,20 @@ def generate_parallel(cfg: SynthConfig, workers: int = 0) -> SynthSet:
         base += len(buf)
         ctgs.append(np.full(len(p.rec_off) - 1, c, dtype=np.int32))
     return SynthSet(cfg, refs, ref_seqs, het, np.concatenate(recs), np.concatenate(offs), np.concatenate(ctgs))
+
+
+def generate_contigs(cfg: SynthConfig, contig_ids, workers: int = 0):
+    """Yield (contig id, SynthSet of that one contig) for the given GLOBAL contig ids, in the given order, from a pool
+    of processes (call before CUDA is initialised: fork).  A contig's content depends on (seed, id) only, so every
+    partition of a contig list over ranks sees the same contigs as one rank generating all of them."""
+    import multiprocessing as mp
+    import os
+    ids = [int(i) for i in contig_ids]
+    workers = workers or min(len(ids), os.cpu_count() or 1)
+    if workers <= 1 or len(ids) <= 1:
+        for ci in ids:
+            yield ci, _gen_one((cfg, ci))
+        return
+    with mp.get_context("fork").Pool(workers) as pool:
+        for ci, part in zip(ids, pool.imap(_gen_one, [(cfg, ci) for ci in ids])):
+            yield ci, part

@@ -15,16 +15,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--replicate", type=int, default=1)
     ap.add_argument("--contigs", type=int, default=0)
     ap.add_argument("--contig-len", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE")
     a = ap.parse_args()
-    cfg, sset = bench.make_workload(a.config, 0, a.replicate, a.contigs, a.contig_len)
+    a.max_batch_mb = 1 << 20
+    cfg = bench.workload_cfg(a)
+    batches, _s = bench.build_workload(cfg, list(range(cfg.n_contigs)), set(), 1 << 62, pin=False,
+                                       workers=min(cfg.n_contigs, os.cpu_count() or 1))
     import torch
     from falcon_unzip_b200 import engine
     eng = engine.Engine(0)
-    pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs], rec_off=sset.rec_off,
-                              assign_qids=False)
+    for kv in a.opt:
+        key, val = kv.split("=")
+        eng.set_option(key, int(val))
+    pb = batches[0]
     db = eng.upload(pb)
     do, st = eng._retry(engine.default_caps(int(pb.ctg_len.sum()), pb.n_rec), 0, lambda d: eng.phase_batch_async(db, d))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
