@@ -190,7 +190,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     size_t p_goff = P.add(8 * (size_t)(n_ctg + 1)), p_fetched = P.add(8);
     const bool dev_qid = in->h_rec_qid == nullptr;
     FuzLayout D;   // device
-    size_t d_rec = D.add((size_t)in->rec_bytes + 32), d_off = D.add(8 * (size_t)(n_rec + 1)), d_qid = D.add(4 * (size_t)(n_rec + 1));
+    size_t d_rec = D.add((size_t)in->rec_bytes + 64), d_off = D.add(8 * (size_t)(n_rec + 1)), d_qid = D.add(4 * (size_t)(n_rec + 1));
     size_t d_cro = D.add(4 * (size_t)(n_ctg + 1)), d_clen = D.add(4 * (size_t)n_ctg), d_goff = D.add(8 * (size_t)(n_ctg + 1));
     size_t d_cnq = D.add(4 * (size_t)n_ctg), d_fetched = D.add(8);
     size_t d_nfirst = D.add(8 * (size_t)(n_rec + 1));
@@ -240,7 +240,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     } else {
         FUZ_CUDA(ctx, h2d(d_rec, in->h_rec_buf, (size_t)in->rec_bytes));
     }
-    FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 32, st));
+    FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_rec + in->rec_bytes, 0, 64, st));
     if (!dev_qid) FUZ_CUDA(ctx, h2d(d_qid, in->h_rec_qid, 4 * (size_t)n_rec));
     FUZ_CUDA(ctx, h2d(d_cro, in->h_ctg_rec_off, 4 * (size_t)(n_ctg + 1)));
     FUZ_CUDA(ctx, h2d(d_clen, in->h_ctg_len, 4 * (size_t)n_ctg));

@@ -113,6 +113,16 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "project_ctas")) {
         if (value < 1 || value > 148 * 6) return fuz_fail(ctx, FUZ_E_ARG, "project_ctas must be in 1 .. 888");
         ctx->project_ctas = (int)value;
+    } else if (!strcmp(key, "trace_ptr")) {
+        ctx->trace = reinterpret_cast<uint32_t *>(static_cast<uintptr_t>(value));
+    } else if (!strcmp(key, "pileup_debug")) {
+        ctx->pileup_debug = (int)value;
+    } else if (!strcmp(key, "seg_cap")) {
+        if (value < 0) return fuz_fail(ctx, FUZ_E_ARG, "seg_cap must be >= 0");
+        ctx->seg_cap_min = value;
+    } else if (!strcmp(key, "ent_cap")) {
+        if (value < 0) return fuz_fail(ctx, FUZ_E_ARG, "ent_cap must be >= 0");
+        ctx->ent_cap_min = value;
     } else if (!strcmp(key, "max_pairs_per_site")) {
         if (value < 1) return fuz_fail(ctx, FUZ_E_ARG, "max_pairs_per_site must be >= 1");
         ctx->max_pairs_per_site = value;

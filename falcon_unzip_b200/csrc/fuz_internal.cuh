@@ -11,10 +11,9 @@
 
 #include "fuz.h"
 
-#define FUZ_TILE 2048              // reference positions per pileup tile (one CTA)
-#define FUZ_TILE_THREADS 256       // 8 positions (one 32-bit word of 4-bit codes) per thread
+#define FUZ_TILE 8192              // reference positions per pileup tile; contigs are padded to whole tiles
+#define FUZ_TILE_THREADS 1024      // cross-check het test (k_het_from_counts): 8 positions per thread
 #define FUZ_NW (FUZ_TILE_THREADS / 32)
-#define FUZ_NSLOT 15               // reads staged per counting round (4-bit lanes hold <= 15)
 #define FUZ_GRID_BLOCKS (148 * 4)  // grid-stride kernels: 4 CTAs of 256 threads per SM
 
 struct fuz_ctx {
@@ -51,6 +50,10 @@ struct fuz_ctx {
     uint8_t *scan_state = nullptr; size_t scan_state_cap = 0;   // tile states of the multi-CTA scan
     bool ingest_pending = false;       // fuz_bgzf_inflate ran; the next fuz_bam_index_records keeps its status
     bool phase_attr_set = false;
+    bool pileup_attr_set = false;
+    int pileup_debug = 0;
+    uint32_t *trace = nullptr;         // host-mapped progress markers (debugging)
+    int64_t seg_cap_min = 0, ent_cap_min = 0;   // reservations of the segment pileup beyond the heuristics (capacity retry)
     // per-launch profile (diagnostics): an event after every kernel launch
     bool profile = false;
     cudaEvent_t prof_start = nullptr;

@@ -314,7 +314,7 @@ class DeviceBatch:
                 d[:t.numel()].copy_(t, non_blocking=True)
                 return d
             return t.to(device, non_blocking=True)
-        self.rec_buf = up(pb.records, pad=32)
+        self.rec_buf = up(pb.records, pad=64)
         self.rec_off = up(pb.rec_off)
         self.dev_qid = pb.rec_qid is None                # q_ids assigned by fuz_phase_batch
         self.rec_qid = up(pb.rec_qid) if pb.n_rec and not self.dev_qid else torch.zeros(1, dtype=torch.int32, device=device)
@@ -501,8 +501,17 @@ class Engine:
             if st.need_pairs > 0 and st.error_index == 4:
                 per_site = st.need_pairs // max(caps["sites"], 1) + 2
                 self.set_option("max_pairs_per_site", int(per_site))
+            self._grow_scratch(st)
             caps = _grow(caps, st)
         raise FuzError(_lib.FUZ_E_CAPACITY, "capacity retry did not converge")
+
+    def _grow_scratch(self, st) -> None:
+        """FUZ_E_CAPACITY index 6 / 9: the batch needs more segment slots / tile entries than the heuristics of
+        fuz_het_call reserve (CIGARs far denser than 1.5 bytes of SEQ + QUAL per base): reserve what the status reports."""
+        if st.error_index == 6:
+            self.set_option("seg_cap", int(st.n_segments * 1.1) + 1024)
+        elif st.error_index == 9:
+            self.set_option("ent_cap", int(st.reserved[0] * 1.5) + 1024)
 
     def phase_device(self, pb: PreparedBatch, caps: Optional[Dict[str, int]] = None,
                      want_counts: bool = False, stage: str = "all") -> PhaseResult:
@@ -768,8 +777,11 @@ class Engine:
                 _lib.check(self.ctx, rc)
             if st.need_pairs > 0 and st.error_index == 4:
                 self.set_option("max_pairs_per_site", int(st.need_pairs // max(caps["sites"], 1) + 2))
-            caps = _grow(caps, st)
-            host_out = None
+            self._grow_scratch(st)
+            new_caps = _grow(caps, st)
+            if new_caps != caps:
+                host_out = None
+            caps = new_caps
         raise FuzError(_lib.FUZ_E_CAPACITY, "capacity retry did not converge")
 
 

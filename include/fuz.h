@@ -34,7 +34,7 @@
  * Device data model (struct-of-arrays, all little endian)
  *   records   verbatim uncompressed BAM alignment records (block_size + body, SAM spec
  *             4.2) concatenated in `rec_buf`; rec_off[i] is the byte offset of record i
- *             (n_rec + 1 entries).  rec_buf must be followed by >= 32 readable bytes.
+ *             (n_rec + 1 entries).  rec_buf must be followed by >= 64 readable bytes.
  *             Records are grouped by contig (ctg_rec_off) and coordinate sorted inside a
  *             contig, i.e. the order `samtools view <bam> <ctg>` prints.
  *   sites     het-SNP sites ordered by (contig, position): site_ctg, site_pos (1-based
@@ -88,7 +88,7 @@ typedef struct {
     int32_t n_ctg;
     int32_t n_rec;
     int64_t rec_bytes;
-    const uint8_t *d_rec_buf;     /* [rec_bytes + 32]                                   */
+    const uint8_t *d_rec_buf;     /* [rec_bytes + 64]                                   */
     const int64_t *d_rec_off;     /* [n_rec + 1]                                        */
     const int32_t *d_rec_qid;     /* [n_rec] q_id of the record's QNAME in its contig, or NULL:
                                    * fuz_phase_batch assigns them (d_ctg_nq / total_nq ignored) */
@@ -140,8 +140,13 @@ int fuz_ctx_create(int device, fuz_ctx **out);
 int fuz_ctx_destroy(fuz_ctx *ctx);
 const char *fuz_last_error(fuz_ctx *ctx);      /* ctx may be NULL: create-time error     */
 int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
-/* options: "pileup_impl" 0 = tiled register pileup fused with the het test (default),
- *          1 = global-atomic pileup + separate het test (cross-check path);
+/* options: "pileup_impl" 0 = segment-list pileup: CIGARs become match segments once, SEQ slices are staged into
+ *                          shared memory by bulk async copies (TMA) and cut straight into bit-sliced counters (default),
+ *          1 = global-atomic pileup + separate het test (cross-check path),
+ *          2 = reference-aligned 4-bit projection of every read + tiled register pileup (cross-check path);
+ *          "seg_cap" / "ent_cap" minimum reservation of segment slots / tile entries of pileup_impl 0 (a batch denser
+ *                          than the built-in heuristics fails with FUZ_E_CAPACITY, error_index 6 / 9, and
+ *                          fuz_status.n_segments / reserved[0] say how much it needs);
  *          "host_fetch" 1 = fuz_phase_batch_host reads page-locked records through the host mapping and
  *                       moves only header/name/CIGAR/SEQ (default), 0 = always copy the whole buffer,
  *          "pdl" 1 = kernels of a call are launched with programmatic stream serialisation, i.e. the
@@ -240,7 +245,7 @@ int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t comp_bytes, co
                      const int32_t *d_csize, const int64_t *d_uoff, const uint32_t *d_crc, int64_t n_blk,
                      uint8_t *d_out, int64_t out_bytes);
 /* Device form of fuz_host_index_records plus the grouping by reference id: d_rec = the alignment
- * records of a coordinate-sorted BAM (everything after the header), followed by >= 32 readable
+ * records of a coordinate-sorted BAM (everything after the header), followed by >= 64 readable
  * bytes.  Fills d_rec_off [cap_rec + 1] and d_ctg_rec_off [n_ref + 1] (records of reference c =
  * [d_ctg_rec_off[c], d_ctg_rec_off[c+1]); unmapped records, refID -1, lie behind d_ctg_rec_off[n_ref]).
  * Synchronises; *h_n_rec = record count.  FUZ_E_CAPACITY: *h_need_rec says how many slots are needed;
@@ -251,8 +256,8 @@ int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes,
  * files) -- the reference leaves one sorted BAM per contig (falcon_unzip/unzip.py:90-91) and runs fc_phasing.py
  * once per file (unzip.py:124).  File s has its alignment records at d_raw[h_seg_start[s], h_seg_end[s])
  * (ascending, not overlapping; the headers lie between them) and h_seg_nref[s] references; d_raw is followed by
- * >= 32 readable bytes.  All files are indexed in one pass; the MAPPED records of all files are written back to
- * back into d_rec_out [cap_bytes + 32] (unmapped tails dropped), d_rec_off [cap_rec + 1] are their offsets in
+ * >= 64 readable bytes.  All files are indexed in one pass; the MAPPED records of all files are written back to
+ * back into d_rec_out [cap_bytes + 64] (unmapped tails dropped), d_rec_off [cap_rec + 1] are their offsets in
  * d_rec_out, d_ctg_rec_off [sum(n_ref) + 1] the record range of every reference, file after file.  cap_rec
  * counts ALL records of the files.  Synchronises; *h_n_rec = mapped records, *h_rec_bytes = their bytes.
  * Errors as fuz_bam_index_records (FUZ_E_BADRECORD: error_index = file or record). */

@@ -26,7 +26,7 @@ def test_python_binding_matches_header():
     from falcon_unzip_b200 import _lib
     bound = sorted(n for n, _r, _a in _lib.SYMBOLS)
     assert bound == header_symbols()
-    assert _lib.lib().fuz_version() == 1 and _lib.lib().fuz_tile_size() == 2048
+    assert _lib.lib().fuz_version() == 1 and _lib.lib().fuz_tile_size() == 8192
 
 
 def test_host_helpers_work_without_gpu():

@@ -82,7 +82,7 @@ def test_prepare_batch_matches_oracle_qids():
         assert np.array_equal(pb.rec_qid[pb.ctg_rec_off[c]:pb.ctg_rec_off[c + 1]], qid)
         assert pb.qnames(c) == names
     t = pb.goff()
-    assert np.all(t % 2048 == 0) and np.all(np.diff(t) >= pb.ctg_len)
+    assert np.all(t % 8192 == 0) and np.all(np.diff(t) >= pb.ctg_len)
 
 
 def test_py27_int_dict_order_vectors_and_emulator():
