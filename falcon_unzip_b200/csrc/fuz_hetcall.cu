@@ -80,12 +80,12 @@ __global__ void __launch_bounds__(256) k_tile_ranges(int n_tiles, int n_ctg, con
     if (st->error) return;
     const int lane = threadIdx.x & 31;
     for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += (gridDim.x * blockDim.x) >> 5) {
-        const int64_t t0 = (int64_t)t * FUZ_TILE;
+        const int64_t t0 = (int64_t)t * FUZ_PTILE;
         // last c with ctg_goff[c] <= t0  =  (first c with ctg_goff[c] >= t0 + 1) - 1
         int c = fuz_warp_lower_bound<int64_t>(ctg_goff, 0, n_ctg + 1, t0 + 1, lane) - 1;
         if (c >= n_ctg) c = n_ctg - 1;
         const int r0 = ctg_rec_off[c], r1 = ctg_rec_off[c + 1];
-        const int t1 = (int)(t0 + FUZ_TILE);
+        const int t1 = (int)(t0 + FUZ_PTILE);
         const int span = S.ctg_maxspan[c];
         const int lr = S.ctg_last_rec[c];
         const int rlo = fuz_warp_lower_bound<int32_t>(S.r_gstart, r0, r1, (int)t0 - span + 1, lane);
@@ -119,7 +119,6 @@ __device__ __forceinline__ bool het_test(uint32_t cA, uint32_t cC, uint32_t cG, 
 // positions (bit i of hetmask: position i is a het site with counts cnt[i][0..3]); sites of
 // a tile land contiguously (in position order) at an atomically claimed base; tiles are put
 // in order afterwards.
-template <bool NAMED_BARRIER = false>      // true: the 256 consumer threads of k_pileup_tma (bar.sync 1), else the whole CTA
 __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t (&cnt)[8][4], int tile, int t0,
                                                 HetScratch &S, int64_t cap_sites, fuz_status *st,
                                                 int *s_warp_tot, int *s_base) {
@@ -127,7 +126,7 @@ __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t
     int nh = __popc(hetmask);
     int incl = fuz_warp_incl_scan(nh, lane);
     if (lane == 31) s_warp_tot[warp] = incl;
-    if (NAMED_BARRIER) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+    __syncthreads();
     if (warp == 0) {
         int t = lane < FUZ_NW ? s_warp_tot[lane] : 0;
         int ti = fuz_warp_incl_scan(t, lane);
@@ -141,7 +140,7 @@ __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t
             *s_base = base;
         }
     }
-    if (NAMED_BARRIER) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+    __syncthreads();
     if (nh) {
         int64_t o = (int64_t)*s_base + s_warp_tot[warp] + (incl - nh);
 #pragma unroll
@@ -503,6 +502,124 @@ __device__ __forceinline__ uint32_t plane_count(const uint32_t (&acc)[8], int bi
     return v;
 }
 
+// One CTA per 2048-position tile, one thread per 8-position word.  Every read overlapping
+// the tile contributes one ALIGNED word load per thread (no shifting: the projection is on
+// the global grid, one-hot A/C/G/T nibbles).  Counting is bit-sliced *vertically*: 15 words
+// are reduced by a carry-save adder tree (11 full adders = 22 LOP3) to a 4-bit number per
+// (position, base) bit, which is rippled into 8 bit planes held in registers (depth <= 255
+// between spills into 16-bit counters).  No atomics, no shared-memory histogram.
+__global__ void __launch_bounds__(FUZ_PTILE_THREADS, 5) k_pileup_gather(HetScratch S, int64_t cap_sites,
+                                                                       uint32_t *__restrict__ counts_out, fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    __shared__ int4 l_ent[FUZ_PTILE_THREADS];             // x = word offset of the projection, y = first word, z = words
+    __shared__ uint32_t c16s[16][FUZ_PTILE_THREADS];      // spill counters (depth > 255 only): [4 * base + j][thread]
+    __shared__ int s_warp_tot[FUZ_NW];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int t0 = tile * FUZ_PTILE, t1 = t0 + FUZ_PTILE;
+    const int Wt = (t0 >> 3) + tid;                       // my word on the global grid
+    const int rlo = S.tile_rlo[tile], rhi = S.tile_rhi[tile];
+    const uint32_t *__restrict__ proj = S.proj;
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};           // bit planes of the per-(position, base) counters
+    // spill: 16-bit counters, base b, positions 2j (low half) / 2j+1 (high half); kept in shared
+    // memory because they are touched only when more than 255 reads cover a tile
+#define C16(b, j) c16s[4 * (b) + (j)][tid]
+    int n_reads_seen = 0, groups_in_acc = 0;
+    bool spilled = false;
+    for (int cb = rlo; cb < rhi; cb += FUZ_PTILE_THREADS) {
+        // compact the records overlapping the tile (any order: only counts matter here)
+        const int r = cb + tid;
+        const bool ok = r < rhi && S.r_flags[r] && S.r_gend[r] > t0 && S.r_gstart[r] < t1;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < FUZ_NW; w++) { int v = s_warp_tot[w]; if (w < warp) off += v; tot += v; }
+        if (ok) l_ent[off + __popc(m & ((1u << lane) - 1u))] = make_int4(S.r_woff[r], S.r_gstart[r] >> 3, S.r_nwords[r], 0);
+        __syncthreads();
+        n_reads_seen += tot;
+        for (int g = 0; g < tot; g += 15) {
+            const int ns = min(15, tot - g);
+            uint32_t x[15];
+#pragma unroll
+            for (int s = 0; s < 15; s++) {
+                x[s] = 0;
+                if (s < ns) {
+                    const int4 e = l_ent[g + s];
+                    const int j = Wt - e.y;
+                    if ((unsigned)j < (unsigned)e.z) x[s] = __ldg(proj + e.x + j);
+                }
+            }
+            // carry-save adder tree: 15 one-bit inputs per bit position -> 4-bit count
+            uint32_t s0, s1, s2, s3, s4, s5, k0, k1, k2, k3, k4, k5, k6, ones, t0_, t1_, d0, d1, d2, twos, fours, eights;
+            FUZ_FA(x[0], x[1], x[2], s0, k0); FUZ_FA(x[3], x[4], x[5], s1, k1); FUZ_FA(x[6], x[7], x[8], s2, k2);
+            FUZ_FA(x[9], x[10], x[11], s3, k3); FUZ_FA(x[12], x[13], x[14], s4, k4);
+            FUZ_FA(s0, s1, s2, s5, k5); FUZ_FA(s3, s4, s5, ones, k6);
+            FUZ_FA(k0, k1, k2, t0_, d0); FUZ_FA(k3, k4, k5, t1_, d1); FUZ_FA(t0_, t1_, k6, twos, d2);
+            FUZ_FA(d0, d1, d2, fours, eights);
+            // ripple the 4-bit number into the 8 planes
+            uint32_t cy = acc[0] & ones; acc[0] ^= ones;
+            uint32_t nc = maj3(acc[1], twos, cy); acc[1] = xor3(acc[1], twos, cy); cy = nc;
+            nc = maj3(acc[2], fours, cy); acc[2] = xor3(acc[2], fours, cy); cy = nc;
+            nc = maj3(acc[3], eights, cy); acc[3] = xor3(acc[3], eights, cy); cy = nc;
+#pragma unroll
+            for (int k = 4; k < 8; k++) { nc = acc[k] & cy; acc[k] ^= cy; cy = nc; }
+            if (++groups_in_acc == 17) {                 // 17 * 15 = 255: planes are full, spill to 16-bit counters
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (!spilled && (i & 1) == 0) C16(b, i >> 1) = 0;
+                        C16(b, i >> 1) += plane_count(acc, 4 * i + b) << ((i & 1) * 16);
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = 0;
+                groups_in_acc = 0;
+                spilled = true;
+            }
+        }
+        __syncthreads();
+    }
+    if (n_reads_seen > 65535 && tid == 0) fuz_raise(st, FUZ_E_DEPTH, tile);
+    const int pos_limit = S.tile_limit[tile];
+    uint32_t cnt[8][4];
+    uint32_t hetmask = 0;
+    if (!spilled && !counts_out) {
+        // a het site needs two bases with count >= 3 (second allele > 25 % of a depth >= 10):
+        // test that on the planes and extract counts only for the few candidate positions
+        const uint32_t ge3 = (acc[0] & acc[1]) | acc[2] | acc[3] | acc[4] | acc[5] | acc[6] | acc[7];
+        const uint32_t two = (ge3 & (ge3 >> 1) & 0x77777777u) | (ge3 & (ge3 >> 2) & 0x33333333u) | (ge3 & (ge3 >> 3) & 0x11111111u);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) cnt[i][b] = 0;
+            if ((two >> (4 * i)) & 7u) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) cnt[i][b] = plane_count(acc, 4 * i + b);
+                if (t0 + tid * 8 + i < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                cnt[i][b] = (spilled ? (C16(b, i >> 1) >> ((i & 1) * 16)) & 0xFFFFu : 0u) + plane_count(acc, 4 * i + b);
+        if (counts_out) {
+            uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+        }
+        hetmask = het_mask_of(cnt, t0, pos_limit);
+    }
+    emit_tile_sites(hetmask, cnt, tile, t0, S, cap_sites, st, s_warp_tot, &s_base);
+}
+
+#undef C16
+
 #include "fuz_pileup_seg.cuh"
 
 // ---------------------------------------------------------------- cross-check pileup (impl 1)
@@ -550,14 +667,14 @@ __global__ void __launch_bounds__(256) k_pileup_atomic(
     }
 }
 
-__global__ void __launch_bounds__(FUZ_TILE_THREADS) k_het_from_counts(
+__global__ void __launch_bounds__(FUZ_PTILE_THREADS) k_het_from_counts(
     const uint32_t *__restrict__ counts, HetScratch S, int64_t cap_sites, fuz_status *st) {
     fuz_pdl_enter();
     if (st->error) return;
     __shared__ int s_warp_tot[FUZ_NW];
     __shared__ int s_base;
     const int tile = blockIdx.x, tid = threadIdx.x;
-    const int t0 = tile * FUZ_TILE;
+    const int t0 = tile * FUZ_PTILE;
     uint32_t cnt[8][4];
     const uint4 *in = reinterpret_cast<const uint4 *>(counts) + (size_t)t0 + (size_t)tid * 8;
 #pragma unroll
@@ -647,7 +764,7 @@ __global__ void __launch_bounds__(256) k_signature(
         const uint32_t code0 = 1u << b0, code1 = 1u << b1;
         const int n0 = O.d_site_cnt[4 * s + b0], n1 = O.d_site_cnt[4 * s + b1];
         // records that can cover the site = candidates of its pileup tile (file order)
-        const int rlo = S.tile_rlo[gp / FUZ_TILE], rhi = S.tile_rhi[gp / FUZ_TILE];
+        const int rlo = S.tile_rlo[gp / FUZ_PTILE], rhi = S.tile_rhi[gp / FUZ_PTILE];
         const int64_t off0 = S.site_row_off[s], off1 = off0 + n0;
         int run0 = 0, run1 = 0;
         for (int rb = rlo; rb < rhi; rb += 32) {
@@ -685,15 +802,16 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
                         (long long)in->total_glen, FUZ_TILE);
     cudaStream_t st = ctx->stream;
     const int n_rec = in->n_rec, n_ctg = in->n_ctg;
-    const int n_tiles = (int)(in->total_glen / FUZ_TILE);
+    const bool seg_path = ctx->pileup_impl == 2;
+    // tiles of the path that runs: 8192 positions (segment pileup) or 2048 (projection pileup, cross-check het test)
+    const int n_tiles = (int)(in->total_glen / (seg_path ? FUZ_TILE : FUZ_PTILE));
     const int64_t cap_sites = out->cap_sites;
-    const bool seg_path = ctx->pileup_impl == 0;
-    // projection path (pileup_impl 1): one word per 8 aligned reference positions.  SEQ holds 2 bases per byte, so
+    // projection paths (pileup_impl 0, 1): one word per 8 aligned reference positions.  SEQ holds 2 bases per byte, so
     // rec_bytes / 4 words cover every M/=/X base; deletions add to the span and are checked on the device
     // (FUZ_E_CAPACITY, index 6).
     const int64_t proj_cap = seg_path ? 0 : in->rec_bytes / 4 + 5 * (int64_t)n_rec + 64;
     if (proj_cap > 0x7fffffffLL) return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (projection exceeds 2^31 words)");
-    // segment path (pileup_impl 0): a record with n CIGAR operations takes n / 2 + 1 segment slots; a read adds one
+    // segment path (pileup_impl 2): a record with n CIGAR operations takes n / 2 + 1 segment slots; a read adds one
     // entry to every tile it overlaps.  Both are bounded by heuristics on the record bytes (a BAM record spends 1.5
     // bytes per base on SEQ + QUAL); a denser batch fails with FUZ_E_CAPACITY (index 6 / 9) and fuz_status says how
     // much is needed (n_segments, reserved[0]): options "seg_cap" / "ent_cap" raise the reservation.
@@ -704,7 +822,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         if (seg_cap > 0x7fffffffLL || ent_cap > 0x7fffffffLL)
             return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (more than 2^31 segments or tile entries)");
     }
-    const int pile_ctas = std::min(n_tiles, 148 * 2);
+    const int pile_ctas = seg_path ? std::min(n_tiles, 148 * 2) : 0;
     HetScratch S;
     FuzLayout L;
     size_t o_gstart = L.add(4 * (size_t)(n_rec + 1)), o_gend = L.add(4 * (size_t)(n_rec + 1));
@@ -767,7 +885,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         ctx->timing_used++;
     }
     if (seg_path) {
-        const size_t smem = FUZ_NSTAGE * sizeof(FuzStage) + 2 * FUZ_G * (FUZ_TILE / 8) * sizeof(uint32_t) + 2 * FUZ_NSTAGE * sizeof(uint64_t);
+        const size_t smem = FUZ_NSTAGE * sizeof(FuzStage) + FUZ_G * (FUZ_TILE / 8) * sizeof(uint32_t) + 2 * FUZ_NSTAGE * sizeof(uint64_t);
         if (!ctx->pileup_attr_set) {
             FUZ_CUDA(ctx, cudaFuncSetAttribute(k_pileup_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctx->pileup_attr_set = true;
@@ -787,6 +905,18 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
                    ctx->pileup_debug, ctx->trace);
         FUZ_LAUNCH_CHECK(ctx, "k_pileup_tma");
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
+    } else if (ctx->pileup_impl == 0) {
+        if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
+        if (n_rec > 0) {
+            fuz_launch(ctx, k_project, ctx->project_ctas, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff,
+                                                       n_ctg, S, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_project");
+        }
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
+        fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_PTILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
+        if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
     } else {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
@@ -801,7 +931,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
         fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
-        fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_TILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
+        fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_PTILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
     fuz_launch(ctx, k_sites_finalize, 1, 1024, 0, st, n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);

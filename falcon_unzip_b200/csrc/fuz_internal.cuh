@@ -11,9 +11,10 @@
 
 #include "fuz.h"
 
-#define FUZ_TILE 8192              // reference positions per pileup tile; contigs are padded to whole tiles
-#define FUZ_TILE_THREADS 1024      // cross-check het test (k_het_from_counts): 8 positions per thread
-#define FUZ_NW (FUZ_TILE_THREADS / 32)
+#define FUZ_TILE 8192              // contigs are padded to whole tiles of this size (= the tile of the segment pileup)
+#define FUZ_PTILE 2048             // tile of the projection pileup and of the cross-check het test (divides FUZ_TILE)
+#define FUZ_PTILE_THREADS 256      // 8 positions (one 32-bit word of 4-bit codes) per thread
+#define FUZ_NW (FUZ_PTILE_THREADS / 32)
 #define FUZ_GRID_BLOCKS (148 * 4)  // grid-stride kernels: 4 CTAs of 256 threads per SM
 
 struct fuz_ctx {

@@ -22,7 +22,7 @@
 #define FUZ_G 4                    // reads per pipeline stage
 #define FUZ_SLICE_CAP 4352         // bytes of SEQ staged per (read, tile): 4096 + alignment margins + insertions
 #define FUZ_SEGW 96                // segments staged per (read, tile)
-#define FUZ_NSTAGE 3
+#define FUZ_NSTAGE 4
 #define FUZ_ENT_SLOW 1             // the slice or the segment list exceed a stage slot: consumers read global memory
 #define FUZ_CONSUMERS 256          // 32 positions each
 #define FUZ_CW (FUZ_CONSUMERS / 32)
@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) k_segments(
             uint32_t rp = 0, qp = 0, skip = 0, aligned = 0;                  // relative to the record start
             int seg_rs = 0, seg_dq = 0;                                      // absolute start, query - reference
             unsigned long long total = 0;
-            bool open = false, badop = false, overrun = false;
+            bool open = false, overrun = false;
+            uint32_t opmax = 0;
             uint32_t prev = __ldg(wp);
             // class of an operation, two bits each: 1 = M = X (advance both), 2 = I S (query), 3 = D (reference), 0 = N H P
             // and unknown codes (nothing, phasing.py:77-96).  Bit 0 = advances the reference, bit0 ^ bit1 = the query
@@ -122,24 +123,28 @@ __global__ void __launch_bounds__(256) k_segments(
                 prev = cur;
                 const uint32_t len = cw >> 4, op = cw & 15;
                 const uint32_t cls = len ? (kClass >> (2 * op)) & 3u : 0u;
-                badop |= op > 8;
+                opmax = max(opmax, op);
                 total += len;
                 if (op == 4) skip += len;
                 if (cls == 1) {
                     if (!open) { open = true; seg_rs = gs + (int)rp; seg_dq = (int)(qp - rp) - gs; }
-                    if (qp + len > (uint32_t)l_seq) overrun = true;          // IndexError phasing.py:84
-                    aligned += len;
                 } else if (cls && open) {                                    // I D S end a segment
                     *out++ = make_int4(seg_rs, gs + (int)rp, seg_dq, 0);
+                    aligned += (uint32_t)(gs + (int)rp - seg_rs);
+                    overrun |= qp > (uint32_t)l_seq;                         // IndexError phasing.py:84
                     open = false;
                 }
                 rp += (cls & 1u) ? len : 0u;
                 qp += ((cls ^ (cls >> 1)) & 1u) ? len : 0u;
             }
-            if (open) *out++ = make_int4(seg_rs, gs + (int)rp, seg_dq, 0);
+            if (open) {
+                *out++ = make_int4(seg_rs, gs + (int)rp, seg_dq, 0);
+                aligned += (uint32_t)(gs + (int)rp - seg_rs);
+                overrun |= qp > (uint32_t)l_seq;
+            }
             const int n_seg = (int)(out - out0);
             span = rp;
-            if (badop || total == 0 || total >= 0x80000000ull || gstart64 + rp > 0x7fffffffLL) {   // unknown op / ZeroDivisionError phasing.py:72
+            if (opmax > 8 || total == 0 || total >= 0x80000000ull || gstart64 + rp > 0x7fffffffLL) {   // unknown op / ZeroDivisionError phasing.py:72
                 fuz_raise(st, FUZ_E_BADRECORD, r);
                 ok = false;
             } else {
@@ -264,14 +269,14 @@ __device__ __forceinline__ void fuz_mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void fuz_mbar_arrive_expect(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void fuz_mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void fuz_mbar_wait(uint32_t bar, uint32_t parity, unsigned sleep_ns = 100) {
     uint32_t done;
     uint32_t spins = 0;
     for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(40);                                              // leave the issue slots to the other warps
+        __nanosleep(sleep_ns);                                             // leave the issue slots to the other warps
         if (++spins > (1u << 24)) __trap();                           // a lost arrival becomes a CUDA error, not a hang
     }
 }
@@ -316,6 +321,25 @@ __device__ __forceinline__ void fuz_cut_quad(const int4 sg, const uint4 *seq, in
     }
 }
 
+// The same cut without branches (shared memory only): nothing survives when `valid` is false.  Four of these run
+// interleaved in the main pass of a stage.
+__device__ __forceinline__ void fuz_cut_quad_bf(const int4 sg, const uint4 *seq, int dqb, int Q0, bool valid, uint32_t (&v)[4]) {
+    const int n = (int)((uint32_t)Q0 + (uint32_t)sg.z + (uint32_t)dqb);
+    const uint4 *cp = seq + (valid ? n >> 5 : 0);
+    const uint4 a = cp[0], b = cp[1];
+    uint32_t m0 = a.x, m1 = a.y, m2 = a.z, m3 = a.w, m4 = b.x, m5 = b.y;
+    if (n & 16) { m0 = m2; m1 = m3; m2 = m4; m3 = m5; m4 = b.z; m5 = b.w; }
+    if (n & 8) { m0 = m1; m1 = m2; m2 = m3; m3 = m4; m4 = m5; }
+    const uint32_t sh = (uint32_t)(n & 7) * 4;
+    const uint32_t b0 = __byte_perm(m0, 0, 0x0123), b1 = __byte_perm(m1, 0, 0x0123), b2 = __byte_perm(m2, 0, 0x0123),
+                   b3 = __byte_perm(m3, 0, 0x0123), b4 = __byte_perm(m4, 0, 0x0123);
+    const int hi = valid ? 4 * min(sg.y - Q0, 32) : 0, lo = 4 * min(max(sg.x - Q0, 0), 32);     // in bits
+    v[0] = __funnelshift_l(b1, b0, sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)lo) & ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(hi, 0));
+    v[1] = __funnelshift_l(b2, b1, sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(lo - 32, 0)) & ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(hi - 32, 0));
+    v[2] = __funnelshift_l(b3, b2, sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(lo - 64, 0)) & ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(hi - 64, 0));
+    v[3] = __funnelshift_l(b4, b3, sh) & __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(lo - 96, 0)) & ~__funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)max(hi - 96, 0));
+}
+
 __device__ __forceinline__ void fuz_fa(uint32_t a, uint32_t b, uint32_t c, uint32_t &s, uint32_t &cy) { s = xor3(a, b, c); cy = maj3(a, b, c); }
 
 // Harley-Seal step of one word: four more one-bit inputs per bit position.  p[0..3] hold the weights 1, 2, 4, 8, the
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FuzStage *stages = reinterpret_cast<FuzStage *>(smem_raw);
     uint32_t (*fix)[FUZ_G][FUZ_TILE / 8] = reinterpret_cast<uint32_t (*)[FUZ_G][FUZ_TILE / 8]>(smem_raw + FUZ_NSTAGE * sizeof(FuzStage));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FUZ_NSTAGE * sizeof(FuzStage) + 2 * sizeof(fix[0]));   // full[], empty[]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FUZ_NSTAGE * sizeof(FuzStage) + sizeof(fix[0]));   // full[], empty[]
     __shared__ int s_warp_tot[FUZ_CW];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -368,7 +392,7 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * FUZ_G * (FUZ_TILE / 8); i += FUZ_PILEUP_THREADS) (&fix[0][0][0])[i] = 0;
+    for (int i = tid; i < FUZ_G * (FUZ_TILE / 8); i += FUZ_PILEUP_THREADS) (&fix[0][0][0])[i] = 0;
     __syncthreads();
     const bool dead = st->error != 0;                                 // an earlier kernel failed: no tile is processed
     if (warp == FUZ_CW) {
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
                     FuzStage &sg = stages[stage];
                     const uint32_t full = fuz_smem_u32(&bars[stage]), empty = fuz_smem_u32(&bars[FUZ_NSTAGE + stage]);
                     FUZ_TR(21);
-                    fuz_mbar_wait(empty, phase ^ 1u);
+                    fuz_mbar_wait(empty, phase ^ 1u, 400);
                     FUZ_TR(22);
                     const bool mine = have && !end && lane / FUZ_G == gi;
                     const int slot = lane % FUZ_G;
@@ -459,7 +483,7 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
     }
     int n_reads_seen = 0, groups16 = 0, sit = 0;                      // sit = stages of the tile so far
     bool spilled = false;
-    int stage = 0, fb = 0;
+    int stage = 0;
     uint32_t phase = 0;
     auto flush16 = [&]() {                                            // a group of 16 reads is complete: planes hold <= 15 * 16 + 15
         if (++groups16 == 15) {
@@ -480,6 +504,10 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
             spilled = true;
         }
     };
+    // Every consumer warp works through the stages on its own (no CTA barrier per stage): it owns one ROW of the tile
+    // (32 quads = 1024 positions), handles the segment starts inside its row as warp-private tasks (fix-up words in its
+    // own slice of `fix`) and only meets the other warps at the end of a tile.
+    uint32_t (*wfix)[128] = reinterpret_cast<uint32_t (*)[128]>(&fix[0][0][0]) + warp * FUZ_G;      // [read][32 quads x 4 words]
     for (;;) {
         FuzStage &sg = stages[stage];
         FUZ_TR(2);
@@ -488,74 +516,107 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
         FUZ_TR(3 | (n << 8) | (tile << 16));
         if (n < 0) break;
         const int t0 = tile * FUZ_TILE;
-        const int Q0 = t0 + 32 * tid;
-        uint32_t (*fx)[FUZ_TILE / 8] = fix[fb];
-        // ---- (1) segment starts inside the tile as dense tasks: segment j >= 1 of read s -> the quad it starts in
-        if (!(debug & 9)) {
-            static_assert(FUZ_G == 4, "task table written for 4 reads per stage");
-            const int tb1 = n > 0 ? max(sg.ent[0].nseg - 1, 0) : 0;
-            const int tb2 = tb1 + (n > 1 ? max(sg.ent[1].nseg - 1, 0) : 0);
-            const int tb3 = tb2 + (n > 2 ? max(sg.ent[2].nseg - 1, 0) : 0);
-            const int tb4 = tb3 + (n > 3 ? max(sg.ent[3].nseg - 1, 0) : 0);
-            for (int k = tid; k < tb4; k += FUZ_CONSUMERS) {
-                const int s = (k >= tb1) + (k >= tb2) + (k >= tb3);
-                const int j = k - (s == 0 ? 0 : s == 1 ? tb1 : s == 2 ? tb2 : tb3) + 1;
-                const bool slow = sg.ent[s].flags != 0;
-                const int4 seg = slow ? __ldg(S.segs + sg.ent[s].seg_src + j) : sg.segs[s][j];
-                if ((seg.x & 31) == 0) continue;                      // starts a quad: the main pass covers it
-                const int q0 = seg.x & ~31;
-                uint32_t v[4];
-                if (slow) fuz_cut_quad<true>(seg, reinterpret_cast<const uint4 *>(rec_buf + sg.ent[s].seq_off), sg.ent[s].dqb, q0, v);
-                else fuz_cut_quad<false>(seg, reinterpret_cast<const uint4 *>(sg.seq[s]), sg.ent[s].dqb, q0, v);
-                uint32_t *dst = &fx[s][(q0 - t0) >> 3];
+        const int Q0 = t0 + 32 * tid, R0 = t0 + 1024 * warp;
+        uint32_t x[FUZ_G][4];
+        bool fast = !(debug & 17);
 #pragma unroll
-                for (int w = 0; w < 4; w++)
-                    if (v[w]) atomicOr(dst + w, v[w]);
+        for (int s = 0; s < FUZ_G; s++) fast = fast && !(s < n && sg.ent[s].flags);
+        if (fast) {
+            // ---- (0) lanes 0 .. 2 FUZ_G - 1: segments of read s starting before the row (even lane) / before its end (odd lane)
+            int cnt_lt = 0, end_prev = 0;
+            {
+                const int s = (lane >> 1) & (FUZ_G - 1);
+                const int bound = R0 + ((lane & 1) ? 1024 : 0);
+                int hi = (lane < 2 * FUZ_G && s < n) ? sg.ent[s].nseg : 0;
+                while (cnt_lt < hi) { const int mid = (cnt_lt + hi) >> 1; if (sg.segs[s][mid].x < bound) cnt_lt = mid + 1; else hi = mid; }
+                if (cnt_lt > 0) end_prev = sg.segs[s][cnt_lt - 1].y;       // end of the last segment starting before the bound
+            }
+            int a[FUZ_G], tb[FUZ_G + 1], c0[FUZ_G];
+            tb[0] = 0;
+#pragma unroll
+            for (int s = 0; s < FUZ_G; s++) {
+                a[s] = __shfl_sync(0xffffffffu, cnt_lt, 2 * s);
+                const int b = __shfl_sync(0xffffffffu, cnt_lt, 2 * s + 1);
+                const int ep = __shfl_sync(0xffffffffu, end_prev, 2 * s);
+                c0[s] = a[s] - (a[s] > 0 && ep > R0 ? 1 : 0);            // segments ending at or before the row start
+                a[s] = max(a[s], 1);                                     // segment 0 is never a task (the main pass masks its start)
+                tb[s + 1] = tb[s] + max(b - a[s], 0);
+            }
+            // ---- (1) segment starts inside my row as dense tasks: the piece of the segment inside the quad it starts in
+            if (!(debug & 8)) {
+                for (int k = lane; k < tb[FUZ_G]; k += 32) {
+                    static_assert(FUZ_G == 4, "task table written for 4 reads per stage");
+                    const int s = (k >= tb[1]) + (k >= tb[2]) + (k >= tb[3]);
+                    const int j = k - (s == 0 ? 0 : s == 1 ? tb[1] : s == 2 ? tb[2] : tb[3]) + (s == 0 ? a[0] : s == 1 ? a[1] : s == 2 ? a[2] : a[3]);
+                    const int4 seg = sg.segs[s][j];
+                    if ((seg.x & 31) == 0) continue;                      // starts a quad: the main pass covers it
+                    const int q0 = seg.x & ~31;
+                    uint32_t v[4];
+                    fuz_cut_quad<false>(seg, reinterpret_cast<const uint4 *>(sg.seq[s]), sg.ent[s].dqb, q0, v);
+                    uint32_t *dst = &wfix[s][(q0 - R0) >> 3];
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if (v[w]) atomicOr(dst + w, v[w]);
+                }
+            }
+            __syncwarp();
+            // ---- (2) the segment covering the start of my quad: four branch-free searches and cuts, interleaved
+            bool ovf = false;
+#pragma unroll
+            for (int s = 0; s < FUZ_G; s++) {
+                const int nseg = s < n ? sg.ent[s].nseg : 0;
+                const int E = c0[s] + lane < nseg ? sg.segs[s][c0[s] + lane].y : 0x7fffffff;
+                const int e31 = __shfl_sync(0xffffffffu, E, 31);
+                int idx = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int t = __shfl_sync(0xffffffffu, E, idx + step - 1);
+                    idx += t <= Q0 ? step : 0;
+                }
+                ovf = ovf || (idx == 31 && e31 <= Q0);                // more than 31 ends inside the row: generic path
+                const int c = c0[s] + idx;
+                const int4 seg = sg.segs[s][min(c, FUZ_SEGW - 1)];
+                fuz_cut_quad_bf(seg, reinterpret_cast<const uint4 *>(sg.seq[s]), sg.ent[s].dqb, Q0, c < nseg && seg.x < Q0 + 32, x[s]);
+            }
+            ovf = __any_sync(0xffffffffu, ovf);
+            uint32_t bad = 0;
+#pragma unroll
+            for (int s = 0; s < FUZ_G; s++) {
+                uint4 *fp = reinterpret_cast<uint4 *>(&wfix[s][4 * lane]);
+                const uint4 f = *fp;
+                *fp = make_uint4(0, 0, 0, 0);
+                x[s][0] |= f.x; x[s][1] |= f.y; x[s][2] |= f.z; x[s][3] |= f.w;
+                bad |= bad_nibbles(x[s][0]) | bad_nibbles(x[s][1]) | bad_nibbles(x[s][2]) | bad_nibbles(x[s][3]);
+            }
+            if (ovf) fast = false;
+            else if (bad & 0x01010101u) {                             // ambiguity codes never count (phasing.py:108-111)
+#pragma unroll
+                for (int s = 0; s < FUZ_G; s++)
+#pragma unroll
+                    for (int w = 0; w < 4; w++) x[s][w] = keep_acgt(x[s][w]);
             }
         }
-        FUZ_TR(4);
-        fuz_consumer_sync();
-        FUZ_TR(5);
-        // ---- (2) the segment covering the start of my quad + the fix-up words
-        uint32_t x[FUZ_G][4];
+        if (!fast) {
+            // generic path (reads whose slice or segment list exceed a stage slot, rows with more than 31 segment ends): every
+            // lane walks the segments that intersect its quad
 #pragma unroll
-        for (int s = 0; s < FUZ_G; s++) {
+            for (int s = 0; s < FUZ_G; s++) {
 #pragma unroll
-            for (int w = 0; w < 4; w++) x[s][w] = 0;
-            if (s < n && !(debug & 1)) {
+                for (int w = 0; w < 4; w++) x[s][w] = 0;
+                if (s >= n || (debug & 17)) continue;
                 const int nseg = sg.ent[s].nseg, dqb = sg.ent[s].dqb;
-                if (nseg > 0) {
-                    if (debug & 16) {
-                    } else if (!sg.ent[s].flags) {
-                        // c = segments ending at or before the start of my quad (the lanes of a warp probe nearly the
-                        // same entries: broadcasts)
-                        int c = 0, hi = nseg;
-                        while (c < hi) {
-                            const int mid = (c + hi) >> 1;
-                            if (sg.segs[s][mid].y <= Q0) c = mid + 1; else hi = mid;
-                        }
-                        if (c < nseg) {
-                            const int4 seg = sg.segs[s][c];
-                            if (seg.x < Q0 + 32) fuz_cut_quad<false>(seg, reinterpret_cast<const uint4 *>(sg.seq[s]), dqb, Q0, x[s]);
-                        }
-                    } else {
-                        const int4 *gs = S.segs + sg.ent[s].seg_src;
-                        int lo = 0, hi = nseg;
-                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&gs[mid].y) <= Q0) lo = mid + 1; else hi = mid; }
-                        if (lo < nseg) {
-                            const int4 seg = __ldg(gs + lo);
-                            if (seg.x < Q0 + 32) fuz_cut_quad<true>(seg, reinterpret_cast<const uint4 *>(rec_buf + sg.ent[s].seq_off), dqb, Q0, x[s]);
-                        }
-                    }
-                    uint4 *fp = reinterpret_cast<uint4 *>(&fx[s][4 * tid]);
-                    const uint4 f = *fp;
-                    if (f.x | f.y | f.z | f.w) *fp = make_uint4(0, 0, 0, 0);
-                    x[s][0] |= f.x; x[s][1] |= f.y; x[s][2] |= f.z; x[s][3] |= f.w;
-                    // ambiguity codes never count (phasing.py:108-111)
-                    if ((bad_nibbles(x[s][0]) | bad_nibbles(x[s][1]) | bad_nibbles(x[s][2]) | bad_nibbles(x[s][3])) & 0x01010101u) {
+                const bool slow = sg.ent[s].flags != 0;
+                const int4 *segs = slow ? S.segs + sg.ent[s].seg_src : &sg.segs[s][0];
+                const uint4 *seq = slow ? reinterpret_cast<const uint4 *>(rec_buf + sg.ent[s].seq_off) : reinterpret_cast<const uint4 *>(sg.seq[s]);
+                int c = 0, hi = nseg;
+                while (c < hi) { const int mid = (c + hi) >> 1; if (segs[mid].y <= Q0) c = mid + 1; else hi = mid; }
+                for (; c < nseg; c++) {
+                    const int4 seg = segs[c];
+                    if (seg.x >= Q0 + 32) break;
+                    uint32_t v[4];
+                    if (slow) fuz_cut_quad<true>(seg, seq, dqb, Q0, v); else fuz_cut_quad<false>(seg, seq, dqb, Q0, v);
 #pragma unroll
-                        for (int w = 0; w < 4; w++) x[s][w] = keep_acgt(x[s][w]);
-                    }
+                    for (int w = 0; w < 4; w++) x[s][w] |= keep_acgt(v[w]);
                 }
             }
         }
@@ -563,7 +624,6 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
         __syncwarp();
         if (lane == 0) fuz_mbar_arrive(fuz_smem_u32(&bars[FUZ_NSTAGE + stage]));      // the stage may be refilled
         if (++stage == FUZ_NSTAGE) { stage = 0; phase ^= 1u; }
-        fb ^= 1;
         n_reads_seen += n;
         {
             uint32_t c16[4];

@@ -140,11 +140,14 @@ int fuz_ctx_create(int device, fuz_ctx **out);
 int fuz_ctx_destroy(fuz_ctx *ctx);
 const char *fuz_last_error(fuz_ctx *ctx);      /* ctx may be NULL: create-time error     */
 int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
-/* options: "pileup_impl" 0 = segment-list pileup: CIGARs become match segments once, SEQ slices are staged into
- *                          shared memory by bulk async copies (TMA) and cut straight into bit-sliced counters (default),
+/* options: "pileup_impl" 0 = reference-aligned 4-bit projection of every read + tiled register pileup fused with the het
+ *                          test (default),
  *          1 = global-atomic pileup + separate het test (cross-check path),
- *          2 = reference-aligned 4-bit projection of every read + tiled register pileup (cross-check path);
- *          "seg_cap" / "ent_cap" minimum reservation of segment slots / tile entries of pileup_impl 0 (a batch denser
+ *          2 = segment-list pileup: CIGARs become match segments once, SEQ slices are staged into shared memory by
+ *              bulk async copies (cp.async.bulk + mbarrier producer / consumer pipeline) and cut straight into
+ *              bit-sliced counters without a projection (measured slower than 0; kept as an
+ *              independent implementation that the tests compare bit for bit);
+ *          "seg_cap" / "ent_cap" minimum reservation of segment slots / tile entries of pileup_impl 2 (a batch denser
  *                          than the built-in heuristics fails with FUZ_E_CAPACITY, error_index 6 / 9, and
  *                          fuz_status.n_segments / reserved[0] say how much it needs);
  *          "host_fetch" 1 = fuz_phase_batch_host reads page-locked records through the host mapping and

@@ -31,7 +31,7 @@ def _assert_same_files(a, b):
                 raise AssertionError("%s/%s: %d vs %d lines" % (ctg, k, len(la), len(lb)))
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_pileup_counts_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
@@ -53,7 +53,7 @@ def test_pileup_counts_match_oracle(eng, cfg, impl):
             name, len(bad), bad[0], want[bad[0]], got[bad[0]])
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_het_call_arrays_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
@@ -97,6 +97,25 @@ def test_fused_batch_files_match_oracle(eng, cfg, host_path, tmp_path):
     _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs,
                                       str(tmp_path / "gpu"), host_path=host_path)
     _assert_same_files(want, got)
+
+
+@pytest.mark.parametrize("cfg", ["quirks", "noisy", "long", "c5_slice"])
+def test_segment_tma_pileup_files_match_oracle(eng, cfg, tmp_path):
+    """pileup_impl 2 (match segments + cp.async.bulk staged SEQ slices, csrc/fuz_pileup_seg.cuh): the six files of every
+    contig against the oracle.  noisy: every read takes the global-memory route (more segments per tile than a stage slot);
+    long: 100 kb reads over many tiles; c5_slice: the bench shape (15 kb reads, 60x), several tiles per CTA."""
+    import dataclasses
+    from falcon_unzip_b200 import phasing, synth
+    if cfg == "c5_slice":
+        sset = synth.generate(dataclasses.replace(synth.CONFIGS["c5"], n_contigs=2, contig_len=150_000))
+    else:
+        sset = synth_set(cfg)
+    eng.set_option("pileup_impl", 2)
+    try:
+        _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs, str(tmp_path / "gpu"))
+    finally:
+        eng.set_option("pileup_impl", 0)
+    _assert_same_files(_oracle_files(sset, tmp_path / "oracle"), got)
 
 
 def test_reference_cli_per_stage_files_match_oracle(eng, tmp_path):
