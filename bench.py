@@ -93,7 +93,7 @@ def sample_ids(cfg, ids, budget_bases: float = 2.5e8, most: int = 16):
 
 
 def build_workload(cfg, ids, keep_ids, max_batch_bytes: int, pin: bool, workers: int):
-    """Generate the contigs `ids` (synth.generate_contigs, a pool of processes) and pack them, in order, into
+    """Generate the contigs `ids` (synth.generate_contigs_fast: libfuz_synth.so on a pool of threads) and pack them, in order, into
     PreparedBatches.  -> (batches, samples {contig id: dict(batch, local, name, ref_seq, records, rec_off)})."""
     from falcon_unzip_b200 import engine, synth
     pk = engine.BatchPacker(max_batch_bytes)
@@ -105,7 +105,9 @@ def build_workload(cfg, ids, keep_ids, max_batch_bytes: int, pin: bool, workers:
             batches.append(engine.build_batch(parts, names, lens, pin=pin, assign_qids=False))
             parts.clear(); names.clear(); lens.clear()
             pk.reset()
-    for ci, part in synth.generate_contigs(cfg, ids, workers):
+    # full-size workloads come from the native generator (threads); configs with planted quirks from the numpy one (processes)
+    gen = synth.generate_contigs_fast(cfg, ids, workers) if synth.fast_supported(cfg) else synth.generate_contigs(cfg, ids, workers)
+    for ci, part in gen:
         name, length = part.refs[0]
         nb, nr = len(part.records), len(part.rec_off) - 1
         if not pk.fits(nb, nr, length):

@@ -321,7 +321,7 @@ def parse_bam_header(data) -> Tuple[str, List[Tuple[str, int]], int]:
     (l_text,) = struct.unpack_from("<i", data, 4)
     if 8 + l_text + 4 > len(data):
         raise IndexError("header text incomplete")
-    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("ascii", "replace")
+    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("latin-1")
     o = 8 + l_text
     (n_ref,) = struct.unpack_from("<i", data, o)
     o += 4
@@ -390,7 +390,7 @@ def read_bam(path: str):
     if bytes(data[:4]) != b"BAM\1":
         raise ValueError("%s: missing BAM magic" % path)
     (l_text,) = struct.unpack_from("<i", data, 4)
-    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("ascii", "replace")
+    text = bytes(data[8:8 + l_text]).split(b"\0", 1)[0].decode("latin-1")
     o = 8 + l_text
     (n_ref,) = struct.unpack_from("<i", data, o)
     o += 4

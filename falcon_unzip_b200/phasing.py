@@ -39,9 +39,29 @@ def makePypeLocalFile(path):
     return SimpleNamespace(path=path)
 
 
-def _open_out(path: str):
-    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-    return open(path, "w")
+class _open_out:
+    """Output file that only appears under its name when it was written completely: text goes to `<path>.tmp`, which
+    replaces `path` when the block ends without an exception (pypeFLOW takes the existence of a file for success; the
+    reference writes in place, phasing.py:39-40,132)."""
+
+    def __init__(self, path: str):
+        self.path = path
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        self.f = open(path + ".tmp", "w")
+
+    def __enter__(self):
+        return self.f
+
+    def __exit__(self, exc_type, exc, tb):
+        self.f.close()
+        if exc_type is None:
+            os.replace(self.path + ".tmp", self.path)
+        else:
+            try:
+                os.unlink(self.path + ".tmp")
+            except OSError:
+                pass
+        return False
 
 
 # --------------------------------------------------------------------------- inputs
@@ -176,6 +196,14 @@ def generate_association_table(self):
 
 
 # --------------------------------------------------------------------------- stage 3
+def get_score(c_score, pos1, pos2, s1, s2):
+    """reference phasing.py:208-214: evidence for the states s1, s2 (allele pairs) of two sites from the table of
+    co-occurrence scores.  The device evaluates the same lookup on packed edges (csrc/fuz_phase.cu, k_ctg_phase); this
+    host form exists for callers of the module-level name."""
+    (lo_pos, lo_state), (hi_pos, hi_state) = sorted(((pos1, s1), (pos2, s2)), key=lambda site: site[0])
+    return c_score[(lo_pos, hi_pos)][(lo_state[0] + hi_state[0], lo_state[1] + hi_state[1])]
+
+
 def get_phased_blocks(self):
     """reference phasing.py:216-421."""
     vmap_fn, atable_fn, p_variant_fn = fn(self.vmap_file), fn(self.atable_file), fn(self.phased_variant_file)
@@ -320,9 +348,8 @@ def write_contig_files(res, sl, c: int, ctg_id: str, ref_seq: str, names: Sequen
                 phased_variants=formats.phased_variants_text(res, s0, s1, ref_seq),
                 phased_reads=formats.phased_reads_text(res, r0, r1, v0, v1, ctg_id, names))
     for k, p in paths.items():
-        with _open_out(p + ".tmp") as f:       # never leave a partial output file behind
+        with _open_out(p) as f:                # never leaves a partial output file behind
             f.write(text[k])
-        os.replace(p + ".tmp", p)
     return paths
 
 

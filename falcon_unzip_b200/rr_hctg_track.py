@@ -206,6 +206,11 @@ def tr_stage1(readlines: Callable[[], Iterable[str]], min_len: int, bestn: int, 
     return rtn
 
 
+def run_tr_stage1(db_fn, fn, min_len, bestn, rid_to_ctg, rid_to_phase):
+    """reference rr_hctg_track.py:25-29: (LAS file name, its heaps)."""
+    return fn, tr_stage1(lambda: read_las_lines(db_fn, fn), min_len, bestn, rid_to_ctg, rid_to_phase)
+
+
 def _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn):
     """the id tables of reference rr_hctg_track.py:70-85."""
     rid_to_ctg = get_rid_to_ctg(read_to_contig_map_fn)
@@ -310,7 +315,7 @@ def run_track_reads(exe_pool, phased_read_file_fn, read_to_contig_map_fn, rawrea
     every LAS file goes through ONE device call (the per-file heaps and their merge, :97-105,
     are replayed inside the kernel)."""
     rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
-    files = sorted(file_list)
+    files = list(file_list)          # the caller's order decides heap arrays and row order (reference :88-105)
     # the LA4Falcon text of all files is parsed on the device; the columns stay there for fuz_rr_track
     lines = la4falcon.DeviceLines([read_las_lines(db_fn, fn) for fn in files], require_id9=False)
     keep, _hn, _hl, _hq, vt_off, vt_ctg, vt_count, vt_score = _track_device(None, None, None, None, None, tab, min_len, bestn,
@@ -338,7 +343,7 @@ def run_track_reads_sharded(phased_read_file_fn, read_to_contig_map_fn, rawread_
     import torch
     import torch.distributed as dist
     rid_to_ctg, tab = _load_tables(phased_read_file_fn, read_to_contig_map_fn, rawread_ids_fn)
-    files = sorted(file_list)
+    files = list(file_list)
     mine = list(range(rank, len(files), world_size))
     backend = dist.get_backend(group)
     if backend == "nccl":                                  # text parsed on the device, only the kept lines come back
@@ -387,7 +392,7 @@ def run_track_reads_sharded(phased_read_file_fn, read_to_contig_map_fn, rawread_
 def try_run_track_reads(n_core, phased_read_file, read_to_contig_map, rawread_ids, min_len, bestn, output):
     """reference rr_hctg_track.py:142-160 (the process pool is gone: one GPU call)."""
     rawread_dir = os.path.abspath("0-rawreads")
-    file_list = glob.glob(os.path.join(rawread_dir, "m*/raw_reads.*.las"))
+    file_list = sorted(glob.glob(os.path.join(rawread_dir, "m*/raw_reads.*.las")))      # upstream: filesystem order (:148)
     db_fn = os.path.join(rawread_dir, "raw_reads.db")
     run_track_reads(None, phased_read_file, read_to_contig_map, rawread_ids, file_list, min_len, bestn, db_fn, output)
 

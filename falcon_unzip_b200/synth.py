@@ -340,3 +340,75 @@ def generate_contigs(cfg: SynthConfig, contig_ids, workers: int = 0):
     with mp.get_context("fork").Pool(workers) as pool:
         for ci, part in zip(ids, pool.imap(_gen_one, [(cfg, ci) for ci in ids])):
             yield ci, part
+
+
+# --------------------------------------------------------------------------- fast generator (bench workloads)
+_synth_lib = None
+
+
+def _fast_lib():
+    """libfuz_synth.so (csrc/fuz_synth.cpp): the same read model with its own random stream, ~100x faster than the
+    vectorised numpy generator; used for the full-size bench workloads (15 G aligned bases)."""
+    global _synth_lib
+    if _synth_lib is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfuz_synth.so")
+        if not os.path.exists(path):
+            raise RuntimeError("libfuz_synth.so is not built (make -C falcon_unzip_b200/csrc)")
+        lib = C.CDLL(path)
+        lib.fuz_synth_bounds.restype = C.c_int64
+        lib.fuz_synth_bounds.argtypes = [C.c_int64, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        lib.fuz_synth_contig.restype = C.c_int64
+        lib.fuz_synth_contig.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_int64, C.c_double, C.c_int64, C.c_int64, C.c_double,
+                                         C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                         C.c_void_p, C.POINTER(C.c_int64)]
+        _synth_lib = lib
+    return _synth_lib
+
+
+def fast_supported(cfg: SynthConfig) -> bool:
+    return (cfg.cigar_style == "=X" and cfg.frac_softclip == 0 and cfg.frac_heavy_clip == 0 and cfg.frac_short == 0
+            and cfg.frac_dup_name == 0 and cfg.n_base_rate == 0)
+
+
+def generate_contig_fast(cfg: SynthConfig, ci: int) -> SynthSet:
+    """One contig (global id ci, refID 0 in its records) from the native generator."""
+    import ctypes as C
+    lib = _fast_lib()
+    n_reads = C.c_int64(0)
+    cap = lib.fuz_synth_bounds(cfg.contig_len, cfg.coverage, cfg.mean_read_len, cfg.min_read_len, C.byref(n_reads))
+    buf = np.empty(cap, np.uint8)
+    off = np.empty(n_reads.value + 1, np.int64)
+    ref = np.empty(cfg.contig_len, np.uint8)
+    n_rec, aligned = C.c_int64(0), C.c_int64(0)
+    n = lib.fuz_synth_contig(cfg.seed, ci, 0, cfg.contig_len, cfg.coverage, cfg.mean_read_len, cfg.min_read_len, cfg.het_rate,
+                             cfg.error_rate, buf.ctypes.data, cap, off.ctypes.data, len(off) - 1, C.byref(n_rec), ref.ctypes.data,
+                             C.byref(aligned))
+    if n < 0:
+        raise RuntimeError("fuz_synth_contig failed (%d)" % n)
+    return SynthSet(dataclasses.replace(cfg, n_contigs=1, first_contig=ci), [(contig_name(ci), cfg.contig_len)],
+                    [ref.tobytes().decode("ascii")], [np.zeros(0, np.int64)], buf[:n], off[:n_rec.value + 1],
+                    np.zeros(n_rec.value, np.int32))
+
+
+def generate_contigs_fast(cfg: SynthConfig, contig_ids, threads: int = 0):
+    """Yield (contig id, SynthSet) in the given order; the contigs are generated on a pool of threads (the native call
+    releases the GIL).  The content depends on (seed, id) only."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    ids = [int(i) for i in contig_ids]
+    threads = threads or min(len(ids), os.cpu_count() or 1)
+    if threads <= 1 or len(ids) <= 1:
+        for ci in ids:
+            yield ci, generate_contig_fast(cfg, ci)
+        return
+    with ThreadPoolExecutor(threads) as ex:
+        window = 2 * threads                                   # bounded look-ahead: a contig is ~200 MB
+        futs = {}
+        nxt = 0
+        for k, ci in enumerate(ids):
+            while nxt < len(ids) and nxt < k + window:
+                futs[nxt] = ex.submit(generate_contig_fast, cfg, ids[nxt])
+                nxt += 1
+            yield ci, futs.pop(k).result()

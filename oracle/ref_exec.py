@@ -6,7 +6,7 @@ be imported.  This module reads the source text from ``$FALCON_UNZIP_REF`` (defa
 /root/reference) AT RUN TIME, applies the enumerated patch list of SURVEY.md Appendix C,
 stubs the missing modules and ``exec``s the result.  Nothing of the reference is copied
 into this repository.  It exists only in the build container (the GPU box has no
-/root/reference): it validates oracle/restated.py + oracle/phasing_oracle.c and
+/root/reference): it validates oracle/phasing_oracle.c, oracle/rr_oracle.py, oracle/ovlp_oracle.py, oracle/select_oracle.py and
 generates the committed fixtures under tests/golden/ (scripts/make_golden.py).
 
 ``available()`` is False when the reference tree is missing; callers skip.

@@ -11,12 +11,6 @@ from oracle import select_oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
-    from falcon_unzip_b200 import engine
-    return engine.get_engine(0)
-
-
 @pytest.mark.parametrize("seed", [7, 8])
 def test_select_reads_from_bam_matches_oracle(eng, tmp_path, seed, capsys):
     from falcon_unzip_b200 import bam, select_reads_from_bam as srb
