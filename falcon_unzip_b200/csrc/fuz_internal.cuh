@@ -46,6 +46,7 @@ struct fuz_ctx {
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
     int project_ctas = 148 * 6;        // CTAs of k_project (persistent warps, records from a global cursor)
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
+    int sweep_passes = 64;             // parallel fixed-point passes of the pass-2 sweep before the sequential walk (0 = none)
     int64_t max_pairs_per_site = 96;
     uint8_t *reads_buf = nullptr; size_t reads_cap = 0;           // scratch of the read stage (runs beside the block stage)
     uint8_t *scan_state = nullptr; size_t scan_state_cap = 0;   // tile states of the multi-CTA scan

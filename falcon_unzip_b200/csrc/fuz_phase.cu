@@ -263,6 +263,7 @@ struct BlockScratch {
     uint8_t *g_slow;    // [sites] their per-site flags (bit 0: generic sweep step, bit 1: site is in positions)
     long long *dbg; // optional: per-contig phase timestamps (16 per contig), diagnostics only
     int staging;    // ctx option "phase_staging"
+    int sweep_passes;   // ctx option "sweep_passes": parallel fixed-point passes before the sequential sweep (0 = none)
 };
 
 #define FUZ_PHASE_THREADS 1024
@@ -550,7 +551,37 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     // live in a warp-uniform bit window (`recent`), the adjacency of the next site is
     // prefetched, the vote is one REDUX, new states are written back one 32-site word at a time.
     if (B.dbg && tid == 0) B.dbg[c * 16 + 3] = clock64();
-    if (warp == 0) {
+    // The sweep is a triangular system: the new state of a site is a function of the FINAL states of its left partners and
+    // of its own initial state (ties keep it), new = sum_q (state(q) ? -d : d) < 0 ? 1 : > 0 ? 0 : initial.  Its unique
+    // solution is also the fixed point of evaluating all sites in parallel, over and over, in place: a pass in which no
+    // bit changes has reached it.  Few sites flip in practice, so a handful of passes of the whole CTA replaces the
+    // site-by-site walk of one warp; contigs whose flips cascade for more than FUZ_SWEEP_PASSES passes restart from the
+    // initial states and take the sequential walk.
+    bool swept = false;
+    if (B.sweep_passes > 0) {
+        uint32_t *sinit = const_cast<uint32_t *>(fp);                 // the forest pointers are not needed any more
+        for (int w = tid; w < nbw; w += nt) sinit[w] = sbits[w];
+        __syncthreads();
+        for (int pass = 0; pass < B.sweep_passes && !swept; pass++) {
+            int changed = 0;
+            for (int i = tid; i < n; i += nt) {
+                int s0 = 0;
+                for (int k = loff(i); k < loff(i + 1); k++) {
+                    const int q = lq(k), d = ld(k);
+                    s0 += ((sbits[q >> 5] >> (q & 31)) & 1u) ? -d : d;
+                }
+                const uint32_t cur = (sbits[i >> 5] >> (i & 31)) & 1u;
+                const uint32_t nw = s0 < 0 ? 1u : s0 > 0 ? 0u : (sinit[i >> 5] >> (i & 31)) & 1u;
+                if (nw != cur) { atomicXor(&sbits[i >> 5], 1u << (i & 31)); changed = 1; }
+            }
+            swept = !__syncthreads_or(changed);
+        }
+        if (!swept) {
+            for (int w = tid; w < nbw; w += nt) sbits[w] = sinit[w];
+            __syncthreads();
+        }
+    }
+    if (!swept && warp == 0) {
         if (staged) sweep_sites_lean(n, lane, sbits, s_loff, s_lq, s_ld, 0, s_pk, s_slow);
         else if (sweep_staged) sweep_sites_lean(n, lane, sbits, s_loff, B.lq + e0, B.ld + e0, cs0, s_pk, s_slow);
         else        // global tier: the same loop over the global arrays (absolute CSR indices); its register pipeline
@@ -559,38 +590,34 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     }
     __syncthreads();
     if (B.dbg && tid == 0) B.dbg[c * 16 + 4] = clock64();
-    // ---- pass 3: scores and extents, one warp per site (positions = 1-based file positions)
-    for (int i = warp; i < n; i += nwarps) {
+    // ---- pass 3: scores and extents, one thread per site (positions = 1-based file positions)
+    for (int i = tid; i < n; i += nt) {
         const int x = cs0 + i;
         const bool in_pos = sweep_staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255;
         const int px = pos_of(i);
         int lscore = 0, rscore = 0, lext = px, rext = px;
         if (in_pos) {
             const uint32_t sx = (sbits[i >> 5] >> (i & 31)) & 1u;
-            for (int k = loff(i) + lane; k < loff(i + 1); k += 32) {
-                int q = lq(k), d = ld(k);
-                uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
-                int dd = sq == sx ? d : -d;
+            for (int k = loff(i); k < loff(i + 1); k++) {
+                const int q = lq(k), d = ld(k);
+                const uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
+                const int dd = sq == sx ? d : -d;
                 lscore += dd;
                 if (dd > 0) lext = min(lext, pos_of(q));
             }
-            for (int k = roff(i) + lane; k < roff(i + 1); k += 32) {
-                int d = rd(k);
+            for (int k = roff(i); k < roff(i + 1); k++) {
+                const int d = rd(k);
                 if (d == 0) continue;
-                int q = rq(k);
-                uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
-                int dd = sq == sx ? d : -d;
+                const int q = rq(k);
+                const uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
+                const int dd = sq == sx ? d : -d;
                 rscore += dd;
                 if (dd > 0) rext = max(rext, pos_of(q));
             }
-            lscore = __reduce_add_sync(0xffffffffu, lscore); rscore = __reduce_add_sync(0xffffffffu, rscore);
-            lext = __reduce_min_sync(0xffffffffu, lext); rext = __reduce_max_sync(0xffffffffu, rext);
-            if (lane == 0) O.d_ph_state[x] = (uint8_t)sx;
+            O.d_ph_state[x] = (uint8_t)sx;
         }
-        if (lane == 0) {
-            O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
-            if (staged) { s_sc[4 * i] = lscore; s_sc[4 * i + 1] = rscore; s_sc[4 * i + 2] = lext; s_sc[4 * i + 3] = rext; }
-        }
+        O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
+        if (staged) { s_sc[4 * i] = lscore; s_sc[4 * i + 1] = rscore; s_sc[4 * i + 2] = lext; s_sc[4 * i + 3] = rext; }
     }
     __syncthreads();
     // ---- pass 4: chain sites into blocks by the running maximum of right extents (never reset)
@@ -808,6 +835,7 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_v
     B.bidx = fuz_at<int32_t>(ctx, o_bi); B.bsize = fuz_at<int32_t>(ctx, o_bs); B.bnew = fuz_at<int32_t>(ctx, o_bn);
     B.dbg = ctx->profile ? fuz_at<long long>(ctx, o_dbg) : nullptr;
     B.staging = ctx->phase_staging;
+    B.sweep_passes = ctx->sweep_passes;
     if (!ctx->phase_attr_set) {
         FUZ_CUDA(ctx, cudaFuncSetAttribute(k_ctg_phase, cudaFuncAttributeMaxDynamicSharedMemorySize, FUZ_PHASE_SMEM));
         ctx->phase_attr_set = true;

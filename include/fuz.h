@@ -158,6 +158,8 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *                           multi-GPU run, the merge then runs on the gathered kept lines), 0 = default,
  *          "phase_staging" 0 = stage as much of a contig as fits in shared memory (default),
  *                          1 = at most the sweep tier, 2 = global memory only (both for tests),
+ *          "sweep_passes" passes of the parallel fixed-point form of the pass-2 sweep (phasing.py:311-344) before
+ *                         the sequential walk takes over (default 64; 0 = sequential only; same result either way),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */
 int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value);
 int fuz_sync(fuz_ctx *ctx);

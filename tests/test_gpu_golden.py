@@ -137,6 +137,28 @@ def test_phase_staging_tiers_vs_oracle(eng, staging, tmp_path):
         assert open(want[k]).read() == open(got[name][k]).read(), k
 
 
+@pytest.mark.parametrize("passes,staging", [(0, 0), (1, 0), (2, 2), (64, 2)])
+def test_sweep_fixed_point_and_sequential_walk_agree(eng, passes, staging, tmp_path):
+    """The pass-2 sweep (phasing.py:311-344) runs as parallel fixed-point passes with the sequential walk as the fallback
+    (option sweep_passes): no pass at all, one or two passes (the fallback takes over after them unless they already
+    converged) and the default give the oracle's files, from shared and from global memory."""
+    from conftest import synth_set
+    from falcon_unzip_b200 import phasing
+    from oracle import c_oracle
+    sset = synth_set("c1", contig_len=300_000)
+    name = sset.refs[0][0]
+    want = c_oracle.run_phasing_stages(sset.contig_records(0), name, sset.ref_seqs[0], str(tmp_path / "oracle"))
+    eng.set_option("sweep_passes", passes)
+    eng.set_option("phase_staging", staging)
+    try:
+        _res, got = phasing.phase_contigs(sset.records, [name], sset.ref_seqs, str(tmp_path / "gpu"))
+    finally:
+        eng.set_option("sweep_passes", 64)
+        eng.set_option("phase_staging", 0)
+    for k in FILES:
+        assert open(want[k]).read() == open(got[name][k]).read(), k
+
+
 def test_c1_full_size_contig_vs_oracle(eng, tmp_path):
     """BASELINE.json config 1 at full size: 1 Mb contig, 0.1 % het, 30x 10 kb reads, 1 % error."""
     from falcon_unzip_b200 import phasing, synth
