@@ -146,7 +146,10 @@ __global__ void k_rr_replay(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, co
     }
 }
 
-// R3: contigs voted by the kept a-reads of a target, in insertion order (:113-123).
+// R3: contigs voted by the kept a-reads of a target, in insertion order (:113-123).  Up to FUZ_RR_MAXC distinct contigs
+// are accumulated in a per-thread table; a target that votes for more (a repeat read among primaries and haplotigs)
+// takes the unbounded path: distinct contigs are counted by first occurrence in the vote sequence and accumulated straight
+// in the output rows, which the count pass reserved.
 #define FUZ_RR_MAXC 64
 __global__ void k_rr_vote(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, int fill, fuz_status *st) {
     fuz_pdl_enter();
@@ -156,20 +159,49 @@ __global__ void k_rr_vote(fuz_rr_input in, fuz_rr_outputs out, RRScratch R, int 
         int ctg[FUZ_RR_MAXC], cnt[FUZ_RR_MAXC];
         long long score[FUZ_RR_MAXC];
         int nc = 0;
+        bool overflow = false;
         const int *gl = out.d_hp_len + (int64_t)t * in.bestn, *gq = out.d_hp_q + (int64_t)t * in.bestn;
-        for (int j = 0; j < ng; j++) {
+        for (int j = 0; j < ng && !overflow; j++) {
             const int rid = gq[j], s = gl[j];
             for (int e = in.d_rc_off[rid]; e < in.d_rc_off[rid + 1]; e++) {      // CPython-2 set order (host)
                 const int c = in.d_rc_ctg[e];
                 int k = 0;
                 while (k < nc && ctg[k] != c) k++;
                 if (k == nc) {
-                    if (nc == FUZ_RR_MAXC) { fuz_raise(st, FUZ_E_CAPACITY, 7); break; }
+                    if (nc == FUZ_RR_MAXC) { overflow = true; break; }
                     ctg[nc] = c; cnt[nc] = 0; score[nc] = 0; nc++;
                 }
                 score[k] += -(long long)s;                                        // ctg_score[ctg][0] += -s (:122)
                 cnt[k] += 1;
             }
+        }
+        if (overflow) {
+            const int64_t o = fill ? out.d_vt_off[t] : 0;
+            nc = 0;
+            for (int j = 0; j < ng; j++) {
+                const int rid = gq[j], s = gl[j];
+                for (int e = in.d_rc_off[rid]; e < in.d_rc_off[rid + 1]; e++) {
+                    const int c = in.d_rc_ctg[e];
+                    int k = -1;
+                    if (fill) {                                                   // rows written so far, insertion order
+                        for (int x = 0; x < nc && k < 0; x++)
+                            if (o + x < out.cap_votes && out.d_vt_ctg[o + x] == c) k = x;
+                    } else {                                                      // seen before in the vote sequence?
+                        for (int j2 = 0; j2 <= j && k < 0; j2++) {
+                            const int r2 = gq[j2], e_end = j2 < j ? in.d_rc_off[r2 + 1] : e;
+                            for (int e2 = in.d_rc_off[r2]; e2 < e_end; e2++)
+                                if (in.d_rc_ctg[e2] == c) { k = 0; break; }
+                        }
+                    }
+                    if (k < 0) {
+                        k = nc++;
+                        if (fill && o + k < out.cap_votes) { out.d_vt_ctg[o + k] = c; out.d_vt_count[o + k] = 0; out.d_vt_score[o + k] = 0; }
+                    }
+                    if (fill && o + k < out.cap_votes) { out.d_vt_count[o + k] += 1; out.d_vt_score[o + k] += -(long long)s; }
+                }
+            }
+            if (!fill) R.vt_cnt[t] = nc;
+            continue;
         }
         if (!fill) { R.vt_cnt[t] = nc; continue; }
         const int64_t o = out.d_vt_off[t];

@@ -72,13 +72,14 @@ def tr_stage1(lines: Iterable[str], min_len: int, bestn: int, rid_to_ctg, rid_to
 
 def run_track_reads(las_lines: Dict[str, Sequence[str]], phased_read_lines: Iterable[str],
                     read_to_contig_map_lines: Iterable[str], rawread_ids_text: str, min_len: int = 2500,
-                    bestn: int = 40) -> str:
+                    bestn: int = 40, file_order: Sequence[str] = None) -> str:
     """-> text of rawread_to_contigs (:67-138).  las_lines: LAS file name -> LA4Falcon -m
-    lines; files are processed in sorted name order (upstream: glob order, B.4)."""
+    lines; files are processed in the order of file_order (the reference walks file_list as given: imap keeps the
+    order of its inputs, :88-98), default: sorted names (upstream: glob order, B.4)."""
     rid_to_ctg = get_rid_to_ctg(read_to_contig_map_lines)
     rid_to_phase = phase_table(phased_read_lines, rawread_ids_text)
     bread_to_areads: Dict[str, list] = {}
-    for fn in sorted(las_lines):
+    for fn in (file_order if file_order is not None else sorted(las_lines)):
         res = tr_stage1(las_lines[fn], min_len, bestn, rid_to_ctg, rid_to_phase)
         for k in py27_str_dict_order(res):                          # :99
             h = bread_to_areads.setdefault(k, [])

@@ -27,10 +27,12 @@ def test_run_track_reads_bytes_match_oracle(eng, seed, bestn, n_files, n_reads, 
     from oracle import rr_oracle
     rr = synth_rr.generate_rr(n_reads=n_reads, n_ctg=3, ctg_len=100_000, n_files=n_files, seed=seed)
     p = _write(rr, str(tmp_path))
-    want = rr_oracle.run_track_reads(rr.las_lines, rr.phased_reads, rr.read_to_contig_map, rr.rawread_ids, 2500, bestn)
+    # the caller's file order is kept (the reference walks file_list as given, rr_hctg_track.py:88-98): reversed names here
+    order = list(reversed(sorted(rr.las_lines)))
+    want = rr_oracle.run_track_reads(rr.las_lines, rr.phased_reads, rr.read_to_contig_map, rr.rawread_ids, 2500, bestn,
+                                     file_order=order)
     monkeypatch.setattr(rr_hctg_track, "read_las_lines", lambda db_fn, fn: iter(rr.las_lines[fn]))
-    rr_hctg_track.run_track_reads(None, p["phased"], p["r2c"], p["ids"], list(reversed(sorted(rr.las_lines))), 2500, bestn,
-                                  "raw_reads.db", p["out"])
+    rr_hctg_track.run_track_reads(None, p["phased"], p["r2c"], p["ids"], order, 2500, bestn, "raw_reads.db", p["out"])
     got = open(p["out"]).read()
     assert len(want.splitlines()) > 200
     assert want == got
@@ -78,3 +80,29 @@ def test_cli_and_known_answers(eng, tmp_path, monkeypatch):
     got = open(p["out"]).read()
     assert want == got
     assert "000000000 000000F_001 2 0 -14000 0\n" in got and "000000000 000000F 1 1 -7000 0\n" in got
+
+
+def test_target_voting_for_more_contigs_than_the_fast_table(eng, tmp_path, monkeypatch):
+    """A repeat read whose 40 kept a-reads map to 3 contigs each (120 distinct contigs): the per-thread vote table of
+    k_rr_vote holds 64; the unbounded path must give the reference's rows (it has no such limit, rr_hctg_track.py:113-138)."""
+    from falcon_unzip_b200 import rr_hctg_track
+    from oracle import rr_oracle
+    n = 42
+    names = ["r%d" % i for i in range(n)]
+    r2c, pid = [], 0
+    for q in range(1, 41):
+        for k in range(3):
+            r2c.append("%09d %09d %s %06dF" % (pid, q, names[q], 3 * q + k))
+            pid += 1
+    r2c.append("%09d %09d %s %06dF" % (pid, 0, names[0], 5))
+    las = {"0-rawreads/m1/raw_reads.1.las": ["%09d %09d %d 99.0 0 0 %d 9000 0 100 %d 8000 overlap" % (q, 0, -(3000 + 10 * q), 3000, 3100)
+                                             for q in range(1, 41)] +
+                                            ["%09d %09d %d 99.0 0 0 %d 9000 0 100 %d 8000 overlap" % (q, 41, -4000, 3000, 3100) for q in (3, 4)]}
+    rr = type("RR", (), dict(phased_reads=[], read_to_contig_map=r2c, rawread_ids="\n".join(names) + "\n"))()
+    p = _write(rr, str(tmp_path))
+    want = rr_oracle.run_track_reads(las, [], r2c, rr.rawread_ids, 2500, 40)
+    monkeypatch.setattr(rr_hctg_track, "read_las_lines", lambda db_fn, fn: iter(las[fn]))
+    rr_hctg_track.run_track_reads(None, p["phased"], p["r2c"], p["ids"], list(las), 2500, 40, "raw_reads.db", p["out"])
+    got = open(p["out"]).read()
+    assert len([l for l in want.splitlines() if l.startswith("000000000 ")]) == 120
+    assert got == want
