@@ -420,6 +420,34 @@ def bam_ingest_leg(eng, pb, aligned, torch, reps: int = 3):
                    "(pinned BAM file image in, host row arrays and fixed-width QNAME rows out; best of %d)" % reps}
 
 
+def disk_to_disk_leg(pb, samples, aligned, device: int, reps: int = 3):
+    """SURVEY.md 8(d) "also report": the user-visible call, files in -> files out.  A coordinate-sorted BAM (BGZF, zlib level 1)
+    and the FASTA on disk -> phasing.phase_bam -> the six files of every contig on disk (device BGZF inflate + record index
+    + four stages + host text formatting + file writes), best of `reps`."""
+    from falcon_unzip_b200 import bam, phasing
+    refs = list(zip(pb.ctg_names, [int(x) for x in pb.ctg_len]))
+    with tempfile.TemporaryDirectory(prefix="fuz_d2d_") as d:
+        fn, fa = os.path.join(d, "in.bam"), os.path.join(d, "ref.fa")
+        rec = pb.records.copy()                                 # refID of a record = contig index inside the file
+        refid = np.repeat(np.arange(pb.n_ctg, dtype="<i4"), np.diff(pb.ctg_rec_off))
+        rec[(pb.rec_off[:-1, None] + 4 + np.arange(4)[None, :])] = refid.view(np.uint8).reshape(-1, 4)
+        bam.write_bam(fn, refs, rec.tobytes(), level=1)
+        seq_of = {s["name"]: s["ref_seq"] for s in samples.values()}
+        with open(fa, "w") as f:
+            for name, _l in refs:
+                f.write(">%s\n%s\n" % (name, seq_of[name]))
+        best, n_files = None, 0
+        for k in range(reps):
+            t0 = time.perf_counter()
+            res, files = phasing.phase_bam(fn, fa, os.path.join(d, "out%d" % k), device=device)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            n_files = sum(len(v) for v in files.values())
+            assert res.aligned_bases == aligned, "disk path and record path disagree"
+        return {"value": aligned / best, "unit": UNIT, "ms": 1e3 * best, "bam_bytes": os.path.getsize(fn), "files_written": n_files,
+                "api": "phasing.phase_bam(bam, fasta, base_dir): BGZF BAM + FASTA on disk -> six files per contig on disk (best of %d)" % reps}
+
+
 # --------------------------------------------------------------------------- GPU arm
 def device_leg(eng, engine, torch, stream, dev, batches, steps, warmup, barrier, flush):
     """Upload the batches, size the outputs, run warmup + timed steps.  -> dict of measurements + device objects."""
@@ -473,12 +501,12 @@ def run_b200(args):
     t_gen0 = time.perf_counter()
     # everything that forks happens before CUDA is initialised
     batches, samples = build_workload(cfg, ids, keep, args.max_batch_mb << 20, pin=False, workers=workers)
-    second = None
+    second, second_samples = None, {}
     if world == 1 and not args.no_secondary and args.config != "c2" and not args.contigs and not args.contig_len:
         from falcon_unzip_b200 import synth
         c2 = synth.CONFIGS["c2"]
-        second, _s = build_workload(c2, list(range(c2.n_contigs)), set(), 1 << 62, pin=False,
-                                    workers=min(c2.n_contigs, os.cpu_count() or 1))
+        second, second_samples = build_workload(c2, list(range(c2.n_contigs)), set(range(c2.n_contigs)), 1 << 62, pin=False,
+                                                workers=min(c2.n_contigs, os.cpu_count() or 1))
     t_gen = time.perf_counter() - t_gen0
     alg = [algorithmic_bytes(pb) for pb in batches]
 
@@ -578,6 +606,10 @@ def run_b200(args):
                             "unit": UNIT, "ms_per_step": m2["ms_per_step"], "gpu_launches_per_step": m2["launches"] // max(args.steps, 10),
                             "roofline_frac": a2 / (m2["kern_ms_per_step"] / 1e3) / 1e9 / peak, "kernel_ms": m2["kern_ms_per_step"],
                             "rows": m2["rows"]}}
+        try:
+            secondary["c2"]["disk_to_disk"] = disk_to_disk_leg(second[0], second_samples, m2["aligned"], local_rank)
+        except Exception as e:                               # noqa: BLE001 -- reported, never fatal for the scored line
+            secondary["c2"]["disk_to_disk"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         if args.bam:
             bam_leg = bam_ingest_leg(eng, second[0], m2["aligned"], torch)
     elif args.bam and world == 1 and len(batches) == 1:

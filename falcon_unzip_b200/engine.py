@@ -657,8 +657,37 @@ class Engine:
     def phase_bam(self, image, caps: Optional[Dict[str, int]] = None, verify_crc: bool = True):
         """BAM file image (or a list of images, see ingest_bams) -> (PhaseResult, BamBatchInfo): the BAM is decoded
         on the device, then the four stages run for every reference in one device call (q_ids assigned on the device)."""
-        torch = self._torch
         db = self.ingest_bams(image, verify_crc) if isinstance(image, (list, tuple)) else self.ingest_bam(image, verify_crc)
+        return self.phase_ingested(db, caps)
+
+    def select_contigs(self, db: DeviceBam, contigs: Sequence[int]) -> DeviceBam:
+        """The records of the given references of a device BAM, back to back in a new device buffer (fuz_gather_records), as a
+        DeviceBam of its own: what a rank of a multi-GPU run phases when the contigs of one BAM are dealt to the ranks."""
+        torch = self._torch
+        dev = self.device
+        cro = db.ctg_rec_off.cpu().numpy().astype(np.int64)
+        contigs = [int(c) for c in contigs]
+        counts = np.asarray([cro[c + 1] - cro[c] for c in contigs], np.int64)
+        m = int(counts.sum())
+        sel = np.concatenate([np.arange(cro[c], cro[c + 1], dtype=np.int64) for c in contigs]) if m else np.zeros(0, np.int64)
+        sel_d = torch.from_numpy(sel).to(dev)
+        sizes = db.rec_off[sel_d + 1] - db.rec_off[sel_d] if m else torch.zeros(0, dtype=torch.int64, device=dev)
+        dst_off = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        if m:
+            torch.cumsum(sizes, 0, out=dst_off[1:])
+        total = int(dst_off[-1].item())
+        dst = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        if m:
+            _lib.check(self.ctx, lib().fuz_gather_records(self.ctx, db.rec_ptr, db.rec_off.data_ptr(), db.n_rec, db.rec_bytes,
+                                                          sel_d.data_ptr(), dst_off.data_ptr(), m, dst.data_ptr(), total))
+            self.sync()
+        sub_cro = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(dev)
+        return DeviceBam([db.refs[c] for c in contigs], dst, dst.data_ptr(), total, dst_off, sub_cro, m, m, 0)
+
+    def phase_ingested(self, db: DeviceBam, caps: Optional[Dict[str, int]] = None):
+        """The four stages for every reference of a device BAM (q_ids assigned on the device) -> (PhaseResult, BamBatchInfo)."""
+        torch = self._torch
         n_ctg = len(db.refs)
         if n_ctg < 1:
             raise FuzError(_lib.FUZ_E_ARG, "the BAM header lists no reference sequence")

@@ -398,11 +398,16 @@ def phase_bam(bam_fn, fasta_fn: str, base_dir: str, device: int = 0, verify_crc:
     ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fasta_fn)}
     eng = engine.get_engine(device)
     res, info = eng.phase_bam(image, verify_crc=verify_crc)
+    return res, write_batch_files(res, info, [ref_seqs.get(n, "") for n in info.ctg_names], base_dir)
+
+
+def write_batch_files(res, info, ref_seqs: Sequence[str], base_dir: str):
+    """The six files of every contig of a device batch (engine.BamBatchInfo: contig names and QNAME rows) -> {contig: paths}."""
     sl = formats.contig_slices(res, info.n_ctg)
     out = {}
     for c, name in enumerate(info.ctg_names):
-        out[name] = write_contig_files(res, sl, c, name, ref_seqs.get(name, ""), info.qnames(c), base_dir)
-    return res, out
+        out[name] = write_contig_files(res, sl, c, name, ref_seqs[c], info.qnames(c), base_dir)
+    return out
 
 
 def parse_args(argv):

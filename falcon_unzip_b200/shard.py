@@ -62,27 +62,46 @@ def phase_bam_sharded(bam_fn: str, fasta_fn: str, base_dir: str, rank: int = 0, 
     writes the per-contig files under base_dir.  With torch.distributed initialised the list of
     finished contigs is gathered on every rank (all_gather_object: host bookkeeping only)."""
     from . import bam, phasing
-    _text, refs, recs = bam.read_bam(bam_fn)
     ref_seqs = {name.split()[0]: seq.upper() for name, seq in bam.read_fasta(fasta_fn)}
-    records = np.frombuffer(recs, dtype=np.uint8)
     from . import engine
-    rec_off = engine.index_records(records)
-    bounds, weights = contig_record_ranges(records, rec_off, len(refs))
-    mine = assign_contigs(weights, world_size)[rank]
-    done = []
-    if mine:
-        sub_names = [refs[c][0] for c in mine]
-        parts, sub_off = [], [0]
-        for c in mine:
-            lo, hi = int(rec_off[bounds[c]]), int(rec_off[bounds[c + 1]])
-            parts.append(records[lo:hi])
-            sub_off.append(sub_off[-1] + (bounds[c + 1] - bounds[c]))
-        sub = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
-        seqs = [ref_seqs.get(n, "") for n in sub_names]
-        fn = phase_fn or (lambda rec, names, sq, bd: phasing.phase_contigs(
-            rec, names, sq, bd, device=device if device is not None else 0, ctg_rec_off=np.asarray(sub_off, np.int32)))
-        fn(sub, sub_names, seqs, base_dir)
-        done = sub_names
+    if phase_fn is None and bam.is_bgzf(bam_fn):
+        # product path: no rank inflates the file on the host.  The BGZF image goes to the rank's GPU as it is, is
+        # decoded and indexed there (milliseconds per GB), the contigs are dealt by their record bytes (LPT) and the
+        # rank's contigs are compacted into a batch of their own on the device (fuz_gather_records) and phased.
+        eng = engine.get_engine(device if device is not None else 0)
+        db = eng.ingest_bam(np.fromfile(bam_fn, dtype=np.uint8))
+        refs = db.refs
+        cro = db.ctg_rec_off.cpu().numpy().astype(np.int64)
+        off_at = db.rec_off[db.ctg_rec_off.long()].cpu().numpy()
+        weights = [float(off_at[c + 1] - off_at[c]) for c in range(len(refs))]
+        mine = assign_contigs(weights, world_size)[rank]
+        done = []
+        if mine:
+            sub = eng.select_contigs(db, mine)
+            del db
+            res, info = eng.phase_ingested(sub)
+            phasing.write_batch_files(res, info, [ref_seqs.get(n, "") for n in info.ctg_names], base_dir)
+            done = list(info.ctg_names)
+    else:
+        _text, refs, recs = bam.read_bam(bam_fn)
+        records = np.frombuffer(recs, dtype=np.uint8)
+        rec_off = engine.index_records(records)
+        bounds, weights = contig_record_ranges(records, rec_off, len(refs))
+        mine = assign_contigs(weights, world_size)[rank]
+        done = []
+        if mine:
+            sub_names = [refs[c][0] for c in mine]
+            parts, sub_off = [], [0]
+            for c in mine:
+                lo, hi = int(rec_off[bounds[c]]), int(rec_off[bounds[c + 1]])
+                parts.append(records[lo:hi])
+                sub_off.append(sub_off[-1] + (bounds[c + 1] - bounds[c]))
+            sub = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+            seqs = [ref_seqs.get(n, "") for n in sub_names]
+            fn = phase_fn or (lambda rec, names, sq, bd: phasing.phase_contigs(
+                rec, names, sq, bd, device=device if device is not None else 0, ctg_rec_off=np.asarray(sub_off, np.int32)))
+            fn(sub, sub_names, seqs, base_dir)
+            done = sub_names
     gathered = [done]
     try:
         import torch.distributed as dist

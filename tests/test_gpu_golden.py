@@ -206,3 +206,30 @@ def test_many_small_contigs_c3_shape(eng, tmp_path):
         want = c_oracle.run_phasing_stages(sset.contig_records(c), names[c], sset.ref_seqs[c], str(tmp_path / "oracle"))
         for k in FILES:
             assert open(want[k]).read() == open(got[names[c]][k]).read(), (names[c], k)
+
+
+def test_c5_shape_contigs_vs_oracle_and_batch_splitting(eng, tmp_path):
+    """BASELINE.json config 5 shape (60x, 15 kb reads, 1 % error, 0.1 % het) from the generator bench.py uses
+    (libfuz_synth.so): three contigs in one batch equal the oracle's files, and the same contigs forced into one batch
+    per contig (engine.plan_batches with a small byte limit) give the same files."""
+    import dataclasses
+    import numpy as np
+    from falcon_unzip_b200 import engine, phasing, synth
+    from oracle import c_oracle
+    cfg = dataclasses.replace(synth.CONFIGS["c5"], contig_len=400_000)
+    parts = [synth.generate_contig_fast(cfg, ci) for ci in (0, 1, 2)]
+    names = [p.refs[0][0] for p in parts]
+    seqs = [p.ref_seqs[0] for p in parts]
+    pb = engine.build_batch([(p.records, p.rec_off) for p in parts], names, [cfg.contig_len] * 3)
+    cro = np.asarray(pb.ctg_rec_off, np.int32)
+    _res, got = phasing.phase_contigs(pb.records, names, seqs, str(tmp_path / "gpu"), ctg_rec_off=cro)
+    res_split, got_split = phasing.phase_contigs(pb.records, names, seqs, str(tmp_path / "split"), ctg_rec_off=cro,
+                                                 max_batch_bytes=len(parts[0].records) + 1000)
+    assert isinstance(res_split, list) and len(res_split) == 3
+    for c, name in enumerate(names):
+        want = c_oracle.run_phasing_stages(parts[c].records.tobytes(), name, seqs[c], str(tmp_path / "oracle"))
+        for k in FILES:
+            ref = open(want[k]).read()
+            assert ref == open(got[name][k]).read(), (name, k)
+            assert ref == open(got_split[name][k]).read(), (name, k, "split")
+    assert len(open(got[names[0]]["phased_reads"]).read().splitlines()) > 1000
