@@ -131,6 +131,8 @@ SYMBOLS = [
                                    C.c_int64, C.c_void_p, C.c_int64]),
     ("fuz_bam_index_records", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         _i64p, _i64p]),
+    ("fuz_bam_index_window", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                        _i64p, _i64p, _i64p]),
     ("fuz_bam_index_files", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, _i64p, _i64p, _i64p]),
     ("fuz_gather_records", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,

@@ -261,7 +261,7 @@ __device__ __forceinline__ bool rec_header_ok(const uint8_t *rec, int64_t o, int
 struct BamIndexScratch {
     int64_t *first, *land, *entry;   // per region: first header-like offset, where its chain leaves the region
     int32_t *cnt, *base;             // records starting in the region (guess), index of the region's first record
-    int64_t *n_rec;                  // [0] record count, [1] needed capacity
+    int64_t *n_rec;                  // [0] record count, [1] needed capacity, [2] end of the indexed records (tail start)
 };
 
 __global__ void __launch_bounds__(256) k_bam_anchor(const uint8_t *__restrict__ rec, int64_t n, int n_ref, int64_t n_reg,
@@ -298,16 +298,23 @@ __global__ void __launch_bounds__(256) k_bam_anchor(const uint8_t *__restrict__ 
 // One warp threads the regions together, 32 at a time: if every region of a group either is
 // entered exactly where it guessed or holds no record start at all, the group is accepted with
 // two warp scans; otherwise lane 0 walks it region by region.
+// allow_tail (windows of a long stream, fuz_bam_index_window): a record cut by the end of the buffer ends the index there
+// instead of breaking the chain; S.n_rec[2] says where it starts.
 __global__ void __launch_bounds__(32) k_bam_resolve(const uint8_t *__restrict__ rec, int64_t n, int64_t n_reg, int64_t cap_rec,
-                                                     BamIndexScratch S, fuz_status *st) {
+                                                     BamIndexScratch S, int allow_tail, fuz_status *st) {
     fuz_pdl_enter();
     if (st->error) return;                         // e.g. a corrupt BGZF block: nothing to index
     const int lane = threadIdx.x;
     int64_t E = 0, N = 0;                          // where the true chain enters the next group; records so far
     bool bad = false;
+    int64_t tail = -1;                             // start of a record cut by the end of the buffer (allow_tail)
     for (int64_t k0 = 0; k0 < n_reg && !bad; k0 += 32) {
         const int64_t k = k0 + lane;
         const bool in = k < n_reg;
+        if (tail >= 0) {                           // everything behind the tail belongs to the cut record
+            if (in) { S.entry[k] = -1; S.base[k] = (int32_t)N; }
+            continue;
+        }
         const int64_t first = in ? S.first[k] : -1, land = in ? S.land[k] : -1;
         const int cnt = in ? S.cnt[k] : 0;
         const int64_t end = min((k + 1) * FUZ_BAM_REGION, n);
@@ -335,22 +342,28 @@ __global__ void __launch_bounds__(32) k_bam_resolve(const uint8_t *__restrict__ 
             const int m = (int)min((int64_t)32, n_reg - k0);
             for (int i = 0; i < m && !bad; i++) {
                 const int64_t kk = k0 + i, e2 = min((kk + 1) * FUZ_BAM_REGION, n);
-                if (E >= e2) { S.entry[kk] = -1; S.base[kk] = (int32_t)N; continue; }
+                if (E >= e2 || tail >= 0) { S.entry[kk] = -1; S.base[kk] = (int32_t)N; continue; }
                 S.entry[kk] = E; S.base[kk] = (int32_t)N;
                 if (S.first[kk] == E && S.land[kk] >= 0) { N += S.cnt[kk]; E = S.land[kk]; continue; }
                 while (E < e2) {                   // the region guessed wrong (or its chain broke): walk it here
                     int64_t nx;
-                    if (!rec_chain_ok(rec, E, n, &nx)) { bad = true; break; }
+                    if (!rec_chain_ok(rec, E, n, &nx)) {
+                        // the record runs past the end of the buffer (or its length field does): the tail of a window
+                        if (allow_tail && (E + 4 > n || (int32_t)ld_u32(rec + E) >= 32)) tail = E; else bad = true;
+                        break;
+                    }
                     N++;
                     E = nx;
                 }
             }
         }
         E = __shfl_sync(0xffffffffu, E, 0); N = __shfl_sync(0xffffffffu, N, 0);
+        tail = __shfl_sync(0xffffffffu, tail, 0);
         bad = __shfl_sync(0xffffffffu, (int)bad, 0) != 0;
     }
     if (lane == 0) {
-        if (bad || E != n) { fuz_raise(st, FUZ_E_BADRECORD, (int)min(N, (int64_t)0x7fffffff)); S.n_rec[0] = 0; S.n_rec[1] = 0; }
+        S.n_rec[2] = tail >= 0 ? tail : n;
+        if (bad || (tail < 0 && E != n)) { fuz_raise(st, FUZ_E_BADRECORD, (int)min(N, (int64_t)0x7fffffff)); S.n_rec[0] = 0; S.n_rec[1] = 0; }
         else {
             S.n_rec[1] = N;
             if (N > cap_rec || N > 0x7fffffff) { fuz_raise(st, FUZ_E_CAPACITY, 7); S.n_rec[0] = 0; }
@@ -364,10 +377,11 @@ __global__ void __launch_bounds__(256) k_bam_fill(const uint8_t *__restrict__ re
     fuz_pdl_enter();
     if (st->error) return;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0) rec_off[S.n_rec[0]] = n;
+    const int64_t lim = S.n_rec[2];                  // end of the indexed records (n, or the start of a cut record)
+    if (k == 0) rec_off[S.n_rec[0]] = lim;
     if (k >= n_reg) return;
     int64_t o = S.entry[k], i = S.base[k];
-    const int64_t end = min((k + 1) * FUZ_BAM_REGION, n);
+    const int64_t end = min(min((k + 1) * FUZ_BAM_REGION, n), lim);
     while (o >= 0 && o < end) {
         rec_off[i++] = o;
         o += 4 + (int64_t)(int32_t)ld_u32(rec + o);
@@ -731,15 +745,15 @@ extern "C" int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t com
     return FUZ_OK;
 }
 
-extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
-                                     int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec) {
+static int bam_index_impl(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                          int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec, int64_t *h_tail) {
     if (!ctx || !d_rec || rec_bytes < 0 || n_ref < 0 || cap_rec < 0 || !d_rec_off || !d_ctg_rec_off || !h_n_rec)
         return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_records: bad argument");
     cudaStream_t st = ctx->stream;
     const int64_t n_reg = (rec_bytes + FUZ_BAM_REGION - 1) / FUZ_BAM_REGION;
     FuzLayout L;
     const size_t o_first = L.add(8 * (size_t)(n_reg + 1)), o_land = L.add(8 * (size_t)(n_reg + 1)), o_entry = L.add(8 * (size_t)(n_reg + 1));
-    const size_t o_cnt = L.add(4 * (size_t)(n_reg + 1)), o_base = L.add(4 * (size_t)(n_reg + 1)), o_n = L.add(16);
+    const size_t o_cnt = L.add(4 * (size_t)(n_reg + 1)), o_base = L.add(4 * (size_t)(n_reg + 1)), o_n = L.add(32);
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
     BamIndexScratch S;
@@ -747,24 +761,36 @@ extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t
     S.cnt = fuz_at<int32_t>(ctx, o_cnt); S.base = fuz_at<int32_t>(ctx, o_base); S.n_rec = fuz_at<int64_t>(ctx, o_n);
     if (!ctx->ingest_pending) FUZ_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(fuz_status), st));
     ctx->ingest_pending = false;
-    FUZ_CUDA(ctx, cudaMemsetAsync(S.n_rec, 0, 16, st));
+    FUZ_CUDA(ctx, cudaMemsetAsync(S.n_rec, 0, 32, st));
     if (n_reg > 0) {
         fuz_launch(ctx, k_bam_anchor, (unsigned)((n_reg * 32 + 255) / 256), 256, 0, st, d_rec, rec_bytes, (int)n_ref, n_reg, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_bam_anchor");
     }
-    fuz_launch(ctx, k_bam_resolve, 1, 32, 0, st, d_rec, rec_bytes, n_reg, cap_rec, S, ctx->d_status);
+    fuz_launch(ctx, k_bam_resolve, 1, 32, 0, st, d_rec, rec_bytes, n_reg, cap_rec, S, h_tail ? 1 : 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_bam_resolve");
     fuz_launch(ctx, k_bam_fill, (unsigned)((n_reg + 256) / 256), 256, 0, st, d_rec, rec_bytes, n_reg, S, d_rec_off, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_bam_fill");
     fuz_launch(ctx, k_bam_ctg_ranges, FUZ_GRID_BLOCKS, 256, 0, st, d_rec, d_rec_off, S.n_rec, (int)n_ref, d_ctg_rec_off, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_bam_ctg_ranges");
-    int64_t h[2] = {0, 0};
-    FUZ_CUDA(ctx, cudaMemcpyAsync(h, S.n_rec, 16, cudaMemcpyDeviceToHost, st));
+    int64_t h[4] = {0, 0, 0, 0};
+    FUZ_CUDA(ctx, cudaMemcpyAsync(h, S.n_rec, 32, cudaMemcpyDeviceToHost, st));
     fuz_status hs;
     rc = fuz_get_status(ctx, &hs);                 // synchronises
     *h_n_rec = h[0];
     if (h_need_rec) *h_need_rec = h[1];
+    if (h_tail) *h_tail = h[2];
     return rc;
+}
+
+extern "C" int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                                     int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec) {
+    return bam_index_impl(ctx, d_rec, rec_bytes, n_ref, cap_rec, d_rec_off, d_ctg_rec_off, h_n_rec, h_need_rec, nullptr);
+}
+
+extern "C" int fuz_bam_index_window(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                                    int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec, int64_t *h_tail) {
+    if (!h_tail) return fuz_fail(ctx, FUZ_E_ARG, "fuz_bam_index_window: h_tail is NULL");
+    return bam_index_impl(ctx, d_rec, rec_bytes, n_ref, cap_rec, d_rec_off, d_ctg_rec_off, h_n_rec, h_need_rec, h_tail);
 }
 
 extern "C" int fuz_bam_index_files(fuz_ctx *ctx, const uint8_t *d_raw, int64_t raw_bytes, int32_t n_seg, const int64_t *h_seg_start,

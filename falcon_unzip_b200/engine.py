@@ -579,6 +579,81 @@ class Engine:
         return DeviceBam(refs, raw, rec_ptr, rec_bytes, rec_off, ctg_rec_off, int(n_rec.value), n_mapped, h2d,
                          keep=(d_comp, d_coff, d_csize, d_uoff, d_crc))
 
+    def ingest_bam_windows(self, path: str, window_bytes: int = 512 << 20, verify_crc: bool = True):
+        """A BAM file of any size as a sequence of DeviceBam WINDOWS: the file is memory-mapped, its BGZF blocks are taken
+        in runs of about `window_bytes` compressed bytes, every run is inflated on the device behind the bytes of the record
+        the previous window cut (fuz_bam_index_window reports where the last whole record ends), so host memory holds one
+        window of compressed bytes and HBM one window of records at a time.  The reference streams such files record by
+        record through pysam (select_reads_from_bam.py:55-76); raw-read BAMs run to hundreds of GB.  Yields DeviceBam
+        objects whose records are whole; refs come from the header."""
+        torch = self._torch
+        from . import bam
+        dev = self.device
+        image = np.memmap(path, dtype=np.uint8, mode="r")
+        n_blk = int(lib().fuz_host_bgzf_index(_np_ptr(image), len(image), 0, None, None, None, None))
+        if n_blk < 0:
+            raise FuzError(_lib.FUZ_E_FORMAT, "not a BGZF file")
+        coff, csize = np.empty(n_blk, np.int64), np.empty(n_blk, np.int32)
+        uoff, crc = np.empty(n_blk + 1, np.int64), np.empty(n_blk, np.uint32)
+        lib().fuz_host_bgzf_index(_np_ptr(image), len(image), n_blk, _np_ptr(coff), _np_ptr(csize), _np_ptr(uoff), _np_ptr(crc))
+        _text, refs, hdr_bytes = bam.read_bam_header(image, coff, csize)
+        carry = torch.zeros(0, dtype=torch.uint8, device=dev)
+        b0, skip = 0, hdr_bytes                              # bytes of the first window that belong to the header
+        while b0 < n_blk:
+            b1 = b0 + 1
+            while b1 < n_blk and coff[b1] + csize[b1] - coff[b0] <= window_bytes:
+                b1 += 1
+            c_lo, c_hi = int(coff[b0]), int(coff[b1 - 1] + csize[b1 - 1])
+            u_lo, u_hi = int(uoff[b0]), int(uoff[b1])
+            n_c, n_u, n_carry = c_hi - c_lo, u_hi - u_lo, int(carry.numel())
+            pad = (-n_carry) % 4                             # the inflate kernel writes from a 4-byte aligned start
+            d_comp = torch.empty((n_c + 3) // 4 * 4 + 16, dtype=torch.uint8, device=dev)
+            d_comp[:n_c].copy_(torch.from_numpy(np.array(image[c_lo:c_hi])))         # (a writable copy of the mapped bytes)
+            d_coff = torch.from_numpy(coff[b0:b1] - c_lo).to(dev)
+            d_csize = torch.from_numpy(csize[b0:b1].copy()).to(dev)
+            d_uoff = torch.from_numpy(np.concatenate([uoff[b0:b1] - u_lo, [n_u]]).astype(np.int64)).to(dev)
+            d_crc = torch.from_numpy(crc[b0:b1].view(np.int32).copy()).to(dev) if verify_crc else None
+            raw = torch.empty(256 + pad + n_carry + n_u + 64, dtype=torch.uint8, device=dev)
+            base = 256 + pad                                 # records start at raw[base]: carry, then the inflated window
+            raw[base:base + n_carry].copy_(carry)
+            raw[base + n_carry + n_u:].zero_()
+            torch.cuda.synchronize(dev)
+            if (raw.data_ptr() + base + n_carry) % 4:
+                raise FuzError(_lib.FUZ_E_ARG, "window start is not 4-byte aligned")
+            _lib.check(self.ctx, lib().fuz_bgzf_inflate(self.ctx, d_comp.data_ptr(), n_c, d_coff.data_ptr(), d_csize.data_ptr(),
+                                                        d_uoff.data_ptr(), d_crc.data_ptr() if verify_crc else None, b1 - b0,
+                                                        raw.data_ptr() + base + n_carry, n_u))
+            start = base + (skip if n_carry == 0 else 0)
+            if n_carry and skip:
+                raise FuzError(_lib.FUZ_E_FORMAT, "BAM header longer than a window")
+            if skip > n_u and n_carry == 0:                  # header not finished inside this window
+                skip -= n_u
+                b0 = b1
+                continue
+            rec_ptr, rec_bytes = raw.data_ptr() + start, base + n_carry + n_u - start
+            skip = 0
+            ctg_rec_off = torch.zeros(len(refs) + 1, dtype=torch.int32, device=dev)
+            cap = rec_bytes // 2048 + 1024
+            n_rec, need, tail = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            for _ in range(2):
+                rec_off = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+                torch.cuda.synchronize(dev)
+                rc = lib().fuz_bam_index_window(self.ctx, rec_ptr, rec_bytes, len(refs), cap, rec_off.data_ptr(),
+                                                ctg_rec_off.data_ptr(), C.byref(n_rec), C.byref(need), C.byref(tail))
+                if rc != _lib.FUZ_E_CAPACITY:
+                    break
+                cap = int(need.value)
+            _lib.check(self.ctx, rc)
+            last = b1 == n_blk
+            if last and tail.value != rec_bytes:
+                raise FuzError(_lib.FUZ_E_BADRECORD, "the BAM file ends inside a record")
+            o = start + int(tail.value)
+            carry = raw[o:base + n_carry + n_u].clone()
+            n_mapped = int(ctg_rec_off[-1].item()) if len(refs) else 0
+            yield DeviceBam(refs, raw, rec_ptr, int(tail.value), rec_off, ctg_rec_off, int(n_rec.value), n_mapped, n_c,
+                            keep=(d_comp, d_coff, d_csize, d_uoff, d_crc))
+            b0 = b1
+
     def ingest_bams(self, images: Sequence, verify_crc: bool = True) -> DeviceBam:
         """Several BAM files (the reference makes one sorted BAM per contig, unzip.py:90) as ONE device batch.  The
         block tables of all files are joined: one upload buffer, ONE launch of the inflate kernel over the blocks of

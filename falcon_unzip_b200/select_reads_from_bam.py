@@ -79,10 +79,9 @@ def merged_header_text(texts: Sequence[str]) -> str:
     return "".join(ln + "\n" for ln in hd + sq + rg + rest)
 
 
-def partition_file(eng, image: np.ndarray, keys: np.ndarray, key_ctg: np.ndarray, n_ctg: int):
-    """One input BAM -> (record bytes grouped by contig, file order inside a contig; byte range [n_ctg + 1] of every
-    contig).  keys: sorted "S" array of read names, key_ctg: their contig index."""
-    db = eng.ingest_bam(image)
+def partition_records(eng, db, keys: np.ndarray, key_ctg: np.ndarray, n_ctg: int):
+    """The records of a device BAM (window) -> (record bytes grouped by contig, file order inside a contig; byte range
+    [n_ctg + 1] of every contig).  keys: sorted "S" array of read names, key_ctg: their contig index."""
     names = eng.name_rows(db)
     width = max(keys.dtype.itemsize, names.dtype.itemsize, 1)
     k, n = keys.astype("S%d" % width), names.astype("S%d" % width)
@@ -98,8 +97,23 @@ def partition_file(eng, image: np.ndarray, keys: np.ndarray, key_ctg: np.ndarray
     return data, off[bounds]
 
 
+def partition_file(eng, image, keys: np.ndarray, key_ctg: np.ndarray, n_ctg: int):
+    """One input BAM given as a whole file image (tests, small inputs)."""
+    return partition_records(eng, eng.ingest_bam(image), keys, key_ctg, n_ctg)
+
+
+WINDOW_BYTES = 512 << 20        # compressed bytes of an input BAM decoded per device call
+
+
+def partition_windows(eng, path: str, keys: np.ndarray, key_ctg: np.ndarray, n_ctg: int, window_bytes: int = 0):
+    """One input BAM of any size: yields (data, bounds) per window of BGZF blocks (Engine.ingest_bam_windows), so host memory
+    and HBM hold one window at a time, like the reference's record loop holds one record (`:55-76`)."""
+    for db in eng.ingest_bam_windows(path, window_bytes or WINDOW_BYTES):
+        yield partition_records(eng, db, keys, key_ctg, n_ctg)
+
+
 def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_fn, sam_dir, device: int = 0, level: int = 6,
-                          rank: int = 0, world_size: int = 1, partition_fn=None):
+                          rank: int = 0, world_size: int = 1, partition_fn=None, window_bytes: int = 0):
     """Write <sam_dir>/<ctg>.bam for every selected contig from the reads of the input BAMs (`:8-89`).
 
     One process per GPU (world_size > 1): the selected contigs are dealt to the ranks by their number of reads
@@ -138,20 +152,25 @@ def select_reads_from_bam(input_bam_fofn_fn, rawread_to_contigs_fn, rawread_ids_
     refs = headers[0][1] if headers else []
     os.makedirs(sam_dir, exist_ok=True)
     eng = engine.get_engine(device) if partition_fn is None else None
-    part = partition_fn or partition_file
     outfile: Dict[str, bam.BamWriter] = {}
+
+    def pieces(fn):
+        if partition_fn is not None:                                     # CPU tests: a host stand-in for the device call
+            yield partition_fn(eng, np.fromfile(fn, dtype=np.uint8), keys, key_ctg, len(ctgs))
+        else:                                                            # one window of one input in memory at a time
+            yield from partition_windows(eng, fn, keys, key_ctg, len(ctgs), window_bytes)
     try:
-        for fn in fns:                                                   # one input in memory at a time
-            data, bounds = part(eng, np.fromfile(fn, dtype=np.uint8), keys, key_ctg, len(ctgs))
-            for i, ctg in enumerate(ctgs):
-                a, b = int(bounds[i]), int(bounds[i + 1])
-                if a == b:
-                    continue
-                if ctg not in outfile:
-                    samfile_fn = os.path.join(sam_dir, "%s.bam" % ctg)
-                    print("samfile_fn:{!r}".format(samfile_fn), file=sys.stderr)
-                    outfile[ctg] = bam.BamWriter(samfile_fn, header_text, refs, level=level)
-                outfile[ctg].write(data[a:b])
+        for fn in fns:
+            for data, bounds in pieces(fn):
+                for i, ctg in enumerate(ctgs):
+                    a, b = int(bounds[i]), int(bounds[i + 1])
+                    if a == b:
+                        continue
+                    if ctg not in outfile:
+                        samfile_fn = os.path.join(sam_dir, "%s.bam" % ctg)
+                        print("samfile_fn:{!r}".format(samfile_fn), file=sys.stderr)
+                        outfile[ctg] = bam.BamWriter(samfile_fn, header_text, refs, level=level)
+                    outfile[ctg].write(data[a:b])
     finally:
         for w in outfile.values():
             w.close()

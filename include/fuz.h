@@ -12,7 +12,7 @@
  *                           chained on the device for a batch of contigs)
  *   fuz_rr_track            falcon_unzip/rr_hctg_track.py:31-65,97-105,113-123
  *                           tr_stage1 + heap merge + contig vote of run_track_reads
- *   fuz_bgzf_inflate, fuz_bam_index_records, fuz_bam_index_files
+ *   fuz_bgzf_inflate, fuz_bam_index_records, fuz_bam_index_window, fuz_bam_index_files
  *                           falcon_unzip/phasing.py:27        the `samtools view` pipe: BGZF
  *                           inflate + record split, on the device
  *   fuz_ovlp_filter         falcon_unzip/ovlp_filter_with_phase.py:49-290  filter_stage1-3
@@ -257,6 +257,12 @@ int fuz_bgzf_inflate(fuz_ctx *ctx, const uint8_t *d_comp, int64_t comp_bytes, co
  * FUZ_E_BADRECORD: broken block_size chain; FUZ_E_UNSORTED: refIDs not ascending. */
 int fuz_bam_index_records(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
                           int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec);
+/* The same for one WINDOW of a record stream that is decoded piece by piece (raw-read BAMs of hundreds of GB, which
+ * select_reads_from_bam.py:55-76 streams record by record): d_rec starts at a record boundary; a record cut by the end of
+ * the buffer ends the index instead of breaking the chain, and *h_tail receives its offset (= rec_bytes when the window
+ * ends on a record boundary).  The caller carries d_rec[*h_tail, rec_bytes) over to the front of the next window. */
+int fuz_bam_index_window(fuz_ctx *ctx, const uint8_t *d_rec, int64_t rec_bytes, int32_t n_ref, int64_t cap_rec,
+                         int64_t *d_rec_off, int32_t *d_ctg_rec_off, int64_t *h_n_rec, int64_t *h_need_rec, int64_t *h_tail);
 /* The same for SEVERAL BAM files inflated into one device buffer (one fuz_bgzf_inflate over the blocks of all
  * files) -- the reference leaves one sorted BAM per contig (falcon_unzip/unzip.py:90-91) and runs fc_phasing.py
  * once per file (unzip.py:124).  File s has its alignment records at d_raw[h_seg_start[s], h_seg_end[s])

@@ -64,3 +64,43 @@ def test_gather_records_and_name_rows(eng, tmp_path):
     assert len(data) == 0 and off.tolist() == [0]
     with pytest.raises(_lib.FuzError):
         eng.gather_records(db, np.asarray([0, 300]))
+
+
+@pytest.mark.parametrize("window", [70_000, 200_000])
+def test_windowed_ingest_equals_oracle(eng, tmp_path, window, capsys):
+    """Inputs decoded in windows of BGZF blocks (Engine.ingest_bam_windows + fuz_bam_index_window): windows of one or three
+    blocks cut records (one of them 100 kb long) at every window border; the carried bytes must make them whole again."""
+    from falcon_unzip_b200 import bam, select_reads_from_bam as srb
+    fofn, r2c, ids = select_cases.make_case(str(tmp_path), seed=7)
+    header, want = select_oracle.select(fofn, r2c, ids)
+    sam_dir = str(tmp_path / "reads_w")
+    made = srb.select_reads_from_bam(fofn, r2c, ids, sam_dir, level=1, window_bytes=window)
+    assert made == sorted(want)
+    for ctg, recs in want.items():
+        _text, _refs, got = bam.read_bam(os.path.join(sam_dir, "%s.bam" % ctg))
+        assert bytes(got) == b"".join(recs), ctg
+
+
+def test_window_index_reports_the_cut_record(eng):
+    """fuz_bam_index_window on a buffer that ends inside a record: the whole records are indexed, the tail offset is the
+    start of the cut one; the plain index rejects the same buffer (broken chain)."""
+    import ctypes as C
+    import torch
+    from conftest import synth_set
+    from falcon_unzip_b200 import _lib, engine
+    sset = synth_set("tiny")
+    off = engine.index_records(sset.records)
+    cut = int(off[40]) + 100                                   # 100 bytes into record 40
+    d = torch.zeros(cut + 64, dtype=torch.uint8, device=eng.device)
+    d[:cut].copy_(torch.from_numpy(sset.records[:cut].copy()))
+    rec_off = torch.zeros(200, dtype=torch.int64, device=eng.device)
+    cro = torch.zeros(len(sset.refs) + 1, dtype=torch.int32, device=eng.device)
+    n_rec, need, tail = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    torch.cuda.synchronize()
+    rc = _lib.lib().fuz_bam_index_window(eng.ctx, d.data_ptr(), cut, len(sset.refs), 199, rec_off.data_ptr(), cro.data_ptr(),
+                                         C.byref(n_rec), C.byref(need), C.byref(tail))
+    assert rc == 0 and n_rec.value == 40 and tail.value == int(off[40])
+    assert rec_off[:41].cpu().numpy().tolist() == off[:41].tolist()
+    rc = _lib.lib().fuz_bam_index_records(eng.ctx, d.data_ptr(), cut, len(sset.refs), 199, rec_off.data_ptr(), cro.data_ptr(),
+                                          C.byref(n_rec), C.byref(need))
+    assert rc == _lib.FUZ_E_BADRECORD
