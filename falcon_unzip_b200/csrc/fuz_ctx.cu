@@ -96,7 +96,7 @@ extern "C" int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream) {
 extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return FUZ_E_ARG;
     if (!strcmp(key, "pileup_impl")) {
-        if (value < 0 || value > 2) return fuz_fail(ctx, FUZ_E_ARG, "pileup_impl must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fuz_fail(ctx, FUZ_E_ARG, "pileup_impl must be 0, 1, 2 or 3");
         ctx->pileup_impl = (int)value;
     } else if (!strcmp(key, "host_fetch")) {
         if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "host_fetch must be 0 or 1");

@@ -802,7 +802,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
                         (long long)in->total_glen, FUZ_TILE);
     cudaStream_t st = ctx->stream;
     const int n_rec = in->n_rec, n_ctg = in->n_ctg;
-    const bool seg_path = ctx->pileup_impl == 2;
+    const bool seg_path = ctx->pileup_impl == 2, seg_proj = ctx->pileup_impl == 3;     // 3: k_segments + k_project_seg + register pileup
     // tiles of the path that runs: 8192 positions (segment pileup) or 2048 (projection pileup, cross-check het test)
     const int n_tiles = (int)(in->total_glen / (seg_path ? FUZ_TILE : FUZ_PTILE));
     const int64_t cap_sites = out->cap_sites;
@@ -816,6 +816,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     // bytes per base on SEQ + QUAL); a denser batch fails with FUZ_E_CAPACITY (index 6 / 9) and fuz_status says how
     // much is needed (n_segments, reserved[0]): options "seg_cap" / "ent_cap" raise the reservation.
     int64_t seg_cap = 0, ent_cap = 0;
+    if (seg_proj) seg_cap = std::max<int64_t>(in->rec_bytes / 20 + 2 * (int64_t)n_rec + 64, ctx->seg_cap_min);
     if (seg_path) {
         seg_cap = std::max<int64_t>(in->rec_bytes / 20 + 2 * (int64_t)n_rec + 64, ctx->seg_cap_min);
         ent_cap = std::max<int64_t>(in->rec_bytes / (FUZ_TILE / 2) + 3 * (int64_t)n_rec + 64, ctx->ent_cap_min);
@@ -828,6 +829,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     size_t o_gstart = L.add(4 * (size_t)(n_rec + 1)), o_gend = L.add(4 * (size_t)(n_rec + 1));
     size_t o_nw = L.add(4 * (size_t)(n_rec + 2)), o_woff = L.add(4 * (size_t)(n_rec + 2));
     size_t o_rseq = L.add(8 * (size_t)(n_rec + 1)), o_flags = L.add((size_t)n_rec + 1);
+    size_t o_segoff = L.add(4 * (size_t)(n_rec + 2)), o_nseg = L.add(4 * (size_t)(n_rec + 2));
     size_t o_proj = L.add(4 * (size_t)proj_cap);
     size_t o_segs = L.add(16 * (size_t)seg_cap), o_ents = L.add(32 * (size_t)ent_cap);
     size_t o_clast = L.add(4 * (size_t)n_ctg), o_cspan = L.add(4 * (size_t)n_ctg);
@@ -853,7 +855,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     S.proj = fuz_at<uint32_t>(ctx, o_proj); S.proj_cap = proj_cap;
     S.segs = fuz_at<int4>(ctx, o_segs); S.seg_cap = seg_cap;
     S.ents = fuz_at<FuzTileEnt>(ctx, o_ents); S.ent_cap = ent_cap;
-    S.r_seg_off = S.r_woff; S.r_nseg = S.r_nwords;       // the two paths never run together
+    S.r_seg_off = fuz_at<int32_t>(ctx, o_segoff); S.r_nseg = fuz_at<int32_t>(ctx, o_nseg);
     S.ctg_last_rec = fuz_at<int32_t>(ctx, o_clast); S.ctg_maxspan = fuz_at<int32_t>(ctx, o_cspan);
     S.rec_cursor = fuz_at<int32_t>(ctx, o_cursor); S.tile_cursor = S.rec_cursor + 1;
     S.tile_ctg = fuz_at<int32_t>(ctx, o_tctg); S.tile_rlo = fuz_at<int32_t>(ctx, o_tlo); S.tile_rhi = fuz_at<int32_t>(ctx, o_thi);
@@ -904,6 +906,21 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         fuz_launch(ctx, k_pileup_tma, pile_ctas, FUZ_PILEUP_THREADS, smem, st, in->d_rec_buf, S, cap_sites, out->d_counts, ctx->d_status,
                    ctx->pileup_debug, ctx->trace);
         FUZ_LAUNCH_CHECK(ctx, "k_pileup_tma");
+        if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
+    } else if (seg_proj) {
+        if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));
+        if (n_rec > 0) {
+            const int ctas = std::min((n_rec + 255) / 256, 148 * 8);
+            fuz_launch(ctx, k_segments, ctas, 256, 0, st, in->d_rec_buf, in->d_rec_off, n_rec, in->d_ctg_rec_off, in->d_ctg_goff, n_ctg, S,
+                       ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_segments");
+            fuz_launch(ctx, k_project_seg, ctx->project_ctas, 256, 0, st, in->d_rec_buf, n_rec, S, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_project_seg");
+        }
+        fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
+        fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_PTILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
+        FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
     } else if (ctx->pileup_impl == 0) {
         if (ev0) FUZ_CUDA(ctx, cudaEventRecord(ev0, st));

@@ -160,6 +160,19 @@ __global__ void __launch_bounds__(256) k_segments(
                 if (accept) { acc_aligned += aligned; acc_accepted += 1; }
             }
         }
+        // the words of the reference-aligned projection (k_project_seg): whole quads, one atomic per warp
+        if (S.proj_cap > 0) {
+            const int nw = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
+            const int incl_w = fuz_warp_incl_scan(nw, lane);
+            const int tot_w = __shfl_sync(0xffffffffu, incl_w, 31);
+            long long pbase = 0;
+            if (lane == 31 && tot_w) pbase = (long long)atomicAdd((unsigned long long *)&st->reserved[0], (unsigned long long)tot_w);
+            pbase = __shfl_sync(0xffffffffu, pbase, 31) + incl_w - nw;
+            if (live) {
+                if (nw && pbase + nw > S.proj_cap) { fuz_raise(st, FUZ_E_CAPACITY, 6); S.r_nwords[r] = 0; S.r_woff[r] = 0; S.r_flags[r] = 0; }
+                else { S.r_nwords[r] = nw; S.r_woff[r] = (int32_t)pbase; }
+            }
+        }
         // last accepted record and longest span of the contig: one atomic per warp when the warp sits in one contig
         const int c0 = __shfl_sync(0xffffffffu, c, 0);
         const int rmax = accept ? r : -1, smax = accept ? (int)span : 0;
@@ -255,6 +268,101 @@ __global__ void __launch_bounds__(256) k_tile_lists(int n_tiles, int n_ctg, cons
             }
             run += __popc(m);
         }
+    }
+}
+
+// ---------------------------------------------------------------- segment-major projection (pileup_impl 3)
+// The reference-aligned 4-bit projection of k_project (one word per 8 positions, A=1 C=2 G=4 T=8), produced from the
+// segment lists of k_segments: one warp per record, one LANE per segment, segments handed out from a warp-local counter.
+// Inside a segment the query - reference offset is constant, so the lane walks its quads in order with a loop-invariant
+// shift and a sliding window over the 4-bit SEQ: four new words, nibble swap, funnel shift, one 128-bit store per quad;
+// no search for the segment of a quad and no masks except in the first and last quad of the segment.  Every quad of the
+// record is written exactly once, by the LAST segment that touches it: that lane ORs in the tails of the earlier segments
+// ending in the quad (a deletion or insertion inside the quad) and writes the zero quads in front of it (long deletions,
+// the padding of the record).
+__global__ void __launch_bounds__(256) k_project_seg(const uint8_t *__restrict__ rec_buf, int n_rec, HetScratch S, const fuz_status *st) {
+    fuz_pdl_enter();
+    if (st->error) return;
+    __shared__ int s_next[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    int r_next = 0;
+    for (int r = warp_g; r < n_rec; r = r_next) {
+        if (lane == 0) r_next = n_warps + atomicAdd(S.rec_cursor, 1);
+        r_next = __shfl_sync(0xffffffffu, r_next, 0);
+        const int n_words = S.r_nwords[r];
+        if (!S.r_flags[r] || n_words == 0) continue;
+        const int ns = S.r_nseg[r], n_quads = n_words >> 2;
+        const int4 *__restrict__ segs = S.segs + S.r_seg_off[r];
+        ProjRec R;
+        {
+            const uintptr_t sa = reinterpret_cast<uintptr_t>(rec_buf + S.r_seq[r]);
+            R.base4 = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
+            R.nphase = (int)(sa & 3) * 2;
+            R.W0 = S.r_gstart[r] >> 3;
+            R.out = S.proj + S.r_woff[r];
+        }
+        auto quad_of = [&](int pos) { return ((pos >> 3) - R.W0) >> 2; };
+        auto quad_pos = [&](int q) { return (R.W0 + 4 * q) << 3; };
+        uint4 *out4 = reinterpret_cast<uint4 *>(R.out);
+        if (ns == 0) {                                                       // a record of deletions only: nothing aligned
+            for (int q = lane; q < n_quads; q += 32) out4[q] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        __syncwarp();
+        if (lane == 0) s_next[wib] = 32;
+        __syncwarp();
+        int j = lane;
+        while (j < ns) {
+            const int4 sg = __ldg(segs + j);
+            const int qf = quad_of(sg.x), ql = quad_of(sg.y - 1);
+            const int q_prev = j > 0 ? quad_of(__ldg(&segs[j - 1].y) - 1) : -1;             // last quad of the previous segment
+            const int qn = j + 1 < ns ? quad_of(__ldg(&segs[j + 1].x)) : 0x7fffffff;         // first quad of the next one
+            for (int q = q_prev + 1; q < qf; q++) out4[q] = make_uint4(0u, 0u, 0u, 0u);      // nothing aligned there
+            // the quads I write: qf .. ql, except ql when the next segment starts inside it
+            const int q_end = qn == ql ? ql - 1 : ql;
+            if (qf <= q_end) {
+                // first quad: masked to my start (and to my end when it is also my last), plus the tails of earlier segments
+                uint32_t v[4];
+                quad_piece(R, quad_pos(qf), sg.x, sg.y, sg.z, v);
+                for (int k = j - 1; k >= 0; k--) {
+                    const int4 sk = __ldg(segs + k);
+                    if (quad_of(sk.y - 1) != qf) break;
+                    uint32_t u[4];
+                    quad_piece(R, quad_pos(qf), sk.x, sk.y, sk.z, u);
+                    v[0] |= u[0]; v[1] |= u[1]; v[2] |= u[2]; v[3] |= u[3];
+                }
+                out4[qf] = make_uint4(v[0], v[1], v[2], v[3]);
+                // middle quads: whole quads of my segment, constant shift, sliding window over SEQ
+                const int q_mid_end = min(q_end, ql - 1);                    // ql itself may be partial: handled below
+                if (qf + 1 <= q_mid_end) {
+                    const int n0 = quad_pos(qf + 1) + sg.z + R.nphase;       // nibble of the first middle position relative to base4
+                    const uint32_t *src = R.base4 + (n0 >> 3);
+                    const uint32_t sh = (uint32_t)(n0 & 7) * 4;
+                    uint32_t m0 = swap_nibbles(__ldg(src));
+                    for (int q = qf + 1; q <= q_mid_end; q++, src += 4) {
+                        const uint32_t m1 = swap_nibbles(__ldg(src + 1)), m2 = swap_nibbles(__ldg(src + 2)),
+                                       m3 = swap_nibbles(__ldg(src + 3)), m4 = swap_nibbles(__ldg(src + 4));
+                        uint32_t w0 = __funnelshift_r(m0, m1, sh), w1 = __funnelshift_r(m1, m2, sh),
+                                 w2 = __funnelshift_r(m2, m3, sh), w3 = __funnelshift_r(m3, m4, sh);
+                        if ((bad_nibbles(w0) | bad_nibbles(w1) | bad_nibbles(w2) | bad_nibbles(w3)) & 0x01010101u) {   // ambiguity codes: rare
+                            w0 = keep_acgt(w0); w1 = keep_acgt(w1); w2 = keep_acgt(w2); w3 = keep_acgt(w3);
+                        }
+                        out4[q] = make_uint4(w0, w1, w2, w3);
+                        m0 = m4;
+                    }
+                }
+                // last quad (when it is not the first): masked to my end
+                if (ql > qf && q_end == ql) {
+                    quad_piece(R, quad_pos(ql), sg.x, sg.y, sg.z, v);
+                    out4[ql] = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+            }
+            if (j + 1 == ns)                                                 // the padding behind the last segment
+                for (int q = ql + 1; q < n_quads; q++) out4[q] = make_uint4(0u, 0u, 0u, 0u);
+            j = atomicAdd(&s_next[wib], 1);
+        }
+        __syncwarp();
     }
 }
 

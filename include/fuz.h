@@ -147,6 +147,8 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *              bulk async copies (cp.async.bulk + mbarrier producer / consumer pipeline) and cut straight into
  *              bit-sliced counters without a projection (measured slower than 0; kept as an
  *              independent implementation that the tests compare bit for bit);
+ *          3 = the projection of 0 produced from segment lists (k_segments + k_project_seg: one lane per segment, no owner
+ *              search; as fast as 0, kept as a cross-check);
  *          "seg_cap" / "ent_cap" minimum reservation of segment slots / tile entries of pileup_impl 2 (a batch denser
  *                          than the built-in heuristics fails with FUZ_E_CAPACITY, error_index 6 / 9, and
  *                          fuz_status.n_segments / reserved[0] say how much it needs);

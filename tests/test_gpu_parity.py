@@ -31,7 +31,7 @@ def _assert_same_files(a, b):
                 raise AssertionError("%s/%s: %d vs %d lines" % (ctg, k, len(la), len(lb)))
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_pileup_counts_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
@@ -53,7 +53,7 @@ def test_pileup_counts_match_oracle(eng, cfg, impl):
             name, len(bad), bad[0], want[bad[0]], got[bad[0]])
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("cfg", ["tiny", "quirks", "noisy", "noisy_m"])
 def test_het_call_arrays_match_oracle(eng, cfg, impl):
     from falcon_unzip_b200 import engine
