@@ -232,7 +232,7 @@ extern "C" int fuz_phase_batch_host(fuz_ctx *ctx, const fuz_host_batch *in, fuz_
     FUZ_CUDA(ctx, h2d(d_off, in->h_rec_off, 8 * (size_t)(n_rec + 1)));
     if (mapped) {
         FUZ_CUDA(ctx, cudaMemsetAsync(dv + d_fetched, 0, 8, st));
-        fuz_launch(ctx, k_fetch_records, FUZ_GRID_BLOCKS * 2, 256, 0, st, mapped, dv + d_rec, reinterpret_cast<const int64_t *>(dv + d_off),
+        fuz_launch(ctx, k_fetch_records, ctx->fetch_ctas, 256, 0, st, mapped, dv + d_rec, reinterpret_cast<const int64_t *>(dv + d_off),
                                                              n_rec, in->rec_bytes,
                                                              reinterpret_cast<unsigned long long *>(dv + d_fetched));
         FUZ_LAUNCH_CHECK(ctx, "k_fetch_records");

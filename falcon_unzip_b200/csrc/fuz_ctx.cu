@@ -110,6 +110,9 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "phase_staging")) {
         if (value < 0 || value > 2) return fuz_fail(ctx, FUZ_E_ARG, "phase_staging must be 0, 1 or 2");
         ctx->phase_staging = (int)value;
+    } else if (!strcmp(key, "fetch_ctas")) {
+        if (value < 1 || value > 148 * 16) return fuz_fail(ctx, FUZ_E_ARG, "fetch_ctas must be in 1 .. 2368");
+        ctx->fetch_ctas = (int)value;
     } else if (!strcmp(key, "sweep_passes")) {
         if (value < 0 || value > 1 << 20) return fuz_fail(ctx, FUZ_E_ARG, "sweep_passes must be in 0 .. 2^20");
         ctx->sweep_passes = (int)value;

@@ -160,6 +160,8 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *                           multi-GPU run, the merge then runs on the gathered kept lines), 0 = default,
  *          "phase_staging" 0 = stage as much of a contig as fits in shared memory (default),
  *                          1 = at most the sweep tier, 2 = global memory only (both for tests),
+ *          "fetch_ctas" CTAs of the selective record fetch of fuz_phase_batch_host (default 1184; two contexts that
+ *                       alternate over the batches of a list use fewer, so that one computes while the other fetches),
  *          "sweep_passes" passes of the parallel fixed-point form of the pass-2 sweep (phasing.py:311-344) before
  *                         the sequential walk takes over (default 64; 0 = sequential only; same result either way),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */
