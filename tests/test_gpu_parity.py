@@ -22,6 +22,9 @@ def _assert_same_files(a, b):
     for ctg in a:
         for k in a[ctg]:
             ta, tb = open(a[ctg][k]).read(), open(b[ctg][k]).read()
+            # order-free content first (does not depend on the CPython-2 container-order emulation), then the bytes
+            assert sorted(ta.splitlines()) == sorted(tb.splitlines()), "%s/%s: row CONTENT differs (%d vs %d rows)" % (
+                ctg, k, len(ta.splitlines()), len(tb.splitlines()))
             if ta != tb:
                 la, lb = ta.splitlines(), tb.splitlines()
                 for i, (x, y) in enumerate(zip(la, lb)):

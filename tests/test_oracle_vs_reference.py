@@ -34,9 +34,12 @@ def run_both(records, refs, ref, tmp, ctg=cases.CTG):
 
 
 def assert_same(want, got):
+    """Two assertions per file: the order-free content (multiset of rows; independent of the emulated CPython-2 container
+    orders of SURVEY.md B.3 / B.4) and then the bytes (row order included)."""
     for k in want:
         a, b = open(want[k]).read(), open(got[k]).read()
-        assert a == b, "%s differs:\nreference:\n%s\noracle:\n%s" % (k, a[:600], b[:600])
+        assert sorted(a.splitlines()) == sorted(b.splitlines()), "%s: CONTENT differs:\nreference:\n%s\noracle:\n%s" % (k, a[:600], b[:600])
+        assert a == b, "%s: same rows, different ORDER:\nreference:\n%s\noracle:\n%s" % (k, a[:600], b[:600])
 
 
 @pytest.mark.parametrize("name", sorted(cases.all_cases()))

@@ -31,6 +31,9 @@ def test_rr_oracle_matches_reference(seed, bestn, n_files, tmp_path):
     want = open(p["out"]).read()
     got = rr_oracle.run_track_reads(rr.las_lines, rr.phased_reads, rr.read_to_contig_map, rr.rawread_ids, 2500, bestn)
     assert len(want.splitlines()) > 500
+    # order-free content first: rows without the rank column (ties in score are ranked by CPython-2 dict order)
+    strip = lambda t: sorted(" ".join(l.split()[:3] + l.split()[4:]) for l in t.splitlines())
+    assert strip(want) == strip(got)
     assert want == got
 
 
