@@ -110,6 +110,9 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "phase_staging")) {
         if (value < 0 || value > 2) return fuz_fail(ctx, FUZ_E_ARG, "phase_staging must be 0, 1 or 2");
         ctx->phase_staging = (int)value;
+    } else if (!strcmp(key, "gather_tma")) {
+        if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "gather_tma must be 0 or 1");
+        ctx->gather_tma = (int)value;
     } else if (!strcmp(key, "fetch_ctas")) {
         if (value < 1 || value > 148 * 16) return fuz_fail(ctx, FUZ_E_ARG, "fetch_ctas must be in 1 .. 2368");
         ctx->fetch_ctas = (int)value;
@@ -279,7 +282,8 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
 // flag and value packed in one 64-bit word; warp 0 looks back 32 tiles at a time.
 #define FUZ_SCAN_TILE 4096
 __global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n,
-                                                    unsigned long long *state, unsigned int *counter) {
+                                                    unsigned long long *state, unsigned int *counter, int fin_op, int64_t fin_cap,
+                                                    fuz_status *st) {
     fuz_pdl_enter();
     __shared__ int s_tile;
     __shared__ int s_warp[32];
@@ -339,7 +343,10 @@ __global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ 
         if (i0 + 2 < n) out[i0 + 2] = excl + v.x + v.y;
         if (i0 + 3 < n) out[i0 + 3] = excl + v.x + v.y + v.z;
     }
-    if (tid == 0 && (int64_t)(tile + 1) * FUZ_SCAN_TILE >= n) out[n] = s_prefix + s_agg;
+    if (tid == 0 && (int64_t)(tile + 1) * FUZ_SCAN_TILE >= n) {
+        out[n] = s_prefix + s_agg;
+        fuz_scan_publish(st, fin_op, fin_cap, (long long)(s_prefix + s_agg));
+    }
 }
 
 int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_cap, const int64_t *d_n, int fin_op,
@@ -351,8 +358,8 @@ int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_ca
 
 // exclusive scan of n entries (host-known n), out[n] = total; uses the context's tile-state buffer:
 // main stream only, one scan at a time
-int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n) {
-    if (n <= 65536) return fuz_scan_i32(ctx, d_in, d_out, n, nullptr, FUZ_FIN_NONE, 0);
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op, int64_t fin_cap) {
+    if (n <= 65536) return fuz_scan_i32(ctx, d_in, d_out, n, nullptr, fin_op, fin_cap);
     const int64_t tiles = (n + FUZ_SCAN_TILE - 1) / FUZ_SCAN_TILE;
     const size_t need = 8 * (size_t)tiles + 64;
     if (need > ctx->scan_state_cap) {
@@ -365,7 +372,7 @@ int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t
     FUZ_CUDA(ctx, cudaMemsetAsync(ctx->scan_state, 0, need, ctx->stream));
     unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->scan_state) + 1;
     fuz_launch(ctx, k_scan_wide, (unsigned)tiles, 1024, 0, ctx->stream, d_in, d_out, n, state,
-               reinterpret_cast<unsigned int *>(ctx->scan_state));
+               reinterpret_cast<unsigned int *>(ctx->scan_state), fin_op, fin_cap, fin_op ? ctx->d_status : (fuz_status *)nullptr);
     FUZ_LAUNCH_CHECK(ctx, "k_scan_wide");
     return FUZ_OK;
 }

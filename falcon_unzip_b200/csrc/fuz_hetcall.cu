@@ -119,6 +119,7 @@ __device__ __forceinline__ bool het_test(uint32_t cA, uint32_t cC, uint32_t cG, 
 // positions (bit i of hetmask: position i is a het site with counts cnt[i][0..3]); sites of
 // a tile land contiguously (in position order) at an atomically claimed base; tiles are put
 // in order afterwards.
+template <bool NAMED_BARRIER = false>      // true: the 256 consumer threads of k_pileup_gather_tma (bar.sync 1), else the whole CTA
 __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t (&cnt)[8][4], int tile, int t0,
                                                 HetScratch &S, int64_t cap_sites, fuz_status *st,
                                                 int *s_warp_tot, int *s_base) {
@@ -126,7 +127,7 @@ __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t
     int nh = __popc(hetmask);
     int incl = fuz_warp_incl_scan(nh, lane);
     if (lane == 31) s_warp_tot[warp] = incl;
-    __syncthreads();
+    if (NAMED_BARRIER) { __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory"); } else __syncthreads();
     if (warp == 0) {
         int t = lane < FUZ_NW ? s_warp_tot[lane] : 0;
         int ti = fuz_warp_incl_scan(t, lane);
@@ -140,7 +141,7 @@ __device__ __forceinline__ void emit_tile_sites(uint32_t hetmask, const uint32_t
             *s_base = base;
         }
     }
-    __syncthreads();
+    if (NAMED_BARRIER) { __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory"); } else __syncthreads();
     if (nh) {
         int64_t o = (int64_t)*s_base + s_warp_tot[warp] + (incl - nh);
 #pragma unroll
@@ -502,6 +503,24 @@ __device__ __forceinline__ uint32_t plane_count(const uint32_t (&acc)[8], int bi
     return v;
 }
 
+// Bit-sliced screen before the exact het test: which of a thread's 8 positions CAN be het sites.  Bit 4i+b of plane k is
+// bit k of the count of base b at position i.  A het site has total >= 10, hence a second base with count >= 3, and
+// 4*c1 > total >= c0 + c1, hence c1 > c0/3 >= 2^h0 / 3 with h0 the top plane of the position: the second base has a bit in
+// plane h0-2 or above.  Positions whose nibble of the result is zero are skipped (one in ~10^4 survives at 60x; the exact
+// test, phasing.py:112-120, runs on the survivors only).
+__device__ __forceinline__ uint32_t nib_spread(uint32_t x) {        // 0xF in every nibble that has a bit set
+    x |= x >> 1; x |= x >> 2;
+    return (x & 0x11111111u) * 15u;
+}
+__device__ __forceinline__ uint32_t het_candidates(const uint32_t (&acc)[8]) {
+    const uint32_t ge3 = (acc[0] & acc[1]) | acc[2] | acc[3] | acc[4] | acc[5] | acc[6] | acc[7];
+    const uint32_t p7 = acc[7], p6 = p7 | acc[6], p5 = p6 | acc[5], p4 = p5 | acc[4], p3 = p4 | acc[3];
+    const uint32_t near_top = acc[7] | acc[6] | acc[5] | (acc[4] & ~nib_spread(p7)) | (acc[3] & ~nib_spread(p6)) |
+                              (acc[2] & ~nib_spread(p5)) | (acc[1] & ~nib_spread(p4)) | (acc[0] & ~nib_spread(p3));
+    const uint32_t q = ge3 & near_top;
+    return (q & (q >> 1) & 0x77777777u) | (q & (q >> 2) & 0x33333333u) | (q & (q >> 3) & 0x11111111u);
+}
+
 // One CTA per 2048-position tile, one thread per 8-position word.  Every read overlapping
 // the tile contributes one ALIGNED word load per thread (no shifting: the projection is on
 // the global grid, one-hot A/C/G/T nibbles).  Counting is bit-sliced *vertically*: 15 words
@@ -590,8 +609,7 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS, 5) k_pileup_gather(HetScrat
     if (!spilled && !counts_out) {
         // a het site needs two bases with count >= 3 (second allele > 25 % of a depth >= 10):
         // test that on the planes and extract counts only for the few candidate positions
-        const uint32_t ge3 = (acc[0] & acc[1]) | acc[2] | acc[3] | acc[4] | acc[5] | acc[6] | acc[7];
-        const uint32_t two = (ge3 & (ge3 >> 1) & 0x77777777u) | (ge3 & (ge3 >> 2) & 0x33333333u) | (ge3 & (ge3 >> 3) & 0x11111111u);
+        const uint32_t two = het_candidates(acc);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
 #pragma unroll
@@ -686,63 +704,38 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS) k_het_from_counts(
 }
 
 // ---------------------------------------------------------------- ordered sites + rows
-// One CTA: exclusive scan of the per-tile site counts (tiles are in position order, so this
-// puts the sites in order), copy of the sites to their ordered slots with the derived fields,
-// exclusive scan of the variant_map rows per site.  Three former launches in one.
-__global__ void __launch_bounds__(1024) k_sites_finalize(int n_tiles, HetScratch S, const int64_t *__restrict__ ctg_goff,
-                                                          fuz_outputs O, fuz_status *st) {
+// Three steps: exclusive scan of the per-tile site counts (tiles are in position order, so this puts the sites in
+// order; fuz_scan_i32 publishes the site count), k_sites_place copies the sites to their ordered slots with the derived
+// fields (one thread per site over the whole grid: at 60 000 sites a batch one CTA spent 50 us here on 15 dependent
+// rounds), then the exclusive scan of the variant_map rows per site.
+__global__ void __launch_bounds__(256) k_sites_place(HetScratch S, const int64_t *__restrict__ ctg_goff, fuz_outputs O, const fuz_status *st) {
     fuz_pdl_enter();
     if (st->error) return;
-    const long long total = fuz_cta_scan_i32(S.tile_site_cnt, S.tile_site_off, n_tiles);
-    if (threadIdx.x == 0) fuz_scan_publish(st, FUZ_FIN_SITES, O.cap_sites, total);
-    __threadfence_block();
-    __syncthreads();
-    if (total > O.cap_sites) return;
-    // one thread per site (claimed slot u of its tile -> ordered slot d), four sites per thread
-    // and round so that the dependent loads (tile -> offsets -> contig origin) of a round overlap
-    for (int u0 = threadIdx.x; u0 < (int)total; u0 += 4 * blockDim.x) {
-        int t[4], d[4], c[4], gp[4];
-        uint4 v[4];
-        int64_t org[4];
+    const int total = (int)st->n_sites;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        // claimed slot u of its tile -> ordered slot dd
+        const int t = S.us_tile[u];
+        const int gp = S.us_gpos[u];
+        const uint4 v = reinterpret_cast<const uint4 *>(S.us_cnt)[u];
+        const int dd = S.tile_site_off[t] + (u - S.tile_site_base[t]);
+        const int c = S.tile_ctg[t];
+        const int64_t org = ctg_goff[c];
+        const uint32_t k[4] = {v.x << 2, (v.y << 2) | 1, (v.z << 2) | 2, (v.w << 2) | 3};
+        uint32_t m0 = max(max(k[0], k[1]), max(k[2], k[3])), m1 = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int u = u0 + j * blockDim.x;
-            t[j] = u < (int)total ? S.us_tile[u] : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int u = min(u0 + j * (int)blockDim.x, (int)total - 1);
-            d[j] = S.tile_site_off[t[j]] + (u - S.tile_site_base[t[j]]);
-            c[j] = S.tile_ctg[t[j]];
-            gp[j] = S.us_gpos[u];
-            v[j] = reinterpret_cast<const uint4 *>(S.us_cnt)[u];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) org[j] = ctg_goff[c[j]];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (u0 + j * blockDim.x >= (int)total) break;
-            const uint32_t k[4] = {v[j].x << 2, (v[j].y << 2) | 1, (v[j].z << 2) | 2, (v[j].w << 2) | 3};
-            uint32_t m0 = max(max(k[0], k[1]), max(k[2], k[3])), m1 = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) if (k[b] != m0) m1 = max(m1, k[b]);
-            const int b0 = m0 & 3, b1 = m1 & 3, dd = d[j];
-            S.s_gpos[dd] = gp[j];
-            O.d_site_ctg[dd] = c[j];
-            O.d_site_pos[dd] = (int32_t)(gp[j] - org[j]) + 1;
-            reinterpret_cast<uint4 *>(O.d_site_cnt)[dd] = v[j];
-            // allele order of the association table = order by "ACTG" (SURVEY.md B.1):
-            // rank A=0 C=1 T=2 G=3 (two bits each in 0xB4)
-            const bool sw = ((0xB4 >> (2 * b0)) & 3) > ((0xB4 >> (2 * b1)) & 3);
-            reinterpret_cast<uchar2 *>(O.d_site_top)[dd] = make_uchar2((uint8_t)b0, (uint8_t)b1);
-            reinterpret_cast<uchar2 *>(O.d_site_al)[dd] = make_uchar2((uint8_t)(sw ? b1 : b0), (uint8_t)(sw ? b0 : b1));
-            S.site_rows[dd] = (int)((m0 >> 2) + (m1 >> 2));
-        }
+        for (int b = 0; b < 4; b++) if (k[b] != m0) m1 = max(m1, k[b]);
+        const int b0 = m0 & 3, b1 = m1 & 3;
+        S.s_gpos[dd] = gp;
+        O.d_site_ctg[dd] = c;
+        O.d_site_pos[dd] = (int32_t)(gp - org) + 1;
+        reinterpret_cast<uint4 *>(O.d_site_cnt)[dd] = v;
+        // allele order of the association table = order by "ACTG" (SURVEY.md B.1):
+        // rank A=0 C=1 T=2 G=3 (two bits each in 0xB4)
+        const bool sw = ((0xB4 >> (2 * b0)) & 3) > ((0xB4 >> (2 * b1)) & 3);
+        reinterpret_cast<uchar2 *>(O.d_site_top)[dd] = make_uchar2((uint8_t)b0, (uint8_t)b1);
+        reinterpret_cast<uchar2 *>(O.d_site_al)[dd] = make_uchar2((uint8_t)(sw ? b1 : b0), (uint8_t)(sw ? b0 : b1));
+        S.site_rows[dd] = (int)((m0 >> 2) + (m1 >> 2));
     }
-    __threadfence_block();
-    __syncthreads();
-    const long long rows = fuz_cta_scan_i32(S.site_rows, S.site_row_off, total);
-    if (threadIdx.x == 0) fuz_scan_publish(st, FUZ_FIN_VMAP, O.cap_vmap, rows);
 }
 
 // One warp per site: the records covering the site, in record (= file) order, 32 at a
@@ -824,13 +817,14 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
             return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (more than 2^31 segments or tile entries)");
     }
     const int pile_ctas = seg_path ? std::min(n_tiles, 148 * 2) : 0;
+    const int gather_ctas = (ctx->pileup_impl == 0 && ctx->gather_tma) ? std::min(n_tiles, 148 * 3) : 0;
     HetScratch S;
     FuzLayout L;
     size_t o_gstart = L.add(4 * (size_t)(n_rec + 1)), o_gend = L.add(4 * (size_t)(n_rec + 1));
     size_t o_nw = L.add(4 * (size_t)(n_rec + 2)), o_woff = L.add(4 * (size_t)(n_rec + 2));
     size_t o_rseq = L.add(8 * (size_t)(n_rec + 1)), o_flags = L.add((size_t)n_rec + 1);
     size_t o_segoff = L.add(4 * (size_t)(n_rec + 2)), o_nseg = L.add(4 * (size_t)(n_rec + 2));
-    size_t o_proj = L.add(4 * (size_t)proj_cap);
+    size_t o_proj = L.add(4 * (size_t)(proj_cap + 4));       // + 4: k_pileup_gather_tma rounds its copies up to 16 bytes
     size_t o_segs = L.add(16 * (size_t)seg_cap), o_ents = L.add(32 * (size_t)ent_cap);
     size_t o_clast = L.add(4 * (size_t)n_ctg), o_cspan = L.add(4 * (size_t)n_ctg);
     size_t o_tctg = L.add(4 * (size_t)n_tiles), o_tlo = L.add(4 * (size_t)n_tiles), o_thi = L.add(4 * (size_t)n_tiles);
@@ -841,7 +835,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     size_t o_sg = L.add(4 * (size_t)cap_sites), o_srow = L.add(4 * (size_t)(cap_sites + 1)),
            o_sroff = L.add(4 * (size_t)(cap_sites + 2));
     size_t o_cursor = L.add(16);
-    size_t o_spill = L.add(seg_path ? 4 * (size_t)pile_ctas * 64 * FUZ_CONSUMERS : 0);
+    size_t o_spill = L.add(seg_path ? 4 * (size_t)pile_ctas * 64 * FUZ_CONSUMERS : 4 * (size_t)gather_ctas * 16 * FUZ_PTILE_THREADS);
     size_t o_counts = 0;
     const bool need_counts = ctx->pileup_impl == 1 && !out->d_counts;
     if (need_counts) o_counts = L.add(16 * (size_t)in->total_glen);
@@ -931,8 +925,18 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         }
         fuz_launch(ctx, k_tile_ranges, (n_tiles + 7) / 8, 256, 0, st, n_tiles, n_ctg, in->d_ctg_goff, in->d_ctg_rec_off, S, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_tile_ranges");
-        fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_PTILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
-        FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
+        if (ctx->gather_tma) {
+            const size_t gsm = FUZ_GSTAGES * sizeof(FuzGStage) + 2 * FUZ_GSTAGES * sizeof(uint64_t);
+            if (!ctx->gather_attr_set) {
+                FUZ_CUDA(ctx, cudaFuncSetAttribute(k_pileup_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+                ctx->gather_attr_set = true;
+            }
+            fuz_launch(ctx, k_pileup_gather_tma, gather_ctas, FUZ_PTILE_THREADS + 32, gsm, st, S, cap_sites, out->d_counts, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather_tma");
+        } else {
+            fuz_launch(ctx, k_pileup_gather, n_tiles, FUZ_PTILE_THREADS, 0, st, S, cap_sites, out->d_counts, ctx->d_status);
+            FUZ_LAUNCH_CHECK(ctx, "k_pileup_gather");
+        }
         if (ev1) FUZ_CUDA(ctx, cudaEventRecord(ev1, st));
     } else {
         FUZ_CUDA(ctx, cudaMemsetAsync(S.counts, 0, 16 * (size_t)in->total_glen, st));
@@ -951,8 +955,10 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_PTILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
-    fuz_launch(ctx, k_sites_finalize, 1, 1024, 0, st, n_tiles, S, in->d_ctg_goff, *out, ctx->d_status);
-    FUZ_LAUNCH_CHECK(ctx, "k_sites_finalize");
+    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, FUZ_FIN_SITES, cap_sites))) return rc;
+    fuz_launch(ctx, k_sites_place, FUZ_GRID_BLOCKS, 256, 0, st, S, in->d_ctg_goff, *out, ctx->d_status);
+    FUZ_LAUNCH_CHECK(ctx, "k_sites_place");
+    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, FUZ_FIN_VMAP, out->cap_vmap))) return rc;
     if (ctx->join_pending) {                  // q_ids assigned on the side stream (fuz_phase_batch)
         FUZ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         ctx->join_pending = false;

@@ -54,6 +54,8 @@ struct fuz_ctx {
     bool ingest_pending = false;       // fuz_bgzf_inflate ran; the next fuz_bam_index_records keeps its status
     bool phase_attr_set = false;
     bool pileup_attr_set = false;
+    bool gather_attr_set = false;
+    int gather_tma = 1;                // pileup_impl 0: TMA-fed persistent gather (1) or the plain tile-per-CTA kernel (0)
     int pileup_debug = 0;
     uint32_t *trace = nullptr;         // host-mapped progress markers (debugging)
     int64_t seg_cap_min = 0, ent_cap_min = 0;   // reservations of the segment pileup beyond the heuristics (capacity retry)
@@ -260,4 +262,4 @@ int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_ca
                  const int64_t *d_n, int fin_op, int64_t fin_cap);
 // the same for a host-known n of millions of entries: multi-CTA single-pass scan (decoupled
 // look-back); main stream only
-int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n);
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op = FUZ_FIN_NONE, int64_t fin_cap = 0);

@@ -919,7 +919,7 @@ int fuz_reads_vote(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *o
     FUZ_LAUNCH_CHECK(ctx, "k_q_pack");
     fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
-    if ((rc = fuz_scan_i32(ctx, R.pr_cnt, R.pr_off, total_nq, nullptr, FUZ_FIN_READS, out->cap_reads))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, R.pr_cnt, R.pr_off, total_nq, FUZ_FIN_READS, out->cap_reads))) return rc;
     fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
     return FUZ_OK;

@@ -400,6 +400,224 @@ __device__ __forceinline__ void fuz_consumer_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(FUZ_CONSUMERS) : "memory");
 }
 
+// ---------------------------------------------------------------- TMA-fed register pileup over the projection (pileup_impl 0)
+// k_pileup_gather as a persistent producer / consumer pipeline.  The projection rows are reference aligned, so the part of a
+// read inside a 2048-position tile is one contiguous run of <= 256 words: the producer warp finds the reads of a tile, turns
+// each into one bulk copy (cp.async.bulk, 16-byte aligned start, completion on the stage's mbarrier) into a ring of 4 stages
+// of 15 reads, and runs ahead across tile borders; the 256 consumer threads (one 8-position word each) read their word of
+// every read from shared memory and feed the carry-save tree.  The dependent chain of the plain kernel (tile range ->
+// record fields -> compaction -> loads, 3.3 waves of short-lived CTAs) is what kept it at 3.5 TB/s.
+#define FUZ_GG 15                   // reads per stage = inputs of one carry-save tree
+#define FUZ_GSLOT 264               // words per read slot: 256 + alignment slack at both ends
+#define FUZ_GSTAGES 4
+struct __align__(16) FuzGStage {
+    uint32_t slot[FUZ_GG][FUZ_GSLOT];
+    int4 ent[FUZ_GG];               // x = first tile word of the read, y = one past its last, z = slot index of tile word 0
+    int32_t n, tile, last, pad;
+};
+
+__global__ void __launch_bounds__(FUZ_PTILE_THREADS + 32, 3) k_pileup_gather_tma(HetScratch S, int64_t cap_sites, uint32_t *__restrict__ counts_out,
+                                                                                  fuz_status *st) {
+    fuz_pdl_enter();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FuzGStage *stages = reinterpret_cast<FuzGStage *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + FUZ_GSTAGES * sizeof(FuzGStage));     // full[], empty[]
+    __shared__ int s_warp_tot[FUZ_NW];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < FUZ_GSTAGES; i++) {
+            fuz_mbar_init(fuz_smem_u32(&bars[i]), 1);
+            fuz_mbar_init(fuz_smem_u32(&bars[FUZ_GSTAGES + i]), FUZ_NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool dead = st->error != 0;
+    if (warp == FUZ_NW) {
+        // ------------------------------------------------------------ producer
+        int stage = 0, fill = 0;
+        uint32_t phase = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        bool open = false;                                            // the current stage has been waited for
+        // Software pipeline: the record fields of the NEXT round of 32 candidates (of this tile or the next) and the tile
+        // after next are requested before the current round is turned into copies -- no load latency between rounds.
+        int f_tile = 0, f_rlo = 0, f_rhi = 0;                         // lane 0: the fetched tile (loads may be in flight)
+        auto fetch_tile = [&]() {
+            if (lane == 0) {
+                const int t = dead ? S.n_tiles : atomicAdd(S.tile_cursor, 1);
+                const bool e = t >= S.n_tiles;
+                f_tile = t; f_rlo = e ? 0 : S.tile_rlo[t]; f_rhi = e ? 0 : S.tile_rhi[t];
+            }
+        };
+        struct Round { int fl, gs, ge, nw, wo; };
+        auto load_round = [&](bool end_, int rhi_, int cb_) {
+            const int r = cb_ + lane;
+            const bool in = !end_ && r < rhi_;
+            Round q;
+            q.fl = in ? S.r_flags[r] : 0; q.gs = in ? S.r_gstart[r] : 0; q.ge = in ? S.r_gend[r] : 0;
+            q.nw = in ? S.r_nwords[r] : 0; q.wo = in ? S.r_woff[r] : 0;
+            return q;
+        };
+        fetch_tile();
+        int tile = __shfl_sync(0xffffffffu, f_tile, 0), rlo = __shfl_sync(0xffffffffu, f_rlo, 0), rhi = __shfl_sync(0xffffffffu, f_rhi, 0);
+        bool end = tile >= S.n_tiles;
+        if (!end) fetch_tile();
+        int cb = rlo;
+        Round cur = load_round(end, rhi, cb);
+        for (;;) {
+            const bool last_round = cb + 32 >= rhi;
+            int n_tile = tile, n_rlo = rlo, n_rhi = rhi, n_cb = cb + 32;
+            bool n_end = end;
+            if (last_round && !end) {
+                n_tile = __shfl_sync(0xffffffffu, f_tile, 0); n_rlo = __shfl_sync(0xffffffffu, f_rlo, 0); n_rhi = __shfl_sync(0xffffffffu, f_rhi, 0);
+                n_end = n_tile >= S.n_tiles;
+                if (!n_end) fetch_tile();
+                n_cb = n_rlo;
+            }
+            const Round nxt = load_round(n_end || (last_round && end), n_rhi, n_cb);
+            {
+                const int t0 = tile * FUZ_PTILE, t1 = t0 + FUZ_PTILE, Wt0 = t0 >> 3;
+                const bool ok = cur.fl && cur.ge > t0 && cur.gs < t1;                      // (fl == 0 outside the range)
+                int4 e = make_int4(0, 0, 0, 0);
+                const uint32_t *src = nullptr;
+                uint32_t bytes = 0;
+                if (ok) {
+                    const int W0 = cur.gs >> 3;
+                    const int lo = max(W0, Wt0) - Wt0, hi = min(W0 + cur.nw, Wt0 + FUZ_PTILE / 8) - Wt0;
+                    const int64_t s0 = (int64_t)cur.wo + (Wt0 + lo - W0);
+                    const int pre = (int)(s0 & 3);
+                    src = S.proj + (s0 - pre);
+                    bytes = 4u * (uint32_t)((pre + (hi - lo) + 3) & ~3);
+                    e = make_int4(lo, hi, pre - lo, 0);
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, ok);
+                do {
+                    FuzGStage &sg = stages[stage];
+                    const uint32_t full = fuz_smem_u32(&bars[stage]), empty = fuz_smem_u32(&bars[FUZ_GSTAGES + stage]);
+                    if (!open) { fuz_mbar_wait(empty, phase ^ 1u, 200); open = true; }
+                    const int take = min(FUZ_GG - fill, __popc(m));
+                    // the `take` lowest set lanes of m go into slots fill .. fill + take - 1
+                    const int my = __popc(m & lt);
+                    const bool mine = ((m >> lane) & 1u) && my < take;
+                    const uint32_t tx = __reduce_add_sync(0xffffffffu, mine ? bytes : 0u);
+                    if (lane == 0 && tx) asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(tx) : "memory");
+                    __syncwarp();
+                    if (mine) {
+                        sg.ent[fill + my] = e;
+                        fuz_bulk_g2s(fuz_smem_u32(&sg.slot[fill + my][0]), src, bytes, full);
+                    }
+                    m &= ~__ballot_sync(0xffffffffu, mine);
+                    fill += take;
+                    const bool tile_done = last_round && m == 0;
+                    if (fill == FUZ_GG || tile_done) {                // post the stage
+                        if (lane == 0) { sg.n = end ? -1 : fill; sg.tile = tile; sg.last = tile_done; }
+                        __syncwarp();
+                        if (lane == 0) fuz_mbar_arrive(full);
+                        fill = 0; open = false;
+                        if (++stage == FUZ_GSTAGES) { stage = 0; phase ^= 1u; }
+                    }
+                } while (m);
+            }
+            if (last_round && end) break;
+            tile = n_tile; rlo = n_rlo; rhi = n_rhi; cb = n_cb; end = n_end;
+            cur = nxt;
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- consumers: thread = one 8-position word of the tile
+    uint32_t *spill = S.spill + (size_t)blockIdx.x * 16 * FUZ_PTILE_THREADS;
+#define C16G(b, j) spill[(4 * (b) + (j)) * FUZ_PTILE_THREADS + tid]
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_reads_seen = 0, groups_in_acc = 0;
+    bool spilled = false;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        FuzGStage &sg = stages[stage];
+        fuz_mbar_wait(fuz_smem_u32(&bars[stage]), phase);
+        const int n = sg.n, tile = sg.tile, last = sg.last;
+        if (n < 0) break;
+        uint32_t x[FUZ_GG];
+#pragma unroll
+        for (int s = 0; s < FUZ_GG; s++) {
+            x[s] = 0;
+            if (s < n) {
+                const int4 e = sg.ent[s];
+                if (tid >= e.x && tid < e.y) x[s] = sg.slot[s][tid + e.z];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) fuz_mbar_arrive(fuz_smem_u32(&bars[FUZ_GSTAGES + stage]));
+        if (++stage == FUZ_GSTAGES) { stage = 0; phase ^= 1u; }
+        n_reads_seen += n;
+        if (n > 0) {
+            uint32_t s0, s1, s2, s3, s4, s5, k0, k1, k2, k3, k4, k5, k6, ones, t0_, t1_, d0, d1, d2, twos, fours, eights;
+            FUZ_FA(x[0], x[1], x[2], s0, k0); FUZ_FA(x[3], x[4], x[5], s1, k1); FUZ_FA(x[6], x[7], x[8], s2, k2);
+            FUZ_FA(x[9], x[10], x[11], s3, k3); FUZ_FA(x[12], x[13], x[14], s4, k4);
+            FUZ_FA(s0, s1, s2, s5, k5); FUZ_FA(s3, s4, s5, ones, k6);
+            FUZ_FA(k0, k1, k2, t0_, d0); FUZ_FA(k3, k4, k5, t1_, d1); FUZ_FA(t0_, t1_, k6, twos, d2);
+            FUZ_FA(d0, d1, d2, fours, eights);
+            uint32_t cy = acc[0] & ones; acc[0] ^= ones;
+            uint32_t nc = maj3(acc[1], twos, cy); acc[1] = xor3(acc[1], twos, cy); cy = nc;
+            nc = maj3(acc[2], fours, cy); acc[2] = xor3(acc[2], fours, cy); cy = nc;
+            nc = maj3(acc[3], eights, cy); acc[3] = xor3(acc[3], eights, cy); cy = nc;
+#pragma unroll
+            for (int k = 4; k < 8; k++) { nc = acc[k] & cy; acc[k] ^= cy; cy = nc; }
+            if (++groups_in_acc == 17) {                 // 17 * 15 = 255: planes are full, spill to 16-bit counters
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (!spilled && (i & 1) == 0) C16G(b, i >> 1) = 0;
+                        C16G(b, i >> 1) += plane_count(acc, 4 * i + b) << ((i & 1) * 16);
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = 0;
+                groups_in_acc = 0;
+                spilled = true;
+            }
+        }
+        if (!last) continue;
+        // ------------------------------------------------------------ end of the tile: het test, ordered sites (as k_pileup_gather)
+        if (n_reads_seen > 65535 && tid == 0) fuz_raise(st, FUZ_E_DEPTH, tile);
+        const int t0 = tile * FUZ_PTILE;
+        const int pos_limit = S.tile_limit[tile];
+        uint32_t cnt[8][4];
+        uint32_t hetmask = 0;
+        if (!spilled && !counts_out) {
+            const uint32_t two = het_candidates(acc);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) cnt[i][b] = 0;
+                if ((two >> (4 * i)) & 7u) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) cnt[i][b] = plane_count(acc, 4 * i + b);
+                    if (t0 + tid * 8 + i < pos_limit && het_test(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3])) hetmask |= 1u << i;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    cnt[i][b] = (spilled ? (C16G(b, i >> 1) >> ((i & 1) * 16)) & 0xFFFFu : 0u) + plane_count(acc, 4 * i + b);
+            if (counts_out) {
+                uint4 *o = reinterpret_cast<uint4 *>(counts_out) + (size_t)t0 + (size_t)tid * 8;
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = make_uint4(cnt[i][0], cnt[i][1], cnt[i][2], cnt[i][3]);
+            }
+            hetmask = het_mask_of(cnt, t0, pos_limit);
+        }
+        emit_tile_sites<true>(hetmask, cnt, tile, t0, S, cap_sites, st, s_warp_tot, &s_base);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0;
+        n_reads_seen = 0; groups_in_acc = 0; spilled = false;
+    }
+#undef C16G
+}
+
 // ---------------------------------------------------------------- the cut
 // The 32 nibbles of the read at reference positions Q0 .. Q0 + 31 under segment sg (position 8k + i of the quad in
 // bits 28 - 4i of v[k]: the BAM nibble order after a byte reversal), masked to the part of the quad the segment
