@@ -178,14 +178,9 @@ __device__ __forceinline__ uint32_t swap_nibbles(uint32_t x) {      // BAM: firs
 __device__ __forceinline__ uint32_t multi_bits(uint32_t x) {     // non-zero inside nibbles with 2+ bits set
     return (x & (x >> 1) & 0x77777777u) | (x & (x >> 2) & 0x33333333u) | (x & (x >> 3) & 0x11111111u);
 }
-// bit 0 of byte i set iff nibble i of the low 16 bits of x is not 0 or a one-hot code: one
-// PRMT as a 16-entry table (selector bit 3 = replicate the sign of the selected byte)
-__device__ __forceinline__ uint32_t bad_nibbles4(uint32_t x) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0x81808000u), "r"(0x81818180u), "r"(x));
-    return d;
-}
-__device__ __forceinline__ uint32_t bad_nibbles(uint32_t x) { return bad_nibbles4(x) | bad_nibbles4(x >> 16); }
+// non-zero iff some nibble of x has two or more bits set: per nibble n & (n - 1), the decrement done on (n | 8) so that no
+// borrow crosses a nibble ((n | 8) - 1 keeps n - 1 in the low three bits, and bit 3 of it is set exactly when n > 8)
+__device__ __forceinline__ uint32_t ambiguous_nibbles(uint32_t x) { return x & ((x | 0x88888888u) - 0x11111111u); }
 __device__ __forceinline__ uint32_t keep_acgt(uint32_t x) {
     uint32_t any = multi_bits(x);
     if (any) {
@@ -212,6 +207,7 @@ struct ProjRec {
     int nphase;                // nibble index of SEQ[0] relative to base4 (0, 2, 4, 6)
     int W0;                    // first word of the record on the global 8-position grid
     uint32_t *out;             // the record's projection
+    const uint32_t *lim;       // end of the record (prefetches stay below it)
 };
 
 // the piece of segment (a, b, dq) inside the quad starting at reference position Q0:
@@ -232,27 +228,66 @@ __device__ __forceinline__ void quad_piece(const ProjRec &R, int Q0, int a, int 
         const uint32_t ml = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(lo4 - 32 * k, 0));
         v[k] = __funnelshift_r(m[k], m[k + 1], sh) & mh & ~ml;
     }
-    if ((bad_nibbles(v[0]) | bad_nibbles(v[1]) | bad_nibbles(v[2]) | bad_nibbles(v[3])) & 0x01010101u) {   // ambiguity codes: rare
+    if (ambiguous_nibbles(v[0]) | ambiguous_nibbles(v[1]) | ambiguous_nibbles(v[2]) | ambiguous_nibbles(v[3])) {   // ambiguity codes: rare
         v[0] = keep_acgt(v[0]); v[1] = keep_acgt(v[1]); v[2] = keep_acgt(v[2]); v[3] = keep_acgt(v[3]);
+    }
+}
+// The same with the position masks from a table in shared memory: s_low[n] = the n lowest nibbles of a quad (n = 0 .. 32).
+// k_project is bound by the integer ALU pipe (ncu: 71 % of its cycles), the two LDS.128 replace 24 ALU operations.
+template <bool PREFETCH>
+__device__ __forceinline__ void quad_piece_t(const ProjRec &R, int Q0, int a, int b, int dq, const uint4 *__restrict__ s_low, uint32_t (&v)[4]) {
+    const uint4 ml = s_low[max(a - Q0, 0)], mh = s_low[min(b - Q0, 32)];
+    const int n = Q0 + dq + R.nphase;
+    const uint32_t *src = R.base4 + (n >> 3);
+    const uint32_t sh = (uint32_t)(n & 7) * 4;
+    uint32_t m[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) m[k] = __ldg(src + k);
+    // the same lane cuts the quad 1024 positions on in the next round of the row loop: its SEQ window sits 512 bytes on
+    // (give or take the indels in between); pull that sector into L1 now -- waiting for these loads from L2 is the largest
+    // single stall of the kernel (ncu source view)
+    if (PREFETCH && src + 128 + 8 <= R.lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + 128 + 2));
+#pragma unroll
+    for (int k = 0; k < 5; k++) m[k] = swap_nibbles(m[k]);
+    v[0] = __funnelshift_r(m[0], m[1], sh) & mh.x & ~ml.x;
+    v[1] = __funnelshift_r(m[1], m[2], sh) & mh.y & ~ml.y;
+    v[2] = __funnelshift_r(m[2], m[3], sh) & mh.z & ~ml.z;
+    v[3] = __funnelshift_r(m[3], m[4], sh) & mh.w & ~ml.w;
+    if (ambiguous_nibbles(v[0]) | ambiguous_nibbles(v[1]) | ambiguous_nibbles(v[2]) | ambiguous_nibbles(v[3])) {   // ambiguity codes: rare
+        v[0] = keep_acgt(v[0]); v[1] = keep_acgt(v[1]); v[2] = keep_acgt(v[2]); v[3] = keep_acgt(v[3]);
+    }
+}
+__device__ __forceinline__ void fill_low_nibble_masks(uint4 *s_low) {        // threads 0 .. 32 of the CTA; barrier by the caller
+    const int n = threadIdx.x;
+    if (n <= 32) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(4 * n - 32 * k, 0));
+        s_low[n] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
 // quads [q_from, q_to) of the record from the segment list (see above)
 __device__ __forceinline__ void emit_quads(const int *__restrict__ s_rs, const int *__restrict__ s_re,
                                            const int *__restrict__ s_dq, int n_seg, int q_from, int q_to,
-                                           const ProjRec &R, int lane) {
+                                           const ProjRec &R, int lane, const uint4 *__restrict__ s_low) {
     if (q_from >= q_to) return;
     auto quad_pos = [&](int q) { return (R.W0 + 4 * q) << 3; };
     // ---- phase 1
-    int row_sp = 0;                                        // first segment with re > first position of the row
+    // The lanes hold the ends of segments row_sp .. row_sp + 31 (a window over the list; every segment before it ends at or
+    // before the row).  The window is moved only when it may not reach the end of the row: at one segment per ~150
+    // positions it serves about four rows of 1024 positions.
+    int row_sp = 0;
+    int re_l = lane < n_seg ? s_re[lane] : 0x7fffffff;
     for (int q_row = q_from; q_row < q_to; q_row += 32) {
         const int Qr = quad_pos(q_row);
-        int re_l;                                          // ends of segments row_sp .. row_sp + 31, one per lane
-        for (;;) {
-            re_l = row_sp + lane < n_seg ? s_re[row_sp + lane] : 0x7fffffff;
-            const int adv = __popc(__ballot_sync(0xffffffffu, re_l <= Qr));
-            if (adv == 0) break;
-            row_sp += adv;
+        if (__shfl_sync(0xffffffffu, re_l, 31) <= Qr + 31 * 32) {
+            for (;;) {                                     // to the first segment with re > first position of the row
+                const int adv = __popc(__ballot_sync(0xffffffffu, re_l <= Qr));
+                if (adv == 0) break;
+                row_sp += adv;
+                re_l = row_sp + lane < n_seg ? s_re[row_sp + lane] : 0x7fffffff;
+            }
         }
         const int q = q_row + lane;
         const int Q0 = Qr + 32 * lane;
@@ -277,7 +312,7 @@ __device__ __forceinline__ void emit_quads(const int *__restrict__ s_rs, const i
             const bool has = s < n_seg;
             const int a = has ? s_rs[s] : 0x7fffffff, b = has ? s_re[s] : 0x7fffffff, dq = has ? s_dq[s] : 0;
             uint32_t v[4] = {0u, 0u, 0u, 0u};
-            if (a < Q0 + 32) quad_piece(R, Q0, a, b, dq, v);
+            if (a < Q0 + 32) quad_piece_t<true>(R, Q0, a, b, dq, s_low, v);
             *reinterpret_cast<uint4 *>(R.out + 4 * q) = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
@@ -290,7 +325,7 @@ __device__ __forceinline__ void emit_quads(const int *__restrict__ s_rs, const i
         const int Q0 = quad_pos(q);
         if (s_re[s - 1] <= Q0) continue;                   // no earlier segment in this quad: s owns it
         uint32_t v[4];
-        quad_piece(R, Q0, a, s_re[s], s_dq[s], v);
+        quad_piece_t<false>(R, Q0, a, s_re[s], s_dq[s], s_low, v);
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (v[k]) atomicOr(R.out + 4 * q + k, v[k]);
@@ -318,11 +353,17 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 // G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
 // Closed segments are appended to the warp's shared-memory list; the list is turned into
 // quads of the projection (emit_quads) when it fills up and at the end of the CIGAR.
-__global__ void __launch_bounds__(256, 6) k_project(
+#ifndef FUZ_PROJ_MINB
+#define FUZ_PROJ_MINB 5             // CTAs per SM: 48 registers; at 6 (40 registers) the spills cost 8 % (measured), 4 is no faster
+#endif
+__global__ void __launch_bounds__(256, FUZ_PROJ_MINB) k_project(
     const uint8_t *__restrict__ rec_buf, const int64_t *__restrict__ rec_off, int n_rec,
     const int32_t *__restrict__ ctg_rec_off, const int64_t *__restrict__ ctg_goff, int n_ctg, HetScratch S, fuz_status *st) {
     fuz_pdl_enter();
     __shared__ int segs[8][3][FUZ_SEGCAP];
+    __shared__ uint4 s_low[33];
+    fill_low_nibble_masks(s_low);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     int *s_rs = segs[threadIdx.x >> 5][0], *s_re = segs[threadIdx.x >> 5][1], *s_dq = segs[threadIdx.x >> 5][2];
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -418,6 +459,7 @@ __global__ void __launch_bounds__(256, 6) k_project(
             R.nphase = (int)(sa & 3) * 2;
             R.W0 = gstart >> 3;
             R.out = S.proj + woff;
+            R.lim = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(rec_buf + off_n)) & ~(uintptr_t)3);
         }
         int n_seg = 0, q_next = 0;
         int carry_rp = gstart, carry_qp = 0;
@@ -455,7 +497,7 @@ __global__ void __launch_bounds__(256, 6) k_project(
                 // emit every quad that no later segment can touch: those before the quad holding
                 // the end of the last segment; keep the (<= 32) segments that reach into that quad
                 const int q_lim = (((s_re[n_seg - 1] - 1) >> 3) - R.W0) >> 2;
-                emit_quads(s_rs, s_re, s_dq, n_seg, q_next, q_lim, R, lane);
+                emit_quads(s_rs, s_re, s_dq, n_seg, q_next, q_lim, R, lane, s_low);
                 q_next = max(q_next, q_lim);
                 const int P = (R.W0 + 4 * q_lim) << 3;
                 const int s = n_seg - 32 + lane;
@@ -472,7 +514,7 @@ __global__ void __launch_bounds__(256, 6) k_project(
             carry_qp += __shfl_sync(0xffffffffu, qinc, 31);
         }
         overrun = __any_sync(0xffffffffu, overrun);
-        if (!overrun) emit_quads(s_rs, s_re, s_dq, n_seg, q_next, n_words >> 2, R, lane);
+        if (!overrun) emit_quads(s_rs, s_re, s_dq, n_seg, q_next, n_words >> 2, R, lane, s_low);
         __syncwarp();
         if (overrun && lane == 0) fuz_raise(st, FUZ_E_BADRECORD, r);
     }

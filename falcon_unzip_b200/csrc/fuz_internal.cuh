@@ -45,7 +45,7 @@ struct fuz_ctx {
     int pdl = 1;                       // programmatic dependent launch between the kernels of a call
     int fetch_ctas = FUZ_GRID_BLOCKS * 2;   // CTAs of k_fetch_records (fewer leave SM room for a second context that computes meanwhile)
     int rr_filter_only = 0;            // fuz_rr_track stops after the overlap filter
-    int project_ctas = 148 * 6;        // CTAs of k_project (persistent warps, records from a global cursor)
+    int project_ctas = 148 * 5;        // CTAs of k_project (persistent warps, records from a global cursor)
     int phase_staging = 0;             // 0 auto, 1 at most the sweep tier, 2 global memory only (tests)
     int sweep_passes = 64;             // parallel fixed-point passes of the pass-2 sweep before the sequential walk (0 = none)
     int64_t max_pairs_per_site = 96;

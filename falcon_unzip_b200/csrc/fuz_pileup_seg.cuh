@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) k_project_seg(const uint8_t *__restrict__
                                        m3 = swap_nibbles(__ldg(src + 3)), m4 = swap_nibbles(__ldg(src + 4));
                         uint32_t w0 = __funnelshift_r(m0, m1, sh), w1 = __funnelshift_r(m1, m2, sh),
                                  w2 = __funnelshift_r(m2, m3, sh), w3 = __funnelshift_r(m3, m4, sh);
-                        if ((bad_nibbles(w0) | bad_nibbles(w1) | bad_nibbles(w2) | bad_nibbles(w3)) & 0x01010101u) {   // ambiguity codes: rare
+                        if (ambiguous_nibbles(w0) | ambiguous_nibbles(w1) | ambiguous_nibbles(w2) | ambiguous_nibbles(w3)) {   // ambiguity codes: rare
                             w0 = keep_acgt(w0); w1 = keep_acgt(w1); w2 = keep_acgt(w2); w3 = keep_acgt(w3);
                         }
                         out4[q] = make_uint4(w0, w1, w2, w3);
@@ -912,10 +912,10 @@ __global__ void __launch_bounds__(FUZ_PILEUP_THREADS, 2) k_pileup_tma(const uint
                 const uint4 f = *fp;
                 *fp = make_uint4(0, 0, 0, 0);
                 x[s][0] |= f.x; x[s][1] |= f.y; x[s][2] |= f.z; x[s][3] |= f.w;
-                bad |= bad_nibbles(x[s][0]) | bad_nibbles(x[s][1]) | bad_nibbles(x[s][2]) | bad_nibbles(x[s][3]);
+                bad |= ambiguous_nibbles(x[s][0]) | ambiguous_nibbles(x[s][1]) | ambiguous_nibbles(x[s][2]) | ambiguous_nibbles(x[s][3]);
             }
             if (ovf) fast = false;
-            else if (bad & 0x01010101u) {                             // ambiguity codes never count (phasing.py:108-111)
+            else if (bad) {                                           // ambiguity codes never count (phasing.py:108-111)
 #pragma unroll
                 for (int s = 0; s < FUZ_G; s++)
 #pragma unroll
