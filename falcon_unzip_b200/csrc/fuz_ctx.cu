@@ -281,10 +281,14 @@ __global__ void __launch_bounds__(1024) k_scan_i32(const int32_t *__restrict__ i
 // waits for tiles that already run); a tile publishes its aggregate, then its inclusive prefix,
 // flag and value packed in one 64-bit word; warp 0 looks back 32 tiles at a time.
 #define FUZ_SCAN_TILE 4096
-__global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n,
-                                                    unsigned long long *state, unsigned int *counter, int fin_op, int64_t fin_cap,
-                                                    fuz_status *st) {
+__global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ in, int32_t *__restrict__ out, int64_t n_cap,
+                                                    const int64_t *__restrict__ d_n, unsigned long long *state, unsigned int *counter,
+                                                    int fin_op, int64_t fin_cap, fuz_status *st) {
     fuz_pdl_enter();
+    int64_t n = d_n ? *d_n : n_cap;                // a device-side length: the grid covers n_cap, tiles past n carry zeros
+    if (n > n_cap) n = n_cap;
+    if (n < 0) n = 0;
+    if (st && st->error) n = 0;
     __shared__ int s_tile;
     __shared__ int s_warp[32];
     __shared__ int s_prefix, s_agg;
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(1024) k_scan_wide(const int32_t *__restrict__ 
         if (i0 + 2 < n) out[i0 + 2] = excl + v.x + v.y;
         if (i0 + 3 < n) out[i0 + 3] = excl + v.x + v.y + v.z;
     }
-    if (tid == 0 && (int64_t)(tile + 1) * FUZ_SCAN_TILE >= n) {
+    if (tid == 0 && (int64_t)(tile + 1) * FUZ_SCAN_TILE >= n && ((int64_t)tile * FUZ_SCAN_TILE < n || tile == 0)) {
         out[n] = s_prefix + s_agg;
         fuz_scan_publish(st, fin_op, fin_cap, (long long)(s_prefix + s_agg));
     }
@@ -358,8 +362,8 @@ int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_ca
 
 // exclusive scan of n entries (host-known n), out[n] = total; uses the context's tile-state buffer:
 // main stream only, one scan at a time
-int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op, int64_t fin_cap) {
-    if (n <= 65536) return fuz_scan_i32(ctx, d_in, d_out, n, nullptr, fin_op, fin_cap);
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op, int64_t fin_cap, const int64_t *d_n) {
+    if (n <= 16384) return fuz_scan_i32(ctx, d_in, d_out, n, d_n, fin_op, fin_cap);
     const int64_t tiles = (n + FUZ_SCAN_TILE - 1) / FUZ_SCAN_TILE;
     const size_t need = 8 * (size_t)tiles + 64;
     if (need > ctx->scan_state_cap) {
@@ -371,8 +375,8 @@ int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t
     }
     FUZ_CUDA(ctx, cudaMemsetAsync(ctx->scan_state, 0, need, ctx->stream));
     unsigned long long *state = reinterpret_cast<unsigned long long *>(ctx->scan_state) + 1;
-    fuz_launch(ctx, k_scan_wide, (unsigned)tiles, 1024, 0, ctx->stream, d_in, d_out, n, state,
-               reinterpret_cast<unsigned int *>(ctx->scan_state), fin_op, fin_cap, fin_op ? ctx->d_status : (fuz_status *)nullptr);
+    fuz_launch(ctx, k_scan_wide, (unsigned)tiles, 1024, 0, ctx->stream, d_in, d_out, n, d_n, state,
+               reinterpret_cast<unsigned int *>(ctx->scan_state), fin_op, fin_cap, (fin_op || d_n) ? ctx->d_status : (fuz_status *)nullptr);
     FUZ_LAUNCH_CHECK(ctx, "k_scan_wide");
     return FUZ_OK;
 }

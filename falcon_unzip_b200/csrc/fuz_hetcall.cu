@@ -38,6 +38,10 @@ struct HetScratch {
 __device__ __forceinline__ bool op_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 
 // ---------------------------------------------------------------- init
+// first word (8 positions) of a record's projection row: the row starts on a 16-byte boundary of the GLOBAL word grid, so
+// that the part of a row inside a pileup tile is a 16-byte aligned run at a 16-byte aligned tile offset (bulk copies)
+__device__ __forceinline__ int fuz_row_w0(int gstart) { return (gstart >> 3) & ~3; }
+
 __global__ void k_het_init(fuz_status *st, int32_t *ctg_last_rec, int32_t *ctg_maxspan, int32_t *rec_cursor, int n_ctg) {   // rec_cursor[1] = tile cursor
     fuz_pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -349,7 +353,7 @@ __device__ __forceinline__ long long warp_sum48(long long v) {
 // Pass 2 (accepted records): walks the CIGAR 32 ops at a time (prefix positions by warp
 // scans), turns runs of adjacent M/=/X ops into match segments and writes the read
 // in REFERENCE coordinates, aligned to the global 8-position grid:
-// proj[r_woff[r] + w] holds positions ((gstart >> 3) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
+// proj[r_woff[r] + w] holds positions (fuz_row_w0(gstart) + w) * 8 .. +7 as 4-bit codes: A=1 C=2
 // G=4 T=8, 0 where the read shows no A/C/G/T (outside the alignment, deletions, N, ...).
 // Closed segments are appended to the warp's shared-memory list; the list is turned into
 // quads of the projection (emit_quads) when it fills up and at the end of the CIGAR.
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(256, FUZ_PROJ_MINB) k_project(
         const bool accept = (skip == 0 || !(1.0 - 1.0 * (double)skip / (double)total < 0.1)) && !(total < 2000);
         const int gstart = (int)gstart64;
         // words of the projection, padded to whole quads (128-bit flushes)
-        const int n_words = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
+        const int n_words = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - ((gstart64 >> 3) & ~3LL) + 4) & ~3LL) : 0;
         int woff = 0;
         if (lane == 0) {
             S.r_gstart[r] = gstart;
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(256, FUZ_PROJ_MINB) k_project(
             const uintptr_t sa = reinterpret_cast<uintptr_t>(rec_buf + seq_off);
             R.base4 = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
             R.nphase = (int)(sa & 3) * 2;
-            R.W0 = gstart >> 3;
+            R.W0 = fuz_row_w0(gstart);
             R.out = S.proj + woff;
             R.lim = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(rec_buf + off_n)) & ~(uintptr_t)3);
         }
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS, 5) k_pileup_gather(HetScrat
         int off = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < FUZ_NW; w++) { int v = s_warp_tot[w]; if (w < warp) off += v; tot += v; }
-        if (ok) l_ent[off + __popc(m & ((1u << lane) - 1u))] = make_int4(S.r_woff[r], S.r_gstart[r] >> 3, S.r_nwords[r], 0);
+        if (ok) l_ent[off + __popc(m & ((1u << lane) - 1u))] = make_int4(S.r_woff[r], fuz_row_w0(S.r_gstart[r]), S.r_nwords[r], 0);
         __syncthreads();
         n_reads_seen += tot;
         for (int g = 0; g < tot; g += 15) {
@@ -806,7 +810,7 @@ __global__ void __launch_bounds__(256) k_signature(
             int r = rb + lane;
             uint32_t nib = 0;
             if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp && S.r_gstart[r] <= gp) {
-                uint32_t w = S.proj[S.r_woff[r] + ((gp >> 3) - (S.r_gstart[r] >> 3))];
+                uint32_t w = S.proj[S.r_woff[r] + ((gp >> 3) - fuz_row_w0(S.r_gstart[r]))];
                 nib = (w >> (4 * (gp & 7))) & 15u;
             }
             uint32_t m0 = __ballot_sync(0xffffffffu, nib == code0);
@@ -844,7 +848,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
     // projection paths (pileup_impl 0, 1): one word per 8 aligned reference positions.  SEQ holds 2 bases per byte, so
     // rec_bytes / 4 words cover every M/=/X base; deletions add to the span and are checked on the device
     // (FUZ_E_CAPACITY, index 6).
-    const int64_t proj_cap = seg_path ? 0 : in->rec_bytes / 4 + 5 * (int64_t)n_rec + 64;
+    const int64_t proj_cap = seg_path ? 0 : in->rec_bytes / 4 + 8 * (int64_t)n_rec + 64;
     if (proj_cap > 0x7fffffffLL) return fuz_fail(ctx, FUZ_E_ARG, "batch too large: split it (projection exceeds 2^31 words)");
     // segment path (pileup_impl 2): a record with n CIGAR operations takes n / 2 + 1 segment slots; a read adds one
     // entry to every tile it overlaps.  Both are bounded by heuristics on the record bytes (a BAM record spends 1.5
@@ -997,10 +1001,10 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         fuz_launch(ctx, k_het_from_counts, n_tiles, FUZ_PTILE_THREADS, 0, st, S.counts, S, cap_sites, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_het_from_counts");
     }
-    if ((rc = fuz_scan_i32(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, nullptr, FUZ_FIN_SITES, cap_sites))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, S.tile_site_cnt, S.tile_site_off, n_tiles, FUZ_FIN_SITES, cap_sites))) return rc;
     fuz_launch(ctx, k_sites_place, FUZ_GRID_BLOCKS, 256, 0, st, S, in->d_ctg_goff, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_sites_place");
-    if ((rc = fuz_scan_i32(ctx, S.site_rows, S.site_row_off, cap_sites, &ctx->d_status->n_sites, FUZ_FIN_VMAP, out->cap_vmap))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, S.site_rows, S.site_row_off, cap_sites, FUZ_FIN_VMAP, out->cap_vmap, &ctx->d_status->n_sites))) return rc;
     if (ctx->join_pending) {                  // q_ids assigned on the side stream (fuz_phase_batch)
         FUZ_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         ctx->join_pending = false;

@@ -262,4 +262,5 @@ int fuz_scan_i32(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n_ca
                  const int64_t *d_n, int fin_op, int64_t fin_cap);
 // the same for a host-known n of millions of entries: multi-CTA single-pass scan (decoupled
 // look-back); main stream only
-int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op = FUZ_FIN_NONE, int64_t fin_cap = 0);
+int fuz_scan_i32_wide(fuz_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int fin_op = FUZ_FIN_NONE, int64_t fin_cap = 0,
+                      const int64_t *d_n = nullptr);   // d_n: device-side length <= n (n = capacity)

@@ -801,10 +801,10 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     }
     fuz_launch(ctx, k_uniq_lists, FUZ_GRID_BLOCKS, 256, 0, st, out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
-    if ((rc = fuz_scan_i32(ctx, A.cand_cnt, A.cand_off, cs, d_ns, FUZ_FIN_PAIRS, A.max_pairs))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, A.cand_cnt, A.cand_off, cs, FUZ_FIN_PAIRS, A.max_pairs, d_ns))) return rc;
     fuz_launch(ctx, k_pair_count, FUZ_GRID_BLOCKS, 256, 0, st, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
-    if ((rc = fuz_scan_i32(ctx, A.at_cnt, A.at_off, cs, d_ns, FUZ_FIN_ATABLE, out->cap_atable))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, A.at_cnt, A.at_off, cs, FUZ_FIN_ATABLE, out->cap_atable, d_ns))) return rc;
     fuz_launch(ctx, k_pair_fill, FUZ_GRID_BLOCKS, 256, 0, st, A, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_fill");
     return FUZ_OK;
@@ -844,7 +844,7 @@ int fuz_blocks_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool at_off_v
     FUZ_LAUNCH_CHECK(ctx, "k_blk_init");
     fuz_launch(ctx, k_edge_count, FUZ_GRID_BLOCKS, 256, 0, st, B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_count");
-    if ((rc = fuz_scan_i32(ctx, B.left_cnt, B.left_off, cs, &ctx->d_status->n_sites, FUZ_FIN_NONE, 0))) return rc;
+    if ((rc = fuz_scan_i32_wide(ctx, B.left_cnt, B.left_off, cs, FUZ_FIN_NONE, 0, &ctx->d_status->n_sites))) return rc;
     fuz_launch(ctx, k_edge_fill, FUZ_GRID_BLOCKS, 256, 0, st, B, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_edge_fill");
     fuz_launch(ctx, k_ctg_phase, n_ctg, FUZ_PHASE_THREADS, FUZ_PHASE_SMEM, st, B, *out, ctx->d_status);

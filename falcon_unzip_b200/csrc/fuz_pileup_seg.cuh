@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) k_segments(
         }
         // the words of the reference-aligned projection (k_project_seg): whole quads, one atomic per warp
         if (S.proj_cap > 0) {
-            const int nw = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - (gstart64 >> 3) + 4) & ~3LL) : 0;
+            const int nw = (accept && span > 0) ? (int)((((gstart64 + span - 1) >> 3) - ((gstart64 >> 3) & ~3LL) + 4) & ~3LL) : 0;
             const int incl_w = fuz_warp_incl_scan(nw, lane);
             const int tot_w = __shfl_sync(0xffffffffu, incl_w, 31);
             long long pbase = 0;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_project_seg(const uint8_t *__restrict__
             const uintptr_t sa = reinterpret_cast<uintptr_t>(rec_buf + S.r_seq[r]);
             R.base4 = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
             R.nphase = (int)(sa & 3) * 2;
-            R.W0 = S.r_gstart[r] >> 3;
+            R.W0 = fuz_row_w0(S.r_gstart[r]);
             R.out = S.proj + S.r_woff[r];
         }
         auto quad_of = [&](int pos) { return ((pos >> 3) - R.W0) >> 2; };
@@ -408,11 +408,11 @@ __device__ __forceinline__ void fuz_consumer_sync() {
 // every read from shared memory and feed the carry-save tree.  The dependent chain of the plain kernel (tile range ->
 // record fields -> compaction -> loads, 3.3 waves of short-lived CTAs) is what kept it at 3.5 TB/s.
 #define FUZ_GG 15                   // reads per stage = inputs of one carry-save tree
-#define FUZ_GSLOT 264               // words per read slot: 256 + alignment slack at both ends
+#define FUZ_GSLOT 256               // words per read slot = words of a tile: tile word j of the read sits at slot[j]
 #define FUZ_GSTAGES 4
 struct __align__(16) FuzGStage {
     uint32_t slot[FUZ_GG][FUZ_GSLOT];
-    int4 ent[FUZ_GG];               // x = first tile word of the read, y = one past its last, z = slot index of tile word 0
+    int2 ent[FUZ_GG + 1];           // x = first tile word of the read, y = its words inside the tile (0: empty slot)
     int32_t n, tile, last, pad;
 };
 
@@ -479,17 +479,17 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS + 32, 3) k_pileup_gather_tma
             {
                 const int t0 = tile * FUZ_PTILE, t1 = t0 + FUZ_PTILE, Wt0 = t0 >> 3;
                 const bool ok = cur.fl && cur.ge > t0 && cur.gs < t1;                      // (fl == 0 outside the range)
-                int4 e = make_int4(0, 0, 0, 0);
+                int2 e = make_int2(0, 0);
                 const uint32_t *src = nullptr;
                 uint32_t bytes = 0;
                 if (ok) {
-                    const int W0 = cur.gs >> 3;
+                    // rows start on 4-word boundaries of the global grid (fuz_row_w0) and are whole quads long: the part of
+                    // the row inside the tile is a 16-byte aligned run, copied to its place in the slot
+                    const int W0 = fuz_row_w0(cur.gs);
                     const int lo = max(W0, Wt0) - Wt0, hi = min(W0 + cur.nw, Wt0 + FUZ_PTILE / 8) - Wt0;
-                    const int64_t s0 = (int64_t)cur.wo + (Wt0 + lo - W0);
-                    const int pre = (int)(s0 & 3);
-                    src = S.proj + (s0 - pre);
-                    bytes = 4u * (uint32_t)((pre + (hi - lo) + 3) & ~3);
-                    e = make_int4(lo, hi, pre - lo, 0);
+                    src = S.proj + ((int64_t)cur.wo + (Wt0 + lo - W0));
+                    bytes = 4u * (uint32_t)(hi - lo);
+                    e = make_int2(lo, hi - lo);
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, ok);
                 do {
@@ -505,13 +505,14 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS + 32, 3) k_pileup_gather_tma
                     __syncwarp();
                     if (mine) {
                         sg.ent[fill + my] = e;
-                        fuz_bulk_g2s(fuz_smem_u32(&sg.slot[fill + my][0]), src, bytes, full);
+                        fuz_bulk_g2s(fuz_smem_u32(&sg.slot[fill + my][e.x]), src, bytes, full);
                     }
                     m &= ~__ballot_sync(0xffffffffu, mine);
                     fill += take;
                     const bool tile_done = last_round && m == 0;
                     if (fill == FUZ_GG || tile_done) {                // post the stage
                         if (lane == 0) { sg.n = end ? -1 : fill; sg.tile = tile; sg.last = tile_done; }
+                        if (lane >= fill && lane <= FUZ_GG) sg.ent[lane] = make_int2(0, 0);      // empty slots contribute nothing
                         __syncwarp();
                         if (lane == 0) fuz_mbar_arrive(full);
                         fill = 0; open = false;
@@ -538,14 +539,16 @@ __global__ void __launch_bounds__(FUZ_PTILE_THREADS + 32, 3) k_pileup_gather_tma
         fuz_mbar_wait(fuz_smem_u32(&bars[stage]), phase);
         const int n = sg.n, tile = sg.tile, last = sg.last;
         if (n < 0) break;
+        // branch free: every slot is read (tile word j of a read sits at slot[j]); what lies outside the read's words in
+        // this tile -- and every empty slot -- is masked with the entry (two entries per 128-bit load)
         uint32_t x[FUZ_GG];
 #pragma unroll
-        for (int s = 0; s < FUZ_GG; s++) {
-            x[s] = 0;
-            if (s < n) {
-                const int4 e = sg.ent[s];
-                if (tid >= e.x && tid < e.y) x[s] = sg.slot[s][tid + e.z];
-            }
+        for (int s = 0; s < FUZ_GG; s++) x[s] = sg.slot[s][tid];
+#pragma unroll
+        for (int s2 = 0; s2 < FUZ_GG + 1; s2 += 2) {
+            const int4 e = *reinterpret_cast<const int4 *>(&sg.ent[s2]);
+            if ((unsigned)(tid - e.x) >= (unsigned)e.y) x[s2] = 0;
+            if (s2 + 1 < FUZ_GG && (unsigned)(tid - e.z) >= (unsigned)e.w) x[s2 + 1] = 0;
         }
         __syncwarp();
         if (lane == 0) fuz_mbar_arrive(fuz_smem_u32(&bars[FUZ_GSTAGES + stage]));
