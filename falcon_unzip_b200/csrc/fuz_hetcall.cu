@@ -1013,7 +1013,7 @@ int fuz_het_call_impl(fuz_ctx *ctx, const fuz_batch *in, fuz_outputs *out) {
         fuz_launch(ctx, k_signature_seg, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_buf, in->d_rec_qid, S, *out, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_signature_seg");
     } else {
-        fuz_launch(ctx, k_signature, FUZ_GRID_BLOCKS, 256, 0, st, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
+        fuz_launch(ctx, k_signature, 148 * ctx->grid_sig, 256, 0, st, in->d_rec_qid, in->d_ctg_rec_off, S, *out, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_signature");
     }
     return FUZ_OK;

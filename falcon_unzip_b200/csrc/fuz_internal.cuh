@@ -55,6 +55,7 @@ struct fuz_ctx {
     bool phase_attr_set = false;
     bool pileup_attr_set = false;
     bool gather_attr_set = false;
+    int grid_sig = 8, grid_assoc = 6, grid_reads = 8;   // CTAs per SM of the latency-bound grid-stride kernels (k_signature / association / read stage): measured against 4
     int gather_tma = 1;                // pileup_impl 0: TMA-fed persistent gather (1) or the plain tile-per-CTA kernel (0)
     int pileup_debug = 0;
     uint32_t *trace = nullptr;         // host-mapped progress markers (debugging)

@@ -56,8 +56,11 @@ struct AssocScratch {
     const int32_t *site_ctg, *site_pos;
     int4 *pair_ct;
     uint8_t *dup;
+    uint32_t *qmask;                 // per site 2 x FUZ_QM_WORDS words: the q_id set of each allele as bits over [qmin & ~31, +544)
+    uint8_t *has_mask;               // 1: qmask[s] is valid (q_id range of the site <= FUZ_UQ_RANGE)
     int64_t max_pairs;
 };
+#define FUZ_QM_WORDS 17              // 512 q_ids from an anchor rounded down to 32
 
 // sorted unique q_id lists per (site, allele): uq[row_off[s] ..) for allele al0 and
 // uq[row_off[s] + na0[s] ..) for allele al1, lengths uq_n[2s], uq_n[2s+1]; duplicate flags
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
         mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
         bad = __any_sync(0xffffffffu, bad);
         if (bad || c0 == 0 || c0 == n) {          // a site must carry exactly two alleles
-            if (lane == 0) { fuz_raise(st, FUZ_E_FORMAT, s); A.cand_cnt[s] = 0; }
+            if (lane == 0) { fuz_raise(st, FUZ_E_FORMAT, s); A.cand_cnt[s] = 0; A.has_mask[s] = 0; }
             continue;
         }
         int u0 = 0, u1 = 0;
@@ -107,13 +110,24 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
             __syncwarp();
             for (int i = lane; i < n; i += 32)
                 A.dup[off + i] = (vm_base[off + i] == al0 ? f0 : f1)[vm_qid[off + i] - mn] != i;
-            for (int base = 0; base < range; base += 32) {
-                const int x = base + lane;
-                const bool p0 = x < range && f0[x] != 0x7fffffff, p1 = x < range && f1[x] != 0x7fffffff;
+            // in q_id order, 32 q_ids per round from the anchor qmin & ~31: the ballots are the words of the site's q_id masks
+            // (k_pair_count intersects two sites by AND + POPC of such words: the anchors differ by whole words)
+            const int sh = mn & 31;
+            uint32_t w0 = 0, w1 = 0;                      // lane w keeps word w
+#pragma unroll 1
+            for (int w = 0; 32 * w < sh + (int)range; w++) {                   // (the words beyond stay 0)
+                const int x = 32 * w + lane - sh;
+                const bool in = x >= 0 && x < range;
+                const bool p0 = in && f0[x] != 0x7fffffff, p1 = in && f1[x] != 0x7fffffff;
                 const uint32_t m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
                 if (p0) A.uq[off + u0 + __popc(m0 & lt)] = mn + x;
                 if (p1) A.uq[off + c0 + u1 + __popc(m1 & lt)] = mn + x;
                 u0 += __popc(m0); u1 += __popc(m1);
+                if (lane == w) { w0 = m0; w1 = m1; }
+            }
+            if (lane < FUZ_QM_WORDS) {
+                A.qmask[(size_t)s * 2 * FUZ_QM_WORDS + lane] = w0;
+                A.qmask[(size_t)s * 2 * FUZ_QM_WORDS + FUZ_QM_WORDS + lane] = w1;
             }
         } else {
             // all-pairs: duplicate flag, then the slot of every first occurrence in its sorted unique list
@@ -139,6 +153,7 @@ __global__ void __launch_bounds__(256) k_uniq_lists(const uint8_t *__restrict__ 
         }
         if (lane == 0) {
             A.na0[s] = c0; A.uq_n[2 * s] = u0; A.uq_n[2 * s + 1] = u1; A.qmin[s] = mn; A.qmax[s] = mx;
+            A.has_mask[s] = range <= FUZ_UQ_RANGE ? 1 : 0;
             // number of later sites of the same contig within 65536 bp (phasing.py:166-170)
             const int c = A.site_ctg[s];
             const long long lim = (long long)A.site_pos[s] + (1 << 16);
@@ -164,14 +179,13 @@ __device__ __forceinline__ int sorted_intersect(const int32_t *__restrict__ a, i
 
 // One warp per left site, one lane per candidate partner: 2x2 set-intersection sizes
 // (phasing.py:187-191), kept for the fill pass; emitted rows are capped at 501 per left
-// site AFTER the total >= 6 filter (phasing.py:192-206).  The two q_id sets of the left site
-// become bit masks over its (small) q_id range in shared memory; every lane then tests the
-// q_ids of its partner against them.  Left sites with a wide q_id range merge sorted lists.
-#define FUZ_PAIR_WORDS 16            // 512-bit masks
+// site AFTER the total >= 6 filter (phasing.py:192-206).  The two q_id sets of every site are bit masks
+// over its (small) q_id range (k_uniq_lists); the left site's sit in shared memory and a pair is 4 x (AND, POPC)
+// per word both sites cover.  A partner without masks is tested q_id by q_id, a left site without merges sorted lists.
 __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *st) {
     fuz_pdl_enter();
     if (st->error) return;
-    __shared__ uint32_t s_mask[8][2][FUZ_PAIR_WORDS];
+    __shared__ uint32_t s_mask[8][2][FUZ_QM_WORDS + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_sites = (int)st->n_sites;
@@ -182,13 +196,14 @@ __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *
         const int o1 = A.row_off[i1], n10 = A.uq_n[2 * i1], n11 = A.uq_n[2 * i1 + 1];
         const int32_t *a0 = A.uq + o1, *a1 = A.uq + o1 + A.na0[i1];
         const int mn1 = A.qmin[i1], mx1 = A.qmax[i1];
-        const bool masked = (long long)mx1 - mn1 < 32 * FUZ_PAIR_WORDS;
+        const int anc1 = mn1 & ~31;
+        const bool masked = A.has_mask[i1] != 0;
         __syncwarp();
-        if (masked && nc > 0) {
-            if (lane < FUZ_PAIR_WORDS) { m0[lane] = 0; m1[lane] = 0; }
-            __syncwarp();
-            for (int e = lane; e < n10; e += 32) { int x = a0[e] - mn1; atomicOr(&m0[x >> 5], 1u << (x & 31)); }
-            for (int e = lane; e < n11; e += 32) { int x = a1[e] - mn1; atomicOr(&m1[x >> 5], 1u << (x & 31)); }
+        if (masked && nc > 0) {                             // the q_id masks of the left site: k_uniq_lists built them
+            if (lane < FUZ_QM_WORDS) {
+                m0[lane] = A.qmask[(size_t)i1 * 2 * FUZ_QM_WORDS + lane];
+                m1[lane] = A.qmask[(size_t)i1 * 2 * FUZ_QM_WORDS + FUZ_QM_WORDS + lane];
+            }
             __syncwarp();
         }
         int emitted = 0;
@@ -198,23 +213,35 @@ __global__ void __launch_bounds__(256) k_pair_count(AssocScratch A, fuz_status *
             int4 ct = make_int4(0, 0, 0, 0);
             if (valid) {
                 const int i2 = i1 + 1 + k;
-                if (A.qmin[i2] <= mx1 && mn1 <= A.qmax[i2]) {     // q_id ranges overlap
-                    const int o2 = A.row_off[i2], n20 = A.uq_n[2 * i2], n21 = A.uq_n[2 * i2 + 1];
-                    const int32_t *b0 = A.uq + o2, *b1 = A.uq + o2 + A.na0[i2];
-                    if (masked) {
-                        for (int e = 0; e < n20; e++) {
-                            const unsigned x = (unsigned)(b0[e] - mn1);
-                            if (x < 32u * FUZ_PAIR_WORDS) { ct.x += (m0[x >> 5] >> (x & 31)) & 1u; ct.z += (m1[x >> 5] >> (x & 31)) & 1u; }
-                        }
-                        for (int e = 0; e < n21; e++) {
-                            const unsigned x = (unsigned)(b1[e] - mn1);
-                            if (x < 32u * FUZ_PAIR_WORDS) { ct.y += (m0[x >> 5] >> (x & 31)) & 1u; ct.w += (m1[x >> 5] >> (x & 31)) & 1u; }
+                const int mn2 = A.qmin[i2];
+                if (mn2 <= mx1 && mn1 <= A.qmax[i2]) {             // q_id ranges overlap
+                    if (masked && A.has_mask[i2]) {
+                        // both sites as masks: the anchors are multiples of 32, so the words line up; only the words both cover
+                        const uint32_t *b0 = A.qmask + (size_t)i2 * 2 * FUZ_QM_WORDS, *b1 = b0 + FUZ_QM_WORDS;
+                        const int dw = ((mn2 & ~31) - anc1) >> 5;            // word of the left mask under word 0 of the right one
+                        const int w_lo = max(0, -dw), w_hi = min(FUZ_QM_WORDS, FUZ_QM_WORDS - dw);
+                        for (int w = w_lo; w < w_hi; w++) {
+                            const uint32_t x0 = b0[w], x1 = b1[w], l0 = m0[w + dw], l1 = m1[w + dw];
+                            ct.x += __popc(l0 & x0); ct.y += __popc(l0 & x1); ct.z += __popc(l1 & x0); ct.w += __popc(l1 & x1);
                         }
                     } else {
-                        ct.x = sorted_intersect(a0, n10, b0, n20);
-                        ct.y = sorted_intersect(a0, n10, b1, n21);
-                        ct.z = sorted_intersect(a1, n11, b0, n20);
-                        ct.w = sorted_intersect(a1, n11, b1, n21);
+                        const int o2 = A.row_off[i2], n20 = A.uq_n[2 * i2], n21 = A.uq_n[2 * i2 + 1];
+                        const int32_t *b0 = A.uq + o2, *b1 = A.uq + o2 + A.na0[i2];
+                        if (masked) {
+                            for (int e = 0; e < n20; e++) {
+                                const unsigned x = (unsigned)(b0[e] - anc1);
+                                if (x < 32u * FUZ_QM_WORDS) { ct.x += (m0[x >> 5] >> (x & 31)) & 1u; ct.z += (m1[x >> 5] >> (x & 31)) & 1u; }
+                            }
+                            for (int e = 0; e < n21; e++) {
+                                const unsigned x = (unsigned)(b1[e] - anc1);
+                                if (x < 32u * FUZ_QM_WORDS) { ct.y += (m0[x >> 5] >> (x & 31)) & 1u; ct.w += (m1[x >> 5] >> (x & 31)) & 1u; }
+                            }
+                        } else {
+                            ct.x = sorted_intersect(a0, n10, b0, n20);
+                            ct.y = sorted_intersect(a0, n10, b1, n21);
+                            ct.z = sorted_intersect(a1, n11, b0, n20);
+                            ct.w = sorted_intersect(a1, n11, b1, n21);
+                        }
                     }
                 }
                 A.pair_ct[base + k] = ct;
@@ -784,6 +811,7 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     size_t o_cc = L.add(4 * (size_t)(cs + 2)), o_co = L.add(4 * (size_t)(cs + 2));
     size_t o_ac = L.add(4 * (size_t)(cs + 2)), o_ao = L.add(4 * (size_t)(cs + 2));
     size_t o_pc = L.add(16 * (size_t)(A.max_pairs + 1));
+    size_t o_qm = L.add(4 * 2 * FUZ_QM_WORDS * (size_t)(cs + 1)), o_hm = L.add((size_t)cs + 1);
     int rc = fuz_arena_commit(ctx, L);
     if (rc) return rc;
     if ((rc = fuz_keep_commit(ctx, cs, cv, &A.row_off, &A.dup, &A.at_off))) return rc;   // at_off = row range per left site, reused by the block stage
@@ -793,19 +821,20 @@ int fuz_association_impl(fuz_ctx *ctx, int32_t n_ctg, fuz_outputs *out, bool row
     A.cand_cnt = fuz_at<int32_t>(ctx, o_cc); A.cand_off = fuz_at<int32_t>(ctx, o_co);
     A.at_cnt = fuz_at<int32_t>(ctx, o_ac); (void)o_ao;
     A.pair_ct = fuz_at<int4>(ctx, o_pc);
+    A.qmask = fuz_at<uint32_t>(ctx, o_qm); A.has_mask = fuz_at<uint8_t>(ctx, o_hm);
     const int64_t *d_ns = &ctx->d_status->n_sites;
 
     if (!row_off_valid) {
         fuz_launch(ctx, k_site_rowoff, FUZ_GRID_BLOCKS, 256, 0, st, out->d_vm_site, A.row_off, ctx->d_status);
         FUZ_LAUNCH_CHECK(ctx, "k_site_rowoff");
     }
-    fuz_launch(ctx, k_uniq_lists, FUZ_GRID_BLOCKS, 256, 0, st, out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
+    fuz_launch(ctx, k_uniq_lists, 148 * ctx->grid_assoc, 256, 0, st, out->d_site_al, out->d_vm_base, out->d_vm_qid, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_uniq_lists");
     if ((rc = fuz_scan_i32_wide(ctx, A.cand_cnt, A.cand_off, cs, FUZ_FIN_PAIRS, A.max_pairs, d_ns))) return rc;
-    fuz_launch(ctx, k_pair_count, FUZ_GRID_BLOCKS, 256, 0, st, A, ctx->d_status);
+    fuz_launch(ctx, k_pair_count, 148 * ctx->grid_assoc, 256, 0, st, A, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_count");
     if ((rc = fuz_scan_i32_wide(ctx, A.at_cnt, A.at_off, cs, FUZ_FIN_ATABLE, out->cap_atable, d_ns))) return rc;
-    fuz_launch(ctx, k_pair_fill, FUZ_GRID_BLOCKS, 256, 0, st, A, *out, ctx->d_status);
+    fuz_launch(ctx, k_pair_fill, 148 * ctx->grid_assoc, 256, 0, st, A, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_pair_fill");
     return FUZ_OK;
 }
@@ -902,10 +931,10 @@ int fuz_reads_csr(fuz_ctx *ctx, int32_t n_ctg, const int32_t *d_ctg_nq, int64_t 
     }
     fuz_launch(ctx, k_rd_init, FUZ_GRID_BLOCKS, 256, 0, st, R);
     FUZ_LAUNCH_CHECK(ctx, "k_rd_init");
-    fuz_launch(ctx, k_q_count, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
+    fuz_launch(ctx, k_q_count, 148 * ctx->grid_reads, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_count");
     if ((rc = fuz_scan_i32(ctx, R.q_cnt, R.q_off, total_nq, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    fuz_launch(ctx, k_q_fill, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
+    fuz_launch(ctx, k_q_fill, 148 * ctx->grid_reads, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_fill");
     return FUZ_OK;
 }
@@ -915,12 +944,12 @@ int fuz_reads_vote(fuz_ctx *ctx, int32_t n_ctg, int64_t total_nq, fuz_outputs *o
     ReadScratch R;
     int rc = reads_scratch(ctx, n_ctg, total_nq, out, R);
     if (rc) return rc;
-    fuz_launch(ctx, k_q_pack, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, ctx->d_status);
+    fuz_launch(ctx, k_q_pack, 148 * ctx->grid_reads, 256, 0, st, R, *out, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_q_pack");
-    fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
+    fuz_launch(ctx, k_vote, 148 * ctx->grid_reads, 256, 0, st, R, *out, n_ctg, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(count)");
     if ((rc = fuz_scan_i32_wide(ctx, R.pr_cnt, R.pr_off, total_nq, FUZ_FIN_READS, out->cap_reads))) return rc;
-    fuz_launch(ctx, k_vote, FUZ_GRID_BLOCKS, 256, 0, st, R, *out, n_ctg, 1, ctx->d_status);
+    fuz_launch(ctx, k_vote, 148 * ctx->grid_reads, 256, 0, st, R, *out, n_ctg, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_vote(fill)");
     return FUZ_OK;
 }
