@@ -489,7 +489,11 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     int *s_lq = s_pk + n_e + (n + 3) / 4 + 1 + n, *s_ld = s_lq + n_e;   // [n_e] partner (contig-local), cis - trans
     int *s_roff = s_ld + n_e;                                 // [n + 1] right row offsets (relative to r0)
     int *s_rq = s_roff + n + 1, *s_rd = s_rq + n_r;           // [n_r] partner (contig-local), cis - trans (0: rejected row)
-    int *s_pos = s_rd + n_r;                                  // [n] 1-based positions
+    // [n] 1-based positions: with the rest of tier "full", else right behind the sweep tier / the phase bits when that fits (pass 3
+    // looks up the position of every cis partner: from global memory that is a second dependent load per edge)
+    const size_t pos_at = staged ? 0 : (sweep_staged ? need_sweep : (size_t)nbw);
+    const bool pos_staged = staged || (pos_at + (size_t)n) * 4 <= FUZ_PHASE_SMEM;
+    int *s_pos = staged ? s_rd + n_r : reinterpret_cast<int *>(smem + pos_at);
     int *s_sc = s_pos + n;                                    // [4n] lscore, rscore, lext, rext of pass 3
     if (B.dbg && tid == 0) B.dbg[c * 16 + 0] = clock64();
     for (int w = tid; w < nbw; w += nt) sbits[w] = 0;
@@ -503,6 +507,8 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
             s_rq[k] = O.d_at_s2[r0 + k] - cs0; s_rd[k] = abs(d) >= 6 ? d : 0;
         }
         for (int i = tid; i < n; i += nt) s_pos[i] = O.d_site_pos[cs0 + i];
+    } else if (pos_staged) {
+        for (int i = tid; i < n; i += nt) s_pos[i] = O.d_site_pos[cs0 + i];
     }
     __syncthreads();
     // accessors (contig-local indices)
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     auto roff = [&](int i) { return staged ? s_roff[i] : B.right_off[cs0 + i] - r0; };
     auto rq = [&](int k) { return staged ? s_rq[k] : O.d_at_s2[r0 + k] - cs0; };
     auto rd = [&](int k) { if (staged) return s_rd[k]; int d = row_d(O.d_at_ct, r0 + k); return abs(d) >= 6 ? d : 0; };
-    auto pos_of = [&](int i) { return staged ? s_pos[i] : O.d_site_pos[cs0 + i]; };
+    auto pos_of = [&](int i) { return pos_staged ? s_pos[i] : O.d_site_pos[cs0 + i]; };
     volatile uint32_t *fp = sweep_staged ? s_fp : reinterpret_cast<volatile uint32_t *>(B.fp + cs0);
     // smallest left partner of site i (slot in the left list), -1 if none
     auto min_left = [&](int i, int &d_out) {
@@ -617,22 +623,30 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
     }
     __syncthreads();
     if (B.dbg && tid == 0) B.dbg[c * 16 + 4] = clock64();
-    // ---- pass 3: scores and extents, one thread per site (positions = 1-based file positions)
-    for (int i = tid; i < n; i += nt) {
+    // ---- pass 3: scores and extents, eight lanes per site, each over every eighth edge (positions = 1-based file positions);
+    //      sums, min and max are exact in any order.  One thread per site walked ~120 edges serially (half of the kernel's time
+    //      at 2 Mb contigs); a whole warp per site leaves too few independent chains of loads in flight (measured: 2x slower).
+    for (int i0 = 0; i0 < n; i0 += nt >> 3) {
+        const int i = i0 + (tid >> 3), sub = tid & 7;
+        const bool live = i < n;
         const int x = cs0 + i;
-        const bool in_pos = sweep_staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255;
-        const int px = pos_of(i);
+        const bool in_pos = live && (sweep_staged ? (s_slow[i] & 2) != 0 : O.d_ph_state[x] != 255);
+        const int px = live ? pos_of(i) : 0;
         int lscore = 0, rscore = 0, lext = px, rext = px;
+        uint32_t sx = 0;
         if (in_pos) {
-            const uint32_t sx = (sbits[i >> 5] >> (i & 31)) & 1u;
-            for (int k = loff(i); k < loff(i + 1); k++) {
+            sx = (sbits[i >> 5] >> (i & 31)) & 1u;
+            const int l_end = loff(i + 1), r_end = roff(i + 1);
+#pragma unroll 4
+            for (int k = loff(i) + sub; k < l_end; k += 8) {
                 const int q = lq(k), d = ld(k);
                 const uint32_t sq = (sbits[q >> 5] >> (q & 31)) & 1u;
                 const int dd = sq == sx ? d : -d;
                 lscore += dd;
                 if (dd > 0) lext = min(lext, pos_of(q));
             }
-            for (int k = roff(i); k < roff(i + 1); k++) {
+#pragma unroll 4
+            for (int k = roff(i) + sub; k < r_end; k += 8) {
                 const int d = rd(k);
                 if (d == 0) continue;
                 const int q = rq(k);
@@ -641,10 +655,18 @@ __global__ void __launch_bounds__(FUZ_PHASE_THREADS) k_ctg_phase(BlockScratch B,
                 rscore += dd;
                 if (dd > 0) rext = max(rext, pos_of(q));
             }
-            O.d_ph_state[x] = (uint8_t)sx;
         }
-        O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
-        if (staged) { s_sc[4 * i] = lscore; s_sc[4 * i + 1] = rscore; s_sc[4 * i + 2] = lext; s_sc[4 * i + 3] = rext; }
+        __syncwarp();
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {                   // butterflies inside the group of eight lanes
+            lscore += __shfl_xor_sync(0xffffffffu, lscore, d); rscore += __shfl_xor_sync(0xffffffffu, rscore, d);
+            lext = min(lext, __shfl_xor_sync(0xffffffffu, lext, d)); rext = max(rext, __shfl_xor_sync(0xffffffffu, rext, d));
+        }
+        if (live && sub == 0) {
+            if (in_pos) O.d_ph_state[x] = (uint8_t)sx;
+            O.d_ph_lscore[x] = lscore; O.d_ph_rscore[x] = rscore; O.d_ph_lext[x] = lext; O.d_ph_rext[x] = rext;
+            if (staged) { s_sc[4 * i] = lscore; s_sc[4 * i + 1] = rscore; s_sc[4 * i + 2] = lext; s_sc[4 * i + 3] = rext; }
+        }
     }
     __syncthreads();
     // ---- pass 4: chain sites into blocks by the running maximum of right extents (never reset)
