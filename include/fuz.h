@@ -162,6 +162,11 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *                          1 = at most the sweep tier, 2 = global memory only (both for tests),
  *          "fetch_ctas" CTAs of the selective record fetch of fuz_phase_batch_host (default 1184; two contexts that
  *                       alternate over the batches of a list use fewer, so that one computes while the other fetches),
+ *          "gather_tma" 1 = the register pileup of pileup_impl 0 / 3 is fed by bulk async copies of the projection rows into a
+ *                       shared-memory ring (persistent producer / consumer kernel, default), 0 = one CTA per tile with plain loads,
+ *          "project_ctas" grid of the projection kernel (default 148 * 5, the CTAs per SM its registers allow),
+ *          "grid_sig" / "grid_assoc" / "grid_reads" CTAs per SM (1 .. 8) of the grid-stride kernels of the signature, the
+ *                       association and the read stage (defaults 8 / 6 / 8: they are latency bound),
  *          "sweep_passes" passes of the parallel fixed-point form of the pass-2 sweep (phasing.py:311-344) before
  *                         the sequential walk takes over (default 64; 0 = sequential only; same result either way),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */

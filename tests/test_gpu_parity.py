@@ -121,6 +121,29 @@ def test_segment_tma_pileup_files_match_oracle(eng, cfg, tmp_path):
     _assert_same_files(_oracle_files(sset, tmp_path / "oracle"), got)
 
 
+@pytest.mark.parametrize("opts", [dict(gather_tma=0), dict(grid_sig=4, grid_assoc=4, grid_reads=4), dict(grid_sig=1, grid_assoc=1, grid_reads=1),
+                                  dict(project_ctas=37), dict(sweep_passes=0)])
+@pytest.mark.parametrize("cfg", ["quirks", "c5_slice"])
+def test_launch_options_do_not_change_the_files(eng, cfg, opts, tmp_path):
+    """The tuning options of the default path (the plain tile-per-CTA gather instead of the TMA-fed one, the CTAs per SM of
+    the grid-stride kernels, the grid of k_project, the sequential sweep) change launch shapes only: same six files."""
+    import dataclasses
+    from falcon_unzip_b200 import phasing, synth
+    if cfg == "c5_slice":
+        sset = synth.generate(dataclasses.replace(synth.CONFIGS["c5"], n_contigs=2, contig_len=150_000))
+    else:
+        sset = synth_set(cfg)
+    defaults = dict(gather_tma=1, grid_sig=8, grid_assoc=6, grid_reads=8, project_ctas=148 * 5, sweep_passes=64)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    try:
+        _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs, str(tmp_path / "gpu"))
+    finally:
+        for k in opts:
+            eng.set_option(k, defaults[k])
+    _assert_same_files(_oracle_files(sset, tmp_path / "oracle"), got)
+
+
 def test_reference_cli_per_stage_files_match_oracle(eng, tmp_path):
     """fc_phasing-style run: BAM + FASTA on disk, the four stage functions chained through
     files exactly like reference phasing.py:482-553."""
