@@ -155,6 +155,12 @@ SYMBOLS = [
                                            C.c_char_p, C.c_int64]),
     ("fuz_host_format_phased_reads", C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_int64, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]),
+    ("fuz_host_format_phased_reads_rows", C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_int64, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int64]),
+    ("fuz_host_format_q_id_map_rows", C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int64]),
+    ("fuz_host_format_variant_pos", C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64]),
+    ("fuz_host_format_phased_variants", C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64]),
     ("fuz_host_py27_str_dict_order", C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fuz_host_rr_bread_order", C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fuz_host_rr_format_rows", C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,

@@ -419,3 +419,25 @@ def read_fasta(path: str) -> Iterator[Tuple[str, str]]:
     for rec in ("\n" + text).split("\n>")[1:]:
         header, _, body = rec.partition("\n")
         yield header.rstrip("\r\n"), "".join(map(str.strip, body.split("\n")))
+
+
+def read_fasta_bytes(path: str) -> Iterator[Tuple[str, bytes]]:
+    """read_fasta with the sequences as bytes (no text decoding of megabases): same record and line rules."""
+    with open(path, "rb") as f:
+        data = f.read()
+    # a record starts at a '>' that opens a line
+    starts = [0] if data[:1] == b">" else []
+    p = data.find(b"\n>")
+    while p >= 0:
+        starts.append(p + 1)
+        p = data.find(b"\n>", p + 1)
+    starts.append(len(data) + 1)
+    for a, b in zip(starts[:-1], starts[1:]):
+        nl = data.find(b"\n", a, b - 1)
+        if nl < 0:
+            yield data[a + 1:b - 1].rstrip(b"\r\n").decode("latin-1"), b""
+            continue
+        header = data[a + 1:nl].rstrip(b"\r\n").decode("latin-1")
+        body = data[nl + 1:b - 1]
+        # one sequence line per record (how assemblers write contigs) needs no split / join
+        yield header, (body.strip() if body.find(b"\n") < 0 else b"".join(map(bytes.strip, body.split(b"\n"))))

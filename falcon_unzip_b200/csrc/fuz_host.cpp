@@ -586,11 +586,11 @@ extern "C" int64_t fuz_host_format_atable(const int32_t *site_pos, const uint8_t
 // appearance in variant_map.  vm_qid: the contig's variant_map rows; pr_*: the contig's
 // phased_reads rows, sorted by q_id; names: blob / offsets of the QNAME of every q_id.  Returns the size of the
 // text (call with out = NULL first), -1 if cap is too small or a q_id has no name.
-extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
-                                                const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
-                                                const char *ctg_id, const char *name_blob, const int64_t *name_off, int64_t n_names,
-                                                char *out, int64_t cap) {
-    if ((!vm_qid && n_vm) || (n_pr && (!pr_qid || !pr_block || !pr_phase || !pr_n0 || !pr_n1)) || !ctg_id || !name_blob || !name_off) return -1;
+// name_of(q, &len) -> pointer to the QNAME of q_id q
+template <class NameOf>
+static int64_t format_phased_reads_core(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                        const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                        const char *ctg_id, int64_t n_names, NameOf name_of, char *out, int64_t cap) {
     Py27Table tab;
     auto eq = [](int64_t a, int64_t b) { return a == b; };
     for (int64_t i = 0; i < n_vm; i++) {
@@ -605,7 +605,8 @@ extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n
         for (const int32_t *p = lo; p < pr_qid + n_pr && *p == (int32_t)q; p++) {
             const int64_t i = p - pr_qid;
             if (q < 0 || q >= n_names) { bad = true; return; }
-            const int64_t nl = name_off[q + 1] - name_off[q];
+            int64_t nl = 0;
+            const char *nm = name_of(q, &nl);
             const int64_t need = 5 * 12 + (int64_t)ctg_len + nl + 8;
             if (out) {
                 if (w + need > cap) { bad = true; return; }
@@ -614,7 +615,7 @@ extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n
                 memcpy(s, ctg_id, ctg_len); s += ctg_len; *s++ = ' ';
                 s = put_int(s, pr_block[i]); *s++ = ' '; s = put_int(s, pr_phase[i]); *s++ = ' ';
                 s = put_int(s, pr_n0[i]); *s++ = ' '; s = put_int(s, pr_n1[i]); *s++ = ' ';
-                memcpy(s, name_blob + name_off[q], (size_t)nl); s += nl; *s++ = '\n';
+                memcpy(s, nm, (size_t)nl); s += nl; *s++ = '\n';
                 w = s - out;
             } else {
                 w += need;                                   // upper bound for the size query
@@ -622,4 +623,117 @@ extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n
         }
     });
     return bad ? -1 : w;
+}
+
+extern "C" int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                                const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                                const char *ctg_id, const char *name_blob, const int64_t *name_off, int64_t n_names,
+                                                char *out, int64_t cap) {
+    if ((!vm_qid && n_vm) || (n_pr && (!pr_qid || !pr_block || !pr_phase || !pr_n0 || !pr_n1)) || !ctg_id || !name_blob || !name_off) return -1;
+    return format_phased_reads_core(vm_qid, n_vm, pr_qid, pr_block, pr_phase, pr_n0, pr_n1, n_pr, ctg_id, n_names,
+                                    [&](int64_t q, int64_t *nl) { *nl = name_off[q + 1] - name_off[q]; return name_blob + name_off[q]; }, out, cap);
+}
+
+// The same with the QNAMEs as fixed-width rows (NUL padded, `width` bytes each: the layout the device gathers them in).
+extern "C" int64_t fuz_host_format_phased_reads_rows(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                                     const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                                     const char *ctg_id, const char *name_rows, int64_t width, int64_t n_names,
+                                                     char *out, int64_t cap) {
+    if ((!vm_qid && n_vm) || (n_pr && (!pr_qid || !pr_block || !pr_phase || !pr_n0 || !pr_n1)) || !ctg_id || (!name_rows && n_names) || width < 1) return -1;
+    return format_phased_reads_core(vm_qid, n_vm, pr_qid, pr_block, pr_phase, pr_n0, pr_n1, n_pr, ctg_id, n_names,
+                                    [&](int64_t q, int64_t *nl) { const char *r = name_rows + q * width; *nl = (int64_t)strnlen(r, (size_t)width); return r; },
+                                    out, cap);
+}
+
+// het_call/q_id_map (phasing.py:132-134): "q_id qname" for q_id = 0 .. n-1 from fixed-width QNAME rows.  cap >= n * (width + 13).
+extern "C" int64_t fuz_host_format_q_id_map_rows(const char *name_rows, int64_t width, int64_t n, char *out, int64_t cap) {
+    if ((!name_rows && n) || !out || width < 1 || n < 0 || n * (width + 13) > cap) return -1;
+    char *p = out;
+    for (int64_t q = 0; q < n; q++) {
+        const char *r = name_rows + q * width;
+        const size_t nl = strnlen(r, (size_t)width);
+        p = put_int(p, q); *p++ = ' ';
+        memcpy(p, r, nl); p += nl; *p++ = '\n';
+    }
+    return p - out;
+}
+
+// het_call/variant_pos (phasing.py:116-124): "pos ref total b0 c0 b1 c1 b2 c2 b3 c3", bases by descending (count, base).
+// site_cnt: 4 counts per site in A, C, G, T order.  cap >= 80 bytes per row.  -2: position outside ref_seq.
+extern "C" int64_t fuz_host_format_variant_pos(const int32_t *site_pos, const int32_t *site_cnt, int64_t s0, int64_t s1,
+                                               const char *ref_seq, int64_t ref_len, char *out, int64_t cap) {
+    if (!site_pos || !site_cnt || !ref_seq || !out || s0 > s1 || (s1 - s0) * 80 > cap) return -1;
+    static const char B[] = "ACGT";
+    char *p = out;
+    for (int64_t i = s0; i < s1; i++) {
+        const int32_t pos = site_pos[i];
+        if (pos < 1 || pos > ref_len) return -2;
+        const int32_t *c = site_cnt + 4 * i;
+        int ord[4] = {0, 1, 2, 3};
+        // descending (count, base): keys 4 * count + base are distinct
+        std::sort(ord, ord + 4, [&](int a, int b) { return 4LL * c[a] + a > 4LL * c[b] + b; });
+        p = put_int(p, pos); *p++ = ' '; *p++ = ref_seq[pos - 1]; *p++ = ' ';
+        p = put_int(p, (long long)c[0] + c[1] + c[2] + c[3]);
+        for (int k = 0; k < 4; k++) { *p++ = ' '; *p++ = B[ord[k]]; *p++ = ' '; p = put_int(p, c[ord[k]]); }
+        *p++ = '\n';
+    }
+    return p - out;
+}
+
+// Python 2 str(float): '%.12g', plus '.0' when the text has no '.', 'e', 'inf' or 'nan' 
+static char *put_py27_float(char *p, double v) {
+    char tmp[40];
+    int n = snprintf(tmp, sizeof(tmp), "%.12g", v);
+    bool plain = true;
+    for (int i = 0; i < n; i++) if (tmp[i] == '.' || tmp[i] == 'e' || tmp[i] == 'n') plain = false;
+    memcpy(p, tmp, (size_t)n); p += n;
+    if (plain) { *p++ = '.'; *p++ = '0'; }
+    return p;
+}
+
+// get_phased_blocks/phased_variants (phasing.py:411-421) for the sites [s0, s1) of one contig: per block id 1 .. max (in
+// ascending order, blocks without sites skipped) a P row "P pid min max span n span/n" and its sites in position order as
+// "V pid pos pos_ref_b0 pos_ref_b1 lext rext lscore rscore" (b0 = the allele of the site's phase).  cap >= 64 + 160 bytes per site.
+extern "C" int64_t fuz_host_format_phased_variants(const int32_t *site_pos, const uint8_t *site_al, const int32_t *ph_block,
+                                                   const uint8_t *ph_state, const int32_t *ph_lext, const int32_t *ph_rext,
+                                                   const int32_t *ph_lscore, const int32_t *ph_rscore, int64_t s0, int64_t s1,
+                                                   const char *ref_seq, int64_t ref_len, char *out, int64_t cap) {
+    if (!site_pos || !site_al || !ph_block || !ph_state || !ph_lext || !ph_rext || !ph_lscore || !ph_rscore || !ref_seq || !out || s0 > s1) return -1;
+    if ((s1 - s0) * 224 + 64 > cap) return -1;
+    static const char B[] = "ACGT";
+    const int64_t n = s1 - s0;
+    int32_t n_blocks = 0;
+    for (int64_t i = s0; i < s1; i++) n_blocks = std::max(n_blocks, ph_block[i]);
+    // sites grouped by block id, file order inside a block (counting sort = numpy's stable argsort)
+    std::vector<int64_t> start((size_t)n_blocks + 2, 0);
+    for (int64_t i = s0; i < s1; i++) if (ph_block[i] >= 1) start[(size_t)ph_block[i] + 1]++;
+    for (int32_t b = 1; b <= n_blocks; b++) start[(size_t)b + 1] += start[(size_t)b];
+    std::vector<int64_t> idx((size_t)n);
+    {
+        std::vector<int64_t> cur(start.begin(), start.end());
+        for (int64_t i = s0; i < s1; i++) if (ph_block[i] >= 1) idx[(size_t)cur[(size_t)ph_block[i]]++] = i;
+    }
+    char *p = out;
+    for (int32_t pid = 1; pid <= n_blocks; pid++) {
+        const int64_t a = start[(size_t)pid], b = start[(size_t)pid + 1];
+        if (a == b) continue;
+        int32_t mn = site_pos[idx[(size_t)a]], mx = mn;
+        for (int64_t k = a; k < b; k++) { const int32_t v = site_pos[idx[(size_t)k]]; mn = std::min(mn, v); mx = std::max(mx, v); }
+        *p++ = 'P'; *p++ = ' '; p = put_int(p, pid); *p++ = ' '; p = put_int(p, mn); *p++ = ' '; p = put_int(p, mx); *p++ = ' ';
+        p = put_int(p, (long long)mx - mn); *p++ = ' '; p = put_int(p, b - a); *p++ = ' ';
+        p = put_py27_float(p, 1.0 * (double)((long long)mx - mn) / (double)(b - a)); *p++ = '\n';
+        for (int64_t k = a; k < b; k++) {
+            const int64_t i = idx[(size_t)k];
+            const int32_t pos = site_pos[i];
+            const int st = ph_state[i];
+            if (pos < 1 || pos > ref_len || st > 1 || site_al[2 * i] > 3 || site_al[2 * i + 1] > 3) return -2;
+            const char rb = ref_seq[pos - 1];
+            *p++ = 'V'; *p++ = ' '; p = put_int(p, pid); *p++ = ' '; p = put_int(p, pos); *p++ = ' ';
+            p = put_int(p, pos); *p++ = '_'; *p++ = rb; *p++ = '_'; *p++ = B[site_al[2 * i + st]]; *p++ = ' ';
+            p = put_int(p, pos); *p++ = '_'; *p++ = rb; *p++ = '_'; *p++ = B[site_al[2 * i + 1 - st]]; *p++ = ' ';
+            p = put_int(p, ph_lext[i]); *p++ = ' '; p = put_int(p, ph_rext[i]); *p++ = ' ';
+            p = put_int(p, ph_lscore[i]); *p++ = ' '; p = put_int(p, ph_rscore[i]); *p++ = '\n';
+        }
+    }
+    return p - out;
 }

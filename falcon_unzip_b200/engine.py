@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -56,6 +57,11 @@ class PreparedBatch:
         o = int(self.rec_off[r])
         l_name = int(self.records[o + 12])
         return self.records[o + 36:o + 36 + l_name - 1].tobytes().decode("ascii")
+
+    def qname_rows(self, c: int):
+        """QNAMEs of contig c as they are kept: fixed-width NUL-padded rows (numpy "S"), else the list of str.  The file
+        formatters of libfuz take the rows as they are."""
+        return self._names[int(self._q_off[c]):int(self._q_off[c + 1])]
 
     def qnames(self, c: int) -> List[str]:
         return [self.qname(c, q) for q in range(int(self.ctg_nq[c]))]
@@ -371,6 +377,11 @@ class BamBatchInfo:
     def n_ctg(self) -> int:
         return len(self.ctg_names)
 
+    def qname_rows(self, c: int):
+        """QNAMEs of contig c as they are kept: fixed-width NUL-padded rows (numpy "S"), else the list of str.  The file
+        formatters of libfuz take the rows as they are."""
+        return self._names[int(self._q_off[c]):int(self._q_off[c + 1])]
+
     def qnames(self, c: int) -> List[str]:
         """QNAME of every q_id of contig c.  The batch keeps the names as fixed-width byte rows (numpy "S"); the str
         objects are made here, for the contig that is being written."""
@@ -531,6 +542,25 @@ class Engine:
                            int(st.n_accepted), int(st.aligned_bases))
 
     # ---- BAM ingest on the device (BGZF inflate + record index)
+    def read_file_pinned(self, path: str) -> np.ndarray:
+        """The bytes of a file in a page-locked buffer that the engine keeps and reuses (grown when a larger file comes): no
+        fresh pages per call, and the upload that follows is a DMA from pinned memory.  The view is valid until the next call."""
+        torch = self._torch
+        n = os.path.getsize(path)
+        buf = getattr(self, "_file_pin", None)
+        if buf is None or buf.numel() < n:
+            self._file_pin = buf = torch.empty(max(n + (n >> 3), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        view = buf.numpy()[:n]
+        with open(path, "rb", buffering=0) as f:
+            got = 0
+            mv = memoryview(view)
+            while got < n:
+                k = f.readinto(mv[got:])
+                if not k:
+                    raise IOError("%s: short read (%d of %d bytes)" % (path, got, n))
+                got += k
+        return view
+
     def ingest_bam(self, image, verify_crc: bool = True, profile: bool = False) -> DeviceBam:
         """image: the bytes of a coordinate-sorted BAM file (numpy uint8, ideally pinned).  The
         compressed image crosses PCIe; inflate, record index and grouping by reference run on

@@ -42,29 +42,38 @@ def contig_slices(res, n_ctg: int) -> Dict[str, np.ndarray]:
     return dict(site=site_off, vmap=vm_off, atable=at_off, reads=pr_off)
 
 
-def variant_pos_text(res, s0: int, s1: int, ref_seq: str) -> str:
-    """het_call/variant_pos: ``pos ref total b0 c0 b1 c1 b2 c2 b3 c3`` (phasing.py:124)."""
-    pos = res.site_pos[s0:s1].tolist()
-    cnt = res.site_cnt[s0:s1]
-    key = cnt.astype(np.int64) * 4 + np.arange(4)[None, :]
-    order = np.argsort(-key, axis=1, kind="stable")            # descending (count, base)
-    tot = cnt.sum(axis=1).tolist()
-    so = order.tolist()
-    sc = np.take_along_axis(cnt, order, axis=1).tolist()
-    return "".join("%d %s %d %s %d %s %d %s %d %s %d\n" % (
-        p, ref_seq[p - 1], t, BASES[o[0]], c[0], BASES[o[1]], c[1], BASES[o[2]], c[2], BASES[o[3]], c[3])
-        for p, t, o, c in zip(pos, tot, so, sc))
-
-
 def _c32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-def variant_map_text(res, s0: int, v0: int, v1: int, ref_seq: str) -> str:
+def _ref_bytes(ref_seq) -> bytes:
+    return ref_seq if isinstance(ref_seq, bytes) else ref_seq.encode("latin-1")
+
+
+def variant_pos_bytes(res, s0: int, s1: int, ref_seq) -> bytes:
+    """het_call/variant_pos: ``pos ref total b0 c0 b1 c1 b2 c2 b3 c3`` (phasing.py:116-124), bases by descending (count, base);
+    rows formatted in libfuz."""
+    site_pos, site_cnt = _c32(res.site_pos), _c32(res.site_cnt)
+    ref = _ref_bytes(ref_seq)
+    cap = 80 * (s1 - s0) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib().fuz_host_format_variant_pos(site_pos.ctypes.data, site_cnt.ctypes.data, s0, s1, ref, len(ref), buf, cap)
+    if n == -2:
+        raise IndexError("string index out of range (ref_seq shorter than a het position; phasing.py:123)")
+    if n < 0:
+        raise RuntimeError("fuz_host_format_variant_pos failed")
+    return buf.raw[:n]
+
+
+def variant_pos_text(res, s0: int, s1: int, ref_seq: str) -> str:
+    return variant_pos_bytes(res, s0, s1, ref_seq).decode("latin-1")
+
+
+def variant_map_bytes(res, s0: int, v0: int, v1: int, ref_seq) -> bytes:
     """het_call/variant_map: ``pos ref allele q_id`` (phasing.py:126,128); rows formatted in libfuz."""
     site_pos, vm_site, vm_qid = _c32(res.site_pos), _c32(res.vm_site), _c32(res.vm_qid)
     vm_base = np.ascontiguousarray(res.vm_base, dtype=np.uint8)
-    ref = ref_seq.encode("latin-1")
+    ref = _ref_bytes(ref_seq)
     cap = 32 * (v1 - v0) + 16
     buf = C.create_string_buffer(cap)
     n = lib().fuz_host_format_variant_map(site_pos.ctypes.data, vm_site.ctypes.data, vm_base.ctypes.data, vm_qid.ctypes.data,
@@ -73,15 +82,41 @@ def variant_map_text(res, s0: int, v0: int, v1: int, ref_seq: str) -> str:
         raise IndexError("string index out of range (ref_seq shorter than a het position; phasing.py:123)")
     if n < 0:
         raise RuntimeError("fuz_host_format_variant_map failed")
-    return buf.raw[:n].decode("latin-1")
+    return buf.raw[:n]
 
 
-def q_id_map_text(names: Sequence[str]) -> str:
-    """het_call/q_id_map (phasing.py:132-134); dense int keys iterate ascending."""
-    return "".join("%d %s\n" % (i, n) for i, n in enumerate(names))
+def variant_map_text(res, s0: int, v0: int, v1: int, ref_seq: str) -> str:
+    return variant_map_bytes(res, s0, v0, v1, ref_seq).decode("latin-1")
 
 
-def atable_text(res, a0: int, a1: int) -> str:
+def _name_rows(names):
+    """names as fixed-width NUL-padded rows (numpy "S"): (array, width), or None for a list / dict of str."""
+    if isinstance(names, np.ndarray) and names.dtype.kind == "S":
+        a = np.ascontiguousarray(names)
+        return a, a.dtype.itemsize
+    return None
+
+
+def q_id_map_bytes(names) -> bytes:
+    """het_call/q_id_map (phasing.py:132-134); dense int keys iterate ascending.  names: list of str, or the fixed-width
+    QNAME rows of a device batch (formatted in libfuz, no str objects)."""
+    rows = _name_rows(names)
+    if rows is None:
+        return "".join("%d %s\n" % (i, n) for i, n in enumerate(names)).encode("latin-1")
+    a, width = rows
+    cap = len(a) * (width + 13) + 16
+    buf = C.create_string_buffer(cap)
+    n = lib().fuz_host_format_q_id_map_rows(a.ctypes.data if len(a) else None, width, len(a), buf, cap)
+    if n < 0:
+        raise RuntimeError("fuz_host_format_q_id_map_rows failed")
+    return buf.raw[:n]
+
+
+def q_id_map_text(names) -> str:
+    return q_id_map_bytes(names).decode("latin-1")
+
+
+def atable_bytes(res, a0: int, a1: int) -> bytes:
     """g_atable/atable: ``pos1 b11 b12 pos2 b21 b22 c11 c12 c21 c22`` (phasing.py:199); rows formatted in libfuz."""
     site_pos, at_s1, at_s2, at_ct = _c32(res.site_pos), _c32(res.at_s1), _c32(res.at_s2), _c32(res.at_ct)
     site_al = np.ascontiguousarray(res.site_al, dtype=np.uint8)
@@ -91,7 +126,27 @@ def atable_text(res, a0: int, a1: int) -> str:
                                      at_ct.ctypes.data, a0, a1, buf, cap)
     if n < 0:
         raise RuntimeError("fuz_host_format_atable failed")
-    return buf.raw[:n].decode("ascii")
+    return buf.raw[:n]
+
+
+def atable_text(res, a0: int, a1: int) -> str:
+    return atable_bytes(res, a0, a1).decode("ascii")
+
+
+def phased_variants_bytes(res, s0: int, s1: int, ref_seq) -> bytes:
+    """get_phased_blocks/phased_variants: P and V rows (phasing.py:411-421), formatted in libfuz."""
+    ref = _ref_bytes(ref_seq)
+    cap = 224 * (s1 - s0) + 80
+    buf = C.create_string_buffer(cap)
+    u8 = lambda a: np.ascontiguousarray(a, dtype=np.uint8)                     # noqa: E731
+    cols = [_c32(res.site_pos), u8(res.site_al), _c32(res.ph_block), u8(res.ph_state), _c32(res.ph_lext), _c32(res.ph_rext),
+            _c32(res.ph_lscore), _c32(res.ph_rscore)]
+    n = lib().fuz_host_format_phased_variants(*[c.ctypes.data for c in cols], s0, s1, ref, len(ref), buf, cap)
+    if n == -2:
+        raise IndexError("string index out of range (ref_seq shorter than a phased position; phasing.py:418)")
+    if n < 0:
+        raise RuntimeError("fuz_host_format_phased_variants failed")
+    return buf.raw[:n]
 
 
 def phased_variants_text(res, s0: int, s1: int, ref_base) -> str:
@@ -123,14 +178,26 @@ def phased_variants_text(res, s0: int, s1: int, ref_base) -> str:
     return "".join(out)
 
 
-def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, names) -> str:
+def phased_reads_bytes(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, names) -> bytes:
     """phased_reads: ``q_id ctg block phase n0 n1 qname`` (phasing.py:478,480), reads in the
     iteration order of the reference's ``read_to_variants`` dict (Python-2 int dict, keys
     inserted in order of first appearance in variant_map).  Rows formatted in libfuz.
     names: list of QNAMEs indexed by q_id, or a dict q_id -> QNAME (file-level stage)."""
     vq = _c32(res.vm_qid[v0:v1])
     if len(vq) == 0:
-        return ""
+        return b""
+    cols = [_c32(getattr(res, k)[r0:r1]) for k in ("pr_qid", "pr_block", "pr_phase", "pr_n0", "pr_n1")]
+    rows = _name_rows(names)
+    if rows is not None:                                   # QNAME rows of a device batch: no str objects
+        a, width = rows
+        args = (vq.ctypes.data, len(vq), *[c.ctypes.data for c in cols], r1 - r0, ctg_id.encode("latin-1"),
+                a.ctypes.data if len(a) else None, width, len(a))
+        cap = 72 * (r1 - r0) + (len(ctg_id) + width) * (r1 - r0) + 16
+        buf = C.create_string_buffer(cap)
+        n = lib().fuz_host_format_phased_reads_rows(*args, buf, cap)
+        if n < 0:
+            raise IndexError("phased_reads row with a q_id that has no QNAME")
+        return buf.raw[:n]
     if isinstance(names, dict):
         n_names = max(names) + 1 if names else 0
         get = names.get
@@ -143,7 +210,6 @@ def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, name
     enc = [n.encode("latin-1") for n in name_list]
     name_off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
     blob = b"".join(enc) + b"\0"
-    cols = [_c32(getattr(res, k)[r0:r1]) for k in ("pr_qid", "pr_block", "pr_phase", "pr_n0", "pr_n1")]
     args = (vq.ctypes.data, len(vq), *[c.ctypes.data for c in cols], r1 - r0, ctg_id.encode("latin-1"), blob, name_off.ctypes.data,
             len(enc))
     cap = lib().fuz_host_format_phased_reads(*args, None, 0)
@@ -153,4 +219,8 @@ def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, name
     n = lib().fuz_host_format_phased_reads(*args, buf, int(cap) + 16)
     if n < 0:
         raise RuntimeError("fuz_host_format_phased_reads failed")
-    return buf.raw[:n].decode("latin-1")
+    return buf.raw[:n]
+
+
+def phased_reads_text(res, r0: int, r1: int, v0: int, v1: int, ctg_id: str, names) -> str:
+    return phased_reads_bytes(res, r0, r1, v0, v1, ctg_id, names).decode("latin-1")

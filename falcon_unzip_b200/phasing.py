@@ -44,10 +44,10 @@ class _open_out:
     replaces `path` when the block ends without an exception (pypeFLOW takes the existence of a file for success; the
     reference writes in place, phasing.py:39-40,132)."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, mode: str = "w"):
         self.path = path
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        self.f = open(path + ".tmp", "w")
+        self.f = open(path + ".tmp", mode)
 
     def __enter__(self):
         return self.f
@@ -341,14 +341,16 @@ def write_contig_files(res, sl, c: int, ctg_id: str, ref_seq: str, names: Sequen
                  atable=os.path.join(base, "g_atable", "atable"),
                  phased_variants=os.path.join(base, "get_phased_blocks", "phased_variants"),
                  phased_reads=os.path.join(base, "phased_reads"))
-    text = dict(variant_pos=formats.variant_pos_text(res, s0, s1, ref_seq),
-                variant_map=formats.variant_map_text(res, s0, v0, v1, ref_seq),
-                q_id_map=formats.q_id_map_text(names),
-                atable=formats.atable_text(res, a0, a1),
-                phased_variants=formats.phased_variants_text(res, s0, s1, ref_seq),
-                phased_reads=formats.phased_reads_text(res, r0, r1, v0, v1, ctg_id, names))
+    # every file as bytes straight from the formatters of libfuz (names: list of str, or the QNAME rows of a device batch)
+    ref = ref_seq if isinstance(ref_seq, bytes) else ref_seq.encode("latin-1")
+    text = dict(variant_pos=formats.variant_pos_bytes(res, s0, s1, ref),
+                variant_map=formats.variant_map_bytes(res, s0, v0, v1, ref),
+                q_id_map=formats.q_id_map_bytes(names),
+                atable=formats.atable_bytes(res, a0, a1),
+                phased_variants=formats.phased_variants_bytes(res, s0, s1, ref),
+                phased_reads=formats.phased_reads_bytes(res, r0, r1, v0, v1, ctg_id, names))
     for k, p in paths.items():
-        with _open_out(p) as f:                # never leaves a partial output file behind
+        with _open_out(p, "wb") as f:          # never leaves a partial output file behind
             f.write(text[k])
     return paths
 
@@ -393,12 +395,31 @@ def phase_bam(bam_fn, fasta_fn: str, base_dir: str, device: int = 0, verify_crc:
     QNAME -> q_id table and the four stages run in HBM; the same six files per contig come out."""
     if isinstance(bam_fn, (list, tuple)):                 # one sorted BAM per contig, as unzip.py:90 leaves them
         image = [np.fromfile(fn_, dtype=np.uint8) for fn_ in bam_fn]
-    else:
-        image = np.fromfile(bam_fn, dtype=np.uint8)
-    ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta(fasta_fn)}
     eng = engine.get_engine(device)
+    reader = None
+    if not isinstance(bam_fn, (list, tuple)):
+        # page-locked buffer, reused from call to call (the upload is a plain DMA); read while the FASTA is parsed
+        import threading
+        box = {}
+
+        def _read():
+            try:
+                box["image"] = eng.read_file_pinned(bam_fn)
+            except BaseException as e:                    # noqa: BLE001 -- re-raised in the caller's thread
+                box["error"] = e
+        reader = threading.Thread(target=_read)
+        reader.start()
+    try:
+        ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta_bytes(fasta_fn)}
+    finally:
+        if reader is not None:
+            reader.join()
+    if reader is not None:
+        if "error" in box:
+            raise box["error"]
+        image = box["image"]
     res, info = eng.phase_bam(image, verify_crc=verify_crc)
-    return res, write_batch_files(res, info, [ref_seqs.get(n, "") for n in info.ctg_names], base_dir)
+    return res, write_batch_files(res, info, [ref_seqs.get(n, b"") for n in info.ctg_names], base_dir)
 
 
 def write_batch_files(res, info, ref_seqs: Sequence[str], base_dir: str):
@@ -406,7 +427,7 @@ def write_batch_files(res, info, ref_seqs: Sequence[str], base_dir: str):
     sl = formats.contig_slices(res, info.n_ctg)
     out = {}
     for c, name in enumerate(info.ctg_names):
-        out[name] = write_contig_files(res, sl, c, name, ref_seqs[c], info.qnames(c), base_dir)
+        out[name] = write_contig_files(res, sl, c, name, ref_seqs[c], info.qname_rows(c), base_dir)
     return out
 
 

@@ -426,6 +426,27 @@ int64_t fuz_host_format_phased_reads(const int32_t *vm_qid, int64_t n_vm, const 
                                      const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
                                      const char *ctg_id, const char *name_blob, const int64_t *name_off, int64_t n_names,
                                      char *out, int64_t cap);
+/* The same with the QNAMEs as fixed-width rows (NUL padded, `width` bytes each: the layout the device gathers them in). */
+int64_t fuz_host_format_phased_reads_rows(const int32_t *vm_qid, int64_t n_vm, const int32_t *pr_qid, const int32_t *pr_block,
+                                          const int32_t *pr_phase, const int32_t *pr_n0, const int32_t *pr_n1, int64_t n_pr,
+                                          const char *ctg_id, const char *name_rows, int64_t width, int64_t n_names,
+                                          char *out, int64_t cap);
+/* Text of het_call/q_id_map (phasing.py:132-134) from fixed-width QNAME rows: "q_id qname" for q_id = 0 .. n-1.
+ * cap >= n * (width + 13).  Returns the size, -1 on bad arguments. */
+int64_t fuz_host_format_q_id_map_rows(const char *name_rows, int64_t width, int64_t n, char *out, int64_t cap);
+/* Text of het_call/variant_pos (phasing.py:116-124) for the sites [s0, s1): "pos ref total b0 c0 b1 c1 b2 c2 b3 c3", bases
+ * by descending (count, base); site_cnt holds 4 counts per site in A, C, G, T order.  cap >= 80 bytes per row.
+ * Returns the size, -1 on bad arguments, -2 if a position lies outside ref_seq (IndexError in the reference, :123). */
+int64_t fuz_host_format_variant_pos(const int32_t *site_pos, const int32_t *site_cnt, int64_t s0, int64_t s1,
+                                    const char *ref_seq, int64_t ref_len, char *out, int64_t cap);
+/* Text of get_phased_blocks/phased_variants (phasing.py:411-421) for the sites [s0, s1) of one contig: per block id in
+ * ascending order a P row ("P pid min max span n span/n", the quotient as Python 2 prints a float) and the V rows of its
+ * sites in position order.  cap >= 64 + 224 bytes per site.  Returns the size, -1 on bad arguments, -2 on a position
+ * outside ref_seq or an invalid phase / allele. */
+int64_t fuz_host_format_phased_variants(const int32_t *site_pos, const uint8_t *site_al, const int32_t *ph_block,
+                                        const uint8_t *ph_state, const int32_t *ph_lext, const int32_t *ph_rext,
+                                        const int32_t *ph_lscore, const int32_t *ph_rscore, int64_t s0, int64_t s1,
+                                        const char *ref_seq, int64_t ref_len, char *out, int64_t cap);
 /* CPython-2.7 dict / set iteration order of str keys (Objects/stringobject.c string_hash + the insert-only table
  * of dictobject.c): keys[i] = blob[off[i], off[i+1]) inserted in order, duplicates ignored;
  * out = index of every distinct key in iteration order.  Returns the number of distinct keys. */

@@ -53,8 +53,10 @@ def model_from_oracle(recs, ctg_id, ref_seq):
     return res, names
 
 
+@pytest.mark.parametrize("name_rows", [False, True])
 @pytest.mark.parametrize("cfg", ["tiny", "quirks"])
-def test_formats_render_oracle_model_to_oracle_bytes(cfg, tmp_path):
+def test_formats_render_oracle_model_to_oracle_bytes(cfg, name_rows, tmp_path):
+    """name_rows: the QNAMEs as the fixed-width byte rows a device batch keeps (formatted in libfuz without str objects)."""
     from falcon_unzip_b200 import formats, phasing
     from oracle import c_oracle
     sset = synth_set(cfg)
@@ -62,10 +64,40 @@ def test_formats_render_oracle_model_to_oracle_bytes(cfg, tmp_path):
         recs = sset.contig_records(c)
         want = c_oracle.run_phasing_stages(recs, name, sset.ref_seqs[c], str(tmp_path / "oracle"))
         res, names = model_from_oracle(recs, name, sset.ref_seqs[c])
+        if name_rows:
+            names = np.array([n.encode("latin-1") for n in names], dtype="S")
         sl = formats.contig_slices(res, 1)
         got = phasing.write_contig_files(res, sl, 0, name, sset.ref_seqs[c], names, str(tmp_path / "fmt"))
         for k in want:
             assert open(want[k]).read() == open(got[k]).read(), (name, k)
+        # the Python rendering of phased_variants (kept for the file-level stage, which looks bases up in a dict) agrees
+        n_sites = len(res.site_pos)
+        assert formats.phased_variants_bytes(res, 0, n_sites, sset.ref_seqs[c]).decode() == \
+            formats.phased_variants_text(res, 0, n_sites, sset.ref_seqs[c])
+
+
+def test_native_formatters_edge_cases():
+    """Python 2 float text of the P rows (integral quotient -> '.0', 12 significant digits), ties in variant_pos (T > G > C > A
+    on equal counts), empty inputs, a position beyond the reference (IndexError like the reference, phasing.py:123)."""
+    from falcon_unzip_b200 import formats
+    z = np.zeros
+    res = SimpleNamespace(site_pos=np.array([3, 10, 17, 20, 1000], np.int32), site_al=np.array([[0, 1], [1, 3], [0, 2], [3, 2], [0, 1]], np.uint8),
+                          site_cnt=np.array([[5, 5, 5, 5], [0, 7, 0, 7], [9, 1, 2, 3], [1, 1, 8, 8], [4, 3, 2, 1]], np.int32),
+                          ph_block=np.array([1, 1, 1, 2, 0], np.int32), ph_state=np.array([0, 1, 0, 1, 255], np.uint8),
+                          ph_lext=np.array([3, 3, 10, 20, 0], np.int32), ph_rext=np.array([17, 17, 17, 20, 0], np.int32),
+                          ph_lscore=np.array([0, 12, 30, 0, 0], np.int32), ph_rscore=np.array([14, 11, 0, 0, 0], np.int32))
+    ref = "ACGTACGTACGTACGTACGTACGT"
+    assert formats.variant_pos_bytes(res, 0, 4, ref) == (b"3 G 20 T 5 G 5 C 5 A 5\n10 C 14 T 7 C 7 G 0 A 0\n"
+                                                         b"17 A 15 A 9 T 3 G 2 C 1\n20 T 18 T 8 G 8 C 1 A 1\n")
+    want = ("P 1 3 17 14 3 4.66666666667\nV 1 3 3_G_A 3_G_C 3 17 0 14\nV 1 10 10_C_T 10_C_C 3 17 12 11\nV 1 17 17_A_A 17_A_G 10 17 30 0\n"
+            "P 2 20 20 0 1 0.0\nV 2 20 20_T_G 20_T_T 20 20 0 0\n")
+    assert formats.phased_variants_bytes(res, 0, 5, ref).decode() == want == formats.phased_variants_text(res, 0, 5, ref)
+    assert formats.phased_variants_bytes(res, 0, 0, ref) == b"" and formats.variant_pos_bytes(res, 2, 2, ref) == b""
+    with pytest.raises(IndexError):
+        formats.variant_pos_bytes(res, 0, 5, ref)
+    rows = np.array([b"m1/1/0_9", b"", b"x" * 12], dtype="S12")
+    assert formats.q_id_map_bytes(rows) == b"0 m1/1/0_9\n1 \n2 xxxxxxxxxxxx\n" == formats.q_id_map_bytes(["m1/1/0_9", "", "x" * 12])
+    assert formats.q_id_map_bytes(np.zeros(0, dtype="S8")) == b""
 
 
 def test_prepare_batch_matches_oracle_qids():
@@ -98,3 +130,14 @@ def test_py27_int_dict_order_vectors_and_emulator():
         assert formats.py27_int_dict_order(keys).tolist() == py2emu.py27_int_dict_order(keys.tolist())
     assert formats.py27_float_str(183848 / 183) == "1004.63387978"
     assert formats.py27_float_str(1000 / 4) == "250.0"
+
+
+def test_read_fasta_bytes_agrees_with_read_fasta(tmp_path):
+    """The bytes reader of phase_bam keeps the record and line rules of the FastaReader stand-in (reference phasing.py:490-494)."""
+    from falcon_unzip_b200 import bam
+    fn = str(tmp_path / "a.fa")
+    with open(fn, "w", newline="") as f:
+        f.write("junk before the first header\n>c1 some description\nACGT\nacgt \n\n>c2\nTTTT\n>c3\n>c4\r\nAA\r\nCC\r\n>c5\nGATTACA")
+    a, b = list(bam.read_fasta(fn)), list(bam.read_fasta_bytes(fn))
+    assert [(h, s.encode()) for h, s in a] == b
+    assert [h for h, _ in b] == ["c1 some description", "c2", "c3", "c4", "c5"] and b[0][1] == b"ACGTacgt" and b[4][1] == b"GATTACA"
