@@ -393,42 +393,50 @@ def phase_bam(bam_fn, fasta_fn: str, base_dir: str, device: int = 0, verify_crc:
     """Every contig of a coordinate-sorted BAM (or of a list of BAMs, e.g. one per contig) in one go, decoded on the device: the file image is
     uploaded as it is, BGZF inflate + record split (the `samtools view` pipe of phasing.py:27), the
     QNAME -> q_id table and the four stages run in HBM; the same six files per contig come out."""
-    if isinstance(bam_fn, (list, tuple)):                 # one sorted BAM per contig, as unzip.py:90 leaves them
-        image = [np.fromfile(fn_, dtype=np.uint8) for fn_ in bam_fn]
     eng = engine.get_engine(device)
-    reader = None
-    if not isinstance(bam_fn, (list, tuple)):
-        # page-locked buffer, reused from call to call (the upload is a plain DMA); read while the FASTA is parsed
-        import threading
-        box = {}
+    # The device side (file image into a reused page-locked buffer, upload, inflate, record index, the four stages, rows back)
+    # runs on a worker thread -- its calls into libfuz / the CUDA runtime release the interpreter -- while this thread parses
+    # the FASTA as bytes.
+    import threading
+    box = {}
 
-        def _read():
-            try:
-                box["image"] = eng.read_file_pinned(bam_fn)
-            except BaseException as e:                    # noqa: BLE001 -- re-raised in the caller's thread
-                box["error"] = e
-        reader = threading.Thread(target=_read)
-        reader.start()
+    def _device_side():
+        try:
+            import torch
+            torch.cuda.set_device(device)                 # the worker's current device (libfuz launches on the caller's)
+            if isinstance(bam_fn, (list, tuple)):         # one sorted BAM per contig, as unzip.py:90 leaves them
+                image = [np.fromfile(fn_, dtype=np.uint8) for fn_ in bam_fn]
+            else:
+                image = eng.read_file_pinned(bam_fn)
+            box["out"] = eng.phase_bam(image, verify_crc=verify_crc)
+        except BaseException as e:                        # noqa: BLE001 -- re-raised in the caller's thread
+            box["error"] = e
+    worker = threading.Thread(target=_device_side)
+    worker.start()
     try:
         ref_seqs = {n.split()[0]: s.upper() for n, s in bam.read_fasta_bytes(fasta_fn)}
     finally:
-        if reader is not None:
-            reader.join()
-    if reader is not None:
-        if "error" in box:
-            raise box["error"]
-        image = box["image"]
-    res, info = eng.phase_bam(image, verify_crc=verify_crc)
+        worker.join()
+    if "error" in box:
+        raise box["error"]
+    res, info = box["out"]
     return res, write_batch_files(res, info, [ref_seqs.get(n, b"") for n in info.ctg_names], base_dir)
 
 
 def write_batch_files(res, info, ref_seqs: Sequence[str], base_dir: str):
     """The six files of every contig of a device batch (engine.BamBatchInfo: contig names and QNAME rows) -> {contig: paths}."""
     sl = formats.contig_slices(res, info.n_ctg)
-    out = {}
-    for c, name in enumerate(info.ctg_names):
-        out[name] = write_contig_files(res, sl, c, name, ref_seqs[c], info.qname_rows(c), base_dir)
-    return out
+
+    def one(c):
+        return write_contig_files(res, sl, c, info.ctg_names[c], ref_seqs[c], info.qname_rows(c), base_dir)
+    if info.n_ctg < 4:
+        paths = [one(c) for c in range(info.n_ctg)]
+    else:
+        # formatting (libfuz) and file I/O release the interpreter: a few threads write the contigs side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, info.n_ctg, os.cpu_count() or 1)) as pool:
+            paths = list(pool.map(one, range(info.n_ctg)))
+    return dict(zip(info.ctg_names, paths))
 
 
 def parse_args(argv):
