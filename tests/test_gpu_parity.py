@@ -144,6 +144,35 @@ def test_launch_options_do_not_change_the_files(eng, cfg, opts, tmp_path):
     _assert_same_files(_oracle_files(sset, tmp_path / "oracle"), got)
 
 
+@pytest.mark.parametrize("opts", [dict(), dict(gather_tma=0), dict(pileup_impl=2)])
+def test_deep_coverage_spills_the_bit_plane_counters(eng, opts, tmp_path):
+    """600x over a 24 kb contig: more than 255 reads cover every pileup tile, so the 8-bit vertical counters of the register
+    pileup are spilled into the 16-bit counters twice per tile (global scratch in the TMA-fed gather, shared memory in the
+    plain one).  Counts and files against the oracle."""
+    import dataclasses
+    from falcon_unzip_b200 import engine, phasing, synth
+    from oracle import c_oracle
+    cfg = dataclasses.replace(synth.CONFIGS["tiny"], name="deep", n_contigs=1, contig_len=24_000, coverage=600.0, mean_read_len=4_000,
+                              min_read_len=2_500, seed=23)
+    sset = synth.generate(cfg)
+    defaults = dict(gather_tma=1, pileup_impl=0)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    try:
+        pb = engine.prepare_batch(sset.records, [r[0] for r in sset.refs], [r[1] for r in sset.refs])
+        res = eng.phase_device(pb, want_counts=True, stage="het")
+        _res, got = phasing.phase_contigs(sset.records, [r[0] for r in sset.refs], sset.ref_seqs, str(tmp_path / "gpu"))
+    finally:
+        for k in opts:
+            eng.set_option(k, defaults[k])
+    recs = sset.contig_records(0)
+    want = c_oracle.pileup_counts(recs, c_oracle.index_records(recs), sset.refs[0][1])
+    assert want.sum(axis=1).max() > 300
+    goff = res.arrays["goff"]
+    assert np.array_equal(res.arrays["counts"][goff[0]:goff[0] + sset.refs[0][1]], want)
+    _assert_same_files(_oracle_files(sset, tmp_path / "oracle"), got)
+
+
 def test_reference_cli_per_stage_files_match_oracle(eng, tmp_path):
     """fc_phasing-style run: BAM + FASTA on disk, the four stage functions chained through
     files exactly like reference phasing.py:482-553."""
