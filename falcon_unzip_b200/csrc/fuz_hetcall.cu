@@ -806,13 +806,18 @@ __global__ void __launch_bounds__(256) k_signature(
         const int rlo = S.tile_rlo[gp / FUZ_PTILE], rhi = S.tile_rhi[gp / FUZ_PTILE];
         const int64_t off0 = S.site_row_off[s], off1 = off0 + n0;
         int run0 = 0, run1 = 0;
+        // the four record fields of a round are independent loads (no short-circuit chain), and those of the NEXT round are
+        // requested before this round's projection word is used: two dependent load levels per round instead of five
+        int fl = 0, ge = 0, gs = 0, wo = 0;
+        if (rlo + lane < rhi) { const int r0 = rlo + lane; fl = S.r_flags[r0]; ge = S.r_gend[r0]; gs = S.r_gstart[r0]; wo = S.r_woff[r0]; }
         for (int rb = rlo; rb < rhi; rb += 32) {
-            int r = rb + lane;
-            uint32_t nib = 0;
-            if (r < rhi && S.r_flags[r] && S.r_gend[r] > gp && S.r_gstart[r] <= gp) {
-                uint32_t w = S.proj[S.r_woff[r] + ((gp >> 3) - fuz_row_w0(S.r_gstart[r]))];
-                nib = (w >> (4 * (gp & 7))) & 15u;
-            }
+            const int r = rb + lane;
+            const bool cov = fl && ge > gp && gs <= gp;
+            uint32_t w = 0;
+            if (cov) w = S.proj[wo + ((gp >> 3) - fuz_row_w0(gs))];
+            fl = 0;
+            if (r + 32 < rhi) { const int rn = r + 32; fl = S.r_flags[rn]; ge = S.r_gend[rn]; gs = S.r_gstart[rn]; wo = S.r_woff[rn]; }
+            const uint32_t nib = cov ? (w >> (4 * (gp & 7))) & 15u : 0u;
             uint32_t m0 = __ballot_sync(0xffffffffu, nib == code0);
             uint32_t m1 = __ballot_sync(0xffffffffu, nib == code1);
             if (nib == code0 || nib == code1) {
