@@ -113,6 +113,9 @@ extern "C" int fuz_set_option(fuz_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "grid_sig") || !strcmp(key, "grid_assoc") || !strcmp(key, "grid_reads")) {
         if (value < 1 || value > 8) return fuz_fail(ctx, FUZ_E_ARG, "%s must be in 1 .. 8 (CTAs per SM)", key);
         (key[5] == 's' ? ctx->grid_sig : key[5] == 'a' ? ctx->grid_assoc : ctx->grid_reads) = (int)value;
+    } else if (!strcmp(key, "grid_rr")) {
+        if (value < 0 || value > 8) return fuz_fail(ctx, FUZ_E_ARG, "grid_rr must be in 0 .. 8");
+        ctx->grid_rr = (int)value;
     } else if (!strcmp(key, "gather_tma")) {
         if (value != 0 && value != 1) return fuz_fail(ctx, FUZ_E_ARG, "gather_tma must be 0 or 1");
         ctx->gather_tma = (int)value;

@@ -55,6 +55,8 @@ struct fuz_ctx {
     bool phase_attr_set = false;
     bool pileup_attr_set = false;
     bool gather_attr_set = false;
+    int grid_rr = 4;                   // tracking path: 0 = every kernel on 4 CTAs per SM; n > 0 = k_rr_replay on n CTAs per SM (more chains in flight
+                                       // thrash the caches: 6 is 25 % slower than 4), k_rr_fill on 8, k_rr_vote on 16 (latency bound)
     int grid_sig = 8, grid_assoc = 6, grid_reads = 8;   // CTAs per SM of the latency-bound grid-stride kernels (k_signature / association / read stage): measured against 4
     int gather_tma = 1;                // pileup_impl 0: TMA-fed persistent gather (1) or the plain tile-per-CTA kernel (0)
     int pileup_debug = 0;

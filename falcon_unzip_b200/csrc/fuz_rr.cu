@@ -248,16 +248,16 @@ extern "C" int fuz_rr_track(fuz_ctx *ctx, const fuz_rr_input *in, fuz_rr_outputs
     FUZ_LAUNCH_CHECK(ctx, "k_rr_filter");
     if (ctx->rr_filter_only) return FUZ_OK;      // map step of the multi-GPU run: d_keep (and reserved[3]) only
     if ((rc = fuz_scan_i32(ctx, R.t_cnt, R.t_off, n_reads, nullptr, FUZ_FIN_NONE, 0))) return rc;
-    fuz_launch(ctx, k_rr_fill, FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
+    fuz_launch(ctx, k_rr_fill, ctx->grid_rr ? 148 * 8 : FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_fill");
-    fuz_launch(ctx, k_rr_replay, FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
+    fuz_launch(ctx, k_rr_replay, ctx->grid_rr ? 148 * ctx->grid_rr : FUZ_GRID_BLOCKS, 256, 0, st, *in, *out, R, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_replay");
-    fuz_launch(ctx, k_rr_vote, FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 0, ctx->d_status);
+    fuz_launch(ctx, k_rr_vote, ctx->grid_rr ? 148 * 16 : FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 0, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_vote(count)");
     if ((rc = fuz_scan_i32(ctx, R.vt_cnt, out->d_vt_off, n_reads, nullptr, FUZ_FIN_NONE, 0))) return rc;
     fuz_launch(ctx, k_rr_votes_total, 1, 32, 0, st, *out, (int)n_reads, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_votes_total");
-    fuz_launch(ctx, k_rr_vote, FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 1, ctx->d_status);
+    fuz_launch(ctx, k_rr_vote, ctx->grid_rr ? 148 * 16 : FUZ_GRID_BLOCKS, 128, 0, st, *in, *out, R, 1, ctx->d_status);
     FUZ_LAUNCH_CHECK(ctx, "k_rr_vote(fill)");
     return FUZ_OK;
 }

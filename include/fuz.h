@@ -167,6 +167,7 @@ int fuz_set_stream(fuz_ctx *ctx, void *cuda_stream);
  *          "project_ctas" grid of the projection kernel (default 148 * 5, the CTAs per SM its registers allow),
  *          "grid_sig" / "grid_assoc" / "grid_reads" CTAs per SM (1 .. 8) of the grid-stride kernels of the signature, the
  *                       association and the read stage (defaults 8 / 6 / 8: they are latency bound),
+ *          "grid_rr" CTAs per SM of k_rr_replay (default 4, the measured optimum; k_rr_fill / k_rr_vote then run on 8 / 16), 0 = all on 4,
  *          "sweep_passes" passes of the parallel fixed-point form of the pass-2 sweep (phasing.py:311-344) before
  *                         the sequential walk takes over (default 64; 0 = sequential only; same result either way),
  *          "max_pairs_per_site" capacity factor of the association scratch (default 96) */

@@ -183,6 +183,8 @@ def main_from_bench(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     eng = engine.Engine(local_rank)
+    if os.environ.get("FUZ_GRID_RR"):                      # A/B of the launch shapes of the tracking kernels (option grid_rr)
+        eng.set_option("grid_rr", int(os.environ["FUZ_GRID_RR"]))
     stream = torch.cuda.Stream(device=dev)
     lib = _lib.lib()
     lib.fuz_set_stream(eng.ctx, stream.cuda_stream)
